@@ -1,0 +1,56 @@
+"""Shared helpers for the test-suite (feeder fixtures, ZIP sets, scenarios)."""
+import json
+import os
+
+import numpy as np
+
+from gigpower_b200.dss_reader import read_dss
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, 'tests', 'golden')
+
+ZIPS = {   # reference tests/test_dss_compare.py:37-40
+    'constant_impedance': [1, 0, 0, 1, 0, 0, .8],
+    'constant_power': [0, 0, 1, 0, 0, 1, .8],
+    'test_zip': [0.10, 0.05, 0.85, 0.10, 0.05, 0.85, 0.80],
+}
+ALL_FEEDERS = ['IEEE_13_Bus_allwye', 'IEEE_13_Bus_allwye_noxfm_noreg', 'IEEE_34_Bus_allwye',
+               'IEEE_34_Bus_allwye_noxfm_noreg', 'IEEE_37_Bus_allwye', 'IEEE_37_Bus_allwye_noxfm_noreg']
+LINES_ONLY = [f for f in ALL_FEEDERS if f.endswith('noxfm_noreg')]
+
+
+def feeder_path(name):
+    return os.path.join(GOLDEN, 'feeders', name + '.json')
+
+
+def load_model(name):
+    return read_dss(feeder_path(name))
+
+
+_cache = {}
+
+
+def snapshots():
+    if 'snap' not in _cache:
+        _cache['snap'] = np.load(os.path.join(GOLDEN, 'ref_snapshots.npz'))
+    return _cache['snap']
+
+
+def scenarios():
+    if 'scen' not in _cache:
+        _cache['scen'] = np.load(os.path.join(GOLDEN, 'ref_scenarios.npz'))
+    return _cache['scen']
+
+
+def recorded():
+    if 'rec' not in _cache:
+        with open(os.path.join(GOLDEN, 'recorded_tables.json')) as f:
+            _cache['rec'] = json.load(f)
+    return _cache['rec']
+
+
+def rel_err(a, b):
+    """max |a-b| / max(1, |b|) elementwise -- the 1e-9 'relative on complex bus
+    voltages' bar of BASELINE.json (voltages are O(1) pu, currents O(1))."""
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0

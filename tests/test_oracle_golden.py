@@ -1,0 +1,121 @@
+"""Pin the CPU oracle (oracle/gp_oracle.py) to the reference.
+
+* full-precision vectors produced by the unmodified reference run behind the
+  opendssdirect stand-in (oracle/make_golden.py -> tests/golden/*.npz);
+* gigpower's own recorded result tables (two decimals), parsed from
+  gigpower/tests/test_compare_{fbs,nr3}_dss/*.out.txt;
+* the known-answer values of SURVEY.md appendix B.
+"""
+import numpy as np
+import pytest
+
+from oracle.gp_oracle import FBSOracle, NR3Oracle, OracleCircuit
+from helpers import (ZIPS, ALL_FEEDERS, LINES_ONLY, load_model, snapshots, scenarios, recorded)
+
+TOL = 1e-12      # oracle vs reference, absolute on pu quantities
+
+
+@pytest.mark.parametrize('zname', list(ZIPS))
+@pytest.mark.parametrize('feeder', ALL_FEEDERS)
+def test_fbs_snapshot(feeder, zname):
+    snap = snapshots()
+    o = FBSOracle(load_model(feeder), ZIPS[zname])
+    r = o.solve()
+    k = f'{feeder}/{zname}/FBS/'
+    assert o.topo_order == list(snap[k + 'topo_order'])
+    assert int(r['iterations'][0]) == int(snap[k + 'iterations'])
+    assert bool(r['converged'][0]) == bool(snap[k + 'converged'])
+    assert abs(r['convergence_diff'][0] - float(snap[k + 'convergence_diff'])) <= 1e-15
+    for p in ('V', 'I', 'sV', 'Vmag', 'Stx', 'Srx'):
+        assert np.abs(r[p][0] - snap[k + p]).max() <= TOL, p
+
+
+@pytest.mark.parametrize('zname', list(ZIPS))
+@pytest.mark.parametrize('feeder', ALL_FEEDERS)
+def test_nr3_snapshot(feeder, zname):
+    snap = snapshots()
+    r = NR3Oracle(load_model(feeder), ZIPS[zname]).solve()
+    k = f'{feeder}/{zname}/NR3/'
+    assert int(r['iterations'][0]) == int(snap[k + 'iterations'])
+    assert np.abs(r['XNR'][0] - snap[k + 'XNR'][:, 0]).max() <= TOL
+    for p in ('V', 'I', 'sV', 'Vmag', 'Stx', 'Srx', 'i_Node'):
+        assert np.abs(r[p][0] - snap[k + p]).max() <= TOL, p
+
+
+@pytest.mark.parametrize('feeder', LINES_ONLY)
+def test_fbs_scenarios(feeder):
+    sc = scenarios()
+    o = FBSOracle(load_model(feeder), ZIPS['test_zip'])
+    mult = sc[feeder + '/mult']
+    c = o.c
+    spu = c.spu_matrix(c.load_kw * mult, c.load_kvar * mult)
+    r = o.solve(spu)
+    assert list(r['iterations']) == list(sc[feeder + '/FBS/iterations'])
+    assert np.abs(r['V'] - sc[feeder + '/FBS/V']).max() <= TOL
+    assert np.abs(r['I'] - sc[feeder + '/FBS/I']).max() <= TOL
+
+
+@pytest.mark.parametrize('feeder', LINES_ONLY)
+def test_nr3_scenarios(feeder):
+    sc = scenarios()
+    o = NR3Oracle(load_model(feeder), ZIPS['test_zip'])
+    X = sc[feeder + '/NR3/XNR']
+    mult = sc[feeder + '/mult'][:len(X)]
+    c = o.c
+    r = o.solve(c.spu_matrix(c.load_kw * mult, c.load_kvar * mult))
+    assert list(r['iterations']) == list(sc[feeder + '/NR3/iterations'])
+    assert np.abs(r['XNR'] - X).max() <= 1e-11
+
+
+# The 34-bus feeder with regulators has its controls ON in OpenDSS; the tap
+# positions OpenDSS chose are not recorded anywhere in the reference, so its
+# recorded tables cannot be reproduced.
+RECORDED_FEEDERS = [f for f in ALL_FEEDERS if f != 'IEEE_34_Bus_allwye']
+
+
+@pytest.mark.parametrize('algo', ['FBS', 'NR3'])
+@pytest.mark.parametrize('zname', list(ZIPS))
+@pytest.mark.parametrize('feeder', RECORDED_FEEDERS)
+def test_recorded_tables(feeder, zname, algo):
+    """gigpower's recorded tables print '{:.2f}': agreement within rounding."""
+    rec = recorded()
+    model = load_model(feeder)
+    if algo == 'FBS':
+        o = FBSOracle(model, ZIPS[zname])
+        r = {k: v[0] for k, v in o.solve().items() if k in ('V', 'I', 'sV', 'Vmag', 'Stx', 'Srx')}
+        r['I'], names_l = r['I'][:o.c.nl], o.c.line_names
+    else:
+        o = NR3Oracle(model, ZIPS[zname])
+        r = {k: v[0].T for k, v in o.solve().items() if k in ('V', 'I', 'sV', 'Vmag', 'Stx', 'Srx')}
+        names_l = o.c.line_names
+    n = 0
+    for p in ('V', 'I', 'sV', 'Vmag', 'Stx', 'Srx'):
+        table = rec[f'{feeder}/{zname}/{algo}/{p}']
+        names = o.c.bus_names if p in ('V', 'sV', 'Vmag') else names_l
+        assert list(table) == list(names)
+        for i, name in enumerate(names):
+            want = np.array([complex(*x) for x in table[name]])
+            assert np.abs(r[p][i].real - want.real).max() <= 0.005 + 1e-9, (p, name)
+            assert np.abs(r[p][i].imag - want.imag).max() <= 0.005 + 1e-9, (p, name)
+            n += 3
+    assert n > 0
+
+
+def test_known_answers_appendix_b():
+    """values of the reference on the 13-bus lines-only feeder."""
+    model = load_model('IEEE_13_Bus_allwye_noxfm_noreg')
+    c = OracleCircuit(model)
+    l = c.line_names.index('line_650_632')
+    assert abs(c.zbase[c.line_tx[l]] - 5.768533333333334) < 1e-15
+    assert abs(c.FZpu[l][0, 0] - (0.022752750554733723 + 0.06683989838286714j)) < 1e-17
+    r = FBSOracle(model).solve()
+    b = c.bus_names.index('675')
+    want = np.array([0.9085896347716701 - 0.11171348099844346j, -0.5405817165643256 - 0.8531996289341933j,
+                     -0.3838855973406417 + 0.7987657480063847j])
+    assert np.abs(r['V'][0, b] - want).max() < 1e-14
+    assert int(r['iterations'][0]) == 8
+    assert abs(r['convergence_diff'][0] - 3.2439829541267554e-07) < 1e-18
+    rn = NR3Oracle(model).solve()
+    want = np.array([0.9186175866955602 - 0.10464543644259171j, -0.5360926994597318 - 0.8502195082139851j,
+                     -0.3880887632230724 + 0.8105221042526009j])
+    assert np.abs(rn['V'][0, :, b] - want).max() < 1e-13
