@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the batched power-flow hot path (BASELINE.json metric:
+power-flow solves/sec).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--workload c2|c3|c4fbs|c5] [--solver fbs|nr3]
+
+A "step" is one pass of the hot path over one batch of synthetic scenarios:
+flat start -> per-scenario convergence -> |V| and losses.  At N=1 the default
+workload is BASELINE config C2 (IEEE 13-bus FBS, 65,536 random load-multiplier
+scenarios).  One process per GPU under torchrun; scenarios are sharded with no
+data-path collective, the only exchange is the final NCCL gather of |V| and
+losses.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+FEEDER_DIR = os.path.join(REPO, 'tests', 'golden', 'feeders')
+WORKLOADS = {
+    # name: (feeder file, solver, scenarios per GPU, seed, multiplier range, description)
+    'c2': ('IEEE_13_Bus_allwye_noxfm_noreg.json', 'fbs', 65536, 13, (0.5, 1.5),
+           'C2: IEEE 13-bus FBS, 65,536 load-multiplier scenarios U(0.5,1.5), seed 13'),
+    'c3': ('IEEE_37_Bus_allwye_noxfm_noreg.json', 'nr3', 16384, 37, (0.5, 1.5),
+           'C3: IEEE 37-bus NR3, 16,384 load-multiplier scenarios U(0.5,1.5), seed 37'),
+    'fbs37': ('IEEE_37_Bus_allwye_noxfm_noreg.json', 'fbs', 65536, 37, (0.5, 1.5),
+              'IEEE 37-bus FBS, 65,536 scenarios'),
+    'fbs34': ('IEEE_34_Bus_allwye_noxfm_noreg.json', 'fbs', 65536, 34, (0.5, 1.3),
+              'IEEE 34-bus FBS, 65,536 scenarios'),
+}
+
+
+def peaks():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                 '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def make_scenarios(sol, S, seed, lo, hi):
+    """Synthetic scenario batch: per-load multipliers -> packed spu rows [n_srows, S]."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    mult = rng.uniform(lo, hi, size=(S, sol.circuit.loads.num_elements))
+    return np.ascontiguousarray(sol.load_weights() @ mult.T), mult
+
+
+# --------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------
+def _cpu_worker(args):
+    feeder, solver, mult = args
+    os.environ['OMP_NUM_THREADS'] = '1'
+    from gigpower_b200.dss_reader import read_dss
+    from oracle.gp_oracle import FBSOracle, NR3Oracle
+    model = read_dss(os.path.join(FEEDER_DIR, feeder))
+    o = FBSOracle(model) if solver == 'fbs' else NR3Oracle(model)
+    c = o.c
+    t0 = time.perf_counter()
+    r = o.solve(c.spu_matrix(c.load_kw * mult, c.load_kvar * mult))
+    return time.perf_counter() - t0, int(r['iterations'].sum())
+
+
+class CpuPool:
+    """Persistent process pool running the oracle port on all host cores."""
+
+    def __init__(self, cores=None):
+        import multiprocessing as mp
+        self.cores = cores or (os.cpu_count() or 1)
+        self.pool = mp.get_context('spawn').Pool(self.cores)
+
+    def step(self, feeder, solver, mult, n_per_proc):
+        """Every core solves `n_per_proc` scenarios of the workload; returns
+        (scenarios solved, wall seconds)."""
+        jobs = []
+        for i in range(self.cores):
+            lo = (i * n_per_proc) % max(len(mult) - n_per_proc + 1, 1)
+            jobs.append((feeder, solver, mult[lo:lo + n_per_proc]))
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_worker, jobs)
+        return sum(len(j[2]) for j in jobs), time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(args, wl):
+    feeder, solver, S, seed, (lo, hi), desc = wl
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from gigpower_b200.dss_reader import read_dss
+    from gigpower_b200.circuit import Circuit
+    c = Circuit(read_dss(os.path.join(FEEDER_DIR, feeder)))
+    rng = np.random.Generator(np.random.PCG64(seed))
+    mult = rng.uniform(lo, hi, size=(S, c.loads.num_elements))
+    pool = CpuPool()
+    cores = pool.cores
+    n_per = 1024 if solver == 'fbs' else 8
+    for _ in range(max(args.warmup, 1)):
+        pool.step(feeder, solver, mult, max(n_per // 8, 1))
+    t0 = time.perf_counter()
+    tot = 0
+    for _ in range(args.steps):
+        n, _w = pool.step(feeder, solver, mult, n_per)
+        tot += n
+    wall = time.perf_counter() - t0
+    pool.close()
+    value = tot / wall
+    line = {
+        'impl': 'reference', 'metric': 'power-flow solves/sec', 'value': value, 'unit': 'solves/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * wall / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': desc, 'solver': solver},
+        'cpu_baseline': {'value': value, 'unit': 'solves/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{n_per} scenarios of the workload per core per step, oracle/gp_oracle.py '
+                                   f'(NumPy port of the reference, batched), persistent process pool'},
+        'e2e': {'value': value, 'unit': 'solves/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from gigpower_b200 import _cabi
+    feeder, solver, S, seed, (lo, hi), desc = wl
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    if solver == 'fbs':
+        from gigpower_b200.solution_fbs import SolutionFBS
+        sol = SolutionFBS(os.path.join(FEEDER_DIR, feeder), device=local)
+    else:
+        from gigpower_b200.solution_nr3 import SolutionNR3
+        sol = SolutionNR3(os.path.join(FEEDER_DIR, feeder), device=local)
+    rows, mult = make_scenarios(sol, S, seed + 1000 * rank, lo, hi)
+    sol._dev()
+    t = sol.tables
+    h = sol._feeder.handle
+    ld = S
+    spu_h = torch.from_numpy(rows).pin_memory()
+    spu_d = spu_h.to(dev)
+    c128, f64, i32 = torch.complex128, torch.float64, torch.int32
+    V = torch.empty((t.n_vrows, ld), dtype=c128, device=dev)
+    I = torch.empty((max(t.n_irows, 1), ld), dtype=c128, device=dev)
+    Vmag = torch.empty((t.n_vrows, ld), dtype=f64, device=dev)
+    loss = torch.empty(S, dtype=c128, device=dev)
+    iters = torch.empty(S, dtype=i32, device=dev)
+    status = torch.empty(S, dtype=i32, device=dev)
+    diff = torch.empty(S, dtype=f64, device=dev)
+    if world > 1:
+        Vmag_all = torch.empty((world, t.n_vrows, ld), dtype=f64, device=dev)
+        loss_all = torch.empty((world, S), dtype=c128, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    stream = torch.cuda.current_stream()
+    tol, maxiter = sol.tolerance, sol.maxiter
+
+    def solve_kernel():
+        _cabi.check(_cabi.gp_fbs_solve_batch(h, S, ld, spu_d.data_ptr(), V.data_ptr(), I.data_ptr(),
+                                             iters.data_ptr(), status.data_ptr(), diff.data_ptr(),
+                                             tol, maxiter, stream.cuda_stream))
+
+    def post_kernel():
+        _cabi.check(_cabi.gp_fbs_post(h, S, ld, spu_d.data_ptr(), V.data_ptr(), I.data_ptr(), None,
+                                      Vmag.data_ptr(), None, None, loss.data_ptr(), stream.cuda_stream))
+
+    def step():
+        solve_kernel()
+        post_kernel()
+        if world > 1:   # the path's one exchange: gather |V| and losses
+            dist.all_gather_into_tensor(Vmag_all, Vmag)
+            dist.all_gather_into_tensor(loss_all, loss)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step()
+    barrier()
+    # ---- timed region: K steps, device-timed per step, L2 flushed in between --------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _cabi.gp_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                 # untimed: evict the previous step's state from L2
+        if world > 1:
+            dist.barrier()
+        ev[k][0].record(stream)
+        solve_kernel()
+        ev[k][1].record(stream)
+        post_kernel()
+        if world > 1:
+            dist.all_gather_into_tensor(Vmag_all, Vmag)
+            dist.all_gather_into_tensor(loss_all, loss)
+        ev[k][2].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = _cabi.gp_launch_count() - launches0
+    ms_steps = np.array([e[0].elapsed_time(e[2]) for e in ev])
+    ms_solve = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    tot_ms = torch.tensor([ms_steps.sum()], dtype=f64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tot_ms.item()) / args.steps
+    value = world * S / (ms_per_step * 1e-3)
+    its = iters.cpu().numpy().astype(np.int64)
+    assert (status.cpu().numpy() == 0).all(), 'bench scenarios must all converge'
+
+    # ---- end to end through the host-buffer C-ABI (pinned host memory both ways) ---------
+    V_h = torch.empty((t.n_vrows, ld), dtype=c128).pin_memory()
+    loss_h = torch.empty(S, dtype=c128).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    sol.solve_batch_host(spu_h, V_h, None, None, loss_h)      # warm-up (allocates staging)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        it_h, st_h, df_h = sol.solve_batch_host(spu_h, V_h, None, None, loss_h)
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=f64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * S / float(e2e_t.item())
+    h2d = int(spu_h.numel() * 16)
+    d2h = int(V_h.numel() * 16 + loss_h.numel() * 16 + S * (4 + 4 + 8))
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        per_it = 16 * (2 * t.n_irows + 3 * t.n_vrows + t.n_srows)
+        once = 16 * (t.n_srows + t.n_vrows + t.n_irows)
+        alg_bytes = float(its.sum()) * per_it + S * once            # solve kernel, per launch
+        solve_ms = float(np.mean(ms_solve))
+        achieved = alg_bytes / (solve_ms * 1e-3) / 1e9
+        line = {
+            'metric': 'power-flow solves/sec', 'value': value, 'unit': 'solves/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': desc, 'solver': solver, 'scenarios_per_gpu': S,
+                       'rows': {'P_b': t.n_vrows, 'P_l': t.n_irows, 'P_L': t.n_srows},
+                       'mean_iterations': float(its.mean()), 'max_iterations': int(its.max()),
+                       'l2': 'flushed between steps (256 MiB write, untimed)',
+                       'timing': 'CUDA events per step on the launch stream, max over ranks',
+                       'parallelism': f'scenario-sharded x{world}, final NCCL all-gather of |V| and losses'},
+            'e2e': {'value': e2e_value, 'unit': 'solves/s', 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
+                    'api': 'gp_fbs_solve_batch_host (pinned host buffers; returns V, losses, iterations, status)'},
+            'gpu_launches': int(launches),
+            'roofline': {'bound': 'hbm', 'kernel': 'fbs_solve_kernel', 'achieved': achieved,
+                         'peak': pk['hbm_gbs'], 'peak_kind': pk_kind, 'unit': 'GB/s',
+                         'frac': achieved / pk['hbm_gbs'], 'traffic': None,
+                         'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': solve_ms,
+                         'kernel_share_of_step': solve_ms / float(np.mean(ms_steps))},
+            'clocks': clocks, 'wall_s_timed_region': t_wall,
+        }
+        if world == 1 and not args.no_cpu:
+            pool = CpuPool()
+            n_per = 1024 if solver == 'fbs' else 8
+            pool.step(feeder, solver, mult, max(n_per // 8, 1))          # warm the workers
+            n, wall, reps = 0, 0.0, 0
+            while wall < 10.0 and reps < 50:
+                dn, dw = pool.step(feeder, solver, mult, n_per)
+                n, wall, reps = n + dn, wall + dw, reps + 1
+            pool.close()
+            line['cpu_baseline'] = {
+                'value': n / wall, 'unit': 'solves/s', 'cores': pool.cores, 'kind': 'port',
+                'sample': f'{n} scenarios of the workload ({n_per} per core per call, {reps} calls, '
+                          f'{wall:.1f} s), oracle/gp_oracle.py batched NumPy port on a process pool'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == '__main__':
+    main()

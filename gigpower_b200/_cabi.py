@@ -1,0 +1,110 @@
+"""ctypes binding of ``include/gigpower_b200.h``.
+
+The library is the product: there is no CPU fallback.  If
+``libgigpower_b200.so`` is missing the import of this module raises, and every
+solve raises if no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libgigpower_b200.so')
+
+
+class GpError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build the CUDA library first "
+        f"(python -m gigpower_b200.csrc.build, or __graft_entry__.build()). "
+        f"gigpower_b200 has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+i32p, f64p, vp = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_void_p
+
+
+class GpFbsDesc(C.Structure):
+    _fields_ = [
+        ('n_steps', C.c_int32), ('n_vrows', C.c_int32), ('n_irows', C.c_int32),
+        ('n_srows', C.c_int32), ('n_child', C.c_int32), ('n_lines', C.c_int32),
+        ('bus_vrow', i32p), ('par_vrow', i32p), ('edge_irow', i32p), ('load_srow', i32p),
+        ('kind', i32p), ('child_begin', i32p), ('child_count', i32p), ('child_irow', i32p),
+        ('z', f64p), ('cappu', f64p), ('vr_gamma', f64p),
+        ('root_vrow', C.c_int32 * 3), ('root_load_srow', C.c_int32 * 3),
+        ('root_cappu', C.c_double * 3), ('vref', C.c_double * 6), ('zip', C.c_double * 3),
+        ('line_irow', i32p), ('line_tx_vrow', i32p), ('line_rx_vrow', i32p),
+    ]
+
+
+def _sig(name, restype, argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = argtypes
+    return fn
+
+
+gp_version = _sig('gp_version', C.c_int, [])
+gp_last_error = _sig('gp_last_error', C.c_int, [C.c_char_p, C.c_size_t])
+gp_launch_count = _sig('gp_launch_count', C.c_int64, [])
+gp_fbs_create = _sig('gp_fbs_create', C.c_int, [C.POINTER(GpFbsDesc), C.c_int, C.POINTER(vp)])
+gp_feeder_destroy = _sig('gp_feeder_destroy', C.c_int, [vp])
+gp_fbs_solve_batch = _sig('gp_fbs_solve_batch', C.c_int,
+                          [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_double, C.c_int32, vp])
+gp_fbs_post = _sig('gp_fbs_post', C.c_int,
+                   [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp])
+gp_fbs_solve_batch_host = _sig('gp_fbs_solve_batch_host', C.c_int,
+                               [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp,
+                                C.c_double, C.c_int32])
+
+EXPORTS = ['gp_version', 'gp_last_error', 'gp_launch_count', 'gp_fbs_create', 'gp_feeder_destroy',
+           'gp_fbs_solve_batch', 'gp_fbs_post', 'gp_fbs_solve_batch_host']
+
+
+def check(rc: int):
+    if rc != 0:
+        buf = C.create_string_buffer(512)
+        gp_last_error(buf, 512)
+        raise GpError(f"gigpower_b200 error {rc}: {buf.value.decode(errors='replace')}")
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def make_fbs_desc(t):
+    """FbsTables -> (GpFbsDesc, keep-alive list)."""
+    keep = {}
+    d = GpFbsDesc()
+    d.n_steps, d.n_vrows, d.n_irows, d.n_srows = t.n_steps, t.n_vrows, t.n_irows, t.n_srows
+    d.n_child, d.n_lines = int(t.child_irow.shape[0]), t.n_lines
+    for name in ('bus_vrow', 'par_vrow', 'edge_irow', 'load_srow', 'kind', 'child_begin',
+                 'child_count', 'child_irow', 'line_irow', 'line_tx_vrow', 'line_rx_vrow'):
+        keep[name] = _i32(getattr(t, name))
+        setattr(d, name, keep[name].ctypes.data_as(i32p))
+    for name in ('z', 'cappu', 'vr_gamma'):
+        keep[name] = _f64(getattr(t, name))
+        setattr(d, name, keep[name].ctypes.data_as(f64p))
+    d.root_vrow = (C.c_int32 * 3)(*[int(x) for x in t.root_vrow])
+    d.root_load_srow = (C.c_int32 * 3)(*[int(x) for x in t.root_load_srow])
+    d.root_cappu = (C.c_double * 3)(*[float(x) for x in t.root_cappu])
+    d.vref = (C.c_double * 6)(*[float(x) for x in t.vref])
+    d.zip = (C.c_double * 3)(*[float(x) for x in t.zip])
+    return d, keep
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise GpError("gigpower_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch

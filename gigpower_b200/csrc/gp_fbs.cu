@@ -1,0 +1,567 @@
+// Batched Forward-Backward Sweep for sm_100a.
+//
+// One thread owns one scenario and walks the feeder tree exactly in the
+// reference's order (solution_fbs.py:87-128): forward sweep over topo_order,
+// ZIP loads, backward sweep over reversed(topo_order) including the parent
+// voltage rewrite, root-mismatch convergence test.  Scenarios are independent,
+// so there is no inter-thread communication; a thread leaves the loop at the
+// iteration its scenario converges, which is the per-scenario "freeze" that
+// 1e-9 parity needs.
+//
+// Memory: state lives in HBM as packed rows [row][ld] of complex128 with the
+// scenario index innermost, so every access of a warp is one 512-byte coalesced
+// 128-bit transaction.  The per-feeder step table is scenario-invariant; all
+// lanes read the same words (broadcast through L1/the read-only path).
+#include "gp_common.cuh"
+
+#include <new>
+#include <vector>
+
+namespace gp {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+struct __align__(16) FbsStep {
+    int bus_vrow[3];
+    int kind;
+    int par_vrow[3];
+    int child_begin;
+    int edge_irow[3];
+    int child_count;
+    int load_srow[3];
+    int pad0;
+    double cap[3];
+    double pad1;
+    double gamma[3];
+    double pad2;
+    double inv_gamma[3];
+    double pad3;
+    double2 z[9];
+};
+static_assert(sizeof(FbsStep) == 64 + 32 + 32 + 32 + 144, "FbsStep layout");
+
+struct FbsConst {
+    int root_vrow[3];
+    int root_load_srow[3];
+    double root_cap[3];
+    double2 vref[3];
+    double aPQ, aI, aZ;
+};
+
+struct FbsImpl {
+    int n_steps = 0, n_vrows = 0, n_irows = 0, n_srows = 0, n_child = 0, n_lines = 0;
+    FbsStep* d_steps = nullptr;
+    int* d_child = nullptr;   // [n_child][3]
+    int* d_lines = nullptr;   // [n_lines][9] irow, tx vrow, rx vrow
+    int* d_vrow_srow = nullptr;   // [n_vrows] spu row of each V row or -1
+    double* d_vrow_cap = nullptr; // [n_vrows]
+    FbsConst k;
+    // host staging for gp_fbs_solve_batch_host
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    void* d_stage[3] = {nullptr, nullptr, nullptr};
+    size_t stage_bytes = 0;
+};
+
+__device__ __forceinline__ double2 ldc(const double2* p) { return *p; }
+
+// |v| as numpy computes it for the ZIP model (abs then square, solution.py:202)
+__device__ __forceinline__ double cabs2(double2 v, double& a) {
+    a = sqrt(fma(v.x, v.x, v.y * v.y));
+    return a * a;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+fbs_solve_kernel(const FbsStep* __restrict__ steps, const int* __restrict__ child_irow,
+                 FbsConst k, int n_steps, int n_vrows, int n_irows, long long S, long long ld,
+                 const double2* __restrict__ spu, double2* __restrict__ V,
+                 double2* __restrict__ I, int* __restrict__ iters_out,
+                 int* __restrict__ status_out, double* __restrict__ diff_out, double tol,
+                 int maxiter) {
+    const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (s >= S) return;
+    const double2* spu_s = spu + s;
+    double2* Vs = V + s;
+    double2* Is = I + s;
+
+    // flat start (solution.py:108-125): V = I = 0.  I is read by the first forward
+    // sweep and V rows that no edge feeds (non-regulated phases below a regulator)
+    // keep their initial value, so both are zeroed here, coalesced, once.
+    for (int r = 0; r < n_vrows; ++r) Vs[(long long)r * ld] = make_double2(0.0, 0.0);
+    for (int r = 0; r < n_irows; ++r) Is[(long long)r * ld] = make_double2(0.0, 0.0);
+    int it = 0;
+    double diff = -1.0;
+    bool converged = false;   // Vtest = 0 -> max|0 - Vref| = 1 > tol (solution_fbs.py:85)
+
+    while (!converged && it < maxiter) {
+        // V[root] = Vref  (:89)
+#pragma unroll
+        for (int p = 0; p < 3; ++p) Vs[(long long)k.root_vrow[p] * ld] = k.vref[p];
+
+        // ---- forward sweep (:92-98, update_voltage_forward :162-184) -------
+        for (int pos = 0; pos < n_steps; ++pos) {
+            const FbsStep* st = steps + pos;
+            const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
+            const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
+            const int brow[3] = {bv.x, bv.y, bv.z};
+            const int prow[3] = {pv.x, pv.y, pv.z};
+            const int kind = bv.w;
+            double2 Vp[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+                Vp[p] = prow[p] >= 0 ? Vs[(long long)prow[p] * ld] : make_double2(0.0, 0.0);
+            if (kind == GP_EDGE_VR) {   // vr_forward :138-160
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const double g = __ldg(&st->gamma[p]);
+                    if (g != 0.0 && brow[p] >= 0)
+                        Vs[(long long)brow[p] * ld] = make_double2(g * Vp[p].x, g * Vp[p].y);
+                }
+                continue;
+            }
+            const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
+            const int erow[3] = {ev.x, ev.y, ev.z};
+            double2 Il[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+                Il[p] = erow[p] >= 0 ? Is[(long long)erow[p] * ld] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                if (brow[p] < 0) continue;
+                double2 v = Vp[p];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (erow[q] < 0) continue;
+                    const double2 z = __ldg(&st->z[3 * p + q]);
+                    v.x -= z.x * Il[q].x - z.y * Il[q].y;
+                    v.y -= z.x * Il[q].y + z.y * Il[q].x;
+                }
+                Vs[(long long)brow[p] * ld] = v;
+            }
+        }
+
+        // ---- backward sweep (:104-121) --------------------------------------
+        for (int pos = n_steps - 1; pos >= 0; --pos) {
+            const FbsStep* st = steps + pos;
+            const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
+            const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
+            const int brow[3] = {bv.x, bv.y, bv.z};
+            const int prow[3] = {pv.x, pv.y, pv.z};
+            const int kind = bv.w;
+            const int child_begin = pv.w;
+            double2 Vb[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+                Vb[p] = brow[p] >= 0 ? Vs[(long long)brow[p] * ld] : make_double2(0.0, 0.0);
+            if (kind == GP_EDGE_VR) {   // vr_current leaves Itx = 0; vr_backward :186-205
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const double g = __ldg(&st->gamma[p]);
+                    if (g != 0.0 && prow[p] >= 0) {
+                        const double ig = __ldg(&st->inv_gamma[p]);
+                        Vs[(long long)prow[p] * ld] = make_double2(ig * Vb[p].x, ig * Vb[p].y);
+                    }
+                }
+                continue;
+            }
+            const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
+            const int4 lv = __ldg(reinterpret_cast<const int4*>(st->load_srow));
+            const int erow[3] = {ev.x, ev.y, ev.z};
+            const int lrow[3] = {lv.x, lv.y, lv.z};
+            const int child_count = ev.w;
+            // calc_sV(bus) (solution.py:177-220) + update_current (:256-288)
+            double2 In[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                In[p] = make_double2(0.0, 0.0);
+                if (brow[p] < 0) continue;
+                const double2 v = Vb[p];
+                double a;
+                const double a2 = cabs2(v, a);
+                double2 sv = make_double2(0.0, 0.0);
+                if (lrow[p] >= 0) {
+                    const double2 sp = spu_s[(long long)lrow[p] * ld];
+                    const double f = k.aPQ + k.aI * a + k.aZ * a2;
+                    sv.x = sp.x * f;
+                    sv.y = sp.y * f;
+                }
+                sv.y -= __ldg(&st->cap[p]) * a2;
+                if (v.x != 0.0 || v.y != 0.0) {
+                    // conj(sV / V) = conj(sV) * V / |V|^2 ... computed as (sV * conj(V)) / |V|^2, conjugated
+                    const double inv = 1.0 / fma(v.x, v.x, v.y * v.y);
+                    const double qr = (sv.x * v.x + sv.y * v.y) * inv;
+                    const double qi = (sv.y * v.x - sv.x * v.y) * inv;
+                    In[p] = make_double2(qr, -qi);
+                }
+            }
+            for (int c = 0; c < child_count; ++c) {
+                const int* cr = child_irow + 3 * (child_begin + c);
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const int r = __ldg(cr + p);
+                    if (r >= 0) {
+                        const double2 ic = Is[(long long)r * ld];
+                        In[p].x += ic.x;
+                        In[p].y += ic.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                if (erow[p] >= 0) {
+                    In[p] = make_double2(nan_to_num(In[p].x), nan_to_num(In[p].y));
+                    Is[(long long)erow[p] * ld] = In[p];
+                } else {
+                    In[p] = make_double2(0.0, 0.0);
+                }
+            }
+            // update_voltage_backward (:207-232): phases of the child bus, masked by the parent
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                if (brow[p] < 0 || prow[p] < 0) continue;
+                double2 v = Vb[p];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (erow[q] < 0) continue;
+                    const double2 z = __ldg(&st->z[3 * p + q]);
+                    v.x += z.x * In[q].x - z.y * In[q].y;
+                    v.y += z.x * In[q].y + z.y * In[q].x;
+                }
+                Vs[(long long)prow[p] * ld] = v;
+            }
+        }
+
+        // ---- convergence (:123-128) -----------------------------------------
+        ++it;
+        diff = 0.0;
+        bool nan = false;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const double2 v = Vs[(long long)k.root_vrow[p] * ld];
+            const double dx = v.x - k.vref[p].x, dy = v.y - k.vref[p].y;
+            const double d = sqrt(fma(dx, dx, dy * dy));
+            nan |= (d != d);
+            diff = fmax(diff, d);   // numpy max propagates NaN; handled below
+        }
+        if (nan) diff = __longlong_as_double(0x7ff8000000000000LL);
+        converged = diff <= tol;
+    }
+    iters_out[s] = it;
+    diff_out[s] = diff;
+    status_out[s] = converged ? GP_ST_CONVERGED : ((diff != diff || isinf(diff)) ? GP_ST_NONFINITE : GP_ST_MAXITER);
+}
+
+// Derived results: sV, |V| per V row; Stx/Srx per line row; loss per scenario.
+__global__ void fbs_post_rows_kernel(int n_vrows, const int* __restrict__ vrow_srow,
+                                     const double* __restrict__ vrow_cap, FbsConst k, long long S,
+                                     long long ld, const double2* __restrict__ spu,
+                                     const double2* __restrict__ V, double2* __restrict__ sV,
+                                     double* __restrict__ Vmag) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    for (int r = blockIdx.y; r < n_vrows; r += gridDim.y) {
+        const double2 v = V[(long long)r * ld + s];
+        double a;
+        const double a2 = cabs2(v, a);
+        if (Vmag) Vmag[(long long)r * ld + s] = a;
+        if (sV) {
+            double2 sv = make_double2(0.0, 0.0);
+            const int lr = __ldg(vrow_srow + r);
+            if (lr >= 0) {
+                const double2 sp = spu[(long long)lr * ld + s];
+                const double f = k.aPQ + k.aI * a + k.aZ * a2;
+                sv.x = sp.x * f;
+                sv.y = sp.y * f;
+            }
+            sv.y -= __ldg(vrow_cap + r) * a2;
+            sV[(long long)r * ld + s] = sv;
+        }
+    }
+}
+
+__global__ void fbs_post_lines_kernel(int n_lines, const int* __restrict__ lines, long long S,
+                                      long long ld, const double2* __restrict__ V,
+                                      const double2* __restrict__ I, double2* __restrict__ Stx,
+                                      double2* __restrict__ Srx, double2* __restrict__ loss) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double2 acc = make_double2(0.0, 0.0);
+    for (int l = 0; l < n_lines; ++l) {
+        const int* rec = lines + 9 * l;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const int ir = __ldg(rec + p);
+            if (ir < 0) continue;   // I is 0 on phases the line lacks -> S = 0
+            const int tr = __ldg(rec + 3 + p), rr = __ldg(rec + 6 + p);
+            const double2 i = I[(long long)ir * ld + s];
+            const double2 vt = tr >= 0 ? V[(long long)tr * ld + s] : make_double2(0.0, 0.0);
+            const double2 vr = rr >= 0 ? V[(long long)rr * ld + s] : make_double2(0.0, 0.0);
+            // V * conj(I)
+            const double2 st = make_double2(vt.x * i.x + vt.y * i.y, vt.y * i.x - vt.x * i.y);
+            const double2 sr = make_double2(vr.x * i.x + vr.y * i.y, vr.y * i.x - vr.x * i.y);
+            if (Stx) Stx[(long long)ir * ld + s] = st;
+            if (Srx) Srx[(long long)ir * ld + s] = sr;
+            acc.x += st.x - sr.x;
+            acc.y += st.y - sr.y;
+        }
+    }
+    if (loss) loss[s] = acc;
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" int gp_version(void) { return 100; }
+
+extern "C" int gp_last_error(char* buf, size_t len) {
+    if (!buf || len == 0) return GP_EINVAL;
+    strncpy(buf, g_err, len - 1);
+    buf[len - 1] = 0;
+    return GP_OK;
+}
+
+extern "C" int64_t gp_launch_count(void) { return g_launches.load(); }
+
+extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
+    if (!d || !out) return fail(GP_EINVAL, "gp_fbs_create: null argument");
+    if (d->n_steps < 0 || d->n_vrows <= 0 || d->n_irows < 0 || d->n_srows < 0)
+        return fail(GP_EINVAL, "gp_fbs_create: bad sizes");
+    GP_CUDA(cudaSetDevice(device));
+    FbsImpl* im = new (std::nothrow) FbsImpl();
+    if (!im) return fail(GP_ENOMEM, "gp_fbs_create: out of host memory");
+    im->n_steps = d->n_steps;
+    im->n_vrows = d->n_vrows;
+    im->n_irows = d->n_irows;
+    im->n_srows = d->n_srows;
+    im->n_child = d->n_child;
+    im->n_lines = d->n_lines;
+    std::vector<FbsStep> steps((size_t)d->n_steps);
+    std::vector<int> vrow_srow((size_t)d->n_vrows, -1);
+    std::vector<double> vrow_cap((size_t)d->n_vrows, 0.0);
+    auto chk = [&](int r, int n) { return r >= -1 && r < n; };
+    for (int i = 0; i < d->n_steps; ++i) {
+        FbsStep& s = steps[i];
+        memset(&s, 0, sizeof(s));
+        s.kind = d->kind[i];
+        s.child_begin = d->child_begin[i];
+        s.child_count = d->child_count[i];
+        if (s.child_begin < 0 || s.child_count < 0 || s.child_begin + s.child_count > d->n_child) {
+            delete im;
+            return fail(GP_EINVAL, "gp_fbs_create: step %d child range out of bounds", i);
+        }
+        for (int p = 0; p < 3; ++p) {
+            s.bus_vrow[p] = d->bus_vrow[3 * i + p];
+            s.par_vrow[p] = d->par_vrow[3 * i + p];
+            s.edge_irow[p] = d->edge_irow[3 * i + p];
+            s.load_srow[p] = d->load_srow[3 * i + p];
+            if (!chk(s.bus_vrow[p], d->n_vrows) || !chk(s.par_vrow[p], d->n_vrows) ||
+                !chk(s.edge_irow[p], d->n_irows) || !chk(s.load_srow[p], d->n_srows)) {
+                delete im;
+                return fail(GP_EINVAL, "gp_fbs_create: step %d row index out of range", i);
+            }
+            s.cap[p] = d->cappu[3 * i + p];
+            s.gamma[p] = d->vr_gamma[3 * i + p];
+            s.inv_gamma[p] = s.gamma[p] != 0.0 ? 1.0 / s.gamma[p] : 0.0;
+            if (s.bus_vrow[p] >= 0) {
+                vrow_srow[s.bus_vrow[p]] = s.load_srow[p];
+                vrow_cap[s.bus_vrow[p]] = s.cap[p];
+            }
+            for (int q = 0; q < 3; ++q) {
+                s.z[3 * p + q].x = d->z[((size_t)i * 9 + 3 * p + q) * 2];
+                s.z[3 * p + q].y = d->z[((size_t)i * 9 + 3 * p + q) * 2 + 1];
+            }
+        }
+    }
+    for (int p = 0; p < 3; ++p) {
+        im->k.root_vrow[p] = d->root_vrow[p];
+        im->k.root_load_srow[p] = d->root_load_srow[p];
+        im->k.root_cap[p] = d->root_cappu[p];
+        im->k.vref[p] = make_double2(d->vref[2 * p], d->vref[2 * p + 1]);
+        if (d->root_vrow[p] < 0 || d->root_vrow[p] >= d->n_vrows) {
+            delete im;
+            return fail(GP_EINVAL, "gp_fbs_create: the root bus must carry all three phases");
+        }
+        vrow_srow[d->root_vrow[p]] = d->root_load_srow[p];
+        vrow_cap[d->root_vrow[p]] = d->root_cappu[p];
+    }
+    im->k.aPQ = d->zip[0];
+    im->k.aI = d->zip[1];
+    im->k.aZ = d->zip[2];
+    std::vector<int> lines((size_t)d->n_lines * 9);
+    for (int l = 0; l < d->n_lines; ++l)
+        for (int p = 0; p < 3; ++p) {
+            lines[9 * l + p] = d->line_irow[3 * l + p];
+            lines[9 * l + 3 + p] = d->line_tx_vrow[3 * l + p];
+            lines[9 * l + 6 + p] = d->line_rx_vrow[3 * l + p];
+        }
+    auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
+        if (e != cudaSuccess) return e;
+        return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    cudaError_t e = up((void**)&im->d_steps, steps.data(), steps.size() * sizeof(FbsStep));
+    if (e == cudaSuccess) e = up((void**)&im->d_child, d->child_irow, (size_t)d->n_child * 3 * sizeof(int));
+    if (e == cudaSuccess) e = up((void**)&im->d_lines, lines.data(), lines.size() * sizeof(int));
+    if (e == cudaSuccess) e = up((void**)&im->d_vrow_srow, vrow_srow.data(), vrow_srow.size() * sizeof(int));
+    if (e == cudaSuccess) e = up((void**)&im->d_vrow_cap, vrow_cap.data(), vrow_cap.size() * sizeof(double));
+    if (e != cudaSuccess) {
+        delete im;
+        return fail(GP_ECUDA, "gp_fbs_create: %s", cudaGetErrorString(e));
+    }
+    GpFeeder* f = new (std::nothrow) GpFeeder();
+    f->device = device;
+    f->kind = 1;
+    f->impl = im;
+    *out = f;
+    return GP_OK;
+}
+
+extern "C" int gp_feeder_destroy(GpFeeder* f) {
+    if (!f) return GP_OK;
+    cudaSetDevice(f->device);
+    if (f->kind == 1) {
+        FbsImpl* im = (FbsImpl*)f->impl;
+        cudaFree(im->d_steps);
+        cudaFree(im->d_child);
+        cudaFree(im->d_lines);
+        cudaFree(im->d_vrow_srow);
+        cudaFree(im->d_vrow_cap);
+        for (int i = 0; i < 3; ++i) {
+            if (im->d_stage[i]) cudaFree(im->d_stage[i]);
+            if (im->streams[i]) cudaStreamDestroy(im->streams[i]);
+        }
+        delete im;
+    }
+    delete f;
+    return GP_OK;
+}
+
+static int fbs_check(GpFeeder* f, int64_t S, int64_t ld, const char* who) {
+    if (!f || f->kind != 1) return fail(GP_EINVAL, "%s: not an FBS feeder handle", who);
+    if (S < 0 || ld < S) return fail(GP_EINVAL, "%s: need 0 <= S <= ld (S=%lld ld=%lld)", who, (long long)S, (long long)ld);
+    return GP_OK;
+}
+
+extern "C" int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const double* spu,
+                                  double* V, double* I, int32_t* iters, int32_t* status,
+                                  double* diff, double tol, int32_t maxiter, void* stream) {
+    int rc = fbs_check(f, S, ld, "gp_fbs_solve_batch");
+    if (rc) return rc;
+    if (S == 0) return GP_OK;
+    FbsImpl* im = (FbsImpl*)f->impl;
+    if (!V || !I || !iters || !status || !diff || (!spu && im->n_srows > 0))
+        return fail(GP_EINVAL, "gp_fbs_solve_batch: null buffer");
+    GP_CUDA(cudaSetDevice(f->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int BLOCK = 128;
+    const unsigned gx = (unsigned)((S + BLOCK - 1) / BLOCK);
+    fbs_solve_kernel<BLOCK><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
+                                                  im->n_irows, S, ld, (const double2*)spu, (double2*)V,
+                                                  (double2*)I, iters, status, diff, tol, maxiter);
+    count_launch();
+    GP_CUDA(cudaGetLastError());
+    return GP_OK;
+}
+
+extern "C" int gp_fbs_post(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const double* V,
+                           const double* I, double* sV, double* Vmag, double* Stx, double* Srx,
+                           double* loss, void* stream) {
+    int rc = fbs_check(f, S, ld, "gp_fbs_post");
+    if (rc) return rc;
+    if (S == 0) return GP_OK;
+    FbsImpl* im = (FbsImpl*)f->impl;
+    if (!V || !I) return fail(GP_EINVAL, "gp_fbs_post: null state buffer");
+    if (sV && !spu && im->n_srows > 0) return fail(GP_EINVAL, "gp_fbs_post: sV needs spu");
+    GP_CUDA(cudaSetDevice(f->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int BLOCK = 128;
+    const unsigned gx = (unsigned)((S + BLOCK - 1) / BLOCK);
+    if (sV || Vmag) {
+        dim3 g(gx, 8);
+        fbs_post_rows_kernel<<<g, BLOCK, 0, st>>>(im->n_vrows, im->d_vrow_srow, im->d_vrow_cap, im->k, S, ld,
+                                                  (const double2*)spu, (const double2*)V, (double2*)sV, Vmag);
+        count_launch();
+    }
+    if (Stx || Srx || loss) {
+        fbs_post_lines_kernel<<<gx, BLOCK, 0, st>>>(im->n_lines, im->d_lines, S, ld, (const double2*)V,
+                                                    (const double2*)I, (double2*)Stx, (double2*)Srx,
+                                                    (double2*)loss);
+        count_launch();
+    }
+    GP_CUDA(cudaGetLastError());
+    return GP_OK;
+}
+
+// Host-buffer path: chunk the batch, triple-buffer H2D / solve / D2H on three streams.
+extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const double* spu_h,
+                                       double* V_h, double* I_h, double* Vmag_h, double* loss_h,
+                                       int32_t* iters_h, int32_t* status_h, double* diff_h,
+                                       double tol, int32_t maxiter) {
+    int rc = fbs_check(f, S, ld, "gp_fbs_solve_batch_host");
+    if (rc) return rc;
+    if (S == 0) return GP_OK;
+    FbsImpl* im = (FbsImpl*)f->impl;
+    if (!spu_h && im->n_srows > 0) return fail(GP_EINVAL, "gp_fbs_solve_batch_host: null spu");
+    GP_CUDA(cudaSetDevice(f->device));
+    // chunk of scenarios per stream: a power of two >= 1024, <= ~16 MB of rows per chunk
+    const int64_t rows = (int64_t)im->n_vrows + im->n_irows + im->n_srows;
+    int64_t C = (int64_t)1 << 15;
+    while (C > 1024 && C * rows * 16 > ((int64_t)16 << 20)) C >>= 1;
+    if (C > S) C = (S + 127) / 128 * 128;
+    // per-chunk device layout: spu | V | I | Vmag | loss | diff | iters | status
+    const size_t b_spu = (size_t)im->n_srows * C * 16, b_V = (size_t)im->n_vrows * C * 16,
+                 b_I = (size_t)im->n_irows * C * 16, b_mag = (size_t)im->n_vrows * C * 8,
+                 b_loss = (size_t)C * 16, b_diff = (size_t)C * 8, b_i32 = (size_t)C * 4;
+    const size_t need = b_spu + b_V + b_I + b_mag + b_loss + b_diff + 2 * b_i32 + 1024;
+    if (need > im->stage_bytes) {
+        for (int i = 0; i < 3; ++i) {
+            if (im->d_stage[i]) cudaFree(im->d_stage[i]);
+            im->d_stage[i] = nullptr;
+            GP_CUDA(cudaMalloc(&im->d_stage[i], need));
+            if (!im->streams[i]) GP_CUDA(cudaStreamCreateWithFlags(&im->streams[i], cudaStreamNonBlocking));
+        }
+        im->stage_bytes = need;
+    }
+    int slot = 0;
+    for (int64_t s0 = 0; s0 < S; s0 += C, slot = (slot + 1) % 3) {
+        const int64_t n = (S - s0 < C) ? (S - s0) : C;
+        cudaStream_t st = im->streams[slot];
+        char* base = (char*)im->d_stage[slot];
+        double* d_spu = (double*)base;
+        double* d_V = (double*)(base + b_spu);
+        double* d_I = (double*)(base + b_spu + b_V);
+        double* d_mag = (double*)(base + b_spu + b_V + b_I);
+        double* d_loss = (double*)(base + b_spu + b_V + b_I + b_mag);
+        double* d_diff = (double*)(base + b_spu + b_V + b_I + b_mag + b_loss);
+        int32_t* d_it = (int32_t*)(base + b_spu + b_V + b_I + b_mag + b_loss + b_diff);
+        int32_t* d_st = d_it + C;
+        if (im->n_srows > 0)
+            GP_CUDA(cudaMemcpy2DAsync(d_spu, (size_t)C * 16, spu_h + 2 * s0, (size_t)ld * 16, (size_t)n * 16,
+                                      im->n_srows, cudaMemcpyHostToDevice, st));
+        rc = gp_fbs_solve_batch(f, n, C, d_spu, d_V, d_I, d_it, d_st, d_diff, tol, maxiter, st);
+        if (rc) return rc;
+        if (Vmag_h || loss_h) {
+            rc = gp_fbs_post(f, n, C, d_spu, d_V, d_I, nullptr, Vmag_h ? d_mag : nullptr, nullptr, nullptr,
+                             loss_h ? d_loss : nullptr, st);
+            if (rc) return rc;
+        }
+        if (V_h)
+            GP_CUDA(cudaMemcpy2DAsync(V_h + 2 * s0, (size_t)ld * 16, d_V, (size_t)C * 16, (size_t)n * 16,
+                                      im->n_vrows, cudaMemcpyDeviceToHost, st));
+        if (I_h && im->n_irows > 0)
+            GP_CUDA(cudaMemcpy2DAsync(I_h + 2 * s0, (size_t)ld * 16, d_I, (size_t)C * 16, (size_t)n * 16,
+                                      im->n_irows, cudaMemcpyDeviceToHost, st));
+        if (Vmag_h)
+            GP_CUDA(cudaMemcpy2DAsync(Vmag_h + s0, (size_t)ld * 8, d_mag, (size_t)C * 8, (size_t)n * 8,
+                                      im->n_vrows, cudaMemcpyDeviceToHost, st));
+        if (loss_h) GP_CUDA(cudaMemcpyAsync(loss_h + 2 * s0, d_loss, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+        if (diff_h) GP_CUDA(cudaMemcpyAsync(diff_h + s0, d_diff, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        if (iters_h) GP_CUDA(cudaMemcpyAsync(iters_h + s0, d_it, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (status_h) GP_CUDA(cudaMemcpyAsync(status_h + s0, d_st, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < 3; ++i)
+        if (im->streams[i]) GP_CUDA(cudaStreamSynchronize(im->streams[i]));
+    return GP_OK;
+}

@@ -1,0 +1,229 @@
+"""Circuit -> flat device tables (the host "flattener").
+
+FBS: the sweep order of the reference is fixed by ``SolutionFBS.set_adj``
+(``src/solution_fbs.py:39-74``) and ``topo_sort`` (``src/utils.py:130-167``);
+both are reproduced here on bus indices, then every non-root bus becomes one
+"step" (bus, parent, incoming edge) of the table described by ``GpFbsDesc`` in
+``include/gigpower_b200.h``.  State rows are packed: only existing
+(bus, phase), (edge, phase) and loaded (bus, phase) pairs get a row.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List
+
+import numpy as np
+
+from .circuit import Circuit
+
+EDGE_LINE, EDGE_VR = 0, 1
+
+
+def fbs_adjacency(c: Circuit) -> Dict[str, List[str]]:
+    """Directed adjacency by bus name: lines in definition order, then
+    transformers, then one edge per regulated bus pair with the upstream leg
+    removed (solution_fbs.py:39-74)."""
+    adj: Dict[str, List[str]] = {}
+    for e in c.lines.get_elements():
+        adj.setdefault(e.tx, []).append(e.rx)
+    for e in c.transformers.get_elements():
+        adj.setdefault(e.tx, []).append(e.rx)
+    pairs: Dict[str, List[str]] = {}
+    for vr in c.voltage_regulators.get_elements():
+        for a, b in ((vr.tx, vr.rx), (vr.rx, vr.tx)):
+            if b not in pairs.setdefault(a, []):
+                pairs[a].append(b)
+    for node, nbrs in pairs.items():
+        adj[node] = adj.get(node, []) + nbrs
+    for vr in c.voltage_regulators.get_elements():
+        if vr.tx in adj.get(vr.rx, []):
+            adj[vr.rx].remove(vr.tx)
+    return adj
+
+
+def topo_sort(bus_names: List[str], adj: Dict[str, List[str]]) -> List[str]:
+    """Reverse DFS finishing order, DFS roots in bus order, children in
+    adjacency order; iterative.  Raises on a cycle like utils.py:163-164."""
+    n = len(bus_names)
+    order: List[str] = [None] * n
+    state = {b: 0 for b in bus_names}           # 0 new, 1 active, 2 finished
+    clock = n
+    for start in bus_names:
+        if state[start] != 0:
+            continue
+        state[start] = 1
+        stack = [(start, iter(adj.get(start, [])))]
+        while stack:
+            node, it = stack[-1]
+            advanced = False
+            for ch in it:
+                if state[ch] == 0:
+                    state[ch] = 1
+                    stack.append((ch, iter(adj.get(ch, []))))
+                    advanced = True
+                    break
+                if state[ch] == 1:
+                    raise ValueError('Not radial. Contains a cycle.')
+            if not advanced:
+                stack.pop()
+                state[node] = 2
+                clock -= 1
+                order[clock] = node
+    return order
+
+
+def reverse_adjacency(adj: Dict[str, List[str]]) -> Dict[str, List[str]]:
+    rev: Dict[str, List[str]] = {}
+    for node, nbrs in adj.items():
+        rev.setdefault(node, [])
+        for v in nbrs:
+            rev.setdefault(v, []).append(node)
+    return rev
+
+
+@dataclass
+class FbsTables:
+    """NumPy image of ``GpFbsDesc`` plus the row maps used to (un)pack results."""
+    n_steps: int
+    n_vrows: int
+    n_irows: int
+    n_srows: int
+    n_lines: int
+    bus_vrow: np.ndarray
+    par_vrow: np.ndarray
+    edge_irow: np.ndarray
+    load_srow: np.ndarray
+    kind: np.ndarray
+    child_begin: np.ndarray
+    child_count: np.ndarray
+    child_irow: np.ndarray
+    z: np.ndarray
+    cappu: np.ndarray
+    vr_gamma: np.ndarray
+    root_vrow: np.ndarray
+    root_load_srow: np.ndarray
+    root_cappu: np.ndarray
+    vref: np.ndarray
+    zip: np.ndarray
+    line_irow: np.ndarray
+    line_tx_vrow: np.ndarray
+    line_rx_vrow: np.ndarray
+    # host-side maps
+    vrow: np.ndarray = field(default=None)      # [nb,3]  V row or -1
+    irow: np.ndarray = field(default=None)      # [nl+ntf+nvr,3]  I row or -1 (VR rows: all -1)
+    srow: np.ndarray = field(default=None)      # [nb,3]  spu row or -1
+    topo_order: List[str] = field(default=None)
+    adj: Dict[str, List[str]] = field(default=None)
+    reverse_adj: Dict[str, List[str]] = field(default=None)
+    tolerance: float = 0.0
+    depth: int = 0
+
+
+def flatten_fbs(c: Circuit) -> FbsTables:
+    names = c.buses.all_names()
+    nb = len(names)
+    bidx = {n: i for i, n in enumerate(names)}
+    adj = fbs_adjacency(c)
+    order = topo_sort(names, adj)
+    rev = reverse_adjacency(adj)
+    root = order[0]
+    bus_pm = c.buses.get_phase_matrix('rows')
+    if bus_pm[bidx[root]].sum() != 3:
+        raise NotImplementedError('the root (source) bus must carry all three phases')
+
+    # packed rows
+    vrow = np.full((nb, 3), -1, dtype=np.int32)
+    k = 0
+    for b in range(nb):
+        for p in range(3):
+            if bus_pm[b, p]:
+                vrow[b, p] = k
+                k += 1
+    n_vrows = k
+    nl, ntf, nvr = c.lines.num_elements, c.transformers.num_elements, c.voltage_regulators.num_elements
+    edges = c.lines.get_elements() + c.transformers.get_elements()
+    irow = np.full((nl + ntf + nvr, 3), -1, dtype=np.int32)
+    k = 0
+    for i, e in enumerate(edges):
+        for p in range(3):
+            if e.phase_matrix[p]:
+                irow[i, p] = k
+                k += 1
+    n_irows = k
+    lmask = c.load_phase_mask()
+    srow = np.full((nb, 3), -1, dtype=np.int32)
+    k = 0
+    for b in range(nb):
+        for p in range(3):
+            if lmask[b, p] and bus_pm[b, p]:
+                srow[b, p] = k
+                k += 1
+    n_srows = k
+    cappu = c._by_bus(c.capacitors, 'cappu', float)
+
+    # edge lookup: real lines win over transformers win over regulators (line_group.py:26-38)
+    edge_of = {}
+    for vr in c.voltage_regulators.get_elements():
+        edge_of.setdefault(vr.key, ('vr', []))[1].append(vr)
+    for i, e in enumerate(c.transformers.get_elements()):
+        edge_of[e.key] = ('line', nl + i, e)
+    for i, e in enumerate(c.lines.get_elements()):
+        edge_of[e.key] = ('line', i, e)
+
+    n_steps = nb - 1
+    S3 = (n_steps, 3)
+    t = dict(bus_vrow=np.full(S3, -1, np.int32), par_vrow=np.full(S3, -1, np.int32),
+             edge_irow=np.full(S3, -1, np.int32), load_srow=np.full(S3, -1, np.int32),
+             kind=np.zeros(n_steps, np.int32), child_begin=np.zeros(n_steps, np.int32),
+             child_count=np.zeros(n_steps, np.int32), z=np.zeros((n_steps, 3, 3, 2)),
+             cappu=np.zeros(S3), vr_gamma=np.zeros(S3))
+    child_rows: List[np.ndarray] = []
+    depth_of = {root: 0}
+    for pos, name in enumerate(order[1:]):
+        parents = rev.get(name, [])
+        if len(parents) > 1:
+            raise ValueError(f"Network not radial. Bus {name} has parents {parents}")
+        if len(parents) == 0:
+            raise ValueError(f"Bus {name} is not connected to the root {root}")
+        parent = parents[0]
+        depth_of[name] = depth_of.get(parent, 0) + 1
+        b, pb = bidx[name], bidx[parent]
+        t['bus_vrow'][pos] = vrow[b]
+        t['par_vrow'][pos] = vrow[pb]
+        t['load_srow'][pos] = srow[b]
+        t['cappu'][pos] = cappu[b]
+        e = edge_of[(parent, name)]
+        if e[0] == 'vr':
+            t['kind'][pos] = EDGE_VR
+            for vr in e[1]:
+                for p in vr.get_ph_idx_matrix():
+                    t['vr_gamma'][pos, p] = vr.gamma
+        else:
+            t['kind'][pos] = EDGE_LINE
+            t['edge_irow'][pos] = irow[e[1]]
+            t['z'][pos, :, :, 0] = e[2].FZpu.real
+            t['z'][pos, :, :, 1] = e[2].FZpu.imag
+        t['child_begin'][pos] = len(child_rows)
+        for ch in adj.get(name, []):
+            ce = edge_of[(name, ch)]
+            if ce[0] == 'line':          # VR children contribute vr.Itx == 0 (solution_fbs.py:278-281)
+                child_rows.append(irow[ce[1]])
+        t['child_count'][pos] = len(child_rows) - t['child_begin'][pos]
+    child_irow = (np.array(child_rows, dtype=np.int32).reshape(-1, 3) if child_rows
+                  else np.zeros((0, 3), np.int32))
+
+    vref = np.array([1, np.exp(1j * 240 * np.pi / 180), np.exp(1j * 120 * np.pi / 180)], dtype=complex)
+    tol = abs((vref[1]) * 10 ** -6)                       # solution_fbs.py:37
+    rb = bidx[root]
+    line_irow = irow[:nl].copy()
+    tx = np.array([bidx[e.tx] for e in c.lines.get_elements()], dtype=int)
+    rx = np.array([bidx[e.rx] for e in c.lines.get_elements()], dtype=int)
+    return FbsTables(
+        n_steps=n_steps, n_vrows=n_vrows, n_irows=n_irows, n_srows=n_srows, n_lines=nl,
+        child_irow=child_irow, root_vrow=vrow[rb].copy(), root_load_srow=srow[rb].copy(),
+        root_cappu=cappu[rb].copy(), vref=np.stack([vref.real, vref.imag], axis=1).reshape(-1).copy(),
+        zip=np.array([c.loads.aPQ_p, c.loads.aI_p, c.loads.aZ_p], dtype=float),
+        line_irow=line_irow, line_tx_vrow=vrow[tx].reshape(-1, 3).copy() if nl else np.zeros((0, 3), np.int32),
+        line_rx_vrow=vrow[rx].reshape(-1, 3).copy() if nl else np.zeros((0, 3), np.int32),
+        vrow=vrow, irow=irow, srow=srow, topo_order=order, adj=adj, reverse_adj=rev,
+        tolerance=float(tol), depth=max(depth_of.values()) if depth_of else 0, **t)

@@ -1,0 +1,252 @@
+"""Drop-in ``SolutionFBS`` backed by the sm_100a batched Forward-Backward Sweep.
+
+Same constructor, ``solve()`` and accessors as the reference
+(``src/solution_fbs.py:27-136``); a single snapshot is a batch of one scenario
+on the GPU.  ``solve_batch`` is the additive, data-parallel entry point.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _cabi
+from .flatten import FbsTables, flatten_fbs
+from .solution import Solution
+
+
+@dataclass
+class BatchResult:
+    """Results of a batched solve in packed row layout (``[rows, S]``); the
+    ``unpack_*`` helpers give the reference's ``[S, n, 3]`` shapes."""
+    tables: object
+    S: int
+    iterations: np.ndarray
+    status: np.ndarray
+    convergence_diff: Optional[np.ndarray] = None
+    V_rows: Optional[object] = None
+    I_rows: Optional[object] = None
+    Vmag_rows: Optional[object] = None
+    loss: Optional[object] = None
+    sV_rows: Optional[object] = None
+    Stx_rows: Optional[object] = None
+    Srx_rows: Optional[object] = None
+
+    @property
+    def converged(self):
+        return np.asarray(self.status) == 0
+
+    @staticmethod
+    def _host(x):
+        return x.cpu().numpy() if hasattr(x, 'cpu') else np.asarray(x)
+
+    def _unpack(self, rows, rowmap, n):
+        rows = self._host(rows)[:, :self.S]
+        out = np.zeros((self.S, n, 3), dtype=rows.dtype)
+        b, p = np.nonzero(rowmap[:n] >= 0)
+        out[:, b, p] = rows[rowmap[b, p]].T
+        return out
+
+    @property
+    def V(self):
+        return self._unpack(self.V_rows, self.tables.vrow, self.tables.vrow.shape[0])
+
+    @property
+    def Vmag(self):
+        return self._unpack(self.Vmag_rows, self.tables.vrow, self.tables.vrow.shape[0])
+
+    @property
+    def sV(self):
+        return self._unpack(self.sV_rows, self.tables.vrow, self.tables.vrow.shape[0])
+
+    @property
+    def I(self):
+        return self._unpack(self.I_rows, self.tables.irow, self.tables.irow.shape[0])
+
+    @property
+    def Stx(self):
+        return self._unpack(self.Stx_rows, self.tables.irow, self.tables.n_lines)
+
+    @property
+    def Srx(self):
+        return self._unpack(self.Srx_rows, self.tables.irow, self.tables.n_lines)
+
+    @property
+    def losses(self):
+        return self._host(self.loss)[:self.S]
+
+
+class _Feeder:
+    """Owns the device handle of one flattened feeder."""
+
+    def __init__(self, desc, keep, create, device):
+        self.handle = C.c_void_p()
+        self._keep = keep
+        _cabi.check(create(C.byref(desc), int(device), C.byref(self.handle)))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _cabi.gp_feeder_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class SolutionFBS(Solution):
+
+    @classmethod
+    def set_zip_values(cls, zip_v):
+        Solution.set_zip_values(zip_v)
+
+    def __init__(self, dss_fp, **kwargs):
+        super().__init__(dss_fp, **kwargs)
+        self.tables: FbsTables = flatten_fbs(self.circuit)
+        self.adj, self.reverse_adj = self.tables.adj, self.tables.reverse_adj
+        self.topo_order = self.tables.topo_order
+        self.root = self.circuit.buses.get_element(self.topo_order[0])
+        self.Vref = np.array([1, np.exp(1j * 240 * np.pi / 180), np.exp(1j * 120 * np.pi / 180)],
+                             dtype=complex)
+        self.tolerance = abs((self.Vref[1]) * 10 ** -6)
+        self._feeder = None
+
+    # ---- device plumbing -----------------------------------------------------
+    def _dev(self):
+        torch = _cabi.require_cuda()
+        if self.device is None:
+            self.device = torch.cuda.current_device()
+        if self._feeder is None:
+            desc, keep = _cabi.make_fbs_desc(self.tables)
+            self._feeder = _Feeder(desc, keep, _cabi.gp_fbs_create, self.device)
+        return torch, torch.device('cuda', self.device)
+
+    def pack_spu(self, spu) -> np.ndarray:
+        """``[S, nb, 3]`` complex (the reference's ``Solution.spu`` per scenario)
+        -> packed ``[n_srows, S]``."""
+        spu = np.asarray(spu, dtype=complex)
+        if spu.ndim == 2:
+            spu = spu[None]
+        b, p = np.nonzero(self.tables.srow >= 0)
+        rows = np.empty((self.tables.n_srows, spu.shape[0]), dtype=complex)
+        rows[self.tables.srow[b, p]] = spu[:, b, p].T
+        return rows
+
+    def load_weights(self) -> np.ndarray:
+        """``[n_srows, n_loads]`` complex W with ``spu_rows = W @ mult.T`` for
+        per-load multipliers (load.py:16-24 split per phase, summed per bus)."""
+        t, c = self.tables, self.circuit
+        W = np.zeros((t.n_srows, c.loads.num_elements), dtype=complex)
+        for j, e in enumerate(c.loads.get_elements()):
+            b = c.buses.get_idx(e.related_bus)
+            for p in e.get_ph_idx_matrix():
+                W[t.srow[b, p], j] += e.spu[p]
+        return W
+
+    # ---- batched solve -------------------------------------------------------
+    def solve_batch(self, spu=None, load_mult=None, spu_rows=None, outputs=('V', 'Vmag', 'loss'),
+                    maxiter=None, tol=None, return_device=False, stream=None) -> BatchResult:
+        """Solve S scenarios from flat start.
+
+        Give ONE of: ``spu`` ``[S, nb, 3]`` complex; ``load_mult`` ``[S, n_loads]``
+        multipliers on every load's kW and kvar; ``spu_rows`` packed
+        ``[n_srows, S]`` complex128 (NumPy, or a CUDA torch tensor for inputs
+        already resident in HBM).  ``outputs`` selects what is produced besides
+        iterations/status: any of V, I, Vmag, loss, sV, Stx, Srx.
+        """
+        torch, dev = self._dev()
+        t = self.tables
+        maxiter = self.maxiter if maxiter is None else int(maxiter)
+        tol = self.tolerance if tol is None else float(tol)
+        if spu_rows is None:
+            if load_mult is not None:
+                spu_rows = self.load_weights() @ np.asarray(load_mult, dtype=float).T
+            elif spu is not None:
+                spu_rows = self.pack_spu(spu)
+            else:
+                spu_rows = self.pack_spu(self.spu)
+        if isinstance(spu_rows, np.ndarray):
+            d_spu = torch.from_numpy(np.ascontiguousarray(spu_rows, dtype=np.complex128)).to(dev)
+        else:
+            d_spu = spu_rows.to(device=dev, dtype=torch.complex128).contiguous()
+        if d_spu.dim() != 2 or d_spu.shape[0] != t.n_srows:
+            raise ValueError(f"spu_rows must be [{t.n_srows}, S], got {tuple(d_spu.shape)}")
+        S = ld = int(d_spu.shape[1])
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream() if stream is None else stream
+            with torch.cuda.stream(st):
+                V = torch.empty((t.n_vrows, ld), dtype=torch.complex128, device=dev)
+                I = torch.empty((max(t.n_irows, 1), ld), dtype=torch.complex128, device=dev)
+                iters = torch.empty(S, dtype=torch.int32, device=dev)
+                status = torch.empty(S, dtype=torch.int32, device=dev)
+                diff = torch.empty(S, dtype=torch.float64, device=dev)
+                _cabi.check(_cabi.gp_fbs_solve_batch(
+                    self._feeder.handle, S, ld, d_spu.data_ptr(), V.data_ptr(), I.data_ptr(),
+                    iters.data_ptr(), status.data_ptr(), diff.data_ptr(), tol, maxiter, st.cuda_stream))
+                want = set(outputs)
+                mk = lambda rows, dt: torch.empty((max(rows, 1), ld), dtype=dt, device=dev)
+                sV = mk(t.n_vrows, torch.complex128) if 'sV' in want else None
+                Vmag = mk(t.n_vrows, torch.float64) if 'Vmag' in want else None
+                Stx = torch.zeros((max(t.n_irows, 1), ld), dtype=torch.complex128, device=dev) if 'Stx' in want else None
+                Srx = torch.zeros((max(t.n_irows, 1), ld), dtype=torch.complex128, device=dev) if 'Srx' in want else None
+                loss = torch.empty(S, dtype=torch.complex128, device=dev) if 'loss' in want else None
+                if want & {'sV', 'Vmag', 'Stx', 'Srx', 'loss'}:
+                    p = lambda x: x.data_ptr() if x is not None else None
+                    _cabi.check(_cabi.gp_fbs_post(
+                        self._feeder.handle, S, ld, d_spu.data_ptr(), V.data_ptr(), I.data_ptr(),
+                        p(sV), p(Vmag), p(Stx), p(Srx), p(loss), st.cuda_stream))
+        res = BatchResult(tables=t, S=S, iterations=iters, status=status, convergence_diff=diff,
+                          V_rows=V if 'V' in want else None, I_rows=I if 'I' in want else None,
+                          Vmag_rows=Vmag, loss=loss, sV_rows=sV, Stx_rows=Stx, Srx_rows=Srx)
+        if not return_device:
+            st.synchronize()
+            for k in ('iterations', 'status', 'convergence_diff', 'V_rows', 'I_rows', 'Vmag_rows', 'loss',
+                      'sV_rows', 'Stx_rows', 'Srx_rows'):
+                v = getattr(res, k)
+                if v is not None:
+                    setattr(res, k, v.cpu().numpy())
+        return res
+
+    def solve_batch_host(self, spu_rows, V_out=None, I_out=None, Vmag_out=None, loss_out=None,
+                         maxiter=None, tol=None):
+        """Host-buffer path through ``gp_fbs_solve_batch_host``: ``spu_rows`` is a
+        (preferably pinned) CPU torch tensor / NumPy array ``[n_srows, S]``
+        complex128; outputs are written into the given host arrays.  Returns
+        (iterations, status, convergence_diff) as NumPy arrays."""
+        torch, dev = self._dev()
+        t = self.tables
+        maxiter = self.maxiter if maxiter is None else int(maxiter)
+        tol = self.tolerance if tol is None else float(tol)
+
+        def ptr(x):
+            if x is None:
+                return None
+            return x.data_ptr() if hasattr(x, 'data_ptr') else x.ctypes.data
+
+        S = ld = int(spu_rows.shape[1])
+        iters = np.empty(S, dtype=np.int32)
+        status = np.empty(S, dtype=np.int32)
+        diff = np.empty(S, dtype=np.float64)
+        _cabi.check(_cabi.gp_fbs_solve_batch_host(
+            self._feeder.handle, S, ld, ptr(spu_rows), ptr(V_out), ptr(I_out), ptr(Vmag_out), ptr(loss_out),
+            iters.ctypes.data, status.ctypes.data, diff.ctypes.data, tol, maxiter))
+        return iters, status, diff
+
+    # ---- single snapshot (solution_fbs.py:76-136) -------------------------------
+    def solve(self):
+        t = self.tables
+        if not (self.iterations > 0 and (self.converged or self.iterations >= self.maxiter)):
+            r = self.solve_batch(spu=self.spu, outputs=('V', 'I', 'Vmag', 'sV', 'Stx', 'Srx'))
+            self._last = r
+            self.iterations = int(r.iterations[0])
+            self.convergence_diff = float(r.convergence_diff[0])
+            self.converged = bool(r.status[0] == 0)
+        r = self._last
+        self.V = r.V[0]
+        self.I = r.I[0]
+        self.sV = r.sV[0]
+        self.Vmag = r.Vmag[0]
+        self.Stx = r.Stx[0]
+        self.Srx = r.Srx[0]
+        self.Vtest = self.V[self.circuit.buses.get_idx(self.root)]

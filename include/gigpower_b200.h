@@ -1,0 +1,160 @@
+/*
+ * gigpower_b200 -- C ABI of the B200-native batched power-flow engine.
+ *
+ * The reference (michael-sankur/gigpower) is pure Python and has no FFI of its
+ * own on this path; the interface each entry point replaces is the Python
+ * method cited beside it (paths relative to gigpower/src/gigpower/).  The
+ * Python drop-in classes in gigpower_b200/ bind this header with ctypes; see
+ * INTEGRATION.md for the stub a gigpower maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative GP_E* code on failure;
+ *     gp_last_error() gives the message of the calling thread's last failure;
+ *   - no exceptions cross the ABI, no allocation of caller-visible buffers
+ *     inside: the caller owns every data buffer;
+ *   - "dev" pointers are CUDA device pointers on the feeder's device, "host"
+ *     pointers are ordinary (preferably pinned) host memory;
+ *   - complex values are interleaved (re, im) doubles; batched arrays are
+ *     ROW-major [row][ld] with the scenario index innermost (ld >= S is the
+ *     row pitch in scenarios), so that a warp reads 32 consecutive scenarios
+ *     of one row with 128-bit loads;
+ *   - a handle is not thread-safe; different handles are independent;
+ *   - per-scenario failure is reported in status[] (GP_ST_*), never as a call
+ *     failure.
+ */
+#ifndef GIGPOWER_B200_H
+#define GIGPOWER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GP_OK 0
+#define GP_EINVAL (-1)   /* bad argument / inconsistent descriptor */
+#define GP_ECUDA (-2)    /* CUDA runtime error (message has the detail) */
+#define GP_ENOMEM (-3)   /* host or device allocation failed */
+
+#define GP_ST_CONVERGED 0
+#define GP_ST_MAXITER 1
+#define GP_ST_NONFINITE 2
+
+/* edge kinds of an FBS step (solution_fbs.py:162-184 / :138-160) */
+#define GP_EDGE_LINE 0   /* Line or Transformer (SyntheticLine with Z = 0, line.py:79-97) */
+#define GP_EDGE_VR 1     /* one or more VoltageRegulators between the same two buses */
+
+typedef struct GpFeeder GpFeeder;
+
+/*
+ * Flattened feeder for Forward-Backward Sweep.
+ *
+ * Replaces the object graph SolutionFBS walks: topo_order / adj / reverse_adj
+ * (solution_fbs.py:29-33, 39-74; utils.py:130-181), Line.FZpu (line.py:38-46),
+ * the phase matrices (circuit_element.py:47-51) and the cached load parameters
+ * (solution.py:99-106).  Rows are PACKED: one V row per existing (bus, phase),
+ * one I row per existing (line|transformer, phase), one spu row per (bus,
+ * phase) that carries a load.
+ *
+ * Step k (0 <= k < n_steps) is the non-root bus at position k+1 of topo_order
+ * together with the edge from its parent.  The forward sweep runs the steps
+ * in order, the backward sweep in reverse order.
+ */
+typedef struct {
+    int32_t n_steps;           /* nb - 1                                              */
+    int32_t n_vrows;           /* P_b: rows of V                                      */
+    int32_t n_irows;           /* P_l: rows of I                                      */
+    int32_t n_srows;           /* P_L: rows of spu                                    */
+    int32_t n_child;           /* entries of child_irow / 3                           */
+    int32_t n_lines;           /* real lines (for Stx/Srx/loss, solution.py:222-230)  */
+    /* per step, [n_steps][3]: row index or -1 when the phase does not exist */
+    const int32_t* bus_vrow;   /* V rows of the step's bus                            */
+    const int32_t* par_vrow;   /* V rows of its parent                                */
+    const int32_t* edge_irow;  /* I rows of the incoming edge (all -1 for GP_EDGE_VR) */
+    const int32_t* load_srow;  /* spu rows of the bus                                 */
+    const int32_t* kind;       /* [n_steps] GP_EDGE_*                                 */
+    const int32_t* child_begin;/* [n_steps] first child edge of the bus in child_irow */
+    const int32_t* child_count;/* [n_steps] number of non-VR child edges              */
+    const int32_t* child_irow; /* [n_child][3] I rows of those child edges, adj order */
+    const double* z;           /* [n_steps][3][3][2] FZpu of the incoming edge        */
+    const double* cappu;       /* [n_steps][3] capacitor pu of the bus                */
+    const double* vr_gamma;    /* [n_steps][3] gamma per regulated phase, 0 elsewhere */
+    /* root bus (topo_order[0]) */
+    int32_t root_vrow[3];
+    int32_t root_load_srow[3];
+    double root_cappu[3];
+    double vref[6];            /* solution_fbs.py:34-35, interleaved                  */
+    double zip[3];             /* aPQ_p, aI_p, aZ_p (solution.py:44-45)               */
+    /* real lines, [n_lines][3] each, -1 where the phase does not exist */
+    const int32_t* line_irow;
+    const int32_t* line_tx_vrow;
+    const int32_t* line_rx_vrow;
+} GpFbsDesc;
+
+/* Library version, e.g. 100 = 0.1.0 */
+int gp_version(void);
+
+/* Copy the calling thread's last error message into buf (NUL-terminated). */
+int gp_last_error(char* buf, size_t len);
+
+/* Number of kernels this library has launched in this process (bench evidence). */
+int64_t gp_launch_count(void);
+
+/*
+ * Build the device-resident feeder tables.  Replaces SolutionFBS.__init__'s
+ * topology setup (solution_fbs.py:27-37).  `device` is a CUDA ordinal.
+ */
+int gp_fbs_create(const GpFbsDesc* desc, int device, GpFeeder** out);
+int gp_feeder_destroy(GpFeeder* f);
+
+/*
+ * Solve S scenarios from flat start with Forward-Backward Sweep; replaces
+ * SolutionFBS.solve() (solution_fbs.py:76-128) for every scenario at once.
+ * Each scenario stops at the iteration at which a separate reference object
+ * would (root-voltage mismatch <= tol, or maxiter).
+ *
+ *   spu_dev   [n_srows][ld] complex   per-scenario bus loads in pu (Solution.spu)
+ *   V_dev     [n_vrows][ld] complex   out: bus voltages
+ *   I_dev     [n_irows][ld] complex   out: line / transformer currents
+ *   iters_dev [S] int32               out: iterations
+ *   status_dev[S] int32               out: GP_ST_*
+ *   diff_dev  [S] double              out: convergence_diff (solution_fbs.py:126)
+ *
+ * Asynchronous on `stream` (a cudaStream_t, NULL = default stream).
+ */
+int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const double* spu_dev,
+                       double* V_dev, double* I_dev, int32_t* iters_dev,
+                       int32_t* status_dev, double* diff_dev, double tol,
+                       int32_t maxiter, void* stream);
+
+/*
+ * Derived results of solved scenarios; replaces the tail of SolutionFBS.solve()
+ * (solution_fbs.py:130-135; solution.py:177-233).  Any output pointer may be NULL.
+ *
+ *   sV_dev   [n_vrows][ld] complex    calc_sV
+ *   Vmag_dev [n_vrows][ld] double     calc_Vmag
+ *   Stx_dev  [n_irows][ld] complex    calc_Stx  (rows of real lines only)
+ *   Srx_dev  [n_irows][ld] complex    calc_Srx
+ *   loss_dev [S] complex              sum over real lines and phases of Stx - Srx
+ */
+int gp_fbs_post(GpFeeder* f, int64_t S, int64_t ld, const double* spu_dev,
+                const double* V_dev, const double* I_dev, double* sV_dev,
+                double* Vmag_dev, double* Stx_dev, double* Srx_dev,
+                double* loss_dev, void* stream);
+
+/*
+ * Host-buffer entry point (what a gigpower caller without device code binds):
+ * copies spu to the device in chunks, solves, and copies the requested results
+ * back, overlapping copies and kernels on internal streams.  Host arrays use
+ * the same [row][ld] layout; any of V/I/Vmag/loss may be NULL.  Synchronous.
+ */
+int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const double* spu_host,
+                            double* V_host, double* I_host, double* Vmag_host,
+                            double* loss_host, int32_t* iters_host, int32_t* status_host,
+                            double* diff_host, double tol, int32_t maxiter);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIGPOWER_B200_H */

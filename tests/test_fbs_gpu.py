@@ -1,0 +1,165 @@
+"""GPU parity tests of the batched FBS path (through the C-ABI) against the
+oracle and the golden vectors.  Bar (BASELINE.json north_star): complex bus
+voltages within 1e-9 relative, identical iteration counts."""
+import numpy as np
+import pytest
+
+from helpers import (ZIPS, ALL_FEEDERS, LINES_ONLY, feeder_path, load_model, snapshots, scenarios, rel_err)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _fbs(feeder, zname='test_zip', **kw):
+    from gigpower_b200.solution_fbs import SolutionFBS
+    return SolutionFBS(feeder_path(feeder), zip_v=np.asarray(ZIPS[zname]), **kw)
+
+
+def _oracle(feeder, zname='test_zip'):
+    from oracle.gp_oracle import FBSOracle
+    return FBSOracle(load_model(feeder), ZIPS[zname])
+
+
+@pytest.mark.parametrize('zname', list(ZIPS))
+@pytest.mark.parametrize('feeder', ALL_FEEDERS)
+def test_snapshot_matches_reference(feeder, zname):
+    snap = snapshots()
+    s = _fbs(feeder, zname)
+    s.solve()
+    k = f'{feeder}/{zname}/FBS/'
+    assert s.iterations == int(snap[k + 'iterations'])
+    assert s.converged == bool(snap[k + 'converged'])
+    assert abs(s.convergence_diff - float(snap[k + 'convergence_diff'])) <= 1e-12
+    for p in ('V', 'I', 'sV', 'Vmag', 'Stx', 'Srx'):
+        assert getattr(s, p).shape == snap[k + p].shape, p
+        assert rel_err(getattr(s, p), snap[k + p]) <= TOL, p
+    # accessors: reference shapes (tests/test_api.py:47-71)
+    for p in s.SOLUTION_PARAMS:
+        rows, cols = s.get_data_frame(p, orient='rows'), s.get_data_frame(p, orient='cols')
+        assert not rows.empty and rows.shape[1] == 3 and cols.shape[0] == 3
+        assert rows.shape == cols.shape[::-1]
+    assert list(s.get_V().index) == s.circuit.buses.all_names()
+    assert s.get_I().shape[0] == s.circuit.lines.num_elements
+    # a second solve() is a no-op, as in the reference (iterations / Vtest persist)
+    V1 = s.V.copy()
+    s.solve()
+    assert np.array_equal(V1, s.V) and s.iterations == int(snap[k + 'iterations'])
+
+
+@pytest.mark.parametrize('feeder', LINES_ONLY)
+def test_golden_scenarios(feeder):
+    sc = scenarios()
+    s = _fbs(feeder)
+    r = s.solve_batch(load_mult=sc[feeder + '/mult'], outputs=('V', 'I'))
+    assert list(r.iterations) == list(sc[feeder + '/FBS/iterations'])
+    assert rel_err(r.V, sc[feeder + '/FBS/V']) <= TOL
+    assert rel_err(r.I, sc[feeder + '/FBS/I']) <= TOL
+
+
+@pytest.mark.parametrize('feeder,S,seed', [('IEEE_13_Bus_allwye_noxfm_noreg', 4096, 1),
+                                            ('IEEE_34_Bus_allwye_noxfm_noreg', 1000, 2),
+                                            ('IEEE_37_Bus_allwye_noxfm_noreg', 1027, 3),
+                                            ('IEEE_13_Bus_allwye', 300, 4),
+                                            ('IEEE_37_Bus_allwye', 129, 5)])
+def test_random_batch_matches_oracle(feeder, S, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    o = _oracle(feeder)
+    mult = rng.uniform(0.5, 1.5, size=(S, len(o.c.load_names)))
+    spu = o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult)
+    want = o.solve(spu)
+    s = _fbs(feeder)
+    r = s.solve_batch(load_mult=mult, outputs=('V', 'I', 'Vmag', 'sV', 'Stx', 'Srx', 'loss'))
+    assert np.array_equal(r.iterations, want['iterations'])
+    assert np.array_equal(r.converged, want['converged'])
+    for p in ('V', 'I', 'Vmag', 'sV', 'Stx', 'Srx'):
+        assert rel_err(getattr(r, p), want[p] if p != 'I' else want['I']) <= TOL, p
+    loss = (want['Stx'] - want['Srx']).sum(axis=(1, 2))
+    assert rel_err(r.losses, loss) <= TOL
+    assert np.abs(r.convergence_diff - want['convergence_diff']).max() <= 1e-12
+    # the same scenarios given as the reference's per-bus spu matrix
+    r2 = s.solve_batch(spu=spu, outputs=('V',))
+    assert np.array_equal(r2.V, r.V)
+
+
+def test_full_size_config_c2_matches_oracle():
+    """BASELINE config C2: 13-bus, 65,536 scenarios, m ~ U(0.5, 1.5), seed 13."""
+    feeder, S = 'IEEE_13_Bus_allwye_noxfm_noreg', 65536
+    rng = np.random.Generator(np.random.PCG64(13))
+    o = _oracle(feeder)
+    mult = rng.uniform(0.5, 1.5, size=(S, len(o.c.load_names)))
+    want = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+    r = _fbs(feeder).solve_batch(load_mult=mult, outputs=('V', 'Vmag', 'loss'))
+    assert np.array_equal(r.iterations, want['iterations'])
+    assert r.converged.all()
+    assert rel_err(r.V, want['V']) <= TOL
+    assert rel_err(r.Vmag, want['Vmag']) <= TOL
+    # size-independent property: losses are non-negative real power, and KCL at the root:
+    assert (r.losses.real > 0).all()
+
+
+def test_edge_cases_empty_ragged_single():
+    feeder = LINES_ONLY[0]
+    s = _fbs(feeder)
+    o = _oracle(feeder)
+    nload = len(o.c.load_names)
+    r0 = s.solve_batch(load_mult=np.zeros((0, nload)))
+    assert r0.S == 0 and r0.V.shape[0] == 0
+    for S in (1, 2, 127, 130):
+        mult = np.linspace(0.5, 1.5, S * nload).reshape(S, nload)
+        want = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+        r = s.solve_batch(load_mult=mult)
+        assert np.array_equal(r.iterations, want['iterations'])
+        assert rel_err(r.V, want['V']) <= TOL
+    # zero load: converges in 2 sweeps to the flat voltage profile
+    r = s.solve_batch(load_mult=np.zeros((3, nload)))
+    want = o.solve(o.c.spu_matrix(o.c.load_kw * 0, o.c.load_kvar * 0)[None].repeat(3, 0))
+    assert np.array_equal(r.iterations, want['iterations'])
+    assert rel_err(r.V, want['V']) <= TOL
+
+
+def test_non_convergent_scenario_reports_status_not_error():
+    """34-bus at 2.0x load does not converge in the reference:
+    flagged per scenario, neighbours unaffected."""
+    feeder = 'IEEE_34_Bus_allwye_noxfm_noreg'
+    o = _oracle(feeder)
+    nload = len(o.c.load_names)
+    mult = np.ones((4, nload))
+    mult[1] = 2.0
+    mult[2] = 1.5      # 59 iterations in the reference
+    want = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+    r = _fbs(feeder).solve_batch(load_mult=mult)
+    assert np.array_equal(r.iterations, want['iterations'])
+    assert r.iterations[1] == 100 and r.status[1] in (1, 2) and not r.converged[1]
+    assert r.converged[[0, 2, 3]].all()
+    assert rel_err(r.V[[0, 2, 3]], want['V'][[0, 2, 3]]) <= TOL
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    import torch
+    feeder, S = LINES_ONLY[0], 20000
+    s = _fbs(feeder)
+    rng = np.random.Generator(np.random.PCG64(7))
+    rows = s.load_weights() @ rng.uniform(0.5, 1.5, size=(S, s.circuit.loads.num_elements)).T
+    r = s.solve_batch(spu_rows=rows, outputs=('V', 'I', 'Vmag', 'loss'))
+    spu_h = torch.from_numpy(np.ascontiguousarray(rows)).pin_memory()
+    t = s.tables
+    V = torch.empty((t.n_vrows, S), dtype=torch.complex128).pin_memory()
+    I = torch.empty((t.n_irows, S), dtype=torch.complex128).pin_memory()
+    Vmag = torch.empty((t.n_vrows, S), dtype=torch.float64).pin_memory()
+    loss = torch.empty(S, dtype=torch.complex128).pin_memory()
+    iters, status, diff = s.solve_batch_host(spu_h, V, I, Vmag, loss)
+    assert np.array_equal(iters, r.iterations) and np.array_equal(status, r.status)
+    assert np.array_equal(V.numpy(), r.V_rows) and np.array_equal(I.numpy(), r.I_rows)
+    assert np.array_equal(Vmag.numpy(), r.Vmag_rows) and np.array_equal(loss.numpy(), r.loss)
+
+
+def test_errors_are_python_exceptions():
+    from gigpower_b200._cabi import GpError
+    s = _fbs(LINES_ONLY[0])
+    with pytest.raises(ValueError):
+        s.solve_batch(spu_rows=np.zeros((3, 4), dtype=complex))
+    s._dev()
+    from gigpower_b200 import _cabi
+    with pytest.raises(GpError):
+        _cabi.check(_cabi.gp_fbs_solve_batch(s._feeder.handle, 4, 2, None, None, None, None, None, None,
+                                             1e-6, 100, None))

@@ -1,0 +1,85 @@
+"""CPU tests of the host side: reader, circuit mirror, flattener, C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gigpower_b200.circuit import Circuit
+from gigpower_b200.flatten import flatten_fbs, topo_sort
+from oracle.gp_oracle import OracleCircuit, FBSOracle
+from helpers import ALL_FEEDERS, LINES_ONLY, ZIPS, REPO, load_model, snapshots
+
+
+@pytest.mark.parametrize('feeder', ALL_FEEDERS)
+def test_circuit_matches_oracle_extraction(feeder):
+    model = load_model(feeder)
+    Circuit._set_zip_values(ZIPS['test_zip'])
+    c, o = Circuit(model), OracleCircuit(model, ZIPS['test_zip'])
+    assert c.buses.all_names() == o.bus_names
+    assert np.array_equal(c.buses.get_phase_matrix('rows'), o.bus_pm)
+    assert np.array_equal(np.array([e.FZpu for e in c.lines.get_elements()]), o.FZpu)
+    assert np.array_equal(np.array([e.rmat for e in c.lines.get_elements()]), o.rmat)
+    assert np.array_equal(c.get_spu_matrix(), o.spu_matrix())
+    assert np.array_equal(c.get_cappu_matrix(), o.cappu)
+    assert np.array_equal(c.get_aPQ_matrix(), o.aPQ)
+    assert np.array_equal(c.get_tx_idx_matrix()[:o.nl], o.line_tx)
+    assert c.get_total_lines() == o.nl + o.ntf + o.nvr
+
+
+@pytest.mark.parametrize('feeder', ALL_FEEDERS)
+def test_topo_order_matches_reference(feeder):
+    model = load_model(feeder)
+    t = flatten_fbs(Circuit(model))
+    want = snapshots()[f'{feeder}/test_zip/FBS/topo_order']
+    assert [model.bus_names.index(n) for n in t.topo_order] == list(want)
+    assert abs(t.tolerance - 1e-6) < 1e-20
+
+
+def test_packed_row_counts_match_survey_table():
+    # P_b, P_l, P_L of the three lines-only feeders
+    want = {'IEEE_13_Bus_allwye_noxfm_noreg': (38, 35, 19), 'IEEE_34_Bus_allwye_noxfm_noreg': (89, 86, 54),
+            'IEEE_37_Bus_allwye_noxfm_noreg': (117, 114, 55)}
+    for f, (pb, pl, pL) in want.items():
+        t = flatten_fbs(Circuit(load_model(f)))
+        assert (t.n_vrows, t.n_irows, t.n_srows) == (pb, pl, pL)
+        assert t.n_steps == len(t.topo_order) - 1
+        assert t.child_count.sum() == t.child_irow.shape[0]
+
+
+def test_topo_sort_cycle_raises():
+    with pytest.raises(ValueError, match='Not radial'):
+        topo_sort(['a', 'b', 'c'], {'a': ['b'], 'b': ['c'], 'c': ['a']})
+
+
+def test_set_kw_changes_spu_like_reference():
+    c = Circuit(load_model(LINES_ONLY[0]))
+    before = c.get_spu_matrix().copy()
+    c.set_kW('671', 2 * 1155)
+    after = c.get_spu_matrix()
+    b = c.buses.get_idx('671')
+    assert np.allclose(after[b].real, 2 * before[b].real) and np.allclose(after[b].imag, before[b].imag)
+    with pytest.raises(KeyError):
+        c.loads.get_element(3.5)
+
+
+def test_cabi_exports_every_declared_symbol():
+    hdr = open(os.path.join(REPO, 'include', 'gigpower_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = sorted(set(re.findall(r'\b(gp_[a-z0-9_]+)\s*\(', hdr)))
+    assert declared, 'no declarations found'
+    lib = ctypes.CDLL(os.path.join(REPO, 'gigpower_b200', 'libgigpower_b200.so'))
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in the header but not exported'
+    lib.gp_version.restype = ctypes.c_int
+    assert lib.gp_version() >= 100
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(REPO, 'gigpower_b200')
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                txt = open(os.path.join(root, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', txt, flags=re.M), f
