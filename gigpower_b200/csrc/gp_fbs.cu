@@ -58,8 +58,9 @@ struct FbsImpl {
     double* d_vrow_cap = nullptr; // [n_vrows]
     FbsConst k;
     // host staging for gp_fbs_solve_batch_host
-    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
-    void* d_stage[3] = {nullptr, nullptr, nullptr};
+    static constexpr int NSTREAM = 4;
+    cudaStream_t streams[NSTREAM] = {nullptr, nullptr, nullptr, nullptr};
+    void* d_stage[NSTREAM] = {nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes = 0;
 };
 
@@ -428,7 +429,7 @@ extern "C" int gp_feeder_destroy(GpFeeder* f) {
         cudaFree(im->d_lines);
         cudaFree(im->d_vrow_srow);
         cudaFree(im->d_vrow_cap);
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < FbsImpl::NSTREAM; ++i) {
             if (im->d_stage[i]) cudaFree(im->d_stage[i]);
             if (im->streams[i]) cudaStreamDestroy(im->streams[i]);
         }
@@ -494,7 +495,7 @@ extern "C" int gp_fbs_post(GpFeeder* f, int64_t S, int64_t ld, const double* spu
     return GP_OK;
 }
 
-// Host-buffer path: chunk the batch, triple-buffer H2D / solve / D2H on three streams.
+// Host-buffer path: chunk the batch, pipeline H2D / solve / D2H over NSTREAM streams.
 extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const double* spu_h,
                                        double* V_h, double* I_h, double* Vmag_h, double* loss_h,
                                        int32_t* iters_h, int32_t* status_h, double* diff_h,
@@ -505,18 +506,21 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
     FbsImpl* im = (FbsImpl*)f->impl;
     if (!spu_h && im->n_srows > 0) return fail(GP_EINVAL, "gp_fbs_solve_batch_host: null spu");
     GP_CUDA(cudaSetDevice(f->device));
-    // chunk of scenarios per stream: a power of two >= 1024, <= ~16 MB of rows per chunk
+    // The solve kernel is latency-bound for a single wave, so a chunk should be as
+    // large as possible while still giving every stream work to overlap with the
+    // other streams' copies: S/NSTREAM scenarios, at most ~64 MB of rows.
     const int64_t rows = (int64_t)im->n_vrows + im->n_irows + im->n_srows;
-    int64_t C = (int64_t)1 << 15;
-    while (C > 1024 && C * rows * 16 > ((int64_t)16 << 20)) C >>= 1;
-    if (C > S) C = (S + 127) / 128 * 128;
+    int64_t C = ((S + FbsImpl::NSTREAM - 1) / FbsImpl::NSTREAM + 127) / 128 * 128;
+    const int64_t cap = (((int64_t)64 << 20) / (rows * 16)) / 128 * 128;
+    if (C > cap) C = cap;
+    if (C < 1024) C = 1024;
     // per-chunk device layout: spu | V | I | Vmag | loss | diff | iters | status
     const size_t b_spu = (size_t)im->n_srows * C * 16, b_V = (size_t)im->n_vrows * C * 16,
                  b_I = (size_t)im->n_irows * C * 16, b_mag = (size_t)im->n_vrows * C * 8,
                  b_loss = (size_t)C * 16, b_diff = (size_t)C * 8, b_i32 = (size_t)C * 4;
     const size_t need = b_spu + b_V + b_I + b_mag + b_loss + b_diff + 2 * b_i32 + 1024;
     if (need > im->stage_bytes) {
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < FbsImpl::NSTREAM; ++i) {
             if (im->d_stage[i]) cudaFree(im->d_stage[i]);
             im->d_stage[i] = nullptr;
             GP_CUDA(cudaMalloc(&im->d_stage[i], need));
@@ -525,7 +529,7 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
         im->stage_bytes = need;
     }
     int slot = 0;
-    for (int64_t s0 = 0; s0 < S; s0 += C, slot = (slot + 1) % 3) {
+    for (int64_t s0 = 0; s0 < S; s0 += C, slot = (slot + 1) % FbsImpl::NSTREAM) {
         const int64_t n = (S - s0 < C) ? (S - s0) : C;
         cudaStream_t st = im->streams[slot];
         char* base = (char*)im->d_stage[slot];
@@ -561,7 +565,7 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
         if (iters_h) GP_CUDA(cudaMemcpyAsync(iters_h + s0, d_it, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         if (status_h) GP_CUDA(cudaMemcpyAsync(status_h + s0, d_st, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     }
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < FbsImpl::NSTREAM; ++i)
         if (im->streams[i]) GP_CUDA(cudaStreamSynchronize(im->streams[i]));
     return GP_OK;
 }

@@ -78,7 +78,7 @@ def test_random_batch_matches_oracle(feeder, S, seed):
     assert np.abs(r.convergence_diff - want['convergence_diff']).max() <= 1e-12
     # the same scenarios given as the reference's per-bus spu matrix
     r2 = s.solve_batch(spu=spu, outputs=('V',))
-    assert np.array_equal(r2.V, r.V)
+    assert np.array_equal(r2.iterations, r.iterations) and rel_err(r2.V, r.V) <= 1e-13
 
 
 def test_full_size_config_c2_matches_oracle():
