@@ -43,6 +43,20 @@ class GpFbsDesc(C.Structure):
     ]
 
 
+class GpNr3Desc(C.Structure):
+    _fields_ = [
+        ('n_steps', C.c_int32), ('n_vrows', C.c_int32), ('n_irows', C.c_int32),
+        ('n_srows', C.c_int32), ('n_child', C.c_int32), ('n_lines', C.c_int32),
+        ('bus_vrow', i32p), ('par_vrow', i32p), ('edge_irow', i32p), ('load_srow', i32p),
+        ('child_begin', i32p), ('child_count', i32p), ('child_step', i32p), ('child_irow', i32p),
+        ('z', f64p), ('cappu', f64p),
+        ('root_vrow', C.c_int32 * 3), ('root_load_srow', C.c_int32 * 3),
+        ('root_cappu', C.c_double * 3), ('vslack', C.c_double * 6), ('zip', C.c_double * 3),
+        ('cA', C.c_double * 3), ('cB', C.c_double * 3), ('f0_absent', C.c_double),
+        ('line_irow', i32p), ('line_tx_vrow', i32p), ('line_rx_vrow', i32p),
+    ]
+
+
 def _sig(name, restype, argtypes):
     fn = getattr(lib, name)
     fn.restype = restype
@@ -63,8 +77,16 @@ gp_fbs_solve_batch_host = _sig('gp_fbs_solve_batch_host', C.c_int,
                                [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp,
                                 C.c_double, C.c_int32])
 
+gp_nr3_create = _sig('gp_nr3_create', C.c_int, [C.POINTER(GpNr3Desc), C.c_int, C.POINTER(vp)])
+gp_nr3_workspace_bytes = _sig('gp_nr3_workspace_bytes', C.c_int64, [vp, C.c_int64])
+gp_nr3_solve_batch = _sig('gp_nr3_solve_batch', C.c_int,
+                          [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32, vp])
+gp_nr3_map_output = _sig('gp_nr3_map_output', C.c_int,
+                         [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
+
 EXPORTS = ['gp_version', 'gp_last_error', 'gp_launch_count', 'gp_fbs_create', 'gp_feeder_destroy',
-           'gp_fbs_solve_batch', 'gp_fbs_post', 'gp_fbs_solve_batch_host']
+           'gp_fbs_solve_batch', 'gp_fbs_post', 'gp_fbs_solve_batch_host', 'gp_nr3_create',
+           'gp_nr3_workspace_bytes', 'gp_nr3_solve_batch', 'gp_nr3_map_output']
 
 
 def check(rc: int):
@@ -100,6 +122,30 @@ def make_fbs_desc(t):
     d.root_cappu = (C.c_double * 3)(*[float(x) for x in t.root_cappu])
     d.vref = (C.c_double * 6)(*[float(x) for x in t.vref])
     d.zip = (C.c_double * 3)(*[float(x) for x in t.zip])
+    return d, keep
+
+
+def make_nr3_desc(t):
+    """Nr3Tables -> (GpNr3Desc, keep-alive dict)."""
+    keep = {}
+    d = GpNr3Desc()
+    d.n_steps, d.n_vrows, d.n_irows, d.n_srows = t.n_steps, t.n_vrows, t.n_irows, t.n_srows
+    d.n_child, d.n_lines = int(t.child_step.shape[0]), t.n_lines
+    for name in ('bus_vrow', 'par_vrow', 'edge_irow', 'load_srow', 'child_begin', 'child_count',
+                 'child_step', 'child_irow', 'line_irow', 'line_tx_vrow', 'line_rx_vrow'):
+        keep[name] = _i32(getattr(t, name))
+        setattr(d, name, keep[name].ctypes.data_as(i32p))
+    for name in ('z', 'cappu'):
+        keep[name] = _f64(getattr(t, name))
+        setattr(d, name, keep[name].ctypes.data_as(f64p))
+    d.root_vrow = (C.c_int32 * 3)(*[int(x) for x in t.root_vrow])
+    d.root_load_srow = (C.c_int32 * 3)(*[int(x) for x in t.root_load_srow])
+    d.root_cappu = (C.c_double * 3)(*[float(x) for x in t.root_cappu])
+    d.vslack = (C.c_double * 6)(*[float(x) for x in t.vslack])
+    d.zip = (C.c_double * 3)(*[float(x) for x in t.zip])
+    d.cA = (C.c_double * 3)(*[float(x) for x in t.cA])
+    d.cB = (C.c_double * 3)(*[float(x) for x in t.cB])
+    d.f0_absent = float(t.f0_absent)
     return d, keep
 
 

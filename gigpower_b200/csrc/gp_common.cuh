@@ -41,6 +41,8 @@ __device__ __forceinline__ double nan_to_num(double x) {
 
 }  // namespace gp
 
+void gp_nr3_destroy_impl(void* impl);
+
 struct GpFeeder {
     int device = 0;
     int kind = 0;  // 1 = FBS, 2 = NR3

@@ -434,6 +434,8 @@ extern "C" int gp_feeder_destroy(GpFeeder* f) {
             if (im->streams[i]) cudaStreamDestroy(im->streams[i]);
         }
         delete im;
+    } else if (f->kind == 2) {
+        gp_nr3_destroy_impl(f->impl);
     }
     delete f;
     return GP_OK;

@@ -1,0 +1,605 @@
+// Batched three-phase Newton-Raphson (NR3) for sm_100a.
+//
+// The reference assembles a dense Jacobian and solves inv(J'J) J' F
+// (solution_nr3.py:618-627).  On a radial feeder J has the structure of the
+// tree: per non-root bus k with incoming edge l from parent p
+//
+//   KVL_l (:141-158):  E dv_p - dv_k - Z di_l            = r1
+//   KCL_k (:265-299):  D dv_k + M di_l - M sum_c di_c    = r2
+//
+// so the Newton step J dx = F is solved exactly by block elimination along the
+// tree: a backward sweep (children first) that carries per bus a 6x6 equivalent
+// admittance Y_k and a 6-vector a_k with  di_l = a_k - Y_k dv_p, then a forward
+// sweep that applies dx.  Residual and Jacobian values are formed on the fly
+// from X (closed forms of the reference's H, g, b tensors), fused with the
+// elimination; nothing of size N x N is ever built.  The pivots are the KVL
+// identity blocks and M = [[A,B],[B,-A]] (|det| = |V|^2 ~ 1), so the fixed
+// elimination order needs no pivoting.
+//
+// One thread owns one scenario (FP64, whole Newton loop in one launch, each
+// scenario stops at its own iteration).  State and the per-bus (Y, a, r1)
+// fronts live in HBM as [row][ld] arrays with the scenario index innermost:
+// every access of a warp is a coalesced 128-bit transaction.
+#include "gp_common.cuh"
+
+#include <new>
+#include <vector>
+
+namespace gp {
+
+struct __align__(16) Nr3Step {
+    int bus_row[3];
+    int child_count;
+    int par_row[3];
+    int child_begin;
+    int edge_row[3];
+    int pad0;
+    int load_srow[3];
+    int pad1;
+    double cap[3];
+    double pad2;
+    double2 z[9];
+};
+static_assert(sizeof(Nr3Step) == 64 + 32 + 144, "Nr3Step layout");
+
+struct Nr3Const {
+    int root_row[3];
+    int n_steps;
+    double2 vslack[3];
+    double cA[3], cB[3];
+    double betaS, aPQ, aI, aZ;
+    double f0_absent;
+};
+
+struct Nr3Impl {
+    int n_steps = 0, n_vrows = 0, n_irows = 0, n_srows = 0, n_child = 0, n_lines = 0;
+    Nr3Step* d_steps = nullptr;
+    int4* d_child = nullptr;      // {child step, child edge rows[3]}
+    int* d_lines = nullptr;       // [n_lines][9] irow, tx vrow, rx vrow (X row indices)
+    int* d_vrow_srow = nullptr;   // [n_vrows]
+    double* d_vrow_cap = nullptr; // [n_vrows]
+    Nr3Const k;
+};
+
+constexpr int FRONT_D2 = 24;   // double2 per step: Y (18) + a (3) + r1 (3)
+
+// In-place LU (Doolittle, no pivoting) of a 6x6 held in registers.
+__device__ __forceinline__ void lu6(double (&T)[6][6]) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double inv = 1.0 / T[k][k];
+#pragma unroll
+        for (int r = k + 1; r < 6; ++r) {
+            const double m = T[r][k] * inv;
+            T[r][k] = m;
+#pragma unroll
+            for (int c = k + 1; c < 6; ++c) T[r][c] = fma(-m, T[k][c], T[r][c]);
+        }
+        T[k][k] = inv;   // keep the reciprocal of the pivot
+    }
+}
+
+__device__ __forceinline__ void lu6_solve(const double (&T)[6][6], double (&b)[6]) {
+#pragma unroll
+    for (int r = 1; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < r; ++c) b[r] = fma(-T[r][c], b[c], b[r]);
+#pragma unroll
+    for (int r = 5; r >= 0; --r) {
+#pragma unroll
+        for (int c = r + 1; c < 6; ++c) b[r] = fma(-T[r][c], b[c], b[r]);
+        b[r] *= T[r][r];
+    }
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ childs, Nr3Const k,
+                 int n_vrows, int n_irows, long long S, long long ld,
+                 const double2* __restrict__ spu, double2* __restrict__ X,
+                 double2* __restrict__ W, double2* __restrict__ DV, int* __restrict__ iters_out,
+                 int* __restrict__ status_out, double* __restrict__ fmax_out, int maxiter) {
+    const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (s >= S) return;
+    const double2* spu_s = spu + s;
+    double2* Xs = X + s;
+    double2* Ws = W + s;
+    double2* DVs = DV + s;
+    const int n_steps = k.n_steps;
+
+    // flat start (solution_nr3.py:37-82): every bus-phase at VSLACK, currents 0.
+    // Absent phases are not stored: their rows of J are identity rows whose first
+    // Newton step sets them to exactly 0 (:417-419, 159-161).
+    for (int pos = 0; pos < n_steps; ++pos) {
+        const int4 bv = __ldg(reinterpret_cast<const int4*>(steps[pos].bus_row));
+        const int4 ev = __ldg(reinterpret_cast<const int4*>(steps[pos].edge_row));
+        const int brow[3] = {bv.x, bv.y, bv.z}, erow[3] = {ev.x, ev.y, ev.z};
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            if (brow[p] >= 0) Xs[(long long)brow[p] * ld] = k.vslack[p];
+            if (erow[p] >= 0) Xs[(long long)erow[p] * ld] = make_double2(0.0, 0.0);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p) Xs[(long long)k.root_row[p] * ld] = k.vslack[p];
+
+    int it = 0;
+    double fm = 1e99;
+    bool nanflag = false;
+    while (fm >= 1e-9 && !nanflag && it < maxiter) {        // :618
+        fm = (it == 0) ? k.f0_absent : 0.0;
+        // ================= backward sweep: residual, Jacobian blocks, elimination =========
+        for (int pos = n_steps - 1; pos >= 0; --pos) {
+            const Nr3Step* st = steps + pos;
+            const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_row));
+            const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_row));
+            const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_row));
+            const int4 lv = __ldg(reinterpret_cast<const int4*>(st->load_srow));
+            const int brow[3] = {bv.x, bv.y, bv.z}, prow[3] = {pv.x, pv.y, pv.z};
+            const int erow[3] = {ev.x, ev.y, ev.z}, lrow[3] = {lv.x, lv.y, lv.z};
+            const int child_count = bv.w, child_begin = pv.w;
+            double2 v[3], inet[3], r1[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                v[p] = inet[p] = r1[p] = make_double2(0.0, 0.0);
+                if (brow[p] < 0) continue;
+                v[p] = Xs[(long long)brow[p] * ld];
+                inet[p] = Xs[(long long)erow[p] * ld];
+                if (prow[p] >= 0) r1[p] = Xs[(long long)prow[p] * ld];
+                r1[p].x -= v[p].x;
+                r1[p].y -= v[p].y;
+            }
+            // KVL residual r1 = E v_p - v - Z i   (:141-158)
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                if (brow[p] < 0) continue;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (brow[q] < 0) continue;
+                    const double2 z = __ldg(&st->z[3 * p + q]);
+                    r1[p].x -= z.x * inet[q].x - z.y * inet[q].y;
+                    r1[p].y -= z.x * inet[q].y + z.y * inet[q].x;
+                }
+            }
+            double Dt[6][6], rt[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                rt[r] = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) Dt[r][c] = 0.0;
+            }
+            // children: net current, and their fronts (Y_c, a_c)
+            for (int c = 0; c < child_count; ++c) {
+                const int4 ch = __ldg(childs + child_begin + c);
+                const int crow[3] = {ch.y, ch.z, ch.w};
+                const double2* Wc = Ws + (long long)ch.x * FRONT_D2 * ld;
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    if (crow[p] < 0) continue;
+                    const double2 ic = Xs[(long long)crow[p] * ld];
+                    inet[p].x -= ic.x;
+                    inet[p].y -= ic.y;
+                    const double2 ac = Wc[(long long)(18 + p) * ld];
+                    rt[2 * p] += ac.x;
+                    rt[2 * p + 1] += ac.y;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        if (crow[q] < 0) continue;
+                        const double2 y0 = Wc[(long long)((2 * p) * 3 + q) * ld];
+                        const double2 y1 = Wc[(long long)((2 * p + 1) * 3 + q) * ld];
+                        Dt[2 * p][2 * q] += y0.x;
+                        Dt[2 * p][2 * q + 1] += y0.y;
+                        Dt[2 * p + 1][2 * q] += y1.x;
+                        Dt[2 * p + 1][2 * q + 1] += y1.y;
+                    }
+                }
+            }
+            // KCL residual and D block per phase (closed form of H, g, b; :226-299, 403-440)
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                if (brow[p] < 0) continue;
+                const double A = v[p].x, B = v[p].y, Cn = inet[p].x, Dn = inet[p].y;
+                double pl = 0.0, ql = 0.0;
+                if (lrow[p] >= 0) {
+                    const double2 sp = spu_s[(long long)lrow[p] * ld];
+                    pl = sp.x;
+                    ql = sp.y;
+                }
+                const double cap = __ldg(&st->cap[p]);
+                const double hAr = -pl * k.cA[p], hBr = -pl * k.cB[p], b0r = -pl * k.betaS;
+                const double hAi = -ql * k.cA[p] + cap * k.cA[p];
+                const double hBi = -ql * k.cB[p] + cap * k.cB[p];
+                const double b0i = (-ql * k.betaS) + (cap * k.betaS);
+                const double fr = A * Cn + B * Dn + hAr * A * A + hBr * B * B + b0r;
+                const double fi = B * Cn - A * Dn + hAi * A * A + hBi * B * B + b0i;
+                nanflag |= (fr != fr) | (fi != fi) | (r1[p].x != r1[p].x) | (r1[p].y != r1[p].y);
+                fm = fmax(fm, fmax(fmax(fabs(fr), fabs(fi)), fmax(fabs(r1[p].x), fabs(r1[p].y))));
+                const double d00 = Cn + 2.0 * hAr * A, d01 = Dn + 2.0 * hBr * B;
+                const double d10 = -Dn + 2.0 * hAi * A, d11 = Cn + 2.0 * hBi * B;
+                const double inv = 1.0 / (A * A + B * B);
+                // M^-1 = M / |V|^2,  M = [[A, B], [B, -A]]
+                Dt[2 * p][2 * p] += (A * d00 + B * d10) * inv;
+                Dt[2 * p][2 * p + 1] += (A * d01 + B * d11) * inv;
+                Dt[2 * p + 1][2 * p] += (B * d00 - A * d10) * inv;
+                Dt[2 * p + 1][2 * p + 1] += (B * d01 - A * d11) * inv;
+                rt[2 * p] += (A * fr + B * fi) * inv;
+                rt[2 * p + 1] += (B * fr - A * fi) * inv;
+            }
+            // rhs_a = rt + Dt r1 ;  T = I - Dt Zr
+            double T[6][6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    rt[r] = fma(Dt[r][2 * q], r1[q].x, rt[r]);
+                    rt[r] = fma(Dt[r][2 * q + 1], r1[q].y, rt[r]);
+                    double t0 = (r == 2 * q) ? 1.0 : 0.0, t1 = (r == 2 * q + 1) ? 1.0 : 0.0;
+                    if (brow[q] >= 0) {
+#pragma unroll
+                        for (int w = 0; w < 3; ++w) {
+                            if (brow[w] < 0) continue;
+                            const double2 z = __ldg(&st->z[3 * w + q]);   // Z[w][q]
+                            // Zr[2w][2q] = R, Zr[2w][2q+1] = -X, Zr[2w+1][2q] = X, Zr[2w+1][2q+1] = R
+                            t0 -= Dt[r][2 * w] * z.x + Dt[r][2 * w + 1] * z.y;
+                            t1 -= -Dt[r][2 * w] * z.y + Dt[r][2 * w + 1] * z.x;
+                        }
+                    }
+                    T[r][2 * q] = t0;
+                    T[r][2 * q + 1] = t1;
+                }
+            }
+            lu6(T);
+            lu6_solve(T, rt);
+            double2* Wk = Ws + (long long)pos * FRONT_D2 * ld;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                if (brow[p] < 0) continue;
+                Wk[(long long)(18 + p) * ld] = make_double2(rt[2 * p], rt[2 * p + 1]);
+                Wk[(long long)(21 + p) * ld] = r1[p];
+            }
+            // Y = T^-1 Dt E, two columns (one phase of the parent) at a time
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                if (brow[q] < 0) continue;
+                double y0[6], y1[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    y0[r] = Dt[r][2 * q];
+                    y1[r] = Dt[r][2 * q + 1];
+                }
+                lu6_solve(T, y0);
+                lu6_solve(T, y1);
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+                    if (brow[r / 2] >= 0) Wk[(long long)(r * 3 + q) * ld] = make_double2(y0[r], y1[r]);
+            }
+        }
+        // ================= slack rows (:84-109) and forward sweep ================================
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const double2 v0 = Xs[(long long)k.root_row[p] * ld];
+            const double2 d = make_double2(v0.x - k.vslack[p].x, v0.y - k.vslack[p].y);
+            nanflag |= (d.x != d.x) | (d.y != d.y);
+            fm = fmax(fm, fmax(fabs(d.x), fabs(d.y)));
+            DVs[(long long)k.root_row[p] * ld] = d;
+            Xs[(long long)k.root_row[p] * ld] = make_double2(v0.x - d.x, v0.y - d.y);
+        }
+        for (int pos = 0; pos < n_steps; ++pos) {
+            const Nr3Step* st = steps + pos;
+            const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_row));
+            const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_row));
+            const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_row));
+            const int brow[3] = {bv.x, bv.y, bv.z}, prow[3] = {pv.x, pv.y, pv.z};
+            const int erow[3] = {ev.x, ev.y, ev.z};
+            const double2* Wk = Ws + (long long)pos * FRONT_D2 * ld;
+            double2 dvp[3], di[3], dv[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+                dvp[p] = (brow[p] >= 0 && prow[p] >= 0) ? DVs[(long long)prow[p] * ld] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                di[p] = make_double2(0.0, 0.0);
+                if (brow[p] < 0) continue;
+                di[p] = Wk[(long long)(18 + p) * ld];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (brow[q] < 0) continue;
+                    const double2 y0 = Wk[(long long)((2 * p) * 3 + q) * ld];
+                    const double2 y1 = Wk[(long long)((2 * p + 1) * 3 + q) * ld];
+                    di[p].x -= y0.x * dvp[q].x + y0.y * dvp[q].y;
+                    di[p].y -= y1.x * dvp[q].x + y1.y * dvp[q].y;
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                if (brow[p] < 0) continue;
+                const double2 r1 = Wk[(long long)(21 + p) * ld];
+                dv[p] = make_double2(dvp[p].x - r1.x, dvp[p].y - r1.y);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (brow[q] < 0) continue;
+                    const double2 z = __ldg(&st->z[3 * p + q]);
+                    dv[p].x -= z.x * di[q].x - z.y * di[q].y;
+                    dv[p].y -= z.x * di[q].y + z.y * di[q].x;
+                }
+                const double2 xv = Xs[(long long)brow[p] * ld];
+                const double2 xi = Xs[(long long)erow[p] * ld];
+                Xs[(long long)brow[p] * ld] = make_double2(xv.x - dv[p].x, xv.y - dv[p].y);
+                Xs[(long long)erow[p] * ld] = make_double2(xi.x - di[p].x, xi.y - di[p].y);
+                DVs[(long long)brow[p] * ld] = dv[p];
+            }
+        }
+        ++it;
+    }
+    iters_out[s] = it;
+    fmax_out[s] = nanflag ? __longlong_as_double(0x7ff8000000000000LL) : fm;
+    status_out[s] = nanflag ? GP_ST_NONFINITE : (fm < 1e-9 ? GP_ST_CONVERGED : (isinf(fm) ? GP_ST_NONFINITE : GP_ST_MAXITER));
+}
+
+// nr3_lib/map_output.py:24-27: |re| <= 1e-12 -> v = imag + 0j (imag lands in the REAL
+// slot); else |im| <= 1e-12 -> v = re + 0j.
+__device__ __forceinline__ double2 scrub(double2 v) {
+    if (fabs(v.x) <= 1e-12) return make_double2(v.y, 0.0);
+    if (fabs(v.y) <= 1e-12) return make_double2(v.x, 0.0);
+    return v;
+}
+
+// X -> V, |V|, sV, i_Node per V row (map_output.py:18-29, 56-77)
+__global__ void nr3_map_rows_kernel(int n_vrows, int n_irows, const int* __restrict__ vrow_srow,
+                                    const double* __restrict__ vrow_cap, Nr3Const k, long long S,
+                                    long long ld, const double2* __restrict__ spu,
+                                    const double2* __restrict__ X, double2* __restrict__ V,
+                                    double2* __restrict__ I, double2* __restrict__ sV,
+                                    double2* __restrict__ iN, double* __restrict__ Vmag) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    for (int r = blockIdx.y; r < n_vrows + n_irows; r += gridDim.y) {
+        const double2 x = scrub(X[(long long)r * ld + s]);
+        if (r >= n_vrows) {
+            if (I) I[(long long)(r - n_vrows) * ld + s] = x;
+            continue;
+        }
+        if (V) V[(long long)r * ld + s] = x;
+        const double a = sqrt(fma(x.x, x.x, x.y * x.y));
+        if (Vmag) Vmag[(long long)r * ld + s] = a;
+        if (sV || iN) {
+            double2 sv = make_double2(0.0, 0.0);
+            const int lr = __ldg(vrow_srow + r);
+            if (lr >= 0) {
+                const double2 sp = spu[(long long)lr * ld + s];
+                const double f = k.aPQ + k.aI * a + k.aZ * (a * a);
+                sv.x = sp.x * f;
+                sv.y = sp.y * f;
+            }
+            sv.y -= __ldg(vrow_cap + r);          // no |V|^2 factor here (map_output.py:60)
+            sv = scrub(sv);
+            if (sV) sV[(long long)r * ld + s] = sv;
+            if (iN) {
+                const double inv = 1.0 / fma(x.x, x.x, x.y * x.y);
+                const double qr = (sv.x * x.x + sv.y * x.y) * inv;
+                const double qi = (sv.y * x.x - sv.x * x.y) * inv;
+                iN[(long long)r * ld + s] = scrub(make_double2(qr, -qi));
+            }
+        }
+    }
+}
+
+__global__ void nr3_map_lines_kernel(int n_lines, int n_vrows, const int* __restrict__ lines, long long S,
+                                     long long ld, const double2* __restrict__ X,
+                                     double2* __restrict__ Stx, double2* __restrict__ Srx,
+                                     double2* __restrict__ loss) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double2 acc = make_double2(0.0, 0.0);
+    for (int l = 0; l < n_lines; ++l) {
+        const int* rec = lines + 9 * l;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const int ir = __ldg(rec + p);
+            if (ir < 0) continue;
+            const int tr = __ldg(rec + 3 + p), rr = __ldg(rec + 6 + p);
+            const double2 i = scrub(X[(long long)ir * ld + s]);
+            const double2 vt = tr >= 0 ? scrub(X[(long long)tr * ld + s]) : make_double2(0.0, 0.0);
+            const double2 vr = rr >= 0 ? scrub(X[(long long)rr * ld + s]) : make_double2(0.0, 0.0);
+            const double2 st = scrub(make_double2(vt.x * i.x + vt.y * i.y, vt.y * i.x - vt.x * i.y));
+            const double2 sr = scrub(make_double2(vr.x * i.x + vr.y * i.y, vr.y * i.x - vr.x * i.y));
+            if (Stx) Stx[(long long)(ir - n_vrows) * ld + s] = st;
+            if (Srx) Srx[(long long)(ir - n_vrows) * ld + s] = sr;
+            acc.x += st.x - sr.x;
+            acc.y += st.y - sr.y;
+        }
+    }
+    if (loss) loss[s] = acc;
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" int gp_nr3_create(const GpNr3Desc* d, int device, GpFeeder** out) {
+    if (!d || !out) return fail(GP_EINVAL, "gp_nr3_create: null argument");
+    if (d->n_steps < 0 || d->n_vrows < 3 || d->n_irows < 0 || d->n_srows < 0)
+        return fail(GP_EINVAL, "gp_nr3_create: bad sizes");
+    GP_CUDA(cudaSetDevice(device));
+    Nr3Impl* im = new (std::nothrow) Nr3Impl();
+    if (!im) return fail(GP_ENOMEM, "gp_nr3_create: out of host memory");
+    im->n_steps = d->n_steps;
+    im->n_vrows = d->n_vrows;
+    im->n_irows = d->n_irows;
+    im->n_srows = d->n_srows;
+    im->n_child = d->n_child;
+    im->n_lines = d->n_lines;
+    const int nx = d->n_vrows + d->n_irows;
+    std::vector<Nr3Step> steps((size_t)d->n_steps);
+    std::vector<int> vrow_srow((size_t)d->n_vrows, -1);
+    std::vector<double> vrow_cap((size_t)d->n_vrows, 0.0);
+    for (int i = 0; i < d->n_steps; ++i) {
+        Nr3Step& s = steps[i];
+        memset(&s, 0, sizeof(s));
+        s.child_begin = d->child_begin[i];
+        s.child_count = d->child_count[i];
+        if (s.child_begin < 0 || s.child_count < 0 || s.child_begin + s.child_count > d->n_child) {
+            delete im;
+            return fail(GP_EINVAL, "gp_nr3_create: step %d child range out of bounds", i);
+        }
+        for (int p = 0; p < 3; ++p) {
+            s.bus_row[p] = d->bus_vrow[3 * i + p];
+            s.par_row[p] = d->par_vrow[3 * i + p];
+            s.edge_row[p] = d->edge_irow[3 * i + p] >= 0 ? d->edge_irow[3 * i + p] + d->n_vrows : -1;
+            s.load_srow[p] = d->load_srow[3 * i + p];
+            const bool has_b = s.bus_row[p] >= 0, has_e = s.edge_row[p] >= 0;
+            if (has_b != has_e || s.bus_row[p] >= d->n_vrows || s.par_row[p] >= d->n_vrows ||
+                s.edge_row[p] >= nx || s.load_srow[p] >= d->n_srows || s.bus_row[p] < -1 ||
+                s.par_row[p] < -1 || s.load_srow[p] < -1) {
+                delete im;
+                return fail(GP_EINVAL, "gp_nr3_create: step %d: a bus must carry exactly the phases of "
+                                       "its incoming edge, with valid row indices", i);
+            }
+            s.cap[p] = d->cappu[3 * i + p];
+            if (has_b) {
+                vrow_srow[s.bus_row[p]] = s.load_srow[p];
+                vrow_cap[s.bus_row[p]] = s.cap[p];
+            }
+            for (int q = 0; q < 3; ++q) {
+                s.z[3 * p + q].x = d->z[((size_t)i * 9 + 3 * p + q) * 2];
+                s.z[3 * p + q].y = d->z[((size_t)i * 9 + 3 * p + q) * 2 + 1];
+            }
+        }
+    }
+    std::vector<int4> childs((size_t)d->n_child);
+    for (int c = 0; c < d->n_child; ++c) {
+        childs[c].x = d->child_step[c];
+        int* rows[3] = {&childs[c].y, &childs[c].z, &childs[c].w};
+        for (int p = 0; p < 3; ++p) {
+            const int r = d->child_irow[3 * c + p];
+            *rows[p] = r >= 0 ? r + d->n_vrows : -1;
+        }
+        if (childs[c].x < 0 || childs[c].x >= d->n_steps) {
+            delete im;
+            return fail(GP_EINVAL, "gp_nr3_create: child %d step index out of range", c);
+        }
+    }
+    for (int p = 0; p < 3; ++p) {
+        im->k.root_row[p] = d->root_vrow[p];
+        if (d->root_vrow[p] < 0 || d->root_vrow[p] >= d->n_vrows) {
+            delete im;
+            return fail(GP_EINVAL, "gp_nr3_create: the slack bus must carry all three phases");
+        }
+        im->k.vslack[p] = make_double2(d->vslack[2 * p], d->vslack[2 * p + 1]);
+        im->k.cA[p] = d->cA[p];
+        im->k.cB[p] = d->cB[p];
+        vrow_srow[d->root_vrow[p]] = d->root_load_srow[p];
+        vrow_cap[d->root_vrow[p]] = d->root_cappu[p];
+    }
+    im->k.n_steps = d->n_steps;
+    im->k.aPQ = d->zip[0];
+    im->k.aI = d->zip[1];
+    im->k.aZ = d->zip[2];
+    im->k.betaS = d->zip[0];
+    im->k.f0_absent = d->f0_absent;
+    std::vector<int> lines((size_t)d->n_lines * 9);
+    for (int l = 0; l < d->n_lines; ++l)
+        for (int p = 0; p < 3; ++p) {
+            const int ir = d->line_irow[3 * l + p];
+            lines[9 * l + p] = ir >= 0 ? ir + d->n_vrows : -1;
+            lines[9 * l + 3 + p] = d->line_tx_vrow[3 * l + p];
+            lines[9 * l + 6 + p] = d->line_rx_vrow[3 * l + p];
+        }
+    auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
+        if (e != cudaSuccess) return e;
+        return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    cudaError_t e = up((void**)&im->d_steps, steps.data(), steps.size() * sizeof(Nr3Step));
+    if (e == cudaSuccess) e = up((void**)&im->d_child, childs.data(), childs.size() * sizeof(int4));
+    if (e == cudaSuccess) e = up((void**)&im->d_lines, lines.data(), lines.size() * sizeof(int));
+    if (e == cudaSuccess) e = up((void**)&im->d_vrow_srow, vrow_srow.data(), vrow_srow.size() * sizeof(int));
+    if (e == cudaSuccess) e = up((void**)&im->d_vrow_cap, vrow_cap.data(), vrow_cap.size() * sizeof(double));
+    if (e != cudaSuccess) {
+        delete im;
+        return fail(GP_ECUDA, "gp_nr3_create: %s", cudaGetErrorString(e));
+    }
+    GpFeeder* f = new (std::nothrow) GpFeeder();
+    f->device = device;
+    f->kind = 2;
+    f->impl = im;
+    *out = f;
+    return GP_OK;
+}
+
+void gp_nr3_destroy_impl(void* impl) {
+    Nr3Impl* im = (Nr3Impl*)impl;
+    cudaFree(im->d_steps);
+    cudaFree(im->d_child);
+    cudaFree(im->d_lines);
+    cudaFree(im->d_vrow_srow);
+    cudaFree(im->d_vrow_cap);
+    delete im;
+}
+
+static int nr3_check(GpFeeder* f, int64_t S, int64_t ld, const char* who) {
+    if (!f || f->kind != 2) return fail(GP_EINVAL, "%s: not an NR3 feeder handle", who);
+    if (S < 0 || ld < S) return fail(GP_EINVAL, "%s: need 0 <= S <= ld (S=%lld ld=%lld)", who, (long long)S, (long long)ld);
+    return GP_OK;
+}
+
+extern "C" int64_t gp_nr3_workspace_bytes(GpFeeder* f, int64_t ld) {
+    if (!f || f->kind != 2 || ld < 0) return fail(GP_EINVAL, "gp_nr3_workspace_bytes: bad argument");
+    Nr3Impl* im = (Nr3Impl*)f->impl;
+    return ((int64_t)im->n_steps * FRONT_D2 + im->n_vrows) * ld * 16 + 256;
+}
+
+extern "C" int gp_nr3_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const double* spu, double* X,
+                                  int32_t* iters, int32_t* status, double* fmax, void* workspace,
+                                  int64_t workspace_bytes, int32_t maxiter, void* stream) {
+    int rc = nr3_check(f, S, ld, "gp_nr3_solve_batch");
+    if (rc) return rc;
+    if (S == 0) return GP_OK;
+    Nr3Impl* im = (Nr3Impl*)f->impl;
+    if (!X || !iters || !status || !fmax || !workspace || (!spu && im->n_srows > 0))
+        return fail(GP_EINVAL, "gp_nr3_solve_batch: null buffer");
+    if (workspace_bytes < gp_nr3_workspace_bytes(f, ld))
+        return fail(GP_EINVAL, "gp_nr3_solve_batch: workspace too small (%lld < %lld bytes)",
+                    (long long)workspace_bytes, (long long)gp_nr3_workspace_bytes(f, ld));
+    GP_CUDA(cudaSetDevice(f->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int BLOCK = 64;
+    const unsigned gx = (unsigned)((S + BLOCK - 1) / BLOCK);
+    double2* W = (double2*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    double2* DV = W + (size_t)im->n_steps * FRONT_D2 * ld;
+    nr3_solve_kernel<BLOCK><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_vrows, im->n_irows, S,
+                                                  ld, (const double2*)spu, (double2*)X, W, DV, iters, status,
+                                                  fmax, maxiter);
+    count_launch();
+    GP_CUDA(cudaGetLastError());
+    return GP_OK;
+}
+
+extern "C" int gp_nr3_map_output(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const double* X,
+                                 double* V, double* I, double* Stx, double* Srx, double* sV, double* iN,
+                                 double* Vmag, double* loss, void* stream) {
+    int rc = nr3_check(f, S, ld, "gp_nr3_map_output");
+    if (rc) return rc;
+    if (S == 0) return GP_OK;
+    Nr3Impl* im = (Nr3Impl*)f->impl;
+    if (!X) return fail(GP_EINVAL, "gp_nr3_map_output: null state buffer");
+    if ((sV || iN) && !spu && im->n_srows > 0) return fail(GP_EINVAL, "gp_nr3_map_output: sV needs spu");
+    GP_CUDA(cudaSetDevice(f->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int BLOCK = 128;
+    const unsigned gx = (unsigned)((S + BLOCK - 1) / BLOCK);
+    if (V || I || sV || iN || Vmag) {
+        dim3 g(gx, 8);
+        nr3_map_rows_kernel<<<g, BLOCK, 0, st>>>(im->n_vrows, im->n_irows, im->d_vrow_srow, im->d_vrow_cap, im->k,
+                                                 S, ld, (const double2*)spu, (const double2*)X, (double2*)V,
+                                                 (double2*)I, (double2*)sV, (double2*)iN, Vmag);
+        count_launch();
+    }
+    if (Stx || Srx || loss) {
+        nr3_map_lines_kernel<<<gx, BLOCK, 0, st>>>(im->n_lines, im->n_vrows, im->d_lines, S, ld,
+                                                   (const double2*)X, (double2*)Stx, (double2*)Srx, (double2*)loss);
+        count_launch();
+    }
+    GP_CUDA(cudaGetLastError());
+    return GP_OK;
+}

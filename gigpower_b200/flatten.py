@@ -227,3 +227,177 @@ def flatten_fbs(c: Circuit) -> FbsTables:
         line_rx_vrow=vrow[rx].reshape(-1, 3).copy() if nl else np.zeros((0, 3), np.int32),
         vrow=vrow, irow=irow, srow=srow, topo_order=order, adj=adj, reverse_adj=rev,
         tolerance=float(tol), depth=max(depth_of.values()) if depth_of else 0, **t)
+
+
+# ==========================================================================
+# NR3
+# ==========================================================================
+@dataclass
+class Nr3Tables:
+    """NumPy image of ``GpNr3Desc`` plus the maps between the packed device
+    state and the reference's ``XNR`` ordering (solution_nr3.py:46-61)."""
+    n_steps: int
+    n_vrows: int
+    n_irows: int
+    n_srows: int
+    n_lines: int
+    bus_vrow: np.ndarray
+    par_vrow: np.ndarray
+    edge_irow: np.ndarray
+    load_srow: np.ndarray
+    child_begin: np.ndarray
+    child_count: np.ndarray
+    child_step: np.ndarray
+    child_irow: np.ndarray
+    z: np.ndarray
+    cappu: np.ndarray
+    root_vrow: np.ndarray
+    root_load_srow: np.ndarray
+    root_cappu: np.ndarray
+    vslack: np.ndarray
+    zip: np.ndarray
+    cA: np.ndarray
+    cB: np.ndarray
+    f0_absent: float
+    line_irow: np.ndarray
+    line_tx_vrow: np.ndarray
+    line_rx_vrow: np.ndarray
+    vrow: np.ndarray = field(default=None)       # [nb,3]
+    irow: np.ndarray = field(default=None)       # [nl+ntf,3]
+    srow: np.ndarray = field(default=None)       # [nb,3]
+    N: int = 0                                    # length of XNR
+    xnr_index: np.ndarray = field(default=None)  # [n_vrows+n_irows] even XNR index of each packed row
+    order: List[int] = field(default=None)
+
+
+def flatten_nr3(c: Circuit) -> Nr3Tables:
+    """Tree tables for the block elimination of ``gp_nr3.cu``.  Supported: radial
+    feeders of Lines and Transformers oriented away from the slack bus (index 0);
+    every bus must carry exactly the phases of its incoming edge."""
+    if c.voltage_regulators.num_elements:
+        raise NotImplementedError('NR3 on feeders with voltage regulators is not built yet')
+    names = c.buses.all_names()
+    nb, nl, ntf = len(names), c.lines.num_elements, c.transformers.num_elements
+    bidx = {n: i for i, n in enumerate(names)}
+    bus_pm = c.buses.get_phase_matrix('rows')
+    if bus_pm[0].sum() != 3:
+        raise NotImplementedError('the slack bus must carry all three phases')
+    edges = c.lines.get_elements() + c.transformers.get_elements()
+    parent, edge_in, children = {}, {}, {b: [] for b in range(nb)}
+    for ei, e in enumerate(edges):
+        tx, rx = bidx[e.tx], bidx[e.rx]
+        if rx in parent:
+            raise ValueError(f"Network not radial. Bus {e.rx} has parents {[names[parent[rx]], e.tx]}")
+        parent[rx], edge_in[rx] = tx, ei
+        children[tx].append(rx)
+    order, stack = [], [0]
+    seen = {0}
+    while stack:                      # parents before children; any such order is valid
+        u = stack.pop()
+        order.append(u)
+        for ch in reversed(children[u]):
+            if ch in seen:
+                raise ValueError('Not radial. Contains a cycle.')
+            seen.add(ch)
+            stack.append(ch)
+    if len(order) != nb:
+        raise ValueError('Network not radial / not connected to the slack bus')
+
+    vrow = np.full((nb, 3), -1, dtype=np.int32)
+    k = 0
+    for b in range(nb):
+        for p in range(3):
+            if bus_pm[b, p]:
+                vrow[b, p] = k
+                k += 1
+    n_vrows = k
+    irow = np.full((nl + ntf, 3), -1, dtype=np.int32)
+    k = 0
+    for i, e in enumerate(edges):
+        for p in range(3):
+            if e.phase_matrix[p]:
+                irow[i, p] = k
+                k += 1
+    n_irows = k
+    lmask = c.load_phase_mask()
+    srow = np.full((nb, 3), -1, dtype=np.int32)
+    k = 0
+    for b in range(nb):
+        for p in range(3):
+            if lmask[b, p] and bus_pm[b, p]:
+                srow[b, p] = k
+                k += 1
+    n_srows = k
+    cappu = c._by_bus(c.capacitors, 'cappu', float)
+
+    n_steps = nb - 1
+    step_of = {b: i for i, b in enumerate(order[1:])}
+    S3 = (n_steps, 3)
+    t = dict(bus_vrow=np.full(S3, -1, np.int32), par_vrow=np.full(S3, -1, np.int32),
+             edge_irow=np.full(S3, -1, np.int32), load_srow=np.full(S3, -1, np.int32),
+             child_begin=np.zeros(n_steps, np.int32), child_count=np.zeros(n_steps, np.int32),
+             z=np.zeros((n_steps, 3, 3, 2)), cappu=np.zeros(S3))
+    child_step, child_rows = [], []
+    for pos, b in enumerate(order[1:]):
+        e = edges[edge_in[b]]
+        if not np.array_equal(e.phase_matrix, bus_pm[b]):
+            raise NotImplementedError(f'bus {names[b]}: phases differ from its incoming edge {e.__name__}')
+        t['bus_vrow'][pos], t['par_vrow'][pos] = vrow[b], vrow[parent[b]]
+        t['edge_irow'][pos], t['load_srow'][pos], t['cappu'][pos] = irow[edge_in[b]], srow[b], cappu[b]
+        if e.kind == 'Line':       # rmat/xmat (line.py:48-73); identical numbers to FZpu on existing phases
+            R, X = e.rmat.reshape(3, 3), e.xmat.reshape(3, 3)
+            pm = e.phase_matrix
+            t['z'][pos, :, :, 0] = R * pm[None, :] * pm[:, None]
+            t['z'][pos, :, :, 1] = X * pm[None, :] * pm[:, None]
+        t['child_begin'][pos] = len(child_step)
+        for ch in children[b]:
+            child_step.append(step_of[ch])
+            child_rows.append(irow[edge_in[ch]])
+        t['child_count'][pos] = len(child_step) - t['child_begin'][pos]
+
+    # second-order ZIP constants per phase (solution_nr3.py:228-261)
+    zp = np.array([c.loads.aPQ_p, c.loads.aI_p, c.loads.aZ_p], dtype=float)
+    cA, cB = np.zeros(3), np.zeros(3)
+    for ph in range(3):
+        A0, B0 = (1, 0) if ph == 0 else ((-1 / 2, -1 * np.sqrt(3) / 2) if ph == 1 else (-1 / 2, np.sqrt(3) / 2))
+        h00 = -((A0 ** 2) * (A0 ** 2 + B0 ** 2) ** (-3 / 2)) + (A0 ** 2 + B0 ** 2) ** (-1 / 2)
+        h11 = -((B0 ** 2) * (A0 ** 2 + B0 ** 2) ** (-3 / 2)) + ((A0 ** 2 + B0 ** 2) ** (-1 / 2))
+        cA[ph] = zp[2] + (0.5 * zp[1] * h00)
+        cB[ph] = zp[2] + (0.5 * zp[1] * h11)
+    vslack = np.array([1, np.exp(1j * -120 * np.pi / 180), np.exp(1j * 120 * np.pi / 180)], dtype=complex)
+    f0 = 0.0
+    for b in range(1, nb):
+        for p in range(3):
+            if not bus_pm[b, p]:
+                f0 = max(f0, abs(vslack[p].real), abs(vslack[p].imag))
+
+    # packed row -> XNR index (solution_nr3.py:46-61; transformer currents after the lines)
+    tf_lines = int(sum(len(e.phases) for e in c.transformers.get_elements()))
+    N = 2 * 3 * (nb + nl) + 2 * tf_lines
+    xnr = np.zeros(n_vrows + n_irows, dtype=np.int64)
+    for b in range(nb):
+        for p in range(3):
+            if vrow[b, p] >= 0:
+                xnr[vrow[b, p]] = 2 * nb * p + 2 * b
+    for l in range(nl):
+        for p in range(3):
+            if irow[l, p] >= 0:
+                xnr[n_vrows + irow[l, p]] = 6 * nb + 2 * p * nl + 2 * l
+    cnt = 0
+    for ti, e in enumerate(c.transformers.get_elements()):
+        for p in range(3):
+            if irow[nl + ti, p] >= 0:
+                xnr[n_vrows + irow[nl + ti, p]] = 6 * (nb + nl) + 2 * cnt
+                cnt += 1
+    tx = np.array([bidx[e.tx] for e in c.lines.get_elements()], dtype=int)
+    rx = np.array([bidx[e.rx] for e in c.lines.get_elements()], dtype=int)
+    return Nr3Tables(
+        n_steps=n_steps, n_vrows=n_vrows, n_irows=n_irows, n_srows=n_srows, n_lines=nl,
+        child_step=np.array(child_step, dtype=np.int32),
+        child_irow=(np.array(child_rows, dtype=np.int32).reshape(-1, 3) if child_rows else np.zeros((0, 3), np.int32)),
+        root_vrow=vrow[0].copy(), root_load_srow=srow[0].copy(), root_cappu=cappu[0].copy(),
+        vslack=np.stack([vslack.real, vslack.imag], axis=1).reshape(-1).copy(), zip=zp, cA=cA, cB=cB,
+        f0_absent=float(f0), line_irow=irow[:nl].copy(),
+        line_tx_vrow=vrow[tx].reshape(-1, 3).copy() if nl else np.zeros((0, 3), np.int32),
+        line_rx_vrow=vrow[rx].reshape(-1, 3).copy() if nl else np.zeros((0, 3), np.int32),
+        vrow=vrow, irow=irow, srow=srow, N=N, xnr_index=xnr, order=order, **t)

@@ -154,6 +154,79 @@ int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const double* sp
                             double* loss_host, int32_t* iters_host, int32_t* status_host,
                             double* diff_host, double tol, int32_t maxiter);
 
+
+/* ------------------------------------------------------------------------
+ * NR3 (three-phase Newton-Raphson), reference src/solution_nr3.py + src/nr3_lib/
+ * ------------------------------------------------------------------------ */
+
+/*
+ * Flattened feeder for NR3.  Replaces the dense tensors SolutionNR3.__init__
+ * builds (g_SB/b_SB :84-109, G_KVL :111-177, H/g/b :179-442): the same rows are
+ * evaluated in closed form from these tables.  The unknown vector X is stored
+ * PACKED as complex rows (A + jB per existing bus-phase, C + jD per existing
+ * edge-phase): rows [0, n_vrows) are bus voltages, rows [n_vrows, n_vrows +
+ * n_irows) edge currents.  Phases that do not exist are identity rows of J whose
+ * solution is exactly 0 and are not stored.
+ *
+ * Step k is a non-slack bus with its incoming edge (Line, or Transformer with
+ * Z = 0) from its parent, parents before children; a bus must carry exactly the
+ * phases of its incoming edge.  The slack bus (index 0, solution.py:20) is the root.
+ */
+typedef struct {
+    int32_t n_steps, n_vrows, n_irows, n_srows, n_child, n_lines;
+    const int32_t* bus_vrow;    /* [n_steps][3] X row of (bus, ph) or -1               */
+    const int32_t* par_vrow;    /* [n_steps][3] X row of (parent, ph) or -1            */
+    const int32_t* edge_irow;   /* [n_steps][3] current row (0-based in the I block)   */
+    const int32_t* load_srow;   /* [n_steps][3] spu row or -1                          */
+    const int32_t* child_begin; /* [n_steps]                                           */
+    const int32_t* child_count; /* [n_steps]                                           */
+    const int32_t* child_step;  /* [n_child] step index of each child bus              */
+    const int32_t* child_irow;  /* [n_child][3] current rows of the child edges        */
+    const double* z;            /* [n_steps][3][3][2] pu impedance (rmat/xmat, line.py:48-73) */
+    const double* cappu;        /* [n_steps][3]                                        */
+    int32_t root_vrow[3];
+    int32_t root_load_srow[3];
+    double root_cappu[3];
+    double vslack[6];           /* solution.py:23-24, interleaved                      */
+    double zip[3];              /* aPQ_p, aI_p, aZ_p (beta_S/I/Z = gamma_S/I/Z, :210-217) */
+    double cA[3];               /* beta_Z + 0.5 beta_I hessian_mag[0][0] per phase (:252-258) */
+    double cB[3];               /* beta_Z + 0.5 beta_I hessian_mag[1][1] per phase     */
+    double f0_absent;           /* max |F| of the identity rows of absent phases at flat start */
+    const int32_t* line_irow;   /* [n_lines][3] real lines, for Stx/Srx (map_output.py:40-55) */
+    const int32_t* line_tx_vrow;
+    const int32_t* line_rx_vrow;
+} GpNr3Desc;
+
+int gp_nr3_create(const GpNr3Desc* desc, int device, GpFeeder** out);
+
+/* Bytes of device scratch gp_nr3_solve_batch needs for row pitch ld (negative = error). */
+int64_t gp_nr3_workspace_bytes(GpFeeder* f, int64_t ld);
+
+/*
+ * Solve S scenarios from flat start; replaces SolutionNR3.solve()
+ * (solution_nr3.py:592-632): X <- X - J^-1 F while max|F(previous X)| >= 1e-9
+ * and it < maxiter, per scenario.
+ *
+ *   spu_dev    [n_srows][ld] complex   per-scenario bus loads (p + jq, load_group.py:25-37)
+ *   X_dev      [n_vrows + n_irows][ld] complex   out: packed solution vector
+ *   iters_dev  [S] int32               out: Newton iterations (the reference's local itercount)
+ *   status_dev [S] int32               out: GP_ST_*
+ *   fmax_dev   [S] double              out: max|F| seen by the last test
+ */
+int gp_nr3_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const double* spu_dev, double* X_dev,
+                       int32_t* iters_dev, int32_t* status_dev, double* fmax_dev,
+                       void* workspace_dev, int64_t workspace_bytes, int32_t maxiter, void* stream);
+
+/*
+ * X -> results; replaces map_XNR / map_output (solution_nr3.py:634-663,
+ * nr3_lib/map_output.py:4-79), including its 1e-12 scrub.  Any output may be NULL.
+ *   V, sV, iNode [n_vrows][ld] complex; Vmag [n_vrows][ld] double;
+ *   I, Stx, Srx  [n_irows][ld] complex (Stx/Srx: rows of real lines); loss [S] complex.
+ */
+int gp_nr3_map_output(GpFeeder* f, int64_t S, int64_t ld, const double* spu_dev, const double* X_dev,
+                      double* V_dev, double* I_dev, double* Stx_dev, double* Srx_dev, double* sV_dev,
+                      double* iNode_dev, double* Vmag_dev, double* loss_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

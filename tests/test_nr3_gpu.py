@@ -1,0 +1,93 @@
+"""GPU parity tests of the batched NR3 path against the oracle (dense normal
+equations, as the reference) and the golden vectors.  Bar: 1e-9 relative on
+complex bus voltages, identical Newton iteration counts."""
+import numpy as np
+import pytest
+
+from helpers import ZIPS, LINES_ONLY, feeder_path, load_model, snapshots, scenarios, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _nr3(feeder, zname='test_zip'):
+    from gigpower_b200.solution_nr3 import SolutionNR3
+    return SolutionNR3(feeder_path(feeder), zip_v=np.asarray(ZIPS[zname]))
+
+
+@pytest.mark.parametrize('zname', list(ZIPS))
+@pytest.mark.parametrize('feeder', LINES_ONLY)
+def test_snapshot_matches_reference(feeder, zname):
+    snap = snapshots()
+    s = _nr3(feeder, zname)
+    s.solve()
+    k = f'{feeder}/{zname}/NR3/'
+    assert s.itercount == int(snap[k + 'iterations'])
+    assert s.converged is True and s.iterations == 0          # reference quirks
+    assert s.XNR.shape == snap[k + 'XNR'].shape
+    assert rel_err(s.XNR, snap[k + 'XNR']) <= TOL
+    for p in ('V', 'I', 'sV', 'Vmag', 'Stx', 'Srx', 'i_Node'):
+        assert getattr(s, p).shape == snap[k + p].shape, p
+        assert rel_err(getattr(s, p), snap[k + p]) <= TOL, p
+    for p in s.SOLUTION_PARAMS:
+        rows, cols = s.get_data_frame(p, orient='rows'), s.get_data_frame(p, orient='cols')
+        assert not rows.empty and rows.shape[1] == 3 and cols.shape[0] == 3
+    assert list(s.get_V().index) == s.circuit.buses.all_names()
+
+
+@pytest.mark.parametrize('feeder', LINES_ONLY)
+def test_golden_scenarios(feeder):
+    sc = scenarios()
+    X = sc[feeder + '/NR3/XNR']
+    r = _nr3(feeder).solve_batch(load_mult=sc[feeder + '/mult'][:len(X)], outputs=('X',))
+    assert list(r.iterations) == list(sc[feeder + '/NR3/iterations'])
+    assert rel_err(r.XNR, X) <= TOL
+
+
+@pytest.mark.parametrize('feeder,S,seed', [('IEEE_13_Bus_allwye_noxfm_noreg', 200, 1),
+                                            ('IEEE_34_Bus_allwye_noxfm_noreg', 48, 2),
+                                            ('IEEE_37_Bus_allwye_noxfm_noreg', 48, 3)])
+def test_random_batch_matches_dense_oracle(feeder, S, seed):
+    from oracle.gp_oracle import NR3Oracle
+    rng = np.random.Generator(np.random.PCG64(seed))
+    o = NR3Oracle(load_model(feeder), ZIPS['test_zip'])
+    mult = rng.uniform(0.5, 1.5, size=(S, len(o.c.load_names)))
+    want = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+    r = _nr3(feeder).solve_batch(load_mult=mult,
+                                 outputs=('X', 'V', 'I', 'Vmag', 'sV', 'i_Node', 'Stx', 'Srx', 'loss'))
+    assert np.array_equal(r.iterations, want['iterations'])
+    assert rel_err(r.XNR, want['XNR']) <= TOL
+    for p in ('V', 'I', 'Vmag', 'sV', 'i_Node', 'Stx', 'Srx'):
+        assert rel_err(getattr(r, p), want[p]) <= TOL, p
+    assert rel_err(r.losses, (want['Stx'] - want['Srx']).sum(axis=(1, 2))) <= TOL
+
+
+@pytest.mark.parametrize('feeder,S,seed', [('IEEE_13_Bus_allwye_noxfm_noreg', 20000, 11),
+                                            ('IEEE_37_Bus_allwye_noxfm_noreg', 16384, 37)])
+def test_large_batch_matches_tree_oracle(feeder, S, seed):
+    """Config C3 size (37-bus, 16,384 scenarios): checked against the NumPy tree
+    elimination, which is itself pinned to the dense oracle on CPU."""
+    from oracle.nr3_tree import NR3TreeOracle
+    rng = np.random.Generator(np.random.PCG64(seed))
+    o = NR3TreeOracle(load_model(feeder), ZIPS['test_zip'])
+    mult = rng.uniform(0.5, 1.5, size=(S, len(o.c.load_names)))
+    want = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+    r = _nr3(feeder).solve_batch(load_mult=mult, outputs=('X',))
+    assert np.array_equal(r.iterations, want['iterations'])
+    assert r.converged.all()
+    assert rel_err(r.XNR, want['XNR']) <= TOL
+
+
+def test_edge_cases_and_zero_load():
+    from oracle.gp_oracle import NR3Oracle
+    feeder = LINES_ONLY[0]
+    o = NR3Oracle(load_model(feeder), ZIPS['test_zip'])
+    s = _nr3(feeder)
+    nload = len(o.c.load_names)
+    assert s.solve_batch(load_mult=np.zeros((0, nload))).S == 0
+    for S in (1, 65, 130):
+        mult = np.linspace(0.0, 1.6, S * nload).reshape(S, nload)
+        want = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+        r = s.solve_batch(load_mult=mult, outputs=('X',))
+        assert np.array_equal(r.iterations, want['iterations'])
+        assert rel_err(r.XNR, want['XNR']) <= TOL

@@ -119,3 +119,21 @@ def test_known_answers_appendix_b():
     want = np.array([0.9186175866955602 - 0.10464543644259171j, -0.5360926994597318 - 0.8502195082139851j,
                      -0.3880887632230724 + 0.8105221042526009j])
     assert np.abs(rn['V'][0, :, b] - want).max() < 1e-13
+
+
+@pytest.mark.parametrize('zname', list(ZIPS))
+@pytest.mark.parametrize('feeder', LINES_ONLY)
+def test_tree_elimination_oracle_equals_dense_oracle(feeder, zname):
+    """oracle/nr3_tree.py (the algorithm the CUDA kernel implements) against the
+    literal restatement (dense J, inv(J'J) J' F) and the reference's golden X."""
+    from oracle.nr3_tree import NR3TreeOracle
+    model = load_model(feeder)
+    o, t = NR3Oracle(model, ZIPS[zname]), NR3TreeOracle(model, ZIPS[zname])
+    rng = np.random.Generator(np.random.PCG64(5))
+    mult = rng.uniform(0.4, 1.6, size=(5, len(o.c.load_names)))
+    mult[0] = 1.0
+    spu = o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult)
+    a, b = o.solve(spu), t.solve(spu)
+    assert np.array_equal(a['iterations'], b['iterations'])
+    assert np.abs(a['XNR'] - b['XNR']).max() <= 1e-12
+    assert np.abs(b['XNR'][0] - snapshots()[f'{feeder}/{zname}/NR3/XNR'][:, 0]).max() <= 1e-12
