@@ -123,6 +123,9 @@ class CpuPool:
     def __init__(self, cores=None):
         import multiprocessing as mp
         self.cores = cores or (os.cpu_count() or 1)
+        # one BLAS thread per worker: the workers inherit the environment at spawn
+        for var in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'NUMEXPR_NUM_THREADS'):
+            os.environ[var] = '1'
         self.pool = mp.get_context('spawn').Pool(self.cores)
 
     def step(self, feeder, solver, mult, n_per_proc):
@@ -153,7 +156,7 @@ def run_reference(args, wl):
     mult = rng.uniform(lo, hi, size=(S, c.loads.num_elements))
     pool = CpuPool()
     cores = pool.cores
-    n_per = 1024 if solver == 'fbs' else 8
+    n_per = 1024 if solver == 'fbs' else 4
     for _ in range(max(args.warmup, 1)):
         pool.step(feeder, solver, mult, max(n_per // 8, 1))
     t0 = time.perf_counter()
@@ -208,8 +211,6 @@ def run_ours(args, wl):
     spu_h = torch.from_numpy(rows).pin_memory()
     spu_d = spu_h.to(dev)
     c128, f64, i32 = torch.complex128, torch.float64, torch.int32
-    V = torch.empty((t.n_vrows, ld), dtype=c128, device=dev)
-    I = torch.empty((max(t.n_irows, 1), ld), dtype=c128, device=dev)
     Vmag = torch.empty((t.n_vrows, ld), dtype=f64, device=dev)
     loss = torch.empty(S, dtype=c128, device=dev)
     iters = torch.empty(S, dtype=i32, device=dev)
@@ -220,16 +221,33 @@ def run_ours(args, wl):
         loss_all = torch.empty((world, S), dtype=c128, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     stream = torch.cuda.current_stream()
-    tol, maxiter = sol.tolerance, sol.maxiter
+    maxiter = sol.maxiter
+    if solver == 'fbs':
+        V = torch.empty((t.n_vrows, ld), dtype=c128, device=dev)
+        I = torch.empty((max(t.n_irows, 1), ld), dtype=c128, device=dev)
+        tol = sol.tolerance
 
-    def solve_kernel():
-        _cabi.check(_cabi.gp_fbs_solve_batch(h, S, ld, spu_d.data_ptr(), V.data_ptr(), I.data_ptr(),
-                                             iters.data_ptr(), status.data_ptr(), diff.data_ptr(),
-                                             tol, maxiter, stream.cuda_stream))
+        def solve_kernel():
+            _cabi.check(_cabi.gp_fbs_solve_batch(h, S, ld, spu_d.data_ptr(), V.data_ptr(), I.data_ptr(),
+                                                 iters.data_ptr(), status.data_ptr(), diff.data_ptr(),
+                                                 tol, maxiter, stream.cuda_stream))
 
-    def post_kernel():
-        _cabi.check(_cabi.gp_fbs_post(h, S, ld, spu_d.data_ptr(), V.data_ptr(), I.data_ptr(), None,
-                                      Vmag.data_ptr(), None, None, loss.data_ptr(), stream.cuda_stream))
+        def post_kernel():
+            _cabi.check(_cabi.gp_fbs_post(h, S, ld, spu_d.data_ptr(), V.data_ptr(), I.data_ptr(), None,
+                                          Vmag.data_ptr(), None, None, loss.data_ptr(), stream.cuda_stream))
+    else:
+        X = torch.empty((t.n_vrows + t.n_irows, ld), dtype=c128, device=dev)
+        wbytes = int(_cabi.gp_nr3_workspace_bytes(h, ld))
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+
+        def solve_kernel():
+            _cabi.check(_cabi.gp_nr3_solve_batch(h, S, ld, spu_d.data_ptr(), X.data_ptr(), iters.data_ptr(),
+                                                 status.data_ptr(), diff.data_ptr(), work.data_ptr(), wbytes,
+                                                 maxiter, stream.cuda_stream))
+
+        def post_kernel():
+            _cabi.check(_cabi.gp_nr3_map_output(h, S, ld, spu_d.data_ptr(), X.data_ptr(), None, None, None, None,
+                                                None, None, Vmag.data_ptr(), loss.data_ptr(), stream.cuda_stream))
 
     def step():
         solve_kernel()
@@ -281,28 +299,57 @@ def run_ours(args, wl):
     its = iters.cpu().numpy().astype(np.int64)
     assert (status.cpu().numpy() == 0).all(), 'bench scenarios must all converge'
 
-    # ---- end to end through the host-buffer C-ABI (pinned host memory both ways) ---------
-    V_h = torch.empty((t.n_vrows, ld), dtype=c128).pin_memory()
-    loss_h = torch.empty(S, dtype=c128).pin_memory()
+    # ---- end to end: host buffers in, results out, copies inside the timed region -----------
     e2e_steps = max(3, min(args.steps, 10))
-    sol.solve_batch_host(spu_h, V_h, None, None, loss_h)      # warm-up (allocates staging)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        it_h, st_h, df_h = sol.solve_batch_host(spu_h, V_h, None, None, loss_h)
-    torch.cuda.synchronize()
+    if solver == 'fbs':
+        V_h = torch.empty((t.n_vrows, ld), dtype=c128).pin_memory()
+        loss_h = torch.empty(S, dtype=c128).pin_memory()
+        sol.solve_batch_host(spu_h, V_h, None, None, loss_h)      # warm-up (allocates staging)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            it_h, st_h, df_h = sol.solve_batch_host(spu_h, V_h, None, None, loss_h)
+        torch.cuda.synchronize()
+        e2e_api = 'gp_fbs_solve_batch_host (pinned host buffers; returns V, losses, iterations, status)'
+        d2h = int(V_h.numel() * 16 + loss_h.numel() * 16 + S * (4 + 4 + 8))
+    else:
+        X_h = torch.empty((t.n_vrows + t.n_irows, ld), dtype=c128).pin_memory()
+        it_h = torch.empty(S, dtype=i32).pin_memory()
+
+        def e2e_step():
+            spu_d.copy_(spu_h, non_blocking=True)
+            solve_kernel()
+            X_h.copy_(X, non_blocking=True)
+            it_h.copy_(iters, non_blocking=True)
+            stream.synchronize()
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e2e_api = 'pinned spu -> device, gp_nr3_solve_batch, X and iterations -> pinned host'
+        d2h = int(X_h.numel() * 16 + S * 4)
     e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=f64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = world * S / float(e2e_t.item())
     h2d = int(spu_h.numel() * 16)
-    d2h = int(V_h.numel() * 16 + loss_h.numel() * 16 + S * (4 + 4 + 8))
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         pk, pk_kind = peaks()
-        per_it = 16 * (2 * t.n_irows + 3 * t.n_vrows + t.n_srows)
-        once = 16 * (t.n_srows + t.n_vrows + t.n_irows)
+        if solver == 'fbs':
+            # per sweep read I, write V | read V, read spu, write I, write V
+            per_it = 16 * (2 * t.n_irows + 3 * t.n_vrows + t.n_srows)
+            once = 16 * (t.n_srows + t.n_vrows + t.n_irows)
+            kname = 'fbs_solve_kernel'
+        else:
+            # per Newton iteration: X read+write, spu read, dV write+read, fronts (Y, a, r1) write+read
+            nph = (t.bus_vrow >= 0).sum(axis=1)
+            fronts = int((8 * ((2 * nph) ** 2 + 4 * nph)).sum())
+            per_it = 2 * 16 * (t.n_vrows + t.n_irows) + 16 * t.n_srows + 2 * 16 * t.n_vrows + 2 * fronts
+            once = 16 * (t.n_vrows + t.n_irows)
+            kname = 'nr3_solve_kernel'
         alg_bytes = float(its.sum()) * per_it + S * once            # solve kernel, per launch
         solve_ms = float(np.mean(ms_solve))
         achieved = alg_bytes / (solve_ms * 1e-3) / 1e9
@@ -319,9 +366,9 @@ def run_ours(args, wl):
                        'parallelism': f'scenario-sharded x{world}, final NCCL all-gather of |V| and losses'},
             'e2e': {'value': e2e_value, 'unit': 'solves/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
-                    'api': 'gp_fbs_solve_batch_host (pinned host buffers; returns V, losses, iterations, status)'},
+                    'api': e2e_api},
             'gpu_launches': int(launches),
-            'roofline': {'bound': 'hbm', 'kernel': 'fbs_solve_kernel', 'achieved': achieved,
+            'roofline': {'bound': 'hbm', 'kernel': kname, 'achieved': achieved,
                          'peak': pk['hbm_gbs'], 'peak_kind': pk_kind, 'unit': 'GB/s',
                          'frac': achieved / pk['hbm_gbs'], 'traffic': None,
                          'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': solve_ms,
@@ -330,7 +377,7 @@ def run_ours(args, wl):
         }
         if world == 1 and not args.no_cpu:
             pool = CpuPool()
-            n_per = 1024 if solver == 'fbs' else 8
+            n_per = 1024 if solver == 'fbs' else 4
             pool.step(feeder, solver, mult, max(n_per // 8, 1))          # warm the workers
             n, wall, reps = 0, 0.0, 0
             while wall < 10.0 and reps < 50:

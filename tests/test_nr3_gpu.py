@@ -32,7 +32,8 @@ def test_snapshot_matches_reference(feeder, zname):
     for p in s.SOLUTION_PARAMS:
         rows, cols = s.get_data_frame(p, orient='rows'), s.get_data_frame(p, orient='cols')
         assert not rows.empty and rows.shape[1] == 3 and cols.shape[0] == 3
-    assert list(s.get_V().index) == s.circuit.buses.all_names()
+    assert list(s.get_V('rows').index) == s.circuit.buses.all_names()
+    assert list(s.get_V().index) == ['A', 'B', 'C']          # NR3 defaults to orient='cols' (:30)
 
 
 @pytest.mark.parametrize('feeder', LINES_ONLY)
