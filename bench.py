@@ -28,12 +28,19 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 FEEDER_DIR = os.path.join(REPO, 'tests', 'golden', 'feeders')
+AUTHORED_DIR = os.path.join(REPO, 'gigpower_b200', 'feeders')
 WORKLOADS = {
     # name: (feeder file, solver, scenarios per GPU, seed, multiplier range, description)
     'c2': ('IEEE_13_Bus_allwye_noxfm_noreg.json', 'fbs', 65536, 13, (0.5, 1.5),
            'C2: IEEE 13-bus FBS, 65,536 load-multiplier scenarios U(0.5,1.5), seed 13'),
     'c3': ('IEEE_37_Bus_allwye_noxfm_noreg.json', 'nr3', 16384, 37, (0.5, 1.5),
            'C3: IEEE 37-bus NR3, 16,384 load-multiplier scenarios U(0.5,1.5), seed 37'),
+    'c4': ('ieee123_allwye_noxfm_noreg.dss', 'fbs', 140160, 123, 'der',
+           'C4: IEEE 123-bus (reconstruction) FBS, 8,760 h x 128 DER scenarios = 1,121,280, 1/8 (140,160) per GPU'),
+    'c4nr3': ('ieee123_allwye_noxfm_noreg.dss', 'nr3', 17520, 123, 'der',
+              'C4: IEEE 123-bus (reconstruction) NR3, fixed 1/8 sub-sample of the 8,760 h x 128 DER set: 17,520 per GPU'),
+    'c5': ('synth2500_radial.dss', 'fbs', 131072, 2500, (0.3, 0.9),
+           'C5: synthetic 2,541-bus radial FBS, 2^20 scenarios U(0.3,0.9), 1/8 (131,072) per GPU'),
     'fbs37': ('IEEE_37_Bus_allwye_noxfm_noreg.json', 'fbs', 65536, 37, (0.5, 1.5),
               'IEEE 37-bus FBS, 65,536 scenarios'),
     'fbs34': ('IEEE_34_Bus_allwye_noxfm_noreg.json', 'fbs', 65536, 34, (0.5, 1.3),
@@ -94,26 +101,73 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def make_scenarios(sol, S, seed, lo, hi):
-    """Synthetic scenario batch: per-load multipliers -> packed spu rows [n_srows, S]."""
+def feeder_file(name):
+    p = os.path.join(FEEDER_DIR, name)
+    return p if os.path.exists(p) else os.path.join(AUTHORED_DIR, name)
+
+
+def make_multipliers(n_loads, S, seed, spec, first=0):
+    """Per-load multipliers [S, n_loads] of scenarios first..first+S of the workload."""
+    if spec == 'der':
+        raise ValueError('DER workloads are generated as spu rows')
     rng = np.random.Generator(np.random.PCG64(seed))
-    mult = rng.uniform(lo, hi, size=(S, sol.circuit.loads.num_elements))
-    return np.ascontiguousarray(sol.load_weights() @ mult.T), mult
+    return rng.uniform(spec[0], spec[1], size=(S, n_loads))
+
+
+def make_der_rows(W0, S, first):
+    """scenario index = d * 8760 + h.  Hour multiplier m_h (seed 123),
+    PV at a random 10-40 % of the loaded bus-phases per DER scenario d (seed 1230 + d),
+    penetration pen_d ~ U(0, 0.8), net spu = m_h * S_load - pen_d * pv(h) * P_load."""
+    H, D = 8760, 128
+    h_all = np.arange(H)
+    rng = np.random.Generator(np.random.PCG64(123))
+    m_h = np.clip(0.6 + 0.25 * np.sin(2 * np.pi * ((h_all % 24) - 9) / 24) + 0.1 * np.sin(2 * np.pi * h_all / H)
+                  + rng.normal(0, 0.02, H), 0.3, 1.2)
+    pv_h = np.maximum(0.0, np.sin(np.pi * ((h_all % 24) - 6) / 12))
+    idx = (first + np.arange(S)) % (H * D)
+    d, h = idx // H, idx % H
+    nrow = W0.shape[0]
+    mask = np.zeros((D, nrow))
+    pen = np.zeros(D)
+    for dd in np.unique(d):
+        r = np.random.Generator(np.random.PCG64(1230 + int(dd)))
+        frac = r.uniform(0.1, 0.4)
+        mask[dd, r.permutation(nrow)[:max(1, int(round(frac * nrow)))]] = 1.0
+        pen[dd] = r.uniform(0.0, 0.8)
+    rows = W0[:, None] * m_h[h][None, :] - (W0.real[:, None] * mask[d].T) * (pen[d] * pv_h[h])[None, :]
+    return np.ascontiguousarray(rows)
+
+
+def make_scenarios(sol, S, seed, spec, first=0):
+    """Synthetic scenario batch -> packed spu rows [n_srows, S] (+ multipliers when they exist)."""
+    W = sol.load_weights()
+    if spec == 'der':
+        return make_der_rows(W.sum(axis=1), S, first), None
+    mult = make_multipliers(sol.circuit.loads.num_elements, S, seed, spec)
+    return np.ascontiguousarray(W @ mult.T), mult
 
 
 # --------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port on the host cores
 # --------------------------------------------------------------------------
 def _cpu_worker(args):
-    feeder, solver, mult = args
-    os.environ['OMP_NUM_THREADS'] = '1'
+    feeder, solver, rows = args
     from gigpower_b200.dss_reader import read_dss
     from oracle.gp_oracle import FBSOracle, NR3Oracle
-    model = read_dss(os.path.join(FEEDER_DIR, feeder))
-    o = FBSOracle(model) if solver == 'fbs' else NR3Oracle(model)
+    from oracle.nr3_tree import NR3TreeOracle
+    model = read_dss(feeder_file(feeder))
+    if solver == 'fbs':
+        o = FBSOracle(model)
+    else:   # the literal dense restatement up to N ~ 500 unknowns, the tree elimination above that
+        o = NR3Oracle(model) if len(model.bus_names) <= 45 else NR3TreeOracle(model)
     c = o.c
+    # packed rows -> the reference's [S, nb, 3] spu matrices
+    lmask = c.zip_mask * c.bus_pm
+    b, p = np.nonzero(lmask)
+    spu = np.zeros((rows.shape[1], c.nb, 3), dtype=complex)
+    spu[:, b, p] = rows.T
     t0 = time.perf_counter()
-    r = o.solve(c.spu_matrix(c.load_kw * mult, c.load_kvar * mult))
+    r = o.solve(spu)
     return time.perf_counter() - t0, int(r['iterations'].sum())
 
 
@@ -128,49 +182,67 @@ class CpuPool:
             os.environ[var] = '1'
         self.pool = mp.get_context('spawn').Pool(self.cores)
 
-    def step(self, feeder, solver, mult, n_per_proc):
-        """Every core solves `n_per_proc` scenarios of the workload; returns
-        (scenarios solved, wall seconds)."""
+    def step(self, feeder, solver, rows, n_per_proc):
+        """Every core solves `n_per_proc` scenarios of the workload (columns of the packed
+        spu rows); returns (scenarios solved, wall seconds)."""
         jobs = []
+        S = rows.shape[1]
         for i in range(self.cores):
-            lo = (i * n_per_proc) % max(len(mult) - n_per_proc + 1, 1)
-            jobs.append((feeder, solver, mult[lo:lo + n_per_proc]))
+            lo = (i * n_per_proc) % max(S - n_per_proc + 1, 1)
+            jobs.append((feeder, solver, np.ascontiguousarray(rows[:, lo:lo + n_per_proc])))
         t0 = time.perf_counter()
         self.pool.map(_cpu_worker, jobs)
-        return sum(len(j[2]) for j in jobs), time.perf_counter() - t0
+        return sum(j[2].shape[1] for j in jobs), time.perf_counter() - t0
 
     def close(self):
         self.pool.close()
         self.pool.join()
 
 
+def cpu_sample_size(solver, nb):
+    """Scenarios per core per step, sized so that a step of the port takes ~0.2-2 s."""
+    if solver == 'fbs':
+        return max(16, min(1024, 15 * 1024 // nb))
+    return 4 if nb <= 45 else max(2, min(64, 126 * 64 // nb))
+
+
 def run_reference(args, wl):
-    feeder, solver, S, seed, (lo, hi), desc = wl
+    feeder, solver, S, seed, spec, desc = wl
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    from gigpower_b200.solution_fbs import SolutionFBS
     from gigpower_b200.dss_reader import read_dss
     from gigpower_b200.circuit import Circuit
-    c = Circuit(read_dss(os.path.join(FEEDER_DIR, feeder)))
-    rng = np.random.Generator(np.random.PCG64(seed))
-    mult = rng.uniform(lo, hi, size=(S, c.loads.num_elements))
+    from gigpower_b200.flatten import flatten_fbs
+
+    class _Host:        # host-only view of the feeder: load weights without touching the GPU
+        def __init__(self, path):
+            self.circuit = Circuit(read_dss(path))
+            self.tables = flatten_fbs(self.circuit)
+        load_weights = SolutionFBS.load_weights
+    sol = _Host(feeder_file(feeder))
+    nb = sol.circuit.buses.num_elements
+    rows, mult = make_scenarios(sol, min(S, 16384), seed, spec)
     pool = CpuPool()
     cores = pool.cores
-    n_per = 1024 if solver == 'fbs' else 4
+    n_per = cpu_sample_size(solver, nb)
     for _ in range(max(args.warmup, 1)):
-        pool.step(feeder, solver, mult, max(n_per // 8, 1))
+        pool.step(feeder, solver, rows, max(n_per // 8, 1))
     t0 = time.perf_counter()
-    tot = 0
+    tot, done = 0, 0
     for _ in range(args.steps):
-        n, _w = pool.step(feeder, solver, mult, n_per)
-        tot += n
+        n, _w = pool.step(feeder, solver, rows, n_per)
+        tot, done = tot + n, done + 1
+        if time.perf_counter() - t0 > 150.0:      # keep the whole arm within a few minutes
+            break
     wall = time.perf_counter() - t0
     pool.close()
     value = tot / wall
     line = {
         'impl': 'reference', 'metric': 'power-flow solves/sec', 'value': value, 'unit': 'solves/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * wall / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'n_gpus': args.gpus, 'steps': done, 'warmup': max(args.warmup, 1),
+        'ms_per_step': 1e3 * wall / done, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': desc, 'solver': solver},
         'cpu_baseline': {'value': value, 'unit': 'solves/s', 'cores': cores, 'kind': 'port',
@@ -189,7 +261,7 @@ def run_ours(args, wl):
     import torch
     import torch.distributed as dist
     from gigpower_b200 import _cabi
-    feeder, solver, S, seed, (lo, hi), desc = wl
+    feeder, solver, S, seed, spec, desc = wl
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -199,11 +271,11 @@ def run_ours(args, wl):
         dist.init_process_group('nccl', device_id=dev)
     if solver == 'fbs':
         from gigpower_b200.solution_fbs import SolutionFBS
-        sol = SolutionFBS(os.path.join(FEEDER_DIR, feeder), device=local)
+        sol = SolutionFBS(feeder_file(feeder), device=local)
     else:
         from gigpower_b200.solution_nr3 import SolutionNR3
-        sol = SolutionNR3(os.path.join(FEEDER_DIR, feeder), device=local)
-    rows, mult = make_scenarios(sol, S, seed + 1000 * rank, lo, hi)
+        sol = SolutionNR3(feeder_file(feeder), device=local)
+    rows, mult = make_scenarios(sol, S, seed + 1000 * rank, spec, first=rank * S)
     sol._dev()
     t = sol.tables
     h = sol._feeder.handle
@@ -377,11 +449,11 @@ def run_ours(args, wl):
         }
         if world == 1 and not args.no_cpu:
             pool = CpuPool()
-            n_per = 1024 if solver == 'fbs' else 4
-            pool.step(feeder, solver, mult, max(n_per // 8, 1))          # warm the workers
+            n_per = cpu_sample_size(solver, sol.circuit.buses.num_elements)
+            pool.step(feeder, solver, rows, max(n_per // 8, 1))          # warm the workers
             n, wall, reps = 0, 0.0, 0
             while wall < 10.0 and reps < 50:
-                dn, dw = pool.step(feeder, solver, mult, n_per)
+                dn, dw = pool.step(feeder, solver, rows, n_per)
                 n, wall, reps = n + dn, wall + dw, reps + 1
             pool.close()
             line['cpu_baseline'] = {

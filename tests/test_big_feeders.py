@@ -1,0 +1,68 @@
+"""The two authored feeders (IEEE-123 reconstruction, synthetic 2,500-node): the
+.dss reader on real .dss text, oracle cross-checks on CPU, CUDA parity on GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from gigpower_b200.dss_reader import read_dss
+from gigpower_b200.circuit import Circuit
+from gigpower_b200.flatten import flatten_fbs, flatten_nr3
+from helpers import REPO, ZIPS, rel_err
+
+FEEDERS = os.path.join(REPO, 'gigpower_b200', 'feeders')
+F123 = os.path.join(FEEDERS, 'ieee123_allwye_noxfm_noreg.dss')
+F2500 = os.path.join(FEEDERS, 'synth2500_radial.dss')
+
+
+def test_reader_on_authored_dss():
+    m = read_dss(F123)
+    assert m.bus_names[0] == '150' and len(m.bus_names) == 126 and len(m.lines) == 125
+    assert len(m.loads) == 91 and len(m.capacitors) == 4
+    assert abs(sum(ld.kw for ld in m.loads) - 3490.0) < 1e-9          # IEEE 123 total spot load
+    assert m.bus_nodes['9'] == [1] and m.bus_nodes['26'] == [1, 3] and m.bus_nodes['150'] == [1, 2, 3]
+    assert abs(m.bus_kvbase['33'] - 4.16 / np.sqrt(3)) < 1e-15
+    sw = [ln for ln in m.lines if ln.is_switch]
+    assert len(sw) == 7 and all(ln.length == 0.001 for ln in sw)
+    t = flatten_fbs(Circuit(m))
+    assert (t.n_vrows, t.n_irows, t.n_srows) == (265, 262, 96)
+    m2 = read_dss(F2500)
+    assert len(m2.bus_names) == 2541 and len(m2.lines) == 2540
+    assert flatten_nr3(Circuit(m2)).N == 6 * (2541 + 2540)
+
+
+def test_tree_oracle_equals_dense_oracle_on_123():
+    from oracle.gp_oracle import NR3Oracle
+    from oracle.nr3_tree import NR3TreeOracle
+    m = read_dss(F123)
+    a, b = NR3Oracle(m).solve(), NR3TreeOracle(m).solve()
+    assert np.array_equal(a['iterations'], b['iterations'])
+    assert np.abs(a['XNR'] - b['XNR']).max() <= 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('path,S,seed,lo,hi', [(F123, 1500, 123, 0.3, 1.2), (F2500, 200, 2500, 0.3, 0.9)])
+def test_fbs_big_feeder_matches_oracle(path, S, seed, lo, hi):
+    from gigpower_b200.solution_fbs import SolutionFBS
+    from oracle.gp_oracle import FBSOracle
+    o = FBSOracle(read_dss(path), ZIPS['test_zip'])
+    mult = np.random.Generator(np.random.PCG64(seed)).uniform(lo, hi, size=(S, len(o.c.load_names)))
+    want = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+    r = SolutionFBS(path, zip_v=np.asarray(ZIPS['test_zip'])).solve_batch(load_mult=mult, outputs=('V', 'I', 'Vmag', 'loss'))
+    assert np.array_equal(r.iterations, want['iterations'])
+    assert r.converged.all()
+    assert rel_err(r.V, want['V']) <= 1e-9 and rel_err(r.I, want['I']) <= 1e-9
+    assert rel_err(r.losses, (want['Stx'] - want['Srx']).sum(axis=(1, 2))) <= 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('path,S,seed,lo,hi', [(F123, 600, 123, 0.3, 1.2), (F2500, 96, 2500, 0.3, 0.9)])
+def test_nr3_big_feeder_matches_tree_oracle(path, S, seed, lo, hi):
+    from gigpower_b200.solution_nr3 import SolutionNR3
+    from oracle.nr3_tree import NR3TreeOracle
+    o = NR3TreeOracle(read_dss(path), ZIPS['test_zip'])
+    mult = np.random.Generator(np.random.PCG64(seed)).uniform(lo, hi, size=(S, len(o.c.load_names)))
+    want = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+    r = SolutionNR3(path, zip_v=np.asarray(ZIPS['test_zip'])).solve_batch(load_mult=mult, outputs=('X',))
+    assert np.array_equal(r.iterations, want['iterations'])
+    assert rel_err(r.XNR, want['XNR']) <= 1e-9
