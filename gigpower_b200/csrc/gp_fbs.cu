@@ -14,6 +14,8 @@
 // lanes read the same words (broadcast through L1/the read-only path).
 #include "gp_common.cuh"
 
+#include <algorithm>
+#include <functional>
 #include <new>
 #include <vector>
 
@@ -21,6 +23,7 @@ namespace gp {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+static bool g_force_sweep_kernel = false;   // gp_set_option("fbs_kernel", 0): the two-sweep kernel
 
 struct __align__(16) FbsStep {
     int bus_vrow[3];
@@ -57,6 +60,9 @@ struct FbsImpl {
     int* d_vrow_srow = nullptr;   // [n_vrows] spu row of each V row or -1
     double* d_vrow_cap = nullptr; // [n_vrows]
     FbsConst k;
+    // fused depth-first schedule (fbs_dfs_kernel): 2 events per step, or none if not applicable
+    int2* d_events = nullptr;
+    int n_events = 0, depth = 0;
     // host staging for gp_fbs_solve_batch_host
     static constexpr int NSTREAM = 4;
     cudaStream_t streams[NSTREAM] = {nullptr, nullptr, nullptr, nullptr};
@@ -253,6 +259,193 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int* __restrict__ chil
     status_out[s] = converged ? GP_ST_CONVERGED : ((diff != diff || isinf(diff)) ? GP_ST_NONFINITE : GP_ST_MAXITER);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Fused depth-first sweep.
+//
+// The reference runs a full forward sweep, then a full backward sweep.  Per scenario the
+// two can be fused into ONE depth-first walk of the tree without changing any value:
+// descending an edge is that edge's forward update (it needs only the parent's FORWARD
+// voltage and last iteration's edge current), ascending it is the bus's backward step
+// (load, current, parent-voltage rewrite), which needs the bus voltage after all its
+// children rewrote it and the children's new currents.  Children are visited latest-in-
+// topo-order first, so the per-phase overwrite of the parent voltage ends with the same
+// "winning child" (earliest in topo_order) as the reference's reversed(topo_order) loop.
+//
+// The walk keeps the path's forward voltage, rewritten voltage and child-current sum in
+// registers for the current bus and in a per-thread stack (local memory, L1-resident)
+// for its ancestors.  HBM traffic per sweep drops from 16(2 P_l + 3 P_b + P_L) to
+// 16(2 P_l + P_b + P_L): I_old read, I_new written, spu read, final V written; the
+// voltage no longer round-trips between the sweeps and the dependent parent->child chain
+// runs through registers/L1 instead of L2.
+// ---------------------------------------------------------------------------------------
+struct PathState {
+    double2 Vf[3];   // forward voltage of the bus
+    double2 Vb[3];   // voltage as rewritten by the children processed so far
+    double2 Ia[3];   // sum of the new currents of those children
+};
+
+template <int BLOCK, int MAXD>
+__global__ void __launch_bounds__(BLOCK)
+fbs_dfs_kernel(const FbsStep* __restrict__ steps, const int2* __restrict__ events, int n_events,
+               FbsConst k, long long S, unsigned ldb, const char* __restrict__ spu, char* __restrict__ V,
+               char* __restrict__ I, int* __restrict__ iters_out, int* __restrict__ status_out,
+               double* __restrict__ diff_out, double tol, int maxiter) {
+    const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (s >= S) return;
+    const char* spu_s = spu + s * 16;
+    char* Vs = V + s * 16;
+    char* Is = I + s * 16;
+#define GP_ROW(base, row) (reinterpret_cast<double2*>((base) + (size_t)(unsigned)(row) * (size_t)ldb))
+#define GP_CROW(base, row) (reinterpret_cast<const double2*>((base) + (size_t)(unsigned)(row) * (size_t)ldb))
+    PathState stk[MAXD];
+    int it = 0;
+    double diff = -1.0;
+    bool converged = false;
+    while (!converged && it < maxiter) {
+        PathState cur;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            cur.Vf[p] = cur.Vb[p] = k.vref[p];                      // V[root] = Vref (:89)
+            cur.Ia[p] = make_double2(0.0, 0.0);
+        }
+        for (int e = 0; e < n_events; ++e) {
+            const int2 ev = __ldg(events + e);
+            const FbsStep* st = steps + ev.x;
+            const int L = ev.y >> 1;
+            const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
+            const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
+            const int brow[3] = {bv.x, bv.y, bv.z};
+            const int prow[3] = {pv.x, pv.y, pv.z};
+            const int kind = bv.w;
+            if ((ev.y & 1) == 0) {
+                // ---------------- descend: forward update of this edge (:162-184 / :138-160)
+                stk[L - 1] = cur;
+                double2 Vc[3];
+                if (kind == GP_EDGE_VR) {
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        const double g = __ldg(&st->gamma[p]);
+                        Vc[p] = (brow[p] >= 0) ? make_double2(g * cur.Vf[p].x, g * cur.Vf[p].y) : make_double2(0.0, 0.0);
+                    }
+                } else {
+                    const int4 er = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
+                    const int erow[3] = {er.x, er.y, er.z};
+                    double2 Il[3];
+#pragma unroll
+                    for (int p = 0; p < 3; ++p)
+                        Il[p] = (it > 0 && erow[p] >= 0) ? *GP_CROW(Is, erow[p]) : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        double2 v = make_double2(0.0, 0.0);
+                        if (brow[p] >= 0) {
+                            v = cur.Vf[p];
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                if (erow[q] < 0) continue;
+                                const double2 z = __ldg(&st->z[3 * p + q]);
+                                v.x -= z.x * Il[q].x - z.y * Il[q].y;
+                                v.y -= z.x * Il[q].y + z.y * Il[q].x;
+                            }
+                        }
+                        Vc[p] = v;
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    cur.Vf[p] = cur.Vb[p] = Vc[p];
+                    cur.Ia[p] = make_double2(0.0, 0.0);
+                }
+                continue;
+            }
+            // -------------------- ascend: backward step of this bus (:104-121)
+            PathState par = stk[L - 1];
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+                if (brow[p] >= 0) *GP_ROW(Vs, brow[p]) = cur.Vb[p];
+            if (kind == GP_EDGE_VR) {   // vr_current leaves Itx = 0; vr_backward :186-205
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const double g = __ldg(&st->gamma[p]);
+                    if (g != 0.0 && prow[p] >= 0) {
+                        const double ig = __ldg(&st->inv_gamma[p]);
+                        par.Vb[p] = make_double2(ig * cur.Vb[p].x, ig * cur.Vb[p].y);
+                    }
+                }
+                cur = par;
+                continue;
+            }
+            const int4 er = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
+            const int4 lv = __ldg(reinterpret_cast<const int4*>(st->load_srow));
+            const int erow[3] = {er.x, er.y, er.z};
+            const int lrow[3] = {lv.x, lv.y, lv.z};
+            double2 In[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                In[p] = make_double2(0.0, 0.0);
+                if (erow[p] < 0) continue;
+                double2 cu = cur.Ia[p];
+                if (brow[p] >= 0) {      // calc_sV (solution.py:177-220) + update_current (:256-288)
+                    const double2 v = cur.Vb[p];
+                    double a;
+                    const double a2 = cabs2(v, a);
+                    double2 sv = make_double2(0.0, 0.0);
+                    if (lrow[p] >= 0) {
+                        const double2 sp = *GP_CROW(spu_s, lrow[p]);
+                        const double f = k.aPQ + k.aI * a + k.aZ * a2;
+                        sv.x = sp.x * f;
+                        sv.y = sp.y * f;
+                    }
+                    sv.y -= __ldg(&st->cap[p]) * a2;
+                    if (v.x != 0.0 || v.y != 0.0) {
+                        const double inv = 1.0 / fma(v.x, v.x, v.y * v.y);
+                        cu.x += (sv.x * v.x + sv.y * v.y) * inv;
+                        cu.y -= (sv.y * v.x - sv.x * v.y) * inv;
+                    }
+                }
+                In[p] = make_double2(nan_to_num(cu.x), nan_to_num(cu.y));
+                *GP_ROW(Is, erow[p]) = In[p];
+                par.Ia[p].x += In[p].x;
+                par.Ia[p].y += In[p].y;
+            }
+            // update_voltage_backward (:207-232): phases of the child bus, masked by the parent
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                if (brow[p] < 0 || prow[p] < 0) continue;
+                double2 v = cur.Vb[p];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (erow[q] < 0) continue;
+                    const double2 z = __ldg(&st->z[3 * p + q]);
+                    v.x += z.x * In[q].x - z.y * In[q].y;
+                    v.y += z.x * In[q].y + z.y * In[q].x;
+                }
+                par.Vb[p] = v;
+            }
+            cur = par;
+        }
+        // ---- root: final voltage and convergence (:123-128) ---------------------------
+        ++it;
+        diff = 0.0;
+        bool nan = false;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            *GP_ROW(Vs, k.root_vrow[p]) = cur.Vb[p];
+            const double dx = cur.Vb[p].x - k.vref[p].x, dy = cur.Vb[p].y - k.vref[p].y;
+            const double d = sqrt(fma(dx, dx, dy * dy));
+            nan |= (d != d);
+            diff = fmax(diff, d);
+        }
+        if (nan) diff = __longlong_as_double(0x7ff8000000000000LL);
+        converged = diff <= tol;
+    }
+#undef GP_ROW
+#undef GP_CROW
+    iters_out[s] = it;
+    diff_out[s] = diff;
+    status_out[s] = converged ? GP_ST_CONVERGED : ((diff != diff || isinf(diff)) ? GP_ST_NONFINITE : GP_ST_MAXITER);
+}
+
 // Derived results: sV, |V| per V row; Stx/Srx per line row; loss per scenario.
 __global__ void fbs_post_rows_kernel(int n_vrows, const int* __restrict__ vrow_srow,
                                      const double* __restrict__ vrow_cap, FbsConst k, long long S,
@@ -324,6 +517,14 @@ extern "C" int gp_last_error(char* buf, size_t len) {
 }
 
 extern "C" int64_t gp_launch_count(void) { return g_launches.load(); }
+
+extern "C" int gp_set_option(const char* name, int value) {
+    if (name && strcmp(name, "fbs_kernel") == 0) {      // 1 = fused depth-first (default), 0 = two-sweep
+        g_force_sweep_kernel = (value == 0);
+        return GP_OK;
+    }
+    return fail(GP_EINVAL, "gp_set_option: unknown option");
+}
 
 extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
     if (!d || !out) return fail(GP_EINVAL, "gp_fbs_create: null argument");
@@ -397,12 +598,59 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
             lines[9 * l + 3 + p] = d->line_tx_vrow[3 * l + p];
             lines[9 * l + 6 + p] = d->line_rx_vrow[3 * l + p];
         }
+    // depth-first schedule for fbs_dfs_kernel: parent step of every step, children visited
+    // latest-in-topo-order first, {step, 2*level + ascend} events.
+    std::vector<int2> events;
+    {
+        std::vector<int> row_step((size_t)d->n_vrows, -2);
+        for (int p = 0; p < 3; ++p) row_step[d->root_vrow[p]] = -1;
+        for (int i = 0; i < d->n_steps; ++i)
+            for (int p = 0; p < 3; ++p)
+                if (steps[i].bus_vrow[p] >= 0) row_step[steps[i].bus_vrow[p]] = i;
+        std::vector<std::vector<int>> kids((size_t)d->n_steps + 1);   // index 0 = root
+        bool ok = true;
+        for (int i = 0; i < d->n_steps && ok; ++i) {
+            int par = -2;
+            for (int p = 0; p < 3; ++p)
+                if (steps[i].par_vrow[p] >= 0) par = row_step[steps[i].par_vrow[p]];
+            if (par < -1 || par >= i) ok = false;                     // parents come first in topo order
+            else kids[par + 1].push_back(i);
+            if (steps[i].kind == GP_EDGE_VR)                          // regulator must cover every bus phase
+                for (int p = 0; p < 3; ++p)
+                    if (steps[i].bus_vrow[p] >= 0 && steps[i].gamma[p] == 0.0) ok = false;
+        }
+        if (ok) {
+            struct Frame { int node, next; };
+            std::vector<Frame> stack;
+            stack.push_back({-1, 0});
+            int depth = 0;
+            for (auto& k : kids) std::sort(k.begin(), k.end(), std::greater<int>());
+            while (!stack.empty()) {
+                Frame& f = stack.back();
+                auto& ks = kids[f.node + 1];
+                if (f.next < (int)ks.size()) {
+                    const int c = ks[f.next++];
+                    const int level = (int)stack.size();
+                    depth = level > depth ? level : depth;
+                    events.push_back(make_int2(c, 2 * level));
+                    stack.push_back({c, 0});
+                } else {
+                    if (f.node >= 0) events.push_back(make_int2(f.node, 2 * ((int)stack.size() - 1) + 1));
+                    stack.pop_back();
+                }
+            }
+            im->depth = depth;
+            if ((int)events.size() != 2 * d->n_steps || depth > 64) events.clear();
+        }
+        im->n_events = (int)events.size();
+    }
     auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
         if (e != cudaSuccess) return e;
         return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
     };
     cudaError_t e = up((void**)&im->d_steps, steps.data(), steps.size() * sizeof(FbsStep));
+    if (e == cudaSuccess) e = up((void**)&im->d_events, events.data(), events.size() * sizeof(int2));
     if (e == cudaSuccess) e = up((void**)&im->d_child, d->child_irow, (size_t)d->n_child * 3 * sizeof(int));
     if (e == cudaSuccess) e = up((void**)&im->d_lines, lines.data(), lines.size() * sizeof(int));
     if (e == cudaSuccess) e = up((void**)&im->d_vrow_srow, vrow_srow.data(), vrow_srow.size() * sizeof(int));
@@ -429,6 +677,7 @@ extern "C" int gp_feeder_destroy(GpFeeder* f) {
         cudaFree(im->d_lines);
         cudaFree(im->d_vrow_srow);
         cudaFree(im->d_vrow_cap);
+        cudaFree(im->d_events);
         for (int i = 0; i < FbsImpl::NSTREAM; ++i) {
             if (im->d_stage[i]) cudaFree(im->d_stage[i]);
             if (im->streams[i]) cudaStreamDestroy(im->streams[i]);
@@ -460,9 +709,23 @@ extern "C" int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int BLOCK = 128;
     const unsigned gx = (unsigned)((S + BLOCK - 1) / BLOCK);
-    fbs_solve_kernel<BLOCK><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
-                                                  im->n_irows, S, ld, (const double2*)spu, (double2*)V,
-                                                  (double2*)I, iters, status, diff, tol, maxiter);
+    const bool dfs = im->n_events > 0 && ld * 16 < ((int64_t)1 << 32) && !g_force_sweep_kernel;
+    if (dfs) {
+        const unsigned ldb = (unsigned)(ld * 16);
+#define GP_DFS(D)                                                                                          \
+    fbs_dfs_kernel<BLOCK, D><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_events, im->n_events, im->k, S, ldb, \
+                                                   (const char*)spu, (char*)V, (char*)I, iters, status,    \
+                                                   diff, tol, maxiter)
+        if (im->depth <= 8) GP_DFS(8);
+        else if (im->depth <= 16) GP_DFS(16);
+        else if (im->depth <= 32) GP_DFS(32);
+        else GP_DFS(64);
+#undef GP_DFS
+    } else {
+        fbs_solve_kernel<BLOCK><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
+                                                      im->n_irows, S, ld, (const double2*)spu, (double2*)V,
+                                                      (double2*)I, iters, status, diff, tol, maxiter);
+    }
     count_launch();
     GP_CUDA(cudaGetLastError());
     return GP_OK;
@@ -497,6 +760,20 @@ extern "C" int gp_fbs_post(GpFeeder* f, int64_t S, int64_t ld, const double* spu
     return GP_OK;
 }
 
+// [rows] pieces of `width` bytes between pitched buffers: one contiguous copy when both
+// pitches equal the width, else one 1-D copy per row (never a pitched 2-D copy).
+static cudaError_t copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width,
+                             int rows, cudaMemcpyKind kind, cudaStream_t st) {
+    if (rows <= 0 || width == 0) return cudaSuccess;
+    if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * rows, kind, st);
+    for (int r = 0; r < rows; ++r) {
+        cudaError_t e = cudaMemcpyAsync((char*)dst + (size_t)r * dpitch, (const char*)src + (size_t)r * spitch,
+                                        width, kind, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 // Host-buffer path: chunk the batch, pipeline H2D / solve / D2H over NSTREAM streams.
 extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const double* spu_h,
                                        double* V_h, double* I_h, double* Vmag_h, double* loss_h,
@@ -512,10 +789,15 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
     // large as possible while still giving every stream work to overlap with the
     // other streams' copies: S/NSTREAM scenarios, at most ~64 MB of rows.
     const int64_t rows = (int64_t)im->n_vrows + im->n_irows + im->n_srows;
+    // Rows are copied one 1-D transfer each (pitched 2-D copies run at ~7 GB/s on this
+    // platform, 1-D pinned copies at ~55 GB/s), so a chunk should also keep a row piece
+    // >= 256 KB (16 Ki scenarios) when memory allows: cap 3 GiB of rows per stream.
     int64_t C = ((S + FbsImpl::NSTREAM - 1) / FbsImpl::NSTREAM + 127) / 128 * 128;
-    const int64_t cap = (((int64_t)64 << 20) / (rows * 16)) / 128 * 128;
+    if (C < 16384) C = 16384;
+    const int64_t cap = (((int64_t)3 << 30) / (rows * 16)) / 128 * 128;
     if (C > cap) C = cap;
     if (C < 1024) C = 1024;
+    if (C > S) C = (S + 127) / 128 * 128;
     // per-chunk device layout: spu | V | I | Vmag | loss | diff | iters | status
     const size_t b_spu = (size_t)im->n_srows * C * 16, b_V = (size_t)im->n_vrows * C * 16,
                  b_I = (size_t)im->n_irows * C * 16, b_mag = (size_t)im->n_vrows * C * 8,
@@ -544,8 +826,8 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
         int32_t* d_it = (int32_t*)(base + b_spu + b_V + b_I + b_mag + b_loss + b_diff);
         int32_t* d_st = d_it + C;
         if (im->n_srows > 0)
-            GP_CUDA(cudaMemcpy2DAsync(d_spu, (size_t)C * 16, spu_h + 2 * s0, (size_t)ld * 16, (size_t)n * 16,
-                                      im->n_srows, cudaMemcpyHostToDevice, st));
+            GP_CUDA(copy_rows(d_spu, (size_t)C * 16, spu_h + 2 * s0, (size_t)ld * 16, (size_t)n * 16,
+                              im->n_srows, cudaMemcpyHostToDevice, st));
         rc = gp_fbs_solve_batch(f, n, C, d_spu, d_V, d_I, d_it, d_st, d_diff, tol, maxiter, st);
         if (rc) return rc;
         if (Vmag_h || loss_h) {
@@ -554,14 +836,14 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
             if (rc) return rc;
         }
         if (V_h)
-            GP_CUDA(cudaMemcpy2DAsync(V_h + 2 * s0, (size_t)ld * 16, d_V, (size_t)C * 16, (size_t)n * 16,
-                                      im->n_vrows, cudaMemcpyDeviceToHost, st));
+            GP_CUDA(copy_rows(V_h + 2 * s0, (size_t)ld * 16, d_V, (size_t)C * 16, (size_t)n * 16,
+                              im->n_vrows, cudaMemcpyDeviceToHost, st));
         if (I_h && im->n_irows > 0)
-            GP_CUDA(cudaMemcpy2DAsync(I_h + 2 * s0, (size_t)ld * 16, d_I, (size_t)C * 16, (size_t)n * 16,
-                                      im->n_irows, cudaMemcpyDeviceToHost, st));
+            GP_CUDA(copy_rows(I_h + 2 * s0, (size_t)ld * 16, d_I, (size_t)C * 16, (size_t)n * 16,
+                              im->n_irows, cudaMemcpyDeviceToHost, st));
         if (Vmag_h)
-            GP_CUDA(cudaMemcpy2DAsync(Vmag_h + s0, (size_t)ld * 8, d_mag, (size_t)C * 8, (size_t)n * 8,
-                                      im->n_vrows, cudaMemcpyDeviceToHost, st));
+            GP_CUDA(copy_rows(Vmag_h + s0, (size_t)ld * 8, d_mag, (size_t)C * 8, (size_t)n * 8,
+                              im->n_vrows, cudaMemcpyDeviceToHost, st));
         if (loss_h) GP_CUDA(cudaMemcpyAsync(loss_h + 2 * s0, d_loss, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
         if (diff_h) GP_CUDA(cudaMemcpyAsync(diff_h + s0, d_diff, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
         if (iters_h) GP_CUDA(cudaMemcpyAsync(iters_h + s0, d_it, (size_t)n * 4, cudaMemcpyDeviceToHost, st));

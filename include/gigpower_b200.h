@@ -102,6 +102,13 @@ int gp_last_error(char* buf, size_t len);
 int64_t gp_launch_count(void);
 
 /*
+ * Process-wide switches.  "fbs_kernel": 1 (default) = fused depth-first sweep kernel when
+ * the feeder allows it, 0 = always the two-sweep kernel (same results; kept for feeders
+ * whose regulators do not cover every phase of the regulated bus, and for A/B timing).
+ */
+int gp_set_option(const char* name, int value);
+
+/*
  * Build the device-resident feeder tables.  Replaces SolutionFBS.__init__'s
  * topology setup (solution_fbs.py:27-37).  `device` is a CUDA ordinal.
  */

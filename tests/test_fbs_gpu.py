@@ -163,3 +163,26 @@ def test_errors_are_python_exceptions():
     with pytest.raises(GpError):
         _cabi.check(_cabi.gp_fbs_solve_batch(s._feeder.handle, 4, 2, None, None, None, None, None, None,
                                              1e-6, 100, None))
+
+
+@pytest.mark.parametrize('feeder', ['IEEE_13_Bus_allwye', 'IEEE_34_Bus_allwye_noxfm_noreg', 'IEEE_37_Bus_allwye'])
+def test_two_sweep_kernel_and_fused_dfs_kernel_agree(feeder):
+    """The library has two FBS kernels (fused depth-first walk = default, two-sweep =
+    general fallback); both must meet the oracle and each other."""
+    from gigpower_b200 import _cabi
+    rng = np.random.Generator(np.random.PCG64(21))
+    o = _oracle(feeder)
+    mult = rng.uniform(0.5, 1.5, size=(777, len(o.c.load_names)))
+    want = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+    s = _fbs(feeder)
+    res = {}
+    try:
+        for mode in (0, 1):
+            _cabi.check(_cabi.gp_set_option(b'fbs_kernel', mode))
+            res[mode] = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
+    finally:
+        _cabi.gp_set_option(b'fbs_kernel', 1)
+    for mode in (0, 1):
+        assert np.array_equal(res[mode].iterations, want['iterations']), mode
+        assert rel_err(res[mode].V, want['V']) <= TOL and rel_err(res[mode].I, want['I']) <= TOL, mode
+    assert rel_err(res[0].V, res[1].V) <= 1e-12
