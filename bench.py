@@ -277,6 +277,7 @@ def run_ours(args, wl):
         sol = SolutionNR3(feeder_file(feeder), device=local)
     rows, mult = make_scenarios(sol, S, seed + 1000 * rank, spec, first=rank * S)
     sol._dev()
+    _cabi.check(_cabi.gp_set_option(b'fbs_kernel', args.fbs_kernel))
     t = sol.tables
     h = sol._feeder.handle
     ld = S
@@ -431,6 +432,7 @@ def run_ours(args, wl):
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
             'config': {'workload': desc, 'solver': solver, 'scenarios_per_gpu': S,
+                       'fbs_kernel': 'fused-dfs' if args.fbs_kernel else 'two-sweep',
                        'rows': {'P_b': t.n_vrows, 'P_l': t.n_irows, 'P_L': t.n_srows},
                        'mean_iterations': float(its.mean()), 'max_iterations': int(its.max()),
                        'l2': 'flushed between steps (256 MiB write, untimed)',
@@ -473,6 +475,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--fbs-kernel', type=int, default=0, choices=[0, 1],
+                    help='0 = two-sweep FBS kernel (default), 1 = fused depth-first kernel (A/B timing)')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':

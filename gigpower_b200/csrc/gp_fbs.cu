@@ -23,7 +23,7 @@ namespace gp {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
-static bool g_force_sweep_kernel = false;   // gp_set_option("fbs_kernel", 0): the two-sweep kernel
+static bool g_force_sweep_kernel = true;    // gp_set_option("fbs_kernel", 1) selects the fused depth-first kernel
 
 struct __align__(16) FbsStep {
     int bus_vrow[3];
@@ -62,6 +62,7 @@ struct FbsImpl {
     FbsConst k;
     // fused depth-first schedule (fbs_dfs_kernel): 2 events per step, or none if not applicable
     int2* d_events = nullptr;
+    int4* d_evrows = nullptr;   // per event: the 3 rows to prefetch, .w = 1 for I rows (descend), 0 for spu rows
     int n_events = 0, depth = 0;
     // host staging for gp_fbs_solve_batch_host
     static constexpr int NSTREAM = 4;
@@ -279,6 +280,9 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int* __restrict__ chil
 // voltage no longer round-trips between the sweeps and the dependent parent->child chain
 // runs through registers/L1 instead of L2.
 // ---------------------------------------------------------------------------------------
+constexpr int EV_ASCEND = 1, EV_VF = 2, EV_VBIA = 4;   // event flags; level = flags >> 4
+constexpr int DFS_PF = 4;                               // prefetch distance in events
+
 struct PathState {
     double2 Vf[3];   // forward voltage of the bus
     double2 Vb[3];   // voltage as rewritten by the children processed so far
@@ -287,7 +291,8 @@ struct PathState {
 
 template <int BLOCK, int MAXD>
 __global__ void __launch_bounds__(BLOCK)
-fbs_dfs_kernel(const FbsStep* __restrict__ steps, const int2* __restrict__ events, int n_events,
+fbs_dfs_kernel(const FbsStep* __restrict__ steps, const int2* __restrict__ events,
+               const int4* __restrict__ evrows, int n_events,
                FbsConst k, long long S, unsigned ldb, const char* __restrict__ spu, char* __restrict__ V,
                char* __restrict__ I, int* __restrict__ iters_out, int* __restrict__ status_out,
                double* __restrict__ diff_out, double tol, int maxiter) {
@@ -299,9 +304,33 @@ fbs_dfs_kernel(const FbsStep* __restrict__ steps, const int2* __restrict__ event
 #define GP_ROW(base, row) (reinterpret_cast<double2*>((base) + (size_t)(unsigned)(row) * (size_t)ldb))
 #define GP_CROW(base, row) (reinterpret_cast<const double2*>((base) + (size_t)(unsigned)(row) * (size_t)ldb))
     PathState stk[MAXD];
+    // Per-thread ring of asynchronously prefetched operand rows (cp.async / LDGSTS), DFS_PF
+    // events ahead: the I_old rows of a descend, the spu rows of an ascend.  Neither depends on
+    // what the walk computes meanwhile, so the HBM latency of event e + DFS_PF overlaps the
+    // arithmetic of event e without holding registers.  Layout [slot][thread]: conflict-free.
+    __shared__ double2 ring[DFS_PF * 3][BLOCK];
+    const int tid = threadIdx.x;
     int it = 0;
     double diff = -1.0;
     bool converged = false;
+    auto issue = [&](int e) {
+        if (e < n_events) {
+            const int4 r = __ldg(evrows + e);
+            const int rows[3] = {r.x, r.y, r.z};
+            const char* base = r.w ? Is : spu_s;
+            if (!(r.w && it == 0)) {                 // flat start: I_old = 0, nothing to fetch
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+                    if (rows[p] >= 0) {
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[(e % DFS_PF) * 3 + p][tid]);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
+                                     "l"(base + (size_t)(unsigned)rows[p] * (size_t)ldb)
+                                     : "memory");
+                    }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     while (!converged && it < maxiter) {
         PathState cur;
 #pragma unroll
@@ -309,18 +338,37 @@ fbs_dfs_kernel(const FbsStep* __restrict__ steps, const int2* __restrict__ event
             cur.Vf[p] = cur.Vb[p] = k.vref[p];                      // V[root] = Vref (:89)
             cur.Ia[p] = make_double2(0.0, 0.0);
         }
+#pragma unroll
+        for (int e = 0; e < DFS_PF; ++e) issue(e);
         for (int e = 0; e < n_events; ++e) {
             const int2 ev = __ldg(events + e);
+            // operands of this event have landed; take them and reuse the slot for e + DFS_PF
+            asm volatile("cp.async.wait_group %0;" ::"n"(DFS_PF - 1) : "memory");
+            double2 D[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) D[p] = ring[(e % DFS_PF) * 3 + p][tid];
+            issue(e + DFS_PF);
             const FbsStep* st = steps + ev.x;
-            const int L = ev.y >> 1;
+            const int L = ev.y >> 4;
             const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
             const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
             const int brow[3] = {bv.x, bv.y, bv.z};
             const int prow[3] = {pv.x, pv.y, pv.z};
             const int kind = bv.w;
-            if ((ev.y & 1) == 0) {
+            if ((ev.y & EV_ASCEND) == 0) {
                 // ---------------- descend: forward update of this edge (:162-184 / :138-160)
-                stk[L - 1] = cur;
+                // Save only what a later event of the parent still needs (see build_events).
+                if (ev.y & EV_VF) {
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) stk[L - 1].Vf[p] = cur.Vf[p];
+                }
+                if (ev.y & EV_VBIA) {
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        stk[L - 1].Vb[p] = cur.Vb[p];
+                        stk[L - 1].Ia[p] = cur.Ia[p];
+                    }
+                }
                 double2 Vc[3];
                 if (kind == GP_EDGE_VR) {
 #pragma unroll
@@ -334,7 +382,7 @@ fbs_dfs_kernel(const FbsStep* __restrict__ steps, const int2* __restrict__ event
                     double2 Il[3];
 #pragma unroll
                     for (int p = 0; p < 3; ++p)
-                        Il[p] = (it > 0 && erow[p] >= 0) ? *GP_CROW(Is, erow[p]) : make_double2(0.0, 0.0);
+                        Il[p] = (it > 0 && erow[p] >= 0) ? D[p] : make_double2(0.0, 0.0);
 #pragma unroll
                     for (int p = 0; p < 3; ++p) {
                         double2 v = make_double2(0.0, 0.0);
@@ -359,7 +407,23 @@ fbs_dfs_kernel(const FbsStep* __restrict__ steps, const int2* __restrict__ event
                 continue;
             }
             // -------------------- ascend: backward step of this bus (:104-121)
-            PathState par = stk[L - 1];
+            PathState par;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) par.Vf[p] = par.Vb[p] = par.Ia[p] = make_double2(0.0, 0.0);
+            if (ev.y & EV_VF) {
+#pragma unroll
+                for (int p = 0; p < 3; ++p) par.Vf[p] = stk[L - 1].Vf[p];
+            }
+            if (ev.y & EV_VBIA) {
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    par.Vb[p] = stk[L - 1].Vb[p];
+                    par.Ia[p] = stk[L - 1].Ia[p];
+                }
+            } else {        // first child of its parent: nothing rewritten / summed yet
+#pragma unroll
+                for (int p = 0; p < 3; ++p) par.Vb[p] = par.Vf[p];
+            }
 #pragma unroll
             for (int p = 0; p < 3; ++p)
                 if (brow[p] >= 0) *GP_ROW(Vs, brow[p]) = cur.Vb[p];
@@ -391,7 +455,7 @@ fbs_dfs_kernel(const FbsStep* __restrict__ steps, const int2* __restrict__ event
                     const double a2 = cabs2(v, a);
                     double2 sv = make_double2(0.0, 0.0);
                     if (lrow[p] >= 0) {
-                        const double2 sp = *GP_CROW(spu_s, lrow[p]);
+                        const double2 sp = D[p];
                         const double f = k.aPQ + k.aI * a + k.aZ * a2;
                         sv.x = sp.x * f;
                         sv.y = sp.y * f;
@@ -519,7 +583,7 @@ extern "C" int gp_last_error(char* buf, size_t len) {
 extern "C" int64_t gp_launch_count(void) { return g_launches.load(); }
 
 extern "C" int gp_set_option(const char* name, int value) {
-    if (name && strcmp(name, "fbs_kernel") == 0) {      // 1 = fused depth-first (default), 0 = two-sweep
+    if (name && strcmp(name, "fbs_kernel") == 0) {      // 0 = two-sweep (default), 1 = fused depth-first
         g_force_sweep_kernel = (value == 0);
         return GP_OK;
     }
@@ -620,6 +684,17 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
                     if (steps[i].bus_vrow[p] >= 0 && steps[i].gamma[p] == 0.0) ok = false;
         }
         if (ok) {
+            // Flags: what the parent must keep across this child's subtree.
+            //  EV_VF   : the parent's forward voltage (another child still descends from it, or the
+            //            first child does not rewrite every phase of the parent);
+            //  EV_VBIA : the parent's rewritten voltage and current sum (not the first child).
+            // A single child carrying all phases of its parent (a chain) saves nothing.
+            auto covers = [&](int c) {        // child c rewrites every existing phase of its parent?
+                for (int p = 0; p < 3; ++p)
+                    if (steps[c].par_vrow[p] >= 0 && steps[c].bus_vrow[p] < 0) return false;
+                if (steps[c].kind == GP_EDGE_VR) return false;       // conservative
+                return true;
+            };
             struct Frame { int node, next; };
             std::vector<Frame> stack;
             stack.push_back({-1, 0});
@@ -628,14 +703,30 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
             while (!stack.empty()) {
                 Frame& f = stack.back();
                 auto& ks = kids[f.node + 1];
-                if (f.next < (int)ks.size()) {
-                    const int c = ks[f.next++];
+                const int m = (int)ks.size();
+                if (f.next < m) {
+                    const int j = f.next++;
+                    const int c = ks[j];
                     const int level = (int)stack.size();
                     depth = level > depth ? level : depth;
-                    events.push_back(make_int2(c, 2 * level));
+                    const bool need_vf = (m > 1) || !covers(c);
+                    int fl = 0;
+                    if (j == 0 && need_vf) fl |= EV_VF;
+                    if (j > 0) fl |= EV_VBIA;
+                    events.push_back(make_int2(c, (level << 4) | fl));
                     stack.push_back({c, 0});
                 } else {
-                    if (f.node >= 0) events.push_back(make_int2(f.node, 2 * ((int)stack.size() - 1) + 1));
+                    if (f.node >= 0) {
+                        // which child of its parent was this?
+                        const Frame& pf = stack[stack.size() - 2];
+                        const auto& pks = kids[pf.node + 1];
+                        const int pm = (int)pks.size(), j = pf.next - 1;
+                        const bool need_vf = (pm > 1) || !covers(f.node);
+                        int fl = EV_ASCEND;
+                        if (j < pm - 1 || (j == 0 && need_vf)) fl |= EV_VF;
+                        if (j > 0) fl |= EV_VBIA;
+                        events.push_back(make_int2(f.node, (((int)stack.size() - 1) << 4) | fl));
+                    }
                     stack.pop_back();
                 }
             }
@@ -644,6 +735,14 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
         }
         im->n_events = (int)events.size();
     }
+    std::vector<int4> evrows(events.size());
+    for (size_t e = 0; e < events.size(); ++e) {
+        const FbsStep& st = steps[events[e].x];
+        const bool asc = (events[e].y & EV_ASCEND) != 0;
+        const int* r = asc ? st.load_srow : st.edge_irow;
+        if (st.kind == GP_EDGE_VR) evrows[e] = make_int4(-1, -1, -1, asc ? 0 : 1);
+        else evrows[e] = make_int4(r[0], r[1], r[2], asc ? 0 : 1);
+    }
     auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
         if (e != cudaSuccess) return e;
@@ -651,6 +750,7 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
     };
     cudaError_t e = up((void**)&im->d_steps, steps.data(), steps.size() * sizeof(FbsStep));
     if (e == cudaSuccess) e = up((void**)&im->d_events, events.data(), events.size() * sizeof(int2));
+    if (e == cudaSuccess) e = up((void**)&im->d_evrows, evrows.data(), evrows.size() * sizeof(int4));
     if (e == cudaSuccess) e = up((void**)&im->d_child, d->child_irow, (size_t)d->n_child * 3 * sizeof(int));
     if (e == cudaSuccess) e = up((void**)&im->d_lines, lines.data(), lines.size() * sizeof(int));
     if (e == cudaSuccess) e = up((void**)&im->d_vrow_srow, vrow_srow.data(), vrow_srow.size() * sizeof(int));
@@ -678,6 +778,7 @@ extern "C" int gp_feeder_destroy(GpFeeder* f) {
         cudaFree(im->d_vrow_srow);
         cudaFree(im->d_vrow_cap);
         cudaFree(im->d_events);
+        cudaFree(im->d_evrows);
         for (int i = 0; i < FbsImpl::NSTREAM; ++i) {
             if (im->d_stage[i]) cudaFree(im->d_stage[i]);
             if (im->streams[i]) cudaStreamDestroy(im->streams[i]);
@@ -713,7 +814,7 @@ extern "C" int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
     if (dfs) {
         const unsigned ldb = (unsigned)(ld * 16);
 #define GP_DFS(D)                                                                                          \
-    fbs_dfs_kernel<BLOCK, D><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_events, im->n_events, im->k, S, ldb, \
+    fbs_dfs_kernel<BLOCK, D><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_events, im->d_evrows, im->n_events, im->k, S, ldb, \
                                                    (const char*)spu, (char*)V, (char*)I, iters, status,    \
                                                    diff, tol, maxiter)
         if (im->depth <= 8) GP_DFS(8);

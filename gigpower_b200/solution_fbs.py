@@ -213,7 +213,8 @@ class SolutionFBS(Solution):
         """Host-buffer path through ``gp_fbs_solve_batch_host``: ``spu_rows`` is a
         (preferably pinned) CPU torch tensor / NumPy array ``[n_srows, S]``
         complex128; outputs are written into the given host arrays.  Returns
-        (iterations, status, convergence_diff) as NumPy arrays."""
+        (iterations, status, convergence_diff) as NumPy views of pinned buffers that the next
+        call reuses."""
         torch, dev = self._dev()
         t = self.tables
         maxiter = self.maxiter if maxiter is None else int(maxiter)
@@ -225,9 +226,13 @@ class SolutionFBS(Solution):
             return x.data_ptr() if hasattr(x, 'data_ptr') else x.ctypes.data
 
         S = ld = int(spu_rows.shape[1])
-        iters = np.empty(S, dtype=np.int32)
-        status = np.empty(S, dtype=np.int32)
-        diff = np.empty(S, dtype=np.float64)
+        # pinned result vectors: a D2H copy into pageable memory would block the host inside
+        # the library and serialise the copy/compute pipeline
+        if getattr(self, '_host_vecs', None) is None or self._host_vecs[0].numel() < S:
+            self._host_vecs = (torch.empty(S, dtype=torch.int32).pin_memory(),
+                               torch.empty(S, dtype=torch.int32).pin_memory(),
+                               torch.empty(S, dtype=torch.float64).pin_memory())
+        iters, status, diff = (v[:S].numpy() for v in self._host_vecs)
         _cabi.check(_cabi.gp_fbs_solve_batch_host(
             self._feeder.handle, S, ld, ptr(spu_rows), ptr(V_out), ptr(I_out), ptr(Vmag_out), ptr(loss_out),
             iters.ctypes.data, status.ctypes.data, diff.ctypes.data, tol, maxiter))

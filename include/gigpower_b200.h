@@ -102,9 +102,9 @@ int gp_last_error(char* buf, size_t len);
 int64_t gp_launch_count(void);
 
 /*
- * Process-wide switches.  "fbs_kernel": 1 (default) = fused depth-first sweep kernel when
- * the feeder allows it, 0 = always the two-sweep kernel (same results; kept for feeders
- * whose regulators do not cover every phase of the regulated bus, and for A/B timing).
+ * Process-wide switches.  "fbs_kernel": 0 (default) = two-sweep kernel (the faster one on
+ * B200 so far, profiles/r01b_*), 1 = fused depth-first sweep kernel when the feeder allows
+ * it (same results; fewer HBM bytes by design, kept for A/B timing).
  */
 int gp_set_option(const char* name, int value);
 

@@ -181,7 +181,7 @@ def test_two_sweep_kernel_and_fused_dfs_kernel_agree(feeder):
             _cabi.check(_cabi.gp_set_option(b'fbs_kernel', mode))
             res[mode] = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
     finally:
-        _cabi.gp_set_option(b'fbs_kernel', 1)
+        _cabi.gp_set_option(b'fbs_kernel', 0)
     for mode in (0, 1):
         assert np.array_equal(res[mode].iterations, want['iterations']), mode
         assert rel_err(res[mode].V, want['V']) <= TOL and rel_err(res[mode].I, want['I']) <= TOL, mode
