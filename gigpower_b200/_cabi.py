@@ -47,9 +47,10 @@ class GpNr3Desc(C.Structure):
     _fields_ = [
         ('n_steps', C.c_int32), ('n_vrows', C.c_int32), ('n_irows', C.c_int32),
         ('n_srows', C.c_int32), ('n_child', C.c_int32), ('n_lines', C.c_int32),
-        ('bus_vrow', i32p), ('par_vrow', i32p), ('edge_irow', i32p), ('load_srow', i32p),
+        ('bus_vrow', i32p), ('par_vrow', i32p), ('edge_irow', i32p), ('edge_orow', i32p),
+        ('load_srow', i32p), ('kind', i32p),
         ('child_begin', i32p), ('child_count', i32p), ('child_step', i32p), ('child_irow', i32p),
-        ('z', f64p), ('cappu', f64p),
+        ('z', f64p), ('cappu', f64p), ('vr_gamma', f64p),
         ('root_vrow', C.c_int32 * 3), ('root_load_srow', C.c_int32 * 3),
         ('root_cappu', C.c_double * 3), ('vslack', C.c_double * 6), ('zip', C.c_double * 3),
         ('cA', C.c_double * 3), ('cB', C.c_double * 3), ('f0_absent', C.c_double),
@@ -132,11 +133,11 @@ def make_nr3_desc(t):
     d = GpNr3Desc()
     d.n_steps, d.n_vrows, d.n_irows, d.n_srows = t.n_steps, t.n_vrows, t.n_irows, t.n_srows
     d.n_child, d.n_lines = int(t.child_step.shape[0]), t.n_lines
-    for name in ('bus_vrow', 'par_vrow', 'edge_irow', 'load_srow', 'child_begin', 'child_count',
-                 'child_step', 'child_irow', 'line_irow', 'line_tx_vrow', 'line_rx_vrow'):
+    for name in ('bus_vrow', 'par_vrow', 'edge_irow', 'edge_orow', 'load_srow', 'kind', 'child_begin',
+                 'child_count', 'child_step', 'child_irow', 'line_irow', 'line_tx_vrow', 'line_rx_vrow'):
         keep[name] = _i32(getattr(t, name))
         setattr(d, name, keep[name].ctypes.data_as(i32p))
-    for name in ('z', 'cappu'):
+    for name in ('z', 'cappu', 'vr_gamma'):
         keep[name] = _f64(getattr(t, name))
         setattr(d, name, keep[name].ctypes.data_as(f64p))
     d.root_vrow = (C.c_int32 * 3)(*[int(x) for x in t.root_vrow])

@@ -32,15 +32,19 @@ struct __align__(16) Nr3Step {
     int child_count;
     int par_row[3];
     int child_begin;
-    int edge_row[3];
-    int pad0;
+    int edge_row[3];    // current entering the bus (line / transformer current, regulator in-leg)
+    int kind;           // GP_EDGE_LINE or GP_EDGE_VR
     int load_srow[3];
-    int pad1;
+    int aux;            // regulator steps: front slot holding (Dt, u, r_a) for the forward sweep
+    int out_row[3];     // current leaving the parent (= edge_row except the regulator out-leg)
+    int pad0;
     double cap[3];
+    double pad1;
+    double gamma[3];
     double pad2;
     double2 z[9];
 };
-static_assert(sizeof(Nr3Step) == 64 + 32 + 144, "Nr3Step layout");
+static_assert(sizeof(Nr3Step) == 80 + 32 + 32 + 144, "Nr3Step layout");
 
 struct Nr3Const {
     int root_row[3];
@@ -59,6 +63,7 @@ struct Nr3Impl {
     int* d_vrow_srow = nullptr;   // [n_vrows]
     double* d_vrow_cap = nullptr; // [n_vrows]
     Nr3Const k;
+    int n_fronts = 0;   // n_steps + one extra slot per regulator step
 };
 
 constexpr int FRONT_D2 = 24;   // double2 per step: Y (18) + a (3) + r1 (3)
@@ -113,11 +118,13 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
     for (int pos = 0; pos < n_steps; ++pos) {
         const int4 bv = __ldg(reinterpret_cast<const int4*>(steps[pos].bus_row));
         const int4 ev = __ldg(reinterpret_cast<const int4*>(steps[pos].edge_row));
-        const int brow[3] = {bv.x, bv.y, bv.z}, erow[3] = {ev.x, ev.y, ev.z};
+        const int4 ov = __ldg(reinterpret_cast<const int4*>(steps[pos].out_row));
+        const int brow[3] = {bv.x, bv.y, bv.z}, erow[3] = {ev.x, ev.y, ev.z}, orow[3] = {ov.x, ov.y, ov.z};
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
             if (brow[p] >= 0) Xs[(long long)brow[p] * ld] = k.vslack[p];
             if (erow[p] >= 0) Xs[(long long)erow[p] * ld] = make_double2(0.0, 0.0);
+            if (orow[p] >= 0) Xs[(long long)orow[p] * ld] = make_double2(0.0, 0.0);
         }
     }
 #pragma unroll
@@ -137,7 +144,7 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             const int4 lv = __ldg(reinterpret_cast<const int4*>(st->load_srow));
             const int brow[3] = {bv.x, bv.y, bv.z}, prow[3] = {pv.x, pv.y, pv.z};
             const int erow[3] = {ev.x, ev.y, ev.z}, lrow[3] = {lv.x, lv.y, lv.z};
-            const int child_count = bv.w, child_begin = pv.w;
+            const int child_count = bv.w, child_begin = pv.w, kind = ev.w, aux = lv.w;
             double2 v[3], inet[3], r1[3];
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
@@ -145,22 +152,29 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                 if (brow[p] < 0) continue;
                 v[p] = Xs[(long long)brow[p] * ld];
                 inet[p] = Xs[(long long)erow[p] * ld];
-                if (prow[p] >= 0) r1[p] = Xs[(long long)prow[p] * ld];
-                r1[p].x -= v[p].x;
-                r1[p].y -= v[p].y;
             }
-            // KVL residual r1 = E v_p - v - Z i   (:141-158)
+            if (kind == GP_EDGE_LINE) {
+                // KVL residual r1 = E v_p - v - Z i   (:141-158; transformers :165-175 with Z = 0)
 #pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                if (brow[p] < 0) continue;
+                for (int p = 0; p < 3; ++p) {
+                    if (brow[p] < 0) continue;
+                    if (prow[p] >= 0) r1[p] = Xs[(long long)prow[p] * ld];
+                    r1[p].x -= v[p].x;
+                    r1[p].y -= v[p].y;
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    if (brow[q] < 0) continue;
-                    const double2 z = __ldg(&st->z[3 * p + q]);
-                    r1[p].x -= z.x * inet[q].x - z.y * inet[q].y;
-                    r1[p].y -= z.x * inet[q].y + z.y * inet[q].x;
+                    for (int q = 0; q < 3; ++q) {
+                        if (brow[q] < 0) continue;
+                        const double2 z = __ldg(&st->z[3 * p + q]);
+                        r1[p].x -= z.x * inet[q].x - z.y * inet[q].y;
+                        r1[p].y -= z.x * inet[q].y + z.y * inet[q].x;
+                    }
+                    nanflag |= (r1[p].x != r1[p].x) | (r1[p].y != r1[p].y);
+                    fm = fmax(fm, fmax(fabs(r1[p].x), fabs(r1[p].y)));
                 }
             }
+            double2 iin[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) iin[p] = inet[p];
             double Dt[6][6], rt[6];
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
@@ -184,7 +198,7 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                     rt[2 * p + 1] += ac.y;
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
-                        if (crow[q] < 0) continue;
+                        if (crow[q] < 0) continue;      // only the child's own phases were stored
                         const double2 y0 = Wc[(long long)((2 * p) * 3 + q) * ld];
                         const double2 y1 = Wc[(long long)((2 * p + 1) * 3 + q) * ld];
                         Dt[2 * p][2 * q] += y0.x;
@@ -212,8 +226,8 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                 const double b0i = (-ql * k.betaS) + (cap * k.betaS);
                 const double fr = A * Cn + B * Dn + hAr * A * A + hBr * B * B + b0r;
                 const double fi = B * Cn - A * Dn + hAi * A * A + hBi * B * B + b0i;
-                nanflag |= (fr != fr) | (fi != fi) | (r1[p].x != r1[p].x) | (r1[p].y != r1[p].y);
-                fm = fmax(fm, fmax(fmax(fabs(fr), fabs(fi)), fmax(fabs(r1[p].x), fabs(r1[p].y))));
+                nanflag |= (fr != fr) | (fi != fi);
+                fm = fmax(fm, fmax(fabs(fr), fabs(fi)));
                 const double d00 = Cn + 2.0 * hAr * A, d01 = Dn + 2.0 * hBr * B;
                 const double d10 = -Dn + 2.0 * hAi * A, d11 = Cn + 2.0 * hBi * B;
                 const double inv = 1.0 / (A * A + B * B);
@@ -224,6 +238,77 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                 Dt[2 * p + 1][2 * p + 1] += (B * d01 - A * d11) * inv;
                 rt[2 * p] += (A * fr + B * fi) * inv;
                 rt[2 * p + 1] += (B * fr - A * fi) * inv;
+            }
+            double2* Wk = Ws + (long long)pos * FRONT_D2 * ld;
+            if (kind == GP_EDGE_VR) {
+                // ---- regulator edge (:444-515): v_r = gamma v_m ; V_m conj(I_out) = V_r conj(I_in).
+                //   dv_r = gamma dv_m + r_a,  di_in = u - Dt gamma dv_m  (u = rt - Dt r_a),
+                //   di_out = a_k - Y_k dv_m  with the 2x2 blocks M(v) = [[A,B],[B,-A]], N(i) = [[C,D],[-D,C]]:
+                //   a_k = Mm^-1 [F/2 + N_in r_a + M_r u],  Y_k = Mm^-1 [N_out - g N_in + M_r Dt g]
+                const int4 ov = __ldg(reinterpret_cast<const int4*>(st->out_row));
+                const int orow[3] = {ov.x, ov.y, ov.z};
+                double2 vm[3], io[3], ra[3];
+                double g[3];
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    vm[p] = io[p] = ra[p] = make_double2(0.0, 0.0);
+                    g[p] = 0.0;
+                    if (brow[p] < 0) continue;
+                    g[p] = __ldg(&st->gamma[p]);
+                    vm[p] = Xs[(long long)prow[p] * ld];
+                    io[p] = Xs[(long long)orow[p] * ld];
+                    ra[p] = make_double2(-g[p] * vm[p].x + v[p].x, -g[p] * vm[p].y + v[p].y);
+                    const double f0 = 2.0 * ((vm[p].x * io[p].x + vm[p].y * io[p].y) - (v[p].x * iin[p].x + v[p].y * iin[p].y));
+                    const double f1 = 2.0 * ((vm[p].y * io[p].x - vm[p].x * io[p].y) - (v[p].y * iin[p].x - v[p].x * iin[p].y));
+                    nanflag |= (f0 != f0) | (f1 != f1) | (ra[p].x != ra[p].x) | (ra[p].y != ra[p].y);
+                    fm = fmax(fm, fmax(fmax(fabs(f0), fabs(f1)), fmax(fabs(ra[p].x), fabs(ra[p].y))));
+                    r1[p] = make_double2(0.5 * f0, 0.5 * f1);       // reuse r1 as F/2
+                }
+                double u[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    u[r] = rt[r];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) u[r] -= Dt[r][2 * q] * ra[q].x + Dt[r][2 * q + 1] * ra[q].y;
+                }
+                double2* Wa = Ws + (long long)aux * FRONT_D2 * ld;
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    if (brow[p] < 0) continue;
+                    Wa[(long long)(18 + p) * ld] = make_double2(u[2 * p], u[2 * p + 1]);
+                    Wa[(long long)(21 + p) * ld] = ra[p];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        if (brow[q] < 0) continue;
+                        Wa[(long long)((2 * p) * 3 + q) * ld] = make_double2(Dt[2 * p][2 * q], Dt[2 * p][2 * q + 1]);
+                        Wa[(long long)((2 * p + 1) * 3 + q) * ld] = make_double2(Dt[2 * p + 1][2 * q], Dt[2 * p + 1][2 * q + 1]);
+                    }
+                    const double A1 = vm[p].x, B1 = vm[p].y, A2 = v[p].x, B2 = v[p].y;
+                    const double Co = io[p].x, Do = io[p].y, Ci = iin[p].x, Di = iin[p].y;
+                    const double im = 1.0 / (A1 * A1 + B1 * B1);
+                    // a_k rows of this phase
+                    const double t0 = r1[p].x + (Ci * ra[p].x + Di * ra[p].y) + (A2 * u[2 * p] + B2 * u[2 * p + 1]);
+                    const double t1 = r1[p].y + (-Di * ra[p].x + Ci * ra[p].y) + (B2 * u[2 * p] - A2 * u[2 * p + 1]);
+                    Wk[(long long)(18 + p) * ld] = make_double2((A1 * t0 + B1 * t1) * im, (B1 * t0 - A1 * t1) * im);
+                    // Y_k rows of this phase: Mm^-1 [ M_r (Dt[rows p] * g) + (N_out - g N_in) on the diagonal block ]
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        if (brow[q] < 0) continue;
+                        double w00 = (A2 * Dt[2 * p][2 * q] + B2 * Dt[2 * p + 1][2 * q]) * g[q];
+                        double w01 = (A2 * Dt[2 * p][2 * q + 1] + B2 * Dt[2 * p + 1][2 * q + 1]) * g[q];
+                        double w10 = (B2 * Dt[2 * p][2 * q] - A2 * Dt[2 * p + 1][2 * q]) * g[q];
+                        double w11 = (B2 * Dt[2 * p][2 * q + 1] - A2 * Dt[2 * p + 1][2 * q + 1]) * g[q];
+                        if (q == p) {
+                            w00 += Co - g[p] * Ci;
+                            w01 += Do - g[p] * Di;
+                            w10 += -Do + g[p] * Di;
+                            w11 += Co - g[p] * Ci;
+                        }
+                        Wk[(long long)((2 * p) * 3 + q) * ld] = make_double2((A1 * w00 + B1 * w10) * im, (A1 * w01 + B1 * w11) * im);
+                        Wk[(long long)((2 * p + 1) * 3 + q) * ld] = make_double2((B1 * w00 - A1 * w10) * im, (B1 * w01 - A1 * w11) * im);
+                    }
+                }
+                continue;
             }
             // rhs_a = rt + Dt r1 ;  T = I - Dt Zr
             double T[6][6];
@@ -250,7 +335,6 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             }
             lu6(T);
             lu6_solve(T, rt);
-            double2* Wk = Ws + (long long)pos * FRONT_D2 * ld;
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
                 if (brow[p] < 0) continue;
@@ -291,11 +375,13 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_row));
             const int brow[3] = {bv.x, bv.y, bv.z}, prow[3] = {pv.x, pv.y, pv.z};
             const int erow[3] = {ev.x, ev.y, ev.z};
+            const int kind = ev.w;
             const double2* Wk = Ws + (long long)pos * FRONT_D2 * ld;
             double2 dvp[3], di[3], dv[3];
 #pragma unroll
             for (int p = 0; p < 3; ++p)
                 dvp[p] = (brow[p] >= 0 && prow[p] >= 0) ? DVs[(long long)prow[p] * ld] : make_double2(0.0, 0.0);
+            // current leaving the parent: di = a - Y dv_p
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
                 di[p] = make_double2(0.0, 0.0);
@@ -309,6 +395,41 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                     di[p].x -= y0.x * dvp[q].x + y0.y * dvp[q].y;
                     di[p].y -= y1.x * dvp[q].x + y1.y * dvp[q].y;
                 }
+            }
+            if (kind == GP_EDGE_VR) {
+                const int4 lv = __ldg(reinterpret_cast<const int4*>(st->load_srow));
+                const int4 ov = __ldg(reinterpret_cast<const int4*>(st->out_row));
+                const int orow[3] = {ov.x, ov.y, ov.z};
+                const double2* Wa = Ws + (long long)lv.w * FRONT_D2 * ld;
+                double2 gdv[3];
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const double g = __ldg(&st->gamma[p]);
+                    gdv[p] = make_double2(g * dvp[p].x, g * dvp[p].y);
+                }
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    if (brow[p] < 0) continue;
+                    const double2 ra = Wa[(long long)(21 + p) * ld];
+                    double2 dii = Wa[(long long)(18 + p) * ld];          // u
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        if (brow[q] < 0) continue;
+                        const double2 d0 = Wa[(long long)((2 * p) * 3 + q) * ld];
+                        const double2 d1 = Wa[(long long)((2 * p + 1) * 3 + q) * ld];
+                        dii.x -= d0.x * gdv[q].x + d0.y * gdv[q].y;
+                        dii.y -= d1.x * gdv[q].x + d1.y * gdv[q].y;
+                    }
+                    dv[p] = make_double2(gdv[p].x + ra.x, gdv[p].y + ra.y);
+                    const double2 xv = Xs[(long long)brow[p] * ld];
+                    const double2 xi = Xs[(long long)erow[p] * ld];
+                    const double2 xo = Xs[(long long)orow[p] * ld];
+                    Xs[(long long)brow[p] * ld] = make_double2(xv.x - dv[p].x, xv.y - dv[p].y);
+                    Xs[(long long)erow[p] * ld] = make_double2(xi.x - dii.x, xi.y - dii.y);
+                    Xs[(long long)orow[p] * ld] = make_double2(xo.x - di[p].x, xo.y - di[p].y);
+                    DVs[(long long)brow[p] * ld] = dv[p];
+                }
+                continue;
             }
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
@@ -430,6 +551,7 @@ extern "C" int gp_nr3_create(const GpNr3Desc* d, int device, GpFeeder** out) {
     im->n_child = d->n_child;
     im->n_lines = d->n_lines;
     const int nx = d->n_vrows + d->n_irows;
+    im->n_fronts = d->n_steps;
     std::vector<Nr3Step> steps((size_t)d->n_steps);
     std::vector<int> vrow_srow((size_t)d->n_vrows, -1);
     std::vector<double> vrow_cap((size_t)d->n_vrows, 0.0);
@@ -438,6 +560,13 @@ extern "C" int gp_nr3_create(const GpNr3Desc* d, int device, GpFeeder** out) {
         memset(&s, 0, sizeof(s));
         s.child_begin = d->child_begin[i];
         s.child_count = d->child_count[i];
+        s.kind = d->kind[i];
+        s.aux = -1;
+        if (s.kind == GP_EDGE_VR) s.aux = im->n_fronts++;
+        else if (s.kind != GP_EDGE_LINE) {
+            delete im;
+            return fail(GP_EINVAL, "gp_nr3_create: step %d: unknown edge kind %d", i, s.kind);
+        }
         if (s.child_begin < 0 || s.child_count < 0 || s.child_begin + s.child_count > d->n_child) {
             delete im;
             return fail(GP_EINVAL, "gp_nr3_create: step %d child range out of bounds", i);
@@ -446,9 +575,13 @@ extern "C" int gp_nr3_create(const GpNr3Desc* d, int device, GpFeeder** out) {
             s.bus_row[p] = d->bus_vrow[3 * i + p];
             s.par_row[p] = d->par_vrow[3 * i + p];
             s.edge_row[p] = d->edge_irow[3 * i + p] >= 0 ? d->edge_irow[3 * i + p] + d->n_vrows : -1;
+            s.out_row[p] = d->edge_orow[3 * i + p] >= 0 ? d->edge_orow[3 * i + p] + d->n_vrows : -1;
+            s.gamma[p] = d->vr_gamma[3 * i + p];
             s.load_srow[p] = d->load_srow[3 * i + p];
             const bool has_b = s.bus_row[p] >= 0, has_e = s.edge_row[p] >= 0;
-            if (has_b != has_e || s.bus_row[p] >= d->n_vrows || s.par_row[p] >= d->n_vrows ||
+            if (has_b != (s.out_row[p] >= 0) || s.out_row[p] >= nx ||
+                (s.kind == GP_EDGE_VR && has_b && (s.gamma[p] == 0.0 || s.par_row[p] < 0 || s.out_row[p] == s.edge_row[p])) ||
+                has_b != has_e || s.bus_row[p] >= d->n_vrows || s.par_row[p] >= d->n_vrows ||
                 s.edge_row[p] >= nx || s.load_srow[p] >= d->n_srows || s.bus_row[p] < -1 ||
                 s.par_row[p] < -1 || s.load_srow[p] < -1) {
                 delete im;
@@ -546,7 +679,7 @@ static int nr3_check(GpFeeder* f, int64_t S, int64_t ld, const char* who) {
 extern "C" int64_t gp_nr3_workspace_bytes(GpFeeder* f, int64_t ld) {
     if (!f || f->kind != 2 || ld < 0) return fail(GP_EINVAL, "gp_nr3_workspace_bytes: bad argument");
     Nr3Impl* im = (Nr3Impl*)f->impl;
-    return ((int64_t)im->n_steps * FRONT_D2 + im->n_vrows) * ld * 16 + 256;
+    return ((int64_t)im->n_fronts * FRONT_D2 + im->n_vrows) * ld * 16 + 256;
 }
 
 extern "C" int gp_nr3_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const double* spu, double* X,
@@ -566,7 +699,7 @@ extern "C" int gp_nr3_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
     constexpr int BLOCK = 64;
     const unsigned gx = (unsigned)((S + BLOCK - 1) / BLOCK);
     double2* W = (double2*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    double2* DV = W + (size_t)im->n_steps * FRONT_D2 * ld;
+    double2* DV = W + (size_t)im->n_fronts * FRONT_D2 * ld;
     nr3_solve_kernel<BLOCK><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_vrows, im->n_irows, S,
                                                   ld, (const double2*)spu, (double2*)X, W, DV, iters, status,
                                                   fmax, maxiter);

@@ -244,13 +244,16 @@ class Nr3Tables:
     bus_vrow: np.ndarray
     par_vrow: np.ndarray
     edge_irow: np.ndarray
+    edge_orow: np.ndarray
     load_srow: np.ndarray
+    kind: np.ndarray
     child_begin: np.ndarray
     child_count: np.ndarray
     child_step: np.ndarray
     child_irow: np.ndarray
     z: np.ndarray
     cappu: np.ndarray
+    vr_gamma: np.ndarray
     root_vrow: np.ndarray
     root_load_srow: np.ndarray
     root_cappu: np.ndarray
@@ -263,7 +266,7 @@ class Nr3Tables:
     line_tx_vrow: np.ndarray
     line_rx_vrow: np.ndarray
     vrow: np.ndarray = field(default=None)       # [nb,3]
-    irow: np.ndarray = field(default=None)       # [nl+ntf,3]
+    irow: np.ndarray = field(default=None)       # [n_edges,3] rows of the current entering the child bus
     srow: np.ndarray = field(default=None)       # [nb,3]
     N: int = 0                                    # length of XNR
     xnr_index: np.ndarray = field(default=None)  # [n_vrows+n_irows] even XNR index of each packed row
@@ -272,22 +275,31 @@ class Nr3Tables:
 
 def flatten_nr3(c: Circuit) -> Nr3Tables:
     """Tree tables for the block elimination of ``gp_nr3.cu``.  Supported: radial
-    feeders of Lines and Transformers oriented away from the slack bus (index 0);
-    every bus must carry exactly the phases of its incoming edge."""
-    if c.voltage_regulators.num_elements:
-        raise NotImplementedError('NR3 on feeders with voltage regulators is not built yet')
+    feeders of Lines, Transformers and VoltageRegulators oriented away from the
+    slack bus (index 0); every bus must carry exactly the phases of its incoming edge."""
     names = c.buses.all_names()
     nb, nl, ntf = len(names), c.lines.num_elements, c.transformers.num_elements
     bidx = {n: i for i, n in enumerate(names)}
     bus_pm = c.buses.get_phase_matrix('rows')
     if bus_pm[0].sum() != 3:
         raise NotImplementedError('the slack bus must carry all three phases')
-    edges = c.lines.get_elements() + c.transformers.get_elements()
+    # edges: lines, transformers, then one edge per regulated bus pair (its VRs merged per phase)
+    edges = [dict(kind=EDGE_LINE, tx=e.tx, rx=e.rx, pm=np.asarray(e.phase_matrix), el=e)
+             for e in c.lines.get_elements() + c.transformers.get_elements()]
+    vr_edges, cnt = {}, 0
+    for vr in c.voltage_regulators.get_elements():        # VR-phase counter in (VR, phase) order (:471-514)
+        e = vr_edges.setdefault(vr.key, dict(kind=EDGE_VR, tx=vr.tx, rx=vr.rx, pm=np.zeros(3, dtype=int),
+                                             gamma=np.zeros(3), slot={}))
+        for p in vr.get_ph_idx_matrix():
+            e['pm'][p], e['gamma'][p], e['slot'][int(p)] = 1, vr.gamma, cnt
+            cnt += 1
+    vr_lines = cnt
+    edges += list(vr_edges.values())
     parent, edge_in, children = {}, {}, {b: [] for b in range(nb)}
     for ei, e in enumerate(edges):
-        tx, rx = bidx[e.tx], bidx[e.rx]
+        tx, rx = bidx[e['tx']], bidx[e['rx']]
         if rx in parent:
-            raise ValueError(f"Network not radial. Bus {e.rx} has parents {[names[parent[rx]], e.tx]}")
+            raise ValueError(f"Network not radial. Bus {e['rx']} has parents {[names[parent[rx]], e['tx']]}")
         parent[rx], edge_in[rx] = tx, ei
         children[tx].append(rx)
     order, stack = [], [0]
@@ -311,13 +323,21 @@ def flatten_nr3(c: Circuit) -> Nr3Tables:
                 vrow[b, p] = k
                 k += 1
     n_vrows = k
-    irow = np.full((nl + ntf, 3), -1, dtype=np.int32)
+    ne = len(edges)
+    irow = np.full((ne, 3), -1, dtype=np.int32)
     k = 0
     for i, e in enumerate(edges):
         for p in range(3):
-            if e.phase_matrix[p]:
+            if e['pm'][p]:
                 irow[i, p] = k
                 k += 1
+    orow = irow.copy()
+    for i, e in enumerate(edges):                 # out-legs of the regulators
+        if e['kind'] == EDGE_VR:
+            for p in range(3):
+                if e['pm'][p]:
+                    orow[i, p] = k
+                    k += 1
     n_irows = k
     lmask = c.load_phase_mask()
     srow = np.full((nb, 3), -1, dtype=np.int32)
@@ -334,25 +354,29 @@ def flatten_nr3(c: Circuit) -> Nr3Tables:
     step_of = {b: i for i, b in enumerate(order[1:])}
     S3 = (n_steps, 3)
     t = dict(bus_vrow=np.full(S3, -1, np.int32), par_vrow=np.full(S3, -1, np.int32),
-             edge_irow=np.full(S3, -1, np.int32), load_srow=np.full(S3, -1, np.int32),
+             edge_irow=np.full(S3, -1, np.int32), edge_orow=np.full(S3, -1, np.int32),
+             load_srow=np.full(S3, -1, np.int32), kind=np.zeros(n_steps, np.int32),
              child_begin=np.zeros(n_steps, np.int32), child_count=np.zeros(n_steps, np.int32),
-             z=np.zeros((n_steps, 3, 3, 2)), cappu=np.zeros(S3))
+             z=np.zeros((n_steps, 3, 3, 2)), cappu=np.zeros(S3), vr_gamma=np.zeros(S3))
     child_step, child_rows = [], []
     for pos, b in enumerate(order[1:]):
         e = edges[edge_in[b]]
-        if not np.array_equal(e.phase_matrix, bus_pm[b]):
-            raise NotImplementedError(f'bus {names[b]}: phases differ from its incoming edge {e.__name__}')
+        if not np.array_equal(e['pm'], bus_pm[b]):
+            raise NotImplementedError(f"bus {names[b]}: phases differ from its incoming edge")
         t['bus_vrow'][pos], t['par_vrow'][pos] = vrow[b], vrow[parent[b]]
-        t['edge_irow'][pos], t['load_srow'][pos], t['cappu'][pos] = irow[edge_in[b]], srow[b], cappu[b]
-        if e.kind == 'Line':       # rmat/xmat (line.py:48-73); identical numbers to FZpu on existing phases
-            R, X = e.rmat.reshape(3, 3), e.xmat.reshape(3, 3)
-            pm = e.phase_matrix
+        t['edge_irow'][pos], t['edge_orow'][pos] = irow[edge_in[b]], orow[edge_in[b]]
+        t['load_srow'][pos], t['cappu'][pos], t['kind'][pos] = srow[b], cappu[b], e['kind']
+        if e['kind'] == EDGE_VR:
+            t['vr_gamma'][pos] = e['gamma']
+        elif e['el'].kind == 'Line':   # rmat/xmat (line.py:48-73); identical numbers to FZpu on existing phases
+            R, X = e['el'].rmat.reshape(3, 3), e['el'].xmat.reshape(3, 3)
+            pm = e['pm']
             t['z'][pos, :, :, 0] = R * pm[None, :] * pm[:, None]
             t['z'][pos, :, :, 1] = X * pm[None, :] * pm[:, None]
         t['child_begin'][pos] = len(child_step)
         for ch in children[b]:
             child_step.append(step_of[ch])
-            child_rows.append(irow[edge_in[ch]])
+            child_rows.append(orow[edge_in[ch]])
         t['child_count'][pos] = len(child_step) - t['child_begin'][pos]
 
     # second-order ZIP constants per phase (solution_nr3.py:228-261)
@@ -371,9 +395,10 @@ def flatten_nr3(c: Circuit) -> Nr3Tables:
             if not bus_pm[b, p]:
                 f0 = max(f0, abs(vslack[p].real), abs(vslack[p].imag))
 
-    # packed row -> XNR index (solution_nr3.py:46-61; transformer currents after the lines)
+    # packed row -> XNR index (solution_nr3.py:46-61): lines, transformer currents, then per
+    # regulated phase the in-leg (even) and out-leg (odd) currents
     tf_lines = int(sum(len(e.phases) for e in c.transformers.get_elements()))
-    N = 2 * 3 * (nb + nl) + 2 * tf_lines
+    N = 2 * 3 * (nb + nl) + 2 * tf_lines + 2 * 2 * vr_lines
     xnr = np.zeros(n_vrows + n_irows, dtype=np.int64)
     for b in range(nb):
         for p in range(3):
@@ -384,11 +409,17 @@ def flatten_nr3(c: Circuit) -> Nr3Tables:
             if irow[l, p] >= 0:
                 xnr[n_vrows + irow[l, p]] = 6 * nb + 2 * p * nl + 2 * l
     cnt = 0
-    for ti, e in enumerate(c.transformers.get_elements()):
+    for ti in range(ntf):
         for p in range(3):
             if irow[nl + ti, p] >= 0:
                 xnr[n_vrows + irow[nl + ti, p]] = 6 * (nb + nl) + 2 * cnt
                 cnt += 1
+    base_r = 6 * (nb + nl) + 2 * tf_lines
+    for i, e in enumerate(edges):
+        if e['kind'] == EDGE_VR:
+            for p, slot in e['slot'].items():
+                xnr[n_vrows + irow[i, p]] = base_r + 2 * (2 * slot)
+                xnr[n_vrows + orow[i, p]] = base_r + 2 * (2 * slot + 1)
     tx = np.array([bidx[e.tx] for e in c.lines.get_elements()], dtype=int)
     rx = np.array([bidx[e.rx] for e in c.lines.get_elements()], dtype=int)
     return Nr3Tables(

@@ -175,22 +175,28 @@ int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const double* sp
  * n_irows) edge currents.  Phases that do not exist are identity rows of J whose
  * solution is exactly 0 and are not stored.
  *
- * Step k is a non-slack bus with its incoming edge (Line, or Transformer with
- * Z = 0) from its parent, parents before children; a bus must carry exactly the
+ * Step k is a non-slack bus with its incoming edge from its parent, parents before
+ * children: a Line, a Transformer (Z = 0, :165-175) or the VoltageRegulators between one
+ * pair of buses (GP_EDGE_VR: ratio rows and power-conservation rows, :444-515, with an
+ * in-leg and an out-leg current per regulated phase).  A bus must carry exactly the
  * phases of its incoming edge.  The slack bus (index 0, solution.py:20) is the root.
  */
 typedef struct {
     int32_t n_steps, n_vrows, n_irows, n_srows, n_child, n_lines;
     const int32_t* bus_vrow;    /* [n_steps][3] X row of (bus, ph) or -1               */
     const int32_t* par_vrow;    /* [n_steps][3] X row of (parent, ph) or -1            */
-    const int32_t* edge_irow;   /* [n_steps][3] current row (0-based in the I block)   */
+    const int32_t* edge_irow;   /* [n_steps][3] row (0-based in the I block) of the current ENTERING the bus */
+    const int32_t* edge_orow;   /* [n_steps][3] row of the current LEAVING the parent: = edge_irow,
+                                   except the out-leg of a regulator                   */
     const int32_t* load_srow;   /* [n_steps][3] spu row or -1                          */
+    const int32_t* kind;        /* [n_steps] GP_EDGE_LINE (also transformers) or GP_EDGE_VR */
     const int32_t* child_begin; /* [n_steps]                                           */
     const int32_t* child_count; /* [n_steps]                                           */
     const int32_t* child_step;  /* [n_child] step index of each child bus              */
-    const int32_t* child_irow;  /* [n_child][3] current rows of the child edges        */
+    const int32_t* child_irow;  /* [n_child][3] edge_orow of the child edges           */
     const double* z;            /* [n_steps][3][3][2] pu impedance (rmat/xmat, line.py:48-73) */
     const double* cappu;        /* [n_steps][3]                                        */
+    const double* vr_gamma;     /* [n_steps][3] gamma per regulated phase, 0 elsewhere */
     int32_t root_vrow[3];
     int32_t root_load_srow[3];
     double root_cappu[3];

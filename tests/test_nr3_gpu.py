@@ -4,7 +4,7 @@ complex bus voltages, identical Newton iteration counts."""
 import numpy as np
 import pytest
 
-from helpers import ZIPS, LINES_ONLY, feeder_path, load_model, snapshots, scenarios, rel_err
+from helpers import ZIPS, ALL_FEEDERS, LINES_ONLY, feeder_path, load_model, snapshots, scenarios, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -16,7 +16,7 @@ def _nr3(feeder, zname='test_zip'):
 
 
 @pytest.mark.parametrize('zname', list(ZIPS))
-@pytest.mark.parametrize('feeder', LINES_ONLY)
+@pytest.mark.parametrize('feeder', ALL_FEEDERS)
 def test_snapshot_matches_reference(feeder, zname):
     snap = snapshots()
     s = _nr3(feeder, zname)
@@ -92,3 +92,18 @@ def test_edge_cases_and_zero_load():
         r = s.solve_batch(load_mult=mult, outputs=('X',))
         assert np.array_equal(r.iterations, want['iterations'])
         assert rel_err(r.XNR, want['XNR']) <= TOL
+
+
+@pytest.mark.parametrize('feeder,S,seed', [('IEEE_13_Bus_allwye', 100, 6), ('IEEE_37_Bus_allwye', 40, 7),
+                                            ('IEEE_34_Bus_allwye', 40, 8)])
+def test_regulator_feeders_batch_matches_dense_oracle(feeder, S, seed):
+    """Transformer and regulator edges in the batched Newton kernel."""
+    from oracle.gp_oracle import NR3Oracle
+    rng = np.random.Generator(np.random.PCG64(seed))
+    o = NR3Oracle(load_model(feeder), ZIPS['test_zip'])
+    mult = rng.uniform(0.5, 1.3, size=(S, len(o.c.load_names)))
+    want = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+    r = _nr3(feeder).solve_batch(load_mult=mult, outputs=('X', 'V', 'I', 'Stx'))
+    assert np.array_equal(r.iterations, want['iterations'])
+    assert rel_err(r.XNR, want['XNR']) <= TOL
+    assert rel_err(r.V, want['V']) <= TOL and rel_err(r.I, want['I']) <= TOL and rel_err(r.Stx, want['Stx']) <= TOL

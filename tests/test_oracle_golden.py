@@ -122,7 +122,7 @@ def test_known_answers_appendix_b():
 
 
 @pytest.mark.parametrize('zname', list(ZIPS))
-@pytest.mark.parametrize('feeder', LINES_ONLY)
+@pytest.mark.parametrize('feeder', ALL_FEEDERS)
 def test_tree_elimination_oracle_equals_dense_oracle(feeder, zname):
     """oracle/nr3_tree.py (the algorithm the CUDA kernel implements) against the
     literal restatement (dense J, inv(J'J) J' F) and the reference's golden X."""
@@ -130,7 +130,7 @@ def test_tree_elimination_oracle_equals_dense_oracle(feeder, zname):
     model = load_model(feeder)
     o, t = NR3Oracle(model, ZIPS[zname]), NR3TreeOracle(model, ZIPS[zname])
     rng = np.random.Generator(np.random.PCG64(5))
-    mult = rng.uniform(0.4, 1.6, size=(5, len(o.c.load_names)))
+    mult = rng.uniform(0.5, 1.3, size=(5, len(o.c.load_names)))
     mult[0] = 1.0
     spu = o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult)
     a, b = o.solve(spu), t.solve(spu)
