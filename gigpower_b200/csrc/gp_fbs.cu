@@ -55,7 +55,7 @@ struct FbsConst {
 struct FbsImpl {
     int n_steps = 0, n_vrows = 0, n_irows = 0, n_srows = 0, n_child = 0, n_lines = 0;
     FbsStep* d_steps = nullptr;
-    int* d_child = nullptr;   // [n_child][3]
+    int4* d_child = nullptr;  // [n_child] {I rows of the child edge, 0}
     int* d_lines = nullptr;   // [n_lines][9] irow, tx vrow, rx vrow
     int* d_vrow_srow = nullptr;   // [n_vrows] spu row of each V row or -1
     double* d_vrow_cap = nullptr; // [n_vrows]
@@ -80,24 +80,30 @@ __device__ __forceinline__ double cabs2(double2 v, double& a) {
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
-fbs_solve_kernel(const FbsStep* __restrict__ steps, const int* __restrict__ child_irow,
-                 FbsConst k, int n_steps, int n_vrows, int n_irows, long long S, long long ld,
-                 const double2* __restrict__ spu, double2* __restrict__ V,
-                 double2* __restrict__ I, int* __restrict__ iters_out,
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)   // <= 64 registers: 1024 resident threads per SM
+fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ child_irow,
+                 FbsConst k, int n_steps, int n_vrows, int n_irows, long long S, unsigned ldb,
+                 const char* __restrict__ spu, char* __restrict__ V,
+                 char* __restrict__ I, int* __restrict__ iters_out,
                  int* __restrict__ status_out, double* __restrict__ diff_out, double tol,
                  int maxiter) {
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (s >= S) return;
-    const double2* spu_s = spu + s;
-    double2* Vs = V + s;
-    double2* Is = I + s;
+    // row r of scenario s lives at base + s*16 + r*ldb: one 32x32->64 multiply-add per access
+    const char* spu_b = spu + s * 16;
+    char* V_b = V + s * 16;
+    char* I_b = I + s * 16;
+#define VROW(r) (*reinterpret_cast<double2*>(V_b + (size_t)(unsigned)(r) * (size_t)ldb))
+#define VLOAD(r) __ldcg(reinterpret_cast<const double2*>(V_b + (size_t)(unsigned)(r) * (size_t)ldb))
+#define ILOAD(r) __ldcg(reinterpret_cast<const double2*>(I_b + (size_t)(unsigned)(r) * (size_t)ldb))
+#define IROW(r) (*reinterpret_cast<double2*>(I_b + (size_t)(unsigned)(r) * (size_t)ldb))
+#define SROW(r) __ldcg(reinterpret_cast<const double2*>(spu_b + (size_t)(unsigned)(r) * (size_t)ldb))
 
     // flat start (solution.py:108-125): V = I = 0.  I is read by the first forward
     // sweep and V rows that no edge feeds (non-regulated phases below a regulator)
     // keep their initial value, so both are zeroed here, coalesced, once.
-    for (int r = 0; r < n_vrows; ++r) Vs[(long long)r * ld] = make_double2(0.0, 0.0);
-    for (int r = 0; r < n_irows; ++r) Is[(long long)r * ld] = make_double2(0.0, 0.0);
+    for (int r = 0; r < n_vrows; ++r) VROW(r) = make_double2(0.0, 0.0);
+    for (int r = 0; r < n_irows; ++r) IROW(r) = make_double2(0.0, 0.0);
     int it = 0;
     double diff = -1.0;
     bool converged = false;   // Vtest = 0 -> max|0 - Vref| = 1 > tol (solution_fbs.py:85)
@@ -105,7 +111,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int* __restrict__ chil
     while (!converged && it < maxiter) {
         // V[root] = Vref  (:89)
 #pragma unroll
-        for (int p = 0; p < 3; ++p) Vs[(long long)k.root_vrow[p] * ld] = k.vref[p];
+        for (int p = 0; p < 3; ++p) VROW(k.root_vrow[p]) = k.vref[p];
 
         // ---- forward sweep (:92-98, update_voltage_forward :162-184) -------
         for (int pos = 0; pos < n_steps; ++pos) {
@@ -118,13 +124,13 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int* __restrict__ chil
             double2 Vp[3];
 #pragma unroll
             for (int p = 0; p < 3; ++p)
-                Vp[p] = prow[p] >= 0 ? Vs[(long long)prow[p] * ld] : make_double2(0.0, 0.0);
+                Vp[p] = prow[p] >= 0 ? VLOAD(prow[p]) : make_double2(0.0, 0.0);
             if (kind == GP_EDGE_VR) {   // vr_forward :138-160
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
                     const double g = __ldg(&st->gamma[p]);
                     if (g != 0.0 && brow[p] >= 0)
-                        Vs[(long long)brow[p] * ld] = make_double2(g * Vp[p].x, g * Vp[p].y);
+                        VROW(brow[p]) = make_double2(g * Vp[p].x, g * Vp[p].y);
                 }
                 continue;
             }
@@ -133,7 +139,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int* __restrict__ chil
             double2 Il[3];
 #pragma unroll
             for (int p = 0; p < 3; ++p)
-                Il[p] = erow[p] >= 0 ? Is[(long long)erow[p] * ld] : make_double2(0.0, 0.0);
+                Il[p] = erow[p] >= 0 ? ILOAD(erow[p]) : make_double2(0.0, 0.0);
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
                 if (brow[p] < 0) continue;
@@ -145,7 +151,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int* __restrict__ chil
                     v.x -= z.x * Il[q].x - z.y * Il[q].y;
                     v.y -= z.x * Il[q].y + z.y * Il[q].x;
                 }
-                Vs[(long long)brow[p] * ld] = v;
+                VROW(brow[p]) = v;
             }
         }
 
@@ -161,14 +167,14 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int* __restrict__ chil
             double2 Vb[3];
 #pragma unroll
             for (int p = 0; p < 3; ++p)
-                Vb[p] = brow[p] >= 0 ? Vs[(long long)brow[p] * ld] : make_double2(0.0, 0.0);
+                Vb[p] = brow[p] >= 0 ? VLOAD(brow[p]) : make_double2(0.0, 0.0);
             if (kind == GP_EDGE_VR) {   // vr_current leaves Itx = 0; vr_backward :186-205
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
                     const double g = __ldg(&st->gamma[p]);
                     if (g != 0.0 && prow[p] >= 0) {
                         const double ig = __ldg(&st->inv_gamma[p]);
-                        Vs[(long long)prow[p] * ld] = make_double2(ig * Vb[p].x, ig * Vb[p].y);
+                        VROW(prow[p]) = make_double2(ig * Vb[p].x, ig * Vb[p].y);
                     }
                 }
                 continue;
@@ -189,7 +195,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int* __restrict__ chil
                 const double a2 = cabs2(v, a);
                 double2 sv = make_double2(0.0, 0.0);
                 if (lrow[p] >= 0) {
-                    const double2 sp = spu_s[(long long)lrow[p] * ld];
+                    const double2 sp = SROW(lrow[p]);
                     const double f = k.aPQ + k.aI * a + k.aZ * a2;
                     sv.x = sp.x * f;
                     sv.y = sp.y * f;
@@ -204,22 +210,26 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int* __restrict__ chil
                 }
             }
             for (int c = 0; c < child_count; ++c) {
-                const int* cr = child_irow + 3 * (child_begin + c);
+                const int4 cr4 = __ldg(child_irow + child_begin + c);
+                const int cr[3] = {cr4.x, cr4.y, cr4.z};
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
-                    const int r = __ldg(cr + p);
+                    const int r = cr[p];
                     if (r >= 0) {
-                        const double2 ic = Is[(long long)r * ld];
+                        const double2 ic = ILOAD(r);
                         In[p].x += ic.x;
                         In[p].y += ic.y;
                     }
                 }
             }
+            // nan_to_num (:288) only does something for non-finite values: one test for all six
+            const bool weird = !(fabs(In[0].x) + fabs(In[0].y) + fabs(In[1].x) + fabs(In[1].y) + fabs(In[2].x) +
+                                 fabs(In[2].y) <= 1.7976931348623157e308);
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
                 if (erow[p] >= 0) {
-                    In[p] = make_double2(nan_to_num(In[p].x), nan_to_num(In[p].y));
-                    Is[(long long)erow[p] * ld] = In[p];
+                    if (weird) In[p] = make_double2(nan_to_num(In[p].x), nan_to_num(In[p].y));
+                    IROW(erow[p]) = In[p];
                 } else {
                     In[p] = make_double2(0.0, 0.0);
                 }
@@ -236,7 +246,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int* __restrict__ chil
                     v.x += z.x * In[q].x - z.y * In[q].y;
                     v.y += z.x * In[q].y + z.y * In[q].x;
                 }
-                Vs[(long long)prow[p] * ld] = v;
+                VROW(prow[p]) = v;
             }
         }
 
@@ -246,7 +256,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int* __restrict__ chil
         bool nan = false;
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
-            const double2 v = Vs[(long long)k.root_vrow[p] * ld];
+            const double2 v = VLOAD(k.root_vrow[p]);
             const double dx = v.x - k.vref[p].x, dy = v.y - k.vref[p].y;
             const double d = sqrt(fma(dx, dx, dy * dy));
             nan |= (d != d);
@@ -257,6 +267,11 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int* __restrict__ chil
     }
     iters_out[s] = it;
     diff_out[s] = diff;
+#undef VROW
+#undef VLOAD
+#undef ILOAD
+#undef IROW
+#undef SROW
     status_out[s] = converged ? GP_ST_CONVERGED : ((diff != diff || isinf(diff)) ? GP_ST_NONFINITE : GP_ST_MAXITER);
 }
 
@@ -751,7 +766,10 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
     cudaError_t e = up((void**)&im->d_steps, steps.data(), steps.size() * sizeof(FbsStep));
     if (e == cudaSuccess) e = up((void**)&im->d_events, events.data(), events.size() * sizeof(int2));
     if (e == cudaSuccess) e = up((void**)&im->d_evrows, evrows.data(), evrows.size() * sizeof(int4));
-    if (e == cudaSuccess) e = up((void**)&im->d_child, d->child_irow, (size_t)d->n_child * 3 * sizeof(int));
+    std::vector<int4> child4((size_t)d->n_child);
+    for (int c = 0; c < d->n_child; ++c)
+        child4[c] = make_int4(d->child_irow[3 * c], d->child_irow[3 * c + 1], d->child_irow[3 * c + 2], 0);
+    if (e == cudaSuccess) e = up((void**)&im->d_child, child4.data(), child4.size() * sizeof(int4));
     if (e == cudaSuccess) e = up((void**)&im->d_lines, lines.data(), lines.size() * sizeof(int));
     if (e == cudaSuccess) e = up((void**)&im->d_vrow_srow, vrow_srow.data(), vrow_srow.size() * sizeof(int));
     if (e == cudaSuccess) e = up((void**)&im->d_vrow_cap, vrow_cap.data(), vrow_cap.size() * sizeof(double));
@@ -806,11 +824,13 @@ extern "C" int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
     FbsImpl* im = (FbsImpl*)f->impl;
     if (!V || !I || !iters || !status || !diff || (!spu && im->n_srows > 0))
         return fail(GP_EINVAL, "gp_fbs_solve_batch: null buffer");
+    if (ld * 16 >= ((int64_t)1 << 32))
+        return fail(GP_EINVAL, "gp_fbs_solve_batch: row pitch ld must be below 2^28 scenarios; split the batch");
     GP_CUDA(cudaSetDevice(f->device));
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int BLOCK = 128;
     const unsigned gx = (unsigned)((S + BLOCK - 1) / BLOCK);
-    const bool dfs = im->n_events > 0 && ld * 16 < ((int64_t)1 << 32) && !g_force_sweep_kernel;
+    const bool dfs = im->n_events > 0 && !g_force_sweep_kernel;
     if (dfs) {
         const unsigned ldb = (unsigned)(ld * 16);
 #define GP_DFS(D)                                                                                          \
@@ -824,8 +844,8 @@ extern "C" int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
 #undef GP_DFS
     } else {
         fbs_solve_kernel<BLOCK><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
-                                                      im->n_irows, S, ld, (const double2*)spu, (double2*)V,
-                                                      (double2*)I, iters, status, diff, tol, maxiter);
+                                                      im->n_irows, S, (unsigned)(ld * 16), (const char*)spu, (char*)V,
+                                                      (char*)I, iters, status, diff, tol, maxiter);
     }
     count_launch();
     GP_CUDA(cudaGetLastError());
