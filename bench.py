@@ -432,7 +432,7 @@ def run_ours(args, wl):
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
             'config': {'workload': desc, 'solver': solver, 'scenarios_per_gpu': S,
-                       'fbs_kernel': 'fused-dfs' if args.fbs_kernel else 'two-sweep',
+                       'fbs_kernel': ['two-sweep', 'fused-dfs', 'phase-parallel'][args.fbs_kernel],
                        'rows': {'P_b': t.n_vrows, 'P_l': t.n_irows, 'P_L': t.n_srows},
                        'mean_iterations': float(its.mean()), 'max_iterations': int(its.max()),
                        'l2': 'flushed between steps (256 MiB write, untimed)',
@@ -475,8 +475,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    ap.add_argument('--fbs-kernel', type=int, default=0, choices=[0, 1],
-                    help='0 = two-sweep FBS kernel (default), 1 = fused depth-first kernel (A/B timing)')
+    ap.add_argument('--fbs-kernel', type=int, default=0, choices=[0, 1, 2],
+                    help='0 = two-sweep FBS kernel (default), 1 = fused depth-first, 2 = phase-parallel lanes')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':

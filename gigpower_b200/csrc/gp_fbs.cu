@@ -23,7 +23,7 @@ namespace gp {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
-static bool g_force_sweep_kernel = true;    // gp_set_option("fbs_kernel", 1) selects the fused depth-first kernel
+static int g_fbs_kernel = 0;   // gp_set_option("fbs_kernel", v): 0 two-sweep, 1 fused depth-first, 2 phase-parallel
 
 struct __align__(16) FbsStep {
     int bus_vrow[3];
@@ -79,6 +79,123 @@ __device__ __forceinline__ double cabs2(double2 v, double& a) {
     return a * a;
 }
 
+// Row r of scenario s lives at base + s*16 + r*ldb: one 32x32->64 multiply-add per access.
+// State rows are read through L2 only (ld.global.cg): they are touched once per sweep, so
+// keeping them out of L1 leaves L1 to the step table that every warp re-reads.
+#define GP_LD(base, r) __ldcg(reinterpret_cast<const double2*>((base) + (size_t)(unsigned)(r) * (size_t)ldb))
+#define GP_ST(base, r, v) (*reinterpret_cast<double2*>((base) + (size_t)(unsigned)(r) * (size_t)ldb) = (v))
+
+// ---- mask-specialised step bodies -----------------------------------------------------------
+// Most buses carry exactly the phases of their incoming line and their parent carries them too.
+// For those steps (FbsStep fast mask M != 0) the phase pattern is a compile-time constant: no
+// row tests, no predicated arithmetic, straight-line FP64.  The branch on M is uniform (every
+// thread walks the same feeder).  Everything else takes the general body below.
+template <int M>
+__device__ __forceinline__ void fwd_fast(const FbsStep* __restrict__ st, const int4 bv, const int4 pv,
+                                         char* V_b, const char* I_b, unsigned ldb) {
+    const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
+    const int brow[3] = {bv.x, bv.y, bv.z}, prow[3] = {pv.x, pv.y, pv.z}, erow[3] = {ev.x, ev.y, ev.z};
+    double2 Vp[3], Il[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+        if ((M >> p) & 1) {
+            Vp[p] = GP_LD(V_b, prow[p]);
+            Il[p] = GP_LD(I_b, erow[p]);
+        }
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+        if ((M >> p) & 1) {
+            double2 v = Vp[p];
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if ((M >> q) & 1) {
+                    const double2 z = __ldg(&st->z[3 * p + q]);
+                    v.x -= z.x * Il[q].x - z.y * Il[q].y;
+                    v.y -= z.x * Il[q].y + z.y * Il[q].x;
+                }
+            GP_ST(V_b, brow[p], v);
+        }
+}
+
+template <int M>
+__device__ __forceinline__ void bwd_fast(const FbsStep* __restrict__ st, const int4 bv, const int4 pv,
+                                         const int4* __restrict__ child_irow, const FbsConst& k,
+                                         char* V_b, char* I_b, const char* spu_b, unsigned ldb) {
+    const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
+    const int4 lv = __ldg(reinterpret_cast<const int4*>(st->load_srow));
+    const int brow[3] = {bv.x, bv.y, bv.z}, prow[3] = {pv.x, pv.y, pv.z};
+    const int erow[3] = {ev.x, ev.y, ev.z}, lrow[3] = {lv.x, lv.y, lv.z};
+    double2 Vb[3], sp[3], In[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+        if ((M >> p) & 1) {
+            Vb[p] = GP_LD(V_b, brow[p]);
+            sp[p] = lrow[p] >= 0 ? GP_LD(spu_b, lrow[p]) : make_double2(0.0, 0.0);
+            In[p] = make_double2(0.0, 0.0);
+        }
+    for (int c = 0; c < ev.w; ++c) {                    // children's currents (:274-284)
+        const int4 cr = __ldg(child_irow + pv.w + c);
+        const int crow[3] = {cr.x, cr.y, cr.z};
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+            if (((M >> p) & 1) && crow[p] >= 0) {
+                const double2 ic = GP_LD(I_b, crow[p]);
+                In[p].x += ic.x;
+                In[p].y += ic.y;
+            }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+        if ((M >> p) & 1) {                             // calc_sV (solution.py:177-220) + update_current (:256-288)
+            const double2 v = Vb[p];
+            double a;
+            const double a2 = cabs2(v, a);
+            const double f = k.aPQ + k.aI * a + k.aZ * a2;
+            double2 sv = make_double2(sp[p].x * f, sp[p].y * f);
+            sv.y -= __ldg(&st->cap[p]) * a2;
+            if (v.x != 0.0 || v.y != 0.0) {
+                const double inv = 1.0 / fma(v.x, v.x, v.y * v.y);
+                In[p].x += (sv.x * v.x + sv.y * v.y) * inv;
+                In[p].y -= (sv.y * v.x - sv.x * v.y) * inv;
+            }
+            sum += fabs(In[p].x) + fabs(In[p].y);
+        }
+    if (!(sum <= 1.7976931348623157e308)) {             // nan_to_num (:288) acts on non-finite values only
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+            if ((M >> p) & 1) In[p] = make_double2(nan_to_num(In[p].x), nan_to_num(In[p].y));
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+        if ((M >> p) & 1) GP_ST(I_b, erow[p], In[p]);
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+        if ((M >> p) & 1) {                             // update_voltage_backward (:207-232)
+            double2 v = Vb[p];
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if ((M >> q) & 1) {
+                    const double2 z = __ldg(&st->z[3 * p + q]);
+                    v.x += z.x * In[q].x - z.y * In[q].y;
+                    v.y += z.x * In[q].y + z.y * In[q].x;
+                }
+            GP_ST(V_b, prow[p], v);
+        }
+}
+
+#define GP_FAST_SWITCH(fn, ...)                 \
+    switch (fast) {                             \
+        case 7: fn<7>(__VA_ARGS__); continue;   \
+        case 1: fn<1>(__VA_ARGS__); continue;   \
+        case 2: fn<2>(__VA_ARGS__); continue;   \
+        case 4: fn<4>(__VA_ARGS__); continue;   \
+        case 3: fn<3>(__VA_ARGS__); continue;   \
+        case 5: fn<5>(__VA_ARGS__); continue;   \
+        case 6: fn<6>(__VA_ARGS__); continue;   \
+        default: break;                         \
+    }
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)   // <= 64 registers: 1024 resident threads per SM
 fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ child_irow,
@@ -89,21 +206,16 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
                  int maxiter) {
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (s >= S) return;
-    // row r of scenario s lives at base + s*16 + r*ldb: one 32x32->64 multiply-add per access
     const char* spu_b = spu + s * 16;
     char* V_b = V + s * 16;
     char* I_b = I + s * 16;
-#define VROW(r) (*reinterpret_cast<double2*>(V_b + (size_t)(unsigned)(r) * (size_t)ldb))
-#define VLOAD(r) __ldcg(reinterpret_cast<const double2*>(V_b + (size_t)(unsigned)(r) * (size_t)ldb))
-#define ILOAD(r) __ldcg(reinterpret_cast<const double2*>(I_b + (size_t)(unsigned)(r) * (size_t)ldb))
-#define IROW(r) (*reinterpret_cast<double2*>(I_b + (size_t)(unsigned)(r) * (size_t)ldb))
-#define SROW(r) __ldcg(reinterpret_cast<const double2*>(spu_b + (size_t)(unsigned)(r) * (size_t)ldb))
+    const double2 zero = make_double2(0.0, 0.0);
 
     // flat start (solution.py:108-125): V = I = 0.  I is read by the first forward
     // sweep and V rows that no edge feeds (non-regulated phases below a regulator)
     // keep their initial value, so both are zeroed here, coalesced, once.
-    for (int r = 0; r < n_vrows; ++r) VROW(r) = make_double2(0.0, 0.0);
-    for (int r = 0; r < n_irows; ++r) IROW(r) = make_double2(0.0, 0.0);
+    for (int r = 0; r < n_vrows; ++r) GP_ST(V_b, r, zero);
+    for (int r = 0; r < n_irows; ++r) GP_ST(I_b, r, zero);
     int it = 0;
     double diff = -1.0;
     bool converged = false;   // Vtest = 0 -> max|0 - Vref| = 1 > tol (solution_fbs.py:85)
@@ -111,26 +223,25 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
     while (!converged && it < maxiter) {
         // V[root] = Vref  (:89)
 #pragma unroll
-        for (int p = 0; p < 3; ++p) VROW(k.root_vrow[p]) = k.vref[p];
+        for (int p = 0; p < 3; ++p) GP_ST(V_b, k.root_vrow[p], k.vref[p]);
 
         // ---- forward sweep (:92-98, update_voltage_forward :162-184) -------
         for (int pos = 0; pos < n_steps; ++pos) {
             const FbsStep* st = steps + pos;
             const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
             const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
+            const int kind = bv.w & 0xff, fast = bv.w >> 8;
+            GP_FAST_SWITCH(fwd_fast, st, bv, pv, V_b, I_b, ldb)
             const int brow[3] = {bv.x, bv.y, bv.z};
             const int prow[3] = {pv.x, pv.y, pv.z};
-            const int kind = bv.w;
             double2 Vp[3];
 #pragma unroll
-            for (int p = 0; p < 3; ++p)
-                Vp[p] = prow[p] >= 0 ? VLOAD(prow[p]) : make_double2(0.0, 0.0);
+            for (int p = 0; p < 3; ++p) Vp[p] = prow[p] >= 0 ? GP_LD(V_b, prow[p]) : zero;
             if (kind == GP_EDGE_VR) {   // vr_forward :138-160
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
                     const double g = __ldg(&st->gamma[p]);
-                    if (g != 0.0 && brow[p] >= 0)
-                        VROW(brow[p]) = make_double2(g * Vp[p].x, g * Vp[p].y);
+                    if (g != 0.0 && brow[p] >= 0) GP_ST(V_b, brow[p], make_double2(g * Vp[p].x, g * Vp[p].y));
                 }
                 continue;
             }
@@ -138,8 +249,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
             const int erow[3] = {ev.x, ev.y, ev.z};
             double2 Il[3];
 #pragma unroll
-            for (int p = 0; p < 3; ++p)
-                Il[p] = erow[p] >= 0 ? ILOAD(erow[p]) : make_double2(0.0, 0.0);
+            for (int p = 0; p < 3; ++p) Il[p] = erow[p] >= 0 ? GP_LD(I_b, erow[p]) : zero;
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
                 if (brow[p] < 0) continue;
@@ -151,7 +261,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
                     v.x -= z.x * Il[q].x - z.y * Il[q].y;
                     v.y -= z.x * Il[q].y + z.y * Il[q].x;
                 }
-                VROW(brow[p]) = v;
+                GP_ST(V_b, brow[p], v);
             }
         }
 
@@ -160,21 +270,21 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
             const FbsStep* st = steps + pos;
             const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
             const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
+            const int kind = bv.w & 0xff, fast = bv.w >> 8;
+            GP_FAST_SWITCH(bwd_fast, st, bv, pv, child_irow, k, V_b, I_b, spu_b, ldb)
             const int brow[3] = {bv.x, bv.y, bv.z};
             const int prow[3] = {pv.x, pv.y, pv.z};
-            const int kind = bv.w;
             const int child_begin = pv.w;
             double2 Vb[3];
 #pragma unroll
-            for (int p = 0; p < 3; ++p)
-                Vb[p] = brow[p] >= 0 ? VLOAD(brow[p]) : make_double2(0.0, 0.0);
+            for (int p = 0; p < 3; ++p) Vb[p] = brow[p] >= 0 ? GP_LD(V_b, brow[p]) : zero;
             if (kind == GP_EDGE_VR) {   // vr_current leaves Itx = 0; vr_backward :186-205
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
                     const double g = __ldg(&st->gamma[p]);
                     if (g != 0.0 && prow[p] >= 0) {
                         const double ig = __ldg(&st->inv_gamma[p]);
-                        VROW(prow[p]) = make_double2(ig * Vb[p].x, ig * Vb[p].y);
+                        GP_ST(V_b, prow[p], make_double2(ig * Vb[p].x, ig * Vb[p].y));
                     }
                 }
                 continue;
@@ -188,21 +298,21 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
             double2 In[3];
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
-                In[p] = make_double2(0.0, 0.0);
+                In[p] = zero;
                 if (brow[p] < 0) continue;
                 const double2 v = Vb[p];
                 double a;
                 const double a2 = cabs2(v, a);
-                double2 sv = make_double2(0.0, 0.0);
+                double2 sv = zero;
                 if (lrow[p] >= 0) {
-                    const double2 sp = SROW(lrow[p]);
+                    const double2 sp = GP_LD(spu_b, lrow[p]);
                     const double f = k.aPQ + k.aI * a + k.aZ * a2;
                     sv.x = sp.x * f;
                     sv.y = sp.y * f;
                 }
                 sv.y -= __ldg(&st->cap[p]) * a2;
                 if (v.x != 0.0 || v.y != 0.0) {
-                    // conj(sV / V) = conj(sV) * V / |V|^2 ... computed as (sV * conj(V)) / |V|^2, conjugated
+                    // conj(sV / V) computed as (sV * conj(V)) / |V|^2, conjugated
                     const double inv = 1.0 / fma(v.x, v.x, v.y * v.y);
                     const double qr = (sv.x * v.x + sv.y * v.y) * inv;
                     const double qi = (sv.y * v.x - sv.x * v.y) * inv;
@@ -213,25 +323,20 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
                 const int4 cr4 = __ldg(child_irow + child_begin + c);
                 const int cr[3] = {cr4.x, cr4.y, cr4.z};
 #pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    const int r = cr[p];
-                    if (r >= 0) {
-                        const double2 ic = ILOAD(r);
+                for (int p = 0; p < 3; ++p)
+                    if (cr[p] >= 0) {
+                        const double2 ic = GP_LD(I_b, cr[p]);
                         In[p].x += ic.x;
                         In[p].y += ic.y;
                     }
-                }
             }
-            // nan_to_num (:288) only does something for non-finite values: one test for all six
-            const bool weird = !(fabs(In[0].x) + fabs(In[0].y) + fabs(In[1].x) + fabs(In[1].y) + fabs(In[2].x) +
-                                 fabs(In[2].y) <= 1.7976931348623157e308);
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
                 if (erow[p] >= 0) {
-                    if (weird) In[p] = make_double2(nan_to_num(In[p].x), nan_to_num(In[p].y));
-                    IROW(erow[p]) = In[p];
+                    In[p] = make_double2(nan_to_num(In[p].x), nan_to_num(In[p].y));
+                    GP_ST(I_b, erow[p], In[p]);
                 } else {
-                    In[p] = make_double2(0.0, 0.0);
+                    In[p] = zero;
                 }
             }
             // update_voltage_backward (:207-232): phases of the child bus, masked by the parent
@@ -246,7 +351,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
                     v.x += z.x * In[q].x - z.y * In[q].y;
                     v.y += z.x * In[q].y + z.y * In[q].x;
                 }
-                VROW(prow[p]) = v;
+                GP_ST(V_b, prow[p], v);
             }
         }
 
@@ -256,7 +361,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
         bool nan = false;
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
-            const double2 v = VLOAD(k.root_vrow[p]);
+            const double2 v = GP_LD(V_b, k.root_vrow[p]);
             const double dx = v.x - k.vref[p].x, dy = v.y - k.vref[p].y;
             const double d = sqrt(fma(dx, dx, dy * dy));
             nan |= (d != d);
@@ -267,12 +372,180 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
     }
     iters_out[s] = it;
     diff_out[s] = diff;
-#undef VROW
+    status_out[s] = converged ? GP_ST_CONVERGED : ((diff != diff || isinf(diff)) ? GP_ST_NONFINITE : GP_ST_MAXITER);
+}
+
+// ---------------------------------------------------------------------------------------
+// Phase-parallel two-sweep kernel.
+//
+// Same sweeps as fbs_solve_kernel, but a scenario is owned by THREE lanes, one per phase
+// (lane = phase * 10 + j inside a warp: 10 scenarios per warp, lanes 30/31 idle).  A lane
+// touches only the rows of its own phase, so there is no cross-lane memory dependency; the
+// 3x3 coupling (Z I) is the only exchange and goes through warp shuffles.  Per warp a row
+// access is three 160-byte coalesced segments.  Compared with one thread per scenario the
+// serial chain per tree step is a third as long and there are three times as many warps to
+// hide latency with, which is what a batch of about one wave (BASELINE config C2) needs.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int sel3(const int4 v, int g) { return g == 0 ? v.x : (g == 1 ? v.y : v.z); }
+
+__device__ __forceinline__ double2 shfl2(double2 v, int src) {
+    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1536 / BLOCK)   // <= 42 registers: 48 warps per SM
+fbs_phase_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ child_irow, FbsConst k,
+                 int n_steps, int n_vrows, int n_irows, long long S, unsigned ldb,
+                 const char* __restrict__ spu, char* __restrict__ V, char* __restrict__ I,
+                 int* __restrict__ iters_out, int* __restrict__ status_out, double* __restrict__ diff_out,
+                 double tol, int maxiter) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * BLOCK + threadIdx.x) >> 5;
+    const int j = lane % 10;
+    const int g = lane < 30 ? lane / 10 : 2;            // phase of this lane (idle lanes mirror phase c)
+    const long long s_raw = warp * 10 + j;
+    const bool owner = lane < 30 && s_raw < S;          // lanes that own real data
+    const long long s = s_raw < S ? s_raw : S - 1;
+    const int src1 = ((g + 1) % 3) * 10 + j, src2 = ((g + 2) % 3) * 10 + j;   // the other two phases
+    const int g1 = (g + 1) % 3, g2 = (g + 2) % 3;
+    const char* spu_b = spu + s * 16;
+    char* V_b = V + s * 16;
+    char* I_b = I + s * 16;
+#define VLOAD(r) __ldcg(reinterpret_cast<const double2*>(V_b + (size_t)(unsigned)(r) * (size_t)ldb))
+#define ILOAD(r) __ldcg(reinterpret_cast<const double2*>(I_b + (size_t)(unsigned)(r) * (size_t)ldb))
+#define SLOAD(r) __ldcg(reinterpret_cast<const double2*>(spu_b + (size_t)(unsigned)(r) * (size_t)ldb))
+#define VSTORE(r, v) (*reinterpret_cast<double2*>(V_b + (size_t)(unsigned)(r) * (size_t)ldb) = (v))
+#define ISTORE(r, v) (*reinterpret_cast<double2*>(I_b + (size_t)(unsigned)(r) * (size_t)ldb) = (v))
+    const double2 zero = make_double2(0.0, 0.0);
+    if (owner) {     // flat start: V = I = 0 (each phase lane clears a third of the rows)
+        for (int r = g; r < n_vrows; r += 3) VSTORE(r, zero);
+        for (int r = g; r < n_irows; r += 3) ISTORE(r, zero);
+    }
+    __syncwarp();
+    const int root_row = g == 0 ? k.root_vrow[0] : (g == 1 ? k.root_vrow[1] : k.root_vrow[2]);
+    const double2 vref = g == 0 ? k.vref[0] : (g == 1 ? k.vref[1] : k.vref[2]);
+    int it = 0;
+    double diff = -1.0;
+    bool converged = false;
+    bool active = owner;
+    while (__any_sync(0xffffffffu, active)) {
+        if (active) VSTORE(root_row, vref);                                  // V[root] = Vref (:89)
+        __syncwarp();        // the zero-fill above was striped over the three lanes of a scenario
+        // ---- forward sweep (:92-98) -----------------------------------------------------
+        for (int pos = 0; pos < n_steps; ++pos) {
+            const FbsStep* st = steps + pos;
+            const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
+            const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
+            const int myb = sel3(bv, g), myp = sel3(pv, g);
+            const double2 Vp = (active && myp >= 0) ? VLOAD(myp) : zero;
+            if ((bv.w & 0xff) == GP_EDGE_VR) {                               // vr_forward :138-160
+                const double gm = __ldg(&st->gamma[g]);
+                if (active && gm != 0.0 && myb >= 0) VSTORE(myb, make_double2(gm * Vp.x, gm * Vp.y));
+                continue;
+            }
+            const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
+            const int mye = sel3(ev, g);
+            const double2 I0 = (active && mye >= 0) ? ILOAD(mye) : zero;
+            const double2 I1 = shfl2(I0, src1), I2 = shfl2(I0, src2);
+            if (active && myb >= 0) {                                        // update_voltage_forward :162-184
+                double2 v = Vp;
+                const double2 z0 = __ldg(&st->z[3 * g + g]), z1 = __ldg(&st->z[3 * g + g1]),
+                              z2 = __ldg(&st->z[3 * g + g2]);
+                v.x -= z0.x * I0.x - z0.y * I0.y;
+                v.y -= z0.x * I0.y + z0.y * I0.x;
+                v.x -= z1.x * I1.x - z1.y * I1.y;
+                v.y -= z1.x * I1.y + z1.y * I1.x;
+                v.x -= z2.x * I2.x - z2.y * I2.y;
+                v.y -= z2.x * I2.y + z2.y * I2.x;
+                VSTORE(myb, v);
+            }
+        }
+        // ---- backward sweep (:104-121) ---------------------------------------------------
+        for (int pos = n_steps - 1; pos >= 0; --pos) {
+            const FbsStep* st = steps + pos;
+            const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
+            const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
+            const int myb = sel3(bv, g), myp = sel3(pv, g);
+            const double2 Vb = (active && myb >= 0) ? VLOAD(myb) : zero;
+            if ((bv.w & 0xff) == GP_EDGE_VR) {                               // vr_backward :186-205
+                const double gm = __ldg(&st->gamma[g]);
+                if (active && gm != 0.0 && myp >= 0) {
+                    const double ig = __ldg(&st->inv_gamma[g]);
+                    VSTORE(myp, make_double2(ig * Vb.x, ig * Vb.y));
+                }
+                continue;
+            }
+            const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
+            const int4 lv = __ldg(reinterpret_cast<const int4*>(st->load_srow));
+            const int mye = sel3(ev, g), myl = sel3(lv, g);
+            const double2 sp = (active && myl >= 0) ? SLOAD(myl) : zero;
+            double2 In = zero;
+            for (int c = 0; c < ev.w; ++c) {                                 // children's currents (:274-284)
+                const int r = sel3(__ldg(child_irow + pv.w + c), g);
+                if (active && r >= 0) {
+                    const double2 ic = ILOAD(r);
+                    In.x += ic.x;
+                    In.y += ic.y;
+                }
+            }
+            if (myb >= 0) {                                                  // calc_sV + update_current
+                double a;
+                const double a2 = cabs2(Vb, a);
+                const double f = k.aPQ + k.aI * a + k.aZ * a2;
+                double2 sv = make_double2(sp.x * f, sp.y * f);
+                sv.y -= __ldg(&st->cap[g]) * a2;
+                if (Vb.x != 0.0 || Vb.y != 0.0) {
+                    const double inv = 1.0 / fma(Vb.x, Vb.x, Vb.y * Vb.y);
+                    In.x += (sv.x * Vb.x + sv.y * Vb.y) * inv;
+                    In.y -= (sv.y * Vb.x - sv.x * Vb.y) * inv;
+                }
+            }
+            if (mye >= 0) {
+                In = make_double2(nan_to_num(In.x), nan_to_num(In.y));
+                if (active) ISTORE(mye, In);
+            } else {
+                In = zero;
+            }
+            const double2 I1 = shfl2(In, src1), I2 = shfl2(In, src2);
+            if (active && myb >= 0 && myp >= 0) {                            // update_voltage_backward :207-232
+                double2 v = Vb;
+                const double2 z0 = __ldg(&st->z[3 * g + g]), z1 = __ldg(&st->z[3 * g + g1]),
+                              z2 = __ldg(&st->z[3 * g + g2]);
+                v.x += z0.x * In.x - z0.y * In.y;
+                v.y += z0.x * In.y + z0.y * In.x;
+                v.x += z1.x * I1.x - z1.y * I1.y;
+                v.y += z1.x * I1.y + z1.y * I1.x;
+                v.x += z2.x * I2.x - z2.y * I2.y;
+                v.y += z2.x * I2.y + z2.y * I2.x;
+                VSTORE(myp, v);
+            }
+        }
+        // ---- convergence (:123-128): max over the three phase lanes ---------------------------
+        double d = 0.0;
+        if (active) {
+            const double2 v = VLOAD(root_row);
+            const double dx = v.x - vref.x, dy = v.y - vref.y;
+            d = sqrt(fma(dx, dx, dy * dy));
+        }
+        const double d1 = __shfl_sync(0xffffffffu, d, src1), d2 = __shfl_sync(0xffffffffu, d, src2);
+        if (active) {
+            ++it;
+            const bool nan = (d != d) | (d1 != d1) | (d2 != d2);
+            diff = nan ? __longlong_as_double(0x7ff8000000000000LL) : fmax(d, fmax(d1, d2));
+            converged = diff <= tol;
+            active = !converged && it < maxiter;
+        }
+    }
 #undef VLOAD
 #undef ILOAD
-#undef IROW
-#undef SROW
-    status_out[s] = converged ? GP_ST_CONVERGED : ((diff != diff || isinf(diff)) ? GP_ST_NONFINITE : GP_ST_MAXITER);
+#undef SLOAD
+#undef VSTORE
+#undef ISTORE
+    if (owner && lane < 10) {
+        iters_out[s] = it;
+        diff_out[s] = diff;
+        status_out[s] = converged ? GP_ST_CONVERGED : ((diff != diff || isinf(diff)) ? GP_ST_NONFINITE : GP_ST_MAXITER);
+    }
 }
 
 
@@ -369,7 +642,7 @@ fbs_dfs_kernel(const FbsStep* __restrict__ steps, const int2* __restrict__ event
             const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
             const int brow[3] = {bv.x, bv.y, bv.z};
             const int prow[3] = {pv.x, pv.y, pv.z};
-            const int kind = bv.w;
+            const int kind = bv.w & 0xff;
             if ((ev.y & EV_ASCEND) == 0) {
                 // ---------------- descend: forward update of this edge (:162-184 / :138-160)
                 // Save only what a later event of the parent still needs (see build_events).
@@ -598,8 +871,8 @@ extern "C" int gp_last_error(char* buf, size_t len) {
 extern "C" int64_t gp_launch_count(void) { return g_launches.load(); }
 
 extern "C" int gp_set_option(const char* name, int value) {
-    if (name && strcmp(name, "fbs_kernel") == 0) {      // 0 = two-sweep (default), 1 = fused depth-first
-        g_force_sweep_kernel = (value == 0);
+    if (name && strcmp(name, "fbs_kernel") == 0 && value >= 0 && value <= 2) {
+        g_fbs_kernel = value;
         return GP_OK;
     }
     return fail(GP_EINVAL, "gp_set_option: unknown option");
@@ -655,6 +928,19 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
             }
         }
     }
+    // fast mask (fwd_fast / bwd_fast): a Line/Transformer edge whose phases are exactly the bus
+    // phases, all present on the parent.  Stored above the kind byte.
+    for (int i = 0; i < d->n_steps; ++i) {
+        FbsStep& s = steps[i];
+        if (s.kind != GP_EDGE_LINE) continue;
+        int mb = 0, me = 0, mp = 0;
+        for (int p = 0; p < 3; ++p) {
+            mb |= (s.bus_vrow[p] >= 0) << p;
+            me |= (s.edge_irow[p] >= 0) << p;
+            mp |= (s.par_vrow[p] >= 0) << p;
+        }
+        if (mb != 0 && mb == me && (mp & mb) == mb) s.kind |= mb << 8;
+    }
     for (int p = 0; p < 3; ++p) {
         im->k.root_vrow[p] = d->root_vrow[p];
         im->k.root_load_srow[p] = d->root_load_srow[p];
@@ -694,7 +980,7 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
                 if (steps[i].par_vrow[p] >= 0) par = row_step[steps[i].par_vrow[p]];
             if (par < -1 || par >= i) ok = false;                     // parents come first in topo order
             else kids[par + 1].push_back(i);
-            if (steps[i].kind == GP_EDGE_VR)                          // regulator must cover every bus phase
+            if ((steps[i].kind & 0xff) == GP_EDGE_VR)                 // regulator must cover every bus phase
                 for (int p = 0; p < 3; ++p)
                     if (steps[i].bus_vrow[p] >= 0 && steps[i].gamma[p] == 0.0) ok = false;
         }
@@ -707,7 +993,7 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
             auto covers = [&](int c) {        // child c rewrites every existing phase of its parent?
                 for (int p = 0; p < 3; ++p)
                     if (steps[c].par_vrow[p] >= 0 && steps[c].bus_vrow[p] < 0) return false;
-                if (steps[c].kind == GP_EDGE_VR) return false;       // conservative
+                if ((steps[c].kind & 0xff) == GP_EDGE_VR) return false;   // conservative
                 return true;
             };
             struct Frame { int node, next; };
@@ -755,7 +1041,7 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
         const FbsStep& st = steps[events[e].x];
         const bool asc = (events[e].y & EV_ASCEND) != 0;
         const int* r = asc ? st.load_srow : st.edge_irow;
-        if (st.kind == GP_EDGE_VR) evrows[e] = make_int4(-1, -1, -1, asc ? 0 : 1);
+        if ((st.kind & 0xff) == GP_EDGE_VR) evrows[e] = make_int4(-1, -1, -1, asc ? 0 : 1);
         else evrows[e] = make_int4(r[0], r[1], r[2], asc ? 0 : 1);
     }
     auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
@@ -830,8 +1116,14 @@ extern "C" int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int BLOCK = 128;
     const unsigned gx = (unsigned)((S + BLOCK - 1) / BLOCK);
-    const bool dfs = im->n_events > 0 && !g_force_sweep_kernel;
-    if (dfs) {
+    const bool dfs = im->n_events > 0 && g_fbs_kernel == 1;
+    if (g_fbs_kernel == 2) {
+        const long long warps = (S + 9) / 10;
+        const unsigned gp = (unsigned)((warps * 32 + BLOCK - 1) / BLOCK);
+        fbs_phase_kernel<BLOCK><<<gp, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
+                                                      im->n_irows, S, (unsigned)(ld * 16), (const char*)spu, (char*)V,
+                                                      (char*)I, iters, status, diff, tol, maxiter);
+    } else if (dfs) {
         const unsigned ldb = (unsigned)(ld * 16);
 #define GP_DFS(D)                                                                                          \
     fbs_dfs_kernel<BLOCK, D><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_events, im->d_evrows, im->n_events, im->k, S, ldb, \

@@ -102,9 +102,9 @@ int gp_last_error(char* buf, size_t len);
 int64_t gp_launch_count(void);
 
 /*
- * Process-wide switches.  "fbs_kernel": 0 (default) = two-sweep kernel (the faster one on
- * B200 so far, profiles/r01b_*), 1 = fused depth-first sweep kernel when the feeder allows
- * it (same results; fewer HBM bytes by design, kept for A/B timing).
+ * Process-wide switches.  "fbs_kernel" selects the FBS solve kernel (identical results):
+ * 0 = two-sweep, one thread per scenario (default); 1 = fused depth-first walk; 2 = two-sweep
+ * with three phase lanes per scenario.
  */
 int gp_set_option(const char* name, int value);
 

@@ -177,12 +177,12 @@ def test_two_sweep_kernel_and_fused_dfs_kernel_agree(feeder):
     s = _fbs(feeder)
     res = {}
     try:
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             _cabi.check(_cabi.gp_set_option(b'fbs_kernel', mode))
             res[mode] = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
     finally:
         _cabi.gp_set_option(b'fbs_kernel', 0)
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         assert np.array_equal(res[mode].iterations, want['iterations']), mode
         assert rel_err(res[mode].V, want['V']) <= TOL and rel_err(res[mode].I, want['I']) <= TOL, mode
-    assert rel_err(res[0].V, res[1].V) <= 1e-12
+    assert rel_err(res[0].V, res[1].V) <= 1e-12 and rel_err(res[0].V, res[2].V) <= 1e-12
