@@ -41,6 +41,10 @@ WORKLOADS = {
               'C4: IEEE 123-bus (reconstruction) NR3, fixed 1/8 sub-sample of the 8,760 h x 128 DER set: 17,520 per GPU'),
     'c5': ('synth2500_radial.dss', 'fbs', 131072, 2500, (0.3, 0.9),
            'C5: synthetic 2,541-bus radial FBS, 2^20 scenarios U(0.3,0.9), 1/8 (131,072) per GPU'),
+    'nr3_37_big': ('IEEE_37_Bus_allwye_noxfm_noreg.json', 'nr3', 262144, 37, (0.5, 1.5),
+                   'IEEE 37-bus NR3, 262,144 scenarios (throughput regime of the C3 kernel)'),
+    'nr3_123_big': ('ieee123_allwye_noxfm_noreg.dss', 'nr3', 140160, 123, 'der',
+                    'IEEE 123-bus NR3, 140,160 DER scenarios (throughput regime)'),
     'fbs37': ('IEEE_37_Bus_allwye_noxfm_noreg.json', 'fbs', 65536, 37, (0.5, 1.5),
               'IEEE 37-bus FBS, 65,536 scenarios'),
     'fbs34': ('IEEE_34_Bus_allwye_noxfm_noreg.json', 'fbs', 65536, 34, (0.5, 1.3),

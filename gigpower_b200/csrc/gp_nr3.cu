@@ -145,22 +145,24 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             const int brow[3] = {bv.x, bv.y, bv.z}, prow[3] = {pv.x, pv.y, pv.z};
             const int erow[3] = {ev.x, ev.y, ev.z}, lrow[3] = {lv.x, lv.y, lv.z};
             const int child_count = bv.w, child_begin = pv.w, kind = ev.w, aux = lv.w;
-            double2 v[3], inet[3], r1[3];
+            // every load of the step is issued before the first use (one exposed round trip, not one per phase)
+            double2 v[3], inet[3], r1[3], vpar[3], spl[3];
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
-                v[p] = inet[p] = r1[p] = make_double2(0.0, 0.0);
+                v[p] = inet[p] = r1[p] = vpar[p] = spl[p] = make_double2(0.0, 0.0);
                 if (brow[p] < 0) continue;
                 v[p] = Xs[(long long)brow[p] * ld];
                 inet[p] = Xs[(long long)erow[p] * ld];
+                if (prow[p] >= 0) vpar[p] = Xs[(long long)prow[p] * ld];
+                if (lrow[p] >= 0) spl[p] = spu_s[(long long)lrow[p] * ld];
             }
             if (kind == GP_EDGE_LINE) {
                 // KVL residual r1 = E v_p - v - Z i   (:141-158; transformers :165-175 with Z = 0)
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
                     if (brow[p] < 0) continue;
-                    if (prow[p] >= 0) r1[p] = Xs[(long long)prow[p] * ld];
-                    r1[p].x -= v[p].x;
-                    r1[p].y -= v[p].y;
+                    r1[p].x = vpar[p].x - v[p].x;
+                    r1[p].y = vpar[p].y - v[p].y;
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
                         if (brow[q] < 0) continue;
@@ -187,24 +189,34 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                 const int4 ch = __ldg(childs + child_begin + c);
                 const int crow[3] = {ch.y, ch.z, ch.w};
                 const double2* Wc = Ws + (long long)ch.x * FRONT_D2 * ld;
+                double2 ic[3], ac[3], yc[6][3];
 #pragma unroll
-                for (int p = 0; p < 3; ++p) {
+                for (int p = 0; p < 3; ++p) {           // issue the child's whole front, then consume it
+                    ic[p] = ac[p] = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) yc[2 * p][q] = yc[2 * p + 1][q] = make_double2(0.0, 0.0);
                     if (crow[p] < 0) continue;
-                    const double2 ic = Xs[(long long)crow[p] * ld];
-                    inet[p].x -= ic.x;
-                    inet[p].y -= ic.y;
-                    const double2 ac = Wc[(long long)(18 + p) * ld];
-                    rt[2 * p] += ac.x;
-                    rt[2 * p + 1] += ac.y;
+                    ic[p] = Xs[(long long)crow[p] * ld];
+                    ac[p] = Wc[(long long)(18 + p) * ld];
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
                         if (crow[q] < 0) continue;      // only the child's own phases were stored
-                        const double2 y0 = Wc[(long long)((2 * p) * 3 + q) * ld];
-                        const double2 y1 = Wc[(long long)((2 * p + 1) * 3 + q) * ld];
-                        Dt[2 * p][2 * q] += y0.x;
-                        Dt[2 * p][2 * q + 1] += y0.y;
-                        Dt[2 * p + 1][2 * q] += y1.x;
-                        Dt[2 * p + 1][2 * q + 1] += y1.y;
+                        yc[2 * p][q] = Wc[(long long)((2 * p) * 3 + q) * ld];
+                        yc[2 * p + 1][q] = Wc[(long long)((2 * p + 1) * 3 + q) * ld];
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    inet[p].x -= ic[p].x;
+                    inet[p].y -= ic[p].y;
+                    rt[2 * p] += ac[p].x;
+                    rt[2 * p + 1] += ac[p].y;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        Dt[2 * p][2 * q] += yc[2 * p][q].x;
+                        Dt[2 * p][2 * q + 1] += yc[2 * p][q].y;
+                        Dt[2 * p + 1][2 * q] += yc[2 * p + 1][q].x;
+                        Dt[2 * p + 1][2 * q + 1] += yc[2 * p + 1][q].y;
                     }
                 }
             }
@@ -213,12 +225,7 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             for (int p = 0; p < 3; ++p) {
                 if (brow[p] < 0) continue;
                 const double A = v[p].x, B = v[p].y, Cn = inet[p].x, Dn = inet[p].y;
-                double pl = 0.0, ql = 0.0;
-                if (lrow[p] >= 0) {
-                    const double2 sp = spu_s[(long long)lrow[p] * ld];
-                    pl = sp.x;
-                    ql = sp.y;
-                }
+                const double pl = spl[p].x, ql = spl[p].y;
                 const double cap = __ldg(&st->cap[p]);
                 const double hAr = -pl * k.cA[p], hBr = -pl * k.cB[p], b0r = -pl * k.betaS;
                 const double hAi = -ql * k.cA[p] + cap * k.cA[p];
@@ -255,7 +262,7 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                     g[p] = 0.0;
                     if (brow[p] < 0) continue;
                     g[p] = __ldg(&st->gamma[p]);
-                    vm[p] = Xs[(long long)prow[p] * ld];
+                    vm[p] = vpar[p];
                     io[p] = Xs[(long long)orow[p] * ld];
                     ra[p] = make_double2(-g[p] * vm[p].x + v[p].x, -g[p] * vm[p].y + v[p].y);
                     const double f0 = 2.0 * ((vm[p].x * io[p].x + vm[p].y * io[p].y) - (v[p].x * iin[p].x + v[p].y * iin[p].y));
@@ -377,23 +384,32 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             const int erow[3] = {ev.x, ev.y, ev.z};
             const int kind = ev.w;
             const double2* Wk = Ws + (long long)pos * FRONT_D2 * ld;
-            double2 dvp[3], di[3], dv[3];
+            double2 dvp[3], di[3], dv[3], yf[6][3], r1f[3], xv[3], xi[3];
 #pragma unroll
-            for (int p = 0; p < 3; ++p)
-                dvp[p] = (brow[p] >= 0 && prow[p] >= 0) ? DVs[(long long)prow[p] * ld] : make_double2(0.0, 0.0);
-            // current leaving the parent: di = a - Y dv_p
+            for (int p = 0; p < 3; ++p) {               // issue every load of the step first
+                dvp[p] = di[p] = r1f[p] = xv[p] = xi[p] = make_double2(0.0, 0.0);
 #pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                di[p] = make_double2(0.0, 0.0);
+                for (int q = 0; q < 3; ++q) yf[2 * p][q] = yf[2 * p + 1][q] = make_double2(0.0, 0.0);
                 if (brow[p] < 0) continue;
+                if (prow[p] >= 0) dvp[p] = DVs[(long long)prow[p] * ld];
                 di[p] = Wk[(long long)(18 + p) * ld];
+                r1f[p] = Wk[(long long)(21 + p) * ld];
+                xv[p] = Xs[(long long)brow[p] * ld];
+                xi[p] = Xs[(long long)erow[p] * ld];
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     if (brow[q] < 0) continue;
-                    const double2 y0 = Wk[(long long)((2 * p) * 3 + q) * ld];
-                    const double2 y1 = Wk[(long long)((2 * p + 1) * 3 + q) * ld];
-                    di[p].x -= y0.x * dvp[q].x + y0.y * dvp[q].y;
-                    di[p].y -= y1.x * dvp[q].x + y1.y * dvp[q].y;
+                    yf[2 * p][q] = Wk[(long long)((2 * p) * 3 + q) * ld];
+                    yf[2 * p + 1][q] = Wk[(long long)((2 * p + 1) * 3 + q) * ld];
+                }
+            }
+            // current leaving the parent: di = a - Y dv_p
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    di[p].x -= yf[2 * p][q].x * dvp[q].x + yf[2 * p][q].y * dvp[q].y;
+                    di[p].y -= yf[2 * p + 1][q].x * dvp[q].x + yf[2 * p + 1][q].y * dvp[q].y;
                 }
             }
             if (kind == GP_EDGE_VR) {
@@ -421,11 +437,9 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                         dii.y -= d1.x * gdv[q].x + d1.y * gdv[q].y;
                     }
                     dv[p] = make_double2(gdv[p].x + ra.x, gdv[p].y + ra.y);
-                    const double2 xv = Xs[(long long)brow[p] * ld];
-                    const double2 xi = Xs[(long long)erow[p] * ld];
                     const double2 xo = Xs[(long long)orow[p] * ld];
-                    Xs[(long long)brow[p] * ld] = make_double2(xv.x - dv[p].x, xv.y - dv[p].y);
-                    Xs[(long long)erow[p] * ld] = make_double2(xi.x - dii.x, xi.y - dii.y);
+                    Xs[(long long)brow[p] * ld] = make_double2(xv[p].x - dv[p].x, xv[p].y - dv[p].y);
+                    Xs[(long long)erow[p] * ld] = make_double2(xi[p].x - dii.x, xi[p].y - dii.y);
                     Xs[(long long)orow[p] * ld] = make_double2(xo.x - di[p].x, xo.y - di[p].y);
                     DVs[(long long)brow[p] * ld] = dv[p];
                 }
@@ -434,8 +448,7 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
                 if (brow[p] < 0) continue;
-                const double2 r1 = Wk[(long long)(21 + p) * ld];
-                dv[p] = make_double2(dvp[p].x - r1.x, dvp[p].y - r1.y);
+                dv[p] = make_double2(dvp[p].x - r1f[p].x, dvp[p].y - r1f[p].y);
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     if (brow[q] < 0) continue;
@@ -443,10 +456,8 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                     dv[p].x -= z.x * di[q].x - z.y * di[q].y;
                     dv[p].y -= z.x * di[q].y + z.y * di[q].x;
                 }
-                const double2 xv = Xs[(long long)brow[p] * ld];
-                const double2 xi = Xs[(long long)erow[p] * ld];
-                Xs[(long long)brow[p] * ld] = make_double2(xv.x - dv[p].x, xv.y - dv[p].y);
-                Xs[(long long)erow[p] * ld] = make_double2(xi.x - di[p].x, xi.y - di[p].y);
+                Xs[(long long)brow[p] * ld] = make_double2(xv[p].x - dv[p].x, xv[p].y - dv[p].y);
+                Xs[(long long)erow[p] * ld] = make_double2(xi[p].x - di[p].x, xi[p].y - di[p].y);
                 DVs[(long long)brow[p] * ld] = dv[p];
             }
         }
