@@ -23,6 +23,7 @@ namespace gp {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+static int g_host_chunks = 0;  // gp_set_option("host_chunks", n): 0 = automatic
 static int g_fbs_kernel = 0;   // gp_set_option("fbs_kernel", v): 0 two-sweep, 1 fused depth-first, 2 phase-parallel
 
 struct __align__(16) FbsStep {
@@ -875,6 +876,10 @@ extern "C" int gp_set_option(const char* name, int value) {
         g_fbs_kernel = value;
         return GP_OK;
     }
+    if (name && strcmp(name, "host_chunks") == 0 && value >= 0 && value <= 64) {
+        g_host_chunks = value;
+        return GP_OK;
+    }
     return fail(GP_EINVAL, "gp_set_option: unknown option");
 }
 
@@ -1205,8 +1210,13 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
     // Rows are copied one 1-D transfer each (pitched 2-D copies run at ~7 GB/s on this
     // platform, 1-D pinned copies at ~55 GB/s), so a chunk should also keep a row piece
     // >= 256 KB (16 Ki scenarios) when memory allows: cap 3 GiB of rows per stream.
-    int64_t C = ((S + FbsImpl::NSTREAM - 1) / FbsImpl::NSTREAM + 127) / 128 * 128;
-    if (C < 16384) C = 16384;
+    // Measured on B200 (scripts/e2e_probe.py): every row piece is its own DMA (~2-4 us of
+    // overhead), so a batch that moves <= 128 MB is fastest as ONE chunk (three contiguous
+    // copies around the kernels); larger batches are cut into NSTREAM pipelined chunks with
+    // row pieces of at least 512 KB (32 Ki scenarios).
+    int want_chunks = g_host_chunks > 0 ? g_host_chunks : (rows * S * 16 <= ((int64_t)128 << 20) ? 1 : FbsImpl::NSTREAM);
+    int64_t C = ((S + want_chunks - 1) / want_chunks + 127) / 128 * 128;
+    if (C < 32768 && g_host_chunks == 0) C = 32768;
     const int64_t cap = (((int64_t)3 << 30) / (rows * 16)) / 128 * 128;
     if (C > cap) C = cap;
     if (C < 1024) C = 1024;

@@ -104,7 +104,8 @@ int64_t gp_launch_count(void);
 /*
  * Process-wide switches.  "fbs_kernel" selects the FBS solve kernel (identical results):
  * 0 = two-sweep, one thread per scenario (default); 1 = fused depth-first walk; 2 = two-sweep
- * with three phase lanes per scenario.
+ * with three phase lanes per scenario.  "host_chunks": number of pipeline chunks of
+ * gp_fbs_solve_batch_host (0 = automatic).
  */
 int gp_set_option(const char* name, int value);
 
