@@ -60,6 +60,32 @@ def peaks():
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
 
 
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` on `workload`, from the
+    committed `ncu --set full` captures (profiles/ncu_traffic.json); None when there is none."""
+    p = os.path.join(REPO, 'profiles', 'ncu_traffic.json')
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        rec = json.load(f).get(f'{workload}:{kernel}')
+    return float(rec['dram_bytes_per_launch']) if rec else None
+
+
+def fbs_flops_per_iteration(t):
+    """Algorithmic FP64 operations of one FBS iteration of one scenario:
+    forward 8 per (bus phase, edge phase) complex multiply-subtract; backward per bus phase 29
+    (|V|^2 3, sqrt 1, square 1, ZIP factor 4, spu scaling 2, capacitor 2, 1/|V|^2 4, conj(sV/V) 8,
+    accumulate 2, finite test 2), 2 per child-edge phase, 8 per (rewritten parent phase, edge
+    phase); root mismatch 18.  Divisions and square roots count as ONE operation each."""
+    line = np.asarray(t.kind) == 0          # GP_EDGE_LINE; regulator steps scale V by gamma
+    nb = (np.asarray(t.bus_vrow) >= 0).sum(axis=1)
+    ne = (np.asarray(t.edge_irow) >= 0).sum(axis=1)
+    npar = ((np.asarray(t.bus_vrow) >= 0) & (np.asarray(t.par_vrow) >= 0)).sum(axis=1)
+    nchild = int((np.asarray(t.child_irow) >= 0).sum())
+    return float((line * (8 * nb * ne + 29 * nb + 8 * npar * ne)).sum() + 2 * nchild + 18
+                 + ((~line) * 4 * nb).sum())
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
@@ -284,6 +310,9 @@ def run_ours(args, wl):
     _cabi.check(_cabi.gp_set_option(b'fbs_kernel', args.fbs_kernel))
     t = sol.tables
     h = sol._feeder.handle
+    if solver == 'fbs' and args.fbs_kernel in (0, 5) and _cabi.gp_fbs_onchip_warps(h) >= 4:
+        sol.specialise()        # what solve_batch does by itself for a batch this size
+    active = int(_cabi.gp_fbs_active_kernel(h)) if solver == 'fbs' else 0
     ld = S
     spu_h = torch.from_numpy(rows).pin_memory()
     spu_d = spu_h.to(dev)
@@ -415,11 +444,25 @@ def run_ours(args, wl):
 
     if rank == 0:
         pk, pk_kind = peaks()
-        if solver == 'fbs':
+        solve_ms = float(np.mean(ms_solve))
+        n_it = float(its.sum())
+        kernel_names = {1: 'fbs_dfs_kernel', 2: 'fbs_phase_kernel', 3: 'fbs_solve_kernel', 4: 'fbs_onchip_kernel',
+                        5: 'gp_fbs_jit_kernel'}
+        variant = {0: None, 1: 'fused-dfs', 2: 'phase-parallel', 3: 'two-sweep streaming (state in HBM)',
+                   4: 'on-chip two-sweep (state in shared memory), table-driven',
+                   5: 'on-chip two-sweep (state in shared memory), feeder-specialised (NVRTC)'}[active]
+        if solver == 'fbs' and active in (4, 5):
+            # on-chip kernel: per iteration only the spu rows are read (L2-resident after the first
+            # sweep); V and I leave the SM once.  The kernel is bound by the FP64 pipe, so the
+            # headline roofline is FP64 (algorithmic flops of the sweeps);
+            # the HBM fraction of the same launch is reported next to it.
+            per_it, once = 16 * t.n_srows, 16 * (t.n_vrows + t.n_irows) + 16
+            kname = kernel_names[active]
+        elif solver == 'fbs':
             # per sweep read I, write V | read V, read spu, write I, write V
             per_it = 16 * (2 * t.n_irows + 3 * t.n_vrows + t.n_srows)
             once = 16 * (t.n_srows + t.n_vrows + t.n_irows)
-            kname = 'fbs_solve_kernel'
+            kname = kernel_names[active]
         else:
             # per Newton iteration: X read+write, spu read, dV write+read, fronts (Y, a, r1) write+read
             nph = (t.bus_vrow >= 0).sum(axis=1)
@@ -427,16 +470,37 @@ def run_ours(args, wl):
             per_it = 2 * 16 * (t.n_vrows + t.n_irows) + 16 * t.n_srows + 2 * 16 * t.n_vrows + 2 * fronts
             once = 16 * (t.n_vrows + t.n_irows)
             kname = 'nr3_solve_kernel'
-        alg_bytes = float(its.sum()) * per_it + S * once            # solve kernel, per launch
-        solve_ms = float(np.mean(ms_solve))
+        alg_bytes = n_it * per_it + S * once            # solve kernel, per launch
         achieved = alg_bytes / (solve_ms * 1e-3) / 1e9
+        traffic = ncu_traffic(args.workload, kname)
+        roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': achieved,
+                    'peak': pk['hbm_gbs'], 'peak_kind': pk_kind, 'unit': 'GB/s',
+                    'frac': achieved / pk['hbm_gbs'], 'traffic': traffic,
+                    'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': solve_ms,
+                    'kernel_share_of_step': solve_ms / float(np.mean(ms_steps))}
+        if solver == 'fbs' and active in (4, 5):
+            import ctypes
+            tf = ctypes.c_double(0.0)
+            _cabi.check(_cabi.gp_measure_fp64_peak(local, ctypes.byref(tf)))
+            flops = n_it * fbs_flops_per_iteration(t)
+            ach_tf = flops / (solve_ms * 1e-3) / 1e12
+            roofline = {'bound': 'fp64', 'kernel': kname, 'achieved': ach_tf, 'peak': tf.value,
+                        'peak_kind': 'measured live (gp_measure_fp64_peak: DFMA chains, 2 flop each)',
+                        'unit': 'TFLOP/s', 'frac': ach_tf / tf.value, 'traffic': traffic,
+                        'algorithmic_flops_per_launch': flops, 'kernel_ms': solve_ms,
+                        'kernel_share_of_step': solve_ms / float(np.mean(ms_steps)),
+                        'hbm': {'achieved': achieved, 'peak': pk['hbm_gbs'], 'peak_kind': pk_kind, 'unit': 'GB/s',
+                                'frac': achieved / pk['hbm_gbs'], 'algorithmic_bytes_per_launch': alg_bytes,
+                                'streaming_formulation_equivalent_gbs':
+                                    (n_it * 16 * (2 * t.n_irows + 3 * t.n_vrows + t.n_srows)
+                                     + S * 16 * (t.n_srows + t.n_vrows + t.n_irows)) / (solve_ms * 1e-3) / 1e9}}
         line = {
             'metric': 'power-flow solves/sec', 'value': value, 'unit': 'solves/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
             'config': {'workload': desc, 'solver': solver, 'scenarios_per_gpu': S,
-                       'fbs_kernel': ['two-sweep', 'fused-dfs', 'phase-parallel'][args.fbs_kernel],
+                       'fbs_kernel': variant,
                        'rows': {'P_b': t.n_vrows, 'P_l': t.n_irows, 'P_L': t.n_srows},
                        'mean_iterations': float(its.mean()), 'max_iterations': int(its.max()),
                        'l2': 'flushed between steps (256 MiB write, untimed)',
@@ -446,11 +510,7 @@ def run_ours(args, wl):
                     'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
                     'api': e2e_api},
             'gpu_launches': int(launches),
-            'roofline': {'bound': 'hbm', 'kernel': kname, 'achieved': achieved,
-                         'peak': pk['hbm_gbs'], 'peak_kind': pk_kind, 'unit': 'GB/s',
-                         'frac': achieved / pk['hbm_gbs'], 'traffic': None,
-                         'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': solve_ms,
-                         'kernel_share_of_step': solve_ms / float(np.mean(ms_steps))},
+            'roofline': roofline,
             'clocks': clocks, 'wall_s_timed_region': t_wall,
         }
         if world == 1 and not args.no_cpu:
@@ -479,8 +539,10 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    ap.add_argument('--fbs-kernel', type=int, default=0, choices=[0, 1, 2],
-                    help='0 = two-sweep FBS kernel (default), 1 = fused depth-first, 2 = phase-parallel lanes')
+    ap.add_argument('--fbs-kernel', type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
+                    help='0 = automatic (on-chip when the feeder fits in shared memory, else two-sweep streaming), '
+                         '1 = fused depth-first, 2 = phase-parallel lanes, 3 = two-sweep streaming, 4 = on-chip table-driven, '
+                         '5 = on-chip feeder-specialised')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':

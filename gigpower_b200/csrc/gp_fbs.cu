@@ -12,7 +12,9 @@
 // scenario index innermost, so every access of a warp is one 512-byte coalesced
 // 128-bit transaction.  The per-feeder step table is scenario-invariant; all
 // lanes read the same words (broadcast through L1/the read-only path).
-#include "gp_common.cuh"
+#include "gp_fbs.cuh"
+
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <functional>
@@ -24,55 +26,10 @@ namespace gp {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 static int g_host_chunks = 0;  // gp_set_option("host_chunks", n): 0 = automatic
-static int g_fbs_kernel = 0;   // gp_set_option("fbs_kernel", v): 0 two-sweep, 1 fused depth-first, 2 phase-parallel
-
-struct __align__(16) FbsStep {
-    int bus_vrow[3];
-    int kind;
-    int par_vrow[3];
-    int child_begin;
-    int edge_irow[3];
-    int child_count;
-    int load_srow[3];
-    int pad0;
-    double cap[3];
-    double pad1;
-    double gamma[3];
-    double pad2;
-    double inv_gamma[3];
-    double pad3;
-    double2 z[9];
-};
-static_assert(sizeof(FbsStep) == 64 + 32 + 32 + 32 + 144, "FbsStep layout");
-
-struct FbsConst {
-    int root_vrow[3];
-    int root_load_srow[3];
-    double root_cap[3];
-    double2 vref[3];
-    double aPQ, aI, aZ;
-};
-
-struct FbsImpl {
-    int n_steps = 0, n_vrows = 0, n_irows = 0, n_srows = 0, n_child = 0, n_lines = 0;
-    FbsStep* d_steps = nullptr;
-    int4* d_child = nullptr;  // [n_child] {I rows of the child edge, 0}
-    int* d_lines = nullptr;   // [n_lines][9] irow, tx vrow, rx vrow
-    int* d_vrow_srow = nullptr;   // [n_vrows] spu row of each V row or -1
-    double* d_vrow_cap = nullptr; // [n_vrows]
-    FbsConst k;
-    // fused depth-first schedule (fbs_dfs_kernel): 2 events per step, or none if not applicable
-    int2* d_events = nullptr;
-    int4* d_evrows = nullptr;   // per event: the 3 rows to prefetch, .w = 1 for I rows (descend), 0 for spu rows
-    int n_events = 0, depth = 0;
-    // host staging for gp_fbs_solve_batch_host
-    static constexpr int NSTREAM = 4;
-    cudaStream_t streams[NSTREAM] = {nullptr, nullptr, nullptr, nullptr};
-    void* d_stage[NSTREAM] = {nullptr, nullptr, nullptr, nullptr};
-    size_t stage_bytes = 0;
-};
-
-__device__ __forceinline__ double2 ldc(const double2* p) { return *p; }
+// gp_set_option("fbs_kernel", v): 0 automatic (on-chip when the feeder fits, else two-sweep), 1 fused
+// depth-first, 2 phase-parallel, 3 two-sweep streaming, 4 on-chip (error if the feeder does not fit),
+// 5 feeder-specialised on-chip kernel (error unless gp_fbs_specialise succeeded)
+static int g_fbs_kernel = 0;
 
 // |v| as numpy computes it for the ZIP model (abs then square, solution.py:202)
 __device__ __forceinline__ double cabs2(double2 v, double& a) {
@@ -80,28 +37,53 @@ __device__ __forceinline__ double cabs2(double2 v, double& a) {
     return a * a;
 }
 
-// Row r of scenario s lives at base + s*16 + r*ldb: one 32x32->64 multiply-add per access.
-// State rows are read through L2 only (ld.global.cg): they are touched once per sweep, so
-// keeping them out of L1 leaves L1 to the step table that every warp re-reads.
-#define GP_LD(base, r) __ldcg(reinterpret_cast<const double2*>((base) + (size_t)(unsigned)(r) * (size_t)ldb))
-#define GP_ST(base, r, v) (*reinterpret_cast<double2*>((base) + (size_t)(unsigned)(r) * (size_t)ldb) = (v))
+// ---- where the state rows live --------------------------------------------------------------
+// The sweep bodies below are written once against a row accessor:
+//   GMem: rows in HBM, [row][ld] complex128 with the scenario innermost.  Row r of scenario s is
+//         at base + s*16 + r*ldb (one 32x32->64 multiply-add per access).  State rows are read
+//         through L2 only (ld.global.cg): they are touched once per sweep, so keeping them out of
+//         L1 leaves L1 to the step table that every warp re-reads.
+//   SMem: V and I rows in shared memory, [row][32 lanes] per warp (512-byte row pitch: lane l reads
+//         bytes 16 l .. 16 l + 15 of a row, conflict-free 128-bit accesses); spu rows stay in HBM.
+struct GMem {
+    char* V;
+    char* I;
+    const char* S;
+    unsigned ldb;
+    __device__ __forceinline__ double2 ldV(int r) const { return __ldcg(reinterpret_cast<const double2*>(V + (size_t)(unsigned)r * (size_t)ldb)); }
+    __device__ __forceinline__ double2 ldI(int r) const { return __ldcg(reinterpret_cast<const double2*>(I + (size_t)(unsigned)r * (size_t)ldb)); }
+    __device__ __forceinline__ double2 ldS(int r) const { return __ldcg(reinterpret_cast<const double2*>(S + (size_t)(unsigned)r * (size_t)ldb)); }
+    __device__ __forceinline__ void stV(int r, double2 v) const { *reinterpret_cast<double2*>(V + (size_t)(unsigned)r * (size_t)ldb) = v; }
+    __device__ __forceinline__ void stI(int r, double2 v) const { *reinterpret_cast<double2*>(I + (size_t)(unsigned)r * (size_t)ldb) = v; }
+};
+
+struct SMem {
+    double2* V;         // this lane's column of the warp's V rows (shared memory)
+    double2* I;
+    const char* S;      // this scenario's column of the spu rows (global memory)
+    unsigned ldb;
+    __device__ __forceinline__ double2 ldV(int r) const { return V[r * 32]; }
+    __device__ __forceinline__ double2 ldI(int r) const { return I[r * 32]; }
+    __device__ __forceinline__ double2 ldS(int r) const { return __ldg(reinterpret_cast<const double2*>(S + (size_t)(unsigned)r * (size_t)ldb)); }
+    __device__ __forceinline__ void stV(int r, double2 v) const { V[r * 32] = v; }
+    __device__ __forceinline__ void stI(int r, double2 v) const { I[r * 32] = v; }
+};
 
 // ---- mask-specialised step bodies -----------------------------------------------------------
 // Most buses carry exactly the phases of their incoming line and their parent carries them too.
 // For those steps (FbsStep fast mask M != 0) the phase pattern is a compile-time constant: no
 // row tests, no predicated arithmetic, straight-line FP64.  The branch on M is uniform (every
-// thread walks the same feeder).  Everything else takes the general body below.
-template <int M>
-__device__ __forceinline__ void fwd_fast(const FbsStep* __restrict__ st, const int4 bv, const int4 pv,
-                                         char* V_b, const char* I_b, unsigned ldb) {
+// thread walks the same feeder).  Everything else takes the general body.
+template <int M, class Mem>
+__device__ __forceinline__ void fwd_fast(const FbsStep* __restrict__ st, const int4 bv, const int4 pv, const Mem& m) {
     const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
     const int brow[3] = {bv.x, bv.y, bv.z}, prow[3] = {pv.x, pv.y, pv.z}, erow[3] = {ev.x, ev.y, ev.z};
     double2 Vp[3], Il[3];
 #pragma unroll
     for (int p = 0; p < 3; ++p)
         if ((M >> p) & 1) {
-            Vp[p] = GP_LD(V_b, prow[p]);
-            Il[p] = GP_LD(I_b, erow[p]);
+            Vp[p] = m.ldV(prow[p]);
+            Il[p] = m.ldI(erow[p]);
         }
 #pragma unroll
     for (int p = 0; p < 3; ++p)
@@ -114,24 +96,22 @@ __device__ __forceinline__ void fwd_fast(const FbsStep* __restrict__ st, const i
                     v.x -= z.x * Il[q].x - z.y * Il[q].y;
                     v.y -= z.x * Il[q].y + z.y * Il[q].x;
                 }
-            GP_ST(V_b, brow[p], v);
+            m.stV(brow[p], v);
         }
 }
 
-template <int M>
+template <int M, class Mem>
 __device__ __forceinline__ void bwd_fast(const FbsStep* __restrict__ st, const int4 bv, const int4 pv,
-                                         const int4* __restrict__ child_irow, const FbsConst& k,
-                                         char* V_b, char* I_b, const char* spu_b, unsigned ldb) {
+                                         const int4* __restrict__ child_irow, const FbsConst& k, const Mem& m,
+                                         const double2 (&sp)[3]) {
     const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
-    const int4 lv = __ldg(reinterpret_cast<const int4*>(st->load_srow));
     const int brow[3] = {bv.x, bv.y, bv.z}, prow[3] = {pv.x, pv.y, pv.z};
-    const int erow[3] = {ev.x, ev.y, ev.z}, lrow[3] = {lv.x, lv.y, lv.z};
-    double2 Vb[3], sp[3], In[3];
+    const int erow[3] = {ev.x, ev.y, ev.z};
+    double2 Vb[3], In[3];
 #pragma unroll
     for (int p = 0; p < 3; ++p)
         if ((M >> p) & 1) {
-            Vb[p] = GP_LD(V_b, brow[p]);
-            sp[p] = lrow[p] >= 0 ? GP_LD(spu_b, lrow[p]) : make_double2(0.0, 0.0);
+            Vb[p] = m.ldV(brow[p]);
             In[p] = make_double2(0.0, 0.0);
         }
     for (int c = 0; c < ev.w; ++c) {                    // children's currents (:274-284)
@@ -140,7 +120,7 @@ __device__ __forceinline__ void bwd_fast(const FbsStep* __restrict__ st, const i
 #pragma unroll
         for (int p = 0; p < 3; ++p)
             if (((M >> p) & 1) && crow[p] >= 0) {
-                const double2 ic = GP_LD(I_b, crow[p]);
+                const double2 ic = m.ldI(crow[p]);
                 In[p].x += ic.x;
                 In[p].y += ic.y;
             }
@@ -169,7 +149,7 @@ __device__ __forceinline__ void bwd_fast(const FbsStep* __restrict__ st, const i
     }
 #pragma unroll
     for (int p = 0; p < 3; ++p)
-        if ((M >> p) & 1) GP_ST(I_b, erow[p], In[p]);
+        if ((M >> p) & 1) m.stI(erow[p], In[p]);
 #pragma unroll
     for (int p = 0; p < 3; ++p)
         if ((M >> p) & 1) {                             // update_voltage_backward (:207-232)
@@ -181,21 +161,176 @@ __device__ __forceinline__ void bwd_fast(const FbsStep* __restrict__ st, const i
                     v.x += z.x * In[q].x - z.y * In[q].y;
                     v.y += z.x * In[q].y + z.y * In[q].x;
                 }
-            GP_ST(V_b, prow[p], v);
+            m.stV(prow[p], v);
         }
 }
 
 #define GP_FAST_SWITCH(fn, ...)                 \
     switch (fast) {                             \
-        case 7: fn<7>(__VA_ARGS__); continue;   \
-        case 1: fn<1>(__VA_ARGS__); continue;   \
-        case 2: fn<2>(__VA_ARGS__); continue;   \
-        case 4: fn<4>(__VA_ARGS__); continue;   \
-        case 3: fn<3>(__VA_ARGS__); continue;   \
-        case 5: fn<5>(__VA_ARGS__); continue;   \
-        case 6: fn<6>(__VA_ARGS__); continue;   \
+        case 7: fn<7>(__VA_ARGS__); return;     \
+        case 1: fn<1>(__VA_ARGS__); return;     \
+        case 2: fn<2>(__VA_ARGS__); return;     \
+        case 4: fn<4>(__VA_ARGS__); return;     \
+        case 3: fn<3>(__VA_ARGS__); return;     \
+        case 5: fn<5>(__VA_ARGS__); return;     \
+        case 6: fn<6>(__VA_ARGS__); return;     \
         default: break;                         \
     }
+
+// forward step of one bus: update_voltage_forward :162-184 / vr_forward :138-160
+template <class Mem>
+__device__ __forceinline__ void fbs_fwd_step(const FbsStep* __restrict__ st, const Mem& m) {
+    const double2 zero = make_double2(0.0, 0.0);
+    const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
+    const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
+    const int kind = bv.w & 0xff, fast = bv.w >> 8;
+    GP_FAST_SWITCH(fwd_fast, st, bv, pv, m)
+    const int brow[3] = {bv.x, bv.y, bv.z};
+    const int prow[3] = {pv.x, pv.y, pv.z};
+    double2 Vp[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) Vp[p] = prow[p] >= 0 ? m.ldV(prow[p]) : zero;
+    if (kind == GP_EDGE_VR) {   // vr_forward :138-160
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const double g = __ldg(&st->gamma[p]);
+            if (g != 0.0 && brow[p] >= 0) m.stV(brow[p], make_double2(g * Vp[p].x, g * Vp[p].y));
+        }
+        return;
+    }
+    const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
+    const int erow[3] = {ev.x, ev.y, ev.z};
+    double2 Il[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) Il[p] = erow[p] >= 0 ? m.ldI(erow[p]) : zero;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        if (brow[p] < 0) continue;
+        double2 v = Vp[p];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            if (erow[q] < 0) continue;
+            const double2 z = __ldg(&st->z[3 * p + q]);
+            v.x -= z.x * Il[q].x - z.y * Il[q].y;
+            v.y -= z.x * Il[q].y + z.y * Il[q].x;
+        }
+        m.stV(brow[p], v);
+    }
+}
+
+// spu rows of the bus of a step (zeros where the bus-phase carries no load)
+template <class Mem>
+__device__ __forceinline__ void fbs_load_spu(const FbsStep* __restrict__ st, const Mem& m, double2 (&sp)[3]) {
+    const int4 lv = __ldg(reinterpret_cast<const int4*>(st->load_srow));
+    const int lrow[3] = {lv.x, lv.y, lv.z};
+#pragma unroll
+    for (int p = 0; p < 3; ++p) sp[p] = lrow[p] >= 0 ? m.ldS(lrow[p]) : make_double2(0.0, 0.0);
+}
+
+// backward step of one bus (:104-121): calc_sV, update_current, update_voltage_backward / vr_backward
+template <class Mem>
+__device__ __forceinline__ void fbs_bwd_step(const FbsStep* __restrict__ st, const int4* __restrict__ child_irow,
+                                             const FbsConst& k, const Mem& m, const double2 (&sp)[3]) {
+    const double2 zero = make_double2(0.0, 0.0);
+    const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
+    const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
+    const int kind = bv.w & 0xff, fast = bv.w >> 8;
+    GP_FAST_SWITCH(bwd_fast, st, bv, pv, child_irow, k, m, sp)
+    const int brow[3] = {bv.x, bv.y, bv.z};
+    const int prow[3] = {pv.x, pv.y, pv.z};
+    const int child_begin = pv.w;
+    double2 Vb[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) Vb[p] = brow[p] >= 0 ? m.ldV(brow[p]) : zero;
+    if (kind == GP_EDGE_VR) {   // vr_current leaves Itx = 0; vr_backward :186-205
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const double g = __ldg(&st->gamma[p]);
+            if (g != 0.0 && prow[p] >= 0) {
+                const double ig = __ldg(&st->inv_gamma[p]);
+                m.stV(prow[p], make_double2(ig * Vb[p].x, ig * Vb[p].y));
+            }
+        }
+        return;
+    }
+    const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
+    const int erow[3] = {ev.x, ev.y, ev.z};
+    const int child_count = ev.w;
+    // calc_sV(bus) (solution.py:177-220) + update_current (:256-288)
+    double2 In[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        In[p] = zero;
+        if (brow[p] < 0) continue;
+        const double2 v = Vb[p];
+        double a;
+        const double a2 = cabs2(v, a);
+        const double f = k.aPQ + k.aI * a + k.aZ * a2;
+        double2 sv = make_double2(sp[p].x * f, sp[p].y * f);   // sp = 0 where there is no load
+        sv.y -= __ldg(&st->cap[p]) * a2;
+        if (v.x != 0.0 || v.y != 0.0) {
+            // conj(sV / V) computed as (sV * conj(V)) / |V|^2, conjugated
+            const double inv = 1.0 / fma(v.x, v.x, v.y * v.y);
+            const double qr = (sv.x * v.x + sv.y * v.y) * inv;
+            const double qi = (sv.y * v.x - sv.x * v.y) * inv;
+            In[p] = make_double2(qr, -qi);
+        }
+    }
+    for (int c = 0; c < child_count; ++c) {
+        const int4 cr4 = __ldg(child_irow + child_begin + c);
+        const int cr[3] = {cr4.x, cr4.y, cr4.z};
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+            if (cr[p] >= 0) {
+                const double2 ic = m.ldI(cr[p]);
+                In[p].x += ic.x;
+                In[p].y += ic.y;
+            }
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        if (erow[p] >= 0) {
+            In[p] = make_double2(nan_to_num(In[p].x), nan_to_num(In[p].y));
+            m.stI(erow[p], In[p]);
+        } else {
+            In[p] = zero;
+        }
+    }
+    // update_voltage_backward (:207-232): phases of the child bus, masked by the parent
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        if (brow[p] < 0 || prow[p] < 0) continue;
+        double2 v = Vb[p];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            if (erow[q] < 0) continue;
+            const double2 z = __ldg(&st->z[3 * p + q]);
+            v.x += z.x * In[q].x - z.y * In[q].y;
+            v.y += z.x * In[q].y + z.y * In[q].x;
+        }
+        m.stV(prow[p], v);
+    }
+}
+
+// root mismatch (:123-128): max_ph |V[root] - Vref|, NaN-propagating like numpy's max
+template <class Mem>
+__device__ __forceinline__ double fbs_root_diff(const FbsConst& k, const Mem& m) {
+    double diff = 0.0;
+    bool nan = false;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const double2 v = m.ldV(k.root_vrow[p]);
+        const double dx = v.x - k.vref[p].x, dy = v.y - k.vref[p].y;
+        const double d = sqrt(fma(dx, dx, dy * dy));
+        nan |= (d != d);
+        diff = fmax(diff, d);
+    }
+    return nan ? __longlong_as_double(0x7ff8000000000000LL) : diff;
+}
+
+__device__ __forceinline__ int fbs_status(bool converged, double diff) {
+    return converged ? GP_ST_CONVERGED : ((diff != diff || isinf(diff)) ? GP_ST_NONFINITE : GP_ST_MAXITER);
+}
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)   // <= 64 registers: 1024 resident threads per SM
@@ -207,173 +342,127 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
                  int maxiter) {
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (s >= S) return;
-    const char* spu_b = spu + s * 16;
-    char* V_b = V + s * 16;
-    char* I_b = I + s * 16;
+    const GMem m{V + s * 16, I + s * 16, spu + s * 16, ldb};
     const double2 zero = make_double2(0.0, 0.0);
 
     // flat start (solution.py:108-125): V = I = 0.  I is read by the first forward
     // sweep and V rows that no edge feeds (non-regulated phases below a regulator)
     // keep their initial value, so both are zeroed here, coalesced, once.
-    for (int r = 0; r < n_vrows; ++r) GP_ST(V_b, r, zero);
-    for (int r = 0; r < n_irows; ++r) GP_ST(I_b, r, zero);
+    for (int r = 0; r < n_vrows; ++r) m.stV(r, zero);
+    for (int r = 0; r < n_irows; ++r) m.stI(r, zero);
     int it = 0;
     double diff = -1.0;
     bool converged = false;   // Vtest = 0 -> max|0 - Vref| = 1 > tol (solution_fbs.py:85)
 
     while (!converged && it < maxiter) {
-        // V[root] = Vref  (:89)
 #pragma unroll
-        for (int p = 0; p < 3; ++p) GP_ST(V_b, k.root_vrow[p], k.vref[p]);
-
-        // ---- forward sweep (:92-98, update_voltage_forward :162-184) -------
-        for (int pos = 0; pos < n_steps; ++pos) {
-            const FbsStep* st = steps + pos;
-            const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
-            const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
-            const int kind = bv.w & 0xff, fast = bv.w >> 8;
-            GP_FAST_SWITCH(fwd_fast, st, bv, pv, V_b, I_b, ldb)
-            const int brow[3] = {bv.x, bv.y, bv.z};
-            const int prow[3] = {pv.x, pv.y, pv.z};
-            double2 Vp[3];
-#pragma unroll
-            for (int p = 0; p < 3; ++p) Vp[p] = prow[p] >= 0 ? GP_LD(V_b, prow[p]) : zero;
-            if (kind == GP_EDGE_VR) {   // vr_forward :138-160
-#pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    const double g = __ldg(&st->gamma[p]);
-                    if (g != 0.0 && brow[p] >= 0) GP_ST(V_b, brow[p], make_double2(g * Vp[p].x, g * Vp[p].y));
-                }
-                continue;
-            }
-            const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
-            const int erow[3] = {ev.x, ev.y, ev.z};
-            double2 Il[3];
-#pragma unroll
-            for (int p = 0; p < 3; ++p) Il[p] = erow[p] >= 0 ? GP_LD(I_b, erow[p]) : zero;
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                if (brow[p] < 0) continue;
-                double2 v = Vp[p];
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    if (erow[q] < 0) continue;
-                    const double2 z = __ldg(&st->z[3 * p + q]);
-                    v.x -= z.x * Il[q].x - z.y * Il[q].y;
-                    v.y -= z.x * Il[q].y + z.y * Il[q].x;
-                }
-                GP_ST(V_b, brow[p], v);
-            }
+        for (int p = 0; p < 3; ++p) m.stV(k.root_vrow[p], k.vref[p]);      // V[root] = Vref  (:89)
+        for (int pos = 0; pos < n_steps; ++pos) fbs_fwd_step(steps + pos, m);          // :92-98
+        for (int pos = n_steps - 1; pos >= 0; --pos) {                                 // :104-121
+            double2 sp[3];
+            fbs_load_spu(steps + pos, m, sp);
+            fbs_bwd_step(steps + pos, child_irow, k, m, sp);
         }
-
-        // ---- backward sweep (:104-121) --------------------------------------
-        for (int pos = n_steps - 1; pos >= 0; --pos) {
-            const FbsStep* st = steps + pos;
-            const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
-            const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
-            const int kind = bv.w & 0xff, fast = bv.w >> 8;
-            GP_FAST_SWITCH(bwd_fast, st, bv, pv, child_irow, k, V_b, I_b, spu_b, ldb)
-            const int brow[3] = {bv.x, bv.y, bv.z};
-            const int prow[3] = {pv.x, pv.y, pv.z};
-            const int child_begin = pv.w;
-            double2 Vb[3];
-#pragma unroll
-            for (int p = 0; p < 3; ++p) Vb[p] = brow[p] >= 0 ? GP_LD(V_b, brow[p]) : zero;
-            if (kind == GP_EDGE_VR) {   // vr_current leaves Itx = 0; vr_backward :186-205
-#pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    const double g = __ldg(&st->gamma[p]);
-                    if (g != 0.0 && prow[p] >= 0) {
-                        const double ig = __ldg(&st->inv_gamma[p]);
-                        GP_ST(V_b, prow[p], make_double2(ig * Vb[p].x, ig * Vb[p].y));
-                    }
-                }
-                continue;
-            }
-            const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
-            const int4 lv = __ldg(reinterpret_cast<const int4*>(st->load_srow));
-            const int erow[3] = {ev.x, ev.y, ev.z};
-            const int lrow[3] = {lv.x, lv.y, lv.z};
-            const int child_count = ev.w;
-            // calc_sV(bus) (solution.py:177-220) + update_current (:256-288)
-            double2 In[3];
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                In[p] = zero;
-                if (brow[p] < 0) continue;
-                const double2 v = Vb[p];
-                double a;
-                const double a2 = cabs2(v, a);
-                double2 sv = zero;
-                if (lrow[p] >= 0) {
-                    const double2 sp = GP_LD(spu_b, lrow[p]);
-                    const double f = k.aPQ + k.aI * a + k.aZ * a2;
-                    sv.x = sp.x * f;
-                    sv.y = sp.y * f;
-                }
-                sv.y -= __ldg(&st->cap[p]) * a2;
-                if (v.x != 0.0 || v.y != 0.0) {
-                    // conj(sV / V) computed as (sV * conj(V)) / |V|^2, conjugated
-                    const double inv = 1.0 / fma(v.x, v.x, v.y * v.y);
-                    const double qr = (sv.x * v.x + sv.y * v.y) * inv;
-                    const double qi = (sv.y * v.x - sv.x * v.y) * inv;
-                    In[p] = make_double2(qr, -qi);
-                }
-            }
-            for (int c = 0; c < child_count; ++c) {
-                const int4 cr4 = __ldg(child_irow + child_begin + c);
-                const int cr[3] = {cr4.x, cr4.y, cr4.z};
-#pragma unroll
-                for (int p = 0; p < 3; ++p)
-                    if (cr[p] >= 0) {
-                        const double2 ic = GP_LD(I_b, cr[p]);
-                        In[p].x += ic.x;
-                        In[p].y += ic.y;
-                    }
-            }
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                if (erow[p] >= 0) {
-                    In[p] = make_double2(nan_to_num(In[p].x), nan_to_num(In[p].y));
-                    GP_ST(I_b, erow[p], In[p]);
-                } else {
-                    In[p] = zero;
-                }
-            }
-            // update_voltage_backward (:207-232): phases of the child bus, masked by the parent
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                if (brow[p] < 0 || prow[p] < 0) continue;
-                double2 v = Vb[p];
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    if (erow[q] < 0) continue;
-                    const double2 z = __ldg(&st->z[3 * p + q]);
-                    v.x += z.x * In[q].x - z.y * In[q].y;
-                    v.y += z.x * In[q].y + z.y * In[q].x;
-                }
-                GP_ST(V_b, prow[p], v);
-            }
-        }
-
-        // ---- convergence (:123-128) -----------------------------------------
         ++it;
-        diff = 0.0;
-        bool nan = false;
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-            const double2 v = GP_LD(V_b, k.root_vrow[p]);
-            const double dx = v.x - k.vref[p].x, dy = v.y - k.vref[p].y;
-            const double d = sqrt(fma(dx, dx, dy * dy));
-            nan |= (d != d);
-            diff = fmax(diff, d);   // numpy max propagates NaN; handled below
-        }
-        if (nan) diff = __longlong_as_double(0x7ff8000000000000LL);
+        diff = fbs_root_diff(k, m);
         converged = diff <= tol;
     }
     iters_out[s] = it;
     diff_out[s] = diff;
-    status_out[s] = converged ? GP_ST_CONVERGED : ((diff != diff || isinf(diff)) ? GP_ST_NONFINITE : GP_ST_MAXITER);
+    status_out[s] = fbs_status(converged, diff);
+}
+
+// ---------------------------------------------------------------------------------------
+// On-chip two-sweep kernel: the whole solve of a scenario runs out of shared memory.
+//
+// For a small feeder the V and I rows of 32 scenarios (one warp) fit in a slice of the SM's
+// 227 KB of shared memory, [row][lane] with a 512-byte pitch.  A warp owns its slice outright -
+// a lane only ever touches its own column - so there is no block-level synchronisation at all.
+// Per solve the HBM traffic drops from it * 16 (2 P_l + 3 P_b + P_L) to the spu reads
+// (it * 16 P_L, L2-resident after the first sweep) plus ONE write of the final V and I rows:
+// the sweep-to-sweep dependency chain runs at shared-memory latency instead of an L2 round trip
+// per tree step, and the kernel becomes FP64-pipe / issue bound instead of HBM-latency bound.
+//
+// Scheduling: one persistent block per SM, NW warps.  Every warp pulls 32-scenario tiles from a
+// global counter until the batch is exhausted (iteration counts differ between tiles, so static
+// assignment would leave SMs idle); the last warp to finish re-arms the counter for the next
+// launch.  The spu rows a backward step needs are fetched two steps ahead into registers.
+// ---------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+fbs_onchip_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ child_irow, FbsConst k, int n_steps,
+                  int n_vrows, int n_irows, long long S, unsigned ldb, const char* __restrict__ spu,
+                  char* __restrict__ V, char* __restrict__ I, int* __restrict__ iters_out,
+                  int* __restrict__ status_out, double* __restrict__ diff_out, double tol, int maxiter,
+                  unsigned* __restrict__ sched) {
+    extern __shared__ __align__(16) double2 gp_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double2* Vs = gp_smem + (size_t)warp * (size_t)(n_vrows + n_irows) * 32 + lane;
+    double2* Is = Vs + (size_t)n_vrows * 32;
+    const long long n_tiles = (S + 31) >> 5;
+    const double2 zero = make_double2(0.0, 0.0);
+    for (;;) {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd(&sched[0], 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if ((long long)tile >= n_tiles) break;
+        const long long s_raw = (long long)tile * 32 + lane;
+        const bool live = s_raw < S;
+        const long long s = live ? s_raw : S - 1;          // idle lanes of the last tile shadow a real scenario
+        const SMem m{Vs, Is, spu + s * 16, ldb};
+        for (int r = 0; r < n_vrows; ++r) m.stV(r, zero);  // flat start (solution.py:108-125)
+        for (int r = 0; r < n_irows; ++r) m.stI(r, zero);
+        int it = 0;
+        double diff = -1.0;
+        bool converged = false;
+        while (!converged && it < maxiter) {
+#pragma unroll
+            for (int p = 0; p < 3; ++p) m.stV(k.root_vrow[p], k.vref[p]);
+            // spu rows of the first two backward steps: in flight during the forward sweep
+            double2 spA[3], spB[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) spA[p] = spB[p] = zero;
+            if (n_steps > 0) fbs_load_spu(steps + (n_steps - 1), m, spA);
+            if (n_steps > 1) fbs_load_spu(steps + (n_steps - 2), m, spB);
+            for (int pos = 0; pos < n_steps; ++pos) fbs_fwd_step(steps + pos, m);
+            for (int pos = n_steps - 1; pos >= 0; --pos) {
+                double2 spC[3];
+#pragma unroll
+                for (int p = 0; p < 3; ++p) spC[p] = zero;
+                if (pos >= 2) fbs_load_spu(steps + (pos - 2), m, spC);
+                fbs_bwd_step(steps + pos, child_irow, k, m, spA);
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    spA[p] = spB[p];
+                    spB[p] = spC[p];
+                }
+            }
+            ++it;
+            diff = fbs_root_diff(k, m);
+            converged = diff <= tol;
+        }
+        __syncwarp();
+        if (live) {         // final V and I rows: one coalesced 512-byte store per row and warp
+            char* Vg = V + s * 16;
+            char* Ig = I + s * 16;
+            for (int r = 0; r < n_vrows; ++r)
+                *reinterpret_cast<double2*>(Vg + (size_t)(unsigned)r * (size_t)ldb) = m.ldV(r);
+            for (int r = 0; r < n_irows; ++r)
+                *reinterpret_cast<double2*>(Ig + (size_t)(unsigned)r * (size_t)ldb) = m.ldI(r);
+            iters_out[s] = it;
+            diff_out[s] = diff;
+            status_out[s] = fbs_status(converged, diff);
+        }
+    }
+    if (lane == 0) {        // the last warp out re-arms the tile counter for the next launch
+        __threadfence();
+        const unsigned done = atomicAdd(&sched[1], 1u);
+        if (done == gridDim.x * NW - 1) {
+            sched[0] = 0u;
+            sched[1] = 0u;
+            __threadfence();
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -872,7 +961,7 @@ extern "C" int gp_last_error(char* buf, size_t len) {
 extern "C" int64_t gp_launch_count(void) { return g_launches.load(); }
 
 extern "C" int gp_set_option(const char* name, int value) {
-    if (name && strcmp(name, "fbs_kernel") == 0 && value >= 0 && value <= 2) {
+    if (name && strcmp(name, "fbs_kernel") == 0 && value >= 0 && value <= 5) {
         g_fbs_kernel = value;
         return GP_OK;
     }
@@ -883,22 +972,76 @@ extern "C" int gp_set_option(const char* name, int value) {
     return fail(GP_EINVAL, "gp_set_option: unknown option");
 }
 
-extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
-    if (!d || !out) return fail(GP_EINVAL, "gp_fbs_create: null argument");
-    if (d->n_steps < 0 || d->n_vrows <= 0 || d->n_irows < 0 || d->n_srows < 0)
-        return fail(GP_EINVAL, "gp_fbs_create: bad sizes");
+extern "C" int gp_fbs_onchip_warps(GpFeeder* f) {
+    if (!f || f->kind != 1) return fail(GP_EINVAL, "gp_fbs_onchip_warps: not an FBS feeder handle");
+    return ((FbsImpl*)f->impl)->onchip_warps;
+}
+
+extern "C" int gp_fbs_active_kernel(GpFeeder* f) {
+    if (!f || f->kind != 1) return fail(GP_EINVAL, "gp_fbs_active_kernel: not an FBS feeder handle");
+    const FbsImpl* im = (const FbsImpl*)f->impl;
+    if (g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) return 5;
+    if (g_fbs_kernel == 4 || (g_fbs_kernel == 0 && im->onchip_warps >= 4)) return 4;
+    if (g_fbs_kernel == 2) return 2;
+    if (g_fbs_kernel == 1 && im->n_events > 0) return 1;
+    return 3;
+}
+
+namespace gp {
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double b, double c) {
+    double a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = (double)(threadIdx.x + j);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fma(a[j], b, c);
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += a[j];
+    if (sum == 12345.678) out[0] = sum;    // never true: keeps the chains alive
+}
+}  // namespace gp
+
+extern "C" int gp_measure_fp64_peak(int device, double* tflops) {
+    if (!tflops) return fail(GP_EINVAL, "gp_measure_fp64_peak: null argument");
     GP_CUDA(cudaSetDevice(device));
-    FbsImpl* im = new (std::nothrow) FbsImpl();
-    if (!im) return fail(GP_ENOMEM, "gp_fbs_create: out of host memory");
-    im->n_steps = d->n_steps;
-    im->n_vrows = d->n_vrows;
-    im->n_irows = d->n_irows;
-    im->n_srows = d->n_srows;
-    im->n_child = d->n_child;
-    im->n_lines = d->n_lines;
-    std::vector<FbsStep> steps((size_t)d->n_steps);
-    std::vector<int> vrow_srow((size_t)d->n_vrows, -1);
-    std::vector<double> vrow_cap((size_t)d->n_vrows, 0.0);
+    int n_sm = 0;
+    GP_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    double* d_out = nullptr;
+    GP_CUDA(cudaMalloc(&d_out, 8));
+    cudaEvent_t e0, e1;
+    GP_CUDA(cudaEventCreate(&e0));
+    GP_CUDA(cudaEventCreate(&e1));
+    const int iters = 8192, blocks = n_sm * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        GP_CUDA(cudaEventRecord(e0, 0));
+        fp64_peak_kernel<<<blocks, 256>>>(d_out, iters, 0.999999, 1e-9);
+        GP_CUDA(cudaEventRecord(e1, 0));
+        GP_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        GP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    GP_CUDA(cudaGetLastError());
+    *tflops = best;
+    return GP_OK;
+}
+
+// GpFbsDesc -> step records, child table, constants (host side; shared by gp_fbs_create and
+// the source generator)
+static int fbs_tables_from_desc(const GpFbsDesc* d, std::vector<FbsStep>& steps, std::vector<int4>& child4,
+                                FbsConst& k, std::vector<int>& vrow_srow, std::vector<double>& vrow_cap) {
+    if (d->n_steps < 0 || d->n_vrows <= 0 || d->n_irows < 0 || d->n_srows < 0 || d->n_child < 0)
+        return fail(GP_EINVAL, "gp_fbs_create: bad sizes");
+    steps.assign((size_t)d->n_steps, FbsStep());
+    vrow_srow.assign((size_t)d->n_vrows, -1);
+    vrow_cap.assign((size_t)d->n_vrows, 0.0);
     auto chk = [&](int r, int n) { return r >= -1 && r < n; };
     for (int i = 0; i < d->n_steps; ++i) {
         FbsStep& s = steps[i];
@@ -906,20 +1049,16 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
         s.kind = d->kind[i];
         s.child_begin = d->child_begin[i];
         s.child_count = d->child_count[i];
-        if (s.child_begin < 0 || s.child_count < 0 || s.child_begin + s.child_count > d->n_child) {
-            delete im;
+        if (s.child_begin < 0 || s.child_count < 0 || s.child_begin + s.child_count > d->n_child)
             return fail(GP_EINVAL, "gp_fbs_create: step %d child range out of bounds", i);
-        }
         for (int p = 0; p < 3; ++p) {
             s.bus_vrow[p] = d->bus_vrow[3 * i + p];
             s.par_vrow[p] = d->par_vrow[3 * i + p];
             s.edge_irow[p] = d->edge_irow[3 * i + p];
             s.load_srow[p] = d->load_srow[3 * i + p];
             if (!chk(s.bus_vrow[p], d->n_vrows) || !chk(s.par_vrow[p], d->n_vrows) ||
-                !chk(s.edge_irow[p], d->n_irows) || !chk(s.load_srow[p], d->n_srows)) {
-                delete im;
+                !chk(s.edge_irow[p], d->n_irows) || !chk(s.load_srow[p], d->n_srows))
                 return fail(GP_EINVAL, "gp_fbs_create: step %d row index out of range", i);
-            }
             s.cap[p] = d->cappu[3 * i + p];
             s.gamma[p] = d->vr_gamma[3 * i + p];
             s.inv_gamma[p] = s.gamma[p] != 0.0 ? 1.0 / s.gamma[p] : 0.0;
@@ -947,20 +1086,140 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
         if (mb != 0 && mb == me && (mp & mb) == mb) s.kind |= mb << 8;
     }
     for (int p = 0; p < 3; ++p) {
-        im->k.root_vrow[p] = d->root_vrow[p];
-        im->k.root_load_srow[p] = d->root_load_srow[p];
-        im->k.root_cap[p] = d->root_cappu[p];
-        im->k.vref[p] = make_double2(d->vref[2 * p], d->vref[2 * p + 1]);
-        if (d->root_vrow[p] < 0 || d->root_vrow[p] >= d->n_vrows) {
-            delete im;
+        k.root_vrow[p] = d->root_vrow[p];
+        k.root_load_srow[p] = d->root_load_srow[p];
+        k.root_cap[p] = d->root_cappu[p];
+        k.vref[p] = make_double2(d->vref[2 * p], d->vref[2 * p + 1]);
+        if (d->root_vrow[p] < 0 || d->root_vrow[p] >= d->n_vrows)
             return fail(GP_EINVAL, "gp_fbs_create: the root bus must carry all three phases");
-        }
         vrow_srow[d->root_vrow[p]] = d->root_load_srow[p];
         vrow_cap[d->root_vrow[p]] = d->root_cappu[p];
     }
-    im->k.aPQ = d->zip[0];
-    im->k.aI = d->zip[1];
-    im->k.aZ = d->zip[2];
+    k.aPQ = d->zip[0];
+    k.aI = d->zip[1];
+    k.aZ = d->zip[2];
+    child4.assign((size_t)d->n_child, make_int4(-1, -1, -1, 0));
+    for (int c = 0; c < d->n_child; ++c) {
+        child4[c] = make_int4(d->child_irow[3 * c], d->child_irow[3 * c + 1], d->child_irow[3 * c + 2], 0);
+        if (!chk(child4[c].x, d->n_irows) || !chk(child4[c].y, d->n_irows) || !chk(child4[c].z, d->n_irows))
+            return fail(GP_EINVAL, "gp_fbs_create: child %d row index out of range", c);
+    }
+    return GP_OK;
+}
+
+extern "C" int64_t gp_fbs_jit_source(const GpFbsDesc* d, int32_t warps, char* buf, int64_t cap) {
+    if (!d || warps < 1 || warps > 16) return fail(GP_EINVAL, "gp_fbs_jit_source: bad argument");
+    std::vector<FbsStep> steps;
+    std::vector<int4> child4;
+    std::vector<int> vrow_srow;
+    std::vector<double> vrow_cap;
+    FbsConst k;
+    int rc = fbs_tables_from_desc(d, steps, child4, k, vrow_srow, vrow_cap);
+    if (rc) return rc;
+    const std::string src = fbs_jit_source(steps, child4, k, d->n_vrows, d->n_irows, d->n_srows, warps);
+    if (src.empty()) return fail(GP_EJIT, "gp_fbs_jit_source: non-finite impedance in the descriptor");
+    if (buf && cap > 0) {
+        const size_t n = std::min((size_t)cap - 1, src.size());
+        memcpy(buf, src.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)src.size();
+}
+
+extern "C" int gp_jit_compile(const char* source, void* cubin, int64_t cap, int64_t* cubin_bytes) {
+    if (!source || !cubin_bytes) return fail(GP_EINVAL, "gp_jit_compile: null argument");
+    std::vector<char> bin;
+    std::string log;
+    const int rc = jit_compile(source, bin, log);
+    if (rc) return fail(rc, "gp_jit_compile: %s", log.substr(0, 400).c_str());
+    *cubin_bytes = (int64_t)bin.size();
+    if (cubin && cap >= (int64_t)bin.size()) memcpy(cubin, bin.data(), bin.size());
+    return GP_OK;
+}
+
+// ---- driver API through dlopen (module load + launch of the specialised kernel) ------------
+namespace {
+struct Driver {
+    void* h = nullptr;
+    int (*ModuleLoadData)(void**, const void*) = nullptr;
+    int (*ModuleGetFunction)(void**, void*, const char*) = nullptr;
+    int (*ModuleUnload)(void*) = nullptr;
+    int (*FuncSetAttribute)(void*, int, int) = nullptr;
+    int (*LaunchKernel)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**,
+                        void**) = nullptr;
+    bool ok = false;
+};
+Driver& driver() {
+    static Driver d;
+    static bool tried = false;
+    if (tried) return d;
+    tried = true;
+    d.h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!d.h) return d;
+    *(void**)(&d.ModuleLoadData) = dlsym(d.h, "cuModuleLoadData");
+    *(void**)(&d.ModuleGetFunction) = dlsym(d.h, "cuModuleGetFunction");
+    *(void**)(&d.ModuleUnload) = dlsym(d.h, "cuModuleUnload");
+    *(void**)(&d.FuncSetAttribute) = dlsym(d.h, "cuFuncSetAttribute");
+    *(void**)(&d.LaunchKernel) = dlsym(d.h, "cuLaunchKernel");
+    d.ok = d.ModuleLoadData && d.ModuleGetFunction && d.ModuleUnload && d.FuncSetAttribute && d.LaunchKernel;
+    return d;
+}
+}  // namespace
+
+extern "C" int gp_fbs_specialise(GpFeeder* f) {
+    if (!f || f->kind != 1) return fail(GP_EINVAL, "gp_fbs_specialise: not an FBS feeder handle");
+    FbsImpl* im = (FbsImpl*)f->impl;
+    if (im->jit_kernel) return GP_OK;
+    if (im->onchip_warps < 1) return fail(GP_EJIT, "gp_fbs_specialise: the feeder does not fit the on-chip kernel");
+    GP_CUDA(cudaSetDevice(f->device));
+    GP_CUDA(cudaFree(0));       // make sure the primary context exists and is current
+    const std::string src = fbs_jit_source(im->h_steps, im->h_child, im->k, im->n_vrows, im->n_irows, im->n_srows,
+                                           im->onchip_warps);
+    if (src.empty()) return fail(GP_EJIT, "gp_fbs_specialise: non-finite impedance");
+    std::vector<char> bin;
+    std::string log;
+    int rc = jit_compile(src, bin, log);
+    if (rc) return fail(rc, "gp_fbs_specialise: %s", log.substr(0, 400).c_str());
+    Driver& dr = driver();
+    if (!dr.ok) return fail(GP_EJIT, "gp_fbs_specialise: libcuda.so.1 could not be loaded");
+    void* mod = nullptr;
+    void* fn = nullptr;
+    int cr = dr.ModuleLoadData(&mod, bin.data());
+    if (cr != 0) return fail(GP_EJIT, "gp_fbs_specialise: cuModuleLoadData failed (%d)", cr);
+    cr = dr.ModuleGetFunction(&fn, mod, "gp_fbs_jit_kernel");
+    const int smem = im->onchip_warps * (im->n_vrows + im->n_irows) * 512;
+    if (cr == 0) cr = dr.FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, smem);
+    if (cr != 0) {
+        dr.ModuleUnload(mod);
+        return fail(GP_EJIT, "gp_fbs_specialise: kernel lookup / shared-memory opt-in failed (%d)", cr);
+    }
+    im->jit_module = mod;
+    im->jit_kernel = fn;
+    im->jit_warps = im->onchip_warps;
+    return GP_OK;
+}
+
+extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
+    if (!d || !out) return fail(GP_EINVAL, "gp_fbs_create: null argument");
+    std::vector<FbsStep> steps;
+    std::vector<int4> child4;
+    std::vector<int> vrow_srow;
+    std::vector<double> vrow_cap;
+    FbsConst k0;
+    int rc0 = fbs_tables_from_desc(d, steps, child4, k0, vrow_srow, vrow_cap);
+    if (rc0) return rc0;
+    GP_CUDA(cudaSetDevice(device));
+    FbsImpl* im = new (std::nothrow) FbsImpl();
+    if (!im) return fail(GP_ENOMEM, "gp_fbs_create: out of host memory");
+    im->n_steps = d->n_steps;
+    im->n_vrows = d->n_vrows;
+    im->n_irows = d->n_irows;
+    im->n_srows = d->n_srows;
+    im->n_child = d->n_child;
+    im->n_lines = d->n_lines;
+    im->k = k0;
+    im->h_steps = steps;
+    im->h_child = child4;
     std::vector<int> lines((size_t)d->n_lines * 9);
     for (int l = 0; l < d->n_lines; ++l)
         for (int p = 0; p < 3; ++p) {
@@ -1057,16 +1316,28 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
     cudaError_t e = up((void**)&im->d_steps, steps.data(), steps.size() * sizeof(FbsStep));
     if (e == cudaSuccess) e = up((void**)&im->d_events, events.data(), events.size() * sizeof(int2));
     if (e == cudaSuccess) e = up((void**)&im->d_evrows, evrows.data(), evrows.size() * sizeof(int4));
-    std::vector<int4> child4((size_t)d->n_child);
-    for (int c = 0; c < d->n_child; ++c)
-        child4[c] = make_int4(d->child_irow[3 * c], d->child_irow[3 * c + 1], d->child_irow[3 * c + 2], 0);
     if (e == cudaSuccess) e = up((void**)&im->d_child, child4.data(), child4.size() * sizeof(int4));
     if (e == cudaSuccess) e = up((void**)&im->d_lines, lines.data(), lines.size() * sizeof(int));
     if (e == cudaSuccess) e = up((void**)&im->d_vrow_srow, vrow_srow.data(), vrow_srow.size() * sizeof(int));
     if (e == cudaSuccess) e = up((void**)&im->d_vrow_cap, vrow_cap.data(), vrow_cap.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&im->d_sched, 16);
+    if (e == cudaSuccess) e = cudaMemset(im->d_sched, 0, 16);
+    int smem_optin = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&im->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) {
         delete im;
         return fail(GP_ECUDA, "gp_fbs_create: %s", cudaGetErrorString(e));
+    }
+    {   // warps per block of the on-chip kernel: one 32-scenario slice of V and I rows per warp
+        const size_t per_warp = (size_t)(d->n_vrows + d->n_irows) * 512;
+        const int fit = (int)((size_t)smem_optin / per_warp);
+        static const int sizes[] = {16, 12, 8, 6, 4, 3, 2, 1};
+        for (int w : sizes)
+            if (w <= fit) {
+                im->onchip_warps = w;
+                break;
+            }
     }
     GpFeeder* f = new (std::nothrow) GpFeeder();
     f->device = device;
@@ -1088,6 +1359,8 @@ extern "C" int gp_feeder_destroy(GpFeeder* f) {
         cudaFree(im->d_vrow_cap);
         cudaFree(im->d_events);
         cudaFree(im->d_evrows);
+        cudaFree(im->d_sched);
+        if (im->jit_module) driver().ModuleUnload(im->jit_module);
         for (int i = 0; i < FbsImpl::NSTREAM; ++i) {
             if (im->d_stage[i]) cudaFree(im->d_stage[i]);
             if (im->streams[i]) cudaStreamDestroy(im->streams[i]);
@@ -1122,14 +1395,61 @@ extern "C" int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
     constexpr int BLOCK = 128;
     const unsigned gx = (unsigned)((S + BLOCK - 1) / BLOCK);
     const bool dfs = im->n_events > 0 && g_fbs_kernel == 1;
-    if (g_fbs_kernel == 2) {
+    const unsigned ldb = (unsigned)(ld * 16);
+    // automatic choice: the on-chip kernel needs at least 4 resident warps per SM to keep the FP64
+    // pipe busy; larger feeders stream their state through HBM with the two-sweep kernel
+    const bool onchip = g_fbs_kernel == 4 || (g_fbs_kernel == 0 && im->onchip_warps >= 4);
+    if (g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) {
+        if (!im->jit_kernel)
+            return fail(GP_EINVAL, "gp_fbs_solve_batch: fbs_kernel = 5 needs a successful gp_fbs_specialise");
+        const long long n_tiles = (S + 31) / 32;
+        const int nw = im->jit_warps;
+        long long blocks = (n_tiles + nw - 1) / nw;
+        if (blocks > im->n_sm) blocks = im->n_sm;
+        const unsigned smem = (unsigned)nw * (unsigned)(im->n_vrows + im->n_irows) * 512u;
+        long long S_arg = S;
+        double tol_arg = tol;
+        int maxiter_arg = maxiter;
+        unsigned ldb_arg = ldb;
+        void* args[] = {(void*)&spu, (void*)&V, (void*)&I, (void*)&iters, (void*)&status, (void*)&diff,
+                        (void*)&S_arg, (void*)&ldb_arg, (void*)&tol_arg, (void*)&maxiter_arg, (void*)&im->d_sched};
+        const int cr = driver().LaunchKernel(im->jit_kernel, (unsigned)blocks, 1, 1, (unsigned)nw * 32, 1, 1, smem,
+                                             (void*)st, args, nullptr);
+        if (cr != 0) return fail(GP_ECUDA, "gp_fbs_solve_batch: cuLaunchKernel failed (%d)", cr);
+    } else if (onchip) {
+        if (im->onchip_warps < 1)
+            return fail(GP_EINVAL, "gp_fbs_solve_batch: the on-chip kernel needs %d bytes of shared memory per warp",
+                        (im->n_vrows + im->n_irows) * 512);
+        const long long n_tiles = (S + 31) / 32;
+        const int nw = im->onchip_warps;
+        const size_t smem = (size_t)nw * (size_t)(im->n_vrows + im->n_irows) * 512;
+        long long blocks = (n_tiles + nw - 1) / nw;
+        if (blocks > im->n_sm) blocks = im->n_sm;
+#define GP_ONCHIP(NW)                                                                                           \
+    case NW: {                                                                                                  \
+        static bool attr_set = false;   /* per template instance; the limit is per function, any device */       \
+        if (!attr_set) {                                                                                        \
+            GP_CUDA(cudaFuncSetAttribute(fbs_onchip_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                         232448));                                                              \
+            attr_set = true;                                                                                    \
+        }                                                                                                       \
+        fbs_onchip_kernel<NW><<<(unsigned)blocks, NW * 32, smem, st>>>(                                         \
+            im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows, im->n_irows, S, ldb, (const char*)spu,   \
+            (char*)V, (char*)I, iters, status, diff, tol, maxiter, im->d_sched);                                \
+        break;                                                                                                  \
+    }
+        switch (nw) {
+            GP_ONCHIP(16) GP_ONCHIP(12) GP_ONCHIP(8) GP_ONCHIP(6) GP_ONCHIP(4) GP_ONCHIP(3) GP_ONCHIP(2) GP_ONCHIP(1)
+            default: return fail(GP_EINVAL, "gp_fbs_solve_batch: bad on-chip warp count %d", nw);
+        }
+#undef GP_ONCHIP
+    } else if (g_fbs_kernel == 2) {
         const long long warps = (S + 9) / 10;
         const unsigned gp = (unsigned)((warps * 32 + BLOCK - 1) / BLOCK);
         fbs_phase_kernel<BLOCK><<<gp, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
-                                                      im->n_irows, S, (unsigned)(ld * 16), (const char*)spu, (char*)V,
+                                                      im->n_irows, S, ldb, (const char*)spu, (char*)V,
                                                       (char*)I, iters, status, diff, tol, maxiter);
     } else if (dfs) {
-        const unsigned ldb = (unsigned)(ld * 16);
 #define GP_DFS(D)                                                                                          \
     fbs_dfs_kernel<BLOCK, D><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_events, im->d_evrows, im->n_events, im->k, S, ldb, \
                                                    (const char*)spu, (char*)V, (char*)I, iters, status,    \
@@ -1141,7 +1461,7 @@ extern "C" int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
 #undef GP_DFS
     } else {
         fbs_solve_kernel<BLOCK><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
-                                                      im->n_irows, S, (unsigned)(ld * 16), (const char*)spu, (char*)V,
+                                                      im->n_irows, S, ldb, (const char*)spu, (char*)V,
                                                       (char*)I, iters, status, diff, tol, maxiter);
     }
     count_launch();

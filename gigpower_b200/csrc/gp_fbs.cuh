@@ -1,0 +1,74 @@
+// FBS feeder tables shared by the kernels (gp_fbs.cu) and the specialised-kernel generator
+// (gp_fbs_jit.cu).
+#pragma once
+#include "gp_common.cuh"
+
+#include <string>
+#include <vector>
+
+namespace gp {
+
+struct __align__(16) FbsStep {
+    int bus_vrow[3];
+    int kind;
+    int par_vrow[3];
+    int child_begin;
+    int edge_irow[3];
+    int child_count;
+    int load_srow[3];
+    int pad0;
+    double cap[3];
+    double pad1;
+    double gamma[3];
+    double pad2;
+    double inv_gamma[3];
+    double pad3;
+    double2 z[9];
+};
+static_assert(sizeof(FbsStep) == 64 + 32 + 32 + 32 + 144, "FbsStep layout");
+
+struct FbsConst {
+    int root_vrow[3];
+    int root_load_srow[3];
+    double root_cap[3];
+    double2 vref[3];
+    double aPQ, aI, aZ;
+};
+
+struct FbsImpl {
+    int n_steps = 0, n_vrows = 0, n_irows = 0, n_srows = 0, n_child = 0, n_lines = 0;
+    FbsStep* d_steps = nullptr;
+    int4* d_child = nullptr;  // [n_child] {I rows of the child edge, 0}
+    int* d_lines = nullptr;   // [n_lines][9] irow, tx vrow, rx vrow
+    int* d_vrow_srow = nullptr;   // [n_vrows] spu row of each V row or -1
+    double* d_vrow_cap = nullptr; // [n_vrows]
+    FbsConst k;
+    // fused depth-first schedule (fbs_dfs_kernel): 2 events per step, or none if not applicable
+    int2* d_events = nullptr;
+    int4* d_evrows = nullptr;   // per event: the 3 rows to prefetch, .w = 1 for I rows (descend), 0 for spu rows
+    int n_events = 0, depth = 0;
+    // on-chip kernel (fbs_onchip_kernel): tile scheduler words {next tile, warps done}, SM count,
+    // warps per block that fit the feeder's V and I rows in shared memory (0 = does not fit)
+    unsigned* d_sched = nullptr;
+    int n_sm = 0, onchip_warps = 0;
+    // feeder-specialised on-chip kernel (gp_fbs_specialise): host copies of the tables the
+    // generator reads, the loaded module and its kernel
+    std::vector<FbsStep> h_steps;
+    std::vector<int4> h_child;
+    void* jit_module = nullptr;   // CUmodule
+    void* jit_kernel = nullptr;   // CUfunction
+    int jit_warps = 0;
+    // host staging for gp_fbs_solve_batch_host
+    static constexpr int NSTREAM = 4;
+    cudaStream_t streams[NSTREAM] = {nullptr, nullptr, nullptr, nullptr};
+    void* d_stage[NSTREAM] = {nullptr, nullptr, nullptr, nullptr};
+    size_t stage_bytes = 0;
+};
+
+
+// gp_fbs_jit.cu: CUDA source of the feeder-specialised on-chip kernel, NVRTC compilation
+std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<int4>& child, const FbsConst& k,
+                           int n_vrows, int n_irows, int n_srows, int nw);
+int jit_compile(const std::string& src, std::vector<char>& cubin, std::string& log);
+
+}  // namespace gp

@@ -111,6 +111,11 @@ class SolutionFBS(Solution):
                              dtype=complex)
         self.tolerance = abs((self.Vref[1]) * 10 ** -6)
         self._feeder = None
+        self._specialised = None      # None = not tried, True / False = outcome of specialise()
+
+    #: batches of at least this many scenarios compile the feeder-specialised kernel (about one
+    #: second with NVRTC, once per instance) when the feeder fits the on-chip kernel
+    SPECIALISE_MIN_BATCH = 8192
 
     # ---- device plumbing -----------------------------------------------------
     def _dev(self):
@@ -121,6 +126,27 @@ class SolutionFBS(Solution):
             desc, keep = _cabi.make_fbs_desc(self.tables)
             self._feeder = _Feeder(desc, keep, _cabi.gp_fbs_create, self.device)
         return torch, torch.device('cuda', self.device)
+
+    def specialise(self) -> bool:
+        """Generate, compile (NVRTC) and load the feeder-specialised on-chip kernel
+        (``gp_fbs_specialise``).  Returns False - and the table-driven kernels keep being used -
+        when the feeder does not fit in shared memory or no runtime compiler is available."""
+        self._dev()
+        if self._specialised is None:
+            rc = _cabi.gp_fbs_specialise(self._feeder.handle)
+            self._specialised = rc == 0
+            if rc != 0:
+                import warnings
+                try:
+                    _cabi.check(rc)
+                except _cabi.GpError as e:
+                    warnings.warn(f'feeder-specialised FBS kernel unavailable, using the table-driven kernel: {e}')
+        return self._specialised
+
+    def _maybe_specialise(self, S):
+        if (self._specialised is None and S >= self.SPECIALISE_MIN_BATCH
+                and _cabi.gp_fbs_onchip_warps(self._feeder.handle) >= 4):
+            self.specialise()
 
     def pack_spu(self, spu) -> np.ndarray:
         """``[S, nb, 3]`` complex (the reference's ``Solution.spu`` per scenario)
@@ -173,6 +199,7 @@ class SolutionFBS(Solution):
         if d_spu.dim() != 2 or d_spu.shape[0] != t.n_srows:
             raise ValueError(f"spu_rows must be [{t.n_srows}, S], got {tuple(d_spu.shape)}")
         S = ld = int(d_spu.shape[1])
+        self._maybe_specialise(S)
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream() if stream is None else stream
             with torch.cuda.stream(st):
@@ -226,6 +253,7 @@ class SolutionFBS(Solution):
             return x.data_ptr() if hasattr(x, 'data_ptr') else x.ctypes.data
 
         S = ld = int(spu_rows.shape[1])
+        self._maybe_specialise(S)
         # pinned result vectors: a D2H copy into pageable memory would block the host inside
         # the library and serialise the copy/compute pipeline
         if getattr(self, '_host_vecs', None) is None or self._host_vecs[0].numel() < S:

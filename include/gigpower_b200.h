@@ -36,6 +36,7 @@ extern "C" {
 #define GP_EINVAL (-1)   /* bad argument / inconsistent descriptor */
 #define GP_ECUDA (-2)    /* CUDA runtime error (message has the detail) */
 #define GP_ENOMEM (-3)   /* host or device allocation failed */
+#define GP_EJIT (-4)     /* the feeder-specialised kernel could not be generated, compiled or loaded */
 
 #define GP_ST_CONVERGED 0
 #define GP_ST_MAXITER 1
@@ -103,11 +104,50 @@ int64_t gp_launch_count(void);
 
 /*
  * Process-wide switches.  "fbs_kernel" selects the FBS solve kernel (identical results):
- * 0 = two-sweep, one thread per scenario (default); 1 = fused depth-first walk; 2 = two-sweep
- * with three phase lanes per scenario.  "host_chunks": number of pipeline chunks of
- * gp_fbs_solve_batch_host (0 = automatic).
+ * 0 = automatic: the on-chip kernel when the feeder's V and I rows of >= 4 warps fit in one SM's
+ * shared memory, else the two-sweep streaming kernel (default); 1 = fused depth-first walk;
+ * 2 = two-sweep with three phase lanes per scenario; 3 = two-sweep streaming (state in HBM);
+ * 4 = on-chip (state in shared memory; the solve fails with GP_EINVAL if not even one warp fits);
+ * 5 = the feeder-specialised on-chip kernel (gp_fbs_specialise must have succeeded).  Under 0 a
+ * specialised feeder runs its specialised kernel.
+ * "host_chunks": number of pipeline chunks of gp_fbs_solve_batch_host (0 = automatic).
  */
 int gp_set_option(const char* name, int value);
+
+/*
+ * Which kernel gp_fbs_solve_batch launches for this feeder under the current "fbs_kernel"
+ * option (1..5 as above; bench.py uses it to pick the roofline that bounds the kernel), and
+ * how many 32-scenario warps of the on-chip kernel fit in one SM (0 = none).
+ */
+int gp_fbs_active_kernel(GpFeeder* f);
+int gp_fbs_onchip_warps(GpFeeder* f);
+
+/*
+ * Feeder-specialised kernel.  A flattened feeder fixes the whole sweep schedule, so for a
+ * feeder that fits the on-chip kernel the library can write that schedule out as straight-line
+ * CUDA C++ (row offsets as immediates, impedances as literals, absent phases and load-free
+ * bus-phases elided, a scenario's loads held in registers), compile it for sm_100a with NVRTC
+ * (dlopen'ed: no link-time dependency) and run it in place of the table-driven kernel.  Same
+ * arithmetic, same outputs.
+ *   gp_fbs_specialise     generate + compile + load for this handle (needs the device); GP_EJIT
+ *                         with a message if NVRTC or the driver is unavailable - the handle then
+ *                         keeps using the table-driven kernels
+ *   gp_fbs_jit_source     host only: the CUDA source for a descriptor and `warps` warps per
+ *                         block; returns its length (excluding the NUL) or a negative GP_E*;
+ *                         copies at most cap-1 characters into buf when buf is not NULL
+ *   gp_jit_compile        host only: NVRTC-compile a source for sm_100a; the cubin size goes
+ *                         to *cubin_bytes, the cubin itself into cubin (cap bytes) when not NULL
+ */
+int gp_fbs_specialise(GpFeeder* f);
+int64_t gp_fbs_jit_source(const GpFbsDesc* desc, int32_t warps, char* buf, int64_t cap);
+int gp_jit_compile(const char* source, void* cubin, int64_t cap, int64_t* cubin_bytes);
+
+/*
+ * Measured FP64 FMA throughput of the device in TFLOP/s (2 flop per DFMA, 8 independent
+ * chains per thread, best of 5 launches timed with CUDA events): the denominator of the
+ * FP64 roofline of the on-chip FBS kernel and of the NR3 elimination.
+ */
+int gp_measure_fp64_peak(int device, double* tflops);
 
 /*
  * Build the device-resident feeder tables.  Replaces SolutionFBS.__init__'s

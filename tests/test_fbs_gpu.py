@@ -165,24 +165,71 @@ def test_errors_are_python_exceptions():
                                              1e-6, 100, None))
 
 
-@pytest.mark.parametrize('feeder', ['IEEE_13_Bus_allwye', 'IEEE_34_Bus_allwye_noxfm_noreg', 'IEEE_37_Bus_allwye'])
-def test_two_sweep_kernel_and_fused_dfs_kernel_agree(feeder):
-    """The library has two FBS kernels (fused depth-first walk = default, two-sweep =
-    general fallback); both must meet the oracle and each other."""
+KERNELS = {0: 'automatic', 1: 'fused depth-first', 2: 'phase-parallel', 3: 'two-sweep streaming', 4: 'on-chip',
+           5: 'feeder-specialised on-chip'}
+
+
+@pytest.mark.parametrize('feeder', ['IEEE_13_Bus_allwye', 'IEEE_13_Bus_allwye_noxfm_noreg',
+                                    'IEEE_34_Bus_allwye_noxfm_noreg', 'IEEE_34_Bus_allwye', 'IEEE_37_Bus_allwye'])
+def test_all_fbs_kernels_agree(feeder):
+    """The library has four FBS kernels (on-chip and two-sweep streaming = the automatic choices,
+    fused depth-first walk and phase-parallel lanes = options); each must meet the oracle, and
+    they must agree with each other to rounding."""
     from gigpower_b200 import _cabi
     rng = np.random.Generator(np.random.PCG64(21))
     o = _oracle(feeder)
     mult = rng.uniform(0.5, 1.5, size=(777, len(o.c.load_names)))
     want = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
     s = _fbs(feeder)
+    assert s.specialise(), 'NVRTC / driver module load failed on the GPU box'
     res = {}
     try:
-        for mode in (0, 1, 2):
+        for mode in KERNELS:
             _cabi.check(_cabi.gp_set_option(b'fbs_kernel', mode))
             res[mode] = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
     finally:
         _cabi.gp_set_option(b'fbs_kernel', 0)
-    for mode in (0, 1, 2):
-        assert np.array_equal(res[mode].iterations, want['iterations']), mode
-        assert rel_err(res[mode].V, want['V']) <= TOL and rel_err(res[mode].I, want['I']) <= TOL, mode
-    assert rel_err(res[0].V, res[1].V) <= 1e-12 and rel_err(res[0].V, res[2].V) <= 1e-12
+    for mode in KERNELS:
+        assert np.array_equal(res[mode].iterations, want['iterations']), KERNELS[mode]
+        assert rel_err(res[mode].V, want['V']) <= TOL and rel_err(res[mode].I, want['I']) <= TOL, KERNELS[mode]
+        assert rel_err(res[3].V, res[mode].V) <= 1e-12, KERNELS[mode]
+    # the on-chip and the streaming kernel run the same arithmetic in the same order: bit-identical
+    assert np.array_equal(res[3].V, res[4].V) and np.array_equal(res[3].I, res[4].I)
+
+
+def test_onchip_kernel_full_batch_and_relaunch():
+    """On-chip kernel at BASELINE C2 size: persistent warps pull 32-scenario tiles from a device
+    counter that the last warp re-arms, so back-to-back launches must give identical results;
+    ragged last tile; results bit-identical to the streaming kernel."""
+    from gigpower_b200 import _cabi
+    feeder, S = 'IEEE_13_Bus_allwye_noxfm_noreg', 65536 + 17
+    rng = np.random.Generator(np.random.PCG64(5))
+    s = _fbs(feeder)
+    mult = rng.uniform(0.5, 1.5, size=(S, s.circuit.loads.num_elements))
+    s._dev()
+    assert _cabi.gp_fbs_onchip_warps(s._feeder.handle) >= 4
+    assert _cabi.gp_fbs_active_kernel(s._feeder.handle) in (4, 5)
+    try:
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 3))
+        ref = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 4))
+        for _ in range(3):
+            r = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
+            assert np.array_equal(r.iterations, ref.iterations) and np.array_equal(r.status, ref.status)
+            assert np.array_equal(r.V, ref.V) and np.array_equal(r.I, ref.I)
+            assert np.array_equal(r.convergence_diff, ref.convergence_diff)
+        for S2 in (1, 31, 33, 4097):
+            r = s.solve_batch(load_mult=mult[:S2], outputs=('V',))
+            assert np.array_equal(r.V, ref.V[:S2]) and np.array_equal(r.iterations, ref.iterations[:S2])
+        # the batch above was large enough to compile the feeder-specialised kernel: automatic = 5 now
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 0))
+        assert s._specialised and _cabi.gp_fbs_active_kernel(s._feeder.handle) == 5
+        for _ in range(2):
+            r = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
+            assert np.array_equal(r.iterations, ref.iterations) and np.array_equal(r.status, ref.status)
+            assert rel_err(r.V, ref.V) <= 1e-13 and rel_err(r.I, ref.I) <= 1e-13
+        for S2 in (1, 31, 33, 4097):
+            r = s.solve_batch(load_mult=mult[:S2], outputs=('V',))
+            assert rel_err(r.V, ref.V[:S2]) <= 1e-13 and np.array_equal(r.iterations, ref.iterations[:S2])
+    finally:
+        _cabi.gp_set_option(b'fbs_kernel', 0)

@@ -83,3 +83,35 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 txt = open(os.path.join(root, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', txt, flags=re.M), f
+
+
+@pytest.mark.parametrize('feeder,warps', [('IEEE_13_Bus_allwye_noxfm_noreg', 6), ('IEEE_13_Bus_allwye', 6),
+                                          ('IEEE_37_Bus_allwye', 1)])
+def test_specialised_kernel_source_generates_and_compiles(feeder, warps):
+    """Host-only half of gp_fbs_specialise: the generator writes the feeder's sweep schedule as
+    straight-line CUDA and NVRTC compiles it for sm_100a (no GPU needed for either)."""
+    import ctypes as C
+    from gigpower_b200 import _cabi
+    from gigpower_b200.circuit import Circuit
+    from gigpower_b200.flatten import flatten_fbs
+    t = flatten_fbs(Circuit(load_model(feeder)))
+    d, keep = _cabi.make_fbs_desc(t)
+    n = _cabi.gp_fbs_jit_source(C.byref(d), warps, None, 0)
+    assert n > 0
+    buf = C.create_string_buffer(n + 1)
+    assert _cabi.gp_fbs_jit_source(C.byref(d), warps, buf, n + 1) == n
+    src = buf.value.decode()
+    assert len(src) == n and 'gp_fbs_jit_kernel' in src and f'#define NV {t.n_vrows}' in src
+    # one forward and one backward block per step, in sweep order
+    assert src.count('// forward step') == t.n_steps and src.count('// backward step') == t.n_steps
+    assert src.index('// forward step 0\n') < src.index(f'// backward step {t.n_steps - 1}\n') \
+        < src.index('// backward step 0\n')
+    size = C.c_int64(0)
+    _cabi.check(_cabi.gp_jit_compile(buf.value, None, 0, C.byref(size)))
+    assert size.value > 10000
+    cubin = C.create_string_buffer(size.value)
+    _cabi.check(_cabi.gp_jit_compile(buf.value, cubin, size.value, C.byref(size)))
+    assert cubin.raw[:4] == b'\x7fELF'
+    # bad arguments are errors, not crashes
+    assert _cabi.gp_fbs_jit_source(C.byref(d), 0, None, 0) < 0
+    assert _cabi.gp_jit_compile(b'this is not CUDA', None, 0, C.byref(size)) == -4
