@@ -233,3 +233,36 @@ def test_onchip_kernel_full_batch_and_relaunch():
             assert rel_err(r.V, ref.V[:S2]) <= 1e-13 and np.array_equal(r.iterations, ref.iterations[:S2])
     finally:
         _cabi.gp_set_option(b'fbs_kernel', 0)
+
+
+def test_specialised_kernel_restarts_diverging_scenarios_exactly():
+    """The specialised kernel runs branch-free arithmetic and restarts a scenario with the exact
+    nan_to_num / division semantics when a current goes non-finite: heavily overloaded scenarios
+    (which blow up) must report the same iterations and status as the table-driven kernel, and
+    their well-behaved neighbours the same voltages."""
+    from gigpower_b200 import _cabi
+    feeder = 'IEEE_13_Bus_allwye_noxfm_noreg'
+    s = _fbs(feeder)
+    assert s.specialise()
+    nload = s.circuit.loads.num_elements
+    rng = np.random.Generator(np.random.PCG64(99))
+    mult = rng.uniform(0.5, 1.5, size=(512, nload))
+    mult[5] *= 40.0
+    mult[100] *= 1e3
+    mult[257] *= 1e6
+    mult[300] = 0.0
+    try:
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 3))
+        ref = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 5))
+        r = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
+    finally:
+        _cabi.gp_set_option(b'fbs_kernel', 0)
+    assert (ref.status != 0).sum() >= 2, 'the overloaded scenarios were expected to fail'
+    assert np.array_equal(r.iterations, ref.iterations) and np.array_equal(r.status, ref.status)
+    ok = ref.status == 0
+    assert rel_err(r.V[ok], ref.V[ok]) <= 1e-12 and rel_err(r.I[ok], ref.I[ok]) <= 1e-12
+    bad = ~ok
+    fin = np.isfinite(ref.V[bad]) & np.isfinite(r.V[bad])
+    assert np.array_equal(np.isfinite(ref.V[bad]), np.isfinite(r.V[bad]))
+    assert rel_err(r.V[bad][fin], ref.V[bad][fin]) <= 1e-9
