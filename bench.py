@@ -333,14 +333,23 @@ def run_ours(args, wl):
         I = torch.empty((max(t.n_irows, 1), ld), dtype=c128, device=dev)
         tol = sol.tolerance
 
+        fused = active == 5     # the specialised kernel writes |V| and losses itself
+
         def solve_kernel():
-            _cabi.check(_cabi.gp_fbs_solve_batch(h, S, ld, spu_d.data_ptr(), V.data_ptr(), I.data_ptr(),
-                                                 iters.data_ptr(), status.data_ptr(), diff.data_ptr(),
-                                                 tol, maxiter, stream.cuda_stream))
+            if fused:
+                _cabi.check(_cabi.gp_fbs_solve_post_batch(h, S, ld, spu_d.data_ptr(), V.data_ptr(), I.data_ptr(),
+                                                          iters.data_ptr(), status.data_ptr(), diff.data_ptr(),
+                                                          Vmag.data_ptr(), loss.data_ptr(), tol, maxiter,
+                                                          stream.cuda_stream))
+            else:
+                _cabi.check(_cabi.gp_fbs_solve_batch(h, S, ld, spu_d.data_ptr(), V.data_ptr(), I.data_ptr(),
+                                                     iters.data_ptr(), status.data_ptr(), diff.data_ptr(),
+                                                     tol, maxiter, stream.cuda_stream))
 
         def post_kernel():
-            _cabi.check(_cabi.gp_fbs_post(h, S, ld, spu_d.data_ptr(), V.data_ptr(), I.data_ptr(), None,
-                                          Vmag.data_ptr(), None, None, loss.data_ptr(), stream.cuda_stream))
+            if not fused:
+                _cabi.check(_cabi.gp_fbs_post(h, S, ld, spu_d.data_ptr(), V.data_ptr(), I.data_ptr(), None,
+                                              Vmag.data_ptr(), None, None, loss.data_ptr(), stream.cuda_stream))
     else:
         X = torch.empty((t.n_vrows + t.n_irows, ld), dtype=c128, device=dev)
         wbytes = int(_cabi.gp_nr3_workspace_bytes(h, ld))

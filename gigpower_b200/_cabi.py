@@ -79,6 +79,8 @@ gp_fbs_create = _sig('gp_fbs_create', C.c_int, [C.POINTER(GpFbsDesc), C.c_int, C
 gp_feeder_destroy = _sig('gp_feeder_destroy', C.c_int, [vp])
 gp_fbs_solve_batch = _sig('gp_fbs_solve_batch', C.c_int,
                           [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_double, C.c_int32, vp])
+gp_fbs_solve_post_batch = _sig('gp_fbs_solve_post_batch', C.c_int,
+                               [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_int32, vp])
 gp_fbs_post = _sig('gp_fbs_post', C.c_int,
                    [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp])
 gp_fbs_solve_batch_host = _sig('gp_fbs_solve_batch_host', C.c_int,
@@ -95,7 +97,7 @@ gp_nr3_map_output = _sig('gp_nr3_map_output', C.c_int,
 EXPORTS = ['gp_version', 'gp_last_error', 'gp_launch_count', 'gp_set_option', 'gp_fbs_active_kernel',
            'gp_fbs_onchip_warps', 'gp_measure_fp64_peak', 'gp_fbs_specialise', 'gp_fbs_jit_source',
            'gp_jit_compile', 'gp_fbs_create', 'gp_feeder_destroy',
-           'gp_fbs_solve_batch', 'gp_fbs_post', 'gp_fbs_solve_batch_host', 'gp_nr3_create',
+           'gp_fbs_solve_batch', 'gp_fbs_solve_post_batch', 'gp_fbs_post', 'gp_fbs_solve_batch_host', 'gp_nr3_create',
            'gp_nr3_workspace_bytes', 'gp_nr3_solve_batch', 'gp_nr3_map_output']
 
 

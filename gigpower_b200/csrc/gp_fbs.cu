@@ -1116,7 +1116,14 @@ extern "C" int64_t gp_fbs_jit_source(const GpFbsDesc* d, int32_t warps, char* bu
     FbsConst k;
     int rc = fbs_tables_from_desc(d, steps, child4, k, vrow_srow, vrow_cap);
     if (rc) return rc;
-    const std::string src = fbs_jit_source(steps, child4, k, d->n_vrows, d->n_irows, d->n_srows, warps);
+    std::vector<int> lines((size_t)std::max(d->n_lines, 0) * 9);
+    for (int l = 0; l < d->n_lines; ++l)
+        for (int p = 0; p < 3; ++p) {
+            lines[9 * l + p] = d->line_irow[3 * l + p];
+            lines[9 * l + 3 + p] = d->line_tx_vrow[3 * l + p];
+            lines[9 * l + 6 + p] = d->line_rx_vrow[3 * l + p];
+        }
+    const std::string src = fbs_jit_source(steps, child4, lines, k, d->n_vrows, d->n_irows, d->n_srows, warps);
     if (src.empty()) return fail(GP_EJIT, "gp_fbs_jit_source: non-finite impedance in the descriptor");
     if (buf && cap > 0) {
         const size_t n = std::min((size_t)cap - 1, src.size());
@@ -1173,8 +1180,8 @@ extern "C" int gp_fbs_specialise(GpFeeder* f) {
     if (im->onchip_warps < 1) return fail(GP_EJIT, "gp_fbs_specialise: the feeder does not fit the on-chip kernel");
     GP_CUDA(cudaSetDevice(f->device));
     GP_CUDA(cudaFree(0));       // make sure the primary context exists and is current
-    const std::string src = fbs_jit_source(im->h_steps, im->h_child, im->k, im->n_vrows, im->n_irows, im->n_srows,
-                                           im->onchip_warps);
+    const std::string src = fbs_jit_source(im->h_steps, im->h_child, im->h_lines, im->k, im->n_vrows, im->n_irows,
+                                           im->n_srows, im->onchip_warps);
     if (src.empty()) return fail(GP_EJIT, "gp_fbs_specialise: non-finite impedance");
     std::vector<char> bin;
     std::string log;
@@ -1227,6 +1234,7 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
             lines[9 * l + 3 + p] = d->line_tx_vrow[3 * l + p];
             lines[9 * l + 6 + p] = d->line_rx_vrow[3 * l + p];
         }
+    im->h_lines = lines;
     // depth-first schedule for fbs_dfs_kernel: parent step of every step, children visited
     // latest-in-topo-order first, {step, 2*level + ascend} events.
     std::vector<int2> events;
@@ -1379,9 +1387,11 @@ static int fbs_check(GpFeeder* f, int64_t S, int64_t ld, const char* who) {
     return GP_OK;
 }
 
-extern "C" int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const double* spu,
-                                  double* V, double* I, int32_t* iters, int32_t* status,
-                                  double* diff, double tol, int32_t maxiter, void* stream) {
+// Launch the solve kernel; *fused is set when the kernel also produced Vmag / loss.
+static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* spu, double* V, double* I,
+                            int32_t* iters, int32_t* status, double* diff, double tol, int32_t maxiter,
+                            void* stream, double* Vmag, double* loss, bool* fused) {
+    *fused = false;
     int rc = fbs_check(f, S, ld, "gp_fbs_solve_batch");
     if (rc) return rc;
     if (S == 0) return GP_OK;
@@ -1399,7 +1409,8 @@ extern "C" int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
     // automatic choice: the on-chip kernel needs at least 4 resident warps per SM to keep the FP64
     // pipe busy; larger feeders stream their state through HBM with the two-sweep kernel
     const bool onchip = g_fbs_kernel == 4 || (g_fbs_kernel == 0 && im->onchip_warps >= 4);
-    if (g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) {
+    // (the specialised kernel always runs at least one sweep: maxiter < 1 goes to the table-driven ones)
+    if ((g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) && (maxiter >= 1 || !im->jit_kernel)) {
         if (!im->jit_kernel)
             return fail(GP_EINVAL, "gp_fbs_solve_batch: fbs_kernel = 5 needs a successful gp_fbs_specialise");
         const long long n_tiles = (S + 31) / 32;
@@ -1412,7 +1423,9 @@ extern "C" int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
         int maxiter_arg = maxiter;
         unsigned ldb_arg = ldb;
         void* args[] = {(void*)&spu, (void*)&V, (void*)&I, (void*)&iters, (void*)&status, (void*)&diff,
-                        (void*)&S_arg, (void*)&ldb_arg, (void*)&tol_arg, (void*)&maxiter_arg, (void*)&im->d_sched};
+                        (void*)&S_arg, (void*)&ldb_arg, (void*)&tol_arg, (void*)&maxiter_arg, (void*)&im->d_sched,
+                        (void*)&Vmag, (void*)&loss};
+        *fused = true;
         const int cr = driver().LaunchKernel(im->jit_kernel, (unsigned)blocks, 1, 1, (unsigned)nw * 32, 1, 1, smem,
                                              (void*)st, args, nullptr);
         if (cr != 0) return fail(GP_ECUDA, "gp_fbs_solve_batch: cuLaunchKernel failed (%d)", cr);
@@ -1467,6 +1480,26 @@ extern "C" int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
     count_launch();
     GP_CUDA(cudaGetLastError());
     return GP_OK;
+}
+
+extern "C" int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const double* spu,
+                                  double* V, double* I, int32_t* iters, int32_t* status,
+                                  double* diff, double tol, int32_t maxiter, void* stream) {
+    bool fused;
+    return fbs_solve_launch(f, S, ld, spu, V, I, iters, status, diff, tol, maxiter, stream, nullptr, nullptr, &fused);
+}
+
+extern "C" int gp_fbs_post(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const double* V,
+                           const double* I, double* sV, double* Vmag, double* Stx, double* Srx,
+                           double* loss, void* stream);
+
+extern "C" int gp_fbs_solve_post_batch(GpFeeder* f, int64_t S, int64_t ld, const double* spu, double* V, double* I,
+                                       int32_t* iters, int32_t* status, double* diff, double* Vmag, double* loss,
+                                       double tol, int32_t maxiter, void* stream) {
+    bool fused;
+    int rc = fbs_solve_launch(f, S, ld, spu, V, I, iters, status, diff, tol, maxiter, stream, Vmag, loss, &fused);
+    if (rc || fused || S == 0 || (!Vmag && !loss)) return rc;
+    return gp_fbs_post(f, S, ld, spu, V, I, nullptr, Vmag, nullptr, nullptr, loss, stream);
 }
 
 extern "C" int gp_fbs_post(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const double* V,
@@ -1571,13 +1604,9 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
         if (im->n_srows > 0)
             GP_CUDA(copy_rows(d_spu, (size_t)C * 16, spu_h + 2 * s0, (size_t)ld * 16, (size_t)n * 16,
                               im->n_srows, cudaMemcpyHostToDevice, st));
-        rc = gp_fbs_solve_batch(f, n, C, d_spu, d_V, d_I, d_it, d_st, d_diff, tol, maxiter, st);
+        rc = gp_fbs_solve_post_batch(f, n, C, d_spu, d_V, d_I, d_it, d_st, d_diff, Vmag_h ? d_mag : nullptr,
+                                     loss_h ? d_loss : nullptr, tol, maxiter, st);
         if (rc) return rc;
-        if (Vmag_h || loss_h) {
-            rc = gp_fbs_post(f, n, C, d_spu, d_V, d_I, nullptr, Vmag_h ? d_mag : nullptr, nullptr, nullptr,
-                             loss_h ? d_loss : nullptr, st);
-            if (rc) return rc;
-        }
         if (V_h)
             GP_CUDA(copy_rows(V_h + 2 * s0, (size_t)ld * 16, d_V, (size_t)C * 16, (size_t)n * 16,
                               im->n_vrows, cudaMemcpyDeviceToHost, st));

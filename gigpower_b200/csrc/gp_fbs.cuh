@@ -55,6 +55,7 @@ struct FbsImpl {
     // generator reads, the loaded module and its kernel
     std::vector<FbsStep> h_steps;
     std::vector<int4> h_child;
+    std::vector<int> h_lines;     // [n_lines][9] irow, tx vrow, rx vrow
     void* jit_module = nullptr;   // CUmodule
     void* jit_kernel = nullptr;   // CUfunction
     int jit_warps = 0;
@@ -67,8 +68,9 @@ struct FbsImpl {
 
 
 // gp_fbs_jit.cu: CUDA source of the feeder-specialised on-chip kernel, NVRTC compilation
-std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<int4>& child, const FbsConst& k,
-                           int n_vrows, int n_irows, int n_srows, int nw);
+std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<int4>& child,
+                           const std::vector<int>& lines, const FbsConst& k, int n_vrows, int n_irows, int n_srows,
+                           int nw);
 int jit_compile(const std::string& src, std::vector<char>& cubin, std::string& log);
 
 }  // namespace gp

@@ -208,9 +208,6 @@ class SolutionFBS(Solution):
                 iters = torch.empty(S, dtype=torch.int32, device=dev)
                 status = torch.empty(S, dtype=torch.int32, device=dev)
                 diff = torch.empty(S, dtype=torch.float64, device=dev)
-                _cabi.check(_cabi.gp_fbs_solve_batch(
-                    self._feeder.handle, S, ld, d_spu.data_ptr(), V.data_ptr(), I.data_ptr(),
-                    iters.data_ptr(), status.data_ptr(), diff.data_ptr(), tol, maxiter, st.cuda_stream))
                 want = set(outputs)
                 mk = lambda rows, dt: torch.empty((max(rows, 1), ld), dtype=dt, device=dev)
                 sV = mk(t.n_vrows, torch.complex128) if 'sV' in want else None
@@ -218,11 +215,16 @@ class SolutionFBS(Solution):
                 Stx = torch.zeros((max(t.n_irows, 1), ld), dtype=torch.complex128, device=dev) if 'Stx' in want else None
                 Srx = torch.zeros((max(t.n_irows, 1), ld), dtype=torch.complex128, device=dev) if 'Srx' in want else None
                 loss = torch.empty(S, dtype=torch.complex128, device=dev) if 'loss' in want else None
-                if want & {'sV', 'Vmag', 'Stx', 'Srx', 'loss'}:
-                    p = lambda x: x.data_ptr() if x is not None else None
+                p = lambda x: x.data_ptr() if x is not None else None
+                # solve + |V| + loss in one call (one launch with the feeder-specialised kernel)
+                _cabi.check(_cabi.gp_fbs_solve_post_batch(
+                    self._feeder.handle, S, ld, d_spu.data_ptr(), V.data_ptr(), I.data_ptr(),
+                    iters.data_ptr(), status.data_ptr(), diff.data_ptr(), p(Vmag), p(loss), tol, maxiter,
+                    st.cuda_stream))
+                if want & {'sV', 'Stx', 'Srx'}:
                     _cabi.check(_cabi.gp_fbs_post(
                         self._feeder.handle, S, ld, d_spu.data_ptr(), V.data_ptr(), I.data_ptr(),
-                        p(sV), p(Vmag), p(Stx), p(Srx), p(loss), st.cuda_stream))
+                        p(sV), None, p(Stx), p(Srx), None, st.cuda_stream))
         res = BatchResult(tables=t, S=S, iterations=iters, status=status, convergence_diff=diff,
                           V_rows=V if 'V' in want else None, I_rows=I if 'I' in want else None,
                           Vmag_rows=Vmag, loss=loss, sV_rows=sV, Stx_rows=Stx, Srx_rows=Srx)

@@ -177,6 +177,16 @@ int gp_fbs_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const double* spu_dev
                        int32_t maxiter, void* stream);
 
 /*
+ * gp_fbs_solve_batch followed by the |V| and loss part of gp_fbs_post (either output may be
+ * NULL) as ONE call: the feeder-specialised kernel writes both while the state is still on chip
+ * (one launch); the other kernels run the solve and then the post kernels.  Same results.
+ *   Vmag_dev [n_vrows][ld] double, loss_dev [S] complex
+ */
+int gp_fbs_solve_post_batch(GpFeeder* f, int64_t S, int64_t ld, const double* spu_dev, double* V_dev,
+                            double* I_dev, int32_t* iters_dev, int32_t* status_dev, double* diff_dev,
+                            double* Vmag_dev, double* loss_dev, double tol, int32_t maxiter, void* stream);
+
+/*
  * Derived results of solved scenarios; replaces the tail of SolutionFBS.solve()
  * (solution_fbs.py:130-135; solution.py:177-233).  Any output pointer may be NULL.
  *

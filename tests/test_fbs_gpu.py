@@ -224,10 +224,14 @@ def test_onchip_kernel_full_batch_and_relaunch():
         # the batch above was large enough to compile the feeder-specialised kernel: automatic = 5 now
         _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 0))
         assert s._specialised and _cabi.gp_fbs_active_kernel(s._feeder.handle) == 5
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 3))
+        ref2 = s.solve_batch(load_mult=mult, outputs=('Vmag', 'loss'))
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 0))
         for _ in range(2):
-            r = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
+            r = s.solve_batch(load_mult=mult, outputs=('V', 'I', 'Vmag', 'loss'))   # |V|, loss fused in the kernel
             assert np.array_equal(r.iterations, ref.iterations) and np.array_equal(r.status, ref.status)
             assert rel_err(r.V, ref.V) <= 1e-13 and rel_err(r.I, ref.I) <= 1e-13
+            assert rel_err(r.Vmag, ref2.Vmag) <= 1e-13 and rel_err(r.losses, ref2.losses) <= 1e-13
         for S2 in (1, 31, 33, 4097):
             r = s.solve_batch(load_mult=mult[:S2], outputs=('V',))
             assert rel_err(r.V, ref.V[:S2]) <= 1e-13 and np.array_equal(r.iterations, ref.iterations[:S2])
