@@ -308,6 +308,8 @@ def run_ours(args, wl):
     rows, mult = make_scenarios(sol, S, seed + 1000 * rank, spec, first=rank * S)
     sol._dev()
     _cabi.check(_cabi.gp_set_option(b'fbs_kernel', args.fbs_kernel))
+    if args.prefetch is not None:
+        _cabi.check(_cabi.gp_set_option(b'fbs_prefetch', args.prefetch))
     t = sol.tables
     h = sol._feeder.handle
     if solver == 'fbs' and args.fbs_kernel in (0, 5) and _cabi.gp_fbs_onchip_warps(h) >= 4:
@@ -548,6 +550,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--prefetch', type=int, default=None, help='L2 prefetch distance of the streaming FBS kernel')
     ap.add_argument('--fbs-kernel', type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
                     help='0 = automatic (on-chip when the feeder fits in shared memory, else two-sweep streaming), '
                          '1 = fused depth-first, 2 = phase-parallel lanes, 3 = two-sweep streaming, 4 = on-chip table-driven, '

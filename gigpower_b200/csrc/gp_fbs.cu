@@ -30,6 +30,10 @@ static int g_host_chunks = 0;  // gp_set_option("host_chunks", n): 0 = automatic
 // depth-first, 2 phase-parallel, 3 two-sweep streaming, 4 on-chip (error if the feeder does not fit),
 // 5 feeder-specialised on-chip kernel (error unless gp_fbs_specialise succeeded)
 static int g_fbs_kernel = 0;
+// gp_set_option("fbs_prefetch", d): L2 prefetch distance of the streaming kernel in steps.  Measured on
+// B200 (C4, C5, C2): every distance > 0 is 2-8 % SLOWER than none - the kernel is bound by DRAM
+// throughput on 512-byte row pieces, not by exposed latency - so the default is off.
+static int g_fbs_prefetch = 0;
 
 // |v| as numpy computes it for the ZIP model (abs then square, solution.py:202)
 __device__ __forceinline__ double cabs2(double2 v, double& a) {
@@ -55,6 +59,11 @@ struct GMem {
     __device__ __forceinline__ double2 ldS(int r) const { return __ldcg(reinterpret_cast<const double2*>(S + (size_t)(unsigned)r * (size_t)ldb)); }
     __device__ __forceinline__ void stV(int r, double2 v) const { *reinterpret_cast<double2*>(V + (size_t)(unsigned)r * (size_t)ldb) = v; }
     __device__ __forceinline__ void stI(int r, double2 v) const { *reinterpret_cast<double2*>(I + (size_t)(unsigned)r * (size_t)ldb) = v; }
+    // L2 prefetch of a row this thread will read a couple of steps from now (no register held)
+    static __device__ __forceinline__ void pf(const char* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+    __device__ __forceinline__ void pfV(int r) const { if (r >= 0) pf(V + (size_t)(unsigned)r * (size_t)ldb); }
+    __device__ __forceinline__ void pfI(int r) const { if (r >= 0) pf(I + (size_t)(unsigned)r * (size_t)ldb); }
+    __device__ __forceinline__ void pfS(int r) const { if (r >= 0) pf(S + (size_t)(unsigned)r * (size_t)ldb); }
 };
 
 struct SMem {
@@ -74,7 +83,9 @@ struct SMem {
 // For those steps (FbsStep fast mask M != 0) the phase pattern is a compile-time constant: no
 // row tests, no predicated arithmetic, straight-line FP64.  The branch on M is uniform (every
 // thread walks the same feeder).  Everything else takes the general body.
-template <int M, class Mem>
+// FIRST = the forward sweep of iteration 0: the currents are the flat start's zeros and are not read
+// (V - Z 0 is computed all the same, so the values are those of the generic path bit for bit).
+template <int M, class Mem, bool FIRST>
 __device__ __forceinline__ void fwd_fast(const FbsStep* __restrict__ st, const int4 bv, const int4 pv, const Mem& m) {
     const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
     const int brow[3] = {bv.x, bv.y, bv.z}, prow[3] = {pv.x, pv.y, pv.z}, erow[3] = {ev.x, ev.y, ev.z};
@@ -83,7 +94,7 @@ __device__ __forceinline__ void fwd_fast(const FbsStep* __restrict__ st, const i
     for (int p = 0; p < 3; ++p)
         if ((M >> p) & 1) {
             Vp[p] = m.ldV(prow[p]);
-            Il[p] = m.ldI(erow[p]);
+            Il[p] = FIRST ? make_double2(0.0, 0.0) : m.ldI(erow[p]);
         }
 #pragma unroll
     for (int p = 0; p < 3; ++p)
@@ -100,7 +111,7 @@ __device__ __forceinline__ void fwd_fast(const FbsStep* __restrict__ st, const i
         }
 }
 
-template <int M, class Mem>
+template <int M, class Mem, bool UNUSED>
 __device__ __forceinline__ void bwd_fast(const FbsStep* __restrict__ st, const int4 bv, const int4 pv,
                                          const int4* __restrict__ child_irow, const FbsConst& k, const Mem& m,
                                          const double2 (&sp)[3]) {
@@ -165,26 +176,26 @@ __device__ __forceinline__ void bwd_fast(const FbsStep* __restrict__ st, const i
         }
 }
 
-#define GP_FAST_SWITCH(fn, ...)                 \
-    switch (fast) {                             \
-        case 7: fn<7>(__VA_ARGS__); return;     \
-        case 1: fn<1>(__VA_ARGS__); return;     \
-        case 2: fn<2>(__VA_ARGS__); return;     \
-        case 4: fn<4>(__VA_ARGS__); return;     \
-        case 3: fn<3>(__VA_ARGS__); return;     \
-        case 5: fn<5>(__VA_ARGS__); return;     \
-        case 6: fn<6>(__VA_ARGS__); return;     \
-        default: break;                         \
+#define GP_FAST_SWITCH(fn, X, ...)                 \
+    switch (fast) {                                \
+        case 7: fn<7, Mem, X>(__VA_ARGS__); return; \
+        case 1: fn<1, Mem, X>(__VA_ARGS__); return; \
+        case 2: fn<2, Mem, X>(__VA_ARGS__); return; \
+        case 4: fn<4, Mem, X>(__VA_ARGS__); return; \
+        case 3: fn<3, Mem, X>(__VA_ARGS__); return; \
+        case 5: fn<5, Mem, X>(__VA_ARGS__); return; \
+        case 6: fn<6, Mem, X>(__VA_ARGS__); return; \
+        default: break;                            \
     }
 
 // forward step of one bus: update_voltage_forward :162-184 / vr_forward :138-160
-template <class Mem>
+template <class Mem, bool FIRST = false>
 __device__ __forceinline__ void fbs_fwd_step(const FbsStep* __restrict__ st, const Mem& m) {
     const double2 zero = make_double2(0.0, 0.0);
     const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
     const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
     const int kind = bv.w & 0xff, fast = bv.w >> 8;
-    GP_FAST_SWITCH(fwd_fast, st, bv, pv, m)
+    GP_FAST_SWITCH(fwd_fast, FIRST, st, bv, pv, m)
     const int brow[3] = {bv.x, bv.y, bv.z};
     const int prow[3] = {pv.x, pv.y, pv.z};
     double2 Vp[3];
@@ -202,7 +213,7 @@ __device__ __forceinline__ void fbs_fwd_step(const FbsStep* __restrict__ st, con
     const int erow[3] = {ev.x, ev.y, ev.z};
     double2 Il[3];
 #pragma unroll
-    for (int p = 0; p < 3; ++p) Il[p] = erow[p] >= 0 ? m.ldI(erow[p]) : zero;
+    for (int p = 0; p < 3; ++p) Il[p] = (!FIRST && erow[p] >= 0) ? m.ldI(erow[p]) : zero;
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
         if (brow[p] < 0) continue;
@@ -235,7 +246,7 @@ __device__ __forceinline__ void fbs_bwd_step(const FbsStep* __restrict__ st, con
     const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
     const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
     const int kind = bv.w & 0xff, fast = bv.w >> 8;
-    GP_FAST_SWITCH(bwd_fast, st, bv, pv, child_irow, k, m, sp)
+    GP_FAST_SWITCH(bwd_fast, false, st, bv, pv, child_irow, k, m, sp)
     const int brow[3] = {bv.x, bv.y, bv.z};
     const int prow[3] = {pv.x, pv.y, pv.z};
     const int child_begin = pv.w;
@@ -339,26 +350,54 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
                  const char* __restrict__ spu, char* __restrict__ V,
                  char* __restrict__ I, int* __restrict__ iters_out,
                  int* __restrict__ status_out, double* __restrict__ diff_out, double tol,
-                 int maxiter) {
+                 int maxiter, int PF, const int* __restrict__ unfed, int n_unfed) {
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (s >= S) return;
     const GMem m{V + s * 16, I + s * 16, spu + s * 16, ldb};
     const double2 zero = make_double2(0.0, 0.0);
 
-    // flat start (solution.py:108-125): V = I = 0.  I is read by the first forward
-    // sweep and V rows that no edge feeds (non-regulated phases below a regulator)
-    // keep their initial value, so both are zeroed here, coalesced, once.
-    for (int r = 0; r < n_vrows; ++r) m.stV(r, zero);
-    for (int r = 0; r < n_irows; ++r) m.stI(r, zero);
+    // flat start (solution.py:108-125): V = I = 0.  Every I row is written by the first backward
+    // sweep before anything reads it again, and the first forward sweep knows I = 0 without
+    // reading it; only V rows that no forward step writes (non-regulated phases below a
+    // regulator) must hold their initial zero.  Zeroing just those saves one write of every
+    // V and I row and one read of every I row per solve.
+    for (int j = 0; j < n_unfed; ++j) m.stV(__ldg(unfed + j), zero);
+    if (maxiter < 1) {          // no sweep at all: the outputs are the flat start itself
+        for (int r = 0; r < n_vrows; ++r) m.stV(r, zero);
+        for (int r = 0; r < n_irows; ++r) m.stI(r, zero);
+    }
     int it = 0;
     double diff = -1.0;
     bool converged = false;   // Vtest = 0 -> max|0 - Vref| = 1 > tol (solution_fbs.py:85)
+    // The rows a step reads that were last written a whole sweep ago (the I rows of its edge in
+    // the forward sweep, the V and spu rows of its bus in the backward sweep) come from DRAM.
+    // Their addresses depend only on the step table, so they are prefetched into L2 PF steps
+    // ahead: the dependent part of a step then waits for an L2 hit instead of a DRAM access.
 
     while (!converged && it < maxiter) {
 #pragma unroll
         for (int p = 0; p < 3; ++p) m.stV(k.root_vrow[p], k.vref[p]);      // V[root] = Vref  (:89)
-        for (int pos = 0; pos < n_steps; ++pos) fbs_fwd_step(steps + pos, m);          // :92-98
+        for (int pos = 0; pos < n_steps; ++pos) {                                      // :92-98
+            if (PF > 0 && pos + PF < n_steps) {
+                const int4 ev = __ldg(reinterpret_cast<const int4*>(steps[pos + PF].edge_irow));
+                m.pfI(ev.x);
+                m.pfI(ev.y);
+                m.pfI(ev.z);
+            }
+            if (it == 0) fbs_fwd_step<GMem, true>(steps + pos, m);
+            else fbs_fwd_step<GMem, false>(steps + pos, m);
+        }
         for (int pos = n_steps - 1; pos >= 0; --pos) {                                 // :104-121
+            if (PF > 0 && pos >= PF) {
+                const int4 bv = __ldg(reinterpret_cast<const int4*>(steps[pos - PF].bus_vrow));
+                const int4 lv = __ldg(reinterpret_cast<const int4*>(steps[pos - PF].load_srow));
+                m.pfV(bv.x);
+                m.pfV(bv.y);
+                m.pfV(bv.z);
+                m.pfS(lv.x);
+                m.pfS(lv.y);
+                m.pfS(lv.z);
+            }
             double2 sp[3];
             fbs_load_spu(steps + pos, m, sp);
             fbs_bwd_step(steps + pos, child_irow, k, m, sp);
@@ -965,6 +1004,10 @@ extern "C" int gp_set_option(const char* name, int value) {
         g_fbs_kernel = value;
         return GP_OK;
     }
+    if (name && strcmp(name, "fbs_prefetch") == 0 && value >= 0 && value <= 64) {
+        g_fbs_prefetch = value;
+        return GP_OK;
+    }
     if (name && strcmp(name, "host_chunks") == 0 && value >= 0 && value <= 64) {
         g_host_chunks = value;
         return GP_OK;
@@ -1328,6 +1371,18 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
     if (e == cudaSuccess) e = up((void**)&im->d_lines, lines.data(), lines.size() * sizeof(int));
     if (e == cudaSuccess) e = up((void**)&im->d_vrow_srow, vrow_srow.data(), vrow_srow.size() * sizeof(int));
     if (e == cudaSuccess) e = up((void**)&im->d_vrow_cap, vrow_cap.data(), vrow_cap.size() * sizeof(double));
+    {   // V rows that no forward step writes: they must hold the flat start's zero
+        std::vector<char> fed((size_t)d->n_vrows, 0);
+        for (int p = 0; p < 3; ++p) fed[d->root_vrow[p]] = 1;
+        for (const FbsStep& st : steps)
+            for (int p = 0; p < 3; ++p)
+                if (st.bus_vrow[p] >= 0 && ((st.kind & 0xff) != GP_EDGE_VR || st.gamma[p] != 0.0)) fed[st.bus_vrow[p]] = 1;
+        std::vector<int> unfed;
+        for (int r = 0; r < d->n_vrows; ++r)
+            if (!fed[r]) unfed.push_back(r);
+        im->n_unfed = (int)unfed.size();
+        if (e == cudaSuccess) e = up((void**)&im->d_unfed, unfed.data(), unfed.size() * sizeof(int));
+    }
     if (e == cudaSuccess) e = cudaMalloc((void**)&im->d_sched, 16);
     if (e == cudaSuccess) e = cudaMemset(im->d_sched, 0, 16);
     int smem_optin = 0;
@@ -1368,6 +1423,7 @@ extern "C" int gp_feeder_destroy(GpFeeder* f) {
         cudaFree(im->d_events);
         cudaFree(im->d_evrows);
         cudaFree(im->d_sched);
+        cudaFree(im->d_unfed);
         if (im->jit_module) driver().ModuleUnload(im->jit_module);
         for (int i = 0; i < FbsImpl::NSTREAM; ++i) {
             if (im->d_stage[i]) cudaFree(im->d_stage[i]);
@@ -1475,7 +1531,8 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     } else {
         fbs_solve_kernel<BLOCK><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
                                                       im->n_irows, S, ldb, (const char*)spu, (char*)V,
-                                                      (char*)I, iters, status, diff, tol, maxiter);
+                                                      (char*)I, iters, status, diff, tol, maxiter, g_fbs_prefetch,
+                                                      im->d_unfed, im->n_unfed);
     }
     count_launch();
     GP_CUDA(cudaGetLastError());

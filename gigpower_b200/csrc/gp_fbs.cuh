@@ -49,6 +49,8 @@ struct FbsImpl {
     int n_events = 0, depth = 0;
     // on-chip kernel (fbs_onchip_kernel): tile scheduler words {next tile, warps done}, SM count,
     // warps per block that fit the feeder's V and I rows in shared memory (0 = does not fit)
+    int* d_unfed = nullptr;       // V rows no forward step writes (kept at the flat start's zero)
+    int n_unfed = 0;
     unsigned* d_sched = nullptr;
     int n_sm = 0, onchip_warps = 0;
     // feeder-specialised on-chip kernel (gp_fbs_specialise): host copies of the tables the
