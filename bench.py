@@ -230,10 +230,12 @@ class CpuPool:
 
 
 def cpu_sample_size(solver, nb):
-    """Scenarios per core per step, sized so that a step of the port takes ~0.2-2 s."""
+    """Scenarios per core per step, sized so that a step of the port takes ~0.2-10 s.  NR3 up to
+    45 buses runs the literal dense restatement of the reference (H tensors of 0.4 GB and ~5 s per
+    solve at 37 buses, like the reference itself): one scenario per core per step."""
     if solver == 'fbs':
         return max(16, min(1024, 15 * 1024 // nb))
-    return 4 if nb <= 45 else max(2, min(64, 126 * 64 // nb))
+    return 1 if nb <= 45 else max(2, min(64, 126 * 64 // nb))
 
 
 def run_reference(args, wl):
@@ -257,14 +259,15 @@ def run_reference(args, wl):
     pool = CpuPool()
     cores = pool.cores
     n_per = cpu_sample_size(solver, nb)
-    for _ in range(max(args.warmup, 1)):
+    slow = solver == 'nr3' and n_per == 1           # dense NR3 restatement: seconds per solve
+    for _ in range(1 if slow else max(args.warmup, 1)):
         pool.step(feeder, solver, rows, max(n_per // 8, 1))
     t0 = time.perf_counter()
     tot, done = 0, 0
     for _ in range(args.steps):
         n, _w = pool.step(feeder, solver, rows, n_per)
         tot, done = tot + n, done + 1
-        if time.perf_counter() - t0 > 150.0:      # keep the whole arm within a few minutes
+        if time.perf_counter() - t0 > (60.0 if slow else 150.0):      # keep the whole arm within a few minutes
             break
     wall = time.perf_counter() - t0
     pool.close()
@@ -309,7 +312,7 @@ def run_ours(args, wl):
     sol._dev()
     _cabi.check(_cabi.gp_set_option(b'fbs_kernel', args.fbs_kernel))
     if args.prefetch is not None:
-        _cabi.check(_cabi.gp_set_option(b'fbs_prefetch', args.prefetch))
+        _cabi.check(_cabi.gp_set_option(b'fbs_prefetch' if solver == 'fbs' else b'nr3_prefetch', args.prefetch))
     t = sol.tables
     h = sol._feeder.handle
     if solver == 'fbs' and args.fbs_kernel in (0, 5) and _cabi.gp_fbs_onchip_warps(h) >= 4:
@@ -527,7 +530,8 @@ def run_ours(args, wl):
         if world == 1 and not args.no_cpu:
             pool = CpuPool()
             n_per = cpu_sample_size(solver, sol.circuit.buses.num_elements)
-            pool.step(feeder, solver, rows, max(n_per // 8, 1))          # warm the workers
+            if not (solver == 'nr3' and n_per == 1):
+                pool.step(feeder, solver, rows, max(n_per // 8, 1))      # warm the workers
             n, wall, reps = 0, 0.0, 0
             while wall < 10.0 and reps < 50:
                 dn, dw = pool.step(feeder, solver, rows, n_per)
@@ -550,7 +554,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    ap.add_argument('--prefetch', type=int, default=None, help='L2 prefetch distance of the streaming FBS kernel')
+    ap.add_argument('--prefetch', type=int, default=None, help='L2 prefetch distance of the streaming FBS kernel / the NR3 kernel')
     ap.add_argument('--fbs-kernel', type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
                     help='0 = automatic (on-chip when the feeder fits in shared memory, else two-sweep streaming), '
                          '1 = fused depth-first, 2 = phase-parallel lanes, 3 = two-sweep streaming, 4 = on-chip table-driven, '

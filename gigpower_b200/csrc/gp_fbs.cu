@@ -25,6 +25,7 @@ namespace gp {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+extern int g_nr3_prefetch;     // gp_nr3.cu
 static int g_host_chunks = 0;  // gp_set_option("host_chunks", n): 0 = automatic
 // gp_set_option("fbs_kernel", v): 0 automatic (on-chip when the feeder fits, else two-sweep), 1 fused
 // depth-first, 2 phase-parallel, 3 two-sweep streaming, 4 on-chip (error if the feeder does not fit),
@@ -1006,6 +1007,10 @@ extern "C" int gp_set_option(const char* name, int value) {
     }
     if (name && strcmp(name, "fbs_prefetch") == 0 && value >= 0 && value <= 64) {
         g_fbs_prefetch = value;
+        return GP_OK;
+    }
+    if (name && strcmp(name, "nr3_prefetch") == 0 && value >= -1 && value <= 64) {
+        g_nr3_prefetch = value;
         return GP_OK;
     }
     if (name && strcmp(name, "host_chunks") == 0 && value >= 0 && value <= 64) {

@@ -97,13 +97,25 @@ __device__ __forceinline__ void lu6_solve(const double (&T)[6][6], double (&b)[6
     }
 }
 
+// Load that is never predicated or branched around: an absent row reads a hot dummy row instead
+// and the value is discarded.  With a branch (or a predicate the compiler turns into one) per
+// phase, each phase's loads were issued only after the previous phase's arithmetic - three
+// exposed memory round trips per step instead of one.  The asm keeps the compiler from
+// re-introducing the control flow; its memory clobber orders it after the thread's own stores.
+__device__ __forceinline__ double2 ld_sel(bool have, const double2* p, const double2* dummy) {
+    const double2* a = have ? p : dummy;
+    double2 t;
+    asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "l"(a) : "memory");
+    return have ? t : make_double2(0.0, 0.0);
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ childs, Nr3Const k,
                  int n_vrows, int n_irows, long long S, long long ld,
                  const double2* __restrict__ spu, double2* __restrict__ X,
                  double2* __restrict__ W, double2* __restrict__ DV, int* __restrict__ iters_out,
-                 int* __restrict__ status_out, double* __restrict__ fmax_out, int maxiter) {
+                 int* __restrict__ status_out, double* __restrict__ fmax_out, int maxiter, int PF) {
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (s >= S) return;
     const double2* spu_s = spu + s;
@@ -111,6 +123,14 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
     double2* Ws = W + s;
     double2* DVs = DV + s;
     const int n_steps = k.n_steps;
+    const double2* dummy = Xs + (long long)k.root_row[0] * ld;
+    // L2 prefetch of the rows a step reads that were written a sweep ago (X rows and loads in the
+    // backward sweep, the step's front and X rows in the forward sweep), PF steps ahead.  With
+    // about one warp per SM sub-partition (BASELINE config C3) every one of those loads is an
+    // exposed DRAM round trip otherwise.
+    auto pf = [&](const double2* base, int row) {
+        if (row >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (long long)row * ld));
+    };
 
     // flat start (solution_nr3.py:37-82): every bus-phase at VSLACK, currents 0.
     // Absent phases are not stored: their rows of J are identity rows whose first
@@ -137,6 +157,15 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
         fm = (it == 0) ? k.f0_absent : 0.0;
         // ================= backward sweep: residual, Jacobian blocks, elimination =========
         for (int pos = n_steps - 1; pos >= 0; --pos) {
+            if (PF > 0 && pos >= PF) {
+                const Nr3Step* sn = steps + (pos - PF);
+                const int4 b2 = __ldg(reinterpret_cast<const int4*>(sn->bus_row));
+                const int4 e2 = __ldg(reinterpret_cast<const int4*>(sn->edge_row));
+                const int4 l2 = __ldg(reinterpret_cast<const int4*>(sn->load_srow));
+                pf(Xs, b2.x); pf(Xs, b2.y); pf(Xs, b2.z);
+                pf(Xs, e2.x); pf(Xs, e2.y); pf(Xs, e2.z);
+                pf(spu_s, l2.x); pf(spu_s, l2.y); pf(spu_s, l2.z);
+            }
             const Nr3Step* st = steps + pos;
             const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_row));
             const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_row));
@@ -146,15 +175,18 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             const int erow[3] = {ev.x, ev.y, ev.z}, lrow[3] = {lv.x, lv.y, lv.z};
             const int child_count = bv.w, child_begin = pv.w, kind = ev.w, aux = lv.w;
             // every load of the step is issued before the first use (one exposed round trip, not one per phase)
+            // (each load is its own predicated instruction - no branch around a group of them - so that
+            // the scheduler can put all of them in flight together)
+            const double2 zz = make_double2(0.0, 0.0);
             double2 v[3], inet[3], r1[3], vpar[3], spl[3];
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
-                v[p] = inet[p] = r1[p] = vpar[p] = spl[p] = make_double2(0.0, 0.0);
-                if (brow[p] < 0) continue;
-                v[p] = Xs[(long long)brow[p] * ld];
-                inet[p] = Xs[(long long)erow[p] * ld];
-                if (prow[p] >= 0) vpar[p] = Xs[(long long)prow[p] * ld];
-                if (lrow[p] >= 0) spl[p] = spu_s[(long long)lrow[p] * ld];
+                const bool hb = brow[p] >= 0;
+                r1[p] = zz;
+                v[p] = ld_sel(hb, Xs + (long long)brow[p] * ld, dummy);
+                inet[p] = ld_sel(hb, Xs + (long long)erow[p] * ld, dummy);
+                vpar[p] = ld_sel(hb && prow[p] >= 0, Xs + (long long)prow[p] * ld, dummy);
+                spl[p] = ld_sel(hb && lrow[p] >= 0, spu_s + (long long)lrow[p] * ld, dummy);
             }
             if (kind == GP_EDGE_LINE) {
                 // KVL residual r1 = E v_p - v - Z i   (:141-158; transformers :165-175 with Z = 0)
@@ -192,17 +224,14 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                 double2 ic[3], ac[3], yc[6][3];
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {           // issue the child's whole front, then consume it
-                    ic[p] = ac[p] = make_double2(0.0, 0.0);
+                    const bool hp = crow[p] >= 0;
+                    ic[p] = ld_sel(hp, Xs + (long long)crow[p] * ld, dummy);
+                    ac[p] = ld_sel(hp, Wc + (long long)(18 + p) * ld, dummy);
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) yc[2 * p][q] = yc[2 * p + 1][q] = make_double2(0.0, 0.0);
-                    if (crow[p] < 0) continue;
-                    ic[p] = Xs[(long long)crow[p] * ld];
-                    ac[p] = Wc[(long long)(18 + p) * ld];
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        if (crow[q] < 0) continue;      // only the child's own phases were stored
-                        yc[2 * p][q] = Wc[(long long)((2 * p) * 3 + q) * ld];
-                        yc[2 * p + 1][q] = Wc[(long long)((2 * p + 1) * 3 + q) * ld];
+                    for (int q = 0; q < 3; ++q) {       // only the child's own phases were stored
+                        const bool hq = hp && crow[q] >= 0;
+                        yc[2 * p][q] = ld_sel(hq, Wc + (long long)((2 * p) * 3 + q) * ld, dummy);
+                        yc[2 * p + 1][q] = ld_sel(hq, Wc + (long long)((2 * p + 1) * 3 + q) * ld, dummy);
                     }
                 }
 #pragma unroll
@@ -366,6 +395,7 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             }
         }
         // ================= slack rows (:84-109) and forward sweep ================================
+        double2 dv_prev[3];
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
             const double2 v0 = Xs[(long long)k.root_row[p] * ld];
@@ -374,8 +404,34 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             fm = fmax(fm, fmax(fabs(d.x), fabs(d.y)));
             DVs[(long long)k.root_row[p] * ld] = d;
             Xs[(long long)k.root_row[p] * ld] = make_double2(v0.x - d.x, v0.y - d.y);
+            dv_prev[p] = d;
         }
+        // The forward sweep runs in reverse post-order: a bus is followed immediately by the child
+        // visited first, so on every chain the parent's dv is the one just computed: it is taken
+        // from registers (dv_prev, rows prev_row) instead of a store -> load round trip through L2.
+        int prev_row[3] = {k.root_row[0], k.root_row[1], k.root_row[2]};
         for (int pos = 0; pos < n_steps; ++pos) {
+            if (PF > 0 && pos + PF < n_steps) {
+                const Nr3Step* sn = steps + (pos + PF);
+                const int4 b2 = __ldg(reinterpret_cast<const int4*>(sn->bus_row));
+                const int4 e2 = __ldg(reinterpret_cast<const int4*>(sn->edge_row));
+                const int br2[3] = {b2.x, b2.y, b2.z};
+                pf(Xs, b2.x); pf(Xs, b2.y); pf(Xs, b2.z);
+                pf(Xs, e2.x); pf(Xs, e2.y); pf(Xs, e2.z);
+                const double2* Wn = Ws + (long long)(pos + PF) * FRONT_D2 * ld;
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    if (br2[p] < 0) continue;
+                    pf(Wn, 18 + p);
+                    pf(Wn, 21 + p);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                        if (br2[q] >= 0) {
+                            pf(Wn, (2 * p) * 3 + q);
+                            pf(Wn, (2 * p + 1) * 3 + q);
+                        }
+                }
+            }
             const Nr3Step* st = steps + pos;
             const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_row));
             const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_row));
@@ -384,23 +440,23 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             const int erow[3] = {ev.x, ev.y, ev.z};
             const int kind = ev.w;
             const double2* Wk = Ws + (long long)pos * FRONT_D2 * ld;
+            const double2 zz = make_double2(0.0, 0.0);
             double2 dvp[3], di[3], dv[3], yf[6][3], r1f[3], xv[3], xi[3];
 #pragma unroll
-            for (int p = 0; p < 3; ++p) {               // issue every load of the step first
-                dvp[p] = di[p] = r1f[p] = xv[p] = xi[p] = make_double2(0.0, 0.0);
-#pragma unroll
-                for (int q = 0; q < 3; ++q) yf[2 * p][q] = yf[2 * p + 1][q] = make_double2(0.0, 0.0);
-                if (brow[p] < 0) continue;
-                if (prow[p] >= 0) dvp[p] = DVs[(long long)prow[p] * ld];
-                di[p] = Wk[(long long)(18 + p) * ld];
-                r1f[p] = Wk[(long long)(21 + p) * ld];
-                xv[p] = Xs[(long long)brow[p] * ld];
-                xi[p] = Xs[(long long)erow[p] * ld];
+            for (int p = 0; p < 3; ++p) {               // issue every load of the step first (predicated, no branches)
+                const bool hb = brow[p] >= 0;
+                const bool hpar = hb && prow[p] >= 0, chain = prow[p] == prev_row[p];
+                const double2 dg = ld_sel(hpar && !chain, DVs + (long long)prow[p] * ld, dummy);
+                dvp[p] = (hpar && chain) ? dv_prev[p] : dg;
+                di[p] = ld_sel(hb, Wk + (long long)(18 + p) * ld, dummy);
+                r1f[p] = ld_sel(hb, Wk + (long long)(21 + p) * ld, dummy);
+                xv[p] = ld_sel(hb, Xs + (long long)brow[p] * ld, dummy);
+                xi[p] = ld_sel(hb, Xs + (long long)erow[p] * ld, dummy);
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
-                    if (brow[q] < 0) continue;
-                    yf[2 * p][q] = Wk[(long long)((2 * p) * 3 + q) * ld];
-                    yf[2 * p + 1][q] = Wk[(long long)((2 * p + 1) * 3 + q) * ld];
+                    const bool hq = hb && brow[q] >= 0;
+                    yf[2 * p][q] = ld_sel(hq, Wk + (long long)((2 * p) * 3 + q) * ld, dummy);
+                    yf[2 * p + 1][q] = ld_sel(hq, Wk + (long long)((2 * p + 1) * 3 + q) * ld, dummy);
                 }
             }
             // current leaving the parent: di = a - Y dv_p
@@ -443,6 +499,11 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                     Xs[(long long)orow[p] * ld] = make_double2(xo.x - di[p].x, xo.y - di[p].y);
                     DVs[(long long)brow[p] * ld] = dv[p];
                 }
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    prev_row[p] = brow[p];
+                    dv_prev[p] = dv[p];
+                }
                 continue;
             }
 #pragma unroll
@@ -459,6 +520,11 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                 Xs[(long long)brow[p] * ld] = make_double2(xv[p].x - dv[p].x, xv[p].y - dv[p].y);
                 Xs[(long long)erow[p] * ld] = make_double2(xi[p].x - di[p].x, xi[p].y - di[p].y);
                 DVs[(long long)brow[p] * ld] = dv[p];
+            }
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                prev_row[p] = brow[p];
+                dv_prev[p] = dv[p];
             }
         }
         ++it;
@@ -681,6 +747,15 @@ void gp_nr3_destroy_impl(void* impl) {
     delete im;
 }
 
+// gp_set_option("nr3_prefetch", d): -1 = automatic (on for batches that leave the SMs latency-bound)
+namespace gp {
+int g_nr3_prefetch = -1;
+}
+static int gp_nr3_prefetch_distance(int64_t S) {
+    if (g_nr3_prefetch >= 0) return g_nr3_prefetch;
+    return S <= 65536 ? 2 : 0;
+}
+
 static int nr3_check(GpFeeder* f, int64_t S, int64_t ld, const char* who) {
     if (!f || f->kind != 2) return fail(GP_EINVAL, "%s: not an NR3 feeder handle", who);
     if (S < 0 || ld < S) return fail(GP_EINVAL, "%s: need 0 <= S <= ld (S=%lld ld=%lld)", who, (long long)S, (long long)ld);
@@ -713,7 +788,7 @@ extern "C" int gp_nr3_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
     double2* DV = W + (size_t)im->n_fronts * FRONT_D2 * ld;
     nr3_solve_kernel<BLOCK><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_vrows, im->n_irows, S,
                                                   ld, (const double2*)spu, (double2*)X, W, DV, iters, status,
-                                                  fmax, maxiter);
+                                                  fmax, maxiter, gp_nr3_prefetch_distance(S));
     count_launch();
     GP_CUDA(cudaGetLastError());
     return GP_OK;
