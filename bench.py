@@ -315,7 +315,7 @@ def run_ours(args, wl):
         _cabi.check(_cabi.gp_set_option(b'fbs_prefetch' if solver == 'fbs' else b'nr3_prefetch', args.prefetch))
     t = sol.tables
     h = sol._feeder.handle
-    if solver == 'fbs' and args.fbs_kernel in (0, 5) and _cabi.gp_fbs_onchip_warps(h) >= 4:
+    if solver == 'fbs' and (args.fbs_kernel == 5 or (args.fbs_kernel == 0 and _cabi.gp_fbs_onchip_warps(h) >= sol.SPECIALISE_MIN_WARPS)):
         sol.specialise()        # what solve_batch does by itself for a batch this size
     active = int(_cabi.gp_fbs_active_kernel(h)) if solver == 'fbs' else 0
     ld = S

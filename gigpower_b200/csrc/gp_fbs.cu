@@ -27,7 +27,7 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 extern int g_nr3_prefetch;     // gp_nr3.cu
 static int g_host_chunks = 0;  // gp_set_option("host_chunks", n): 0 = automatic
-// gp_set_option("fbs_kernel", v): 0 automatic (on-chip when the feeder fits, else two-sweep), 1 fused
+// gp_set_option("fbs_kernel", v): 0 automatic (feeder-specialised on-chip kernel once built, else two-sweep), 1 fused
 // depth-first, 2 phase-parallel, 3 two-sweep streaming, 4 on-chip (error if the feeder does not fit),
 // 5 feeder-specialised on-chip kernel (error unless gp_fbs_specialise succeeded)
 static int g_fbs_kernel = 0;
@@ -1029,7 +1029,7 @@ extern "C" int gp_fbs_active_kernel(GpFeeder* f) {
     if (!f || f->kind != 1) return fail(GP_EINVAL, "gp_fbs_active_kernel: not an FBS feeder handle");
     const FbsImpl* im = (const FbsImpl*)f->impl;
     if (g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) return 5;
-    if (g_fbs_kernel == 4 || (g_fbs_kernel == 0 && im->onchip_warps >= 4)) return 4;
+    if (g_fbs_kernel == 4) return 4;
     if (g_fbs_kernel == 2) return 2;
     if (g_fbs_kernel == 1 && im->n_events > 0) return 1;
     return 3;
@@ -1467,9 +1467,11 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     const unsigned gx = (unsigned)((S + BLOCK - 1) / BLOCK);
     const bool dfs = im->n_events > 0 && g_fbs_kernel == 1;
     const unsigned ldb = (unsigned)(ld * 16);
-    // automatic choice: the on-chip kernel needs at least 4 resident warps per SM to keep the FP64
-    // pipe busy; larger feeders stream their state through HBM with the two-sweep kernel
-    const bool onchip = g_fbs_kernel == 4 || (g_fbs_kernel == 0 && im->onchip_warps >= 4);
+    // automatic choice: the feeder-specialised on-chip kernel when gp_fbs_specialise has built it,
+    // else the two-sweep kernel that streams the state through HBM.  (The table-driven on-chip
+    // kernel is slower than streaming on B200 - interpretation overhead with only a handful of
+    // warps per SM - and runs only on request.)
+    const bool onchip = g_fbs_kernel == 4;
     // (the specialised kernel always runs at least one sweep: maxiter < 1 goes to the table-driven ones)
     if ((g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) && (maxiter >= 1 || !im->jit_kernel)) {
         if (!im->jit_kernel)

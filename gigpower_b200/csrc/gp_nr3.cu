@@ -174,6 +174,96 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             const int brow[3] = {bv.x, bv.y, bv.z}, prow[3] = {pv.x, pv.y, pv.z};
             const int erow[3] = {ev.x, ev.y, ev.z}, lrow[3] = {lv.x, lv.y, lv.z};
             const int child_count = bv.w, child_begin = pv.w, kind = ev.w, aux = lv.w;
+            // ---- single-phase bus on a Line/Transformer edge (55 of the 125 steps of the IEEE-123
+            // feeder): the 6x6 system is the identity outside one 2x2 block, so the same elimination
+            // (same operations, same order on that block) runs on 2-vectors: 7 loads instead of 12-36,
+            // a 2x2 instead of a 6x6 LU and three instead of seven triangular solves.
+            const int nph = (bv.x >= 0) + (bv.y >= 0) + (bv.z >= 0);
+            if (nph == 1 && kind == GP_EDGE_LINE) {
+                const int p = bv.x >= 0 ? 0 : (bv.y >= 0 ? 1 : 2);
+                const int rb = p == 0 ? bv.x : (p == 1 ? bv.y : bv.z), re = p == 0 ? ev.x : (p == 1 ? ev.y : ev.z);
+                const int rp = p == 0 ? pv.x : (p == 1 ? pv.y : pv.z), rl = p == 0 ? lv.x : (p == 1 ? lv.y : lv.z);
+                const double2 v1 = ld_sel(true, Xs + (long long)rb * ld, dummy);
+                double2 in1 = ld_sel(true, Xs + (long long)re * ld, dummy);
+                const double2 vp1 = ld_sel(rp >= 0, Xs + (long long)rp * ld, dummy);
+                const double2 sp1 = ld_sel(rl >= 0, spu_s + (long long)rl * ld, dummy);
+                const double2 z = __ldg(&st->z[4 * p]);                 // Z[p][p]
+                const double cap = __ldg(&st->cap[p]);
+                double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0, ra = 0.0, rb2 = 0.0;     // Dt block, rt
+                // KVL residual (:141-158)
+                double2 r1s = make_double2(vp1.x - v1.x, vp1.y - v1.y);
+                r1s.x -= z.x * in1.x - z.y * in1.y;
+                r1s.y -= z.x * in1.y + z.y * in1.x;
+                nanflag |= (r1s.x != r1s.x) | (r1s.y != r1s.y);
+                fm = fmax(fm, fmax(fabs(r1s.x), fabs(r1s.y)));
+                for (int c = 0; c < child_count; ++c) {                 // children carry the same single phase
+                    const int4 ch = __ldg(childs + child_begin + c);
+                    const int cr = p == 0 ? ch.y : (p == 1 ? ch.z : ch.w);
+                    const double2* Wc = Ws + (long long)ch.x * FRONT_D2 * ld;
+                    const bool hc = cr >= 0;
+                    const double2 ic = ld_sel(hc, Xs + (long long)cr * ld, dummy);
+                    const double2 ac = ld_sel(hc, Wc + (long long)(18 + p) * ld, dummy);
+                    const double2 y0c = ld_sel(hc, Wc + (long long)((2 * p) * 3 + p) * ld, dummy);
+                    const double2 y1c = ld_sel(hc, Wc + (long long)((2 * p + 1) * 3 + p) * ld, dummy);
+                    in1.x -= ic.x;
+                    in1.y -= ic.y;
+                    ra += ac.x;
+                    rb2 += ac.y;
+                    d00 += y0c.x;
+                    d01 += y0c.y;
+                    d10 += y1c.x;
+                    d11 += y1c.y;
+                }
+                {   // KCL residual and D block (closed form of H, g, b; :226-299, 403-440)
+                    const double A = v1.x, B = v1.y, Cn = in1.x, Dn = in1.y;
+                    const double pl = sp1.x, ql = sp1.y;
+                    const double cA = p == 0 ? k.cA[0] : (p == 1 ? k.cA[1] : k.cA[2]);
+                    const double cB = p == 0 ? k.cB[0] : (p == 1 ? k.cB[1] : k.cB[2]);
+                    const double hAr = -pl * cA, hBr = -pl * cB, b0r = -pl * k.betaS;
+                    const double hAi = -ql * cA + cap * cA;
+                    const double hBi = -ql * cB + cap * cB;
+                    const double b0i = (-ql * k.betaS) + (cap * k.betaS);
+                    const double fr = A * Cn + B * Dn + hAr * A * A + hBr * B * B + b0r;
+                    const double fi = B * Cn - A * Dn + hAi * A * A + hBi * B * B + b0i;
+                    nanflag |= (fr != fr) | (fi != fi);
+                    fm = fmax(fm, fmax(fabs(fr), fabs(fi)));
+                    const double e00 = Cn + 2.0 * hAr * A, e01 = Dn + 2.0 * hBr * B;
+                    const double e10 = -Dn + 2.0 * hAi * A, e11 = Cn + 2.0 * hBi * B;
+                    const double inv = 1.0 / (A * A + B * B);
+                    d00 += (A * e00 + B * e10) * inv;
+                    d01 += (A * e01 + B * e11) * inv;
+                    d10 += (B * e00 - A * e10) * inv;
+                    d11 += (B * e01 - A * e11) * inv;
+                    ra += (A * fr + B * fi) * inv;
+                    rb2 += (B * fr - A * fi) * inv;
+                }
+                // rhs = rt + Dt r1 ;  T = I - Dt Zr (Zr = [[R, -X], [X, R]])
+                ra = fma(d00, r1s.x, ra);
+                ra = fma(d01, r1s.y, ra);
+                rb2 = fma(d10, r1s.x, rb2);
+                rb2 = fma(d11, r1s.y, rb2);
+                const double t00 = 1.0 - (d00 * z.x + d01 * z.y), t01 = 0.0 - (-d00 * z.y + d01 * z.x);
+                const double t10 = 0.0 - (d10 * z.x + d11 * z.y), t11 = 1.0 - (-d10 * z.y + d11 * z.x);
+                // Doolittle LU of the 2x2 block, as lu6 does it
+                const double i0 = 1.0 / t00, mlu = t10 * i0;
+                const double i1 = 1.0 / fma(-mlu, t01, t11);
+                // a = T^-1 rhs ; Y = T^-1 Dt (two columns)
+                double xa = ra, xb = fma(-mlu, ra, rb2);
+                xb *= i1;
+                xa = fma(-t01, xb, xa) * i0;
+                double y0a = d00, y0b = fma(-mlu, d00, d10);
+                y0b *= i1;
+                y0a = fma(-t01, y0b, y0a) * i0;
+                double y1a = d01, y1b = fma(-mlu, d01, d11);
+                y1b *= i1;
+                y1a = fma(-t01, y1b, y1a) * i0;
+                double2* Wk1 = Ws + (long long)pos * FRONT_D2 * ld;
+                Wk1[(long long)(18 + p) * ld] = make_double2(xa, xb);
+                Wk1[(long long)(21 + p) * ld] = r1s;
+                Wk1[(long long)((2 * p) * 3 + p) * ld] = make_double2(y0a, y1a);
+                Wk1[(long long)((2 * p + 1) * 3 + p) * ld] = make_double2(y0b, y1b);
+                continue;
+            }
             // every load of the step is issued before the first use (one exposed round trip, not one per phase)
             // (each load is its own predicated instruction - no branch around a group of them - so that
             // the scheduler can put all of them in flight together)
@@ -441,6 +531,37 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             const int kind = ev.w;
             const double2* Wk = Ws + (long long)pos * FRONT_D2 * ld;
             const double2 zz = make_double2(0.0, 0.0);
+            if ((bv.x >= 0) + (bv.y >= 0) + (bv.z >= 0) == 1 && kind == GP_EDGE_LINE) {   // single-phase bus
+                const int p = bv.x >= 0 ? 0 : (bv.y >= 0 ? 1 : 2);
+                const int rb = p == 0 ? bv.x : (p == 1 ? bv.y : bv.z), re = p == 0 ? ev.x : (p == 1 ? ev.y : ev.z);
+                const int rp = p == 0 ? pv.x : (p == 1 ? pv.y : pv.z);
+                const int rprev = p == 0 ? prev_row[0] : (p == 1 ? prev_row[1] : prev_row[2]);
+                const double2 dprev = p == 0 ? dv_prev[0] : (p == 1 ? dv_prev[1] : dv_prev[2]);
+                const bool hpar = rp >= 0, chain = rp == rprev;
+                const double2 dg = ld_sel(hpar && !chain, DVs + (long long)rp * ld, dummy);
+                const double2 dvp1 = (hpar && chain) ? dprev : dg;
+                double2 di1 = ld_sel(true, Wk + (long long)(18 + p) * ld, dummy);
+                const double2 r1f1 = ld_sel(true, Wk + (long long)(21 + p) * ld, dummy);
+                const double2 xv1 = ld_sel(true, Xs + (long long)rb * ld, dummy);
+                const double2 xi1 = ld_sel(true, Xs + (long long)re * ld, dummy);
+                const double2 y0 = ld_sel(true, Wk + (long long)((2 * p) * 3 + p) * ld, dummy);
+                const double2 y1 = ld_sel(true, Wk + (long long)((2 * p + 1) * 3 + p) * ld, dummy);
+                const double2 z = __ldg(&st->z[4 * p]);
+                di1.x -= y0.x * dvp1.x + y0.y * dvp1.y;
+                di1.y -= y1.x * dvp1.x + y1.y * dvp1.y;
+                double2 dv1 = make_double2(dvp1.x - r1f1.x, dvp1.y - r1f1.y);
+                dv1.x -= z.x * di1.x - z.y * di1.y;
+                dv1.y -= z.x * di1.y + z.y * di1.x;
+                Xs[(long long)rb * ld] = make_double2(xv1.x - dv1.x, xv1.y - dv1.y);
+                Xs[(long long)re * ld] = make_double2(xi1.x - di1.x, xi1.y - di1.y);
+                DVs[(long long)rb * ld] = dv1;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    prev_row[q] = q == p ? rb : -1;
+                    dv_prev[q] = dv1;
+                }
+                continue;
+            }
             double2 dvp[3], di[3], dv[3], yf[6][3], r1f[3], xv[3], xi[3];
 #pragma unroll
             for (int p = 0; p < 3; ++p) {               // issue every load of the step first (predicated, no branches)

@@ -116,6 +116,9 @@ class SolutionFBS(Solution):
     #: batches of at least this many scenarios compile the feeder-specialised kernel (about one
     #: second with NVRTC, once per instance) when the feeder fits the on-chip kernel
     SPECIALISE_MIN_BATCH = 8192
+    #: ... and at least this many 32-scenario warps of its state fit in one SM's shared memory
+    #: (measured on B200: 34-bus, 2 warps: 1.4x faster than streaming; 37-bus, 1 warp: slower)
+    SPECIALISE_MIN_WARPS = 2
 
     # ---- device plumbing -----------------------------------------------------
     def _dev(self):
@@ -145,7 +148,7 @@ class SolutionFBS(Solution):
 
     def _maybe_specialise(self, S):
         if (self._specialised is None and S >= self.SPECIALISE_MIN_BATCH
-                and _cabi.gp_fbs_onchip_warps(self._feeder.handle) >= 4):
+                and _cabi.gp_fbs_onchip_warps(self._feeder.handle) >= self.SPECIALISE_MIN_WARPS):
             self.specialise()
 
     def pack_spu(self, spu) -> np.ndarray:

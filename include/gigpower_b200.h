@@ -104,12 +104,13 @@ int64_t gp_launch_count(void);
 
 /*
  * Process-wide switches.  "fbs_kernel" selects the FBS solve kernel (identical results):
- * 0 = automatic: the on-chip kernel when the feeder's V and I rows of >= 4 warps fit in one SM's
- * shared memory, else the two-sweep streaming kernel (default); 1 = fused depth-first walk;
- * 2 = two-sweep with three phase lanes per scenario; 3 = two-sweep streaming (state in HBM);
- * 4 = on-chip (state in shared memory; the solve fails with GP_EINVAL if not even one warp fits);
- * 5 = the feeder-specialised on-chip kernel (gp_fbs_specialise must have succeeded).  Under 0 a
- * specialised feeder runs its specialised kernel.
+ * 0 = automatic: the feeder-specialised on-chip kernel once gp_fbs_specialise has built it, else
+ * the two-sweep streaming kernel (default); 1 = fused depth-first walk; 2 = two-sweep with three
+ * phase lanes per scenario; 3 = two-sweep streaming (state in HBM); 4 = table-driven on-chip
+ * kernel (state in shared memory; the solve fails with GP_EINVAL if not even one warp fits);
+ * 5 = the feeder-specialised on-chip kernel (GP_EINVAL unless gp_fbs_specialise succeeded).
+ * "fbs_prefetch" / "nr3_prefetch": L2 prefetch distance in tree steps of the streaming FBS kernel
+ * (default 0) and of the NR3 kernel (default -1 = automatic: 2 for batches up to 65,536).
  * "host_chunks": number of pipeline chunks of gp_fbs_solve_batch_host (0 = automatic).
  */
 int gp_set_option(const char* name, int value);
