@@ -6,7 +6,9 @@ power-flow solves/sec).
                   [--workload c2|c3|c4fbs|c5] [--solver fbs|nr3]
 
 A "step" is one pass of the hot path over one batch of synthetic scenarios:
-flat start -> per-scenario convergence -> |V| and losses.  At N=1 the default
+flat start -> per-scenario convergence -> |V| and losses (-> all-gather of both
+for N > 1, on a side stream so that it overlaps the next step's solve).  Steps
+rotate over enough buffer sets that nothing is found in L2 from the last use.  At N=1 the default
 workload is BASELINE config C2 (IEEE 13-bus FBS, 65,536 random load-multiplier
 scenarios).  One process per GPU under torchrun; scenarios are sharded with no
 data-path collective, the only exchange is the final NCCL gather of |V| and
@@ -301,6 +303,8 @@ def run_ours(args, wl):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout by default; stdout carries the one JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     if solver == 'fbs':
         from gigpower_b200.solution_fbs import SolutionFBS
@@ -320,102 +324,138 @@ def run_ours(args, wl):
     active = int(_cabi.gp_fbs_active_kernel(h)) if solver == 'fbs' else 0
     ld = S
     spu_h = torch.from_numpy(rows).pin_memory()
-    spu_d = spu_h.to(dev)
     c128, f64, i32 = torch.complex128, torch.float64, torch.int32
-    Vmag = torch.empty((t.n_vrows, ld), dtype=f64, device=dev)
-    loss = torch.empty(S, dtype=c128, device=dev)
-    iters = torch.empty(S, dtype=i32, device=dev)
-    status = torch.empty(S, dtype=i32, device=dev)
-    diff = torch.empty(S, dtype=f64, device=dev)
-    if world > 1:
-        Vmag_all = torch.empty((world, t.n_vrows, ld), dtype=f64, device=dev)
-        loss_all = torch.empty((world, S), dtype=c128, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     stream = torch.cuda.current_stream()
+    side = torch.cuda.Stream(device=dev)          # the gather of step k overlaps the solve of step k+1
     maxiter = sol.maxiter
-    if solver == 'fbs':
-        V = torch.empty((t.n_vrows, ld), dtype=c128, device=dev)
-        I = torch.empty((max(t.n_irows, 1), ld), dtype=c128, device=dev)
-        tol = sol.tolerance
+    tol = sol.tolerance if solver == 'fbs' else 0.0
+    fused = active == 5     # the specialised FBS kernel writes |V| and losses itself
+    wbytes = int(_cabi.gp_nr3_workspace_bytes(h, ld)) if solver == 'nr3' else 0
 
-        fused = active == 5     # the specialised kernel writes |V| and losses itself
+    class BufSet:
+        """Inputs, state and outputs of one step.  The timed loop rotates over enough sets that a
+        step never finds its inputs or state in L2 from the previous use (total > 2.5 x L2)."""
 
-        def solve_kernel():
-            if fused:
-                _cabi.check(_cabi.gp_fbs_solve_post_batch(h, S, ld, spu_d.data_ptr(), V.data_ptr(), I.data_ptr(),
-                                                          iters.data_ptr(), status.data_ptr(), diff.data_ptr(),
-                                                          Vmag.data_ptr(), loss.data_ptr(), tol, maxiter,
-                                                          stream.cuda_stream))
+        def __init__(self):
+            self.spu = spu_h.to(dev)
+            self.Vmag = torch.empty((t.n_vrows, ld), dtype=f64, device=dev)
+            self.loss = torch.empty(S, dtype=c128, device=dev)
+            self.iters = torch.empty(S, dtype=i32, device=dev)
+            self.status = torch.empty(S, dtype=i32, device=dev)
+            self.diff = torch.empty(S, dtype=f64, device=dev)
+            if solver == 'fbs':
+                self.V = torch.empty((t.n_vrows, ld), dtype=c128, device=dev)
+                self.I = torch.empty((max(t.n_irows, 1), ld), dtype=c128, device=dev)
             else:
-                _cabi.check(_cabi.gp_fbs_solve_batch(h, S, ld, spu_d.data_ptr(), V.data_ptr(), I.data_ptr(),
-                                                     iters.data_ptr(), status.data_ptr(), diff.data_ptr(),
-                                                     tol, maxiter, stream.cuda_stream))
+                self.X = torch.empty((t.n_vrows + t.n_irows, ld), dtype=c128, device=dev)
+                self.work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+            if world > 1:
+                self.Vmag_all = torch.empty((world, t.n_vrows, ld), dtype=f64, device=dev)
+                self.loss_all = torch.empty((world, S), dtype=c128, device=dev)
+            self.gathered = None        # event: the gather that last read this set has finished
 
-        def post_kernel():
-            if not fused:
-                _cabi.check(_cabi.gp_fbs_post(h, S, ld, spu_d.data_ptr(), V.data_ptr(), I.data_ptr(), None,
-                                              Vmag.data_ptr(), None, None, loss.data_ptr(), stream.cuda_stream))
-    else:
-        X = torch.empty((t.n_vrows + t.n_irows, ld), dtype=c128, device=dev)
-        wbytes = int(_cabi.gp_nr3_workspace_bytes(h, ld))
-        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        def nbytes(self):
+            return sum(v.numel() * v.element_size() for k, v in vars(self).items()
+                       if hasattr(v, 'numel') and not k.endswith('_all'))
 
-        def solve_kernel():
-            _cabi.check(_cabi.gp_nr3_solve_batch(h, S, ld, spu_d.data_ptr(), X.data_ptr(), iters.data_ptr(),
-                                                 status.data_ptr(), diff.data_ptr(), work.data_ptr(), wbytes,
-                                                 maxiter, stream.cuda_stream))
+        def solve(self):
+            if solver == 'fbs' and fused:
+                _cabi.check(_cabi.gp_fbs_solve_post_batch(h, S, ld, self.spu.data_ptr(), self.V.data_ptr(),
+                                                          self.I.data_ptr(), self.iters.data_ptr(),
+                                                          self.status.data_ptr(), self.diff.data_ptr(),
+                                                          self.Vmag.data_ptr(), self.loss.data_ptr(), tol, maxiter,
+                                                          stream.cuda_stream))
+            elif solver == 'fbs':
+                _cabi.check(_cabi.gp_fbs_solve_batch(h, S, ld, self.spu.data_ptr(), self.V.data_ptr(),
+                                                     self.I.data_ptr(), self.iters.data_ptr(), self.status.data_ptr(),
+                                                     self.diff.data_ptr(), tol, maxiter, stream.cuda_stream))
+            else:
+                _cabi.check(_cabi.gp_nr3_solve_batch(h, S, ld, self.spu.data_ptr(), self.X.data_ptr(),
+                                                     self.iters.data_ptr(), self.status.data_ptr(),
+                                                     self.diff.data_ptr(), self.work.data_ptr(), wbytes, maxiter,
+                                                     stream.cuda_stream))
 
-        def post_kernel():
-            _cabi.check(_cabi.gp_nr3_map_output(h, S, ld, spu_d.data_ptr(), X.data_ptr(), None, None, None, None,
-                                                None, None, Vmag.data_ptr(), loss.data_ptr(), stream.cuda_stream))
+        def post(self):
+            if solver == 'fbs' and not fused:
+                _cabi.check(_cabi.gp_fbs_post(h, S, ld, self.spu.data_ptr(), self.V.data_ptr(), self.I.data_ptr(),
+                                              None, self.Vmag.data_ptr(), None, None, self.loss.data_ptr(),
+                                              stream.cuda_stream))
+            elif solver == 'nr3':
+                _cabi.check(_cabi.gp_nr3_map_output(h, S, ld, self.spu.data_ptr(), self.X.data_ptr(), None, None,
+                                                    None, None, None, None, self.Vmag.data_ptr(),
+                                                    self.loss.data_ptr(), stream.cuda_stream))
 
-    def step():
-        solve_kernel()
-        post_kernel()
-        if world > 1:   # the path's one exchange: gather |V| and losses
-            dist.all_gather_into_tensor(Vmag_all, Vmag)
-            dist.all_gather_into_tensor(loss_all, loss)
+        def gather(self):
+            """The path's one exchange (|V| and losses of every rank), on the side stream."""
+            done = torch.cuda.Event()
+            done.record(stream)
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                dist.all_gather_into_tensor(self.Vmag_all, self.Vmag)
+                dist.all_gather_into_tensor(self.loss_all, self.loss)
+                self.gathered = torch.cuda.Event()
+                self.gathered.record(side)
+
+    L2_BYTES = 126 << 20
+    sets = [BufSet()]
+    n_sets = max(1, min(8, -(-int(2.5 * L2_BYTES) // sets[0].nbytes())))
+    sets += [BufSet() for _ in range(n_sets - 1)]
+
+    def step(k):
+        b = sets[k % n_sets]
+        if b.gathered is not None:
+            stream.wait_event(b.gathered)       # the previous gather out of this set's buffers is done
+        b.solve()
+        mid = torch.cuda.Event(enable_timing=True)
+        mid.record(stream)
+        b.post()
+        if world > 1:
+            b.gather()
+        return mid
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_()
-        step()
+    for k in range(max(args.warmup, 3)):
+        step(k)
     barrier()
-    # ---- timed region: K steps, device-timed per step, L2 flushed in between --------------
+    # ---- timed region: K steps back to back between two events; solve kernels timed individually ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = _cabi.gp_launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mids = []
     barrier()
     t_wall0 = time.perf_counter()
+    e_begin.record(stream)
     for k in range(args.steps):
-        flush.zero_()                 # untimed: evict the previous step's state from L2
-        if world > 1:
-            dist.barrier()
-        ev[k][0].record(stream)
-        solve_kernel()
-        ev[k][1].record(stream)
-        post_kernel()
-        if world > 1:
-            dist.all_gather_into_tensor(Vmag_all, Vmag)
-            dist.all_gather_into_tensor(loss_all, loss)
-        ev[k][2].record(stream)
+        e0[k].record(stream)
+        mids.append(step(k))
+    stream.wait_stream(side)                      # the last gathers belong to the timed steps
+    e_end.record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = _cabi.gp_launch_count() - launches0
-    ms_steps = np.array([e[0].elapsed_time(e[2]) for e in ev])
-    ms_solve = np.array([e[0].elapsed_time(e[1]) for e in ev])
-    tot_ms = torch.tensor([ms_steps.sum()], dtype=f64, device=dev)
+    ms_total = e_begin.elapsed_time(e_end)
+    ms_solve = np.array([e0[k].elapsed_time(mids[k]) for k in range(args.steps)])
+    tot_ms = torch.tensor([ms_total], dtype=f64, device=dev)
     if world > 1:
         dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(tot_ms.item()) / args.steps
+    ms_steps = np.full(args.steps, ms_per_step)
     value = world * S / (ms_per_step * 1e-3)
+    last = sets[(args.steps - 1) % n_sets]
+    iters, status = last.iters, last.status
+    spu_d = last.spu
+    if solver == 'nr3':
+        X = last.X
+
+        def solve_kernel():
+            last.solve()
     its = iters.cpu().numpy().astype(np.int64)
     assert (status.cpu().numpy() == 0).all(), 'bench scenarios must all converge'
 
@@ -517,8 +557,11 @@ def run_ours(args, wl):
                        'fbs_kernel': variant,
                        'rows': {'P_b': t.n_vrows, 'P_l': t.n_irows, 'P_L': t.n_srows},
                        'mean_iterations': float(its.mean()), 'max_iterations': int(its.max()),
-                       'l2': 'flushed between steps (256 MiB write, untimed)',
-                       'timing': 'CUDA events per step on the launch stream, max over ranks',
+                       'l2': f'no reuse across steps: {n_sets} rotating buffer set(s) of {sets[0].nbytes() >> 20} MiB '
+                             f'(inputs + state + outputs) against a 126 MiB L2',
+                       'timing': 'CUDA events around the K back-to-back steps on the launch stream (gather of step k '
+                                 'on a side stream, overlapping the solve of step k+1), max over ranks; solve kernels '
+                                 'timed individually for the roofline',
                        'parallelism': f'scenario-sharded x{world}, final NCCL all-gather of |V| and losses'},
             'e2e': {'value': e2e_value, 'unit': 'solves/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
