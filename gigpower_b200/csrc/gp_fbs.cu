@@ -26,6 +26,7 @@ namespace gp {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 extern int g_nr3_prefetch;     // gp_nr3.cu
+static int g_host_zero_copy = 1;   // gp_set_option("host_zero_copy", 0|1): one-launch host path of the specialised kernel
 static int g_host_chunks = 0;  // gp_set_option("host_chunks", n): 0 = automatic
 // gp_set_option("fbs_kernel", v): 0 automatic (feeder-specialised on-chip kernel once built, else two-sweep), 1 fused
 // depth-first, 2 phase-parallel, 3 two-sweep streaming, 4 on-chip (error if the feeder does not fit),
@@ -1013,6 +1014,10 @@ extern "C" int gp_set_option(const char* name, int value) {
         g_nr3_prefetch = value;
         return GP_OK;
     }
+    if (name && strcmp(name, "host_zero_copy") == 0 && (value == 0 || value == 1)) {
+        g_host_zero_copy = value;
+        return GP_OK;
+    }
     if (name && strcmp(name, "host_chunks") == 0 && value >= 0 && value <= 64) {
         g_host_chunks = value;
         return GP_OK;
@@ -1429,6 +1434,7 @@ extern "C" int gp_feeder_destroy(GpFeeder* f) {
         cudaFree(im->d_evrows);
         cudaFree(im->d_sched);
         cudaFree(im->d_unfed);
+        cudaFree(im->d_zc);
         if (im->jit_module) driver().ModuleUnload(im->jit_module);
         for (int i = 0; i < FbsImpl::NSTREAM; ++i) {
             if (im->d_stage[i]) cudaFree(im->d_stage[i]);
@@ -1445,6 +1451,30 @@ extern "C" int gp_feeder_destroy(GpFeeder* f) {
 static int fbs_check(GpFeeder* f, int64_t S, int64_t ld, const char* who) {
     if (!f || f->kind != 1) return fail(GP_EINVAL, "%s: not an FBS feeder handle", who);
     if (S < 0 || ld < S) return fail(GP_EINVAL, "%s: need 0 <= S <= ld (S=%lld ld=%lld)", who, (long long)S, (long long)ld);
+    return GP_OK;
+}
+
+// Launch of the feeder-specialised kernel.  `stage` != NULL: spu is mapped host memory and is staged
+// through these device rows by the kernel itself; V, I, Vmag, loss, iters, status, diff may then be
+// mapped host memory too (the kernel's final stores go straight over PCIe).
+static int fbs_jit_launch(FbsImpl* im, int64_t S, int64_t ld, const double* spu, double* V, double* I,
+                          int32_t* iters, int32_t* status, double* diff, double tol, int32_t maxiter,
+                          cudaStream_t st, double* Vmag, double* loss, void* stage) {
+    const long long n_tiles = (S + 31) / 32;
+    const int nw = im->jit_warps;
+    long long blocks = (n_tiles + nw - 1) / nw;
+    if (blocks > im->n_sm) blocks = im->n_sm;
+    const unsigned smem = (unsigned)nw * (unsigned)(im->n_vrows + im->n_irows) * 512u;
+    long long S_arg = S;
+    double tol_arg = tol;
+    int maxiter_arg = maxiter;
+    unsigned ldb_arg = (unsigned)(ld * 16);
+    void* args[] = {(void*)&spu, (void*)&V, (void*)&I, (void*)&iters, (void*)&status, (void*)&diff,
+                    (void*)&S_arg, (void*)&ldb_arg, (void*)&tol_arg, (void*)&maxiter_arg, (void*)&im->d_sched,
+                    (void*)&Vmag, (void*)&loss, (void*)&stage};
+    const int cr = driver().LaunchKernel(im->jit_kernel, (unsigned)blocks, 1, 1, (unsigned)nw * 32, 1, 1, smem,
+                                         (void*)st, args, nullptr);
+    if (cr != 0) return fail(GP_ECUDA, "gp_fbs_solve_batch: cuLaunchKernel failed (%d)", cr);
     return GP_OK;
 }
 
@@ -1476,22 +1506,9 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     if ((g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) && (maxiter >= 1 || !im->jit_kernel)) {
         if (!im->jit_kernel)
             return fail(GP_EINVAL, "gp_fbs_solve_batch: fbs_kernel = 5 needs a successful gp_fbs_specialise");
-        const long long n_tiles = (S + 31) / 32;
-        const int nw = im->jit_warps;
-        long long blocks = (n_tiles + nw - 1) / nw;
-        if (blocks > im->n_sm) blocks = im->n_sm;
-        const unsigned smem = (unsigned)nw * (unsigned)(im->n_vrows + im->n_irows) * 512u;
-        long long S_arg = S;
-        double tol_arg = tol;
-        int maxiter_arg = maxiter;
-        unsigned ldb_arg = ldb;
-        void* args[] = {(void*)&spu, (void*)&V, (void*)&I, (void*)&iters, (void*)&status, (void*)&diff,
-                        (void*)&S_arg, (void*)&ldb_arg, (void*)&tol_arg, (void*)&maxiter_arg, (void*)&im->d_sched,
-                        (void*)&Vmag, (void*)&loss};
+        rc = fbs_jit_launch(im, S, ld, spu, V, I, iters, status, diff, tol, maxiter, st, Vmag, loss, nullptr);
+        if (rc) return rc;
         *fused = true;
-        const int cr = driver().LaunchKernel(im->jit_kernel, (unsigned)blocks, 1, 1, (unsigned)nw * 32, 1, 1, smem,
-                                             (void*)st, args, nullptr);
-        if (cr != 0) return fail(GP_ECUDA, "gp_fbs_solve_batch: cuLaunchKernel failed (%d)", cr);
     } else if (onchip) {
         if (im->onchip_warps < 1)
             return fail(GP_EINVAL, "gp_fbs_solve_batch: the on-chip kernel needs %d bytes of shared memory per warp",
@@ -1631,6 +1648,44 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
     // overhead), so a batch that moves <= 128 MB is fastest as ONE chunk (three contiguous
     // copies around the kernels); larger batches are cut into NSTREAM pipelined chunks with
     // row pieces of at least 512 KB (32 Ki scenarios).
+    // One-launch path: with the feeder-specialised kernel and pinned (device-mapped) host buffers the
+    // kernel reads spu and writes its results over PCIe itself, tile by tile: upload, solve and
+    // download overlap inside one launch and there is nothing to chunk.
+    if (im->jit_kernel && maxiter >= 1 && g_host_zero_copy && (g_fbs_kernel == 0 || g_fbs_kernel == 5) &&
+        ld * 16 < ((int64_t)1 << 32)) {
+        const void* hp[] = {spu_h, V_h, I_h, Vmag_h, loss_h, iters_h, status_h, diff_h};
+        void* dp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        bool ok = iters_h && status_h && diff_h;
+        for (int i = 0; i < 8 && ok; ++i) {
+            if (!hp[i]) continue;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, hp[i]) != cudaSuccess || at.type != cudaMemoryTypeHost ||
+                !at.devicePointer) {
+                cudaGetLastError();
+                ok = false;
+            } else {
+                dp[i] = at.devicePointer;
+            }
+        }
+        if (ok) {
+            const size_t need_stage = (size_t)im->n_srows * (size_t)ld * 16 + 256;
+            if (need_stage > im->zc_bytes) {
+                if (im->d_zc) cudaFree(im->d_zc);
+                im->d_zc = nullptr;
+                im->zc_bytes = 0;
+                GP_CUDA(cudaMalloc(&im->d_zc, need_stage));
+                im->zc_bytes = need_stage;
+            }
+            if (!im->streams[0]) GP_CUDA(cudaStreamCreateWithFlags(&im->streams[0], cudaStreamNonBlocking));
+            rc = fbs_jit_launch(im, S, ld, (const double*)dp[0], (double*)dp[1], (double*)dp[2], (int32_t*)dp[5],
+                                (int32_t*)dp[6], (double*)dp[7], tol, maxiter, im->streams[0], (double*)dp[3],
+                                (double*)dp[4], im->d_zc);
+            if (rc) return rc;
+            count_launch();
+            GP_CUDA(cudaStreamSynchronize(im->streams[0]));
+            return GP_OK;
+        }
+    }
     int want_chunks = g_host_chunks > 0 ? g_host_chunks : (rows * S * 16 <= ((int64_t)128 << 20) ? 1 : FbsImpl::NSTREAM);
     int64_t C = ((S + want_chunks - 1) / want_chunks + 127) / 128 * 128;
     if (C < 32768 && g_host_chunks == 0) C = 32768;

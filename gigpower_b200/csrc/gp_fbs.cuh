@@ -61,6 +61,8 @@ struct FbsImpl {
     void* jit_module = nullptr;   // CUmodule
     void* jit_kernel = nullptr;   // CUfunction
     int jit_warps = 0;
+    void* d_zc = nullptr;         // device staging rows of the one-launch host path
+    size_t zc_bytes = 0;
     // host staging for gp_fbs_solve_batch_host
     static constexpr int NSTREAM = 4;
     cudaStream_t streams[NSTREAM] = {nullptr, nullptr, nullptr, nullptr};

@@ -270,3 +270,42 @@ def test_specialised_kernel_restarts_diverging_scenarios_exactly():
     fin = np.isfinite(ref.V[bad]) & np.isfinite(r.V[bad])
     assert np.array_equal(np.isfinite(ref.V[bad]), np.isfinite(r.V[bad]))
     assert rel_err(r.V[bad][fin], ref.V[bad][fin]) <= 1e-9
+
+
+def test_host_entry_point_one_launch_path_matches_staged_path():
+    """gp_fbs_solve_batch_host with the specialised kernel and pinned buffers runs as ONE launch that
+    reads spu and writes the results over PCIe itself; it must give exactly what the staged
+    (copy - solve - copy) path gives, with any subset of the optional outputs, and pageable buffers
+    must fall back to the staged path."""
+    import torch
+    from gigpower_b200 import _cabi
+    feeder, S = 'IEEE_13_Bus_allwye_noxfm_noreg', 30000 + 7
+    s = _fbs(feeder)
+    assert s.specialise()
+    rng = np.random.Generator(np.random.PCG64(17))
+    rows = np.ascontiguousarray(s.load_weights() @ rng.uniform(0.5, 1.5, size=(S, s.circuit.loads.num_elements)).T)
+    t = s.tables
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+    spu_h = torch.from_numpy(rows).pin_memory()
+    out = {}
+    try:
+        for zc in (0, 1):
+            _cabi.check(_cabi.gp_set_option(b'host_zero_copy', zc))
+            V, I = pin((t.n_vrows, S), torch.complex128), pin((t.n_irows, S), torch.complex128)
+            Vmag, loss = pin((t.n_vrows, S), torch.float64), pin(S, torch.complex128)
+            n0 = _cabi.gp_launch_count()
+            it, st, df = s.solve_batch_host(spu_h, V, I, Vmag, loss)
+            out[zc] = (it.copy(), st.copy(), df.copy(), V.numpy().copy(), I.numpy().copy(), Vmag.numpy().copy(),
+                       loss.numpy().copy(), _cabi.gp_launch_count() - n0)
+    finally:
+        _cabi.gp_set_option(b'host_zero_copy', 1)
+    assert out[1][7] == 1 and out[0][7] >= 1
+    for a, b in zip(out[0][:7], out[1][:7]):
+        assert np.array_equal(a, b)
+    # only V requested; and pageable (not pinned) buffers -> staged path, same numbers
+    V2 = pin((t.n_vrows, S), torch.complex128)
+    it2, st2, _ = s.solve_batch_host(spu_h, V2)
+    assert np.array_equal(V2.numpy(), out[1][3]) and np.array_equal(it2, out[1][0])
+    V3 = np.empty((t.n_vrows, S), dtype=complex)
+    it3, _, _ = s.solve_batch_host(rows, V3)
+    assert np.array_equal(V3, out[1][3]) and np.array_equal(it3, out[1][0])
