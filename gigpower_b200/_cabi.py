@@ -87,6 +87,11 @@ gp_fbs_solve_batch_host = _sig('gp_fbs_solve_batch_host', C.c_int,
                                [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp,
                                 C.c_double, C.c_int32])
 
+gp_der_rows = _sig('gp_der_rows', C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                             vp, vp, vp, vp, vp, vp, vp])
+gp_vmag_summary = _sig('gp_vmag_summary', C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int32, vp, C.c_double,
+                                                     C.c_double, vp, vp, vp, vp])
+
 gp_nr3_create = _sig('gp_nr3_create', C.c_int, [C.POINTER(GpNr3Desc), C.c_int, C.POINTER(vp)])
 gp_nr3_workspace_bytes = _sig('gp_nr3_workspace_bytes', C.c_int64, [vp, C.c_int64])
 gp_nr3_solve_batch = _sig('gp_nr3_solve_batch', C.c_int,
@@ -97,7 +102,7 @@ gp_nr3_map_output = _sig('gp_nr3_map_output', C.c_int,
 EXPORTS = ['gp_version', 'gp_last_error', 'gp_launch_count', 'gp_set_option', 'gp_fbs_active_kernel',
            'gp_fbs_onchip_warps', 'gp_measure_fp64_peak', 'gp_fbs_specialise', 'gp_fbs_jit_source',
            'gp_jit_compile', 'gp_fbs_create', 'gp_feeder_destroy',
-           'gp_fbs_solve_batch', 'gp_fbs_solve_post_batch', 'gp_fbs_post', 'gp_fbs_solve_batch_host', 'gp_nr3_create',
+           'gp_fbs_solve_batch', 'gp_fbs_solve_post_batch', 'gp_fbs_post', 'gp_fbs_solve_batch_host', 'gp_der_rows', 'gp_vmag_summary', 'gp_nr3_create',
            'gp_nr3_workspace_bytes', 'gp_nr3_solve_batch', 'gp_nr3_map_output']
 
 

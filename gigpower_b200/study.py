@@ -1,0 +1,130 @@
+"""Scenario studies on top of the batched solvers.
+
+The reference runs a study one snapshot at a time: ``circuit.set_kW / set_kvar``
+(``circuit.py:66-88``), ``solve()``, read the DataFrames (``solution.py:127-155``).
+Here a study is a batch: its scenarios are synthesised on the device from small
+tables, solved in chunks, and reduced on the device to what the study keeps per
+scenario (losses, iteration counts, min / max |V|, voltage-band violations).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import pandas as pd
+
+from . import _cabi
+
+
+def voltage_summary(Vmag_rows, S: Optional[int] = None, vmin: float = 0.95, vmax: float = 1.05, stream=None):
+    """Per-scenario (min |V|, max |V|, number of bus-phases outside [vmin, vmax]) of packed
+    ``Vmag_rows`` ``[n_vrows, ld]`` (CUDA tensor; a NumPy array is uploaded) through
+    ``gp_vmag_summary``.  Returns three CUDA tensors of length S."""
+    torch = _cabi.require_cuda()
+    if isinstance(Vmag_rows, np.ndarray):
+        Vmag_rows = torch.from_numpy(np.ascontiguousarray(Vmag_rows, dtype=np.float64)).cuda()
+    if Vmag_rows.dtype != torch.float64 or Vmag_rows.dim() != 2 or not Vmag_rows.is_contiguous():
+        raise ValueError('Vmag_rows must be a contiguous [n_vrows, ld] float64 tensor')
+    n_vrows, ld = int(Vmag_rows.shape[0]), int(Vmag_rows.shape[1])
+    S = ld if S is None else int(S)
+    dev = Vmag_rows.device
+    lo = torch.empty(S, dtype=torch.float64, device=dev)
+    hi = torch.empty(S, dtype=torch.float64, device=dev)
+    cnt = torch.empty(S, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream(dev) if stream is None else stream
+    _cabi.check(_cabi.gp_vmag_summary(dev.index, S, ld, n_vrows, Vmag_rows.data_ptr(), float(vmin), float(vmax),
+                                      lo.data_ptr(), hi.data_ptr(), cnt.data_ptr(), st.cuda_stream))
+    return lo, hi, cnt
+
+
+def scenario_frame(solution, result, param: str, scenario: int, orient: str = '') -> pd.DataFrame:
+    """One scenario of a ``BatchResult`` as the DataFrame ``Solution.get_data_frame`` returns for a
+    snapshot (``solution.py:127-155``): index = element names in OpenDSS order, columns A, B, C."""
+    if param not in solution.SOLUTION_PARAMS:
+        raise KeyError(param)
+    element_group, cols, datatype = solution.SOLUTION_PARAMS[param]
+    data = getattr(result, param)
+    if data is None:
+        raise ValueError(f'{param} was not among the outputs of this batch')
+    index = getattr(solution.circuit, element_group).all_names()
+    one = np.asarray(data[scenario])
+    if type(solution).__name__ == 'SolutionNR3':       # NR3 keeps 3 x n (solution_nr3.py:634-663)
+        one = one.T
+    frame = pd.DataFrame(data=one[:len(index)], index=index, columns=cols, dtype=datatype)
+    orient = orient or solution._orient
+    return frame.transpose() if orient == 'cols' else frame
+
+
+class DerStudy:
+    """Hourly load profile x DER scenario study (BASELINE config C4).
+
+    Scenario ``d * H + h`` is hour ``h`` of DER scenario ``d``:
+    ``spu = m_h[h] * S_load - pen[d] * pv_h[h] * mask[d] * P_load`` per loaded bus-phase
+    (SURVEY.md section 8(d), C4).  ``m_h``, ``pv_h``: ``[H]``; ``mask``: ``[D, n_srows]`` 0/1;
+    ``pen``: ``[D]``.  Works with ``SolutionFBS`` and ``SolutionNR3``.
+    """
+
+    def __init__(self, solution, m_h, pv_h, mask, pen):
+        self.sol = solution
+        torch, dev = solution._dev()
+        self.torch, self.dev = torch, dev
+        t = solution.tables
+        self.H, self.D = int(len(m_h)), int(len(pen))
+        mask = np.ascontiguousarray(mask, dtype=np.float64)
+        if mask.shape != (self.D, t.n_srows) or len(pv_h) != self.H:
+            raise ValueError(f'mask must be [{self.D}, {t.n_srows}] and pv_h [{self.H}]')
+        self.W0 = torch.from_numpy(np.ascontiguousarray(solution.load_weights().sum(axis=1))).to(dev)
+        self.upload(m_h, pv_h, mask, pen)
+        self.is_fbs = hasattr(solution, 'tolerance')
+        self._host, self._spu = None, None
+
+    def upload(self, m_h, pv_h, mask, pen):
+        """(Re)load the hour and DER tables - the only inputs of the study that cross PCIe."""
+        up = lambda a: self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.dev)
+        self.m_h, self.pv_h, self.mask, self.pen = up(m_h), up(pv_h), up(mask), up(pen)
+
+    @property
+    def n_scenarios(self) -> int:
+        return self.H * self.D
+
+    def spu_rows(self, first: int, S: int, out=None, stream=None):
+        """Packed spu rows ``[n_srows, S]`` of scenarios ``first .. first + S`` (CUDA tensor)."""
+        torch, t = self.torch, self.sol.tables
+        if out is None:
+            out = torch.empty((t.n_srows, S), dtype=torch.complex128, device=self.dev)
+        st = torch.cuda.current_stream(self.dev) if stream is None else stream
+        _cabi.check(_cabi.gp_der_rows(self.dev.index, S, int(out.shape[1]), int(first), self.H, self.D, t.n_srows,
+                                      self.W0.data_ptr(), self.m_h.data_ptr(), self.pv_h.data_ptr(),
+                                      self.mask.data_ptr(), self.pen.data_ptr(), out.data_ptr(), st.cuda_stream))
+        return out
+
+    def run(self, first: int = 0, count: Optional[int] = None, chunk: int = 131072, vmin: float = 0.95,
+            vmax: float = 1.05) -> Dict[str, np.ndarray]:
+        """Solve scenarios ``first .. first + count`` in chunks; per scenario keep iterations, status,
+        loss, min |V|, max |V| and the number of bus-phases outside ``[vmin, vmax]`` (pinned host
+        arrays; 36 bytes per scenario cross PCIe, nothing goes up but the tables)."""
+        torch, sol, t = self.torch, self.sol, self.sol.tables
+        count = self.n_scenarios - first if count is None else int(count)
+        chunk = max(1, min(int(chunk), count))
+        kinds = {'iterations': torch.int32, 'status': torch.int32, 'loss': torch.complex128,
+                 'vmin': torch.float64, 'vmax': torch.float64, 'violations': torch.int32}
+        if self._host is None or self._host['status'].numel() < count:      # pinning is slow: keep the buffers
+            self._host = {k: torch.empty(count, dtype=dt).pin_memory() for k, dt in kinds.items()}
+        host = {k: v[:count] for k, v in self._host.items()}
+        if self._spu is None or self._spu.shape[1] != chunk:
+            self._spu = torch.empty((t.n_srows, chunk), dtype=torch.complex128, device=self.dev)
+        spu = self._spu
+        if self.is_fbs:
+            sol._maybe_specialise(chunk)
+        st = torch.cuda.current_stream(self.dev)
+        for lo in range(0, count, chunk):
+            n = min(chunk, count - lo)
+            self.spu_rows(first + lo, n, out=spu, stream=st)
+            r = sol.solve_batch(spu_rows=spu[:, :n] if n == chunk else spu[:, :n].contiguous(),
+                                outputs=('Vmag', 'loss'), return_device=True, stream=st)
+            vlo, vhi, cnt = voltage_summary(r.Vmag_rows, n, vmin, vmax, stream=st)
+            for key, src in (('iterations', r.iterations), ('status', r.status), ('loss', r.loss), ('vmin', vlo),
+                             ('vmax', vhi), ('violations', cnt)):
+                host[key][lo:lo + n].copy_(src[:n], non_blocking=True)
+        st.synchronize()
+        return {k: v.numpy() for k, v in host.items()}      # views of pinned buffers the next run() reuses

@@ -213,6 +213,27 @@ int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const double* sp
                             double* loss_host, int32_t* iters_host, int32_t* status_host,
                             double* diff_host, double tol, int32_t maxiter);
 
+/*
+ * Scenario studies (callers: a time-series driver looping over what the
+ * reference does one `Circuit.set_kW / set_kvar` + `solve()` at a time, circuit.py:66-88).
+ *
+ * gp_der_rows: packed spu rows of an hourly profile x DER scenario study, built on the device.
+ * Scenario first + s is hour h = idx % H of DER scenario d = idx / H (idx taken modulo H * D):
+ *     spu[r][s] = m_h[h] * W0[r] - (Re W0[r] * mask[d][r]) * (pen[d] * pv_h[h])       (real part only)
+ * with W0 [n_srows] complex the nominal load of each loaded bus-phase, m_h / pv_h [H] the hourly load
+ * multiplier and PV shape, mask [D][n_srows] (0 / 1) the bus-phases that carry PV in DER scenario d and
+ * pen [D] its penetration.  Each product and the difference are rounded separately, so the rows equal
+ * the NumPy expression of bench.py:make_der_rows bit for bit.  All pointers are device pointers.
+ *
+ * gp_vmag_summary: per scenario min |V|, max |V| and the number of bus-phases with |V| outside
+ * [vmin, vmax] (NaN counts as outside) over the rows of Vmag [n_vrows][ld]; any output may be NULL.
+ */
+int gp_der_rows(int device, int64_t S, int64_t ld, int64_t first, int32_t H, int32_t D, int32_t n_srows,
+                const double* W0_dev, const double* m_h_dev, const double* pv_h_dev, const double* mask_dev,
+                const double* pen_dev, double* spu_dev, void* stream);
+int gp_vmag_summary(int device, int64_t S, int64_t ld, int32_t n_vrows, const double* Vmag_dev, double vmin,
+                    double vmax, double* min_dev, double* max_dev, int32_t* count_dev, void* stream);
+
 
 /* ------------------------------------------------------------------------
  * NR3 (three-phase Newton-Raphson), reference src/solution_nr3.py + src/nr3_lib/
