@@ -26,6 +26,7 @@ namespace gp {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 extern int g_nr3_prefetch;     // gp_nr3.cu
+extern int g_nr3_kernel;
 static int g_host_zero_copy = 1;   // gp_set_option("host_zero_copy", 0|1): one-launch host path of the specialised kernel
 static int g_host_chunks = 0;  // gp_set_option("host_chunks", n): 0 = automatic
 // gp_set_option("fbs_kernel", v): 0 automatic (feeder-specialised on-chip kernel once built, else two-sweep), 1 fused
@@ -1008,6 +1009,10 @@ extern "C" int gp_set_option(const char* name, int value) {
     }
     if (name && strcmp(name, "fbs_prefetch") == 0 && value >= 0 && value <= 64) {
         g_fbs_prefetch = value;
+        return GP_OK;
+    }
+    if (name && strcmp(name, "nr3_kernel") == 0 && value >= 0 && value <= 2) {
+        g_nr3_kernel = value;
         return GP_OK;
     }
     if (name && strcmp(name, "nr3_prefetch") == 0 && value >= -1 && value <= 64) {

@@ -64,6 +64,8 @@ struct Nr3Impl {
     double* d_vrow_cap = nullptr; // [n_vrows]
     Nr3Const k;
     int n_fronts = 0;   // n_steps + one extra slot per regulator step
+    bool lines_only = true;   // no regulator step: eligible for the phase-parallel kernel
+    bool mostly_3ph = false;  // at least 5 of 6 non-root buses carry all three phases
 };
 
 constexpr int FRONT_D2 = 24;   // double2 per step: Y (18) + a (3) + r1 (3)
@@ -655,6 +657,303 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
     status_out[s] = nanflag ? GP_ST_NONFINITE : (fm < 1e-9 ? GP_ST_CONVERGED : (isinf(fm) ? GP_ST_NONFINITE : GP_ST_MAXITER));
 }
 
+// ---------------------------------------------------------------------------------------
+// Phase-parallel Newton kernel (Line / Transformer feeders).
+//
+// A scenario is owned by THREE lanes, one per phase (lane = phase * 10 + j: ten scenarios per
+// warp, lanes 30 and 31 idle).  Lane g holds the two real rows 2g, 2g+1 of everything the step
+// builds - Dt, the right-hand sides, T = I - Dt Zr - and touches only the memory rows of its own
+// phase.  The 6x6 system is reduced by Gauss-Jordan on the augmented rows [T | rhs | Dt]: per
+// pivot the owning lane's row is broadcast with warp shuffles and every lane eliminates the
+// pivot column from its own two rows, so the seven solves of the thread-per-scenario kernel
+// (a = T^-1 rhs, Y = T^-1 Dt) come out of one sweep over the pivots with no back-substitution.
+// Compared with one thread per scenario this needs about 130 registers instead of 254 (twice
+// the resident warps), a third of the dependent chain per step, and three times the warps for
+// a given batch - which is what BASELINE's small NR3 batches (16,384 scenarios = one warp per
+// SM sub-partition at a thread per scenario) lack.  Same equations, same stop rule.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 shfl_d2(double2 v, int src) {
+    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+__device__ __forceinline__ int pick3(const int4 v, int g) { return g == 0 ? v.x : (g == 1 ? v.y : v.z); }
+__device__ __forceinline__ int pick3c(const int4 v, int g) { return g == 0 ? v.y : (g == 1 ? v.z : v.w); }
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ childs, Nr3Const k,
+                 long long S, long long ld, const double2* __restrict__ spu, double2* __restrict__ X,
+                 double2* __restrict__ W, double2* __restrict__ DV, int* __restrict__ iters_out,
+                 int* __restrict__ status_out, double* __restrict__ fmax_out, int maxiter) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * BLOCK + threadIdx.x) >> 5;
+    const int j = lane % 10;
+    const int g = lane < 30 ? lane / 10 : 2;
+    const long long s_raw = warp * 10 + j;
+    const bool owner = lane < 30 && s_raw < S;
+    const long long s = s_raw < S ? s_raw : S - 1;          // idle lanes shadow a real scenario (loads only)
+    const int src0 = j, src1 = 10 + j, src2 = 20 + j;
+    const double2* spu_s = spu + s;
+    double2* Xs = X + s;
+    double2* Ws = W + s;
+    double2* DVs = DV + s;
+    const int n_steps = k.n_steps;
+    const double2 zz = make_double2(0.0, 0.0);
+    const double2* dummy = Xs + (long long)k.root_row[0] * ld;
+    const int my_root = g == 0 ? k.root_row[0] : (g == 1 ? k.root_row[1] : k.root_row[2]);
+    const double2 my_slack = g == 0 ? k.vslack[0] : (g == 1 ? k.vslack[1] : k.vslack[2]);
+    const double my_cA = g == 0 ? k.cA[0] : (g == 1 ? k.cA[1] : k.cA[2]);
+    const double my_cB = g == 0 ? k.cB[0] : (g == 1 ? k.cB[1] : k.cB[2]);
+
+    // flat start (solution_nr3.py:37-82)
+    if (owner) {
+        for (int pos = 0; pos < n_steps; ++pos) {
+            const int b = pick3(__ldg(reinterpret_cast<const int4*>(steps[pos].bus_row)), g);
+            const int e = pick3(__ldg(reinterpret_cast<const int4*>(steps[pos].edge_row)), g);
+            if (b >= 0) Xs[(long long)b * ld] = my_slack;
+            if (e >= 0) Xs[(long long)e * ld] = zz;
+        }
+        Xs[(long long)my_root * ld] = my_slack;
+    }
+    __syncwarp();
+
+    int it = 0;
+    double fm = 1e99;
+    bool nanflag = false;
+    bool active = owner && maxiter > 0;
+    while (__any_sync(0xffffffffu, active)) {
+        double fml = (it == 0) ? k.f0_absent : 0.0;          // this lane's share of max |F|
+        bool nanl = false;
+        // ================= backward sweep =================
+        for (int pos = n_steps - 1; pos >= 0; --pos) {
+            const Nr3Step* st = steps + pos;
+            const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_row));
+            const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_row));
+            const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_row));
+            const int4 lv = __ldg(reinterpret_cast<const int4*>(st->load_srow));
+            const int my_b = pick3(bv, g), my_p = pick3(pv, g), my_e = pick3(ev, g), my_l = pick3(lv, g);
+            const bool hb = my_b >= 0;
+            const int child_count = bv.w, child_begin = pv.w;
+            const double2 v = ld_sel(hb, Xs + (long long)my_b * ld, dummy);
+            double2 inet = ld_sel(hb, Xs + (long long)my_e * ld, dummy);
+            const double2 vpar = ld_sel(hb && my_p >= 0, Xs + (long long)my_p * ld, dummy);
+            const double2 spl = ld_sel(hb && my_l >= 0, spu_s + (long long)my_l * ld, dummy);
+            // KVL residual r1 = E v_p - v - Z i (:141-158): the currents of all three phases
+            const double2 i0 = shfl_d2(inet, src0), i1 = shfl_d2(inet, src1), i2 = shfl_d2(inet, src2);
+            const double2 zg0 = __ldg(&st->z[3 * g]), zg1 = __ldg(&st->z[3 * g + 1]), zg2 = __ldg(&st->z[3 * g + 2]);
+            double2 r1 = zz;
+            if (hb) {
+                r1.x = vpar.x - v.x;
+                r1.y = vpar.y - v.y;
+                r1.x -= zg0.x * i0.x - zg0.y * i0.y;
+                r1.y -= zg0.x * i0.y + zg0.y * i0.x;
+                r1.x -= zg1.x * i1.x - zg1.y * i1.y;
+                r1.y -= zg1.x * i1.y + zg1.y * i1.x;
+                r1.x -= zg2.x * i2.x - zg2.y * i2.y;
+                r1.y -= zg2.x * i2.y + zg2.y * i2.x;
+                nanl |= (r1.x != r1.x) | (r1.y != r1.y);
+                fml = fmax(fml, fmax(fabs(r1.x), fabs(r1.y)));
+            }
+            // augmented rows of this lane: columns 0-5 T, 6 rhs, 7-12 Dt
+            double R0[13], R1[13];
+#pragma unroll
+            for (int c = 0; c < 13; ++c) R0[c] = R1[c] = 0.0;
+            for (int c = 0; c < child_count; ++c) {         // children: net current, fronts (Y_c, a_c)
+                const int4 ch = __ldg(childs + child_begin + c);
+                const int cr = pick3c(ch, g);
+                const bool hc = cr >= 0;
+                const double2* Wc = Ws + (long long)ch.x * FRONT_D2 * ld;
+                const double2 ic = ld_sel(hc, Xs + (long long)cr * ld, dummy);
+                const double2 ac = ld_sel(hc, Wc + (long long)(18 + g) * ld, dummy);
+                double2 y0[3], y1[3];
+                const bool hq[3] = {hc && ch.y >= 0, hc && ch.z >= 0, hc && ch.w >= 0};
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    y0[q] = ld_sel(hq[q], Wc + (long long)((2 * g) * 3 + q) * ld, dummy);
+                    y1[q] = ld_sel(hq[q], Wc + (long long)((2 * g + 1) * 3 + q) * ld, dummy);
+                }
+                inet.x -= ic.x;
+                inet.y -= ic.y;
+                R0[6] += ac.x;
+                R1[6] += ac.y;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    R0[7 + 2 * q] += y0[q].x;
+                    R0[8 + 2 * q] += y0[q].y;
+                    R1[7 + 2 * q] += y1[q].x;
+                    R1[8 + 2 * q] += y1[q].y;
+                }
+            }
+            if (hb) {       // KCL residual and D block of this phase (:226-299, 403-440)
+                const double A = v.x, B = v.y, Cn = inet.x, Dn = inet.y;
+                const double pl = spl.x, ql = spl.y;
+                const double cap = g == 0 ? __ldg(&st->cap[0]) : (g == 1 ? __ldg(&st->cap[1]) : __ldg(&st->cap[2]));
+                const double hAr = -pl * my_cA, hBr = -pl * my_cB, b0r = -pl * k.betaS;
+                const double hAi = -ql * my_cA + cap * my_cA;
+                const double hBi = -ql * my_cB + cap * my_cB;
+                const double b0i = (-ql * k.betaS) + (cap * k.betaS);
+                const double fr = A * Cn + B * Dn + hAr * A * A + hBr * B * B + b0r;
+                const double fi = B * Cn - A * Dn + hAi * A * A + hBi * B * B + b0i;
+                nanl |= (fr != fr) | (fi != fi);
+                fml = fmax(fml, fmax(fabs(fr), fabs(fi)));
+                const double d00 = Cn + 2.0 * hAr * A, d01 = Dn + 2.0 * hBr * B;
+                const double d10 = -Dn + 2.0 * hAi * A, d11 = Cn + 2.0 * hBi * B;
+                const double inv = 1.0 / (A * A + B * B);
+                const double e00 = (A * d00 + B * d10) * inv, e01 = (A * d01 + B * d11) * inv;
+                const double e10 = (B * d00 - A * d10) * inv, e11 = (B * d01 - A * d11) * inv;
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    if (q == g) {
+                        R0[7 + 2 * q] += e00;
+                        R0[8 + 2 * q] += e01;
+                        R1[7 + 2 * q] += e10;
+                        R1[8 + 2 * q] += e11;
+                    }
+                R0[6] += (A * fr + B * fi) * inv;
+                R1[6] += (B * fr - A * fi) * inv;
+            }
+            // rhs = rt + Dt r1 ;  T = I - Dt Zr
+            {
+                const double2 ra = shfl_d2(r1, src0), rb = shfl_d2(r1, src1), rc = shfl_d2(r1, src2);
+                R0[6] = fma(R0[7], ra.x, R0[6]);
+                R0[6] = fma(R0[8], ra.y, R0[6]);
+                R0[6] = fma(R0[9], rb.x, R0[6]);
+                R0[6] = fma(R0[10], rb.y, R0[6]);
+                R0[6] = fma(R0[11], rc.x, R0[6]);
+                R0[6] = fma(R0[12], rc.y, R0[6]);
+                R1[6] = fma(R1[7], ra.x, R1[6]);
+                R1[6] = fma(R1[8], ra.y, R1[6]);
+                R1[6] = fma(R1[9], rb.x, R1[6]);
+                R1[6] = fma(R1[10], rb.y, R1[6]);
+                R1[6] = fma(R1[11], rc.x, R1[6]);
+                R1[6] = fma(R1[12], rc.y, R1[6]);
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                double t00 = (q == g) ? 1.0 : 0.0, t01 = 0.0, t10 = 0.0, t11 = (q == g) ? 1.0 : 0.0;
+#pragma unroll
+                for (int w = 0; w < 3; ++w) {
+                    const double2 z = __ldg(&st->z[3 * w + q]);      // Z[w][q]; zero where a phase is absent
+                    t00 -= R0[7 + 2 * w] * z.x + R0[8 + 2 * w] * z.y;
+                    t01 -= -R0[7 + 2 * w] * z.y + R0[8 + 2 * w] * z.x;
+                    t10 -= R1[7 + 2 * w] * z.x + R1[8 + 2 * w] * z.y;
+                    t11 -= -R1[7 + 2 * w] * z.y + R1[8 + 2 * w] * z.x;
+                }
+                R0[2 * q] = t00;
+                R0[2 * q + 1] = t01;
+                R1[2 * q] = t10;
+                R1[2 * q + 1] = t11;
+            }
+            // Gauss-Jordan over the six pivots; pivot rows stay unnormalised, 1/pivot is kept per row
+            double inv0 = 1.0, inv1 = 1.0;
+#pragma unroll
+            for (int kk = 0; kk < 6; ++kk) {
+                const int own = (kk >> 1) * 10 + j;                  // lane that owns pivot row kk
+                const bool mine = (kk >> 1) == g;
+                double pvr[13];
+#pragma unroll
+                for (int c = kk; c < 13; ++c) pvr[c] = __shfl_sync(0xffffffffu, (kk & 1) ? R1[c] : R0[c], own);
+                const double pinv = 1.0 / pvr[kk];
+                if (mine) {
+                    if (kk & 1) inv1 = pinv;
+                    else inv0 = pinv;
+                }
+                const double f0 = (mine && !(kk & 1)) ? 0.0 : R0[kk] * pinv;
+                const double f1 = (mine && (kk & 1)) ? 0.0 : R1[kk] * pinv;
+#pragma unroll
+                for (int c = kk + 1; c < 13; ++c) {
+                    R0[c] = fma(-f0, pvr[c], R0[c]);
+                    R1[c] = fma(-f1, pvr[c], R1[c]);
+                }
+            }
+            if (hb && active) {
+                double2* Wk = Ws + (long long)pos * FRONT_D2 * ld;
+                Wk[(long long)(18 + g) * ld] = make_double2(R0[6] * inv0, R1[6] * inv1);
+                Wk[(long long)(21 + g) * ld] = r1;
+                const int br[3] = {bv.x, bv.y, bv.z};
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    if (br[q] >= 0) {
+                        Wk[(long long)((2 * g) * 3 + q) * ld] = make_double2(R0[7 + 2 * q] * inv0, R0[8 + 2 * q] * inv0);
+                        Wk[(long long)((2 * g + 1) * 3 + q) * ld] = make_double2(R1[7 + 2 * q] * inv1, R1[8 + 2 * q] * inv1);
+                    }
+            }
+        }
+        // ================= slack rows (:84-109), stop rule, forward sweep =================
+        {
+            const double2 v0 = Xs[(long long)my_root * ld];
+            const double2 d = make_double2(v0.x - my_slack.x, v0.y - my_slack.y);
+            nanl |= (d.x != d.x) | (d.y != d.y);
+            fml = fmax(fml, fmax(fabs(d.x), fabs(d.y)));
+            if (active) {
+                DVs[(long long)my_root * ld] = d;
+                Xs[(long long)my_root * ld] = make_double2(v0.x - d.x, v0.y - d.y);
+            }
+        }
+        {   // max |F| and the NaN flag over the three phase lanes of the scenario
+            const double f1 = __shfl_sync(0xffffffffu, fml, src0), f2 = __shfl_sync(0xffffffffu, fml, src1),
+                         f3 = __shfl_sync(0xffffffffu, fml, src2);
+            const unsigned nb = __ballot_sync(0xffffffffu, nanl);
+            if (active) {
+                fm = fmax(f1, fmax(f2, f3));
+                nanflag = ((nb >> src0) | (nb >> src1) | (nb >> src2)) & 1u;
+            }
+        }
+        __syncwarp();       // the dv of a parent is read by the other two lanes of the scenario below
+        for (int pos = 0; pos < n_steps; ++pos) {
+            const Nr3Step* st = steps + pos;
+            const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_row));
+            const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_row));
+            const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_row));
+            const int my_b = pick3(bv, g), my_e = pick3(ev, g);
+            const bool hb = my_b >= 0;
+            const int br[3] = {bv.x, bv.y, bv.z}, pr[3] = {pv.x, pv.y, pv.z};
+            const double2* Wk = Ws + (long long)pos * FRONT_D2 * ld;
+            double2 di = ld_sel(hb, Wk + (long long)(18 + g) * ld, dummy);
+            const double2 r1f = ld_sel(hb, Wk + (long long)(21 + g) * ld, dummy);
+            const double2 xv = ld_sel(hb, Xs + (long long)my_b * ld, dummy);
+            const double2 xi = ld_sel(hb, Xs + (long long)my_e * ld, dummy);
+            double2 dvp[3], y0[3], y1[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const bool hq = hb && br[q] >= 0;
+                dvp[q] = ld_sel(hq && pr[q] >= 0, DVs + (long long)pr[q] * ld, dummy);
+                y0[q] = ld_sel(hq, Wk + (long long)((2 * g) * 3 + q) * ld, dummy);
+                y1[q] = ld_sel(hq, Wk + (long long)((2 * g + 1) * 3 + q) * ld, dummy);
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {                   // di = a - Y dv_p
+                di.x -= y0[q].x * dvp[q].x + y0[q].y * dvp[q].y;
+                di.y -= y1[q].x * dvp[q].x + y1[q].y * dvp[q].y;
+            }
+            const double2 d0 = shfl_d2(di, src0), d1 = shfl_d2(di, src1), d2 = shfl_d2(di, src2);
+            if (hb && active) {
+                const double2 zg0 = __ldg(&st->z[3 * g]), zg1 = __ldg(&st->z[3 * g + 1]), zg2 = __ldg(&st->z[3 * g + 2]);
+                const double2 dp = g == 0 ? dvp[0] : (g == 1 ? dvp[1] : dvp[2]);
+                double2 dv = make_double2(dp.x - r1f.x, dp.y - r1f.y);
+                dv.x -= zg0.x * d0.x - zg0.y * d0.y;
+                dv.y -= zg0.x * d0.y + zg0.y * d0.x;
+                dv.x -= zg1.x * d1.x - zg1.y * d1.y;
+                dv.y -= zg1.x * d1.y + zg1.y * d1.x;
+                dv.x -= zg2.x * d2.x - zg2.y * d2.y;
+                dv.y -= zg2.x * d2.y + zg2.y * d2.x;
+                Xs[(long long)my_b * ld] = make_double2(xv.x - dv.x, xv.y - dv.y);
+                Xs[(long long)my_e * ld] = make_double2(xi.x - di.x, xi.y - di.y);
+                DVs[(long long)my_b * ld] = dv;
+            }
+            __syncwarp();   // dv rows written above are the dvp of the children, read by all three lanes
+        }
+        if (active) {
+            ++it;
+            active = fm >= 1e-9 && !nanflag && it < maxiter;        // :618
+        }
+    }
+    if (owner && g == 0) {
+        iters_out[s] = it;
+        fmax_out[s] = nanflag ? __longlong_as_double(0x7ff8000000000000LL) : fm;
+        status_out[s] = nanflag ? GP_ST_NONFINITE : (fm < 1e-9 ? GP_ST_CONVERGED : (isinf(fm) ? GP_ST_NONFINITE : GP_ST_MAXITER));
+    }
+}
+
 // nr3_lib/map_output.py:24-27: |re| <= 1e-12 -> v = imag + 0j (imag lands in the REAL
 // slot); else |im| <= 1e-12 -> v = re + 0j.
 __device__ __forceinline__ double2 scrub(double2 v) {
@@ -760,7 +1059,10 @@ extern "C" int gp_nr3_create(const GpNr3Desc* d, int device, GpFeeder** out) {
         s.child_count = d->child_count[i];
         s.kind = d->kind[i];
         s.aux = -1;
-        if (s.kind == GP_EDGE_VR) s.aux = im->n_fronts++;
+        if (s.kind == GP_EDGE_VR) {
+            s.aux = im->n_fronts++;
+            im->lines_only = false;
+        }
         else if (s.kind != GP_EDGE_LINE) {
             delete im;
             return fail(GP_EINVAL, "gp_nr3_create: step %d: unknown edge kind %d", i, s.kind);
@@ -796,6 +1098,11 @@ extern "C" int gp_nr3_create(const GpNr3Desc* d, int device, GpFeeder** out) {
                 s.z[3 * p + q].y = d->z[((size_t)i * 9 + 3 * p + q) * 2 + 1];
             }
         }
+    }
+    {
+        int n3 = 0;
+        for (const Nr3Step& st : steps) n3 += st.bus_row[0] >= 0 && st.bus_row[1] >= 0 && st.bus_row[2] >= 0;
+        im->mostly_3ph = 6 * n3 >= 5 * d->n_steps;
     }
     std::vector<int4> childs((size_t)d->n_child);
     for (int c = 0; c < d->n_child; ++c) {
@@ -871,6 +1178,7 @@ void gp_nr3_destroy_impl(void* impl) {
 // gp_set_option("nr3_prefetch", d): -1 = automatic (on for batches that leave the SMs latency-bound)
 namespace gp {
 int g_nr3_prefetch = -1;
+int g_nr3_kernel = 0;
 }
 static int gp_nr3_prefetch_distance(int64_t S) {
     if (g_nr3_prefetch >= 0) return g_nr3_prefetch;
@@ -907,9 +1215,26 @@ extern "C" int gp_nr3_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
     const unsigned gx = (unsigned)((S + BLOCK - 1) / BLOCK);
     double2* W = (double2*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     double2* DV = W + (size_t)im->n_fronts * FRONT_D2 * ld;
-    nr3_solve_kernel<BLOCK><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_vrows, im->n_irows, S,
-                                                  ld, (const double2*)spu, (double2*)X, W, DV, iters, status,
-                                                  fmax, maxiter, gp_nr3_prefetch_distance(S));
+    // nr3_kernel option: 0 automatic (phase-parallel lanes on Line / Transformer feeders, one thread
+    // per scenario when the feeder has regulator edges), 1 thread per scenario, 2 phase-parallel
+    // Measured on B200 (round 1b): the phase-parallel kernel wins only where a thread per scenario
+    // leaves the SMs nearly empty AND most buses are three-phase - C3 (37-bus, 16,384 scenarios):
+    // 1.17 ms vs 1.46 ms; 123-bus (44 % single-phase buses) and batches past ~64 Ki scenarios are
+    // 8-60 % faster with a thread per scenario (fewer shuffles, full 512-byte row pieces).
+    const bool phase = g_nr3_kernel == 2 || (g_nr3_kernel == 0 && im->lines_only && S <= 65536 && im->mostly_3ph);
+    if (phase) {
+        if (!im->lines_only)
+            return fail(GP_EINVAL, "gp_nr3_solve_batch: the phase-parallel kernel does not handle regulator edges");
+        constexpr int PB = 128;
+        const long long warps = (S + 9) / 10;
+        const unsigned gp2 = (unsigned)((warps * 32 + PB - 1) / PB);
+        nr3_phase_kernel<PB><<<gp2, PB, 0, st>>>(im->d_steps, im->d_child, im->k, S, ld, (const double2*)spu,
+                                                 (double2*)X, W, DV, iters, status, fmax, maxiter);
+    } else {
+        nr3_solve_kernel<BLOCK><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_vrows, im->n_irows, S,
+                                                      ld, (const double2*)spu, (double2*)X, W, DV, iters, status,
+                                                      fmax, maxiter, gp_nr3_prefetch_distance(S));
+    }
     count_launch();
     GP_CUDA(cudaGetLastError());
     return GP_OK;

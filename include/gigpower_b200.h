@@ -109,6 +109,8 @@ int64_t gp_launch_count(void);
  * phase lanes per scenario; 3 = two-sweep streaming (state in HBM); 4 = table-driven on-chip
  * kernel (state in shared memory; the solve fails with GP_EINVAL if not even one warp fits);
  * 5 = the feeder-specialised on-chip kernel (GP_EINVAL unless gp_fbs_specialise succeeded).
+ * "nr3_kernel": 0 = automatic (default), 1 = one thread per scenario, 2 = three phase lanes per scenario
+ * (Line / Transformer feeders only; automatic for small batches of mostly three-phase feeders).
  * "fbs_prefetch" / "nr3_prefetch": L2 prefetch distance in tree steps of the streaming FBS kernel
  * (default 0) and of the NR3 kernel (default -1 = automatic: 2 for batches up to 65,536).
  * "host_chunks": number of pipeline chunks of gp_fbs_solve_batch_host (0 = automatic).

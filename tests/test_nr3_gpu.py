@@ -107,3 +107,30 @@ def test_regulator_feeders_batch_matches_dense_oracle(feeder, S, seed):
     assert np.array_equal(r.iterations, want['iterations'])
     assert rel_err(r.XNR, want['XNR']) <= TOL
     assert rel_err(r.V, want['V']) <= TOL and rel_err(r.I, want['I']) <= TOL and rel_err(r.Stx, want['Stx']) <= TOL
+
+
+@pytest.mark.parametrize('feeder,S', [('IEEE_13_Bus_allwye_noxfm_noreg', 777), ('IEEE_34_Bus_allwye_noxfm_noreg', 333),
+                                      ('IEEE_37_Bus_allwye_noxfm_noreg', 1029)])
+def test_both_nr3_kernels_meet_the_oracle_and_each_other(feeder, S):
+    """nr3_kernel = 1 (one thread per scenario, 6x6 LU in registers) and 2 (three phase lanes per
+    scenario, Gauss-Jordan over warp shuffles) solve the same Newton systems: both within 1e-9 of
+    the tree oracle with its iteration counts, and within 1e-11 of each other."""
+    from gigpower_b200 import _cabi
+    from oracle.nr3_tree import NR3TreeOracle
+    rng = np.random.Generator(np.random.PCG64(11))
+    o = NR3TreeOracle(load_model(feeder), ZIPS['test_zip'])
+    mult = rng.uniform(0.4, 1.6, size=(S, len(o.c.load_names)))
+    want = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+    s = _nr3(feeder)
+    res = {}
+    try:
+        for kern in (1, 2):
+            _cabi.check(_cabi.gp_set_option(b'nr3_kernel', kern))
+            res[kern] = s.solve_batch(load_mult=mult, outputs=('X', 'V', 'I'))
+    finally:
+        _cabi.gp_set_option(b'nr3_kernel', 0)
+    for kern in (1, 2):
+        assert np.array_equal(res[kern].iterations, want['iterations']), kern
+        assert (res[kern].status == 0).all()
+        assert rel_err(res[kern].XNR, want['XNR']) <= TOL, kern
+    assert rel_err(res[1].XNR, res[2].XNR) <= 1e-11
