@@ -316,13 +316,14 @@ def run_ours(args, wl):
         from gigpower_b200.solution_nr3 import SolutionNR3
         sol = SolutionNR3(feeder_file(feeder), device=local)
     rows, mult = make_scenarios(sol, S, seed + 1000 * rank, spec, first=rank * S)
+    _cabi.check(_cabi.gp_set_option(b'jit_i_global', args.jit_ig))
     sol._dev()
     _cabi.check(_cabi.gp_set_option(b'fbs_kernel', args.fbs_kernel))
     if args.prefetch is not None:
         _cabi.check(_cabi.gp_set_option(b'fbs_prefetch' if solver == 'fbs' else b'nr3_prefetch', args.prefetch))
     t = sol.tables
     h = sol._feeder.handle
-    if solver == 'fbs' and (args.fbs_kernel == 5 or (args.fbs_kernel == 0 and _cabi.gp_fbs_onchip_warps(h) >= sol.SPECIALISE_MIN_WARPS)):
+    if solver == 'fbs' and (args.fbs_kernel == 5 or (args.fbs_kernel == 0 and _cabi.gp_fbs_jit_warps(h) >= sol.SPECIALISE_MIN_WARPS)):
         sol.specialise()        # what solve_batch does by itself for a batch this size
     active = int(_cabi.gp_fbs_active_kernel(h)) if solver == 'fbs' else 0
     ld = S
@@ -635,6 +636,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--jit-ig', type=int, default=-1, choices=[-1, 0, 1],
+                    help='I rows of the specialised FBS kernel in global memory: -1 automatic, 0 no, 1 yes')
     ap.add_argument('--prefetch', type=int, default=None, help='L2 prefetch distance of the streaming FBS kernel / the NR3 kernel')
     ap.add_argument('--fbs-kernel', type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
                     help='0 = automatic (on-chip when the feeder fits in shared memory, else two-sweep streaming), '

@@ -73,7 +73,8 @@ gp_fbs_active_kernel = _sig('gp_fbs_active_kernel', C.c_int, [vp])
 gp_fbs_onchip_warps = _sig('gp_fbs_onchip_warps', C.c_int, [vp])
 gp_measure_fp64_peak = _sig('gp_measure_fp64_peak', C.c_int, [C.c_int, f64p])
 gp_fbs_specialise = _sig('gp_fbs_specialise', C.c_int, [vp])
-gp_fbs_jit_source = _sig('gp_fbs_jit_source', C.c_int64, [C.POINTER(GpFbsDesc), C.c_int32, C.c_char_p, C.c_int64])
+gp_fbs_jit_source = _sig('gp_fbs_jit_source', C.c_int64, [C.POINTER(GpFbsDesc), C.c_int32, C.c_int32, C.c_char_p, C.c_int64])
+gp_fbs_jit_warps = _sig('gp_fbs_jit_warps', C.c_int, [vp])
 gp_jit_compile = _sig('gp_jit_compile', C.c_int, [C.c_char_p, vp, C.c_int64, C.POINTER(C.c_int64)])
 gp_fbs_create = _sig('gp_fbs_create', C.c_int, [C.POINTER(GpFbsDesc), C.c_int, C.POINTER(vp)])
 gp_feeder_destroy = _sig('gp_feeder_destroy', C.c_int, [vp])
@@ -100,7 +101,7 @@ gp_nr3_map_output = _sig('gp_nr3_map_output', C.c_int,
                          [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
 
 EXPORTS = ['gp_version', 'gp_last_error', 'gp_launch_count', 'gp_set_option', 'gp_fbs_active_kernel',
-           'gp_fbs_onchip_warps', 'gp_measure_fp64_peak', 'gp_fbs_specialise', 'gp_fbs_jit_source',
+           'gp_fbs_onchip_warps', 'gp_measure_fp64_peak', 'gp_fbs_specialise', 'gp_fbs_jit_source', 'gp_fbs_jit_warps',
            'gp_jit_compile', 'gp_fbs_create', 'gp_feeder_destroy',
            'gp_fbs_solve_batch', 'gp_fbs_solve_post_batch', 'gp_fbs_post', 'gp_fbs_solve_batch_host', 'gp_der_rows', 'gp_vmag_summary', 'gp_nr3_create',
            'gp_nr3_workspace_bytes', 'gp_nr3_solve_batch', 'gp_nr3_map_output']

@@ -27,6 +27,7 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 extern int g_nr3_prefetch;     // gp_nr3.cu
 extern int g_nr3_kernel;
+static int g_jit_i_global = -1;    // gp_set_option("jit_i_global", -1|0|1): I rows of the specialised kernel in global memory
 static int g_host_zero_copy = 1;   // gp_set_option("host_zero_copy", 0|1): one-launch host path of the specialised kernel
 static int g_host_chunks = 0;  // gp_set_option("host_chunks", n): 0 = automatic
 // gp_set_option("fbs_kernel", v): 0 automatic (feeder-specialised on-chip kernel once built, else two-sweep), 1 fused
@@ -1019,6 +1020,10 @@ extern "C" int gp_set_option(const char* name, int value) {
         g_nr3_prefetch = value;
         return GP_OK;
     }
+    if (name && strcmp(name, "jit_i_global") == 0 && value >= -1 && value <= 1) {
+        g_jit_i_global = value;      // takes effect for feeders created afterwards
+        return GP_OK;
+    }
     if (name && strcmp(name, "host_zero_copy") == 0 && (value == 0 || value == 1)) {
         g_host_zero_copy = value;
         return GP_OK;
@@ -1033,6 +1038,11 @@ extern "C" int gp_set_option(const char* name, int value) {
 extern "C" int gp_fbs_onchip_warps(GpFeeder* f) {
     if (!f || f->kind != 1) return fail(GP_EINVAL, "gp_fbs_onchip_warps: not an FBS feeder handle");
     return ((FbsImpl*)f->impl)->onchip_warps;
+}
+
+extern "C" int gp_fbs_jit_warps(GpFeeder* f) {
+    if (!f || f->kind != 1) return fail(GP_EINVAL, "gp_fbs_jit_warps: not an FBS feeder handle");
+    return ((FbsImpl*)f->impl)->jit_plan_warps;
 }
 
 extern "C" int gp_fbs_active_kernel(GpFeeder* f) {
@@ -1165,7 +1175,7 @@ static int fbs_tables_from_desc(const GpFbsDesc* d, std::vector<FbsStep>& steps,
     return GP_OK;
 }
 
-extern "C" int64_t gp_fbs_jit_source(const GpFbsDesc* d, int32_t warps, char* buf, int64_t cap) {
+extern "C" int64_t gp_fbs_jit_source(const GpFbsDesc* d, int32_t warps, int32_t i_global, char* buf, int64_t cap) {
     if (!d || warps < 1 || warps > 16) return fail(GP_EINVAL, "gp_fbs_jit_source: bad argument");
     std::vector<FbsStep> steps;
     std::vector<int4> child4;
@@ -1181,7 +1191,8 @@ extern "C" int64_t gp_fbs_jit_source(const GpFbsDesc* d, int32_t warps, char* bu
             lines[9 * l + 3 + p] = d->line_tx_vrow[3 * l + p];
             lines[9 * l + 6 + p] = d->line_rx_vrow[3 * l + p];
         }
-    const std::string src = fbs_jit_source(steps, child4, lines, k, d->n_vrows, d->n_irows, d->n_srows, warps);
+    const std::string src = fbs_jit_source(steps, child4, lines, k, d->n_vrows, d->n_irows, d->n_srows, warps,
+                                           i_global != 0);
     if (src.empty()) return fail(GP_EJIT, "gp_fbs_jit_source: non-finite impedance in the descriptor");
     if (buf && cap > 0) {
         const size_t n = std::min((size_t)cap - 1, src.size());
@@ -1235,11 +1246,13 @@ extern "C" int gp_fbs_specialise(GpFeeder* f) {
     if (!f || f->kind != 1) return fail(GP_EINVAL, "gp_fbs_specialise: not an FBS feeder handle");
     FbsImpl* im = (FbsImpl*)f->impl;
     if (im->jit_kernel) return GP_OK;
-    if (im->onchip_warps < 1) return fail(GP_EJIT, "gp_fbs_specialise: the feeder does not fit the on-chip kernel");
+    if (im->jit_plan_warps < 1) return fail(GP_EJIT, "gp_fbs_specialise: the feeder does not fit the on-chip kernel");
     GP_CUDA(cudaSetDevice(f->device));
     GP_CUDA(cudaFree(0));       // make sure the primary context exists and is current
+    const int nw = im->jit_plan_warps;
+    const bool ig = im->jit_plan_ig;
     const std::string src = fbs_jit_source(im->h_steps, im->h_child, im->h_lines, im->k, im->n_vrows, im->n_irows,
-                                           im->n_srows, im->onchip_warps);
+                                           im->n_srows, nw, ig);
     if (src.empty()) return fail(GP_EJIT, "gp_fbs_specialise: non-finite impedance");
     std::vector<char> bin;
     std::string log;
@@ -1252,15 +1265,16 @@ extern "C" int gp_fbs_specialise(GpFeeder* f) {
     int cr = dr.ModuleLoadData(&mod, bin.data());
     if (cr != 0) return fail(GP_EJIT, "gp_fbs_specialise: cuModuleLoadData failed (%d)", cr);
     cr = dr.ModuleGetFunction(&fn, mod, "gp_fbs_jit_kernel");
-    const int smem = im->onchip_warps * (im->n_vrows + im->n_irows) * 512;
+    const int smem = nw * (im->n_vrows + (ig ? 0 : im->n_irows)) * 512;
     if (cr == 0) cr = dr.FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, smem);
     if (cr != 0) {
         dr.ModuleUnload(mod);
         return fail(GP_EJIT, "gp_fbs_specialise: kernel lookup / shared-memory opt-in failed (%d)", cr);
     }
+    im->jit_warps = nw;
+    im->jit_ig = ig;
     im->jit_module = mod;
     im->jit_kernel = fn;
-    im->jit_warps = im->onchip_warps;
     return GP_OK;
 }
 
@@ -1417,6 +1431,21 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
                 break;
             }
     }
+    {   // plan of the specialised kernel: I rows in shared memory next to V, or in global memory (the I
+        // array) when that lets more warps run per SM; at most 8 warps (about 240 registers per thread)
+        static const int sizes[] = {8, 6, 4, 3, 2, 1};
+        auto pick = [&](size_t per_warp) {
+            const int fit = (int)((size_t)smem_optin / per_warp);
+            for (int w : sizes)
+                if (w <= fit) return w;
+            return 0;
+        };
+        const int w_is = pick((size_t)(d->n_vrows + d->n_irows) * 512), w_ig = pick((size_t)d->n_vrows * 512);
+        // measured on B200: 13-bus 6 -> 8 warps: no gain (the register-passed currents spill);
+        // 34-bus 2 -> 4 warps: 1.21x; 37-bus 1 -> 3 warps: 1.49x  =>  only when it at least doubles the warps
+        im->jit_plan_ig = g_jit_i_global == 1 || (g_jit_i_global < 0 && w_ig >= 2 * w_is && w_ig > 0);
+        im->jit_plan_warps = im->jit_plan_ig ? w_ig : w_is;
+    }
     GpFeeder* f = new (std::nothrow) GpFeeder();
     f->device = device;
     f->kind = 1;
@@ -1464,19 +1493,19 @@ static int fbs_check(GpFeeder* f, int64_t S, int64_t ld, const char* who) {
 // mapped host memory too (the kernel's final stores go straight over PCIe).
 static int fbs_jit_launch(FbsImpl* im, int64_t S, int64_t ld, const double* spu, double* V, double* I,
                           int32_t* iters, int32_t* status, double* diff, double tol, int32_t maxiter,
-                          cudaStream_t st, double* Vmag, double* loss, void* stage) {
+                          cudaStream_t st, double* Vmag, double* loss, void* stage, double* Iout) {
     const long long n_tiles = (S + 31) / 32;
     const int nw = im->jit_warps;
     long long blocks = (n_tiles + nw - 1) / nw;
     if (blocks > im->n_sm) blocks = im->n_sm;
-    const unsigned smem = (unsigned)nw * (unsigned)(im->n_vrows + im->n_irows) * 512u;
+    const unsigned smem = (unsigned)nw * (unsigned)(im->n_vrows + (im->jit_ig ? 0 : im->n_irows)) * 512u;
     long long S_arg = S;
     double tol_arg = tol;
     int maxiter_arg = maxiter;
     unsigned ldb_arg = (unsigned)(ld * 16);
     void* args[] = {(void*)&spu, (void*)&V, (void*)&I, (void*)&iters, (void*)&status, (void*)&diff,
                     (void*)&S_arg, (void*)&ldb_arg, (void*)&tol_arg, (void*)&maxiter_arg, (void*)&im->d_sched,
-                    (void*)&Vmag, (void*)&loss, (void*)&stage};
+                    (void*)&Vmag, (void*)&loss, (void*)&stage, (void*)&Iout};
     const int cr = driver().LaunchKernel(im->jit_kernel, (unsigned)blocks, 1, 1, (unsigned)nw * 32, 1, 1, smem,
                                          (void*)st, args, nullptr);
     if (cr != 0) return fail(GP_ECUDA, "gp_fbs_solve_batch: cuLaunchKernel failed (%d)", cr);
@@ -1511,7 +1540,7 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     if ((g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) && (maxiter >= 1 || !im->jit_kernel)) {
         if (!im->jit_kernel)
             return fail(GP_EINVAL, "gp_fbs_solve_batch: fbs_kernel = 5 needs a successful gp_fbs_specialise");
-        rc = fbs_jit_launch(im, S, ld, spu, V, I, iters, status, diff, tol, maxiter, st, Vmag, loss, nullptr);
+        rc = fbs_jit_launch(im, S, ld, spu, V, I, iters, status, diff, tol, maxiter, st, Vmag, loss, nullptr, nullptr);
         if (rc) return rc;
         *fused = true;
     } else if (onchip) {
@@ -1673,7 +1702,8 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
             }
         }
         if (ok) {
-            const size_t need_stage = (size_t)im->n_srows * (size_t)ld * 16 + 256;
+            const size_t b_stage = ((size_t)im->n_srows * (size_t)ld * 16 + 255) & ~(size_t)255;
+            const size_t need_stage = b_stage + (im->jit_ig ? (size_t)im->n_irows * (size_t)ld * 16 : 0) + 256;
             if (need_stage > im->zc_bytes) {
                 if (im->d_zc) cudaFree(im->d_zc);
                 im->d_zc = nullptr;
@@ -1682,9 +1712,11 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
                 im->zc_bytes = need_stage;
             }
             if (!im->streams[0]) GP_CUDA(cudaStreamCreateWithFlags(&im->streams[0], cudaStreamNonBlocking));
-            rc = fbs_jit_launch(im, S, ld, (const double*)dp[0], (double*)dp[1], (double*)dp[2], (int32_t*)dp[5],
+            // I rows kept in global memory must stay on the device; the host copy is a second destination
+            double* I_state = im->jit_ig ? (double*)((char*)im->d_zc + b_stage) : (double*)dp[2];
+            rc = fbs_jit_launch(im, S, ld, (const double*)dp[0], (double*)dp[1], I_state, (int32_t*)dp[5],
                                 (int32_t*)dp[6], (double*)dp[7], tol, maxiter, im->streams[0], (double*)dp[3],
-                                (double*)dp[4], im->d_zc);
+                                (double*)dp[4], im->d_zc, im->jit_ig ? (double*)dp[2] : nullptr);
             if (rc) return rc;
             count_launch();
             GP_CUDA(cudaStreamSynchronize(im->streams[0]));

@@ -61,6 +61,9 @@ struct FbsImpl {
     void* jit_module = nullptr;   // CUmodule
     void* jit_kernel = nullptr;   // CUfunction
     int jit_warps = 0;
+    bool jit_ig = false;          // the specialised kernel keeps the I rows in global memory (the I array)
+    int jit_plan_warps = 0;       // warps per block gp_fbs_specialise will use (0 = feeder does not fit)
+    bool jit_plan_ig = false;
     void* d_zc = nullptr;         // device staging rows of the one-launch host path
     size_t zc_bytes = 0;
     // host staging for gp_fbs_solve_batch_host
@@ -74,7 +77,7 @@ struct FbsImpl {
 // gp_fbs_jit.cu: CUDA source of the feeder-specialised on-chip kernel, NVRTC compilation
 std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<int4>& child,
                            const std::vector<int>& lines, const FbsConst& k, int n_vrows, int n_irows, int n_srows,
-                           int nw);
+                           int nw, bool ig);
 int jit_compile(const std::string& src, std::vector<char>& cubin, std::string& log);
 
 }  // namespace gp

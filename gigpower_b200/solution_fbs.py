@@ -148,7 +148,7 @@ class SolutionFBS(Solution):
 
     def _maybe_specialise(self, S):
         if (self._specialised is None and S >= self.SPECIALISE_MIN_BATCH
-                and _cabi.gp_fbs_onchip_warps(self._feeder.handle) >= self.SPECIALISE_MIN_WARPS):
+                and _cabi.gp_fbs_jit_warps(self._feeder.handle) >= self.SPECIALISE_MIN_WARPS):
             self.specialise()
 
     def pack_spu(self, spu) -> np.ndarray:

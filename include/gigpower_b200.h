@@ -136,13 +136,19 @@ int gp_fbs_onchip_warps(GpFeeder* f);
  *                         with a message if NVRTC or the driver is unavailable - the handle then
  *                         keeps using the table-driven kernels
  *   gp_fbs_jit_source     host only: the CUDA source for a descriptor and `warps` warps per
- *                         block; returns its length (excluding the NUL) or a negative GP_E*;
+ *                         block, with the I rows in shared memory (i_global = 0) or in global
+ *                         memory (1); returns its length (excluding the NUL) or a negative GP_E*;
  *                         copies at most cap-1 characters into buf when buf is not NULL
+ *   gp_fbs_jit_warps      warps per block gp_fbs_specialise uses for this handle (0 = the feeder
+ *                         does not fit): the V rows of a warp's 32 scenarios take shared memory, the
+ *                         I rows too unless keeping them in the (L2-resident) I array lets more
+ *                         warps run ("jit_i_global" option: -1 automatic, 0, 1)
  *   gp_jit_compile        host only: NVRTC-compile a source for sm_100a; the cubin size goes
  *                         to *cubin_bytes, the cubin itself into cubin (cap bytes) when not NULL
  */
 int gp_fbs_specialise(GpFeeder* f);
-int64_t gp_fbs_jit_source(const GpFbsDesc* desc, int32_t warps, char* buf, int64_t cap);
+int64_t gp_fbs_jit_source(const GpFbsDesc* desc, int32_t warps, int32_t i_global, char* buf, int64_t cap);
+int gp_fbs_jit_warps(GpFeeder* f);
 int gp_jit_compile(const char* source, void* cubin, int64_t cap, int64_t* cubin_bytes);
 
 /*

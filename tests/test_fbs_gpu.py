@@ -309,3 +309,44 @@ def test_host_entry_point_one_launch_path_matches_staged_path():
     V3 = np.empty((t.n_vrows, S), dtype=complex)
     it3, _, _ = s.solve_batch_host(rows, V3)
     assert np.array_equal(V3, out[1][3]) and np.array_equal(it3, out[1][0])
+
+
+@pytest.mark.parametrize('feeder', ['IEEE_13_Bus_allwye_noxfm_noreg', 'IEEE_13_Bus_allwye', 'IEEE_34_Bus_allwye_noxfm_noreg',
+                                    'IEEE_37_Bus_allwye'])
+def test_specialised_kernel_with_i_rows_in_shared_or_global_memory(feeder):
+    """The specialised kernel keeps the I rows either in shared memory or in the (L2-resident) I
+    array ("jit_i_global"); both placements must reproduce the streaming kernel, through the device
+    entry point and through the one-launch host entry point, with and without an I output."""
+    import torch
+    from gigpower_b200 import _cabi
+    rng = np.random.Generator(np.random.PCG64(31))
+    ref = None
+    try:
+        for ig in (0, 1):
+            _cabi.check(_cabi.gp_set_option(b'jit_i_global', ig))
+            s = _fbs(feeder)
+            mult = np.random.Generator(np.random.PCG64(31)).uniform(0.5, 1.5, size=(2500, s.circuit.loads.num_elements))
+            assert s.specialise()
+            if ref is None:
+                _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 3))
+                ref = s.solve_batch(load_mult=mult, outputs=('V', 'I', 'Vmag', 'loss'))
+            _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 5))
+            for _ in range(2):
+                r = s.solve_batch(load_mult=mult, outputs=('V', 'I', 'Vmag', 'loss'))
+                assert np.array_equal(r.iterations, ref.iterations) and np.array_equal(r.status, ref.status)
+                assert rel_err(r.V, ref.V) <= 1e-12 and rel_err(r.I, ref.I) <= 1e-12
+                assert rel_err(r.Vmag, ref.Vmag) <= 1e-12 and rel_err(r.losses, ref.losses) <= 1e-12
+            rows = np.ascontiguousarray(s.load_weights() @ mult.T)
+            t = s.tables
+            spu_h = torch.from_numpy(rows).pin_memory()
+            V = torch.empty((t.n_vrows, 2500), dtype=torch.complex128).pin_memory()
+            I = torch.empty((t.n_irows, 2500), dtype=torch.complex128).pin_memory()
+            it, st, df = s.solve_batch_host(spu_h, V, I)
+            assert np.array_equal(it, ref.iterations)
+            assert np.array_equal(V.numpy(), np.asarray(r.V_rows)) and np.array_equal(I.numpy(), np.asarray(r.I_rows))
+            V2 = torch.empty((t.n_vrows, 2500), dtype=torch.complex128).pin_memory()
+            s.solve_batch_host(spu_h, V2)
+            assert np.array_equal(V2.numpy(), V.numpy())
+    finally:
+        _cabi.gp_set_option(b'jit_i_global', -1)
+        _cabi.gp_set_option(b'fbs_kernel', 0)

@@ -85,9 +85,9 @@ def test_product_never_imports_oracle():
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', txt, flags=re.M), f
 
 
-@pytest.mark.parametrize('feeder,warps', [('IEEE_13_Bus_allwye_noxfm_noreg', 6), ('IEEE_13_Bus_allwye', 6),
-                                          ('IEEE_37_Bus_allwye', 1)])
-def test_specialised_kernel_source_generates_and_compiles(feeder, warps):
+@pytest.mark.parametrize('feeder,warps,ig', [('IEEE_13_Bus_allwye_noxfm_noreg', 6, 0), ('IEEE_13_Bus_allwye', 8, 1),
+                                             ('IEEE_37_Bus_allwye', 1, 0), ('IEEE_34_Bus_allwye_noxfm_noreg', 4, 1)])
+def test_specialised_kernel_source_generates_and_compiles(feeder, warps, ig):
     """Host-only half of gp_fbs_specialise: the generator writes the feeder's sweep schedule as
     straight-line CUDA and NVRTC compiles it for sm_100a (no GPU needed for either)."""
     import ctypes as C
@@ -96,10 +96,10 @@ def test_specialised_kernel_source_generates_and_compiles(feeder, warps):
     from gigpower_b200.flatten import flatten_fbs
     t = flatten_fbs(Circuit(load_model(feeder)))
     d, keep = _cabi.make_fbs_desc(t)
-    n = _cabi.gp_fbs_jit_source(C.byref(d), warps, None, 0)
+    n = _cabi.gp_fbs_jit_source(C.byref(d), warps, ig, None, 0)
     assert n > 0
     buf = C.create_string_buffer(n + 1)
-    assert _cabi.gp_fbs_jit_source(C.byref(d), warps, buf, n + 1) == n
+    assert _cabi.gp_fbs_jit_source(C.byref(d), warps, ig, buf, n + 1) == n
     src = buf.value.decode()
     assert len(src) == n and 'gp_fbs_jit_kernel' in src and f'#define NV {t.n_vrows}' in src
     # one forward and one backward block per step, in sweep order
@@ -113,5 +113,5 @@ def test_specialised_kernel_source_generates_and_compiles(feeder, warps):
     _cabi.check(_cabi.gp_jit_compile(buf.value, cubin, size.value, C.byref(size)))
     assert cubin.raw[:4] == b'\x7fELF'
     # bad arguments are errors, not crashes
-    assert _cabi.gp_fbs_jit_source(C.byref(d), 0, None, 0) < 0
+    assert _cabi.gp_fbs_jit_source(C.byref(d), 0, ig, None, 0) < 0
     assert _cabi.gp_jit_compile(b'this is not CUDA', None, 0, C.byref(size)) == -4
