@@ -317,6 +317,7 @@ def run_ours(args, wl):
         sol = SolutionNR3(feeder_file(feeder), device=local)
     rows, mult = make_scenarios(sol, S, seed + 1000 * rank, spec, first=rank * S)
     _cabi.check(_cabi.gp_set_option(b'jit_i_global', args.jit_ig))
+    _cabi.check(_cabi.gp_set_option(b'nr3_kernel', args.nr3_kernel))
     sol._dev()
     _cabi.check(_cabi.gp_set_option(b'fbs_kernel', args.fbs_kernel))
     if args.prefetch is not None:
@@ -638,6 +639,8 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--jit-ig', type=int, default=-1, choices=[-1, 0, 1],
                     help='I rows of the specialised FBS kernel in global memory: -1 automatic, 0 no, 1 yes')
+    ap.add_argument('--nr3-kernel', type=int, default=0, choices=[0, 1, 2],
+                    help='0 automatic, 1 one thread per scenario, 2 three phase lanes per scenario')
     ap.add_argument('--prefetch', type=int, default=None, help='L2 prefetch distance of the streaming FBS kernel / the NR3 kernel')
     ap.add_argument('--fbs-kernel', type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
                     help='0 = automatic (on-chip when the feeder fits in shared memory, else two-sweep streaming), '

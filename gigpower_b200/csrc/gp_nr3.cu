@@ -733,6 +733,88 @@ nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             const int my_b = pick3(bv, g), my_p = pick3(pv, g), my_e = pick3(ev, g), my_l = pick3(lv, g);
             const bool hb = my_b >= 0;
             const int child_count = bv.w, child_begin = pv.w;
+            if ((bv.x >= 0) + (bv.y >= 0) + (bv.z >= 0) == 1) {
+                // single-phase bus: the system is the identity outside one 2x2 block, which the lane of
+                // that phase solves alone (no shuffles); the other two lanes have nothing to do
+                if (hb) {
+                    const double2 v1 = ld_sel(true, Xs + (long long)my_b * ld, dummy);
+                    double2 in1 = ld_sel(true, Xs + (long long)my_e * ld, dummy);
+                    const double2 vp1 = ld_sel(my_p >= 0, Xs + (long long)my_p * ld, dummy);
+                    const double2 sp1 = ld_sel(my_l >= 0, spu_s + (long long)my_l * ld, dummy);
+                    const double2 z = g == 0 ? __ldg(&st->z[0]) : (g == 1 ? __ldg(&st->z[4]) : __ldg(&st->z[8]));
+                    const double cap = g == 0 ? __ldg(&st->cap[0]) : (g == 1 ? __ldg(&st->cap[1]) : __ldg(&st->cap[2]));
+                    double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0, ra = 0.0, rb2 = 0.0;
+                    double2 r1s = make_double2(vp1.x - v1.x, vp1.y - v1.y);
+                    r1s.x -= z.x * in1.x - z.y * in1.y;
+                    r1s.y -= z.x * in1.y + z.y * in1.x;
+                    nanl |= (r1s.x != r1s.x) | (r1s.y != r1s.y);
+                    fml = fmax(fml, fmax(fabs(r1s.x), fabs(r1s.y)));
+                    for (int c = 0; c < child_count; ++c) {
+                        const int4 ch = __ldg(childs + child_begin + c);
+                        const int cr = pick3c(ch, g);
+                        const double2* Wc = Ws + (long long)ch.x * FRONT_D2 * ld;
+                        const bool hc = cr >= 0;
+                        const double2 ic = ld_sel(hc, Xs + (long long)cr * ld, dummy);
+                        const double2 ac = ld_sel(hc, Wc + (long long)(18 + g) * ld, dummy);
+                        const double2 y0c = ld_sel(hc, Wc + (long long)((2 * g) * 3 + g) * ld, dummy);
+                        const double2 y1c = ld_sel(hc, Wc + (long long)((2 * g + 1) * 3 + g) * ld, dummy);
+                        in1.x -= ic.x;
+                        in1.y -= ic.y;
+                        ra += ac.x;
+                        rb2 += ac.y;
+                        d00 += y0c.x;
+                        d01 += y0c.y;
+                        d10 += y1c.x;
+                        d11 += y1c.y;
+                    }
+                    {
+                        const double A = v1.x, B = v1.y, Cn = in1.x, Dn = in1.y;
+                        const double pl = sp1.x, ql = sp1.y;
+                        const double hAr = -pl * my_cA, hBr = -pl * my_cB, b0r = -pl * k.betaS;
+                        const double hAi = -ql * my_cA + cap * my_cA;
+                        const double hBi = -ql * my_cB + cap * my_cB;
+                        const double b0i = (-ql * k.betaS) + (cap * k.betaS);
+                        const double fr = A * Cn + B * Dn + hAr * A * A + hBr * B * B + b0r;
+                        const double fi = B * Cn - A * Dn + hAi * A * A + hBi * B * B + b0i;
+                        nanl |= (fr != fr) | (fi != fi);
+                        fml = fmax(fml, fmax(fabs(fr), fabs(fi)));
+                        const double e00 = Cn + 2.0 * hAr * A, e01 = Dn + 2.0 * hBr * B;
+                        const double e10 = -Dn + 2.0 * hAi * A, e11 = Cn + 2.0 * hBi * B;
+                        const double inv = 1.0 / (A * A + B * B);
+                        d00 += (A * e00 + B * e10) * inv;
+                        d01 += (A * e01 + B * e11) * inv;
+                        d10 += (B * e00 - A * e10) * inv;
+                        d11 += (B * e01 - A * e11) * inv;
+                        ra += (A * fr + B * fi) * inv;
+                        rb2 += (B * fr - A * fi) * inv;
+                    }
+                    ra = fma(d00, r1s.x, ra);
+                    ra = fma(d01, r1s.y, ra);
+                    rb2 = fma(d10, r1s.x, rb2);
+                    rb2 = fma(d11, r1s.y, rb2);
+                    const double t00 = 1.0 - (d00 * z.x + d01 * z.y), t01 = 0.0 - (-d00 * z.y + d01 * z.x);
+                    const double t10 = 0.0 - (d10 * z.x + d11 * z.y), t11 = 1.0 - (-d10 * z.y + d11 * z.x);
+                    const double i0 = 1.0 / t00, mlu = t10 * i0;
+                    const double i1 = 1.0 / fma(-mlu, t01, t11);
+                    double xa = ra, xb = fma(-mlu, ra, rb2);
+                    xb *= i1;
+                    xa = fma(-t01, xb, xa) * i0;
+                    double y0a = d00, y0b = fma(-mlu, d00, d10);
+                    y0b *= i1;
+                    y0a = fma(-t01, y0b, y0a) * i0;
+                    double y1a = d01, y1b = fma(-mlu, d01, d11);
+                    y1b *= i1;
+                    y1a = fma(-t01, y1b, y1a) * i0;
+                    if (active) {
+                        double2* Wk1 = Ws + (long long)pos * FRONT_D2 * ld;
+                        Wk1[(long long)(18 + g) * ld] = make_double2(xa, xb);
+                        Wk1[(long long)(21 + g) * ld] = r1s;
+                        Wk1[(long long)((2 * g) * 3 + g) * ld] = make_double2(y0a, y1a);
+                        Wk1[(long long)((2 * g + 1) * 3 + g) * ld] = make_double2(y0b, y1b);
+                    }
+                }
+                continue;
+            }
             const double2 v = ld_sel(hb, Xs + (long long)my_b * ld, dummy);
             double2 inet = ld_sel(hb, Xs + (long long)my_e * ld, dummy);
             const double2 vpar = ld_sel(hb && my_p >= 0, Xs + (long long)my_p * ld, dummy);
@@ -908,6 +990,31 @@ nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             const bool hb = my_b >= 0;
             const int br[3] = {bv.x, bv.y, bv.z}, pr[3] = {pv.x, pv.y, pv.z};
             const double2* Wk = Ws + (long long)pos * FRONT_D2 * ld;
+            if ((bv.x >= 0) + (bv.y >= 0) + (bv.z >= 0) == 1) {       // single-phase bus: its lane alone
+                if (hb) {
+                    const int my_p = pick3(pv, g);
+                    const double2 dvp1 = ld_sel(my_p >= 0, DVs + (long long)my_p * ld, dummy);
+                    double2 di1 = ld_sel(true, Wk + (long long)(18 + g) * ld, dummy);
+                    const double2 r1f1 = ld_sel(true, Wk + (long long)(21 + g) * ld, dummy);
+                    const double2 xv1 = ld_sel(true, Xs + (long long)my_b * ld, dummy);
+                    const double2 xi1 = ld_sel(true, Xs + (long long)my_e * ld, dummy);
+                    const double2 ya = ld_sel(true, Wk + (long long)((2 * g) * 3 + g) * ld, dummy);
+                    const double2 yb = ld_sel(true, Wk + (long long)((2 * g + 1) * 3 + g) * ld, dummy);
+                    const double2 z = g == 0 ? __ldg(&st->z[0]) : (g == 1 ? __ldg(&st->z[4]) : __ldg(&st->z[8]));
+                    di1.x -= ya.x * dvp1.x + ya.y * dvp1.y;
+                    di1.y -= yb.x * dvp1.x + yb.y * dvp1.y;
+                    double2 dv1 = make_double2(dvp1.x - r1f1.x, dvp1.y - r1f1.y);
+                    dv1.x -= z.x * di1.x - z.y * di1.y;
+                    dv1.y -= z.x * di1.y + z.y * di1.x;
+                    if (active) {
+                        Xs[(long long)my_b * ld] = make_double2(xv1.x - dv1.x, xv1.y - dv1.y);
+                        Xs[(long long)my_e * ld] = make_double2(xi1.x - di1.x, xi1.y - di1.y);
+                        DVs[(long long)my_b * ld] = dv1;
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
             double2 di = ld_sel(hb, Wk + (long long)(18 + g) * ld, dummy);
             const double2 r1f = ld_sel(hb, Wk + (long long)(21 + g) * ld, dummy);
             const double2 xv = ld_sel(hb, Xs + (long long)my_b * ld, dummy);
@@ -1217,11 +1324,11 @@ extern "C" int gp_nr3_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
     double2* DV = W + (size_t)im->n_fronts * FRONT_D2 * ld;
     // nr3_kernel option: 0 automatic (phase-parallel lanes on Line / Transformer feeders, one thread
     // per scenario when the feeder has regulator edges), 1 thread per scenario, 2 phase-parallel
-    // Measured on B200 (round 1b): the phase-parallel kernel wins only where a thread per scenario
-    // leaves the SMs nearly empty AND most buses are three-phase - C3 (37-bus, 16,384 scenarios):
-    // 1.17 ms vs 1.46 ms; 123-bus (44 % single-phase buses) and batches past ~64 Ki scenarios are
-    // 8-60 % faster with a thread per scenario (fewer shuffles, full 512-byte row pieces).
-    const bool phase = g_nr3_kernel == 2 || (g_nr3_kernel == 0 && im->lines_only && S <= 65536 && im->mostly_3ph);
+    // Measured on B200 (round 1b): the phase-parallel kernel wins where a thread per scenario leaves
+    // the SMs nearly empty - C3 (37-bus, 16,384 scenarios) 1.15 ms vs 1.48 ms, 123-bus 17,520 scenarios
+    // 3.38 ms vs 3.72 ms; once a thread per scenario fills the machine (8 warps x 148 SMs = 37,888
+    // scenarios) it is 25-35 % faster (fewer shuffles, full 512-byte row pieces).
+    const bool phase = g_nr3_kernel == 2 || (g_nr3_kernel == 0 && im->lines_only && S <= 32768);
     if (phase) {
         if (!im->lines_only)
             return fail(GP_EINVAL, "gp_nr3_solve_batch: the phase-parallel kernel does not handle regulator edges");
