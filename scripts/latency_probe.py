@@ -13,12 +13,13 @@ if not os.path.exists(p):
     p = os.path.join(REPO, 'gigpower_b200', 'feeders', feeder)
 sol = SolutionFBS(p)
 sol._dev()
+sol.specialise()
 t = sol.tables
 dev = torch.device('cuda', 0)
 rng = np.random.Generator(np.random.PCG64(13))
 W = sol.load_weights()
 SIZES = [int(x) for x in os.environ.get('GP_SIZES', '320,2560,16384,65536,262144').split(',')]
-KERNELS = [int(x) for x in os.environ.get('GP_KERNELS', '3,4').split(',')]
+KERNELS = [int(x) for x in os.environ.get('GP_KERNELS', '3,5').split(',')]
 for S in SIZES:
     mult = rng.uniform(0.5, 1.5, size=(S, W.shape[1]))
     mult[:] = mult[0]                      # identical scenarios: every lane runs the same iteration count
