@@ -66,3 +66,90 @@ def test_nr3_big_feeder_matches_tree_oracle(path, S, seed, lo, hi):
     r = SolutionNR3(path, zip_v=np.asarray(ZIPS['test_zip'])).solve_batch(load_mult=mult, outputs=('X',))
     assert np.array_equal(r.iterations, want['iterations'])
     assert rel_err(r.XNR, want['XNR']) <= 1e-9
+
+
+def _der_rows(sol, S, first=0):
+    import sys
+    sys.path.insert(0, REPO)
+    import bench
+    return bench.make_der_rows(sol.load_weights().sum(axis=1), S, first)
+
+
+@pytest.mark.gpu
+def test_config_c4_full_size_fbs_batch_independence_and_oracle_sample():
+    """BASELINE config C4 at its per-GPU size (123-bus, 140,160 hour x DER scenarios): every scenario
+    converges; a random sample re-solved as its own small batch is bit-identical (a scenario's
+    result does not depend on the batch around it) and matches the oracle at 1e-9 with its
+    iteration counts; losses are positive real power."""
+    from gigpower_b200.solution_fbs import SolutionFBS
+    from oracle.gp_oracle import FBSOracle
+    sol = SolutionFBS(F123)
+    S = 140160
+    rows = _der_rows(sol, S)
+    r = sol.solve_batch(spu_rows=rows, outputs=('V', 'loss'), return_device=True)
+    status, iters = r.status.cpu().numpy(), r.iterations.cpu().numpy()
+    assert (status == 0).all() and iters.min() >= 3 and iters.max() <= 12
+    loss = r.loss.cpu().numpy()
+    assert (loss.real > 0).all() and np.isfinite(loss).all()
+    pick = np.sort(np.random.Generator(np.random.PCG64(4)).choice(S, 384, replace=False))
+    Vs = r.V_rows[:, pick].cpu().numpy()
+    r2 = sol.solve_batch(spu_rows=np.ascontiguousarray(rows[:, pick]), outputs=('V', 'loss'))
+    assert np.array_equal(r2.iterations, iters[pick])
+    assert np.array_equal(np.asarray(r2.V_rows), Vs) and np.array_equal(r2.losses, loss[pick])
+    o = FBSOracle(read_dss(F123), ZIPS['test_zip'])
+    lmask = o.c.zip_mask * o.c.bus_pm
+    b, p = np.nonzero(lmask)
+    spu = np.zeros((len(pick), o.c.nb, 3), dtype=complex)
+    spu[:, b, p] = rows[:, pick].T
+    want = o.solve(spu)
+    assert np.array_equal(r2.iterations, want['iterations'])
+    assert rel_err(r2.V, want['V']) <= 1e-9
+    assert rel_err(r2.losses, (want['Stx'] - want['Srx']).sum(axis=(1, 2))) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_config_c5_full_size_fbs_sample_matches_oracle():
+    """BASELINE config C5 at its per-GPU size (2,541-bus feeder, 131,072 scenarios, 22 GB of state):
+    all converge in the same number of sweeps as the oracle's sample, which matches at 1e-9."""
+    import torch
+    from gigpower_b200.solution_fbs import SolutionFBS
+    from oracle.gp_oracle import FBSOracle
+    sol = SolutionFBS(F2500)
+    S = 131072
+    nl = sol.circuit.loads.num_elements
+    rng = np.random.Generator(np.random.PCG64(2500))
+    W = sol.load_weights()
+    mult = rng.uniform(0.3, 0.9, size=(S, nl))
+    rows = torch.from_numpy(W).cuda() @ torch.from_numpy(mult.T).to(torch.complex128).cuda()
+    r = sol.solve_batch(spu_rows=rows, outputs=('V',), return_device=True)
+    status, iters = r.status.cpu().numpy(), r.iterations.cpu().numpy()
+    assert (status == 0).all()
+    pick = np.sort(rng.choice(S, 24, replace=False))
+    Vs = sol.solve_batch(spu_rows=rows[:, pick].contiguous(), outputs=('V',))
+    assert np.array_equal(np.asarray(Vs.V_rows), r.V_rows[:, pick].cpu().numpy())
+    o = FBSOracle(read_dss(F2500), ZIPS['test_zip'])
+    want = o.solve(o.c.spu_matrix(o.c.load_kw * mult[pick], o.c.load_kvar * mult[pick]))
+    assert np.array_equal(iters[pick], want['iterations'])
+    assert rel_err(Vs.V, want['V']) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_config_c4_nr3_batch_independence_and_oracle_sample():
+    """C4's NR3 share (123-bus, 17,520 scenarios, phase-parallel kernel) and the same rows in a batch
+    large enough for the thread-per-scenario kernel: both match the tree oracle on a sample."""
+    from gigpower_b200.solution_nr3 import SolutionNR3
+    from oracle.nr3_tree import NR3TreeOracle
+    sol = SolutionNR3(F123)
+    o = NR3TreeOracle(read_dss(F123), ZIPS['test_zip'])
+    lmask = o.c.zip_mask * o.c.bus_pm
+    b, p = np.nonzero(lmask)
+    for S in (17520, 40000):
+        rows = _der_rows(sol, S, first=8760 * 7)
+        r = sol.solve_batch(spu_rows=rows, outputs=('X',))
+        assert (r.status == 0).all()
+        pick = np.sort(np.random.Generator(np.random.PCG64(S)).choice(S, 128, replace=False))
+        spu = np.zeros((len(pick), o.c.nb, 3), dtype=complex)
+        spu[:, b, p] = rows[:, pick].T
+        want = o.solve(spu)
+        assert np.array_equal(r.iterations[pick], want['iterations'])
+        assert rel_err(r.XNR[pick], want['XNR']) <= 1e-9
