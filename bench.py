@@ -182,6 +182,15 @@ def make_scenarios(sol, S, seed, spec, first=0):
     return np.ascontiguousarray(W @ mult.T), mult
 
 
+def make_probe_inputs(workload, S=0):
+    """(SolutionFBS, packed spu rows) of a bench workload, for the scripts under scripts/."""
+    from gigpower_b200.solution_fbs import SolutionFBS
+    feeder, solver, S0, seed, spec, _ = WORKLOADS[workload]
+    sol = SolutionFBS(feeder_file(feeder))
+    rows, _ = make_scenarios(sol, S or S0, seed, spec)
+    return sol, rows
+
+
 # --------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port on the host cores
 # --------------------------------------------------------------------------

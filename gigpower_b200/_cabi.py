@@ -88,6 +88,18 @@ gp_fbs_solve_batch_host = _sig('gp_fbs_solve_batch_host', C.c_int,
                                [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp,
                                 C.c_double, C.c_int32])
 
+
+
+class GpSolveExtras(C.Structure):
+    """Optional per-scenario inputs of a solve (include/gigpower_b200.h: GpSolveExtras)."""
+    _fields_ = [('gamma_dev', vp), ('warm_start', C.c_int32), ('reserved', C.c_int32)]
+
+
+gp_gamma_rows = _sig('gp_gamma_rows', C.c_int, [vp])
+gp_fbs_solve_batch_ex = _sig('gp_fbs_solve_batch_ex', C.c_int,
+                             [vp, C.c_int64, C.c_int64, vp, C.POINTER(GpSolveExtras), vp, vp, vp, vp, vp, vp, vp,
+                              C.c_double, C.c_int32, vp])
+
 gp_der_rows = _sig('gp_der_rows', C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                              vp, vp, vp, vp, vp, vp, vp])
 gp_vmag_summary = _sig('gp_vmag_summary', C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int32, vp, C.c_double,
@@ -97,6 +109,9 @@ gp_nr3_create = _sig('gp_nr3_create', C.c_int, [C.POINTER(GpNr3Desc), C.c_int, C
 gp_nr3_workspace_bytes = _sig('gp_nr3_workspace_bytes', C.c_int64, [vp, C.c_int64])
 gp_nr3_solve_batch = _sig('gp_nr3_solve_batch', C.c_int,
                           [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32, vp])
+gp_nr3_solve_batch_ex = _sig('gp_nr3_solve_batch_ex', C.c_int,
+                             [vp, C.c_int64, C.c_int64, vp, C.POINTER(GpSolveExtras), vp, vp, vp, vp, vp, C.c_int64,
+                              C.c_int32, vp])
 gp_nr3_map_output = _sig('gp_nr3_map_output', C.c_int,
                          [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
 
@@ -104,7 +119,19 @@ EXPORTS = ['gp_version', 'gp_last_error', 'gp_launch_count', 'gp_set_option', 'g
            'gp_fbs_onchip_warps', 'gp_measure_fp64_peak', 'gp_fbs_specialise', 'gp_fbs_jit_source', 'gp_fbs_jit_warps',
            'gp_jit_compile', 'gp_fbs_create', 'gp_feeder_destroy',
            'gp_fbs_solve_batch', 'gp_fbs_solve_post_batch', 'gp_fbs_post', 'gp_fbs_solve_batch_host', 'gp_der_rows', 'gp_vmag_summary', 'gp_nr3_create',
-           'gp_nr3_workspace_bytes', 'gp_nr3_solve_batch', 'gp_nr3_map_output']
+           'gp_nr3_workspace_bytes', 'gp_nr3_solve_batch', 'gp_nr3_map_output',
+           'gp_gamma_rows', 'gp_fbs_solve_batch_ex', 'gp_nr3_solve_batch_ex']
+
+
+def make_extras(gamma=None, warm_start=False):
+    """GpSolveExtras for a device tensor of regulator ratios ``[n_gamma_rows, ld]`` float64 and / or a
+    warm start; returns None when neither is asked for."""
+    if gamma is None and not warm_start:
+        return None
+    ex = GpSolveExtras()
+    ex.gamma_dev = gamma.data_ptr() if gamma is not None else None
+    ex.warm_start = 1 if warm_start else 0
+    return ex
 
 
 def check(rc: int):

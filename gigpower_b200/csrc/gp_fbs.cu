@@ -27,6 +27,7 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 extern int g_nr3_prefetch;     // gp_nr3.cu
 extern int g_nr3_kernel;
+int nr3_gamma_rows(GpFeeder* f);   // gp_nr3.cu
 static int g_jit_i_global = -1;    // gp_set_option("jit_i_global", -1|0|1): I rows of the specialised kernel in global memory
 static int g_host_zero_copy = 1;   // gp_set_option("host_zero_copy", 0|1): one-launch host path of the specialised kernel
 static int g_host_chunks = 0;  // gp_set_option("host_chunks", n): 0 = automatic
@@ -53,11 +54,18 @@ __device__ __forceinline__ double cabs2(double2 v, double& a) {
 //         L1 leaves L1 to the step table that every warp re-reads.
 //   SMem: V and I rows in shared memory, [row][32 lanes] per warp (512-byte row pitch: lane l reads
 //         bytes 16 l .. 16 l + 15 of a row, conflict-free 128-bit accesses); spu rows stay in HBM.
-struct GMem {
+//   TAPS: the accessor also carries this scenario's column of the per-scenario regulator ratios
+//         (GpSolveExtras.gamma_dev, [row][ld] doubles); the plain instance has no such member.
+template <bool TAPS>
+struct GMemT {
+    static constexpr bool kTaps = TAPS;
     char* V;
     char* I;
     const char* S;
     unsigned ldb;
+    const char* G;
+    __device__ __forceinline__ bool hasG() const { return TAPS && G != nullptr; }
+    __device__ __forceinline__ double ldG(int r) const { return __ldg(reinterpret_cast<const double*>(G + (size_t)(unsigned)r * (size_t)(ldb >> 1))); }
     __device__ __forceinline__ double2 ldV(int r) const { return __ldcg(reinterpret_cast<const double2*>(V + (size_t)(unsigned)r * (size_t)ldb)); }
     __device__ __forceinline__ double2 ldI(int r) const { return __ldcg(reinterpret_cast<const double2*>(I + (size_t)(unsigned)r * (size_t)ldb)); }
     __device__ __forceinline__ double2 ldS(int r) const { return __ldcg(reinterpret_cast<const double2*>(S + (size_t)(unsigned)r * (size_t)ldb)); }
@@ -69,8 +77,12 @@ struct GMem {
     __device__ __forceinline__ void pfI(int r) const { if (r >= 0) pf(I + (size_t)(unsigned)r * (size_t)ldb); }
     __device__ __forceinline__ void pfS(int r) const { if (r >= 0) pf(S + (size_t)(unsigned)r * (size_t)ldb); }
 };
+using GMem = GMemT<false>;
 
 struct SMem {
+    static constexpr bool kTaps = false;
+    __device__ __forceinline__ bool hasG() const { return false; }
+    __device__ __forceinline__ double ldG(int) const { return 0.0; }
     double2* V;         // this lane's column of the warp's V rows (shared memory)
     double2* I;
     const char* S;      // this scenario's column of the spu rows (global memory)
@@ -208,8 +220,11 @@ __device__ __forceinline__ void fbs_fwd_step(const FbsStep* __restrict__ st, con
     if (kind == GP_EDGE_VR) {   // vr_forward :138-160
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
-            const double g = __ldg(&st->gamma[p]);
-            if (g != 0.0 && brow[p] >= 0) m.stV(brow[p], make_double2(g * Vp[p].x, g * Vp[p].y));
+            double g = __ldg(&st->gamma[p]);
+            if (g != 0.0 && brow[p] >= 0) {
+                if (m.hasG()) g = m.ldG(__ldg(&st->gam_row[p]));        // this scenario's tap position
+                m.stV(brow[p], make_double2(g * Vp[p].x, g * Vp[p].y));
+            }
         }
         return;
     }
@@ -262,7 +277,8 @@ __device__ __forceinline__ void fbs_bwd_step(const FbsStep* __restrict__ st, con
         for (int p = 0; p < 3; ++p) {
             const double g = __ldg(&st->gamma[p]);
             if (g != 0.0 && prow[p] >= 0) {
-                const double ig = __ldg(&st->inv_gamma[p]);
+                double ig = __ldg(&st->inv_gamma[p]);
+                if (m.hasG()) ig = 1.0 / m.ldG(__ldg(&st->gam_row[p]));     // 1/gamma * V (:205)
                 m.stV(prow[p], make_double2(ig * Vb[p].x, ig * Vb[p].y));
             }
         }
@@ -347,18 +363,23 @@ __device__ __forceinline__ int fbs_status(bool converged, double diff) {
     return converged ? GP_ST_CONVERGED : ((diff != diff || isinf(diff)) ? GP_ST_NONFINITE : GP_ST_MAXITER);
 }
 
-template <int BLOCK>
+// EX = the instance behind gp_fbs_solve_batch_ex: per-scenario regulator ratios (gam != NULL) and / or a
+// warm start (V and I hold an earlier solution).  The plain instance carries neither argument.
+template <int BLOCK, bool EX>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)   // <= 64 registers: 1024 resident threads per SM
 fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ child_irow,
                  FbsConst k, int n_steps, int n_vrows, int n_irows, long long S, unsigned ldb,
                  const char* __restrict__ spu, char* __restrict__ V,
                  char* __restrict__ I, int* __restrict__ iters_out,
                  int* __restrict__ status_out, double* __restrict__ diff_out, double tol,
-                 int maxiter, int PF, const int* __restrict__ unfed, int n_unfed) {
+                 int maxiter, int PF, const int* __restrict__ unfed, int n_unfed,
+                 const char* __restrict__ gam, int warm) {
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (s >= S) return;
-    const GMem m{V + s * 16, I + s * 16, spu + s * 16, ldb};
+    typedef GMemT<EX> GMem;
+    const GMem m{V + s * 16, I + s * 16, spu + s * 16, ldb, (EX && gam) ? gam + s * 8 : nullptr};
     const double2 zero = make_double2(0.0, 0.0);
+    if (EX && warm) n_unfed = 0;    // warm start: every V and I row keeps the earlier solution
 
     // flat start (solution.py:108-125): V = I = 0.  Every I row is written by the first backward
     // sweep before anything reads it again, and the first forward sweep knows I = 0 without
@@ -366,7 +387,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
     // regulator) must hold their initial zero.  Zeroing just those saves one write of every
     // V and I row and one read of every I row per solve.
     for (int j = 0; j < n_unfed; ++j) m.stV(__ldg(unfed + j), zero);
-    if (maxiter < 1) {          // no sweep at all: the outputs are the flat start itself
+    if (maxiter < 1 && !(EX && warm)) {   // no sweep at all: the outputs are the flat start itself
         for (int r = 0; r < n_vrows; ++r) m.stV(r, zero);
         for (int r = 0; r < n_irows; ++r) m.stI(r, zero);
     }
@@ -388,7 +409,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
                 m.pfI(ev.y);
                 m.pfI(ev.z);
             }
-            if (it == 0) fbs_fwd_step<GMem, true>(steps + pos, m);
+            if (it == 0 && !(EX && warm)) fbs_fwd_step<GMem, true>(steps + pos, m);
             else fbs_fwd_step<GMem, false>(steps + pos, m);
         }
         for (int pos = n_steps - 1; pos >= 0; --pos) {                                 // :104-121
@@ -1140,6 +1161,13 @@ static int fbs_tables_from_desc(const GpFbsDesc* d, std::vector<FbsStep>& steps,
             }
         }
     }
+    // rows of a per-scenario gamma array: regulated (step, phase) pairs in step, then phase order
+    {
+        int g = 0;
+        for (int i = 0; i < d->n_steps; ++i)
+            for (int p = 0; p < 3; ++p)
+                steps[i].gam_row[p] = (steps[i].kind == GP_EDGE_VR && steps[i].gamma[p] != 0.0) ? g++ : -1;
+    }
     // fast mask (fwd_fast / bwd_fast): a Line/Transformer edge whose phases are exactly the bus
     // phases, all present on the parent.  Stored above the kind byte.
     for (int i = 0; i < d->n_steps; ++i) {
@@ -1296,6 +1324,8 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
     im->n_srows = d->n_srows;
     im->n_child = d->n_child;
     im->n_lines = d->n_lines;
+    for (const FbsStep& st : steps)
+        for (int p = 0; p < 3; ++p) im->n_grows += st.gam_row[p] >= 0;
     im->k = k0;
     im->h_steps = steps;
     im->h_child = child4;
@@ -1515,12 +1545,18 @@ static int fbs_jit_launch(FbsImpl* im, int64_t S, int64_t ld, const double* spu,
 // Launch the solve kernel; *fused is set when the kernel also produced Vmag / loss.
 static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* spu, double* V, double* I,
                             int32_t* iters, int32_t* status, double* diff, double tol, int32_t maxiter,
-                            void* stream, double* Vmag, double* loss, bool* fused) {
+                            void* stream, double* Vmag, double* loss, bool* fused,
+                            const GpSolveExtras* ex = nullptr) {
     *fused = false;
     int rc = fbs_check(f, S, ld, "gp_fbs_solve_batch");
     if (rc) return rc;
     if (S == 0) return GP_OK;
     FbsImpl* im = (FbsImpl*)f->impl;
+    const char* gam = ex ? (const char*)ex->gamma_dev : nullptr;
+    const int warm = ex ? ex->warm_start : 0;
+    if (warm != 0 && warm != 1) return fail(GP_EINVAL, "gp_fbs_solve_batch_ex: warm_start must be 0 or 1");
+    if (gam && im->n_grows == 0) gam = nullptr;     // no regulators: nothing to read
+    const bool extras = gam || warm;
     if (!V || !I || !iters || !status || !diff || (!spu && im->n_srows > 0))
         return fail(GP_EINVAL, "gp_fbs_solve_batch: null buffer");
     if (ld * 16 >= ((int64_t)1 << 32))
@@ -1537,7 +1573,14 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     // warps per SM - and runs only on request.)
     const bool onchip = g_fbs_kernel == 4;
     // (the specialised kernel always runs at least one sweep: maxiter < 1 goes to the table-driven ones)
-    if ((g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) && (maxiter >= 1 || !im->jit_kernel)) {
+    if (extras) {
+        // per-scenario ratios / warm start: the streaming kernel's EX instance (the on-chip kernels
+        // bake the ratios into their code or tables and always start flat)
+        fbs_solve_kernel<BLOCK, true><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
+                                                            im->n_irows, S, ldb, (const char*)spu, (char*)V,
+                                                            (char*)I, iters, status, diff, tol, maxiter, g_fbs_prefetch,
+                                                            im->d_unfed, im->n_unfed, gam, warm);
+    } else if ((g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) && (maxiter >= 1 || !im->jit_kernel)) {
         if (!im->jit_kernel)
             return fail(GP_EINVAL, "gp_fbs_solve_batch: fbs_kernel = 5 needs a successful gp_fbs_specialise");
         rc = fbs_jit_launch(im, S, ld, spu, V, I, iters, status, diff, tol, maxiter, st, Vmag, loss, nullptr, nullptr);
@@ -1587,10 +1630,10 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
         else GP_DFS(64);
 #undef GP_DFS
     } else {
-        fbs_solve_kernel<BLOCK><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
-                                                      im->n_irows, S, ldb, (const char*)spu, (char*)V,
-                                                      (char*)I, iters, status, diff, tol, maxiter, g_fbs_prefetch,
-                                                      im->d_unfed, im->n_unfed);
+        fbs_solve_kernel<BLOCK, false><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
+                                                             im->n_irows, S, ldb, (const char*)spu, (char*)V,
+                                                             (char*)I, iters, status, diff, tol, maxiter, g_fbs_prefetch,
+                                                             im->d_unfed, im->n_unfed, nullptr, 0);
     }
     count_launch();
     GP_CUDA(cudaGetLastError());
@@ -1615,6 +1658,20 @@ extern "C" int gp_fbs_solve_post_batch(GpFeeder* f, int64_t S, int64_t ld, const
     int rc = fbs_solve_launch(f, S, ld, spu, V, I, iters, status, diff, tol, maxiter, stream, Vmag, loss, &fused);
     if (rc || fused || S == 0 || (!Vmag && !loss)) return rc;
     return gp_fbs_post(f, S, ld, spu, V, I, nullptr, Vmag, nullptr, nullptr, loss, stream);
+}
+
+extern "C" int gp_fbs_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const GpSolveExtras* ex,
+                                     double* V, double* I, int32_t* iters, int32_t* status, double* diff,
+                                     double* Vmag, double* loss, double tol, int32_t maxiter, void* stream) {
+    bool fused;
+    int rc = fbs_solve_launch(f, S, ld, spu, V, I, iters, status, diff, tol, maxiter, stream, Vmag, loss, &fused, ex);
+    if (rc || fused || S == 0 || (!Vmag && !loss)) return rc;
+    return gp_fbs_post(f, S, ld, spu, V, I, nullptr, Vmag, nullptr, nullptr, loss, stream);
+}
+
+extern "C" int gp_gamma_rows(GpFeeder* f) {
+    if (!f || !f->impl) return fail(GP_EINVAL, "gp_gamma_rows: null handle");
+    return f->kind == 1 ? ((FbsImpl*)f->impl)->n_grows : nr3_gamma_rows(f);
 }
 
 extern "C" int gp_fbs_post(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const double* V,

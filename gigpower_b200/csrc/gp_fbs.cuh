@@ -24,8 +24,10 @@ struct __align__(16) FbsStep {
     double inv_gamma[3];
     double pad3;
     double2 z[9];
+    int gam_row[3];   // row of the per-scenario gamma array (GpSolveExtras.gamma_dev) per regulated phase, else -1
+    int pad4;
 };
-static_assert(sizeof(FbsStep) == 64 + 32 + 32 + 32 + 144, "FbsStep layout");
+static_assert(sizeof(FbsStep) == 64 + 32 + 32 + 32 + 144 + 16, "FbsStep layout");
 
 struct FbsConst {
     int root_vrow[3];
@@ -37,6 +39,7 @@ struct FbsConst {
 
 struct FbsImpl {
     int n_steps = 0, n_vrows = 0, n_irows = 0, n_srows = 0, n_child = 0, n_lines = 0;
+    int n_grows = 0;              // regulated (step, phase) pairs = rows of a per-scenario gamma array
     FbsStep* d_steps = nullptr;
     int4* d_child = nullptr;  // [n_child] {I rows of the child edge, 0}
     int* d_lines = nullptr;   // [n_lines][9] irow, tx vrow, rx vrow

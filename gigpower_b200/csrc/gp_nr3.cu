@@ -43,8 +43,10 @@ struct __align__(16) Nr3Step {
     double gamma[3];
     double pad2;
     double2 z[9];
+    int gam_row[3];     // row of the per-scenario gamma array (GpSolveExtras.gamma_dev) per regulated phase, else -1
+    int pad3;
 };
-static_assert(sizeof(Nr3Step) == 80 + 32 + 32 + 144, "Nr3Step layout");
+static_assert(sizeof(Nr3Step) == 80 + 32 + 32 + 144 + 16, "Nr3Step layout");
 
 struct Nr3Const {
     int root_row[3];
@@ -63,6 +65,7 @@ struct Nr3Impl {
     int* d_vrow_srow = nullptr;   // [n_vrows]
     double* d_vrow_cap = nullptr; // [n_vrows]
     Nr3Const k;
+    int n_grows = 0;    // regulated (step, phase) pairs = rows of a per-scenario gamma array
     int n_fronts = 0;   // n_steps + one extra slot per regulator step
     bool lines_only = true;   // no regulator step: eligible for the phase-parallel kernel
     bool mostly_3ph = false;  // at least 5 of 6 non-root buses carry all three phases
@@ -111,15 +114,20 @@ __device__ __forceinline__ double2 ld_sel(bool have, const double2* p, const dou
     return have ? t : make_double2(0.0, 0.0);
 }
 
-template <int BLOCK>
+// EX = the instance behind gp_nr3_solve_batch_ex: per-scenario regulator ratios (gam != NULL) and / or a
+// warm start (X holds an earlier solution, solution_nr3.py:598).  The plain instance has neither.
+template <int BLOCK, bool EX>
 __global__ void __launch_bounds__(BLOCK)
 nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ childs, Nr3Const k,
                  int n_vrows, int n_irows, long long S, long long ld,
                  const double2* __restrict__ spu, double2* __restrict__ X,
                  double2* __restrict__ W, double2* __restrict__ DV, int* __restrict__ iters_out,
-                 int* __restrict__ status_out, double* __restrict__ fmax_out, int maxiter, int PF) {
+                 int* __restrict__ status_out, double* __restrict__ fmax_out, int maxiter, int PF,
+                 const double* __restrict__ gam, int warm) {
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (s >= S) return;
+    const double* Gs = (EX && gam) ? gam + s : nullptr;
+    const bool flat = !(EX && warm);
     const double2* spu_s = spu + s;
     double2* Xs = X + s;
     double2* Ws = W + s;
@@ -137,7 +145,7 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
     // flat start (solution_nr3.py:37-82): every bus-phase at VSLACK, currents 0.
     // Absent phases are not stored: their rows of J are identity rows whose first
     // Newton step sets them to exactly 0 (:417-419, 159-161).
-    for (int pos = 0; pos < n_steps; ++pos) {
+    for (int pos = 0; flat && pos < n_steps; ++pos) {
         const int4 bv = __ldg(reinterpret_cast<const int4*>(steps[pos].bus_row));
         const int4 ev = __ldg(reinterpret_cast<const int4*>(steps[pos].edge_row));
         const int4 ov = __ldg(reinterpret_cast<const int4*>(steps[pos].out_row));
@@ -156,7 +164,8 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
     double fm = 1e99;
     bool nanflag = false;
     while (fm >= 1e-9 && !nanflag && it < maxiter) {        // :618
-        fm = (it == 0) ? k.f0_absent : 0.0;
+        // (absent phases sit at VSLACK only in the flat start; an earlier solution has them at 0)
+        fm = (it == 0 && flat) ? k.f0_absent : 0.0;
         // ================= backward sweep: residual, Jacobian blocks, elimination =========
         for (int pos = n_steps - 1; pos >= 0; --pos) {
             if (PF > 0 && pos >= PF) {
@@ -383,6 +392,7 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                     g[p] = 0.0;
                     if (brow[p] < 0) continue;
                     g[p] = __ldg(&st->gamma[p]);
+                    if (EX && Gs) g[p] = __ldg(Gs + (long long)__ldg(&st->gam_row[p]) * ld);
                     vm[p] = vpar[p];
                     io[p] = Xs[(long long)orow[p] * ld];
                     ra[p] = make_double2(-g[p] * vm[p].x + v[p].x, -g[p] * vm[p].y + v[p].y);
@@ -599,7 +609,8 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                 double2 gdv[3];
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
-                    const double g = __ldg(&st->gamma[p]);
+                    double g = __ldg(&st->gamma[p]);
+                    if (EX && Gs && brow[p] >= 0) g = __ldg(Gs + (long long)__ldg(&st->gam_row[p]) * ld);
                     gdv[p] = make_double2(g * dvp[p].x, g * dvp[p].y);
                 }
 #pragma unroll
@@ -1206,6 +1217,9 @@ extern "C" int gp_nr3_create(const GpNr3Desc* d, int device, GpFeeder** out) {
             }
         }
     }
+    for (Nr3Step& st : steps)      // rows of a per-scenario gamma array: step, then phase order
+        for (int p = 0; p < 3; ++p)
+            st.gam_row[p] = (st.kind == GP_EDGE_VR && st.gamma[p] != 0.0) ? im->n_grows++ : -1;
     {
         int n3 = 0;
         for (const Nr3Step& st : steps) n3 += st.bus_row[0] >= 0 && st.bus_row[1] >= 0 && st.bus_row[2] >= 0;
@@ -1286,6 +1300,7 @@ void gp_nr3_destroy_impl(void* impl) {
 namespace gp {
 int g_nr3_prefetch = -1;
 int g_nr3_kernel = 0;
+int nr3_gamma_rows(GpFeeder* f) { return ((Nr3Impl*)f->impl)->n_grows; }
 }
 static int gp_nr3_prefetch_distance(int64_t S) {
     if (g_nr3_prefetch >= 0) return g_nr3_prefetch;
@@ -1307,10 +1322,21 @@ extern "C" int64_t gp_nr3_workspace_bytes(GpFeeder* f, int64_t ld) {
 extern "C" int gp_nr3_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const double* spu, double* X,
                                   int32_t* iters, int32_t* status, double* fmax, void* workspace,
                                   int64_t workspace_bytes, int32_t maxiter, void* stream) {
+    return gp_nr3_solve_batch_ex(f, S, ld, spu, nullptr, X, iters, status, fmax, workspace, workspace_bytes, maxiter,
+                                 stream);
+}
+
+extern "C" int gp_nr3_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const GpSolveExtras* ex,
+                                     double* X, int32_t* iters, int32_t* status, double* fmax, void* workspace,
+                                     int64_t workspace_bytes, int32_t maxiter, void* stream) {
     int rc = nr3_check(f, S, ld, "gp_nr3_solve_batch");
     if (rc) return rc;
     if (S == 0) return GP_OK;
     Nr3Impl* im = (Nr3Impl*)f->impl;
+    const double* gam = (ex && im->n_grows > 0) ? ex->gamma_dev : nullptr;
+    const int warm = ex ? ex->warm_start : 0;
+    if (warm != 0 && warm != 1) return fail(GP_EINVAL, "gp_nr3_solve_batch_ex: warm_start must be 0 or 1");
+    const bool extras = gam || warm;
     if (!X || !iters || !status || !fmax || !workspace || (!spu && im->n_srows > 0))
         return fail(GP_EINVAL, "gp_nr3_solve_batch: null buffer");
     if (workspace_bytes < gp_nr3_workspace_bytes(f, ld))
@@ -1328,8 +1354,12 @@ extern "C" int gp_nr3_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
     // the SMs nearly empty - C3 (37-bus, 16,384 scenarios) 1.15 ms vs 1.48 ms, 123-bus 17,520 scenarios
     // 3.38 ms vs 3.72 ms; once a thread per scenario fills the machine (8 warps x 148 SMs = 37,888
     // scenarios) it is 25-35 % faster (fewer shuffles, full 512-byte row pieces).
-    const bool phase = g_nr3_kernel == 2 || (g_nr3_kernel == 0 && im->lines_only && S <= 32768);
-    if (phase) {
+    const bool phase = !extras && (g_nr3_kernel == 2 || (g_nr3_kernel == 0 && im->lines_only && S <= 32768));
+    if (extras) {
+        nr3_solve_kernel<BLOCK, true><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_vrows, im->n_irows, S,
+                                                            ld, (const double2*)spu, (double2*)X, W, DV, iters, status,
+                                                            fmax, maxiter, gp_nr3_prefetch_distance(S), gam, warm);
+    } else if (phase) {
         if (!im->lines_only)
             return fail(GP_EINVAL, "gp_nr3_solve_batch: the phase-parallel kernel does not handle regulator edges");
         constexpr int PB = 128;
@@ -1338,9 +1368,9 @@ extern "C" int gp_nr3_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const doub
         nr3_phase_kernel<PB><<<gp2, PB, 0, st>>>(im->d_steps, im->d_child, im->k, S, ld, (const double2*)spu,
                                                  (double2*)X, W, DV, iters, status, fmax, maxiter);
     } else {
-        nr3_solve_kernel<BLOCK><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_vrows, im->n_irows, S,
-                                                      ld, (const double2*)spu, (double2*)X, W, DV, iters, status,
-                                                      fmax, maxiter, gp_nr3_prefetch_distance(S));
+        nr3_solve_kernel<BLOCK, false><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_vrows, im->n_irows, S,
+                                                             ld, (const double2*)spu, (double2*)X, W, DV, iters, status,
+                                                             fmax, maxiter, gp_nr3_prefetch_distance(S), nullptr, 0);
     }
     count_launch();
     GP_CUDA(cudaGetLastError());

@@ -72,6 +72,22 @@ def topo_sort(bus_names: List[str], adj: Dict[str, List[str]]) -> List[str]:
     return order
 
 
+def gamma_row_map(kind: np.ndarray, vr_gamma: np.ndarray, gamma_vr: np.ndarray):
+    """Rows of a per-scenario regulator-ratio array (``GpSolveExtras.gamma_dev``): one per regulated
+    (step, phase), numbered in step order and, inside a step, phase order - the rule the library
+    applies to ``vr_gamma`` (``gp_gamma_rows``).  Returns ``grow [n_steps, 3]`` (row or -1) and
+    ``grow_vr [n_rows]``, the index of the regulator (order of ``circuit.voltage_regulators``) whose
+    tap sets that row."""
+    grow = np.full(vr_gamma.shape, -1, np.int32)
+    owner = []
+    for i in range(vr_gamma.shape[0]):
+        for p in range(3):
+            if kind[i] == EDGE_VR and vr_gamma[i, p] != 0.0:
+                grow[i, p] = len(owner)
+                owner.append(int(gamma_vr[i, p]))
+    return grow, np.array(owner, dtype=np.int32)
+
+
 def reverse_adjacency(adj: Dict[str, List[str]]) -> Dict[str, List[str]]:
     rev: Dict[str, List[str]] = {}
     for node, nbrs in adj.items():
@@ -117,6 +133,8 @@ class FbsTables:
     reverse_adj: Dict[str, List[str]] = field(default=None)
     tolerance: float = 0.0
     depth: int = 0
+    grow: np.ndarray = field(default=None)      # [n_steps,3] row of a per-scenario gamma array or -1
+    grow_vr: np.ndarray = field(default=None)   # [n_grows] regulator index behind each gamma row
 
 
 def flatten_fbs(c: Circuit) -> FbsTables:
@@ -178,6 +196,8 @@ def flatten_fbs(c: Circuit) -> FbsTables:
              child_count=np.zeros(n_steps, np.int32), z=np.zeros((n_steps, 3, 3, 2)),
              cappu=np.zeros(S3), vr_gamma=np.zeros(S3))
     child_rows: List[np.ndarray] = []
+    gamma_vr = np.full(S3, -1, np.int32)
+    vr_index = {id(vr): i for i, vr in enumerate(c.voltage_regulators.get_elements())}
     depth_of = {root: 0}
     for pos, name in enumerate(order[1:]):
         parents = rev.get(name, [])
@@ -198,6 +218,7 @@ def flatten_fbs(c: Circuit) -> FbsTables:
             for vr in e[1]:
                 for p in vr.get_ph_idx_matrix():
                     t['vr_gamma'][pos, p] = vr.gamma
+                    gamma_vr[pos, p] = vr_index[id(vr)]
         else:
             t['kind'][pos] = EDGE_LINE
             t['edge_irow'][pos] = irow[e[1]]
@@ -218,7 +239,9 @@ def flatten_fbs(c: Circuit) -> FbsTables:
     line_irow = irow[:nl].copy()
     tx = np.array([bidx[e.tx] for e in c.lines.get_elements()], dtype=int)
     rx = np.array([bidx[e.rx] for e in c.lines.get_elements()], dtype=int)
+    grow, grow_vr = gamma_row_map(t['kind'], t['vr_gamma'], gamma_vr)
     return FbsTables(
+        grow=grow, grow_vr=grow_vr,
         n_steps=n_steps, n_vrows=n_vrows, n_irows=n_irows, n_srows=n_srows, n_lines=nl,
         child_irow=child_irow, root_vrow=vrow[rb].copy(), root_load_srow=srow[rb].copy(),
         root_cappu=cappu[rb].copy(), vref=np.stack([vref.real, vref.imag], axis=1).reshape(-1).copy(),
@@ -271,6 +294,8 @@ class Nr3Tables:
     N: int = 0                                    # length of XNR
     xnr_index: np.ndarray = field(default=None)  # [n_vrows+n_irows] even XNR index of each packed row
     order: List[int] = field(default=None)
+    grow: np.ndarray = field(default=None)       # [n_steps,3] row of a per-scenario gamma array or -1
+    grow_vr: np.ndarray = field(default=None)    # [n_grows] regulator index behind each gamma row
 
 
 def flatten_nr3(c: Circuit) -> Nr3Tables:
@@ -287,11 +312,13 @@ def flatten_nr3(c: Circuit) -> Nr3Tables:
     edges = [dict(kind=EDGE_LINE, tx=e.tx, rx=e.rx, pm=np.asarray(e.phase_matrix), el=e)
              for e in c.lines.get_elements() + c.transformers.get_elements()]
     vr_edges, cnt = {}, 0
+    vr_index = {id(vr): i for i, vr in enumerate(c.voltage_regulators.get_elements())}
     for vr in c.voltage_regulators.get_elements():        # VR-phase counter in (VR, phase) order (:471-514)
         e = vr_edges.setdefault(vr.key, dict(kind=EDGE_VR, tx=vr.tx, rx=vr.rx, pm=np.zeros(3, dtype=int),
-                                             gamma=np.zeros(3), slot={}))
+                                             gamma=np.zeros(3), slot={}, vr=np.full(3, -1, np.int32)))
         for p in vr.get_ph_idx_matrix():
             e['pm'][p], e['gamma'][p], e['slot'][int(p)] = 1, vr.gamma, cnt
+            e['vr'][p] = vr_index[id(vr)]
             cnt += 1
     vr_lines = cnt
     edges += list(vr_edges.values())
@@ -359,6 +386,7 @@ def flatten_nr3(c: Circuit) -> Nr3Tables:
              child_begin=np.zeros(n_steps, np.int32), child_count=np.zeros(n_steps, np.int32),
              z=np.zeros((n_steps, 3, 3, 2)), cappu=np.zeros(S3), vr_gamma=np.zeros(S3))
     child_step, child_rows = [], []
+    gamma_vr = np.full(S3, -1, np.int32)
     for pos, b in enumerate(order[1:]):
         e = edges[edge_in[b]]
         if not np.array_equal(e['pm'], bus_pm[b]):
@@ -368,6 +396,7 @@ def flatten_nr3(c: Circuit) -> Nr3Tables:
         t['load_srow'][pos], t['cappu'][pos], t['kind'][pos] = srow[b], cappu[b], e['kind']
         if e['kind'] == EDGE_VR:
             t['vr_gamma'][pos] = e['gamma']
+            gamma_vr[pos] = e['vr']
         elif e['el'].kind == 'Line':   # rmat/xmat (line.py:48-73); identical numbers to FZpu on existing phases
             R, X = e['el'].rmat.reshape(3, 3), e['el'].xmat.reshape(3, 3)
             pm = e['pm']
@@ -431,4 +460,6 @@ def flatten_nr3(c: Circuit) -> Nr3Tables:
         f0_absent=float(f0), line_irow=irow[:nl].copy(),
         line_tx_vrow=vrow[tx].reshape(-1, 3).copy() if nl else np.zeros((0, 3), np.int32),
         line_rx_vrow=vrow[rx].reshape(-1, 3).copy() if nl else np.zeros((0, 3), np.int32),
-        vrow=vrow, irow=irow, srow=srow, N=N, xnr_index=xnr, order=order, **t)
+        vrow=vrow, irow=irow, srow=srow, N=N, xnr_index=xnr, order=order,
+        grow=gamma_row_map(t['kind'], t['vr_gamma'], gamma_vr)[0],
+        grow_vr=gamma_row_map(t['kind'], t['vr_gamma'], gamma_vr)[1], **t)

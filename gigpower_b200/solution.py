@@ -68,6 +68,36 @@ class Solution:
                 else getattr(self.circuit, group).num_elements
             setattr(self, param, np.zeros((rows, len(cols)), dtype=dtype))
 
+    # ---- per-scenario regulator taps ---------------------------
+    def gamma_rows_from_taps(self, taps, S, dev):
+        """Per-scenario tap numbers -> the ``[n_gamma_rows, S]`` float64 device tensor behind
+        ``GpSolveExtras.gamma_dev``.  ``taps``: ``[S, n_regulators]`` integers in the order of
+        ``circuit.voltage_regulators`` (NumPy or torch), or a dict ``{regcontrol name: [S] or scalar}``
+        (regulators left out keep the tap they were built with).  gamma = 0.9 + 0.2 (tap + 16) / 32
+        with the reference's operation order (voltage_regulator.py:23-39), evaluated on the device."""
+        import torch
+        t = self.tables
+        vrs = self.circuit.voltage_regulators.get_elements()
+        if len(t.grow_vr) == 0:
+            return None
+        if isinstance(taps, dict):
+            low = {str(k).lower(): v for k, v in taps.items()}
+            unknown = set(low) - {vr.__name__ for vr in vrs}
+            if unknown:
+                raise KeyError(f'no such regulator(s): {sorted(unknown)}')
+            cols = [torch.as_tensor(np.asarray(low.get(vr.__name__, vr.tap)), dtype=torch.float64).expand(S)
+                    if np.ndim(low.get(vr.__name__, vr.tap)) == 0
+                    else torch.as_tensor(np.asarray(low[vr.__name__]), dtype=torch.float64) for vr in vrs]
+            taps = torch.stack(cols, dim=1)
+        taps = torch.as_tensor(taps).to(device=dev, dtype=torch.float64)
+        if taps.dim() != 2 or tuple(taps.shape) != (S, len(vrs)):
+            raise ValueError(f'taps must be [S={S}, n_regulators={len(vrs)}], got {tuple(taps.shape)}')
+        g = (taps + 16) / 32
+        g = g * (1.10 - .90)
+        g = g + .90
+        rows = torch.as_tensor(np.asarray(t.grow_vr, dtype=np.int64), device=dev)
+        return g.t().index_select(0, rows).contiguous()
+
     # ---- accessors (solution.py:127-175, 235-315) ------------------------------
     def get_data_frame(self, param: str, orient: str = '') -> pd.DataFrame:
         if not orient:

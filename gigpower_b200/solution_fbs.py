@@ -175,7 +175,8 @@ class SolutionFBS(Solution):
 
     # ---- batched solve -------------------------------------------------------
     def solve_batch(self, spu=None, load_mult=None, spu_rows=None, outputs=('V', 'Vmag', 'loss'),
-                    maxiter=None, tol=None, return_device=False, stream=None) -> BatchResult:
+                    maxiter=None, tol=None, return_device=False, stream=None, taps=None,
+                    warm_start=None) -> BatchResult:
         """Solve S scenarios from flat start.
 
         Give ONE of: ``spu`` ``[S, nb, 3]`` complex; ``load_mult`` ``[S, n_loads]``
@@ -183,6 +184,13 @@ class SolutionFBS(Solution):
         ``[n_srows, S]`` complex128 (NumPy, or a CUDA torch tensor for inputs
         already resident in HBM).  ``outputs`` selects what is produced besides
         iterations/status: any of V, I, Vmag, loss, sV, Stx, Srx.
+
+        ``taps``: per-scenario regulator tap numbers (see ``gamma_rows_from_taps``); scenario s is
+        then what a reference object built with ``taps[s]`` computes.  ``warm_start``: a
+        ``BatchResult`` of an earlier ``solve_batch(..., outputs=(... 'V', 'I'), return_device=True)``
+        with the same number of scenarios; the sweep continues from its V and I (what the reference
+        does when ``Vtest`` and ``iterations`` are reset and ``solve()`` is called again) instead of
+        the flat start, and the result's V/I tensors are the SAME device tensors, updated in place.
         """
         torch, dev = self._dev()
         t = self.tables
@@ -206,8 +214,17 @@ class SolutionFBS(Solution):
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream() if stream is None else stream
             with torch.cuda.stream(st):
-                V = torch.empty((t.n_vrows, ld), dtype=torch.complex128, device=dev)
-                I = torch.empty((max(t.n_irows, 1), ld), dtype=torch.complex128, device=dev)
+                if warm_start is not None:
+                    V, I = warm_start.V_rows, warm_start.I_rows
+                    if (V is None or I is None or not hasattr(V, 'data_ptr') or tuple(V.shape) != (t.n_vrows, ld)
+                            or tuple(I.shape) != (max(t.n_irows, 1), ld)):
+                        raise ValueError('warm_start needs the V and I device tensors of an earlier solve_batch('
+                                         "outputs=(..., 'V', 'I'), return_device=True) with the same S")
+                else:
+                    V = torch.empty((t.n_vrows, ld), dtype=torch.complex128, device=dev)
+                    I = torch.empty((max(t.n_irows, 1), ld), dtype=torch.complex128, device=dev)
+                gamma = self.gamma_rows_from_taps(taps, S, dev) if taps is not None else None
+                extras = _cabi.make_extras(gamma, warm_start is not None)
                 iters = torch.empty(S, dtype=torch.int32, device=dev)
                 status = torch.empty(S, dtype=torch.int32, device=dev)
                 diff = torch.empty(S, dtype=torch.float64, device=dev)
@@ -220,16 +237,17 @@ class SolutionFBS(Solution):
                 loss = torch.empty(S, dtype=torch.complex128, device=dev) if 'loss' in want else None
                 p = lambda x: x.data_ptr() if x is not None else None
                 # solve + |V| + loss in one call (one launch with the feeder-specialised kernel)
-                _cabi.check(_cabi.gp_fbs_solve_post_batch(
-                    self._feeder.handle, S, ld, d_spu.data_ptr(), V.data_ptr(), I.data_ptr(),
-                    iters.data_ptr(), status.data_ptr(), diff.data_ptr(), p(Vmag), p(loss), tol, maxiter,
-                    st.cuda_stream))
+                _cabi.check(_cabi.gp_fbs_solve_batch_ex(
+                    self._feeder.handle, S, ld, d_spu.data_ptr(), C.byref(extras) if extras is not None else None,
+                    V.data_ptr(), I.data_ptr(), iters.data_ptr(), status.data_ptr(), diff.data_ptr(), p(Vmag),
+                    p(loss), tol, maxiter, st.cuda_stream))
                 if want & {'sV', 'Stx', 'Srx'}:
                     _cabi.check(_cabi.gp_fbs_post(
                         self._feeder.handle, S, ld, d_spu.data_ptr(), V.data_ptr(), I.data_ptr(),
                         p(sV), None, p(Stx), p(Srx), None, st.cuda_stream))
         res = BatchResult(tables=t, S=S, iterations=iters, status=status, convergence_diff=diff,
-                          V_rows=V if 'V' in want else None, I_rows=I if 'I' in want else None,
+                          V_rows=V if ('V' in want or warm_start is not None) else None,
+                          I_rows=I if ('I' in want or warm_start is not None) else None,
                           Vmag_rows=Vmag, loss=loss, sV_rows=sV, Stx_rows=Stx, Srx_rows=Srx)
         if not return_device:
             st.synchronize()

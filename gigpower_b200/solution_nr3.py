@@ -129,10 +129,15 @@ class SolutionNR3(Solution):
 
     def solve_batch(self, spu=None, load_mult=None, spu_rows=None,
                     outputs=('X', 'V', 'Vmag', 'loss'), maxiter=None, return_device=False,
-                    stream=None) -> Nr3BatchResult:
+                    stream=None, taps=None, warm_start=None) -> Nr3BatchResult:
         """Newton-solve S scenarios from flat start.  Inputs as in
         ``SolutionFBS.solve_batch``; ``outputs`` from X, V, I, Vmag, sV, i_Node,
-        Stx, Srx, loss."""
+        Stx, Srx, loss.
+
+        ``taps``: per-scenario regulator tap numbers (``gamma_rows_from_taps``).  ``warm_start``: an
+        ``Nr3BatchResult`` of an earlier ``solve_batch(..., return_device=True)`` with X among its
+        outputs and the same S: Newton starts from that X (as ``SolutionNR3.solve()`` called a second
+        time starts from ``self.XNR``, solution_nr3.py:598) and updates the same tensor in place."""
         torch, dev = self._dev()
         t = self.tables
         maxiter = self.maxiter if maxiter is None else int(maxiter)
@@ -159,7 +164,15 @@ class SolutionNR3(Solution):
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream() if stream is None else stream
             with torch.cuda.stream(st):
-                X = torch.empty((t.n_vrows + t.n_irows, ld), dtype=c128, device=dev)
+                if warm_start is not None:
+                    X = warm_start.X_rows
+                    if X is None or not hasattr(X, 'data_ptr') or tuple(X.shape) != (t.n_vrows + t.n_irows, ld):
+                        raise ValueError("warm_start needs the X device tensor of an earlier solve_batch("
+                                         "outputs=('X', ...), return_device=True) with the same S")
+                else:
+                    X = torch.empty((t.n_vrows + t.n_irows, ld), dtype=c128, device=dev)
+                gamma = self.gamma_rows_from_taps(taps, S, dev) if taps is not None else None
+                extras = _cabi.make_extras(gamma, warm_start is not None)
                 iters = torch.empty(S, dtype=torch.int32, device=dev)
                 status = torch.empty(S, dtype=torch.int32, device=dev)
                 fmax = torch.empty(S, dtype=f64, device=dev)
@@ -167,9 +180,10 @@ class SolutionNR3(Solution):
                 if wbytes < 0:
                     _cabi.check(wbytes)
                 work = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=dev)
-                _cabi.check(_cabi.gp_nr3_solve_batch(h, S, ld, d_spu.data_ptr(), X.data_ptr(), iters.data_ptr(),
-                                                     status.data_ptr(), fmax.data_ptr(), work.data_ptr(), wbytes,
-                                                     maxiter, st.cuda_stream))
+                _cabi.check(_cabi.gp_nr3_solve_batch_ex(
+                    h, S, ld, d_spu.data_ptr(), C.byref(extras) if extras is not None else None, X.data_ptr(),
+                    iters.data_ptr(), status.data_ptr(), fmax.data_ptr(), work.data_ptr(), wbytes, maxiter,
+                    st.cuda_stream))
                 mk = lambda rows, dt: torch.zeros((max(rows, 1), ld), dtype=dt, device=dev)
                 V = mk(t.n_vrows, c128) if 'V' in want else None
                 I = mk(t.n_irows, c128) if 'I' in want else None
@@ -185,7 +199,7 @@ class SolutionNR3(Solution):
                                                         p(Srx), p(sV), p(iN), p(Vmag), p(loss), st.cuda_stream))
                 del work
         res = Nr3BatchResult(tables=t, S=S, iterations=iters, status=status, fmax=fmax,
-                             X_rows=X if 'X' in want else None, V_rows=V, I_rows=I, Vmag_rows=Vmag, sV_rows=sV,
+                             X_rows=X if ('X' in want or warm_start is not None) else None, V_rows=V, I_rows=I, Vmag_rows=Vmag, sV_rows=sV,
                              iNode_rows=iN, Stx_rows=Stx, Srx_rows=Srx, loss=loss)
         if not return_device:
             st.synchronize()

@@ -222,6 +222,42 @@ int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const double* sp
                             double* diff_host, double tol, int32_t maxiter);
 
 /*
+ * Optional per-scenario inputs of a solve.  Zero-initialise; a NULL
+ * pointer / 0 keeps the behaviour of the plain entry points.
+ *
+ * gamma_dev: regulator ratios as a per-scenario input.  The reference fixes a regulator's ratio
+ *   when the Solution object is built (voltage_regulator.py:10-39: gamma = 0.9 + 0.2 (tap + 16) / 32
+ *   from RegControls.TapNumber()), so scenario s with ratios gamma[.][s] is "a fresh reference
+ *   object built with those taps".  One row per regulated (step, phase), i.e. per non-zero entry of
+ *   GpFbsDesc.vr_gamma / GpNr3Desc.vr_gamma, numbered in step order and, inside a step, phase
+ *   order (gp_gamma_rows() = their count); [n_gamma_rows][ld] doubles.  FBS forward sweep
+ *   V[reg] = gamma V[tx] (solution_fbs.py:138-160), backward sweep V[tx] = (1 / gamma) V[reg]
+ *   (:186-205); NR3 ratio rows -gamma A_in + A_out = 0 (solution_nr3.py:480-483).
+ *
+ * warm_start: 1 = continue from an earlier solution instead of the flat start.  FBS: V_dev and I_dev
+ *   hold that solution (what a reference object does when Vtest and iterations are reset and
+ *   solve() is called again with new loads: V and I are not re-initialised, solution_fbs.py:76-90);
+ *   NR3: X_dev holds it (SolutionNR3.solve() starts from self.XNR, solution_nr3.py:598).  The stop
+ *   rules are unchanged, so a warm-started scenario usually needs fewer iterations and its result
+ *   differs from the flat-started one within the solver tolerance.
+ */
+typedef struct {
+    const double* gamma_dev;
+    int32_t warm_start;
+    int32_t reserved;
+} GpSolveExtras;
+
+/* Number of rows of GpSolveExtras.gamma_dev for this feeder (0 = no regulators; negative = error). */
+int gp_gamma_rows(GpFeeder* f);
+
+/* gp_fbs_solve_post_batch with the optional inputs above (extras may be NULL).  Per-scenario ratios
+ * and warm starts run on the streaming kernel. */
+int gp_fbs_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const double* spu_dev, const GpSolveExtras* extras,
+                          double* V_dev, double* I_dev, int32_t* iters_dev, int32_t* status_dev,
+                          double* diff_dev, double* Vmag_dev, double* loss_dev, double tol, int32_t maxiter,
+                          void* stream);
+
+/*
  * Scenario studies (callers: a time-series driver looping over what the
  * reference does one `Circuit.set_kW / set_kvar` + `solve()` at a time, circuit.py:66-88).
  *
@@ -310,6 +346,12 @@ int64_t gp_nr3_workspace_bytes(GpFeeder* f, int64_t ld);
 int gp_nr3_solve_batch(GpFeeder* f, int64_t S, int64_t ld, const double* spu_dev, double* X_dev,
                        int32_t* iters_dev, int32_t* status_dev, double* fmax_dev,
                        void* workspace_dev, int64_t workspace_bytes, int32_t maxiter, void* stream);
+
+/* gp_nr3_solve_batch with the optional per-scenario inputs of GpSolveExtras (extras may be NULL).
+ * Per-scenario ratios and warm starts run on the thread-per-scenario kernel. */
+int gp_nr3_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const double* spu_dev, const GpSolveExtras* extras,
+                          double* X_dev, int32_t* iters_dev, int32_t* status_dev, double* fmax_dev,
+                          void* workspace_dev, int64_t workspace_bytes, int32_t maxiter, void* stream);
 
 /*
  * X -> results; replaces map_XNR / map_output (solution_nr3.py:634-663,

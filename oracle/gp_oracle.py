@@ -318,10 +318,14 @@ class FBSOracle:
                 V[:, parent] = V[:, parent] * c.bus_pm[parent]
         return V, I
 
-    def solve(self, spu=None, maxiter=MAXITER):
+    def solve(self, spu=None, maxiter=MAXITER, V0=None, I0=None):
         """Flat-start solve of ``S`` scenarios; ``spu[S,nb,3]`` complex (default:
         the feeder's nominal loads, ``S=1``).  Each scenario stops at its own
-        iteration exactly as a separate reference object would."""
+        iteration exactly as a separate reference object would.
+
+        ``V0, I0``: warm start - what a reference object does whose ``Vtest`` and
+        ``iterations`` are reset before ``solve()`` is called again: ``self.V`` and
+        ``self.I`` keep the earlier solution (:76-90 never re-initialise them)."""
         c = self.c
         if spu is None:
             spu = c.spu_matrix()[None]
@@ -329,6 +333,8 @@ class FBSOracle:
         S = spu.shape[0]
         V = np.zeros((S, c.nb, 3), dtype=complex)                                 # solution.py:108-125
         I = np.zeros((S, self.nrows_I, 3), dtype=complex)
+        if V0 is not None:
+            V[:], I[:] = V0, I0
         iters = np.zeros(S, dtype=np.int32)
         diff = np.full(S, -1.0)
         Vtest = np.zeros((S, 3), dtype=complex)
@@ -628,15 +634,17 @@ class NR3Oracle:
                 X[:, 2 * ph * nb + 2 * k + 1] = VSLACK[ph].imag
         return X
 
-    def solve(self, spu=None, maxiter=MAXITER, chunk=16, return_history=False):
+    def solve(self, spu=None, maxiter=MAXITER, chunk=16, return_history=False, X0=None):
         """Flat-start Newton solve of ``S`` scenarios (:592-632).  ``spu[S,nb,3]``
-        holds the per-bus load sums (p = real, q = imag)."""
+        holds the per-bus load sums (p = real, q = imag).  ``X0[S,N]``: start from an
+        earlier solution instead (``solve()`` starts from ``self.XNR``, :598, which a
+        second call finds at the previous solution)."""
         c = self.c
         if spu is None:
             spu = c.spu_matrix()[None]
         spu = np.asarray(spu, dtype=complex)
         S = spu.shape[0]
-        X = self.x0(S)
+        X = self.x0(S) if X0 is None else np.array(X0, dtype=float)
         iters = np.zeros(S, dtype=np.int32)
         hist = [[] for _ in range(S)]
         for s0 in range(0, S, chunk):
@@ -711,3 +719,42 @@ class NR3Oracle:
             iN[:, PH != 0] = np.conj(sV[:, PH != 0] / V[:, PH != 0])
         iN = self._scrub(iN)
         return dict(V=V, I=I, Stx=Stx, Srx=Srx, i_Node=iN, sV=sV, Vmag=np.abs(V))
+
+
+# ==========================================================================
+# per-scenario regulator taps
+# ==========================================================================
+def gamma_of_tap(tap):
+    """voltage_regulator.py:23-39, operation for operation."""
+    g = (np.asarray(tap, dtype=float) + 16) / 32
+    g = g * (1.10 - .90)
+    g = g + .90
+    return g
+
+
+def solve_with_taps(oracle_cls, model, spu, taps, zip_v=DEFAULT_ZIP, **kw):
+    """Scenario s = a fresh reference object whose regulators sit at ``taps[s]``
+    (the reference reads a tap once, when the object is built:
+    voltage_regulator.py:10-22).  ``taps[S, n_regcontrols]`` integers in the
+    order of ``model.regcontrols``; scenarios are grouped by tap vector and each
+    group is solved by an oracle built on a copy of ``model`` with those taps.
+    Returns the oracle's result dict with the groups scattered back."""
+    import copy
+    spu = np.asarray(spu, dtype=complex)
+    taps = np.asarray(taps, dtype=int).reshape(spu.shape[0], -1)
+    out = {}
+    uniq, inv = np.unique(taps, axis=0, return_inverse=True)
+    inv = np.asarray(inv).reshape(-1)
+    for g, tv in enumerate(uniq):
+        idx = np.nonzero(inv == g)[0]
+        m = copy.deepcopy(model)
+        for rc, t in zip(m.regcontrols, tv):
+            rc.tap = int(t)
+        r = oracle_cls(m, zip_v).solve(spu[idx], **kw)
+        for k, v in r.items():
+            if not isinstance(v, np.ndarray) or v.shape[:1] != (len(idx),):
+                continue
+            if k not in out:
+                out[k] = np.zeros((spu.shape[0],) + v.shape[1:], dtype=v.dtype)
+            out[k][idx] = v
+    return out

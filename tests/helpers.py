@@ -54,3 +54,26 @@ def rel_err(a, b):
     voltages' bar of BASELINE.json (voltages are O(1) pu, currents O(1))."""
     a, b = np.asarray(a), np.asarray(b)
     return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0
+
+
+def taps_golden():
+    """tests/golden/ref_taps.npz (oracle/make_golden_taps.py): one unmodified reference object
+    per scenario, built with that scenario's regulator taps."""
+    if 'taps' not in _cache:
+        _cache['taps'] = np.load(os.path.join(GOLDEN, 'ref_taps.npz'))
+    return _cache['taps']
+
+
+TAP_FEEDERS = ['IEEE_13_Bus_allwye', 'IEEE_37_Bus_allwye', 'IEEE_34_Bus_allwye']
+
+
+def warm_golden():
+    """tests/golden/ref_warm.npz (oracle/make_golden_warm.py): one unmodified reference object per
+    feeder driven through a sequence of load levels, each solve starting from the previous one."""
+    if 'warm' not in _cache:
+        _cache['warm'] = np.load(os.path.join(GOLDEN, 'ref_warm.npz'))
+    return _cache['warm']
+
+
+WARM_FEEDERS = {'IEEE_13_Bus_allwye_noxfm_noreg': {}, 'IEEE_13_Bus_allwye': {'reg1': 9, 'reg2': 7, 'reg3': 9},
+                'IEEE_37_Bus_allwye_noxfm_noreg': {}}

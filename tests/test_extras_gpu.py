@@ -1,0 +1,240 @@
+"""GPU parity tests of the optional per-scenario inputs (GpSolveExtras, through the C-ABI):
+regulator taps as a batch input and warm-started solves (8(f)-3).
+
+Golden vectors come from the unmodified reference (oracle/make_golden_taps.py: one reference object
+per scenario, built with that scenario's taps; oracle/make_golden_warm.py: one reference object
+driven through a load sequence).  Bar: 1e-9 relative on complex voltages, identical iteration counts."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import (ZIPS, LINES_ONLY, TAP_FEEDERS, WARM_FEEDERS, feeder_path, load_model, taps_golden, warm_golden,
+                     rel_err)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _fbs(feeder, **kw):
+    from gigpower_b200.solution_fbs import SolutionFBS
+    return SolutionFBS(feeder_path(feeder), zip_v=np.asarray(ZIPS['test_zip']), **kw)
+
+
+def _nr3(feeder, **kw):
+    from gigpower_b200.solution_nr3 import SolutionNR3
+    return SolutionNR3(feeder_path(feeder), zip_v=np.asarray(ZIPS['test_zip']), **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# per-scenario taps
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('feeder', TAP_FEEDERS)
+def test_fbs_taps_match_reference_objects(feeder):
+    tg = taps_golden()
+    s = _fbs(feeder)
+    assert [vr.__name__ for vr in s.circuit.voltage_regulators.get_elements()] == list(tg[feeder + '/regs'])
+    r = s.solve_batch(load_mult=tg[feeder + '/mult'], taps=tg[feeder + '/taps'], outputs=('V', 'I'))
+    assert list(r.iterations) == list(tg[feeder + '/FBS/iterations'])
+    assert rel_err(r.V, tg[feeder + '/FBS/V']) <= TOL
+    # the reference keeps all-zero I rows for regulators after the line and transformer rows
+    want_I = tg[feeder + '/FBS/I']
+    assert rel_err(r.I, want_I[:, :r.I.shape[1]]) <= TOL
+
+
+@pytest.mark.parametrize('feeder,S,n_combo,seed', [('IEEE_13_Bus_allwye', 700, 12, 11),
+                                                    ('IEEE_34_Bus_allwye', 130, 6, 12),
+                                                    ('IEEE_37_Bus_allwye', 257, 8, 13)])
+def test_fbs_taps_random_batch_matches_oracle(feeder, S, n_combo, seed):
+    from oracle.gp_oracle import FBSOracle, OracleCircuit, solve_with_taps
+    rng = np.random.Generator(np.random.PCG64(seed))
+    model = load_model(feeder)
+    c = OracleCircuit(model)
+    combos = rng.integers(-16, 17, size=(n_combo, len(model.regcontrols)))
+    taps = combos[rng.integers(0, n_combo, size=S)]
+    mult = rng.uniform(0.5, 1.5, size=(S, len(c.load_names)))
+    want = solve_with_taps(FBSOracle, model, c.spu_matrix(c.load_kw * mult, c.load_kvar * mult), taps, ZIPS['test_zip'])
+    s = _fbs(feeder)
+    r = s.solve_batch(load_mult=mult, taps=taps, outputs=('V', 'I', 'Vmag', 'loss'))
+    assert np.array_equal(r.iterations, want['iterations'])
+    assert np.array_equal(r.converged, want['converged'])
+    assert rel_err(r.V, want['V']) <= TOL and rel_err(r.Vmag, want['Vmag']) <= TOL
+    assert rel_err(r.losses, (want['Stx'] - want['Srx']).sum(axis=(1, 2))) <= TOL
+
+
+def test_fbs_constant_taps_equal_a_feeder_built_with_them():
+    """Ratios read per scenario or baked into the step table: the same arithmetic, bit for bit."""
+    from gigpower_b200 import _cabi
+    feeder, taps = 'IEEE_13_Bus_allwye', {'reg1': -3, 'reg2': 12, 'reg3': 5}
+    rng = np.random.Generator(np.random.PCG64(5))
+    mult = rng.uniform(0.5, 1.5, size=(333, 15))
+    s = _fbs(feeder)
+    a = s.solve_batch(load_mult=mult, taps=taps, outputs=('V', 'I'))                 # dict form, scalars
+    tv = np.tile(np.array([[-3, 12, 5]]), (333, 1))
+    a2 = s.solve_batch(load_mult=mult, taps=tv, outputs=('V', 'I'))
+    model = load_model(feeder)
+    for rc in model.regcontrols:
+        rc.tap = taps[rc.name]
+    from gigpower_b200.solution_fbs import SolutionFBS
+    b_sol = SolutionFBS(model, zip_v=np.asarray(ZIPS['test_zip']))
+    b_sol._dev()
+    _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 3))
+    try:
+        b = b_sol.solve_batch(load_mult=mult, outputs=('V', 'I'))
+    finally:
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 0))
+    for r in (a, a2):
+        assert np.array_equal(r.iterations, b.iterations)
+        assert np.array_equal(r.V_rows, b.V_rows) and np.array_equal(r.I_rows, b.I_rows)
+    with pytest.raises(KeyError):
+        s.solve_batch(load_mult=mult, taps={'nosuchreg': 1})
+    with pytest.raises(ValueError):
+        s.solve_batch(load_mult=mult, taps=tv[:, :2])
+
+
+def test_taps_on_a_feeder_without_regulators_are_ignored():
+    from gigpower_b200 import _cabi
+    feeder = LINES_ONLY[0]
+    s = _fbs(feeder)
+    s._dev()
+    assert _cabi.gp_gamma_rows(s._feeder.handle) == 0
+    mult = np.random.Generator(np.random.PCG64(3)).uniform(0.5, 1.5, size=(100, s.circuit.loads.num_elements))
+    a = s.solve_batch(load_mult=mult)
+    b = s.solve_batch(load_mult=mult, taps=np.zeros((100, 0)))
+    assert np.array_equal(a.iterations, b.iterations) and rel_err(a.V, b.V) <= 1e-12
+    for f, make in (('IEEE_34_Bus_allwye', _fbs), ('IEEE_13_Bus_allwye', _nr3)):
+        x = make(f)
+        x._dev()
+        assert _cabi.gp_gamma_rows(x._feeder.handle) == len(x.tables.grow_vr) > 0
+
+
+@pytest.mark.parametrize('feeder', ['IEEE_13_Bus_allwye', 'IEEE_37_Bus_allwye'])
+def test_nr3_taps_match_reference_objects(feeder):
+    tg = taps_golden()
+    X = tg[feeder + '/NR3/XNR']
+    n = len(X)
+    s = _nr3(feeder)
+    r = s.solve_batch(load_mult=tg[feeder + '/mult'][:n], taps=tg[feeder + '/taps'][:n], outputs=('X', 'V'))
+    assert list(r.iterations) == list(tg[feeder + '/NR3/iterations'])
+    assert rel_err(r.XNR, X) <= TOL
+    assert rel_err(r.V, tg[feeder + '/NR3/V']) <= TOL
+
+
+@pytest.mark.parametrize('feeder,S,n_combo,seed', [('IEEE_13_Bus_allwye', 300, 10, 21), ('IEEE_37_Bus_allwye', 200, 6, 22),
+                                                    ('IEEE_34_Bus_allwye', 150, 5, 23)])
+def test_nr3_taps_random_batch_matches_tree_oracle(feeder, S, n_combo, seed):
+    from oracle.gp_oracle import OracleCircuit, solve_with_taps
+    from oracle.nr3_tree import NR3TreeOracle
+    rng = np.random.Generator(np.random.PCG64(seed))
+    model = load_model(feeder)
+    c = OracleCircuit(model)
+    combos = rng.integers(-16, 17, size=(n_combo, len(model.regcontrols)))
+    taps = combos[rng.integers(0, n_combo, size=S)]
+    mult = rng.uniform(0.5, 1.3, size=(S, len(c.load_names)))
+    want = solve_with_taps(NR3TreeOracle, model, c.spu_matrix(c.load_kw * mult, c.load_kvar * mult), taps,
+                           ZIPS['test_zip'])
+    r = _nr3(feeder).solve_batch(load_mult=mult, taps=taps, outputs=('X',))
+    assert np.array_equal(r.iterations, want['iterations'])
+    assert rel_err(r.XNR, want['XNR']) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# warm start
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('feeder', list(WARM_FEEDERS))
+def test_fbs_warm_sequence_matches_reference_object(feeder):
+    wg = warm_golden()
+    s = _fbs(feeder, taps=WARM_FEEDERS[feeder])
+    mult = wg[feeder + '/mult']
+    prev = None
+    for h in range(len(wg[feeder + '/FBS/iterations'])):
+        prev = s.solve_batch(load_mult=mult[h:h + 1], outputs=('V', 'I'), return_device=True, warm_start=prev)
+        assert int(prev.iterations[0]) == int(wg[feeder + '/FBS/iterations'][h]), h
+        assert rel_err(prev.V[0], wg[feeder + '/FBS/V'][h]) <= TOL
+        want_I = wg[feeder + '/FBS/I'][h]
+        assert rel_err(prev.I[0], want_I[:prev.I.shape[1]]) <= TOL
+
+
+@pytest.mark.parametrize('feeder,S,steps,seed', [('IEEE_13_Bus_allwye_noxfm_noreg', 1000, 4, 31),
+                                                  ('IEEE_37_Bus_allwye', 150, 3, 32)])
+def test_fbs_warm_batch_matches_oracle(feeder, S, steps, seed):
+    from oracle.gp_oracle import FBSOracle
+    rng = np.random.Generator(np.random.PCG64(seed))
+    o = FBSOracle(load_model(feeder), ZIPS['test_zip'])
+    c = o.c
+    s = _fbs(feeder)
+    level = rng.uniform(0.6, 1.2, size=(S, 1))
+    prev, V0, I0 = None, None, None
+    total_warm = total_flat = 0
+    for h in range(steps):
+        level = level * rng.uniform(0.9, 1.1, size=(S, 1))
+        mult = level * (1 + rng.normal(0, 0.02, size=(S, len(c.load_names))))
+        want = o.solve(c.spu_matrix(c.load_kw * mult, c.load_kvar * mult), V0=V0, I0=I0)
+        prev = s.solve_batch(load_mult=mult, outputs=('V', 'I'), return_device=True, warm_start=prev)
+        assert np.array_equal(prev.iterations.cpu().numpy(), want['iterations']), h
+        assert rel_err(prev.V, want['V']) <= TOL
+        V0, I0 = want['V'], want['I']
+        if h > 0:
+            total_warm += int(want['iterations'].sum())
+            total_flat += int(s.solve_batch(load_mult=mult).iterations.sum())
+    assert total_warm < total_flat          # the point of the warm start
+
+
+@pytest.mark.parametrize('feeder', list(WARM_FEEDERS))
+def test_nr3_warm_sequence_matches_reference_object(feeder):
+    wg = warm_golden()
+    s = _nr3(feeder, taps=WARM_FEEDERS[feeder])
+    mult = wg[feeder + '/mult']
+    prev = None
+    for h in range(len(wg[feeder + '/NR3/iterations'])):
+        prev = s.solve_batch(load_mult=mult[h:h + 1], outputs=('X',), return_device=True, warm_start=prev)
+        assert int(prev.iterations[0]) == int(wg[feeder + '/NR3/iterations'][h]), h
+        assert rel_err(prev.XNR[0], wg[feeder + '/NR3/XNR'][h]) <= TOL
+
+
+def test_nr3_warm_batch_matches_dense_oracle():
+    from oracle.gp_oracle import NR3Oracle
+    feeder, S = 'IEEE_13_Bus_allwye_noxfm_noreg', 96
+    rng = np.random.Generator(np.random.PCG64(41))
+    o = NR3Oracle(load_model(feeder), ZIPS['test_zip'])
+    c = o.c
+    s = _nr3(feeder)
+    level = rng.uniform(0.6, 1.2, size=(S, 1))
+    prev, X0 = None, None
+    for h in range(3):
+        level = level * rng.uniform(0.9, 1.1, size=(S, 1))
+        mult = level * (1 + rng.normal(0, 0.02, size=(S, len(c.load_names))))
+        want = o.solve(c.spu_matrix(c.load_kw * mult, c.load_kvar * mult), X0=X0)
+        prev = s.solve_batch(load_mult=mult, outputs=('X',), return_device=True, warm_start=prev)
+        assert np.array_equal(prev.iterations.cpu().numpy(), want['iterations']), h
+        assert rel_err(prev.XNR, want['XNR']) <= TOL
+        X0 = want['XNR']
+
+
+def test_extras_argument_checks():
+    from gigpower_b200 import _cabi
+    import torch
+    s = _fbs('IEEE_13_Bus_allwye')
+    _, dev = s._dev()
+    t = s.tables
+    S = 8
+    spu = torch.zeros((t.n_srows, S), dtype=torch.complex128, device=dev)
+    V = torch.zeros((t.n_vrows, S), dtype=torch.complex128, device=dev)
+    I = torch.zeros((t.n_irows, S), dtype=torch.complex128, device=dev)
+    it = torch.zeros(S, dtype=torch.int32, device=dev)
+    st = torch.zeros(S, dtype=torch.int32, device=dev)
+    df = torch.zeros(S, dtype=torch.float64, device=dev)
+    ex = _cabi.GpSolveExtras()
+    ex.warm_start = 2
+    rc = _cabi.gp_fbs_solve_batch_ex(s._feeder.handle, S, S, spu.data_ptr(), C.byref(ex), V.data_ptr(), I.data_ptr(),
+                                     it.data_ptr(), st.data_ptr(), df.data_ptr(), None, None, 1e-6, 100, None)
+    assert rc == -1
+    with pytest.raises(ValueError):
+        s.solve_batch(load_mult=np.ones((4, 15)), warm_start=s.solve_batch(load_mult=np.ones((5, 15)),
+                                                                           outputs=('V', 'I'), return_device=True))
+    # extras = NULL is the plain entry point
+    rc = _cabi.gp_fbs_solve_batch_ex(s._feeder.handle, S, S, spu.data_ptr(), None, V.data_ptr(), I.data_ptr(),
+                                     it.data_ptr(), st.data_ptr(), df.data_ptr(), None, None, 1e-6, 100, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert int(it.max()) >= 1

@@ -115,3 +115,26 @@ def test_specialised_kernel_source_generates_and_compiles(feeder, warps, ig):
     # bad arguments are errors, not crashes
     assert _cabi.gp_fbs_jit_source(C.byref(d), 0, ig, None, 0) < 0
     assert _cabi.gp_jit_compile(b'this is not CUDA', None, 0, C.byref(size)) == -4
+
+
+@pytest.mark.parametrize('feeder,n_rows', [('IEEE_13_Bus_allwye', 3), ('IEEE_34_Bus_allwye', 6), ('IEEE_37_Bus_allwye', 3),
+                                           ('IEEE_13_Bus_allwye_noxfm_noreg', 0)])
+def test_gamma_rows_follow_the_step_table(feeder, n_rows):
+    """Rows of a per-scenario regulator-ratio array (GpSolveExtras.gamma_dev): one per regulated
+    (step, phase) in step then phase order, each owned by the regulator that set that ratio."""
+    from gigpower_b200.circuit import Circuit
+    from gigpower_b200.flatten import flatten_fbs, flatten_nr3, EDGE_VR
+    for taps in ({}, {'reg1': 5, 'reg2': -7, 'reg3': 11, 'reg1a': 1, 'reg1b': 2, 'reg1c': 3, 'reg2a': 4,
+                      'reg2b': 5, 'reg2c': 6}):
+        model = load_model(feeder)
+        for rc in model.regcontrols:
+            rc.tap = taps.get(rc.name, rc.tap)
+        c = Circuit(model)
+        vrs = c.voltage_regulators.get_elements()
+        for t in (flatten_fbs(c), flatten_nr3(c)):
+            assert len(t.grow_vr) == n_rows
+            rows = t.grow[t.grow >= 0]
+            assert list(rows) == list(range(n_rows))                 # step-major, phase-minor numbering
+            assert ((t.grow >= 0) == ((t.kind[:, None] == EDGE_VR) & (t.vr_gamma != 0))).all()
+            for i, p in zip(*np.nonzero(t.grow >= 0)):
+                assert t.vr_gamma[i, p] == vrs[t.grow_vr[t.grow[i, p]]].gamma

@@ -137,3 +137,86 @@ def test_tree_elimination_oracle_equals_dense_oracle(feeder, zname):
     assert np.array_equal(a['iterations'], b['iterations'])
     assert np.abs(a['XNR'] - b['XNR']).max() <= 1e-12
     assert np.abs(b['XNR'][0] - snapshots()[f'{feeder}/{zname}/NR3/XNR'][:, 0]).max() <= 1e-12
+
+
+# ---- per-scenario regulator taps --------------------------------
+from oracle.gp_oracle import solve_with_taps, gamma_of_tap          # noqa: E402
+from helpers import taps_golden, TAP_FEEDERS                         # noqa: E402
+
+
+def test_gamma_of_tap_is_the_reference_mapping():
+    # voltage_regulator.py:23-39: -16 -> 0.90, +16 -> 1.10, and the rounding of the python expression
+    for tap in range(-16, 17):
+        g = (tap + 16) / 32
+        g *= 1.10 - .90
+        g += .90
+        assert gamma_of_tap(tap) == g
+    assert gamma_of_tap(np.array([-16, 16]))[0] == .90 and abs(gamma_of_tap(16) - 1.10) < 1e-15
+
+
+@pytest.mark.parametrize('feeder', TAP_FEEDERS)
+def test_fbs_per_scenario_taps(feeder):
+    tg = taps_golden()
+    model = load_model(feeder)
+    assert [rc.name for rc in model.regcontrols] == list(tg[feeder + '/regs'])
+    c = OracleCircuit(model)
+    mult = tg[feeder + '/mult']
+    spu = c.spu_matrix(c.load_kw * mult, c.load_kvar * mult)
+    r = solve_with_taps(FBSOracle, model, spu, tg[feeder + '/taps'], ZIPS['test_zip'])
+    assert list(r['iterations']) == list(tg[feeder + '/FBS/iterations'])
+    assert np.abs(r['V'] - tg[feeder + '/FBS/V']).max() <= TOL
+    assert np.abs(r['I'] - tg[feeder + '/FBS/I']).max() <= TOL
+
+
+@pytest.mark.parametrize('feeder', [f for f in TAP_FEEDERS if f != 'IEEE_34_Bus_allwye'])
+def test_nr3_per_scenario_taps(feeder):
+    from oracle.nr3_tree import NR3TreeOracle
+    tg = taps_golden()
+    model = load_model(feeder)
+    c = OracleCircuit(model)
+    X = tg[feeder + '/NR3/XNR']
+    n = len(X)
+    mult = tg[feeder + '/mult'][:n]
+    spu = c.spu_matrix(c.load_kw * mult, c.load_kvar * mult)
+    r = solve_with_taps(NR3Oracle, model, spu, tg[feeder + '/taps'][:n], ZIPS['test_zip'])
+    assert list(r['iterations']) == list(tg[feeder + '/NR3/iterations'])
+    assert np.abs(r['XNR'] - X).max() <= 1e-11
+    t = solve_with_taps(NR3TreeOracle, model, spu, tg[feeder + '/taps'][:n], ZIPS['test_zip'])
+    assert list(t['iterations']) == list(tg[feeder + '/NR3/iterations'])
+    assert np.abs(t['XNR'] - X).max() <= 1e-10
+
+
+# ---- warm-started sequences ---------------------------------------
+from helpers import warm_golden, WARM_FEEDERS                       # noqa: E402
+
+
+@pytest.mark.parametrize('feeder', list(WARM_FEEDERS))
+def test_fbs_warm_started_sequence(feeder):
+    wg = warm_golden()
+    o = FBSOracle(load_model(feeder), ZIPS['test_zip'])
+    c = o.c
+    mult = wg[feeder + '/mult']
+    V0 = I0 = None
+    for h in range(len(wg[feeder + '/FBS/iterations'])):
+        r = o.solve(c.spu_matrix(c.load_kw * mult[h], c.load_kvar * mult[h])[None], V0=V0, I0=I0)
+        assert int(r['iterations'][0]) == int(wg[feeder + '/FBS/iterations'][h]), h
+        assert np.abs(r['V'][0] - wg[feeder + '/FBS/V'][h]).max() <= TOL
+        assert np.abs(r['I'][0] - wg[feeder + '/FBS/I'][h]).max() <= TOL
+        V0, I0 = r['V'], r['I']
+    # the warm start is what saves iterations: the same loads from flat start take more sweeps
+    flat = o.solve(c.spu_matrix(c.load_kw * mult[1], c.load_kvar * mult[1])[None])
+    assert int(flat['iterations'][0]) > int(wg[feeder + '/FBS/iterations'][1])
+
+
+@pytest.mark.parametrize('feeder', list(WARM_FEEDERS))
+def test_nr3_warm_started_sequence(feeder):
+    wg = warm_golden()
+    o = NR3Oracle(load_model(feeder), ZIPS['test_zip'])
+    c = o.c
+    mult = wg[feeder + '/mult']
+    X0 = None
+    for h in range(len(wg[feeder + '/NR3/iterations'])):
+        r = o.solve(c.spu_matrix(c.load_kw * mult[h], c.load_kvar * mult[h])[None], X0=X0)
+        assert int(r['iterations'][0]) == int(wg[feeder + '/NR3/iterations'][h]), h
+        assert np.abs(r['XNR'][0] - wg[feeder + '/NR3/XNR'][h]).max() <= 1e-11
+        X0 = r['XNR']
