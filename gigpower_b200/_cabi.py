@@ -102,6 +102,8 @@ gp_fbs_solve_batch_ex = _sig('gp_fbs_solve_batch_ex', C.c_int,
 
 gp_der_rows = _sig('gp_der_rows', C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                              vp, vp, vp, vp, vp, vp, vp])
+gp_der_rows_strided = _sig('gp_der_rows_strided', C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                                             C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp])
 gp_vmag_summary = _sig('gp_vmag_summary', C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int32, vp, C.c_double,
                                                      C.c_double, vp, vp, vp, vp])
 
@@ -120,7 +122,7 @@ EXPORTS = ['gp_version', 'gp_last_error', 'gp_launch_count', 'gp_set_option', 'g
            'gp_jit_compile', 'gp_fbs_create', 'gp_feeder_destroy',
            'gp_fbs_solve_batch', 'gp_fbs_solve_post_batch', 'gp_fbs_post', 'gp_fbs_solve_batch_host', 'gp_der_rows', 'gp_vmag_summary', 'gp_nr3_create',
            'gp_nr3_workspace_bytes', 'gp_nr3_solve_batch', 'gp_nr3_map_output',
-           'gp_gamma_rows', 'gp_fbs_solve_batch_ex', 'gp_nr3_solve_batch_ex']
+           'gp_gamma_rows', 'gp_fbs_solve_batch_ex', 'gp_nr3_solve_batch_ex', 'gp_der_rows_strided']
 
 
 def make_extras(gamma=None, warm_start=False):

@@ -18,12 +18,12 @@ namespace gp {
 // (__dmul_rn / __dsub_rn, no FMA contraction) so that the rows are bit-identical to the NumPy
 // expression the workload is defined by (bench.py:make_der_rows).
 __global__ void __launch_bounds__(256)
-der_rows_kernel(long long S, long long ld, long long first, int H, int D, int n_srows,
+der_rows_kernel(long long S, long long ld, long long first, long long stride, int H, int D, int n_srows,
                 const double2* __restrict__ W0, const double* __restrict__ m_h, const double* __restrict__ pv_h,
                 const double* __restrict__ mask, const double* __restrict__ pen, double2* __restrict__ spu) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    const long long idx = (first + s) % ((long long)H * D);
+    const long long idx = (first + s * stride) % ((long long)H * D);
     const int d = (int)(idx / H), h = (int)(idx % H);
     const double m = __ldg(m_h + h);
     const double g = __dmul_rn(__ldg(pen + d), __ldg(pv_h + h));
@@ -60,14 +60,22 @@ using namespace gp;
 extern "C" int gp_der_rows(int device, int64_t S, int64_t ld, int64_t first, int32_t H, int32_t D, int32_t n_srows,
                            const double* W0_dev, const double* m_h_dev, const double* pv_h_dev,
                            const double* mask_dev, const double* pen_dev, double* spu_dev, void* stream) {
-    if (S < 0 || ld < S || H <= 0 || D <= 0 || n_srows < 0 || first < 0)
+    return gp_der_rows_strided(device, S, ld, first, 1, H, D, n_srows, W0_dev, m_h_dev, pv_h_dev, mask_dev, pen_dev,
+                               spu_dev, stream);
+}
+
+extern "C" int gp_der_rows_strided(int device, int64_t S, int64_t ld, int64_t first, int64_t stride, int32_t H,
+                                   int32_t D, int32_t n_srows, const double* W0_dev, const double* m_h_dev,
+                                   const double* pv_h_dev, const double* mask_dev, const double* pen_dev,
+                                   double* spu_dev, void* stream) {
+    if (S < 0 || ld < S || H <= 0 || D <= 0 || n_srows < 0 || first < 0 || stride < 1)
         return fail(GP_EINVAL, "gp_der_rows: bad sizes");
     if (S == 0 || n_srows == 0) return GP_OK;
     if (!W0_dev || !m_h_dev || !pv_h_dev || !mask_dev || !pen_dev || !spu_dev)
         return fail(GP_EINVAL, "gp_der_rows: null buffer");
     GP_CUDA(cudaSetDevice(device));
     dim3 grid((unsigned)((S + 255) / 256), (unsigned)(n_srows < 8 ? n_srows : 8));
-    der_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(S, ld, first, H, D, n_srows, (const double2*)W0_dev,
+    der_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(S, ld, first, stride, H, D, n_srows, (const double2*)W0_dev,
                                                             m_h_dev, pv_h_dev, mask_dev, pen_dev, (double2*)spu_dev);
     count_launch();
     GP_CUDA(cudaGetLastError());

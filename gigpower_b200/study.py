@@ -87,16 +87,52 @@ class DerStudy:
     def n_scenarios(self) -> int:
         return self.H * self.D
 
-    def spu_rows(self, first: int, S: int, out=None, stream=None):
-        """Packed spu rows ``[n_srows, S]`` of scenarios ``first .. first + S`` (CUDA tensor)."""
+    def spu_rows(self, first: int, S: int, out=None, stream=None, stride: int = 1):
+        """Packed spu rows ``[n_srows, S]`` of scenarios ``first + s * stride``, s < S (CUDA tensor)."""
         torch, t = self.torch, self.sol.tables
         if out is None:
             out = torch.empty((t.n_srows, S), dtype=torch.complex128, device=self.dev)
         st = torch.cuda.current_stream(self.dev) if stream is None else stream
-        _cabi.check(_cabi.gp_der_rows(self.dev.index, S, int(out.shape[1]), int(first), self.H, self.D, t.n_srows,
-                                      self.W0.data_ptr(), self.m_h.data_ptr(), self.pv_h.data_ptr(),
-                                      self.mask.data_ptr(), self.pen.data_ptr(), out.data_ptr(), st.cuda_stream))
+        _cabi.check(_cabi.gp_der_rows_strided(self.dev.index, S, int(out.shape[1]), int(first), int(stride), self.H,
+                                              self.D, t.n_srows, self.W0.data_ptr(), self.m_h.data_ptr(),
+                                              self.pv_h.data_ptr(), self.mask.data_ptr(), self.pen.data_ptr(),
+                                              out.data_ptr(), st.cuda_stream))
         return out
+
+    def run_chained(self, chain_hours: int = 24, first_chain: int = 0, chains: Optional[int] = None,
+                    vmin: float = 0.95, vmax: float = 1.05) -> Dict[str, np.ndarray]:
+        """The study as a time series: the ``H * D`` scenarios are cut into chains of
+        ``chain_hours`` consecutive hours of one DER scenario (``H`` must be a multiple; a chain is a day by
+        default); all chains advance together, one launch per hour of the chain, and hour k of a chain starts
+        from the solution of hour k - 1 (``warm_start``) instead of the flat start - the first hour of
+        every chain starts flat.  Same stop rule, so every result is a converged solution of the same
+        equations within the solver tolerance, reached in fewer sweeps.  Returns the arrays of ``run``
+        in scenario order (``chain * chain_hours + k``), for chains ``first_chain .. first_chain + chains``."""
+        torch, sol, t = self.torch, self.sol, self.sol.tables
+        L = int(chain_hours)
+        if L < 1 or self.H % L:
+            raise ValueError(f'chain_hours must divide H = {self.H}')
+        n_all = self.n_scenarios // L
+        chains = n_all - first_chain if chains is None else int(chains)
+        if chains < 1 or first_chain < 0 or first_chain + chains > n_all:
+            raise ValueError('chain range out of bounds')
+        kinds = {'iterations': torch.int32, 'status': torch.int32, 'loss': torch.complex128,
+                 'vmin': torch.float64, 'vmax': torch.float64, 'violations': torch.int32}
+        dev_out = {k: torch.empty((chains, L), dtype=dt, device=self.dev) for k, dt in kinds.items()}
+        spu = torch.empty((t.n_srows, chains), dtype=torch.complex128, device=self.dev)
+        st = torch.cuda.current_stream(self.dev)
+        state_outputs = ('V', 'I', 'Vmag', 'loss') if self.is_fbs else ('X', 'Vmag', 'loss')
+        prev = None
+        for k in range(L):
+            self.spu_rows(first_chain * L + k, chains, out=spu, stream=st, stride=L)
+            prev = sol.solve_batch(spu_rows=spu, outputs=state_outputs, return_device=True, stream=st,
+                                   warm_start=prev)
+            vlo, vhi, cnt = voltage_summary(prev.Vmag_rows, chains, vmin, vmax, stream=st)
+            for key, src in (('iterations', prev.iterations), ('status', prev.status), ('loss', prev.loss),
+                             ('vmin', vlo), ('vmax', vhi), ('violations', cnt)):
+                dev_out[key][:, k].copy_(src[:chains])
+        st.synchronize()
+        return {k: v.reshape(-1).cpu().numpy() for k, v in dev_out.items()}
 
     def run(self, first: int = 0, count: Optional[int] = None, chunk: int = 131072, vmin: float = 0.95,
             vmax: float = 1.05) -> Dict[str, np.ndarray]:

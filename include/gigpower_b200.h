@@ -275,6 +275,11 @@ int gp_fbs_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const double* spu_
 int gp_der_rows(int device, int64_t S, int64_t ld, int64_t first, int32_t H, int32_t D, int32_t n_srows,
                 const double* W0_dev, const double* m_h_dev, const double* pv_h_dev, const double* mask_dev,
                 const double* pen_dev, double* spu_dev, void* stream);
+/* gp_der_rows for the scenarios first + s * stride (s < S): the hour-k members of all chains of a chained
+ * (warm-started, hour after hour) study, whose chains are runs of `stride` consecutive hours. */
+int gp_der_rows_strided(int device, int64_t S, int64_t ld, int64_t first, int64_t stride, int32_t H, int32_t D,
+                        int32_t n_srows, const double* W0_dev, const double* m_h_dev, const double* pv_h_dev,
+                        const double* mask_dev, const double* pen_dev, double* spu_dev, void* stream);
 int gp_vmag_summary(int device, int64_t S, int64_t ld, int32_t n_vrows, const double* Vmag_dev, double vmin,
                     double vmax, double* min_dev, double* max_dev, int32_t* count_dev, void* stream);
 

@@ -109,3 +109,53 @@ def test_scenario_frame_matches_the_snapshot_accessor():
         assert rel_err(scenario_frame(s, r, 'Vmag', 1).values, s.get_data_frame('Vmag').values) > 1e-4
         with pytest.raises(KeyError):
             scenario_frame(s, r, 'nope', 0)
+
+
+def test_chained_study_matches_the_warm_started_oracle():
+    """DerStudy.run_chained (hour k of a chain starts from hour k - 1) against the oracle driven the
+    way a reused reference object runs (oracle/make_golden_warm.py pins that to the reference)."""
+    import bench
+    from gigpower_b200.dss_reader import read_dss
+    from gigpower_b200.study import DerStudy
+    from oracle.gp_oracle import FBSOracle
+    sol = _fbs123()
+    t = sol.tables
+    m_h, pv_h, mask, pen = _c4_tables(t.n_srows)
+    study = DerStudy(sol, m_h, pv_h, mask, pen)
+    L, first_chain, chains = 24, 365 * 7 + 100, 20
+    out = study.run_chained(chain_hours=L, first_chain=first_chain, chains=chains)
+    o = FBSOracle(read_dss(os.path.join(REPO, 'gigpower_b200', 'feeders', 'ieee123_allwye_noxfm_noreg.dss')))
+    W0 = sol.load_weights().sum(axis=1)
+    b, p = np.nonzero(t.srow >= 0)
+    V0 = I0 = None
+    its, loss = np.zeros((chains, L), np.int64), np.zeros((chains, L), complex)
+    for k in range(L):
+        rows = np.concatenate([bench.make_der_rows(W0, 1, (first_chain + c) * L + k) for c in range(chains)], axis=1)
+        spu = np.zeros((chains, o.c.nb, 3), complex)
+        spu[:, b, p] = rows[t.srow[b, p]].T
+        r = o.solve(spu, V0=V0 if k else None, I0=I0 if k else None)
+        V0, I0 = r['V'], r['I']
+        its[:, k], loss[:, k] = r['iterations'], (r['Stx'] - r['Srx']).sum(axis=(1, 2))
+    assert np.array_equal(out['iterations'].reshape(chains, L), its)
+    assert (out['status'] == 0).all()
+    assert rel_err(out['loss'].reshape(chains, L), loss) <= 1e-9
+    # against the flat-started study: same solutions within the solver tolerance, fewer sweeps
+    flat = study.run(first=first_chain * L, count=chains * L)
+    assert np.abs(out['vmin'] - flat['vmin']).max() <= 1e-5
+    assert out['iterations'].sum() < flat['iterations'].sum()
+    assert np.array_equal(out['iterations'].reshape(chains, L)[:, 0], flat['iterations'].reshape(chains, L)[:, 0])
+
+
+def test_chained_study_nr3_agrees_with_the_flat_study():
+    from gigpower_b200.solution_nr3 import SolutionNR3
+    from gigpower_b200.study import DerStudy
+    sol = SolutionNR3(os.path.join(REPO, 'gigpower_b200', 'feeders', 'ieee123_allwye_noxfm_noreg.dss'))
+    m_h, pv_h, mask, pen = _c4_tables(sol.tables.n_srows)
+    study = DerStudy(sol, m_h, pv_h, mask, pen)
+    out = study.run_chained(chain_hours=12, first_chain=4000, chains=64)
+    flat = study.run(first=4000 * 12, count=64 * 12)
+    assert (out['status'] == 0).all()
+    assert np.abs(out['vmin'] - flat['vmin']).max() <= 1e-8 and rel_err(out['loss'], flat['loss']) <= 1e-8
+    assert out['iterations'].sum() < flat['iterations'].sum()
+    with pytest.raises(ValueError):
+        study.run_chained(chain_hours=7)
