@@ -11,12 +11,14 @@ for N > 1, on a side stream so that it overlaps the next step's solve).  Steps
 rotate over enough buffer sets that nothing is found in L2 from the last use.  At N=1 the default
 workload is BASELINE config C2 (IEEE 13-bus FBS, 65,536 random load-multiplier
 scenarios).  One process per GPU under torchrun; scenarios are sharded with no
-data-path collective, the only exchange is the final NCCL gather of |V| and
-losses.  Prints ONE JSON line on rank 0.
+data-path collective, the only exchange is the final all-gather of |V| and
+losses: stores from the solve kernel's epilogue (or copy-engine pushes) into every rank's
+peer-mapped buffer over NVLink, or NCCL with --gather nccl.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -55,6 +57,29 @@ WORKLOADS = {
     'fbs34': ('IEEE_34_Bus_allwye_noxfm_noreg.json', 'fbs', 65536, 34, (0.5, 1.3),
               'IEEE 34-bus FBS, 65,536 scenarios'),
 }
+
+
+_JSON_FD = None
+
+
+def protect_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back
+    (NCCL prints its version there when NCCL_DEBUG is set in the environment), so fd 1 is pointed at
+    stderr for the whole run and the line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def peaks():
@@ -298,7 +323,7 @@ def run_reference(args, wl):
         'e2e': {'value': value, 'unit': 'solves/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------
@@ -344,6 +369,7 @@ def run_ours(args, wl):
     maxiter = sol.maxiter
     tol = sol.tolerance if solver == 'fbs' else 0.0
     fused = active == 5     # the specialised FBS kernel writes |V| and losses itself
+    pg = None               # peer-mapped gather buffers (world > 1, --gather peer)
     wbytes = int(_cabi.gp_nr3_workspace_bytes(h, ld)) if solver == 'nr3' else 0
 
     class BufSet:
@@ -363,7 +389,7 @@ def run_ours(args, wl):
             else:
                 self.X = torch.empty((t.n_vrows + t.n_irows, ld), dtype=c128, device=dev)
                 self.work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
-            if world > 1:
+            if world > 1 and args.gather == 'nccl':
                 self.Vmag_all = torch.empty((world, t.n_vrows, ld), dtype=f64, device=dev)
                 self.loss_all = torch.empty((world, S), dtype=c128, device=dev)
             self.gathered = None        # event: the gather that last read this set has finished
@@ -372,8 +398,17 @@ def run_ours(args, wl):
             return sum(v.numel() * v.element_size() for k, v in vars(self).items()
                        if hasattr(v, 'numel') and not k.endswith('_all'))
 
-        def solve(self):
-            if solver == 'fbs' and fused:
+        def solve(self, slot=0):
+            if solver == 'fbs' and fused and pg is not None:
+                # one launch: solve + |V| + losses + all-gather (the epilogue stores each scenario's |V| rows
+                # and loss into block `rank` of every rank's gather buffer over NVLink)
+                ex = _cabi.make_extras(peers=pg.destinations(slot))
+                _cabi.check(_cabi.gp_fbs_solve_batch_ex(h, S, ld, self.spu.data_ptr(), ctypes.byref(ex),
+                                                        self.V.data_ptr(), self.I.data_ptr(), self.iters.data_ptr(),
+                                                        self.status.data_ptr(), self.diff.data_ptr(),
+                                                        self.Vmag.data_ptr(), self.loss.data_ptr(), tol, maxiter,
+                                                        stream.cuda_stream))
+            elif solver == 'fbs' and fused:
                 _cabi.check(_cabi.gp_fbs_solve_post_batch(h, S, ld, self.spu.data_ptr(), self.V.data_ptr(),
                                                           self.I.data_ptr(), self.iters.data_ptr(),
                                                           self.status.data_ptr(), self.diff.data_ptr(),
@@ -399,14 +434,21 @@ def run_ours(args, wl):
                                                     None, None, None, None, self.Vmag.data_ptr(),
                                                     self.loss.data_ptr(), stream.cuda_stream))
 
-        def gather(self):
-            """The path's one exchange (|V| and losses of every rank), on the side stream."""
+        def gather(self, slot=0):
+            """The path's one exchange (|V| and losses of every rank), on the side stream: copy-engine
+            pushes into every rank's peer-mapped buffer, or (--gather nccl) an NCCL all-gather.  The
+            feeder-specialised FBS kernel has already done it from its epilogue."""
+            if pg is not None and fused:
+                return
             done = torch.cuda.Event()
             done.record(stream)
             side.wait_event(done)
             with torch.cuda.stream(side):
-                dist.all_gather_into_tensor(self.Vmag_all, self.Vmag)
-                dist.all_gather_into_tensor(self.loss_all, self.loss)
+                if pg is not None:
+                    pg.push(slot, self.Vmag, self.loss, stream=side)
+                else:
+                    dist.all_gather_into_tensor(self.Vmag_all, self.Vmag)
+                    dist.all_gather_into_tensor(self.loss_all, self.loss)
                 self.gathered = torch.cuda.Event()
                 self.gathered.record(side)
 
@@ -414,17 +456,24 @@ def run_ours(args, wl):
     sets = [BufSet()]
     n_sets = max(1, min(8, -(-int(2.5 * L2_BYTES) // sets[0].nbytes())))
     sets += [BufSet() for _ in range(n_sets - 1)]
+    n_slots = max(2, n_sets)
+    if world > 1 and args.gather == 'peer':
+        from gigpower_b200.sharding import PeerGather
+        pg = PeerGather(t.n_vrows, ld, slots=n_slots)
 
     def step(k):
         b = sets[k % n_sets]
-        if b.gathered is not None:
+        fused_gather = pg is not None and fused
+        if b.gathered is not None and (fused or pg is None):
             stream.wait_event(b.gathered)       # the previous gather out of this set's buffers is done
-        b.solve()
+        b.solve(k % n_slots)
         mid = torch.cuda.Event(enable_timing=True)
         mid.record(stream)
-        b.post()
-        if world > 1:
-            b.gather()
+        if b.gathered is not None and not (fused or pg is None):
+            stream.wait_event(b.gathered)       # |V| and losses of this set are still being pushed: only the
+        b.post()                                # kernels that overwrite them wait, not the solve
+        if world > 1 and not fused_gather:
+            b.gather(k % n_slots)
         return mid
 
     def barrier():
@@ -454,6 +503,15 @@ def run_ours(args, wl):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = _cabi.gp_launch_count() - launches0
+    if pg is not None:
+        # every rank's last step sits in block r of the slot on this rank
+        slot = (args.steps - 1) % n_slots
+        mine = sets[(args.steps - 1) % n_sets]
+        got = pg.vmag_all(slot)
+        assert torch.equal(got[rank], mine.Vmag), 'gathered |V| differs from the local result'
+        assert torch.equal(pg.loss_all(slot)[rank], mine.loss), 'gathered losses differ from the local result'
+        other = got[(rank + 1) % world]
+        assert bool(torch.isfinite(other).all()) and float(other.min()) > 0.3, 'peer block not filled'
     ms_total = e_begin.elapsed_time(e_end)
     ms_solve = np.array([e0[k].elapsed_time(mids[k]) for k in range(args.steps)])
     tot_ms = torch.tensor([ms_total], dtype=f64, device=dev)
@@ -572,7 +630,9 @@ def run_ours(args, wl):
             fronts = int((8 * ((2 * nph) ** 2 + 4 * nph)).sum())
             per_it = 2 * 16 * (t.n_vrows + t.n_irows) + 16 * t.n_srows + 2 * 16 * t.n_vrows + 2 * fronts
             once = 16 * (t.n_vrows + t.n_irows)
-            kname = 'nr3_solve_kernel'
+            phase_lanes = args.nr3_kernel == 2 or (args.nr3_kernel == 0 and bool((np.asarray(t.kind) == 0).all())
+                                                   and S <= 32768)      # the library's automatic choice
+            kname = 'nr3_phase_kernel' if phase_lanes else 'nr3_solve_kernel'
         alg_bytes = n_it * per_it + S * once            # solve kernel, per launch
         achieved = alg_bytes / (solve_ms * 1e-3) / 1e9
         traffic = ncu_traffic(args.workload, kname)
@@ -582,7 +642,6 @@ def run_ours(args, wl):
                     'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': solve_ms,
                     'kernel_share_of_step': solve_ms / float(np.mean(ms_steps))}
         if solver == 'fbs' and active in (4, 5):
-            import ctypes
             tf = ctypes.c_double(0.0)
             _cabi.check(_cabi.gp_measure_fp64_peak(local, ctypes.byref(tf)))
             flops = n_it * fbs_flops_per_iteration(t)
@@ -611,7 +670,13 @@ def run_ours(args, wl):
                        'timing': 'CUDA events around the K back-to-back steps on the launch stream (gather of step k '
                                  'on a side stream, overlapping the solve of step k+1), max over ranks; solve kernels '
                                  'timed individually for the roofline',
-                       'parallelism': f'scenario-sharded x{world}, final NCCL all-gather of |V| and losses'},
+                       'parallelism': f'scenario-sharded x{world}, ' + (
+                           'single GPU: no exchange' if world == 1 else
+                           'all-gather of |V| and losses by NCCL on a side stream' if pg is None else
+                           'all-gather of |V| and losses fused into the solve kernel (epilogue stores over NVLink into '
+                           'every rank\'s peer-mapped buffer)' if fused else
+                           'all-gather of |V| and losses by copy-engine pushes into every rank\'s peer-mapped buffer '
+                           'on a side stream')},
             'e2e': {'value': e2e_value, 'unit': 'solves/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
                     'api': e2e_api},
@@ -633,7 +698,7 @@ def run_ours(args, wl):
                 'value': n / wall, 'unit': 'solves/s', 'cores': pool.cores, 'kind': 'port',
                 'sample': f'{n} scenarios of the workload ({n_per} per core per call, {reps} calls, '
                           f'{wall:.1f} s), oracle/gp_oracle.py batched NumPy port on a process pool'}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -646,6 +711,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'],
+                    help='N > 1: the all-gather of |V| and losses through peer-mapped memory (fused into the '
+                         'specialised FBS kernel, copy-engine pushes otherwise) or by NCCL')
     ap.add_argument('--jit-ig', type=int, default=-1, choices=[-1, 0, 1],
                     help='I rows of the specialised FBS kernel in global memory: -1 automatic, 0 no, 1 yes')
     ap.add_argument('--nr3-kernel', type=int, default=0, choices=[0, 1, 2],
@@ -656,6 +724,7 @@ def main():
                          '1 = fused depth-first, 2 = phase-parallel lanes, 3 = two-sweep streaming, 4 = on-chip table-driven, '
                          '5 = on-chip feeder-specialised')
     args = ap.parse_args()
+    protect_stdout()
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':
         run_reference(args, wl)

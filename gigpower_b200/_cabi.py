@@ -92,7 +92,17 @@ gp_fbs_solve_batch_host = _sig('gp_fbs_solve_batch_host', C.c_int,
 
 class GpSolveExtras(C.Structure):
     """Optional per-scenario inputs of a solve (include/gigpower_b200.h: GpSolveExtras)."""
-    _fields_ = [('gamma_dev', vp), ('warm_start', C.c_int32), ('reserved', C.c_int32)]
+    _fields_ = [('gamma_dev', vp), ('warm_start', C.c_int32), ('n_peers', C.c_int32),
+                ('peer_vmag', C.POINTER(vp)), ('peer_loss', C.POINTER(vp))]
+
+
+GP_MAX_PEERS = 16
+GP_PEER_HANDLE_BYTES = 64
+gp_peer_alloc = _sig('gp_peer_alloc', C.c_int, [C.c_int, C.c_int64, C.POINTER(vp), vp])
+gp_peer_free = _sig('gp_peer_free', C.c_int, [C.c_int, vp])
+gp_peer_open = _sig('gp_peer_open', C.c_int, [C.c_int, vp, C.POINTER(vp)])
+gp_peer_close = _sig('gp_peer_close', C.c_int, [C.c_int, vp])
+gp_peer_push = _sig('gp_peer_push', C.c_int, [C.c_int, C.c_int32, C.POINTER(vp), vp, C.c_int64, vp])
 
 
 gp_gamma_rows = _sig('gp_gamma_rows', C.c_int, [vp])
@@ -122,17 +132,27 @@ EXPORTS = ['gp_version', 'gp_last_error', 'gp_launch_count', 'gp_set_option', 'g
            'gp_jit_compile', 'gp_fbs_create', 'gp_feeder_destroy',
            'gp_fbs_solve_batch', 'gp_fbs_solve_post_batch', 'gp_fbs_post', 'gp_fbs_solve_batch_host', 'gp_der_rows', 'gp_vmag_summary', 'gp_nr3_create',
            'gp_nr3_workspace_bytes', 'gp_nr3_solve_batch', 'gp_nr3_map_output',
-           'gp_gamma_rows', 'gp_fbs_solve_batch_ex', 'gp_nr3_solve_batch_ex', 'gp_der_rows_strided']
+           'gp_gamma_rows', 'gp_fbs_solve_batch_ex', 'gp_nr3_solve_batch_ex', 'gp_der_rows_strided',
+           'gp_peer_alloc', 'gp_peer_free', 'gp_peer_open', 'gp_peer_close', 'gp_peer_push']
 
 
-def make_extras(gamma=None, warm_start=False):
-    """GpSolveExtras for a device tensor of regulator ratios ``[n_gamma_rows, ld]`` float64 and / or a
-    warm start; returns None when neither is asked for."""
-    if gamma is None and not warm_start:
+def make_extras(gamma=None, warm_start=False, peers=None):
+    """GpSolveExtras for a device tensor of regulator ratios ``[n_gamma_rows, ld]`` float64, a warm
+    start and / or the destinations of the fused all-gather (``peers`` = (|V| pointers, loss pointers),
+    two equally long lists of device addresses); returns None when nothing is asked for."""
+    if gamma is None and not warm_start and not peers:
         return None
     ex = GpSolveExtras()
     ex.gamma_dev = gamma.data_ptr() if gamma is not None else None
     ex.warm_start = 1 if warm_start else 0
+    if peers:
+        vm, ls = peers
+        if len(vm) != len(ls) or not 0 < len(vm) <= GP_MAX_PEERS:
+            raise ValueError(f'need 1..{GP_MAX_PEERS} peer destinations')
+        ex._keep = ((vp * len(vm))(*[int(x) for x in vm]), (vp * len(ls))(*[int(x) for x in ls]))
+        ex.n_peers = len(vm)
+        ex.peer_vmag = C.cast(ex._keep[0], C.POINTER(vp))
+        ex.peer_loss = C.cast(ex._keep[1], C.POINTER(vp))
     return ex
 
 

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, 'libgigpower_b200.so')
-SOURCES = ['gp_fbs.cu', 'gp_fbs_jit.cu', 'gp_nr3.cu', 'gp_study.cu']
+SOURCES = ['gp_fbs.cu', 'gp_fbs_jit.cu', 'gp_nr3.cu', 'gp_study.cu', 'gp_peer.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
          '-Xcompiler', '-fPIC', '-shared', '--use_fast_math=false'.replace('--use_fast_math=false', '-Xptxas=-v')]

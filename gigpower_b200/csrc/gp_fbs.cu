@@ -957,7 +957,7 @@ __global__ void fbs_post_rows_kernel(int n_vrows, const int* __restrict__ vrow_s
                                      const double* __restrict__ vrow_cap, FbsConst k, long long S,
                                      long long ld, const double2* __restrict__ spu,
                                      const double2* __restrict__ V, double2* __restrict__ sV,
-                                     double* __restrict__ Vmag) {
+                                     double* __restrict__ Vmag, const PeerDst peers) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     for (int r = blockIdx.y; r < n_vrows; r += gridDim.y) {
@@ -965,6 +965,9 @@ __global__ void fbs_post_rows_kernel(int n_vrows, const int* __restrict__ vrow_s
         double a;
         const double a2 = cabs2(v, a);
         if (Vmag) Vmag[(long long)r * ld + s] = a;
+#pragma unroll
+        for (int q = 0; q < GP_MAX_PEERS; ++q)      // fused all-gather: the same value to every rank's buffer
+            if (q < peers.n) peers.vmag[q][(long long)r * ld + s] = a;
         if (sV) {
             double2 sv = make_double2(0.0, 0.0);
             const int lr = __ldg(vrow_srow + r);
@@ -983,7 +986,7 @@ __global__ void fbs_post_rows_kernel(int n_vrows, const int* __restrict__ vrow_s
 __global__ void fbs_post_lines_kernel(int n_lines, const int* __restrict__ lines, long long S,
                                       long long ld, const double2* __restrict__ V,
                                       const double2* __restrict__ I, double2* __restrict__ Stx,
-                                      double2* __restrict__ Srx, double2* __restrict__ loss) {
+                                      double2* __restrict__ Srx, double2* __restrict__ loss, const PeerDst peers) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     double2 acc = make_double2(0.0, 0.0);
@@ -1007,6 +1010,9 @@ __global__ void fbs_post_lines_kernel(int n_lines, const int* __restrict__ lines
         }
     }
     if (loss) loss[s] = acc;
+#pragma unroll
+    for (int q = 0; q < GP_MAX_PEERS; ++q)
+        if (q < peers.n) peers.loss[q][s] = acc;
 }
 
 }  // namespace gp
@@ -1523,7 +1529,8 @@ static int fbs_check(GpFeeder* f, int64_t S, int64_t ld, const char* who) {
 // mapped host memory too (the kernel's final stores go straight over PCIe).
 static int fbs_jit_launch(FbsImpl* im, int64_t S, int64_t ld, const double* spu, double* V, double* I,
                           int32_t* iters, int32_t* status, double* diff, double tol, int32_t maxiter,
-                          cudaStream_t st, double* Vmag, double* loss, void* stage, double* Iout) {
+                          cudaStream_t st, double* Vmag, double* loss, void* stage, double* Iout,
+                          const PeerDst* peers = nullptr) {
     const long long n_tiles = (S + 31) / 32;
     const int nw = im->jit_warps;
     long long blocks = (n_tiles + nw - 1) / nw;
@@ -1533,12 +1540,30 @@ static int fbs_jit_launch(FbsImpl* im, int64_t S, int64_t ld, const double* spu,
     double tol_arg = tol;
     int maxiter_arg = maxiter;
     unsigned ldb_arg = (unsigned)(ld * 16);
+    PeerDst pd;
+    memset(&pd, 0, sizeof(pd));
+    if (peers) pd = *peers;
     void* args[] = {(void*)&spu, (void*)&V, (void*)&I, (void*)&iters, (void*)&status, (void*)&diff,
                     (void*)&S_arg, (void*)&ldb_arg, (void*)&tol_arg, (void*)&maxiter_arg, (void*)&im->d_sched,
-                    (void*)&Vmag, (void*)&loss, (void*)&stage, (void*)&Iout};
+                    (void*)&Vmag, (void*)&loss, (void*)&stage, (void*)&Iout, (void*)&pd};
     const int cr = driver().LaunchKernel(im->jit_kernel, (unsigned)blocks, 1, 1, (unsigned)nw * 32, 1, 1, smem,
                                          (void*)st, args, nullptr);
     if (cr != 0) return fail(GP_ECUDA, "gp_fbs_solve_batch: cuLaunchKernel failed (%d)", cr);
+    return GP_OK;
+}
+
+// GpSolveExtras.peer_* -> the by-value kernel argument
+static int peers_from_extras(const GpSolveExtras* ex, PeerDst& pd) {
+    memset(&pd, 0, sizeof(pd));
+    if (!ex || ex->n_peers == 0) return GP_OK;
+    if (ex->n_peers < 0 || ex->n_peers > GP_MAX_PEERS || !ex->peer_vmag || !ex->peer_loss)
+        return fail(GP_EINVAL, "GpSolveExtras: n_peers must be 0..%d with both pointer arrays set", GP_MAX_PEERS);
+    for (int q = 0; q < ex->n_peers; ++q) {
+        if (!ex->peer_vmag[q] || !ex->peer_loss[q]) return fail(GP_EINVAL, "GpSolveExtras: null peer destination %d", q);
+        pd.vmag[q] = ex->peer_vmag[q];
+        pd.loss[q] = (double2*)ex->peer_loss[q];
+    }
+    pd.n = ex->n_peers;
     return GP_OK;
 }
 
@@ -1557,6 +1582,9 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     if (warm != 0 && warm != 1) return fail(GP_EINVAL, "gp_fbs_solve_batch_ex: warm_start must be 0 or 1");
     if (gam && im->n_grows == 0) gam = nullptr;     // no regulators: nothing to read
     const bool extras = gam || warm;
+    PeerDst pd;
+    rc = peers_from_extras(ex, pd);
+    if (rc) return rc;
     if (!V || !I || !iters || !status || !diff || (!spu && im->n_srows > 0))
         return fail(GP_EINVAL, "gp_fbs_solve_batch: null buffer");
     if (ld * 16 >= ((int64_t)1 << 32))
@@ -1583,7 +1611,8 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     } else if ((g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) && (maxiter >= 1 || !im->jit_kernel)) {
         if (!im->jit_kernel)
             return fail(GP_EINVAL, "gp_fbs_solve_batch: fbs_kernel = 5 needs a successful gp_fbs_specialise");
-        rc = fbs_jit_launch(im, S, ld, spu, V, I, iters, status, diff, tol, maxiter, st, Vmag, loss, nullptr, nullptr);
+        rc = fbs_jit_launch(im, S, ld, spu, V, I, iters, status, diff, tol, maxiter, st, Vmag, loss, nullptr, nullptr,
+                            &pd);
         if (rc) return rc;
         *fused = true;
     } else if (onchip) {
@@ -1660,13 +1689,19 @@ extern "C" int gp_fbs_solve_post_batch(GpFeeder* f, int64_t S, int64_t ld, const
     return gp_fbs_post(f, S, ld, spu, V, I, nullptr, Vmag, nullptr, nullptr, loss, stream);
 }
 
+static int fbs_post_impl(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const double* V, const double* I,
+                         double* sV, double* Vmag, double* Stx, double* Srx, double* loss, void* stream,
+                         const PeerDst& pd);
+
 extern "C" int gp_fbs_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const GpSolveExtras* ex,
                                      double* V, double* I, int32_t* iters, int32_t* status, double* diff,
                                      double* Vmag, double* loss, double tol, int32_t maxiter, void* stream) {
     bool fused;
     int rc = fbs_solve_launch(f, S, ld, spu, V, I, iters, status, diff, tol, maxiter, stream, Vmag, loss, &fused, ex);
-    if (rc || fused || S == 0 || (!Vmag && !loss)) return rc;
-    return gp_fbs_post(f, S, ld, spu, V, I, nullptr, Vmag, nullptr, nullptr, loss, stream);
+    PeerDst pd;
+    if (!rc) rc = peers_from_extras(ex, pd);
+    if (rc || fused || S == 0 || (!Vmag && !loss && pd.n == 0)) return rc;
+    return fbs_post_impl(f, S, ld, spu, V, I, nullptr, Vmag, nullptr, nullptr, loss, stream, pd);
 }
 
 extern "C" int gp_gamma_rows(GpFeeder* f) {
@@ -1677,6 +1712,14 @@ extern "C" int gp_gamma_rows(GpFeeder* f) {
 extern "C" int gp_fbs_post(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const double* V,
                            const double* I, double* sV, double* Vmag, double* Stx, double* Srx,
                            double* loss, void* stream) {
+    PeerDst pd;
+    memset(&pd, 0, sizeof(pd));
+    return fbs_post_impl(f, S, ld, spu, V, I, sV, Vmag, Stx, Srx, loss, stream, pd);
+}
+
+static int fbs_post_impl(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const double* V, const double* I,
+                         double* sV, double* Vmag, double* Stx, double* Srx, double* loss, void* stream,
+                         const PeerDst& pd) {
     int rc = fbs_check(f, S, ld, "gp_fbs_post");
     if (rc) return rc;
     if (S == 0) return GP_OK;
@@ -1687,16 +1730,16 @@ extern "C" int gp_fbs_post(GpFeeder* f, int64_t S, int64_t ld, const double* spu
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int BLOCK = 128;
     const unsigned gx = (unsigned)((S + BLOCK - 1) / BLOCK);
-    if (sV || Vmag) {
+    if (sV || Vmag || pd.n) {
         dim3 g(gx, 8);
         fbs_post_rows_kernel<<<g, BLOCK, 0, st>>>(im->n_vrows, im->d_vrow_srow, im->d_vrow_cap, im->k, S, ld,
-                                                  (const double2*)spu, (const double2*)V, (double2*)sV, Vmag);
+                                                  (const double2*)spu, (const double2*)V, (double2*)sV, Vmag, pd);
         count_launch();
     }
-    if (Stx || Srx || loss) {
+    if (Stx || Srx || loss || pd.n) {
         fbs_post_lines_kernel<<<gx, BLOCK, 0, st>>>(im->n_lines, im->d_lines, S, ld, (const double2*)V,
                                                     (const double2*)I, (double2*)Stx, (double2*)Srx,
-                                                    (double2*)loss);
+                                                    (double2*)loss, pd);
         count_launch();
     }
     GP_CUDA(cudaGetLastError());

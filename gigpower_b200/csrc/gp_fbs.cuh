@@ -29,6 +29,14 @@ struct __align__(16) FbsStep {
 };
 static_assert(sizeof(FbsStep) == 64 + 32 + 32 + 32 + 144 + 16, "FbsStep layout");
 
+// Destinations of the fused all-gather (GpSolveExtras.peer_vmag / peer_loss), passed to kernels by value
+struct PeerDst {
+    double* vmag[GP_MAX_PEERS];
+    double2* loss[GP_MAX_PEERS];
+    int n;
+    int pad;
+};
+
 struct FbsConst {
     int root_vrow[3];
     int root_load_srow[3];

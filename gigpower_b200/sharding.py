@@ -67,3 +67,124 @@ def solve_sharded(solution, spu_rows: np.ndarray, outputs=('Vmag', 'loss'), grou
     if 'loss' in outputs:
         out['loss'] = gather_rows(res.loss, S, group)
     return out
+
+
+class _DevArray:
+    """Raw device memory as something ``torch.as_tensor`` wraps without a copy."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False),
+                                         'version': 3, 'strides': None}
+
+
+class PeerGather:
+    """The path's one exchange without a collective kernel.
+
+    Every rank owns ``slots`` gather buffers, each ``[world][n_vrows][ld]`` float64 (|V|) plus
+    ``[world][ld]`` complex128 (losses), allocated through ``gp_peer_alloc`` and mapped into every
+    other rank's process with CUDA IPC (``gp_peer_open``; the handles travel through
+    ``torch.distributed.all_gather_object`` - NCCL or gloo, control plane only).  A rank's solve
+    then writes block ``rank`` of the chosen slot on EVERY rank: either the solve kernel's own
+    epilogue does it (``solve_batch(gather=(pg, slot))``, stores over NVLink / NVSwitch that
+    overlap the next tile), or ``push`` moves finished rows with the copy engines.  Nothing
+    competes with the solve for SMs, which is what an NCCL all-gather next to a persistent
+    one-block-per-SM kernel does (measured on 8 x B200: the two serialise).
+
+    ``wait()`` makes a slot readable: this rank's stream work is complete and so is every
+    other rank's (barrier).  Re-using a slot needs the same wait on the reader's side first.
+    """
+
+    def __init__(self, n_vrows: int, ld: int, slots: int = 1, group=None, device=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _cabi
+        self._cabi, self._C, self._torch = _cabi, C, torch
+        self.group = group
+        multi = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if multi else 1
+        self.rank = dist.get_rank(group) if multi else 0
+        if self.world > _cabi.GP_MAX_PEERS:
+            raise ValueError(f'at most {_cabi.GP_MAX_PEERS} ranks')
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.n_vrows, self.ld, self.slots = int(n_vrows), int(ld), int(slots)
+        self.vmag_bytes = self.world * self.n_vrows * self.ld * 8
+        self.loss_bytes = self.world * self.ld * 16
+        self.slot_bytes = (self.vmag_bytes + self.loss_bytes + 255) // 256 * 256
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(_cabi.GP_PEER_HANDLE_BYTES)
+        _cabi.check(_cabi.gp_peer_alloc(self.device, self.slot_bytes * self.slots, C.byref(ptr), handle))
+        self._local = ptr.value
+        self.bases = [None] * self.world                 # base address of every rank's buffer in THIS process
+        self.bases[self.rank] = self._local
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (self.rank, bytes(handle.raw)), group=group)
+            for r, h in handles:
+                if r == self.rank:
+                    continue
+                p = C.c_void_p()
+                _cabi.check(_cabi.gp_peer_open(self.device, C.create_string_buffer(h, len(h)), C.byref(p)))
+                self.bases[r] = p.value
+            dist.barrier(group=group)
+
+    # ---- addresses -----------------------------------------------------------------------
+    def destinations(self, slot: int):
+        """(|V| addresses, loss addresses): block ``rank`` of ``slot`` in every rank's buffer, in the
+        order rank + 1, rank + 2, ..., rank: at any moment the ranks of a box then write to DIFFERENT
+        peers (a permutation) instead of all converging on rank 0's NVLink ingress first."""
+        if not 0 <= slot < self.slots:
+            raise ValueError('no such slot')
+        off = slot * self.slot_bytes
+        order = [(self.rank + 1 + i) % self.world for i in range(self.world)]
+        vm = [self.bases[q] + off + self.rank * self.n_vrows * self.ld * 8 for q in order]
+        ls = [self.bases[q] + off + self.vmag_bytes + self.rank * self.ld * 16 for q in order]
+        return vm, ls
+
+    def vmag_all(self, slot: int):
+        """``[world, n_vrows, ld]`` float64 view of this rank's copy of ``slot`` (no copy)."""
+        dev = self._torch.device('cuda', self.device)
+        a = _DevArray(self._local + slot * self.slot_bytes, (self.world, self.n_vrows, self.ld), '<f8')
+        return self._torch.as_tensor(a, device=dev)
+
+    def loss_all(self, slot: int):
+        """``[world, ld]`` complex128 view of this rank's copy of ``slot`` (no copy)."""
+        dev = self._torch.device('cuda', self.device)
+        a = _DevArray(self._local + slot * self.slot_bytes + self.vmag_bytes, (self.world, self.ld), '<c16')
+        return self._torch.as_tensor(a, device=dev)
+
+    # ---- copy-engine transport -----------------------------------------------------------
+    def push(self, slot: int, Vmag_rows, loss, stream=None):
+        """All-gather step for results that already sit in device memory (the streaming and NR3
+        kernels): DMA ``Vmag_rows [n_vrows, ld]`` and ``loss [ld]`` into block ``rank`` of ``slot``
+        on every rank, asynchronously on ``stream``."""
+        C, _cabi, torch = self._C, self._cabi, self._torch
+        st = torch.cuda.current_stream(self.device) if stream is None else stream
+        vm, ls = self.destinations(slot)
+        n = len(vm)
+        arr_v, arr_l = (C.c_void_p * n)(*vm), (C.c_void_p * n)(*ls)
+        _cabi.check(_cabi.gp_peer_push(self.device, n, arr_v, Vmag_rows.data_ptr(), self.n_vrows * self.ld * 8,
+                                       st.cuda_stream))
+        _cabi.check(_cabi.gp_peer_push(self.device, n, arr_l, loss.data_ptr(), self.ld * 16, st.cuda_stream))
+
+    def wait(self, stream=None):
+        """After this returns every rank's contribution issued before its own ``wait`` is in place."""
+        import torch.distributed as dist
+        (self._torch.cuda.current_stream(self.device) if stream is None else stream).synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def close(self):
+        if getattr(self, '_local', None) is None:
+            return
+        import torch.distributed as dist
+        self._torch.cuda.synchronize(self.device)
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)             # nobody is still writing into a buffer about to go
+        for r, b in enumerate(self.bases):
+            if r != self.rank and b is not None:
+                self._cabi.gp_peer_close(self.device, b)
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)             # every mapping is closed before the memory is freed
+        self._cabi.gp_peer_free(self.device, self._local)
+        self._local = None

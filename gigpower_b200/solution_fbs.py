@@ -176,7 +176,7 @@ class SolutionFBS(Solution):
     # ---- batched solve -------------------------------------------------------
     def solve_batch(self, spu=None, load_mult=None, spu_rows=None, outputs=('V', 'Vmag', 'loss'),
                     maxiter=None, tol=None, return_device=False, stream=None, taps=None,
-                    warm_start=None) -> BatchResult:
+                    warm_start=None, gather=None) -> BatchResult:
         """Solve S scenarios from flat start.
 
         Give ONE of: ``spu`` ``[S, nb, 3]`` complex; ``load_mult`` ``[S, n_loads]``
@@ -191,6 +191,10 @@ class SolutionFBS(Solution):
         with the same number of scenarios; the sweep continues from its V and I (what the reference
         does when ``Vtest`` and ``iterations`` are reset and ``solve()`` is called again) instead of
         the flat start, and the result's V/I tensors are the SAME device tensors, updated in place.
+        ``gather``: ``(PeerGather, slot)`` (``gigpower_b200.sharding``): the solve also stores this rank's
+        |V| rows and losses into that slot of every rank's gather buffer (the all-gather of SURVEY.md
+        8(e), fused into the kernel epilogue); read them with ``PeerGather.vmag_all / loss_all`` after
+        ``PeerGather.wait()``.  The batch must have the PeerGather's per-rank size.
         """
         torch, dev = self._dev()
         t = self.tables
@@ -224,7 +228,14 @@ class SolutionFBS(Solution):
                     V = torch.empty((t.n_vrows, ld), dtype=torch.complex128, device=dev)
                     I = torch.empty((max(t.n_irows, 1), ld), dtype=torch.complex128, device=dev)
                 gamma = self.gamma_rows_from_taps(taps, S, dev) if taps is not None else None
-                extras = _cabi.make_extras(gamma, warm_start is not None)
+                peers = None
+                if gather is not None:
+                    pg, slot = gather
+                    if (pg.n_vrows, pg.ld) != (t.n_vrows, ld):
+                        raise ValueError(f'gather buffers are for [{pg.n_vrows}, {pg.ld}] blocks, this batch is '
+                                         f'[{t.n_vrows}, {ld}]')
+                    peers = pg.destinations(slot)
+                extras = _cabi.make_extras(gamma, warm_start is not None, peers)
                 iters = torch.empty(S, dtype=torch.int32, device=dev)
                 status = torch.empty(S, dtype=torch.int32, device=dev)
                 diff = torch.empty(S, dtype=torch.float64, device=dev)

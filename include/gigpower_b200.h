@@ -240,12 +240,43 @@ int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const double* sp
  *   NR3: X_dev holds it (SolutionNR3.solve() starts from self.XNR, solution_nr3.py:598).  The stop
  *   rules are unchanged, so a warm-started scenario usually needs fewer iterations and its result
  *   differs from the flat-started one within the solver tolerance.
+ *
+ * n_peers, peer_vmag, peer_loss: the path's one exchange (the all-gather of per-scenario
+ *   voltage magnitudes and losses across the GPUs of a box) fused into the solve.  Each destination is
+ *   this rank's block inside the gather buffer of one GPU - its own or a peer's, mapped into this
+ *   process with gp_peer_open - and receives what Vmag_dev / loss_dev receive, written by the same kernel
+ *   epilogue with plain stores that travel over NVLink / NVSwitch while the next tile is being solved
+ *   (no collective kernel, no SM taken from the solve).  With the feeder-specialised kernel that is one
+ *   launch for solve + |V| + losses + all-gather; with the other kernels the |V| and loss kernels
+ *   (gp_fbs_post / gp_nr3_map_output) do the stores.  Completion is the completion of the stream's
+ *   work on every rank: consumers synchronise their stream and then cross a rank barrier.
  */
+#define GP_MAX_PEERS 16
 typedef struct {
     const double* gamma_dev;
     int32_t warm_start;
-    int32_t reserved;
+    int32_t n_peers;            /* fused all-gather of |V| and losses: number of destinations (0 = none)     */
+    double* const* peer_vmag;   /* host array [n_peers] of device pointers, each a [n_vrows][ld] double block */
+    double* const* peer_loss;   /* host array [n_peers] of device pointers, each a [S] complex block          */
 } GpSolveExtras;
+
+/*
+ * Peer memory for the fused all-gather (one process per GPU: CUDA IPC).
+ *   gp_peer_alloc  device memory that other processes of the box can map; `handle_out` receives the
+ *                  GP_PEER_HANDLE_BYTES opaque bytes to send them (any channel: torch.distributed
+ *                  all_gather_object, a file, a pipe);
+ *   gp_peer_open   map a peer's allocation into this process (on this process' current device `device`,
+ *                  peer access over NVLink is enabled on demand); gp_peer_close unmaps it;
+ *   gp_peer_push   copy-engine all-gather step for results that already sit in device memory: copies
+ *                  `bytes` from src_dev to dst[q] for every q, asynchronously on `stream` (DMA over NVLink,
+ *                  no SM involved).
+ */
+#define GP_PEER_HANDLE_BYTES 64
+int gp_peer_alloc(int device, int64_t bytes, void** ptr_out, void* handle_out);
+int gp_peer_free(int device, void* ptr);
+int gp_peer_open(int device, const void* handle, void** ptr_out);
+int gp_peer_close(int device, void* ptr);
+int gp_peer_push(int device, int32_t n_dst, void* const* dst, const void* src_dev, int64_t bytes, void* stream);
 
 /* Number of rows of GpSolveExtras.gamma_dev for this feeder (0 = no regulators; negative = error). */
 int gp_gamma_rows(GpFeeder* f);

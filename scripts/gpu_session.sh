@@ -1,7 +1,7 @@
 #!/bin/bash
-# Full GPU session: parity tests, smoke, bench lines, ncu launch list and full captures (round 1b)
+# Full GPU session: parity tests, smoke, bench lines, ncu launch list and full captures
 mkdir -p gpurun_out
-T=${1:-r1b}
+T=${1:-r1c}
 timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/${T}_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/${T}_tests.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/${T}_smoke.log 2>&1; tail -1 gpurun_out/${T}_smoke.log
 timeout 600 python bench.py > gpurun_out/${T}_bench_c2.json 2> gpurun_out/${T}_bench_c2.err; echo "bench rc=$?"
@@ -21,4 +21,4 @@ PY
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches_c2.csv python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/${T}_ncu_l.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gp_fbs_jit -c 1 -s 4 -o gpurun_out/${T}_jit_c2 python bench.py --workload c2 --steps 2 --warmup 3 --no-cpu > gpurun_out/${T}_ncu1.log 2>&1; tail -1 gpurun_out/${T}_ncu1.log
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fbs_solve_kernel -c 1 -s 4 -o gpurun_out/${T}_stream_c4 python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu > gpurun_out/${T}_ncu2.log 2>&1; tail -1 gpurun_out/${T}_ncu2.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:nr3_ -c 1 -s 4 -o gpurun_out/${T}_nr3_c3 python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu > gpurun_out/${T}_ncu3.log 2>&1; tail -1 gpurun_out/${T}_ncu3.log
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:nr3_(solve|phase)_kernel' -c 1 -s 4 -o gpurun_out/${T}_nr3_c3 python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu > gpurun_out/${T}_ncu3.log 2>&1; tail -1 gpurun_out/${T}_ncu3.log
