@@ -402,7 +402,7 @@ def run_ours(args, wl):
             if solver == 'fbs' and fused and pg is not None:
                 # one launch: solve + |V| + losses + all-gather (the epilogue stores each scenario's |V| rows
                 # and loss into block `rank` of every rank's gather buffer over NVLink)
-                ex = _cabi.make_extras(peers=pg.destinations(slot))
+                ex = _cabi.make_extras(peers=pg.own_destination(slot) if args.gather == 'dma' else pg.destinations(slot))
                 _cabi.check(_cabi.gp_fbs_solve_batch_ex(h, S, ld, self.spu.data_ptr(), ctypes.byref(ex),
                                                         self.V.data_ptr(), self.I.data_ptr(), self.iters.data_ptr(),
                                                         self.status.data_ptr(), self.diff.data_ptr(),
@@ -438,13 +438,17 @@ def run_ours(args, wl):
             """The path's one exchange (|V| and losses of every rank), on the side stream: copy-engine
             pushes into every rank's peer-mapped buffer, or (--gather nccl) an NCCL all-gather.  The
             feeder-specialised FBS kernel has already done it from its epilogue."""
-            if pg is not None and fused:
+            if pg is not None and fused and args.gather != 'dma':
                 return
             done = torch.cuda.Event()
             done.record(stream)
             side.wait_event(done)
             with torch.cuda.stream(side):
-                if pg is not None:
+                if pg is not None and fused:
+                    pg.push_own(slot, stream=side)          # the kernel wrote this rank's block of its own buffer
+                    slot_pushed[slot] = torch.cuda.Event()
+                    slot_pushed[slot].record(side)
+                elif pg is not None:
                     pg.push(slot, self.Vmag, self.loss, stream=side)
                 else:
                     dist.all_gather_into_tensor(self.Vmag_all, self.Vmag)
@@ -457,13 +461,16 @@ def run_ours(args, wl):
     n_sets = max(1, min(8, -(-int(2.5 * L2_BYTES) // sets[0].nbytes())))
     sets += [BufSet() for _ in range(n_sets - 1)]
     n_slots = max(2, n_sets)
-    if world > 1 and args.gather == 'peer':
+    slot_pushed = {}
+    if world > 1 and args.gather in ('peer', 'dma'):
         from gigpower_b200.sharding import PeerGather
         pg = PeerGather(t.n_vrows, ld, slots=n_slots)
 
     def step(k):
         b = sets[k % n_sets]
-        fused_gather = pg is not None and fused
+        fused_gather = pg is not None and fused and args.gather != 'dma'
+        if (k % n_slots) in slot_pushed:
+            stream.wait_event(slot_pushed[k % n_slots])     # the DMA out of this slot's own block is done
         if b.gathered is not None and (fused or pg is None):
             stream.wait_event(b.gathered)       # the previous gather out of this set's buffers is done
         b.solve(k % n_slots)
@@ -673,6 +680,8 @@ def run_ours(args, wl):
                        'parallelism': f'scenario-sharded x{world}, ' + (
                            'single GPU: no exchange' if world == 1 else
                            'all-gather of |V| and losses by NCCL on a side stream' if pg is None else
+                           'all-gather of |V| and losses: the solve kernel writes this rank\'s block of its own gather '
+                           'buffer, copy engines push it to every peer on a side stream' if fused and args.gather == 'dma' else
                            'all-gather of |V| and losses fused into the solve kernel (epilogue stores over NVLink into '
                            'every rank\'s peer-mapped buffer)' if fused else
                            'all-gather of |V| and losses by copy-engine pushes into every rank\'s peer-mapped buffer '
@@ -711,7 +720,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'],
+    ap.add_argument('--gather', default='peer', choices=['peer', 'dma', 'nccl'],
                     help='N > 1: the all-gather of |V| and losses through peer-mapped memory (fused into the '
                          'specialised FBS kernel, copy-engine pushes otherwise) or by NCCL')
     ap.add_argument('--jit-ig', type=int, default=-1, choices=[-1, 0, 1],

@@ -72,21 +72,23 @@ def solve_sharded(solution, spu_rows: np.ndarray, outputs=('Vmag', 'loss'), grou
 class _DevArray:
     """Raw device memory as something ``torch.as_tensor`` wraps without a copy."""
 
-    def __init__(self, ptr, shape, typestr):
+    def __init__(self, ptr, shape, typestr, strides=None):
         self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False),
-                                         'version': 3, 'strides': None}
+                                         'version': 3, 'strides': tuple(strides) if strides else None}
 
 
 class PeerGather:
     """The path's one exchange without a collective kernel.
 
-    Every rank owns ``slots`` gather buffers, each ``[world][n_vrows][ld]`` float64 (|V|) plus
-    ``[world][ld]`` complex128 (losses), allocated through ``gp_peer_alloc`` and mapped into every
+    Every rank owns ``slots`` gather buffers, each made of ``world`` contiguous blocks - block r =
+    rank r's ``[n_vrows][ld]`` float64 |V| rows followed by its ``[ld]`` complex128 losses -
+    allocated through ``gp_peer_alloc`` and mapped into every
     other rank's process with CUDA IPC (``gp_peer_open``; the handles travel through
     ``torch.distributed.all_gather_object`` - NCCL or gloo, control plane only).  A rank's solve
     then writes block ``rank`` of the chosen slot on EVERY rank: either the solve kernel's own
     epilogue does it (``solve_batch(gather=(pg, slot))``, stores over NVLink / NVSwitch that
-    overlap the next tile), or ``push`` moves finished rows with the copy engines.  Nothing
+    overlap the next tile), or the copy engines move finished rows (``push``; ``push_own`` when the
+    solve wrote this rank's block of its own buffer, ``gather=(pg, slot, 'own')``).  Nothing
     competes with the solve for SMs, which is what an NCCL all-gather next to a persistent
     one-block-per-SM kernel does (measured on 8 x B200: the two serialise).
 
@@ -108,9 +110,9 @@ class PeerGather:
             raise ValueError(f'at most {_cabi.GP_MAX_PEERS} ranks')
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.n_vrows, self.ld, self.slots = int(n_vrows), int(ld), int(slots)
-        self.vmag_bytes = self.world * self.n_vrows * self.ld * 8
-        self.loss_bytes = self.world * self.ld * 16
-        self.slot_bytes = (self.vmag_bytes + self.loss_bytes + 255) // 256 * 256
+        self.vmag_bytes = self.n_vrows * self.ld * 8              # per rank
+        self.block_bytes = self.vmag_bytes + self.ld * 16         # one rank's |V| rows + losses
+        self.slot_bytes = (self.world * self.block_bytes + 255) // 256 * 256
         ptr = C.c_void_p()
         handle = C.create_string_buffer(_cabi.GP_PEER_HANDLE_BYTES)
         _cabi.check(_cabi.gp_peer_alloc(self.device, self.slot_bytes * self.slots, C.byref(ptr), handle))
@@ -135,22 +137,28 @@ class PeerGather:
         peers (a permutation) instead of all converging on rank 0's NVLink ingress first."""
         if not 0 <= slot < self.slots:
             raise ValueError('no such slot')
-        off = slot * self.slot_bytes
+        off = slot * self.slot_bytes + self.rank * self.block_bytes
         order = [(self.rank + 1 + i) % self.world for i in range(self.world)]
-        vm = [self.bases[q] + off + self.rank * self.n_vrows * self.ld * 8 for q in order]
-        ls = [self.bases[q] + off + self.vmag_bytes + self.rank * self.ld * 16 for q in order]
-        return vm, ls
+        vm = [self.bases[q] + off for q in order]
+        return vm, [v + self.vmag_bytes for v in vm]
+
+    def own_destination(self, slot: int):
+        """This rank's block of ``slot`` in its OWN buffer only (then ``push_own`` it)."""
+        vm, ls = self.destinations(slot)
+        return vm[-1:], ls[-1:]
 
     def vmag_all(self, slot: int):
         """``[world, n_vrows, ld]`` float64 view of this rank's copy of ``slot`` (no copy)."""
         dev = self._torch.device('cuda', self.device)
-        a = _DevArray(self._local + slot * self.slot_bytes, (self.world, self.n_vrows, self.ld), '<f8')
+        a = _DevArray(self._local + slot * self.slot_bytes, (self.world, self.n_vrows, self.ld), '<f8',
+                      (self.block_bytes, self.ld * 8, 8))
         return self._torch.as_tensor(a, device=dev)
 
     def loss_all(self, slot: int):
         """``[world, ld]`` complex128 view of this rank's copy of ``slot`` (no copy)."""
         dev = self._torch.device('cuda', self.device)
-        a = _DevArray(self._local + slot * self.slot_bytes + self.vmag_bytes, (self.world, self.ld), '<c16')
+        a = _DevArray(self._local + slot * self.slot_bytes + self.vmag_bytes, (self.world, self.ld), '<c16',
+                      (self.block_bytes, 16))
         return self._torch.as_tensor(a, device=dev)
 
     # ---- copy-engine transport -----------------------------------------------------------
@@ -166,6 +174,16 @@ class PeerGather:
         _cabi.check(_cabi.gp_peer_push(self.device, n, arr_v, Vmag_rows.data_ptr(), self.n_vrows * self.ld * 8,
                                        st.cuda_stream))
         _cabi.check(_cabi.gp_peer_push(self.device, n, arr_l, loss.data_ptr(), self.ld * 16, st.cuda_stream))
+
+    def push_own(self, slot: int, stream=None):
+        """The same step when the solve has written this rank's block into its own buffer: one DMA of
+        the whole block (|V| rows and losses are contiguous) to every peer."""
+        C, _cabi, torch = self._C, self._cabi, self._torch
+        st = torch.cuda.current_stream(self.device) if stream is None else stream
+        vm, _ = self.destinations(slot)
+        if len(vm) > 1:
+            arr = (C.c_void_p * (len(vm) - 1))(*vm[:-1])
+            _cabi.check(_cabi.gp_peer_push(self.device, len(vm) - 1, arr, vm[-1], self.block_bytes, st.cuda_stream))
 
     def wait(self, stream=None):
         """After this returns every rank's contribution issued before its own ``wait`` is in place."""

@@ -194,7 +194,9 @@ class SolutionFBS(Solution):
         ``gather``: ``(PeerGather, slot)`` (``gigpower_b200.sharding``): the solve also stores this rank's
         |V| rows and losses into that slot of every rank's gather buffer (the all-gather of SURVEY.md
         8(e), fused into the kernel epilogue); read them with ``PeerGather.vmag_all / loss_all`` after
-        ``PeerGather.wait()``.  The batch must have the PeerGather's per-rank size.
+        ``PeerGather.wait()``.  ``(PeerGather, slot, 'own')`` stores into this rank's own buffer only,
+        for ``PeerGather.push_own`` to distribute with the copy engines.  The batch must have the
+        PeerGather's per-rank size.
         """
         torch, dev = self._dev()
         t = self.tables
@@ -230,11 +232,12 @@ class SolutionFBS(Solution):
                 gamma = self.gamma_rows_from_taps(taps, S, dev) if taps is not None else None
                 peers = None
                 if gather is not None:
-                    pg, slot = gather
+                    pg, slot = gather[0], gather[1]
                     if (pg.n_vrows, pg.ld) != (t.n_vrows, ld):
                         raise ValueError(f'gather buffers are for [{pg.n_vrows}, {pg.ld}] blocks, this batch is '
                                          f'[{t.n_vrows}, {ld}]')
-                    peers = pg.destinations(slot)
+                    own = len(gather) > 2 and gather[2] == 'own'
+                    peers = pg.own_destination(slot) if own else pg.destinations(slot)
                 extras = _cabi.make_extras(gamma, warm_start is not None, peers)
                 iters = torch.empty(S, dtype=torch.int32, device=dev)
                 status = torch.empty(S, dtype=torch.int32, device=dev)

@@ -93,6 +93,18 @@ def _rank(rank, world, port, S, kernel, q):
         pg.wait()
         got_v2 = torch.cat([pg.vmag_all(0)[r] for r in range(world)], dim=1).cpu().numpy()
         ok = ok and rel_err(got_v2, full.Vmag_rows) <= 1e-12
+        # third: the solve writes this rank's block of its OWN buffer, one DMA per peer distributes it
+        pg.wait()
+        pg.vmag_all(0).zero_()
+        pg.loss_all(0).zero_()
+        pg.wait()
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', kernel))
+        s.solve_batch(load_mult=mult[lo:hi], outputs=(), return_device=True, gather=(pg, 0, 'own'))
+        pg.push_own(0)
+        pg.wait()
+        got_v3 = torch.cat([pg.vmag_all(0)[r] for r in range(world)], dim=1).cpu().numpy()
+        got_l3 = torch.cat([pg.loss_all(0)[r] for r in range(world)], dim=0).cpu().numpy()
+        ok = ok and rel_err(got_v3, full.Vmag_rows) <= 1e-12 and rel_err(got_l3, full.loss) <= 1e-12
         pg.close()
         q.put((rank, bool(ok)))
     finally:
