@@ -116,6 +116,61 @@ def fbs_flops_per_iteration(t):
                  + ((~line) * 4 * nb).sum())
 
 
+class NvmlSampler:
+    """SM clock and clock-event (throttle) reasons DURING the timed region, read through NVML from a
+    thread every millisecond: the timed region of the default workload lasts tens of milliseconds,
+    which `nvidia-smi -lms 100` (ClockSampler below, the fallback) samples once at best."""
+
+    def __init__(self, gpu_index):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        idx = gpu_index
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            try:
+                idx = int(vis.split(',')[gpu_index])
+            except Exception:
+                pass
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        self.sm, self.mask, self.stop_flag = [], 0, False
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def stop(self):
+        nv = self.nv
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        names = {'hw_slowdown': nv.nvmlClocksEventReasonHwSlowdown,
+                 'hw_thermal_slowdown': nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 'sw_thermal_slowdown': nv.nvmlClocksEventReasonSwThermalSlowdown,
+                 'sw_power_cap': nv.nvmlClocksEventReasonSwPowerCap,
+                 'hw_power_brake_slowdown': nv.nvmlClocksEventReasonHwPowerBrakeSlowdown}
+        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.max_mhz,
+                'samples': len(self.sm), 'reasons': sorted(n for n, bit in names.items() if self.mask & bit),
+                'source': 'NVML, 1 ms period, timed region only'}
+
+
+def make_sampler(gpu_index):
+    try:
+        return NvmlSampler(gpu_index)
+    except Exception:
+        return ClockSampler(gpu_index)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
@@ -462,9 +517,25 @@ def run_ours(args, wl):
     sets += [BufSet() for _ in range(n_sets - 1)]
     n_slots = max(2, n_sets)
     slot_pushed = {}
+    gather_note = None
     if world > 1 and args.gather in ('peer', 'dma'):
         from gigpower_b200.sharding import PeerGather
-        pg = PeerGather(t.n_vrows, ld, slots=n_slots)
+        try:
+            pg = PeerGather(t.n_vrows, ld, slots=n_slots)
+            ok = torch.ones(1, device=dev)
+        except Exception as e:          # no CUDA IPC between the ranks (container policy): NCCL does the gather
+            pg, ok = None, torch.zeros(1, device=dev)
+            gather_note = f'peer-mapped gather unavailable ({e}); NCCL all-gather instead'
+            print(gather_note, file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)       # all ranks or none
+        if float(ok.item()) == 0.0:
+            if pg is not None:
+                pg.close()
+            pg, args.gather = None, 'nccl'
+            gather_note = gather_note or 'peer-mapped gather unavailable on another rank; NCCL all-gather instead'
+            for b in sets:
+                b.Vmag_all = torch.empty((world, t.n_vrows, ld), dtype=f64, device=dev)
+                b.loss_all = torch.empty((world, S), dtype=c128, device=dev)
 
     def step(k):
         b = sets[k % n_sets]
@@ -492,7 +563,7 @@ def run_ours(args, wl):
         step(k)
     barrier()
     # ---- timed region: K steps back to back between two events; solve kernels timed individually ----
-    sampler = ClockSampler(local)
+    sampler = make_sampler(local)
     if rank == 0:
         sampler.start()
     launches0 = _cabi.gp_launch_count()
@@ -509,6 +580,7 @@ def run_ours(args, wl):
     e_end.record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
     launches = _cabi.gp_launch_count() - launches0
     if pg is not None:
         # every rank's last step sits in block r of the slot on this rank
@@ -608,7 +680,6 @@ def run_ours(args, wl):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = world * S / float(e2e_t.item())
     h2d = int(spu_h.numel() * 16) if args.workload != 'c4ts' else h2d_override
-    clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         pk, pk_kind = peaks()

@@ -115,20 +115,43 @@ class PeerGather:
         self.slot_bytes = (self.world * self.block_bytes + 255) // 256 * 256
         ptr = C.c_void_p()
         handle = C.create_string_buffer(_cabi.GP_PEER_HANDLE_BYTES)
-        _cabi.check(_cabi.gp_peer_alloc(self.device, self.slot_bytes * self.slots, C.byref(ptr), handle))
-        self._local = ptr.value
+        self._local, err = None, None
+        try:
+            _cabi.check(_cabi.gp_peer_alloc(self.device, self.slot_bytes * self.slots, C.byref(ptr), handle))
+            self._local = ptr.value
+        except _cabi.GpError as e:
+            if self.world == 1:
+                raise
+            err = str(e)
         self.bases = [None] * self.world                 # base address of every rank's buffer in THIS process
         self.bases[self.rank] = self._local
         if self.world > 1:
+            # failures are made collective: every rank takes part in both exchanges, then all raise or none
             handles = [None] * self.world
-            dist.all_gather_object(handles, (self.rank, bytes(handle.raw)), group=group)
-            for r, h in handles:
-                if r == self.rank:
-                    continue
-                p = C.c_void_p()
-                _cabi.check(_cabi.gp_peer_open(self.device, C.create_string_buffer(h, len(h)), C.byref(p)))
-                self.bases[r] = p.value
-            dist.barrier(group=group)
+            dist.all_gather_object(handles, (self.rank, bytes(handle.raw) if err is None else None, err), group=group)
+            errs = [f'rank {r}: {e}' for r, h, e in handles if h is None]
+            if not errs:
+                try:
+                    for r, h, _ in handles:
+                        if r == self.rank:
+                            continue
+                        p = C.c_void_p()
+                        _cabi.check(_cabi.gp_peer_open(self.device, C.create_string_buffer(h, len(h)), C.byref(p)))
+                        self.bases[r] = p.value
+                except _cabi.GpError as e:
+                    err = str(e)
+            opened = [None] * self.world
+            dist.all_gather_object(opened, (self.rank, err), group=group)
+            errs += [f'rank {r}: {e}' for r, e in opened if e is not None]
+            if errs:
+                for r, b in enumerate(self.bases):
+                    if r != self.rank and b is not None:
+                        _cabi.gp_peer_close(self.device, b)
+                dist.barrier(group=group)
+                if self._local is not None:
+                    _cabi.gp_peer_free(self.device, self._local)
+                self._local = None
+                raise _cabi.GpError('peer-mapped gather buffers unavailable: ' + '; '.join(sorted(set(errs))))
 
     # ---- addresses -----------------------------------------------------------------------
     def destinations(self, slot: int):

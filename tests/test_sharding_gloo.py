@@ -82,3 +82,37 @@ def test_gloo_gather_ragged(world, S):
         assert p.exitcode == 0
     results = dict(q.get(timeout=5) for _ in range(world))
     assert results == {r: True for r in range(world)}
+
+
+def _peer_fail_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from gigpower_b200 import _cabi
+        from gigpower_b200.sharding import PeerGather
+        try:
+            PeerGather(5, 64, slots=1, device=0)          # no CUDA device here: the allocation fails on every rank
+            q.put((rank, 'no error'))
+        except _cabi.GpError as e:
+            q.put((rank, 'GpError' if 'rank 0' in str(e) and 'rank 1' in str(e) else str(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='needs a box without a GPU')
+def test_peer_gather_setup_fails_collectively_without_cuda():
+    """PeerGather's set-up errors are collective (all ranks raise, nobody is left waiting in an exchange):
+    the product path has no CPU fallback, so without a CUDA device every rank gets a GpError."""
+    with socket.socket() as sk:
+        sk.bind(('127.0.0.1', 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_fail_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert dict(q.get(timeout=5) for _ in range(2)) == {0: 'GpError', 1: 'GpError'}
