@@ -612,6 +612,7 @@ def run_ours(args, wl):
 
     # ---- end to end: host buffers in, results out, copies inside the timed region -----------
     e2e_steps = max(3, min(args.steps, 10))
+    e2e_extra = {}
     if args.workload == 'c4ts':
         # the study driver: hour / DER tables up (kilobytes), 36 bytes of summaries per scenario down
         from gigpower_b200.study import DerStudy
@@ -658,6 +659,20 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
         e2e_api = 'gp_fbs_solve_batch_host (pinned host buffers; returns V, losses, iterations, status)'
         d2h = int(V_h.numel() * 16 + loss_h.numel() * 16 + S * (4 + 4 + 8))
+        t_full = (time.perf_counter() - t0) / e2e_steps
+        # the same call returning what the sharded path gathers (|V| and losses) instead of complex V
+        Vm_h = torch.empty((t.n_vrows, ld), dtype=f64).pin_memory()
+        sol.solve_batch_host(spu_h, None, None, Vm_h, loss_h)
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sol.solve_batch_host(spu_h, None, None, Vm_h, loss_h)
+        torch.cuda.synchronize()
+        e2e_extra = {'returning_vmag_and_losses_only': {
+            'seconds_per_step_this_rank': (time.perf_counter() - t1) / e2e_steps,
+            'value_this_rank': S / ((time.perf_counter() - t1) / e2e_steps), 'unit': 'solves/s per GPU',
+            'd2h_bytes_per_step': int(Vm_h.numel() * 8 + loss_h.numel() * 16 + S * (4 + 4 + 8))}}
+        t0 = time.perf_counter() - t_full * e2e_steps      # the headline e2e stays the call that returns V
     else:
         X_h = torch.empty((t.n_vrows + t.n_irows, ld), dtype=c128).pin_memory()
         it_h = torch.empty(S, dtype=i32).pin_memory()
@@ -759,7 +774,7 @@ def run_ours(args, wl):
                            'on a side stream')},
             'e2e': {'value': e2e_value, 'unit': 'solves/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
-                    'api': e2e_api},
+                    'api': e2e_api, **e2e_extra},
             'gpu_launches': int(launches),
             'roofline': roofline,
             'clocks': clocks, 'wall_s_timed_region': t_wall,

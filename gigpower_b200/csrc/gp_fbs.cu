@@ -29,6 +29,7 @@ extern int g_nr3_prefetch;     // gp_nr3.cu
 extern int g_nr3_kernel;
 int nr3_gamma_rows(GpFeeder* f);   // gp_nr3.cu
 static int g_jit_i_global = -1;    // gp_set_option("jit_i_global", -1|0|1): I rows of the specialised kernel in global memory
+static int g_host_read_ahead = 1;  // gp_set_option("host_read_ahead", 0|1): read-ahead build of the one-launch host path
 static int g_host_zero_copy = 1;   // gp_set_option("host_zero_copy", 0|1): one-launch host path of the specialised kernel
 static int g_host_chunks = 0;  // gp_set_option("host_chunks", n): 0 = automatic
 // gp_set_option("fbs_kernel", v): 0 automatic (feeder-specialised on-chip kernel once built, else two-sweep), 1 fused
@@ -1055,6 +1056,10 @@ extern "C" int gp_set_option(const char* name, int value) {
         g_host_zero_copy = value;
         return GP_OK;
     }
+    if (name && strcmp(name, "host_read_ahead") == 0 && (value == 0 || value == 1)) {
+        g_host_read_ahead = value;
+        return GP_OK;
+    }
     if (name && strcmp(name, "host_chunks") == 0 && value >= 0 && value <= 64) {
         g_host_chunks = value;
         return GP_OK;
@@ -1276,17 +1281,15 @@ Driver& driver() {
 }
 }  // namespace
 
-extern "C" int gp_fbs_specialise(GpFeeder* f) {
-    if (!f || f->kind != 1) return fail(GP_EINVAL, "gp_fbs_specialise: not an FBS feeder handle");
+// Generate, compile and load one variant of the feeder-specialised kernel: the device-buffer kernel
+// (read_ahead = false) or the kernel of the one-launch host path, which fetches a warp's next tile over
+// PCIe before it stores the current one (read_ahead = true; more registers, so it is its own build).
+static int fbs_jit_build(GpFeeder* f, int nw, bool ig, bool read_ahead, void** mod_out, void** fn_out) {
     FbsImpl* im = (FbsImpl*)f->impl;
-    if (im->jit_kernel) return GP_OK;
-    if (im->jit_plan_warps < 1) return fail(GP_EJIT, "gp_fbs_specialise: the feeder does not fit the on-chip kernel");
     GP_CUDA(cudaSetDevice(f->device));
     GP_CUDA(cudaFree(0));       // make sure the primary context exists and is current
-    const int nw = im->jit_plan_warps;
-    const bool ig = im->jit_plan_ig;
     const std::string src = fbs_jit_source(im->h_steps, im->h_child, im->h_lines, im->k, im->n_vrows, im->n_irows,
-                                           im->n_srows, nw, ig);
+                                           im->n_srows, nw, ig, read_ahead);
     if (src.empty()) return fail(GP_EJIT, "gp_fbs_specialise: non-finite impedance");
     std::vector<char> bin;
     std::string log;
@@ -1305,8 +1308,21 @@ extern "C" int gp_fbs_specialise(GpFeeder* f) {
         dr.ModuleUnload(mod);
         return fail(GP_EJIT, "gp_fbs_specialise: kernel lookup / shared-memory opt-in failed (%d)", cr);
     }
-    im->jit_warps = nw;
-    im->jit_ig = ig;
+    *mod_out = mod;
+    *fn_out = fn;
+    return GP_OK;
+}
+
+extern "C" int gp_fbs_specialise(GpFeeder* f) {
+    if (!f || f->kind != 1) return fail(GP_EINVAL, "gp_fbs_specialise: not an FBS feeder handle");
+    FbsImpl* im = (FbsImpl*)f->impl;
+    if (im->jit_kernel) return GP_OK;
+    if (im->jit_plan_warps < 1) return fail(GP_EJIT, "gp_fbs_specialise: the feeder does not fit the on-chip kernel");
+    void *mod = nullptr, *fn = nullptr;
+    int rc = fbs_jit_build(f, im->jit_plan_warps, im->jit_plan_ig, false, &mod, &fn);
+    if (rc) return rc;
+    im->jit_warps = im->jit_plan_warps;
+    im->jit_ig = im->jit_plan_ig;
     im->jit_module = mod;
     im->jit_kernel = fn;
     return GP_OK;
@@ -1506,6 +1522,7 @@ extern "C" int gp_feeder_destroy(GpFeeder* f) {
         cudaFree(im->d_unfed);
         cudaFree(im->d_zc);
         if (im->jit_module) driver().ModuleUnload(im->jit_module);
+        if (im->jit_module_host) driver().ModuleUnload(im->jit_module_host);
         for (int i = 0; i < FbsImpl::NSTREAM; ++i) {
             if (im->d_stage[i]) cudaFree(im->d_stage[i]);
             if (im->streams[i]) cudaStreamDestroy(im->streams[i]);
@@ -1530,7 +1547,7 @@ static int fbs_check(GpFeeder* f, int64_t S, int64_t ld, const char* who) {
 static int fbs_jit_launch(FbsImpl* im, int64_t S, int64_t ld, const double* spu, double* V, double* I,
                           int32_t* iters, int32_t* status, double* diff, double tol, int32_t maxiter,
                           cudaStream_t st, double* Vmag, double* loss, void* stage, double* Iout,
-                          const PeerDst* peers = nullptr) {
+                          const PeerDst* peers = nullptr, void* kernel = nullptr) {
     const long long n_tiles = (S + 31) / 32;
     const int nw = im->jit_warps;
     long long blocks = (n_tiles + nw - 1) / nw;
@@ -1546,7 +1563,7 @@ static int fbs_jit_launch(FbsImpl* im, int64_t S, int64_t ld, const double* spu,
     void* args[] = {(void*)&spu, (void*)&V, (void*)&I, (void*)&iters, (void*)&status, (void*)&diff,
                     (void*)&S_arg, (void*)&ldb_arg, (void*)&tol_arg, (void*)&maxiter_arg, (void*)&im->d_sched,
                     (void*)&Vmag, (void*)&loss, (void*)&stage, (void*)&Iout, (void*)&pd};
-    const int cr = driver().LaunchKernel(im->jit_kernel, (unsigned)blocks, 1, 1, (unsigned)nw * 32, 1, 1, smem,
+    const int cr = driver().LaunchKernel(kernel ? kernel : im->jit_kernel, (unsigned)blocks, 1, 1, (unsigned)nw * 32, 1, 1, smem,
                                          (void*)st, args, nullptr);
     if (cr != 0) return fail(GP_ECUDA, "gp_fbs_solve_batch: cuLaunchKernel failed (%d)", cr);
     return GP_OK;
@@ -1812,11 +1829,19 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
                 im->zc_bytes = need_stage;
             }
             if (!im->streams[0]) GP_CUDA(cudaStreamCreateWithFlags(&im->streams[0], cudaStreamNonBlocking));
+            // the host path's own build of the kernel (next tile's PCIe reads issued before this tile's stores);
+            // feeders with more than 32 load rows, or a failed build, keep the device-path kernel
+            if (!im->jit_host_tried && im->n_srows <= 32 && g_host_read_ahead) {
+                im->jit_host_tried = true;
+                if (fbs_jit_build(f, im->jit_warps, im->jit_ig, true, &im->jit_module_host, &im->jit_kernel_host) != GP_OK)
+                    im->jit_module_host = im->jit_kernel_host = nullptr;
+            }
             // I rows kept in global memory must stay on the device; the host copy is a second destination
             double* I_state = im->jit_ig ? (double*)((char*)im->d_zc + b_stage) : (double*)dp[2];
             rc = fbs_jit_launch(im, S, ld, (const double*)dp[0], (double*)dp[1], I_state, (int32_t*)dp[5],
                                 (int32_t*)dp[6], (double*)dp[7], tol, maxiter, im->streams[0], (double*)dp[3],
-                                (double*)dp[4], im->d_zc, im->jit_ig ? (double*)dp[2] : nullptr);
+                                (double*)dp[4], im->d_zc, im->jit_ig ? (double*)dp[2] : nullptr, nullptr,
+                                g_host_read_ahead ? im->jit_kernel_host : nullptr);
             if (rc) return rc;
             count_launch();
             GP_CUDA(cudaStreamSynchronize(im->streams[0]));

@@ -71,6 +71,9 @@ struct FbsImpl {
     std::vector<int> h_lines;     // [n_lines][9] irow, tx vrow, rx vrow
     void* jit_module = nullptr;   // CUmodule
     void* jit_kernel = nullptr;   // CUfunction
+    void* jit_module_host = nullptr;  // the read-ahead build of the one-launch host path (built on first use)
+    void* jit_kernel_host = nullptr;
+    bool jit_host_tried = false;
     int jit_warps = 0;
     bool jit_ig = false;          // the specialised kernel keeps the I rows in global memory (the I array)
     int jit_plan_warps = 0;       // warps per block gp_fbs_specialise will use (0 = feeder does not fit)
@@ -88,7 +91,7 @@ struct FbsImpl {
 // gp_fbs_jit.cu: CUDA source of the feeder-specialised on-chip kernel, NVRTC compilation
 std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<int4>& child,
                            const std::vector<int>& lines, const FbsConst& k, int n_vrows, int n_irows, int n_srows,
-                           int nw, bool ig);
+                           int nw, bool ig, bool read_ahead = false);
 int jit_compile(const std::string& src, std::vector<char>& cubin, std::string& log);
 
 }  // namespace gp

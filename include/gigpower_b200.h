@@ -114,6 +114,9 @@ int64_t gp_launch_count(void);
  * "fbs_prefetch" / "nr3_prefetch": L2 prefetch distance in tree steps of the streaming FBS kernel
  * (default 0) and of the NR3 kernel (default -1 = automatic: 2 for batches up to 65,536).
  * "host_chunks": number of pipeline chunks of gp_fbs_solve_batch_host (0 = automatic).
+ * "host_read_ahead": 1 (default) = the one-launch host path uses its own build of the specialised kernel
+ *   in which a warp issues the PCIe reads of its next tile before the stores of the tile it has solved
+ *   (upload and download then overlap instead of alternating); 0 = the device-path kernel.
  */
 int gp_set_option(const char* name, int value);
 

@@ -289,8 +289,9 @@ def test_host_entry_point_one_launch_path_matches_staged_path():
     spu_h = torch.from_numpy(rows).pin_memory()
     out = {}
     try:
-        for zc in (0, 1):
-            _cabi.check(_cabi.gp_set_option(b'host_zero_copy', zc))
+        for zc in (0, 1, 2):       # staged; one launch with the read-ahead build of the kernel; one launch without
+            _cabi.check(_cabi.gp_set_option(b'host_zero_copy', min(zc, 1)))
+            _cabi.check(_cabi.gp_set_option(b'host_read_ahead', 0 if zc == 2 else 1))
             V, I = pin((t.n_vrows, S), torch.complex128), pin((t.n_irows, S), torch.complex128)
             Vmag, loss = pin((t.n_vrows, S), torch.float64), pin(S, torch.complex128)
             n0 = _cabi.gp_launch_count()
@@ -299,9 +300,10 @@ def test_host_entry_point_one_launch_path_matches_staged_path():
                        loss.numpy().copy(), _cabi.gp_launch_count() - n0)
     finally:
         _cabi.gp_set_option(b'host_zero_copy', 1)
-    assert out[1][7] == 1 and out[0][7] >= 1
-    for a, b in zip(out[0][:7], out[1][:7]):
-        assert np.array_equal(a, b)
+        _cabi.gp_set_option(b'host_read_ahead', 1)
+    assert out[1][7] == 1 and out[2][7] == 1 and out[0][7] >= 1
+    for a, b, c in zip(out[0][:7], out[1][:7], out[2][:7]):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
     # only V requested; and pageable (not pinned) buffers -> staged path, same numbers
     V2 = pin((t.n_vrows, S), torch.complex128)
     it2, st2, _ = s.solve_batch_host(spu_h, V2)
