@@ -93,7 +93,7 @@ gp_fbs_solve_batch_host = _sig('gp_fbs_solve_batch_host', C.c_int,
 class GpSolveExtras(C.Structure):
     """Optional per-scenario inputs of a solve (include/gigpower_b200.h: GpSolveExtras)."""
     _fields_ = [('gamma_dev', vp), ('warm_start', C.c_int32), ('n_peers', C.c_int32),
-                ('peer_vmag', C.POINTER(vp)), ('peer_loss', C.POINTER(vp))]
+                ('peer_vmag', C.POINTER(vp)), ('peer_loss', C.POINTER(vp)), ('wpu_dev', vp)]
 
 
 GP_MAX_PEERS = 16
@@ -110,6 +110,8 @@ gp_fbs_solve_batch_ex = _sig('gp_fbs_solve_batch_ex', C.c_int,
                              [vp, C.c_int64, C.c_int64, vp, C.POINTER(GpSolveExtras), vp, vp, vp, vp, vp, vp, vp,
                               C.c_double, C.c_int32, vp])
 
+gp_fbs_post_ex = _sig('gp_fbs_post_ex', C.c_int,
+                      [vp, C.c_int64, C.c_int64, vp, C.POINTER(GpSolveExtras), vp, vp, vp, vp, vp, vp, vp, vp])
 gp_der_rows = _sig('gp_der_rows', C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                              vp, vp, vp, vp, vp, vp, vp])
 gp_der_rows_strided = _sig('gp_der_rows_strided', C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
@@ -133,17 +135,18 @@ EXPORTS = ['gp_version', 'gp_last_error', 'gp_launch_count', 'gp_set_option', 'g
            'gp_fbs_solve_batch', 'gp_fbs_solve_post_batch', 'gp_fbs_post', 'gp_fbs_solve_batch_host', 'gp_der_rows', 'gp_vmag_summary', 'gp_nr3_create',
            'gp_nr3_workspace_bytes', 'gp_nr3_solve_batch', 'gp_nr3_map_output',
            'gp_gamma_rows', 'gp_fbs_solve_batch_ex', 'gp_nr3_solve_batch_ex', 'gp_der_rows_strided',
-           'gp_peer_alloc', 'gp_peer_free', 'gp_peer_open', 'gp_peer_close', 'gp_peer_push']
+           'gp_peer_alloc', 'gp_peer_free', 'gp_peer_open', 'gp_peer_close', 'gp_peer_push', 'gp_fbs_post_ex']
 
 
-def make_extras(gamma=None, warm_start=False, peers=None):
+def make_extras(gamma=None, warm_start=False, peers=None, wpu=None):
     """GpSolveExtras for a device tensor of regulator ratios ``[n_gamma_rows, ld]`` float64, a warm
     start and / or the destinations of the fused all-gather (``peers`` = (|V| pointers, loss pointers),
     two equally long lists of device addresses); returns None when nothing is asked for."""
-    if gamma is None and not warm_start and not peers:
+    if gamma is None and not warm_start and not peers and wpu is None:
         return None
     ex = GpSolveExtras()
     ex.gamma_dev = gamma.data_ptr() if gamma is not None else None
+    ex.wpu_dev = wpu.data_ptr() if wpu is not None else None
     ex.warm_start = 1 if warm_start else 0
     if peers:
         vm, ls = peers

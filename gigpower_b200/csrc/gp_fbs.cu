@@ -65,6 +65,9 @@ struct GMemT {
     const char* S;
     unsigned ldb;
     const char* G;
+    const char* W;      // this scenario's column of the per-scenario Solution.wpu rows ([V row][ld] doubles)
+    __device__ __forceinline__ bool hasW() const { return TAPS && W != nullptr; }
+    __device__ __forceinline__ double ldW(int r) const { return __ldg(reinterpret_cast<const double*>(W + (size_t)(unsigned)r * (size_t)(ldb >> 1))); }
     __device__ __forceinline__ bool hasG() const { return TAPS && G != nullptr; }
     __device__ __forceinline__ double ldG(int r) const { return __ldg(reinterpret_cast<const double*>(G + (size_t)(unsigned)r * (size_t)(ldb >> 1))); }
     __device__ __forceinline__ double2 ldV(int r) const { return __ldcg(reinterpret_cast<const double2*>(V + (size_t)(unsigned)r * (size_t)ldb)); }
@@ -82,6 +85,8 @@ using GMem = GMemT<false>;
 
 struct SMem {
     static constexpr bool kTaps = false;
+    __device__ __forceinline__ bool hasW() const { return false; }
+    __device__ __forceinline__ double ldW(int) const { return 0.0; }
     __device__ __forceinline__ bool hasG() const { return false; }
     __device__ __forceinline__ double ldG(int) const { return 0.0; }
     double2* V;         // this lane's column of the warp's V rows (shared memory)
@@ -163,6 +168,7 @@ __device__ __forceinline__ void bwd_fast(const FbsStep* __restrict__ st, const i
             const double f = k.aPQ + k.aI * a + k.aZ * a2;
             double2 sv = make_double2(sp[p].x * f, sp[p].y * f);
             sv.y -= __ldg(&st->cap[p]) * a2;
+            if (m.hasW()) sv.y += m.ldW(brow[p]);           // + 1j * wpu (solution.py:203)
             if (v.x != 0.0 || v.y != 0.0) {
                 const double inv = 1.0 / fma(v.x, v.x, v.y * v.y);
                 In[p].x += (sv.x * v.x + sv.y * v.y) * inv;
@@ -300,6 +306,7 @@ __device__ __forceinline__ void fbs_bwd_step(const FbsStep* __restrict__ st, con
         const double f = k.aPQ + k.aI * a + k.aZ * a2;
         double2 sv = make_double2(sp[p].x * f, sp[p].y * f);   // sp = 0 where there is no load
         sv.y -= __ldg(&st->cap[p]) * a2;
+        if (m.hasW()) sv.y += m.ldW(brow[p]);                   // + 1j * wpu (solution.py:203)
         if (v.x != 0.0 || v.y != 0.0) {
             // conj(sV / V) computed as (sV * conj(V)) / |V|^2, conjugated
             const double inv = 1.0 / fma(v.x, v.x, v.y * v.y);
@@ -374,11 +381,12 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
                  char* __restrict__ I, int* __restrict__ iters_out,
                  int* __restrict__ status_out, double* __restrict__ diff_out, double tol,
                  int maxiter, int PF, const int* __restrict__ unfed, int n_unfed,
-                 const char* __restrict__ gam, int warm) {
+                 const char* __restrict__ gam, int warm, const char* __restrict__ wpu) {
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (s >= S) return;
     typedef GMemT<EX> GMem;
-    const GMem m{V + s * 16, I + s * 16, spu + s * 16, ldb, (EX && gam) ? gam + s * 8 : nullptr};
+    const GMem m{V + s * 16, I + s * 16, spu + s * 16, ldb, (EX && gam) ? gam + s * 8 : nullptr,
+                 (EX && wpu) ? wpu + s * 8 : nullptr};
     const double2 zero = make_double2(0.0, 0.0);
     if (EX && warm) n_unfed = 0;    // warm start: every V and I row keeps the earlier solution
 
@@ -958,7 +966,8 @@ __global__ void fbs_post_rows_kernel(int n_vrows, const int* __restrict__ vrow_s
                                      const double* __restrict__ vrow_cap, FbsConst k, long long S,
                                      long long ld, const double2* __restrict__ spu,
                                      const double2* __restrict__ V, double2* __restrict__ sV,
-                                     double* __restrict__ Vmag, const PeerDst peers) {
+                                     double* __restrict__ Vmag, const PeerDst peers,
+                                     const double* __restrict__ wpu) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     for (int r = blockIdx.y; r < n_vrows; r += gridDim.y) {
@@ -979,6 +988,7 @@ __global__ void fbs_post_rows_kernel(int n_vrows, const int* __restrict__ vrow_s
                 sv.y = sp.y * f;
             }
             sv.y -= __ldg(vrow_cap + r) * a2;
+            if (wpu) sv.y += wpu[(long long)r * ld + s];
             sV[(long long)r * ld + s] = sv;
         }
     }
@@ -1596,9 +1606,10 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     FbsImpl* im = (FbsImpl*)f->impl;
     const char* gam = ex ? (const char*)ex->gamma_dev : nullptr;
     const int warm = ex ? ex->warm_start : 0;
+    const char* wpu = ex ? (const char*)ex->wpu_dev : nullptr;
     if (warm != 0 && warm != 1) return fail(GP_EINVAL, "gp_fbs_solve_batch_ex: warm_start must be 0 or 1");
     if (gam && im->n_grows == 0) gam = nullptr;     // no regulators: nothing to read
-    const bool extras = gam || warm;
+    const bool extras = gam || warm || wpu;
     PeerDst pd;
     rc = peers_from_extras(ex, pd);
     if (rc) return rc;
@@ -1624,7 +1635,7 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
         fbs_solve_kernel<BLOCK, true><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
                                                             im->n_irows, S, ldb, (const char*)spu, (char*)V,
                                                             (char*)I, iters, status, diff, tol, maxiter, g_fbs_prefetch,
-                                                            im->d_unfed, im->n_unfed, gam, warm);
+                                                            im->d_unfed, im->n_unfed, gam, warm, wpu);
     } else if ((g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) && (maxiter >= 1 || !im->jit_kernel)) {
         if (!im->jit_kernel)
             return fail(GP_EINVAL, "gp_fbs_solve_batch: fbs_kernel = 5 needs a successful gp_fbs_specialise");
@@ -1679,7 +1690,7 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
         fbs_solve_kernel<BLOCK, false><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
                                                              im->n_irows, S, ldb, (const char*)spu, (char*)V,
                                                              (char*)I, iters, status, diff, tol, maxiter, g_fbs_prefetch,
-                                                             im->d_unfed, im->n_unfed, nullptr, 0);
+                                                             im->d_unfed, im->n_unfed, nullptr, 0, nullptr);
     }
     count_launch();
     GP_CUDA(cudaGetLastError());
@@ -1708,7 +1719,7 @@ extern "C" int gp_fbs_solve_post_batch(GpFeeder* f, int64_t S, int64_t ld, const
 
 static int fbs_post_impl(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const double* V, const double* I,
                          double* sV, double* Vmag, double* Stx, double* Srx, double* loss, void* stream,
-                         const PeerDst& pd);
+                         const PeerDst& pd, const double* wpu = nullptr);
 
 extern "C" int gp_fbs_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const GpSolveExtras* ex,
                                      double* V, double* I, int32_t* iters, int32_t* status, double* diff,
@@ -1734,9 +1745,17 @@ extern "C" int gp_fbs_post(GpFeeder* f, int64_t S, int64_t ld, const double* spu
     return fbs_post_impl(f, S, ld, spu, V, I, sV, Vmag, Stx, Srx, loss, stream, pd);
 }
 
+extern "C" int gp_fbs_post_ex(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const GpSolveExtras* ex,
+                              const double* V, const double* I, double* sV, double* Vmag, double* Stx, double* Srx,
+                              double* loss, void* stream) {
+    PeerDst pd;
+    memset(&pd, 0, sizeof(pd));
+    return fbs_post_impl(f, S, ld, spu, V, I, sV, Vmag, Stx, Srx, loss, stream, pd, ex ? ex->wpu_dev : nullptr);
+}
+
 static int fbs_post_impl(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const double* V, const double* I,
                          double* sV, double* Vmag, double* Stx, double* Srx, double* loss, void* stream,
-                         const PeerDst& pd) {
+                         const PeerDst& pd, const double* wpu) {
     int rc = fbs_check(f, S, ld, "gp_fbs_post");
     if (rc) return rc;
     if (S == 0) return GP_OK;
@@ -1750,7 +1769,7 @@ static int fbs_post_impl(GpFeeder* f, int64_t S, int64_t ld, const double* spu, 
     if (sV || Vmag || pd.n) {
         dim3 g(gx, 8);
         fbs_post_rows_kernel<<<g, BLOCK, 0, st>>>(im->n_vrows, im->d_vrow_srow, im->d_vrow_cap, im->k, S, ld,
-                                                  (const double2*)spu, (const double2*)V, (double2*)sV, Vmag, pd);
+                                                  (const double2*)spu, (const double2*)V, (double2*)sV, Vmag, pd, wpu);
         count_launch();
     }
     if (Stx || Srx || loss || pd.n) {

@@ -176,7 +176,7 @@ class SolutionFBS(Solution):
     # ---- batched solve -------------------------------------------------------
     def solve_batch(self, spu=None, load_mult=None, spu_rows=None, outputs=('V', 'Vmag', 'loss'),
                     maxiter=None, tol=None, return_device=False, stream=None, taps=None,
-                    warm_start=None, gather=None) -> BatchResult:
+                    warm_start=None, gather=None, wpu=None) -> BatchResult:
         """Solve S scenarios from flat start.
 
         Give ONE of: ``spu`` ``[S, nb, 3]`` complex; ``load_mult`` ``[S, n_loads]``
@@ -197,6 +197,9 @@ class SolutionFBS(Solution):
         ``PeerGather.wait()``.  ``(PeerGather, slot, 'own')`` stores into this rank's own buffer only,
         for ``PeerGather.push_own`` to distribute with the copy engines.  The batch must have the
         PeerGather's per-rank size.
+        ``wpu``: per-scenario ``Solution.wpu`` - the controllable reactive injection ``+ 1j * wpu`` of
+        ``calc_sV`` (solution.py:106, 203), zero in the reference unless the caller sets the attribute:
+        ``[S, nb, 3]`` real pu, or packed ``[n_vrows, S]`` float64 rows (NumPy or CUDA tensor).
         """
         torch, dev = self._dev()
         t = self.tables
@@ -230,6 +233,20 @@ class SolutionFBS(Solution):
                     V = torch.empty((t.n_vrows, ld), dtype=torch.complex128, device=dev)
                     I = torch.empty((max(t.n_irows, 1), ld), dtype=torch.complex128, device=dev)
                 gamma = self.gamma_rows_from_taps(taps, S, dev) if taps is not None else None
+                d_wpu = None
+                if wpu is not None:
+                    if isinstance(wpu, np.ndarray) or not hasattr(wpu, 'data_ptr'):
+                        w = np.asarray(wpu, dtype=np.float64)
+                        if w.ndim == 3:                    # [S, nb, 3] like Solution.wpu per scenario
+                            b_, p_ = np.nonzero(t.vrow >= 0)
+                            rows_w = np.zeros((t.n_vrows, w.shape[0]))
+                            rows_w[t.vrow[b_, p_]] = w[:, b_, p_].T
+                            w = rows_w
+                        d_wpu = torch.from_numpy(np.ascontiguousarray(w)).to(dev)
+                    else:
+                        d_wpu = wpu.to(device=dev, dtype=torch.float64).contiguous()
+                    if tuple(d_wpu.shape) != (t.n_vrows, ld):
+                        raise ValueError(f'wpu must be [S, nb, 3] or packed [{t.n_vrows}, {ld}], got {tuple(d_wpu.shape)}')
                 peers = None
                 if gather is not None:
                     pg, slot = gather[0], gather[1]
@@ -238,7 +255,7 @@ class SolutionFBS(Solution):
                                          f'[{t.n_vrows}, {ld}]')
                     own = len(gather) > 2 and gather[2] == 'own'
                     peers = pg.own_destination(slot) if own else pg.destinations(slot)
-                extras = _cabi.make_extras(gamma, warm_start is not None, peers)
+                extras = _cabi.make_extras(gamma, warm_start is not None, peers, d_wpu)
                 iters = torch.empty(S, dtype=torch.int32, device=dev)
                 status = torch.empty(S, dtype=torch.int32, device=dev)
                 diff = torch.empty(S, dtype=torch.float64, device=dev)
@@ -256,9 +273,9 @@ class SolutionFBS(Solution):
                     V.data_ptr(), I.data_ptr(), iters.data_ptr(), status.data_ptr(), diff.data_ptr(), p(Vmag),
                     p(loss), tol, maxiter, st.cuda_stream))
                 if want & {'sV', 'Stx', 'Srx'}:
-                    _cabi.check(_cabi.gp_fbs_post(
-                        self._feeder.handle, S, ld, d_spu.data_ptr(), V.data_ptr(), I.data_ptr(),
-                        p(sV), None, p(Stx), p(Srx), None, st.cuda_stream))
+                    _cabi.check(_cabi.gp_fbs_post_ex(
+                        self._feeder.handle, S, ld, d_spu.data_ptr(), C.byref(extras) if extras is not None else None,
+                        V.data_ptr(), I.data_ptr(), p(sV), None, p(Stx), p(Srx), None, st.cuda_stream))
         res = BatchResult(tables=t, S=S, iterations=iters, status=status, convergence_diff=diff,
                           V_rows=V if ('V' in want or warm_start is not None) else None,
                           I_rows=I if ('I' in want or warm_start is not None) else None,

@@ -164,3 +164,64 @@ class DerStudy:
                 host[key][lo:lo + n].copy_(src[:n], non_blocking=True)
         st.synchronize()
         return {k: v.numpy() for k, v in host.items()}      # views of pinned buffers the next run() reuses
+
+
+def volt_var_q(Vmag, points, minQ: float, maxQ: float):
+    """``VoltVARController.get_Q`` (volt_var_controller.py:20-38) on a CUDA tensor of |V| (any shape),
+    same arithmetic in the same order: maxQ below V1, a ramp to 0 at V2, 0 up to V3, a ramp to minQ at
+    V4, minQ above; the sign of the result is flipped as the reference does."""
+    import torch
+    V1, V2, V3, V4 = (float(x) for x in points)
+    lo_slope = (- maxQ) / (V2 - V1)
+    lo_b = - (lo_slope * V2)
+    hi_slope = (minQ) / (V4 - V3)
+    hi_b = - (hi_slope * V3)
+    q = torch.full_like(Vmag, float(minQ))
+    q = torch.where(Vmag <= V4, hi_slope * Vmag + hi_b, q)
+    q = torch.where(Vmag <= V3, torch.zeros_like(Vmag), q)
+    q = torch.where(Vmag <= V2, lo_slope * Vmag + lo_b, q)
+    q = torch.where(Vmag <= V1, torch.full_like(Vmag, float(maxQ)), q)
+    return -q
+
+
+class VoltVarStudy:
+    """Quasi-static volt-var droop around the batched FBS solve.
+
+    One controller per listed (bus, phase): after every solve its reactive injection becomes
+    ``wpu = get_Q(|V|)`` (``VoltVARController``, volt_var_controller.py:20-38; Q in pu) and the next
+    solve starts from the last state (warm start) with that ``Solution.wpu`` - the loop a caller of the
+    reference writes around ``solve()``, for every scenario of a batch at once.  Everything stays on the
+    device between rounds; per round one solve launch, one gather of the controlled |V| rows and a
+    handful of elementwise kernels."""
+
+    def __init__(self, solution, controllers, points=(0.95, 0.98, 1.02, 1.05), minQ=-0.05, maxQ=0.05):
+        self.sol = solution
+        t = solution.tables
+        names = solution.circuit.buses.all_names()
+        self.ctl = []
+        for bus, ph in controllers:
+            b = names.index(bus) if isinstance(bus, str) else int(bus)
+            row = int(t.vrow[b, ph])
+            if row < 0:
+                raise ValueError(f'bus {names[b]} has no phase {ph}')
+            self.ctl.append(row)
+        self.points, self.minQ, self.maxQ = tuple(points), float(minQ), float(maxQ)
+
+    def run(self, spu_rows=None, load_mult=None, rounds: int = 4, outputs=('V', 'Vmag')):
+        """``rounds`` solves; returns (last BatchResult, Q ``[rounds, n_controllers, S]`` CUDA tensor of the
+        injections computed after each round, iterations ``[rounds, S]`` CUDA tensor)."""
+        torch, dev = self.sol._dev()
+        t = self.sol.tables
+        rows = torch.as_tensor(self.ctl, device=dev, dtype=torch.long)
+        want = tuple(set(outputs) | {'V', 'I', 'Vmag'})
+        prev, wpu, Q, its = None, None, [], []
+        for _ in range(int(rounds)):
+            prev = self.sol.solve_batch(spu_rows=spu_rows, load_mult=load_mult, outputs=want, return_device=True,
+                                        warm_start=prev, wpu=wpu)
+            q = volt_var_q(prev.Vmag_rows.index_select(0, rows), self.points, self.minQ, self.maxQ)
+            if wpu is None:
+                wpu = torch.zeros((t.n_vrows, prev.Vmag_rows.shape[1]), dtype=torch.float64, device=dev)
+            wpu.index_copy_(0, rows, q)
+            Q.append(q)
+            its.append(prev.iterations.clone())
+        return prev, torch.stack(Q), torch.stack(its)

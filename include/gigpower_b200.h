@@ -244,6 +244,12 @@ int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const double* sp
  *   rules are unchanged, so a warm-started scenario usually needs fewer iterations and its result
  *   differs from the flat-started one within the solver tolerance.
  *
+ * wpu_dev (FBS): the controllable reactive injection of calc_sV, sV = spu (aPQ + aI |V| + aZ |V|^2)
+ *   - j cappu |V|^2 + j wpu (solution.py:203), per scenario and V row.  The reference keeps Solution.wpu at
+ *   zero (circuit.py:164-171) but it is a plain attribute of the object; a caller that sets it - a volt-var
+ *   droop evaluated between solves, volt_var_controller.py:20-38 - gets this term.  Runs on the streaming
+ *   kernel; gp_fbs_post_ex gives the matching sV.
+ *
  * n_peers, peer_vmag, peer_loss: the path's one exchange (the all-gather of per-scenario
  *   voltage magnitudes and losses across the GPUs of a box) fused into the solve.  Each destination is
  *   this rank's block inside the gather buffer of one GPU - its own or a peer's, mapped into this
@@ -261,6 +267,7 @@ typedef struct {
     int32_t n_peers;            /* fused all-gather of |V| and losses: number of destinations (0 = none)     */
     double* const* peer_vmag;   /* host array [n_peers] of device pointers, each a [n_vrows][ld] double block */
     double* const* peer_loss;   /* host array [n_peers] of device pointers, each a [S] complex block          */
+    const double* wpu_dev;      /* FBS: [n_vrows][ld] doubles, Solution.wpu per scenario (NULL = zeros)       */
 } GpSolveExtras;
 
 /*
@@ -280,6 +287,11 @@ int gp_peer_free(int device, void* ptr);
 int gp_peer_open(int device, const void* handle, void** ptr_out);
 int gp_peer_close(int device, void* ptr);
 int gp_peer_push(int device, int32_t n_dst, void* const* dst, const void* src_dev, int64_t bytes, void* stream);
+
+/* gp_fbs_post with GpSolveExtras.wpu_dev added to sV (extras may be NULL; its other fields are ignored). */
+int gp_fbs_post_ex(GpFeeder* f, int64_t S, int64_t ld, const double* spu_dev, const GpSolveExtras* extras,
+                   const double* V_dev, const double* I_dev, double* sV_dev, double* Vmag_dev, double* Stx_dev,
+                   double* Srx_dev, double* loss_dev, void* stream);
 
 /* Number of rows of GpSolveExtras.gamma_dev for this feeder (0 = no regulators; negative = error). */
 int gp_gamma_rows(GpFeeder* f);

@@ -255,20 +255,21 @@ class FBSOracle:
         self.nrows_I = c.nl + c.ntf + c.nvr                                       # circuit.py:173-184
 
     # solution.py:177-220
-    def _calc_sV(self, V, spu, b=None):
+    def _calc_sV(self, V, spu, b=None, wpu=None):
         c = self.c
+        w = c.wpu if wpu is None else wpu          # Solution.wpu (solution.py:106, 188-203): [nb,3] or [S,nb,3]
         if b is None:
             aV = np.abs(V)
-            upd = spu * (c.aPQ + c.aI * aV + c.aZ * aV ** 2) - 1j * c.cappu * aV ** 2 + 1j * c.wpu
+            upd = spu * (c.aPQ + c.aI * aV + c.aZ * aV ** 2) - 1j * c.cappu * aV ** 2 + 1j * w
             upd[..., c.bus_pm == 0] = 0
             return upd
         aV = np.abs(V[:, b])
         upd = spu[:, b] * (c.aPQ[b] + c.aI[b] * aV + c.aZ[b] * aV ** 2) \
-            - 1j * c.cappu[b] * aV ** 2 + 1j * c.wpu[b]
+            - 1j * c.cappu[b] * aV ** 2 + 1j * (w[b] if w.ndim == 2 else w[:, b])
         upd[:, c.bus_pm[b] == 0] = 0
         return upd
 
-    def _sweep(self, V, I, spu):
+    def _sweep(self, V, I, spu, wpu=None):
         """One pass of the while-body of ``solve`` (:88-121) on arrays
         ``V[S,nb,3]``, ``I[S,rows,3]`` in place."""
         c = self.c
@@ -284,14 +285,14 @@ class FBSOracle:
                     _, row, Z, _pm = e
                     newV = V[:, bus] - np.einsum('ij,sj->si', Z, I[:, row])
                     V[:, child] = newV * c.bus_pm[child]
-        sV = self._calc_sV(V, spu)                                                # :101
+        sV = self._calc_sV(V, spu, wpu=wpu)                                       # :101
         for bus in reversed(self.topo_order):                                     # :104-121
             parents = self.parents.get(bus, [])
             if len(parents) > 1:
                 raise ValueError(f"Network not radial. Bus {bus} has parents {parents}")
             if len(parents) == 1:
                 parent = parents[0]
-                sV[:, bus] = self._calc_sV(V, spu, bus)                           # :114
+                sV[:, bus] = self._calc_sV(V, spu, bus, wpu=wpu)                  # :114
                 e = self.edge[(parent, bus)]
                 if e[0] == 'vr':
                     # vr_current :234-254 -> Itx stays 0 (aliased row never written)
@@ -318,14 +319,16 @@ class FBSOracle:
                 V[:, parent] = V[:, parent] * c.bus_pm[parent]
         return V, I
 
-    def solve(self, spu=None, maxiter=MAXITER, V0=None, I0=None):
+    def solve(self, spu=None, maxiter=MAXITER, V0=None, I0=None, wpu=None):
         """Flat-start solve of ``S`` scenarios; ``spu[S,nb,3]`` complex (default:
         the feeder's nominal loads, ``S=1``).  Each scenario stops at its own
         iteration exactly as a separate reference object would.
 
         ``V0, I0``: warm start - what a reference object does whose ``Vtest`` and
         ``iterations`` are reset before ``solve()`` is called again: ``self.V`` and
-        ``self.I`` keep the earlier solution (:76-90 never re-initialise them)."""
+        ``self.I`` keep the earlier solution (:76-90 never re-initialise them).
+        ``wpu[S,nb,3]`` real: per-scenario ``Solution.wpu`` (the controllable reactive
+        injection of ``calc_sV``, solution.py:106, 203; all zeros unless a caller sets it)."""
         c = self.c
         if spu is None:
             spu = c.spu_matrix()[None]
@@ -342,7 +345,7 @@ class FBSOracle:
         active = (~converged) & (iters < maxiter)
         while active.any():                                                       # :87
             idx = np.nonzero(active)[0]
-            Vs, Is = self._sweep(V[idx], I[idx], spu[idx])
+            Vs, Is = self._sweep(V[idx], I[idx], spu[idx], None if wpu is None else wpu[idx])
             V[idx], I[idx] = Vs, Is
             iters[idx] += 1                                                       # :123
             Vtest[idx] = Vs[:, self.root]                                         # :125
@@ -350,7 +353,7 @@ class FBSOracle:
                 diff[idx] = np.max(np.abs(Vtest[idx] - self.Vref), axis=1)        # :126
                 converged[idx] = diff[idx] <= self.tolerance                      # :128
             active = (~converged) & (iters < maxiter)
-        sV = self._calc_sV(V, spu)                                                # :132
+        sV = self._calc_sV(V, spu, wpu=wpu)                                       # :132
         Vmag = np.abs(V)                                                          # solution.py:232
         nl = c.nl
         Srx = V[:, c.line_rx] * np.conj(I[:, :nl])                                # solution.py:227-230
@@ -758,3 +761,50 @@ def solve_with_taps(oracle_cls, model, spu, taps, zip_v=DEFAULT_ZIP, **kw):
                 out[k] = np.zeros((spu.shape[0],) + v.shape[1:], dtype=v.dtype)
             out[k][idx] = v
     return out
+
+
+# ==========================================================================
+# volt-var droop around the FBS solve
+# ==========================================================================
+def vvc_get_Q(V_pu, points, minQ, maxQ):
+    """``VoltVARController.get_Q`` (volt_var_controller.py:20-38) elementwise on an array."""
+    V1, V2, V3, V4 = points
+    V_pu = np.asarray(V_pu, dtype=float)
+    out = np.empty_like(V_pu)
+    for i, v in np.ndenumerate(V_pu):
+        if v <= V1:
+            q = maxQ
+        elif v <= V2:
+            slope = (- maxQ) / (V2 - V1)
+            b = - (slope * V2)
+            q = slope * v + b
+        elif v <= V3:
+            q = 0
+        elif v <= V4:
+            slope = (minQ) / (V4 - V3)
+            b = - (slope * V3)
+            q = slope * v + b
+        else:
+            q = minQ
+        out[i] = -q
+    return out
+
+
+def fbs_volt_var(oracle: FBSOracle, spu, ctl, points, minQ, maxQ, rounds):
+    """The quasi-static loop of ``oracle/make_golden_wpu.py`` on a batch: solve (round 0 from flat
+    start, then from the last state), ``wpu[ctl] = get_Q(|V[ctl]|)``, again.  ``ctl``: (bus, phase)
+    pairs.  Returns per round V ``[rounds,S,nb,3]``, Q ``[rounds,S,n_ctl]``, iterations ``[rounds,S]``."""
+    spu = np.asarray(spu, dtype=complex)
+    S = spu.shape[0]
+    wpu = np.zeros((S, oracle.c.nb, 3))
+    V0 = I0 = None
+    Vs, Qs, its = [], [], []
+    for _ in range(rounds):
+        r = oracle.solve(spu, V0=V0, I0=I0, wpu=wpu)
+        V0, I0 = r['V'], r['I']
+        q = np.stack([vvc_get_Q(np.abs(r['V'][:, k, p]), points, minQ, maxQ) for k, p in ctl], axis=1)
+        wpu = np.zeros((S, oracle.c.nb, 3))
+        for j, (k, p) in enumerate(ctl):
+            wpu[:, k, p] = q[:, j]
+        Vs.append(r['V']), Qs.append(q), its.append(r['iterations'])
+    return np.array(Vs), np.array(Qs), np.array(its)

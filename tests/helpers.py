@@ -77,3 +77,11 @@ def warm_golden():
 
 WARM_FEEDERS = {'IEEE_13_Bus_allwye_noxfm_noreg': {}, 'IEEE_13_Bus_allwye': {'reg1': 9, 'reg2': 7, 'reg3': 9},
                 'IEEE_37_Bus_allwye_noxfm_noreg': {}}
+
+
+def wpu_golden():
+    """tests/golden/ref_wpu.npz (oracle/make_golden_wpu.py): unmodified reference objects with a non-zero
+    Solution.wpu attribute, and the reference's VoltVARController driven around them."""
+    if 'wpu' not in _cache:
+        _cache['wpu'] = np.load(os.path.join(GOLDEN, 'ref_wpu.npz'))
+    return _cache['wpu']

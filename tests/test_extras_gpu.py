@@ -63,7 +63,8 @@ def test_fbs_taps_random_batch_matches_oracle(feeder, S, n_combo, seed):
 
 
 def test_fbs_constant_taps_equal_a_feeder_built_with_them():
-    """Ratios read per scenario or baked into the step table: the same arithmetic, bit for bit."""
+    """Ratios read per scenario or baked into the step table: the same sweeps (the two kernel instances
+    may contract multiply-adds differently, so the comparison is at rounding level, not bitwise)."""
     from gigpower_b200 import _cabi
     feeder, taps = 'IEEE_13_Bus_allwye', {'reg1': -3, 'reg2': 12, 'reg3': 5}
     rng = np.random.Generator(np.random.PCG64(5))
@@ -85,7 +86,7 @@ def test_fbs_constant_taps_equal_a_feeder_built_with_them():
         _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 0))
     for r in (a, a2):
         assert np.array_equal(r.iterations, b.iterations)
-        assert np.array_equal(r.V_rows, b.V_rows) and np.array_equal(r.I_rows, b.I_rows)
+        assert rel_err(r.V_rows, b.V_rows) <= 1e-13 and rel_err(r.I_rows, b.I_rows) <= 1e-13
     with pytest.raises(KeyError):
         s.solve_batch(load_mult=mult, taps={'nosuchreg': 1})
     with pytest.raises(ValueError):
@@ -238,3 +239,81 @@ def test_extras_argument_checks():
     assert rc == 0
     torch.cuda.synchronize()
     assert int(it.max()) >= 1
+
+
+# ---------------------------------------------------------------------------------------------
+# Solution.wpu (reactive injection) and the volt-var droop
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('feeder', list(WARM_FEEDERS))
+def test_fbs_reactive_injection_matches_reference_objects(feeder):
+    from helpers import wpu_golden
+    g = wpu_golden()
+    s = _fbs(feeder, taps=WARM_FEEDERS[feeder])
+    r = s.solve_batch(load_mult=g[feeder + '/mult'], wpu=g[feeder + '/wpu'], outputs=('V', 'I', 'sV'))
+    assert list(r.iterations) == list(g[feeder + '/FBS/iterations'])
+    assert rel_err(r.V, g[feeder + '/FBS/V']) <= TOL and rel_err(r.sV, g[feeder + '/FBS/sV']) <= TOL
+    assert rel_err(r.I, g[feeder + '/FBS/I'][:, :r.I.shape[1]]) <= TOL
+    # without the injection the voltages differ (the term is really applied)
+    r0 = s.solve_batch(load_mult=g[feeder + '/mult'], outputs=('V',))
+    assert rel_err(r0.V, g[feeder + '/FBS/V']) > 1e-5
+
+
+def test_fbs_reactive_injection_random_batch_matches_oracle():
+    from oracle.gp_oracle import FBSOracle
+    feeder, S = 'IEEE_34_Bus_allwye', 400
+    rng = np.random.Generator(np.random.PCG64(51))
+    o = FBSOracle(load_model(feeder), ZIPS['test_zip'])
+    c = o.c
+    mult = rng.uniform(0.5, 1.3, size=(S, len(c.load_names)))
+    wpu = rng.uniform(-0.02, 0.02, size=(S, c.nb, 3)) * (c.bus_pm[None] != 0) * (rng.uniform(size=(S, c.nb, 3)) < 0.3)
+    want = o.solve(c.spu_matrix(c.load_kw * mult, c.load_kvar * mult), wpu=wpu)
+    s = _fbs(feeder)
+    r = s.solve_batch(load_mult=mult, wpu=wpu, outputs=('V', 'sV', 'Vmag', 'loss'))
+    assert np.array_equal(r.iterations, want['iterations'])
+    assert rel_err(r.V, want['V']) <= TOL and rel_err(r.sV, want['sV']) <= TOL
+    # packed rows on the device give the same
+    import torch
+    b, p = np.nonzero(s.tables.vrow >= 0)
+    rows = np.zeros((s.tables.n_vrows, S))
+    rows[s.tables.vrow[b, p]] = wpu[:, b, p].T
+    r2 = s.solve_batch(load_mult=mult, wpu=torch.from_numpy(rows).cuda(), outputs=('V',))
+    assert np.array_equal(r2.V_rows, r.V_rows)
+    with pytest.raises(ValueError):
+        s.solve_batch(load_mult=mult, wpu=rows[:, :5])
+
+
+@pytest.mark.parametrize('feeder', list(WARM_FEEDERS))
+def test_volt_var_study_matches_the_reference_controller(feeder):
+    from helpers import wpu_golden
+    from gigpower_b200.study import VoltVarStudy
+    g = wpu_golden()
+    s = _fbs(feeder, taps=WARM_FEEDERS[feeder])
+    want_V, want_Q, want_it = g[feeder + '/VVC/V'], g[feeder + '/VVC/Q'], g[feeder + '/VVC/iterations']
+    n, rounds = want_V.shape[0], want_V.shape[1]
+    minQ, maxQ = g[feeder + '/VVC/q']
+    study = VoltVarStudy(s, [tuple(int(v) for v in x) for x in g[feeder + '/VVC/ctl']],
+                         points=tuple(g[feeder + '/VVC/points']), minQ=minQ, maxQ=maxQ)
+    last, Q, its = study.run(load_mult=g[feeder + '/mult'][:n], rounds=rounds)
+    assert np.array_equal(its.cpu().numpy().T, want_it)
+    assert rel_err(Q.cpu().numpy().transpose(2, 0, 1), want_Q) <= TOL
+    assert rel_err(last.V, want_V[:, -1]) <= TOL
+
+
+def test_volt_var_study_batch_matches_oracle_loop():
+    from oracle.gp_oracle import FBSOracle, fbs_volt_var
+    from gigpower_b200.study import VoltVarStudy
+    feeder, S, rounds = 'IEEE_13_Bus_allwye_noxfm_noreg', 300, 5
+    rng = np.random.Generator(np.random.PCG64(61))
+    o = FBSOracle(load_model(feeder), ZIPS['test_zip'])
+    c = o.c
+    mult = rng.uniform(0.4, 1.6, size=(S, len(c.load_names)))
+    ctl = [(c.bus_names.index('675'), p) for p in range(3)] + [(c.bus_names.index('634'), 1)]
+    pts = (0.93, 0.97, 1.0, 1.04)
+    V, Q, its = fbs_volt_var(o, c.spu_matrix(c.load_kw * mult, c.load_kvar * mult), ctl, pts, -0.1, 0.1, rounds)
+    s = _fbs(feeder)
+    study = VoltVarStudy(s, [('675', 0), ('675', 1), ('675', 2), ('634', 1)], points=pts, minQ=-0.1, maxQ=0.1)
+    last, Qg, itg = study.run(load_mult=mult, rounds=rounds)
+    assert np.array_equal(itg.cpu().numpy(), its)
+    assert rel_err(Qg.cpu().numpy().transpose(0, 2, 1), Q) <= TOL
+    assert rel_err(last.V, V[-1]) <= TOL
+    assert np.abs(Q).max() > 0.01 and (its[-1] <= its[0]).all()

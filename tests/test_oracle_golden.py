@@ -220,3 +220,38 @@ def test_nr3_warm_started_sequence(feeder):
         assert int(r['iterations'][0]) == int(wg[feeder + '/NR3/iterations'][h]), h
         assert np.abs(r['XNR'][0] - wg[feeder + '/NR3/XNR'][h]).max() <= 1e-11
         X0 = r['XNR']
+
+
+# ---- Solution.wpu and the volt-var droop -----------------------------
+from oracle.gp_oracle import fbs_volt_var, vvc_get_Q                # noqa: E402
+from helpers import wpu_golden                                       # noqa: E402
+
+
+@pytest.mark.parametrize('feeder', list(WARM_FEEDERS))
+def test_fbs_with_reactive_injection(feeder):
+    g = wpu_golden()
+    o = FBSOracle(load_model(feeder), ZIPS['test_zip'])
+    c = o.c
+    mult = g[feeder + '/mult']
+    r = o.solve(c.spu_matrix(c.load_kw * mult, c.load_kvar * mult), wpu=g[feeder + '/wpu'])
+    assert list(r['iterations']) == list(g[feeder + '/FBS/iterations'])
+    for p in ('V', 'I', 'sV'):
+        assert np.abs(r[p] - g[feeder + '/FBS/' + p]).max() <= TOL, p
+
+
+@pytest.mark.parametrize('feeder', list(WARM_FEEDERS))
+def test_volt_var_loop_matches_the_reference_controller(feeder):
+    g = wpu_golden()
+    o = FBSOracle(load_model(feeder), ZIPS['test_zip'])
+    c = o.c
+    n = g[feeder + '/VVC/V'].shape[0]
+    mult = g[feeder + '/mult'][:n]
+    ctl = [tuple(x) for x in g[feeder + '/VVC/ctl']]
+    minQ, maxQ = g[feeder + '/VVC/q']
+    V, Q, its = fbs_volt_var(o, c.spu_matrix(c.load_kw * mult, c.load_kvar * mult), ctl, tuple(g[feeder + '/VVC/points']),
+                             minQ, maxQ, g[feeder + '/VVC/V'].shape[1])
+    assert np.array_equal(its.T, g[feeder + '/VVC/iterations'])
+    assert np.abs(np.swapaxes(V, 0, 1) - g[feeder + '/VVC/V']).max() <= TOL
+    assert np.abs(np.swapaxes(Q, 0, 1) - g[feeder + '/VVC/Q']).max() <= TOL
+    assert np.abs(Q).max() > 1e-3            # the droop is active in these cases
+    assert vvc_get_Q(np.array([0.9, 1.0, 1.1]), (0.95, 0.98, 1.02, 1.05), -0.05, 0.05).tolist() == [-0.05, -0.0, 0.05]
