@@ -64,6 +64,19 @@ def taps_golden():
     return _cache['taps']
 
 
+def pinned_34():
+    """tests/golden/ref_34_taps.npz (oracle/pin_taps_34.py): the taps behind gigpower's recorded
+    tables of IEEE_34_Bus_allwye.dss, and the unmodified reference's full-precision results at them."""
+    if 'p34' not in _cache:
+        _cache['p34'] = np.load(os.path.join(GOLDEN, 'ref_34_taps.npz'))
+    return _cache['p34']
+
+
+def pinned_34_taps():
+    z = pinned_34()
+    return {str(n): int(t) for n, t in zip(z['regcontrols'], z['taps'])}
+
+
 TAP_FEEDERS = ['IEEE_13_Bus_allwye', 'IEEE_37_Bus_allwye', 'IEEE_34_Bus_allwye']
 
 

@@ -4,7 +4,8 @@ voltages within 1e-9 relative, identical iteration counts."""
 import numpy as np
 import pytest
 
-from helpers import (ZIPS, ALL_FEEDERS, LINES_ONLY, feeder_path, load_model, snapshots, scenarios, rel_err)
+from helpers import (ZIPS, ALL_FEEDERS, LINES_ONLY, feeder_path, load_model, snapshots, scenarios, rel_err,
+                     recorded, pinned_34, pinned_34_taps)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -44,6 +45,29 @@ def test_snapshot_matches_reference(feeder, zname):
     V1 = s.V.copy()
     s.solve()
     assert np.array_equal(V1, s.V) and s.iterations == int(snap[k + 'iterations'])
+
+
+@pytest.mark.parametrize('zname', list(ZIPS))
+def test_34_bus_snapshot_at_the_taps_of_the_recorded_tables(zname):
+    """IEEE_34_Bus_allwye.dss with the six taps recovered by oracle/pin_taps_34.py: the
+    unmodified reference's full-precision results, and gigpower's own recorded tables."""
+    z, rec = pinned_34(), recorded()
+    s = _fbs('IEEE_34_Bus_allwye', zname, taps=pinned_34_taps())
+    s.solve()
+    k = f'{zname}/FBS/'
+    assert s.iterations == int(z[k + 'iterations'])
+    assert abs(s.convergence_diff - float(z[k + 'convergence_diff'])) <= 1e-12
+    for p in ('V', 'I', 'sV', 'Vmag', 'Stx', 'Srx'):
+        assert getattr(s, p).shape == z[k + p].shape, p
+        assert rel_err(getattr(s, p), z[k + p]) <= TOL, p
+    for p in ('V', 'I', 'sV', 'Vmag', 'Stx', 'Srx'):
+        table = rec[f'IEEE_34_Bus_allwye/{zname}/FBS/{p}']
+        frame = s.get_data_frame(p, orient='rows')
+        assert list(table) == list(frame.index)
+        want = np.array([[complex(*x) for x in table[n]] for n in table])
+        got = frame.to_numpy()
+        assert np.abs(got.real - want.real).max() <= 0.005 + 1e-9, p
+        assert np.abs(got.imag - want.imag).max() <= 0.005 + 1e-9, p
 
 
 @pytest.mark.parametrize('feeder', LINES_ONLY)

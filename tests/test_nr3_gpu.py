@@ -4,15 +4,16 @@ complex bus voltages, identical Newton iteration counts."""
 import numpy as np
 import pytest
 
-from helpers import ZIPS, ALL_FEEDERS, LINES_ONLY, feeder_path, load_model, snapshots, scenarios, rel_err
+from helpers import (ZIPS, ALL_FEEDERS, LINES_ONLY, feeder_path, load_model, snapshots, scenarios, rel_err,
+                     recorded, pinned_34, pinned_34_taps)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
 
-def _nr3(feeder, zname='test_zip'):
+def _nr3(feeder, zname='test_zip', **kw):
     from gigpower_b200.solution_nr3 import SolutionNR3
-    return SolutionNR3(feeder_path(feeder), zip_v=np.asarray(ZIPS[zname]))
+    return SolutionNR3(feeder_path(feeder), zip_v=np.asarray(ZIPS[zname]), **kw)
 
 
 @pytest.mark.parametrize('zname', list(ZIPS))
@@ -34,6 +35,29 @@ def test_snapshot_matches_reference(feeder, zname):
         assert not rows.empty and rows.shape[1] == 3 and cols.shape[0] == 3
     assert list(s.get_V('rows').index) == s.circuit.buses.all_names()
     assert list(s.get_V().index) == ['A', 'B', 'C']          # NR3 defaults to orient='cols' (:30)
+
+
+@pytest.mark.parametrize('zname', list(ZIPS))
+def test_34_bus_snapshot_at_the_taps_of_the_recorded_tables(zname):
+    """IEEE_34_Bus_allwye.dss with the six taps recovered by oracle/pin_taps_34.py: the
+    unmodified reference's full-precision results, and gigpower's own recorded tables."""
+    z, rec = pinned_34(), recorded()
+    s = _nr3('IEEE_34_Bus_allwye', zname, taps=pinned_34_taps())
+    s.solve()
+    k = f'{zname}/NR3/'
+    assert s.itercount == int(z[k + 'iterations'])
+    assert rel_err(s.XNR, z[k + 'XNR']) <= TOL
+    for p in ('V', 'I', 'sV', 'Vmag', 'Stx', 'Srx', 'i_Node'):
+        assert getattr(s, p).shape == z[k + p].shape, p
+        assert rel_err(getattr(s, p), z[k + p]) <= TOL, p
+    for p in ('V', 'I', 'sV', 'Vmag', 'Stx', 'Srx'):
+        table = rec[f'IEEE_34_Bus_allwye/{zname}/NR3/{p}']
+        frame = s.get_data_frame(p, orient='rows')
+        assert list(table) == list(frame.index)
+        want = np.array([[complex(*x) for x in table[n]] for n in table])
+        got = frame.to_numpy()
+        assert np.abs(got.real - want.real).max() <= 0.005 + 1e-9, p
+        assert np.abs(got.imag - want.imag).max() <= 0.005 + 1e-9, p
 
 
 @pytest.mark.parametrize('feeder', LINES_ONLY)
