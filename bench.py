@@ -785,7 +785,7 @@ def run_ours(args, wl):
             if not (solver == 'nr3' and n_per == 1):
                 pool.step(feeder, solver, rows, max(n_per // 8, 1))      # warm the workers
             n, wall, reps = 0, 0.0, 0
-            while wall < 10.0 and reps < 50:
+            while wall < 10.0 and reps < 200:
                 dn, dw = pool.step(feeder, solver, rows, n_per)
                 n, wall, reps = n + dn, wall + dw, reps + 1
             pool.close()
