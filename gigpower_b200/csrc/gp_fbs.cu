@@ -1312,7 +1312,7 @@ static int fbs_jit_build(GpFeeder* f, int nw, bool ig, bool read_ahead, void** m
     int cr = dr.ModuleLoadData(&mod, bin.data());
     if (cr != 0) return fail(GP_EJIT, "gp_fbs_specialise: cuModuleLoadData failed (%d)", cr);
     cr = dr.ModuleGetFunction(&fn, mod, "gp_fbs_jit_kernel");
-    const int smem = nw * (im->n_vrows + (ig ? 0 : im->n_irows)) * 512;
+    const int smem = nw * (im->n_vrows + (ig ? 0 : im->n_islots)) * 512;
     if (cr == 0) cr = dr.FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, smem);
     if (cr != 0) {
         dr.ModuleUnload(mod);
@@ -1494,15 +1494,21 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
             }
     }
     {   // plan of the specialised kernel: I rows in shared memory next to V, or in global memory (the I
-        // array) when that lets more warps run per SM; at most 8 warps (about 240 registers per thread)
-        static const int sizes[] = {8, 6, 4, 3, 2, 1};
+        // array) when that lets more warps run per SM; at most 8 warps (about 240 registers per thread).
+        // In shared memory the I rows take one slot per DISTINCT value (fbs_jit_islots).
+        {
+            std::vector<int> slot;
+            std::vector<char> owner;
+            im->n_islots = fbs_jit_islots(im->h_steps, im->h_child, d->n_irows, slot, owner);
+        }
+        static const int sizes[] = {8, 7, 6, 5, 4, 3, 2, 1};
         auto pick = [&](size_t per_warp) {
             const int fit = (int)((size_t)smem_optin / per_warp);
             for (int w : sizes)
                 if (w <= fit) return w;
             return 0;
         };
-        const int w_is = pick((size_t)(d->n_vrows + d->n_irows) * 512), w_ig = pick((size_t)d->n_vrows * 512);
+        const int w_is = pick((size_t)(d->n_vrows + im->n_islots) * 512), w_ig = pick((size_t)d->n_vrows * 512);
         // measured on B200: 13-bus 6 -> 8 warps: no gain (the register-passed currents spill);
         // 34-bus 2 -> 4 warps: 1.21x; 37-bus 1 -> 3 warps: 1.49x  =>  only when it at least doubles the warps
         im->jit_plan_ig = g_jit_i_global == 1 || (g_jit_i_global < 0 && w_ig >= 2 * w_is && w_ig > 0);
@@ -1562,7 +1568,7 @@ static int fbs_jit_launch(FbsImpl* im, int64_t S, int64_t ld, const double* spu,
     const int nw = im->jit_warps;
     long long blocks = (n_tiles + nw - 1) / nw;
     if (blocks > im->n_sm) blocks = im->n_sm;
-    const unsigned smem = (unsigned)nw * (unsigned)(im->n_vrows + (im->jit_ig ? 0 : im->n_irows)) * 512u;
+    const unsigned smem = (unsigned)nw * (unsigned)(im->n_vrows + (im->jit_ig ? 0 : im->n_islots)) * 512u;
     long long S_arg = S;
     double tol_arg = tol;
     int maxiter_arg = maxiter;

@@ -76,6 +76,7 @@ struct FbsImpl {
     bool jit_host_tried = false;
     int jit_warps = 0;
     bool jit_ig = false;          // the specialised kernel keeps the I rows in global memory (the I array)
+    int n_islots = 0;             // shared-memory slots the specialised kernel needs for the I rows (fbs_jit_islots)
     int jit_plan_warps = 0;       // warps per block gp_fbs_specialise will use (0 = feeder does not fit)
     bool jit_plan_ig = false;
     void* d_zc = nullptr;         // device staging rows of the one-launch host path
@@ -92,6 +93,8 @@ struct FbsImpl {
 std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<int4>& child,
                            const std::vector<int>& lines, const FbsConst& k, int n_vrows, int n_irows, int n_srows,
                            int nw, bool ig, bool read_ahead = false);
+int fbs_jit_islots(const std::vector<FbsStep>& steps, const std::vector<int4>& child, int n_irows,
+                   std::vector<int>& slot, std::vector<char>& owner);
 int jit_compile(const std::string& src, std::vector<char>& cubin, std::string& log);
 
 }  // namespace gp

@@ -52,6 +52,45 @@ std::string lit(double x) {
 
 }  // namespace
 
+// Shared-memory slots of the I rows.  Two kinds of row need no storage of their own:
+//  * a bus-phase without load and capacitor whose current comes from exactly one child edge carries
+//    that child's current unchanged (I = 0 + I_child, update_current :256-288): the row shares the
+//    child's slot and its store is dropped (the value is already there);
+//  * without load, capacitor and any child current the row stays at the flat start's zero.
+// IEEE 13-bus: 35 rows -> 24 slots, which is what lets a seventh warp fit into an SM.
+// slot[r] = shared-memory slot of I row r, -1 = constant zero; owner[r] = the row's step stores it.
+int fbs_jit_islots(const std::vector<FbsStep>& steps, const std::vector<int4>& child, int n_irows,
+                   std::vector<int>& slot, std::vector<char>& owner) {
+    slot.assign((size_t)(n_irows > 0 ? n_irows : 0), -2);
+    owner.assign(slot.size(), 0);
+    int n_slots = 0;
+    for (int i = (int)steps.size() - 1; i >= 0; --i) {      // children before parents
+        const FbsStep& st = steps[i];
+        if ((st.kind & 0xff) == GP_EDGE_VR) continue;
+        for (int p = 0; p < 3; ++p) {
+            const int r = st.edge_irow[p];
+            if (r < 0 || r >= n_irows) continue;
+            const bool has_load = st.bus_vrow[p] >= 0 && st.load_srow[p] >= 0;
+            const bool has_cap = st.bus_vrow[p] >= 0 && st.cap[p] != 0.0;
+            int n_src = 0, src = -1;
+            bool known = true;
+            for (int c = 0; c < st.child_count; ++c) {
+                const int4 cr = child[st.child_begin + c];
+                const int crow = p == 0 ? cr.x : (p == 1 ? cr.y : cr.z);
+                if (crow < 0) continue;
+                if (crow >= n_irows || slot[crow] == -2) known = false;     // not a row of a later step: keep apart
+                else if (slot[crow] >= 0) { ++n_src; src = slot[crow]; }
+            }
+            if (!known || has_load || has_cap || n_src > 1) { slot[r] = n_slots++; owner[r] = 1; }
+            else if (n_src == 1) slot[r] = src;
+            else slot[r] = -1;
+        }
+    }
+    for (size_t r = 0; r < slot.size(); ++r)
+        if (slot[r] == -2) { slot[r] = n_slots++; owner[r] = 1; }           // rows no step owns (defensive)
+    return n_slots;
+}
+
 std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<int4>& child,
                            const std::vector<int>& lines, const FbsConst& k, int n_vrows, int n_irows, int n_srows,
                            int nw, bool ig, bool read_ahead) {
@@ -67,7 +106,25 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
     const bool spu_regs = n_srows <= 32;      // <= 128 registers of loads held for the whole solve
     o("// generated by libgigpower_b200 (gp_fbs_jit.cu): %d steps, %d V rows, %d I rows, %d spu rows\n", n_steps,
       n_vrows, n_irows, n_srows);
-    o("#define NW %d\n#define NV %d\n#define NI %d\n#define NS %d\n", nw, n_vrows, n_irows, n_srows);
+    // I row -> storage: shared-memory slots with aliasing (fbs_jit_islots) or, with ig, the caller's rows as they are
+    std::vector<int> islot;
+    std::vector<char> iowner;
+    int n_islots = n_irows;
+    if (ig) {
+        islot.resize((size_t)n_irows);
+        for (int r = 0; r < n_irows; ++r) islot[r] = r;
+        iowner.assign((size_t)n_irows, 1);
+    } else {
+        n_islots = fbs_jit_islots(steps, child, n_irows, islot, iowner);
+    }
+    auto ild = [&](int r) {                 // expression for the value of I row r
+        if (islot[r] < 0) return std::string("zero");
+        char b[48];
+        snprintf(b, sizeof(b), "ILD(%d)", islot[r]);
+        return std::string(b);
+    };
+    o("#define NW %d\n#define NV %d\n#define NI %d\n#define NIP %d\n#define NS %d\n", nw, n_vrows, n_irows, n_islots,
+      n_srows);
     o("#define IG_MODE %d\n", ig ? 1 : 0);
     o("#define READ_AHEAD %d\n", (read_ahead && n_srows <= 32) ? 1 : 0);   // the next tile's loads are held in registers
     o("struct GpPeerDst { double* vmag[%d]; double2* loss[%d]; int n; int pad; };\n", GP_MAX_PEERS, GP_MAX_PEERS);
@@ -76,7 +133,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
           "#define ILD(r) __ldcg(reinterpret_cast<const double2*>(Ip + (size_t)(r) * (size_t)ldb))\n"
           "#define IST(r, v) (*reinterpret_cast<double2*>(Ip + (size_t)(r) * (size_t)ldb) = (v))\n");
     else
-        o("#define IPTR double2*\n#define SROWS (NV + NI)\n"
+        o("#define IPTR double2*\n#define SROWS (NV + NIP)\n"
           "#define ILD(r) Ip[(r) * 32]\n"
           "#define IST(r, v) (Ip[(r) * 32] = (v))\n");
     std::vector<int> row2step((size_t)(n_irows > 0 ? n_irows : 1), -1);
@@ -177,14 +234,14 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
         for (int q = 0; q < 3; ++q)
             if (st.edge_irow[q] >= 0) {
                 if (ig) o("                const double2 i%d = fi%d_%d;\n", q, i, q);
-                else o("                const double2 i%d = ILD(%d);\n", q, st.edge_irow[q]);
+                else o("                const double2 i%d = %s;\n", q, ild(st.edge_irow[q]).c_str());
             }
         for (int p = 0; p < 3; ++p) {       // update_voltage_forward :162-184
             if (st.bus_vrow[p] < 0) continue;
             if (st.par_vrow[p] >= 0) o("                { double2 v = Vs[%d];\n", st.par_vrow[p] * 32);
             else o("                { double2 v = zero;\n");
             for (int q = 0; q < 3; ++q) {
-                if (st.edge_irow[q] < 0) continue;
+                if (st.edge_irow[q] < 0 || islot[st.edge_irow[q]] < 0) continue;    // Z * 0: nothing to subtract
                 const int zi = 9 * i + 3 * p + q;
                 // complex multiply-subtract: four fused multiply-adds on the fast path (the
                 // three-operation form of fbs_fwd_step, bit for bit, on the exact path)
@@ -233,7 +290,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
                         o("                n%d.x += cn%d_%d.x; n%d.y += cn%d_%d.y;\n", p, row2step[crow[p]], p, p,
                           row2step[crow[p]], p);
                     else
-                        o("                { const double2 c = ILD(%d); n%d.x += c.x; n%d.y += c.y; }\n", crow[p], p, p);
+                        o("                { const double2 c = %s; n%d.x += c.x; n%d.y += c.y; }\n", ild(crow[p]).c_str(), p, p);
                 }
             }
             // calc_sV (solution.py:177-220) + update_current (:256-288); a bus-phase without load
@@ -284,7 +341,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
               "                }\n");
             for (int p = 0; p < 3; ++p)
                 if (st.edge_irow[p] >= 0) {
-                    o("                IST(%d, n%d);\n", st.edge_irow[p], p);
+                    if (iowner[st.edge_irow[p]]) o("                IST(%d, n%d);\n", islot[st.edge_irow[p]], p);
                     if (ig) o("                cn%d_%d = n%d;\n", i, p, p);
                 }
         }
@@ -292,7 +349,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
             if (st.bus_vrow[p] < 0 || st.par_vrow[p] < 0) continue;
             o("                { double2 v = b%d;\n", p);
             for (int q = 0; q < 3; ++q) {
-                if (st.edge_irow[q] < 0) continue;
+                if (st.edge_irow[q] < 0 || islot[st.edge_irow[q]] < 0) continue;    // a current that is always zero
                 const int zi = 9 * i + 3 * p + q;
                 o("                  if (EXACT) {\n");
                 o("                    v.x += ZR[%d] * n%d.x - ZI[%d] * n%d.y;\n", zi, q, zi, q);
@@ -317,6 +374,11 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
       "            bad_out = bad;\n"
       "            return diff;\n"
       "}\n");
+    // every I row of the caller's layout from its slot (shared rows are written once per row that carries them)
+    o("#define GP_I_ROWS_OUT(dst)");
+    for (int r = 0; r < n_irows; ++r)
+        o(" \\\n    *reinterpret_cast<double2*>((dst) + (size_t)%d * (size_t)ldb) = %s;", r, ild(r).c_str());
+    o("\n");
     o("extern \"C\" __global__ void __launch_bounds__(NW * 32, 1)\n"
       "gp_fbs_jit_kernel(const char* __restrict__ spu, char* __restrict__ V, char* __restrict__ I,\n"
       "                  int* __restrict__ iters_out, int* __restrict__ status_out, double* __restrict__ diff_out,\n"
@@ -370,7 +432,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
       "        }\n"
       "        IPTR const Ip = %s;\n"
       "        for (int r = 0; r < NV; ++r) Vs[r * 32] = zero;           // flat start (solution.py:108-125)\n"
-      "        for (int r = 0; r < NI; ++r) IST(r, zero);\n"
+      "        for (int r = 0; r < NIP; ++r) IST(r, zero);\n"
       "        int it = 0;\n"
       "        double diff = -1.0;\n"
       "        bool converged = false, exact = false;\n"
@@ -380,7 +442,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
       "            else diff = gp_sweep<false>(Vs, Ip, sp, ldb, bad);\n"
       "            if (bad) {      // a non-finite current: redo this scenario from flat start, exact arithmetic\n"
       "                for (int r = 0; r < NV; ++r) Vs[r * 32] = zero;\n"
-      "                for (int r = 0; r < NI; ++r) IST(r, zero);\n"
+      "                for (int r = 0; r < NIP; ++r) IST(r, zero);\n"
       "                it = 0;\n"
       "                exact = true;\n"
       "                continue;\n"
@@ -405,8 +467,8 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
       "            if (V) for (int r = 0; r < NV; ++r) *reinterpret_cast<double2*>(Vg + (size_t)r * (size_t)ldb) = Vs[r * 32];\n"
       "            // I rows: already in place when they live in the caller's (device) I array; copied out of shared\n"
       "            // memory otherwise; Iout is an optional second destination (mapped host memory in the one-launch path)\n"
-      "            if (!IG_MODE && I) { char* Ig = I + s * 16; for (int r = 0; r < NI; ++r) *reinterpret_cast<double2*>(Ig + (size_t)r * (size_t)ldb) = ILD(r); }\n"
-      "            if (Iout) { char* Io = Iout + s * 16; for (int r = 0; r < NI; ++r) *reinterpret_cast<double2*>(Io + (size_t)r * (size_t)ldb) = ILD(r); }\n"
+      "            if (!IG_MODE && I) { char* Ig = I + s * 16; GP_I_ROWS_OUT(Ig) }\n"
+      "            if (Iout) { char* Io = Iout + s * 16; GP_I_ROWS_OUT(Io) }\n"
       "            iters_out[s] = it;\n"
       "            diff_out[s] = diff;\n"
       "            status_out[s] = converged ? %d : ((diff != diff || isinf(diff)) ? %d : %d);\n",
@@ -440,7 +502,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
         for (int p = 0; p < 3; ++p) {
             const int ir = lines[9 * l + p], tr = lines[9 * l + 3 + p], rr = lines[9 * l + 6 + p];
             if (ir < 0) continue;
-            o("                { const double2 i = ILD(%d);", ir);
+            o("                { const double2 i = %s;", ild(ir).c_str());
             if (tr >= 0) o(" const double2 vt = Vs[%d];", tr * 32);
             else o(" const double2 vt = zero;");
             if (rr >= 0) o(" const double2 vr = Vs[%d];", rr * 32);
