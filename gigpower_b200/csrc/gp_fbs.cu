@@ -40,6 +40,9 @@ static int g_fbs_kernel = 0;
 // B200 (C4, C5, C2): every distance > 0 is 2-8 % SLOWER than none - the kernel is bound by DRAM
 // throughput on 512-byte row pieces, not by exposed latency - so the default is off.
 static int g_fbs_prefetch = 0;
+// gp_set_option("fbs_share_rows", 0|1): the streaming kernel skips the HBM round trips of I rows that only
+// repeat a child's current or stay zero (default 1; 0 = every row travels, for A/B measurements)
+static int g_fbs_share_rows = 1;
 
 // |v| as numpy computes it for the ZIP model (abs then square, solution.py:202)
 __device__ __forceinline__ double cabs2(double2 v, double& a) {
@@ -181,9 +184,10 @@ __device__ __forceinline__ void bwd_fast(const FbsStep* __restrict__ st, const i
         for (int p = 0; p < 3; ++p)
             if ((M >> p) & 1) In[p] = make_double2(nan_to_num(In[p].x), nan_to_num(In[p].y));
     }
+    const int no_store = (bv.w >> 16) & 7;
 #pragma unroll
     for (int p = 0; p < 3; ++p)
-        if ((M >> p) & 1) m.stI(erow[p], In[p]);
+        if (((M >> p) & 1) && !((no_store >> p) & 1)) m.stI(erow[p], In[p]);
 #pragma unroll
     for (int p = 0; p < 3; ++p)
         if ((M >> p) & 1) {                             // update_voltage_backward (:207-232)
@@ -217,7 +221,7 @@ __device__ __forceinline__ void fbs_fwd_step(const FbsStep* __restrict__ st, con
     const double2 zero = make_double2(0.0, 0.0);
     const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
     const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
-    const int kind = bv.w & 0xff, fast = bv.w >> 8;
+    const int kind = bv.w & 0xff, fast = (bv.w >> 8) & 0xff;
     GP_FAST_SWITCH(fwd_fast, FIRST, st, bv, pv, m)
     const int brow[3] = {bv.x, bv.y, bv.z};
     const int prow[3] = {pv.x, pv.y, pv.z};
@@ -271,7 +275,8 @@ __device__ __forceinline__ void fbs_bwd_step(const FbsStep* __restrict__ st, con
     const double2 zero = make_double2(0.0, 0.0);
     const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
     const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
-    const int kind = bv.w & 0xff, fast = bv.w >> 8;
+    const int kind = bv.w & 0xff, fast = (bv.w >> 8) & 0xff;
+    const int no_store = (bv.w >> 16) & 7;      // phases whose I row is a shared row: value in place already
     GP_FAST_SWITCH(bwd_fast, false, st, bv, pv, child_irow, k, m, sp)
     const int brow[3] = {bv.x, bv.y, bv.z};
     const int prow[3] = {pv.x, pv.y, pv.z};
@@ -330,7 +335,7 @@ __device__ __forceinline__ void fbs_bwd_step(const FbsStep* __restrict__ st, con
     for (int p = 0; p < 3; ++p) {
         if (erow[p] >= 0) {
             In[p] = make_double2(nan_to_num(In[p].x), nan_to_num(In[p].y));
-            m.stI(erow[p], In[p]);
+            if (!((no_store >> p) & 1)) m.stI(erow[p], In[p]);
         } else {
             In[p] = zero;
         }
@@ -381,7 +386,8 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
                  char* __restrict__ I, int* __restrict__ iters_out,
                  int* __restrict__ status_out, double* __restrict__ diff_out, double tol,
                  int maxiter, int PF, const int* __restrict__ unfed, int n_unfed,
-                 const char* __restrict__ gam, int warm, const char* __restrict__ wpu) {
+                 const char* __restrict__ gam, int warm, const char* __restrict__ wpu,
+                 const int2* __restrict__ alias, int n_alias) {
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (s >= S) return;
     typedef GMemT<EX> GMem;
@@ -439,6 +445,11 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
         ++it;
         diff = fbs_root_diff(k, m);
         converged = diff <= tol;
+    }
+    // shared I rows (steps = the d_steps_a tables): the caller's array gets every row, once
+    for (int j = 0; j < n_alias; ++j) {
+        const int2 a = __ldg(alias + j);
+        m.stI(a.x, a.y >= 0 ? m.ldI(a.y) : zero);
     }
     iters_out[s] = it;
     diff_out[s] = diff;
@@ -1050,6 +1061,10 @@ extern "C" int gp_set_option(const char* name, int value) {
         g_fbs_prefetch = value;
         return GP_OK;
     }
+    if (name && strcmp(name, "fbs_share_rows") == 0 && (value == 0 || value == 1)) {
+        g_fbs_share_rows = value;
+        return GP_OK;
+    }
     if (name && strcmp(name, "nr3_kernel") == 0 && value >= 0 && value <= 2) {
         g_nr3_kernel = value;
         return GP_OK;
@@ -1460,6 +1475,37 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
     if (e == cudaSuccess) e = up((void**)&im->d_evrows, evrows.data(), evrows.size() * sizeof(int4));
     if (e == cudaSuccess) e = up((void**)&im->d_child, child4.data(), child4.size() * sizeof(int4));
     if (e == cudaSuccess) e = up((void**)&im->d_lines, lines.data(), lines.size() * sizeof(int));
+    {   // the streaming kernel's tables with shared I rows (fbs_jit_islots has the rule): an I row of a
+        // bus-phase without load and capacitor that is fed by exactly one child row IS that row's value
+        // (0 + I_child), so its forward read goes to the child's row and its backward store is dropped
+        // (bits 16..18 of `kind`); one that nothing feeds stays zero and leaves the tables altogether
+        // (the step then takes the generic body, which skips absent rows).  Per sweep that is one write
+        // and one read less per such row; the rows themselves are filled in once after the last sweep.
+        std::vector<int> slot;
+        std::vector<char> owner;
+        fbs_jit_islots(steps, child4, d->n_irows, slot, owner);
+        std::vector<int> owner_row(slot.size() + 1, -1);
+        for (size_t r = 0; r < slot.size(); ++r)
+            if (owner[r] && slot[r] >= 0) owner_row[slot[r]] = (int)r;
+        auto remap = [&](int r) { return (r < 0 || r >= d->n_irows) ? r : (slot[r] < 0 ? -1 : owner_row[slot[r]]); };
+        std::vector<FbsStep> steps_a = steps;
+        std::vector<int4> child_a = child4;
+        std::vector<int2> alias;
+        for (FbsStep& st : steps_a)
+            for (int p = 0; p < 3; ++p) {
+                const int r = st.edge_irow[p];
+                if (r < 0 || r >= d->n_irows || owner[r]) continue;
+                alias.push_back(make_int2(r, remap(r)));
+                st.edge_irow[p] = remap(r);
+                if (st.edge_irow[p] < 0) st.kind &= ~0xff00;        // a dropped row: no mask-specialised body
+                else st.kind |= 1 << (16 + p);
+            }
+        for (int4& c : child_a) c = make_int4(remap(c.x), remap(c.y), remap(c.z), c.w);
+        im->n_alias = (int)alias.size();
+        if (e == cudaSuccess) e = up((void**)&im->d_steps_a, steps_a.data(), steps_a.size() * sizeof(FbsStep));
+        if (e == cudaSuccess) e = up((void**)&im->d_child_a, child_a.data(), child_a.size() * sizeof(int4));
+        if (e == cudaSuccess) e = up((void**)&im->d_alias, alias.data(), alias.size() * sizeof(int2));
+    }
     if (e == cudaSuccess) e = up((void**)&im->d_vrow_srow, vrow_srow.data(), vrow_srow.size() * sizeof(int));
     if (e == cudaSuccess) e = up((void**)&im->d_vrow_cap, vrow_cap.data(), vrow_cap.size() * sizeof(double));
     {   // V rows that no forward step writes: they must hold the flat start's zero
@@ -1529,6 +1575,9 @@ extern "C" int gp_feeder_destroy(GpFeeder* f) {
         FbsImpl* im = (FbsImpl*)f->impl;
         cudaFree(im->d_steps);
         cudaFree(im->d_child);
+        cudaFree(im->d_steps_a);
+        cudaFree(im->d_child_a);
+        cudaFree(im->d_alias);
         cudaFree(im->d_lines);
         cudaFree(im->d_vrow_srow);
         cudaFree(im->d_vrow_cap);
@@ -1641,7 +1690,7 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
         fbs_solve_kernel<BLOCK, true><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
                                                             im->n_irows, S, ldb, (const char*)spu, (char*)V,
                                                             (char*)I, iters, status, diff, tol, maxiter, g_fbs_prefetch,
-                                                            im->d_unfed, im->n_unfed, gam, warm, wpu);
+                                                            im->d_unfed, im->n_unfed, gam, warm, wpu, nullptr, 0);
     } else if ((g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) && (maxiter >= 1 || !im->jit_kernel)) {
         if (!im->jit_kernel)
             return fail(GP_EINVAL, "gp_fbs_solve_batch: fbs_kernel = 5 needs a successful gp_fbs_specialise");
@@ -1693,10 +1742,13 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
         else GP_DFS(64);
 #undef GP_DFS
     } else {
-        fbs_solve_kernel<BLOCK, false><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
-                                                             im->n_irows, S, ldb, (const char*)spu, (char*)V,
+        const bool share = g_fbs_share_rows && im->n_alias > 0;
+        fbs_solve_kernel<BLOCK, false><<<gx, BLOCK, 0, st>>>(share ? im->d_steps_a : im->d_steps,
+                                                             share ? im->d_child_a : im->d_child, im->k, im->n_steps,
+                                                             im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V,
                                                              (char*)I, iters, status, diff, tol, maxiter, g_fbs_prefetch,
-                                                             im->d_unfed, im->n_unfed, nullptr, 0, nullptr);
+                                                             im->d_unfed, im->n_unfed, nullptr, 0, nullptr,
+                                                             share ? im->d_alias : nullptr, share ? im->n_alias : 0);
     }
     count_launch();
     GP_CUDA(cudaGetLastError());

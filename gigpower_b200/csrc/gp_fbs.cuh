@@ -50,6 +50,13 @@ struct FbsImpl {
     int n_grows = 0;              // regulated (step, phase) pairs = rows of a per-scenario gamma array
     FbsStep* d_steps = nullptr;
     int4* d_child = nullptr;  // [n_child] {I rows of the child edge, 0}
+    // the streaming kernel's own copy of the two tables with shared I rows (see gp_fbs_create): an I row
+    // that only repeats a child's current reads that child's row and is not stored during the sweeps, a
+    // row that stays zero is dropped; d_alias lists {row, source row or -1} for the one copy-out at the end
+    FbsStep* d_steps_a = nullptr;
+    int4* d_child_a = nullptr;
+    int2* d_alias = nullptr;
+    int n_alias = 0;
     int* d_lines = nullptr;   // [n_lines][9] irow, tx vrow, rx vrow
     int* d_vrow_srow = nullptr;   // [n_vrows] spu row of each V row or -1
     double* d_vrow_cap = nullptr; // [n_vrows]

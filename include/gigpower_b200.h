@@ -113,6 +113,9 @@ int64_t gp_launch_count(void);
  * (Line / Transformer feeders only; automatic for small batches of mostly three-phase feeders).
  * "fbs_prefetch" / "nr3_prefetch": L2 prefetch distance in tree steps of the streaming FBS kernel
  * (default 0) and of the NR3 kernel (default -1 = automatic: 2 for batches up to 65,536).
+ * "fbs_share_rows": 1 (default) = in the streaming FBS kernel an I row that only repeats a child's current (a
+ *   bus-phase without load and capacitor fed by one child edge) or stays zero makes no HBM round trips during
+ *   the sweeps and is filled in once at the end; 0 = every row is stored and re-read each sweep.  Same results.
  * "host_chunks": number of pipeline chunks of gp_fbs_solve_batch_host (0 = automatic).
  * "host_read_ahead": 1 (default) = the one-launch host path uses its own build of the specialised kernel
  *   in which a warp issues the PCIe reads of its next tile before the stores of the tile it has solved
