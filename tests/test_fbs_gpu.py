@@ -211,14 +211,23 @@ def test_all_fbs_kernels_agree(feeder):
         for mode in KERNELS:
             _cabi.check(_cabi.gp_set_option(b'fbs_kernel', mode))
             res[mode] = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
+        # the streaming kernel with every I row travelling (no shared rows)
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 3))
+        _cabi.check(_cabi.gp_set_option(b'fbs_share_rows', 0))
+        plain = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
     finally:
         _cabi.gp_set_option(b'fbs_kernel', 0)
+        _cabi.gp_set_option(b'fbs_share_rows', 1)
     for mode in KERNELS:
         assert np.array_equal(res[mode].iterations, want['iterations']), KERNELS[mode]
         assert rel_err(res[mode].V, want['V']) <= TOL and rel_err(res[mode].I, want['I']) <= TOL, KERNELS[mode]
         assert rel_err(res[3].V, res[mode].V) <= 1e-12, KERNELS[mode]
     # the on-chip and the streaming kernel run the same arithmetic in the same order: bit-identical
-    assert np.array_equal(res[3].V, res[4].V) and np.array_equal(res[3].I, res[4].I)
+    # (with shared I rows the streaming kernel takes the generic body for steps that lose a row, which
+    # adds the load current and the children's currents in the other order: equal to rounding)
+    assert np.array_equal(plain.V, res[4].V) and np.array_equal(plain.I, res[4].I)
+    assert np.array_equal(plain.iterations, res[3].iterations) and np.array_equal(plain.status, res[3].status)
+    assert rel_err(res[3].V, plain.V) <= 1e-13 and rel_err(res[3].I, plain.I) <= 1e-13
 
 
 def test_onchip_kernel_full_batch_and_relaunch():
@@ -235,7 +244,12 @@ def test_onchip_kernel_full_batch_and_relaunch():
     assert _cabi.gp_fbs_active_kernel(s._feeder.handle) == 3      # nothing specialised yet: streaming
     try:
         _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 3))
+        shared = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
+        _cabi.check(_cabi.gp_set_option(b'fbs_share_rows', 0))         # bit-identity holds row for row
         ref = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
+        _cabi.check(_cabi.gp_set_option(b'fbs_share_rows', 1))
+        assert np.array_equal(shared.iterations, ref.iterations) and np.array_equal(shared.status, ref.status)
+        assert rel_err(shared.V, ref.V) <= 1e-13 and rel_err(shared.I, ref.I) <= 1e-13
         _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 4))
         for _ in range(3):
             r = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
@@ -261,6 +275,7 @@ def test_onchip_kernel_full_batch_and_relaunch():
             assert rel_err(r.V, ref.V[:S2]) <= 1e-13 and np.array_equal(r.iterations, ref.iterations[:S2])
     finally:
         _cabi.gp_set_option(b'fbs_kernel', 0)
+        _cabi.gp_set_option(b'fbs_share_rows', 1)
 
 
 def test_specialised_kernel_restarts_diverging_scenarios_exactly():
