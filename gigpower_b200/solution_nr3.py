@@ -219,6 +219,16 @@ class SolutionNR3(Solution):
         self.converged = True                      # unconditional in the reference (:631)
         self.map_XNR()
 
+    def change_KCL_matrices(self, der=0, capacitance=0, t=-1):
+        """Not provided (solution_nr3.py:517-590).  The reference rewrites its dense
+        H and b tensors in place with ONE scalar `der` / `capacitance` for every bus; this engine never builds
+        those tensors.  The same studies are explicit per-scenario inputs here: ``solve_batch(spu=...)`` or
+        ``solve_batch(load_mult=...)`` for loads and DER injections, ``circuit.set_kW`` / ``set_kvar`` for a
+        single snapshot."""
+        raise NotImplementedError(
+            'change_KCL_matrices rewrites the dense NR3 tensors of the reference, which this engine does not build; '
+            'pass per-scenario loads / DER injections to solve_batch(spu=... | load_mult=...) instead')
+
     def map_XNR(self):
         r = self._last
         self.V, self.I = r.V[0], r.I[0]

@@ -88,3 +88,12 @@ def test_params_and_result_shapes_match_the_reference(api, feeder, cls):
     assert [float(x) for x in p['zip_v']] == rec['params']['zip_v']
     for q, shape in rec['shapes'].items():
         assert list(np.asarray(getattr(s, q)).shape) == shape, q
+
+
+def test_out_of_scope_entry_points_fail_with_an_explanation():
+    """N10 change_KCL_matrices and SolutionDSS are outside the accelerated path: a caller gets a clear error."""
+    s = _cls('SolutionNR3')(feeder_path(ALL_FEEDERS[1]))
+    with pytest.raises(NotImplementedError, match='solve_batch'):
+        s.change_KCL_matrices(der=0.1)
+    with pytest.raises(ImportError, match='OpenDSS'):
+        from gigpower_b200.solution_dss import SolutionDSS  # noqa: F401
