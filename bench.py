@@ -407,6 +407,8 @@ def run_ours(args, wl):
     rows, mult = make_scenarios(sol, S, seed + 1000 * rank, spec, first=rank * S)
     _cabi.check(_cabi.gp_set_option(b'jit_i_global', args.jit_ig))
     _cabi.check(_cabi.gp_set_option(b'fbs_share_rows', args.share_rows))
+    if args.host_warps:
+        _cabi.check(_cabi.gp_set_option(b'host_warps', args.host_warps))
     _cabi.check(_cabi.gp_set_option(b'nr3_kernel', args.nr3_kernel))
     sol._dev()
     _cabi.check(_cabi.gp_set_option(b'fbs_kernel', args.fbs_kernel))
@@ -812,6 +814,8 @@ def main():
                          'specialised FBS kernel, copy-engine pushes otherwise) or by NCCL')
     ap.add_argument('--jit-ig', type=int, default=-1, choices=[-1, 0, 1],
                     help='I rows of the specialised FBS kernel in global memory: -1 automatic, 0 no, 1 yes')
+    ap.add_argument('--host-warps', type=int, default=0,
+                    help='warps per SM of the one-launch host path (e2e); 0 = the library default')
     ap.add_argument('--share-rows', type=int, default=1, choices=[0, 1],
                     help='streaming FBS kernel: 1 = I rows that repeat a child\'s current or stay zero make no HBM round '
                          'trips (default), 0 = every row travels')

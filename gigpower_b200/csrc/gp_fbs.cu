@@ -31,6 +31,12 @@ int nr3_gamma_rows(GpFeeder* f);   // gp_nr3.cu
 static int g_jit_i_global = -1;    // gp_set_option("jit_i_global", -1|0|1): I rows of the specialised kernel in global memory
 static int g_host_read_ahead = 1;  // gp_set_option("host_read_ahead", 0|1): read-ahead build of the one-launch host path
 static int g_host_zero_copy = 1;   // gp_set_option("host_zero_copy", 0|1): one-launch host path of the specialised kernel
+// gp_set_option("host_warps", n): warps per SM of the one-launch host path's kernel build.  The host path is
+// bound by PCIe, not by the solve: a wave of warps uploads before anything downloads, so MORE warps per SM
+// lengthen the part of a call in which only one PCIe direction is busy.  Measured on C2 (65,536 scenarios,
+// V returned / |V| + losses returned, solves/s): 7 warps 5.85e7 / -, 6 warps 6.01e7 / 8.98e7,
+// 4 warps 6.26e7 / 9.58e7, 3 warps 6.36e7 / 8.53e7.  Default 4; the device path uses every warp that fits.
+static int g_host_warps = 4;
 static int g_host_chunks = 0;  // gp_set_option("host_chunks", n): 0 = automatic
 // gp_set_option("fbs_kernel", v): 0 automatic (feeder-specialised on-chip kernel once built, else two-sweep), 1 fused
 // depth-first, 2 phase-parallel, 3 two-sweep streaming, 4 on-chip (error if the feeder does not fit),
@@ -1085,6 +1091,10 @@ extern "C" int gp_set_option(const char* name, int value) {
         g_host_read_ahead = value;
         return GP_OK;
     }
+    if (name && strcmp(name, "host_warps") == 0 && value >= 1 && value <= 8) {
+        g_host_warps = value;
+        return GP_OK;
+    }
     if (name && strcmp(name, "host_chunks") == 0 && value >= 0 && value <= 64) {
         g_host_chunks = value;
         return GP_OK;
@@ -1612,9 +1622,9 @@ static int fbs_check(GpFeeder* f, int64_t S, int64_t ld, const char* who) {
 static int fbs_jit_launch(FbsImpl* im, int64_t S, int64_t ld, const double* spu, double* V, double* I,
                           int32_t* iters, int32_t* status, double* diff, double tol, int32_t maxiter,
                           cudaStream_t st, double* Vmag, double* loss, void* stage, double* Iout,
-                          const PeerDst* peers = nullptr, void* kernel = nullptr) {
+                          const PeerDst* peers = nullptr, void* kernel = nullptr, int kernel_warps = 0) {
     const long long n_tiles = (S + 31) / 32;
-    const int nw = im->jit_warps;
+    const int nw = (kernel && kernel_warps > 0) ? kernel_warps : im->jit_warps;   // a build's own block size
     long long blocks = (n_tiles + nw - 1) / nw;
     if (blocks > im->n_sm) blocks = im->n_sm;
     const unsigned smem = (unsigned)nw * (unsigned)(im->n_vrows + (im->jit_ig ? 0 : im->n_islots)) * 512u;
@@ -1910,7 +1920,8 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
             // feeders with more than 32 load rows, or a failed build, keep the device-path kernel
             if (!im->jit_host_tried && im->n_srows <= 32 && g_host_read_ahead) {
                 im->jit_host_tried = true;
-                if (fbs_jit_build(f, im->jit_warps, im->jit_ig, true, &im->jit_module_host, &im->jit_kernel_host) != GP_OK)
+                im->jit_warps_host = im->jit_warps < g_host_warps ? im->jit_warps : g_host_warps;
+                if (fbs_jit_build(f, im->jit_warps_host, im->jit_ig, true, &im->jit_module_host, &im->jit_kernel_host) != GP_OK)
                     im->jit_module_host = im->jit_kernel_host = nullptr;
             }
             // I rows kept in global memory must stay on the device; the host copy is a second destination
@@ -1918,7 +1929,7 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
             rc = fbs_jit_launch(im, S, ld, (const double*)dp[0], (double*)dp[1], I_state, (int32_t*)dp[5],
                                 (int32_t*)dp[6], (double*)dp[7], tol, maxiter, im->streams[0], (double*)dp[3],
                                 (double*)dp[4], im->d_zc, im->jit_ig ? (double*)dp[2] : nullptr, nullptr,
-                                g_host_read_ahead ? im->jit_kernel_host : nullptr);
+                                g_host_read_ahead ? im->jit_kernel_host : nullptr, im->jit_warps_host);
             if (rc) return rc;
             count_launch();
             GP_CUDA(cudaStreamSynchronize(im->streams[0]));

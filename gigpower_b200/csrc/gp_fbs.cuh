@@ -82,6 +82,7 @@ struct FbsImpl {
     void* jit_kernel_host = nullptr;
     bool jit_host_tried = false;
     int jit_warps = 0;
+    int jit_warps_host = 0;       // warps per block of the host path's build (gp_set_option("host_warps"))
     bool jit_ig = false;          // the specialised kernel keeps the I rows in global memory (the I array)
     int n_islots = 0;             // shared-memory slots the specialised kernel needs for the I rows (fbs_jit_islots)
     int jit_plan_warps = 0;       // warps per block gp_fbs_specialise will use (0 = feeder does not fit)

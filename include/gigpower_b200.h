@@ -116,6 +116,9 @@ int64_t gp_launch_count(void);
  * "fbs_share_rows": 1 (default) = in the streaming FBS kernel an I row that only repeats a child's current (a
  *   bus-phase without load and capacitor fed by one child edge) or stays zero makes no HBM round trips during
  *   the sweeps and is filled in once at the end; 0 = every row is stored and re-read each sweep.  Same results.
+ * "host_warps": warps per SM of the one-launch host path's kernel build (1..8, default 4; read when that build is
+ *   made, i.e. at the first gp_fbs_solve_batch_host call of a handle).  The host path is PCIe-bound and a smaller
+ *   wave of warps shortens the part of a call in which only one PCIe direction is busy.
  * "host_chunks": number of pipeline chunks of gp_fbs_solve_batch_host (0 = automatic).
  * "host_read_ahead": 1 (default) = the one-launch host path uses its own build of the specialised kernel
  *   in which a warp issues the PCIe reads of its next tile before the stores of the tile it has solved
