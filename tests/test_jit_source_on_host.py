@@ -129,3 +129,22 @@ def test_generated_sweep_run_on_the_host_matches_the_oracle(feeder, tmp_path):
     assert np.abs(Vr[t.vrow[bb, pp]].T - want['V'][:, bb, pp]).max() <= 1e-9
     ll, qq = np.nonzero(t.irow >= 0)
     assert np.abs(Ir[t.irow[ll, qq]].T - want['I'][:, ll, qq]).max() <= 1e-9
+
+
+@pytest.mark.parametrize('feeder,n_irows,n_slots', [('IEEE_13_Bus_allwye_noxfm_noreg', 35, 22), ('IEEE_13_Bus_allwye', 35, 22),
+                                                    ('IEEE_34_Bus_allwye_noxfm_noreg', 86, 55), ('IEEE_34_Bus_allwye', 86, 55),
+                                                    ('IEEE_37_Bus_allwye_noxfm_noreg', 114, 77), ('IEEE_37_Bus_allwye', 111, 77)])
+def test_shared_i_slots_per_feeder(feeder, n_irows, n_slots):
+    """fbs_jit_islots: one shared-memory slot per distinct I value (rows that repeat a child's current share
+    its slot, rows that stay zero take none); with I rows in global memory every row keeps its own."""
+    from gigpower_b200 import _cabi
+    from gigpower_b200.circuit import Circuit
+    from gigpower_b200.flatten import flatten_fbs
+    t = flatten_fbs(Circuit(load_model(feeder)))
+    d, keep = _cabi.make_fbs_desc(t)
+    for ig, want in ((0, n_slots), (1, n_irows)):
+        n = _cabi.gp_fbs_jit_source(C.byref(d), 2, ig, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        assert _cabi.gp_fbs_jit_source(C.byref(d), 2, ig, buf, n + 1) == n
+        defs = dict(ln.split()[1:3] for ln in buf.value.decode().splitlines() if ln.startswith('#define N'))
+        assert int(defs['NI']) == t.n_irows == n_irows and int(defs['NIP']) == want
