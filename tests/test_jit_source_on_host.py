@@ -46,7 +46,11 @@ int main(int argc, char** argv) {
     for (long s = 0; s < S; ++s) {
         std::vector<double2> sm((size_t)SROWS * 32 + 32, zero);
         double2* const Vs = sm.data();
+#if IG_MODE
+        IPTR const Ip = reinterpret_cast<char*>(I.data() + s);      // I rows in the caller's array, [row][S]
+#else
         IPTR const Ip = Vs + NV * 32;
+#endif
         const char* sp = reinterpret_cast<const char*>(spu.data() + s);
         for (int r = 0; r < NV; ++r) Vs[r * 32] = zero;
         for (int r = 0; r < NIP; ++r) IST(r, zero);
@@ -63,8 +67,10 @@ int main(int argc, char** argv) {
             ++it; converged = diff <= tol;
         }
         for (int r = 0; r < NV; ++r) V[(size_t)r * S + s] = Vs[r * 32];
+#if !IG_MODE
         char* Ig = reinterpret_cast<char*>(I.data() + s);
         GP_I_ROWS_OUT(Ig)
+#endif
         its[s] = it;
     }
     f = fopen(argv[5], "wb"); if (!f) return 4;
@@ -87,8 +93,9 @@ def host_program(src: str) -> str:
     return SHIMS + '\n'.join(lines) + '\n' + MAIN
 
 
+@pytest.mark.parametrize('ig', [0, 1])
 @pytest.mark.parametrize('feeder', ALL_FEEDERS)
-def test_generated_sweep_run_on_the_host_matches_the_oracle(feeder, tmp_path):
+def test_generated_sweep_run_on_the_host_matches_the_oracle(feeder, ig, tmp_path):
     from gigpower_b200 import _cabi
     from gigpower_b200.circuit import Circuit
     from gigpower_b200.flatten import flatten_fbs
@@ -96,12 +103,12 @@ def test_generated_sweep_run_on_the_host_matches_the_oracle(feeder, tmp_path):
     model = load_model(feeder)
     t = flatten_fbs(Circuit(model))
     d, keep = _cabi.make_fbs_desc(t)
-    n = _cabi.gp_fbs_jit_source(C.byref(d), 2, 0, None, 0)
+    n = _cabi.gp_fbs_jit_source(C.byref(d), 2, ig, None, 0)      # ig = 1: I rows in global memory
     buf = C.create_string_buffer(n + 1)
-    assert _cabi.gp_fbs_jit_source(C.byref(d), 2, 0, buf, n + 1) == n
+    assert _cabi.gp_fbs_jit_source(C.byref(d), 2, ig, buf, n + 1) == n
     src = buf.value.decode()
     nip = int([ln for ln in src.splitlines() if ln.startswith('#define NIP ')][0].split()[-1])
-    assert 0 < nip <= t.n_irows
+    assert 0 < nip <= t.n_irows and (nip == t.n_irows if ig else True)
     cpp, exe = tmp_path / 'sweep.cpp', tmp_path / 'sweep'
     cpp.write_text(host_program(src))
     subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-w', '-o', str(exe), str(cpp)], check=True)
