@@ -1,25 +1,40 @@
 #!/usr/bin/env python
 """Benchmark of the batched power-flow hot path (BASELINE.json metric:
-power-flow solves/sec).
+power-flow solves/sec, FBS & NR3, IEEE-123, at 1/2/4/8 B200).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--workload c2|c3|c4fbs|c5] [--solver fbs|nr3]
+                  [--workload c4|c2|c3|c4nr3|c5|...] [--sub c2,c3,c4nr3,c5|none]
 
 A "step" is one pass of the hot path over one batch of synthetic scenarios:
 flat start -> per-scenario convergence -> |V| and losses (-> all-gather of both
-for N > 1, on a side stream so that it overlaps the next step's solve).  Steps
-rotate over enough buffer sets that nothing is found in L2 from the last use.  At N=1 the default
-workload is BASELINE config C2 (IEEE 13-bus FBS, 65,536 random load-multiplier
-scenarios).  One process per GPU under torchrun; scenarios are sharded with no
-data-path collective, the only exchange is the final all-gather of |V| and
-losses: stores from the solve kernel's epilogue (or copy-engine pushes) into every rank's
-peer-mapped buffer over NVLink, or NCCL with --gather nccl.  Prints ONE JSON line on rank 0.
+for N > 1, overlapping the next step's solve).  Steps rotate over enough buffer
+sets that nothing is found in L2 from the last use.
+
+The headline line is BASELINE config C4 at every N: IEEE 123-bus FBS, the
+8,760 h x 128 DER scenario set, 140,160 scenarios per GPU (weak scaling; 8 GPUs
+hold the whole set).  The K timed steps are repeated until the timed region
+lasts >= 0.6 s, so the value is sustained and the clock record has hundreds of
+samples.  The other BASELINE configs (C2 13-bus FBS, C3 37-bus NR3, C4 123-bus
+NR3, C5 2,541-bus FBS) run after it, each with its own timed loop, and are
+reported in the same JSON line under "sub_results".
+
+One process per GPU under torchrun; scenarios are sharded with no data-path
+collective, the only exchange is the final all-gather of |V| and losses: stores
+from the solve kernel's epilogue (or copy-engine pushes) into every rank's
+peer-mapped buffer over NVLink, or NCCL with --gather nccl.  Prints ONE JSON
+line on rank 0.
+
+--impl reference: the reference's own CPU implementation on all host cores: the
+UNMODIFIED gigpower package from baseline/_ref (copied there by
+__graft_entry__.build()) behind the opendssdirect stand-in when it is present,
+else the oracle port; the port's figure is reported next to it either way.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes
 import json
+import math
 import os
 import subprocess
 import sys
@@ -31,8 +46,10 @@ import numpy as np
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-FEEDER_DIR = os.path.join(REPO, 'tests', 'golden', 'feeders')
-AUTHORED_DIR = os.path.join(REPO, 'gigpower_b200', 'feeders')
+FEEDER_DIR = os.path.join(REPO, 'gigpower_b200', 'feeders')
+GOLDEN_FEEDER_DIR = os.path.join(REPO, 'tests', 'golden', 'feeders')
+REF_DIR = os.path.join(REPO, 'baseline', '_ref')
+STANDIN_DIR = os.path.join(REPO, 'oracle', 'standin')
 WORKLOADS = {
     # name: (feeder file, solver, scenarios per GPU, seed, multiplier range, description)
     'c2': ('IEEE_13_Bus_allwye_noxfm_noreg.json', 'fbs', 65536, 13, (0.5, 1.5),
@@ -57,9 +74,15 @@ WORKLOADS = {
     'fbs34': ('IEEE_34_Bus_allwye_noxfm_noreg.json', 'fbs', 65536, 34, (0.5, 1.3),
               'IEEE 34-bus FBS, 65,536 scenarios'),
 }
-
+DEFAULT_WORKLOAD = 'c4'
+DEFAULT_SUBS = ('c2', 'c3', 'c4nr3', 'c5')
+MIN_TIMED_SECONDS = 0.6
 
 _JSON_FD = None
+
+
+def log(*a):
+    print('[bench]', *a, file=sys.stderr, flush=True)
 
 
 def protect_stdout():
@@ -86,8 +109,8 @@ def peaks():
     p = os.path.join(REPO, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f), 'measured'
-    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
+            return json.load(f), 'measured (MEASURED_PEAKS.json)'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback (B200_PROFILING.md)'
 
 
 def ncu_traffic(workload, kernel):
@@ -118,8 +141,7 @@ def fbs_flops_per_iteration(t):
 
 class NvmlSampler:
     """SM clock and clock-event (throttle) reasons DURING the timed region, read through NVML from a
-    thread every millisecond: the timed region of the default workload lasts tens of milliseconds,
-    which `nvidia-smi -lms 100` (ClockSampler below, the fallback) samples once at best."""
+    thread every millisecond."""
 
     def __init__(self, gpu_index):
         import pynvml
@@ -218,7 +240,7 @@ class ClockSampler:
 
 def feeder_file(name):
     p = os.path.join(FEEDER_DIR, name)
-    return p if os.path.exists(p) else os.path.join(AUTHORED_DIR, name)
+    return p if os.path.exists(p) else os.path.join(GOLDEN_FEEDER_DIR, name)
 
 
 def make_multipliers(n_loads, S, seed, spec, first=0):
@@ -229,36 +251,51 @@ def make_multipliers(n_loads, S, seed, spec, first=0):
     return rng.uniform(spec[0], spec[1], size=(S, n_loads))
 
 
-def make_der_rows(W0, S, first):
-    """scenario index = d * 8760 + h.  Hour multiplier m_h (seed 123),
-    PV at a random 10-40 % of the loaded bus-phases per DER scenario d (seed 1230 + d),
-    penetration pen_d ~ U(0, 0.8), net spu = m_h * S_load - pen_d * pv(h) * P_load."""
+def der_tables(nrow):
+    """hour multiplier m_h (seed 123), pv(h), and per DER scenario d (seed 1230 + d) the
+    bus-phases that carry PV (a random 10-40 % of the loaded ones) and the penetration pen_d ~ U(0, 0.8)."""
     H, D = 8760, 128
     h_all = np.arange(H)
     rng = np.random.Generator(np.random.PCG64(123))
     m_h = np.clip(0.6 + 0.25 * np.sin(2 * np.pi * ((h_all % 24) - 9) / 24) + 0.1 * np.sin(2 * np.pi * h_all / H)
                   + rng.normal(0, 0.02, H), 0.3, 1.2)
     pv_h = np.maximum(0.0, np.sin(np.pi * ((h_all % 24) - 6) / 12))
-    idx = (first + np.arange(S)) % (H * D)
-    d, h = idx // H, idx % H
-    nrow = W0.shape[0]
-    mask = np.zeros((D, nrow))
-    pen = np.zeros(D)
-    for dd in np.unique(d):
-        r = np.random.Generator(np.random.PCG64(1230 + int(dd)))
+    mask, pen = np.zeros((D, nrow)), np.zeros(D)
+    for dd in range(D):
+        r = np.random.Generator(np.random.PCG64(1230 + dd))
         frac = r.uniform(0.1, 0.4)
         mask[dd, r.permutation(nrow)[:max(1, int(round(frac * nrow)))]] = 1.0
         pen[dd] = r.uniform(0.0, 0.8)
+    return m_h, pv_h, mask, pen
+
+
+def make_der_rows(W0, S, first):
+    """scenario index = d * 8760 + h; net spu = m_h * S_load - pen_d * pv(h) * P_load."""
+    H, D = 8760, 128
+    m_h, pv_h, mask, pen = der_tables(W0.shape[0])
+    idx = (first + np.arange(S)) % (H * D)
+    d, h = idx // H, idx % H
     rows = W0[:, None] * m_h[h][None, :] - (W0.real[:, None] * mask[d].T) * (pen[d] * pv_h[h])[None, :]
     return np.ascontiguousarray(rows)
 
 
-def make_scenarios(sol, S, seed, spec, first=0):
-    """Synthetic scenario batch -> packed spu rows [n_srows, S] (+ multipliers when they exist)."""
+def make_scenarios(sol, S, seed, spec, first=0, device=None):
+    """Synthetic scenario batch -> packed spu rows [n_srows, S] (+ multipliers when they exist).
+    With `device` (a torch CUDA device) a large multiplier batch is expanded on the GPU (W @ mult.T is a
+    dense product of some 10^11 operations for the 2,541-bus feeder: input synthesis, not the path) and
+    the rows are returned as a CUDA tensor."""
     W = sol.load_weights()
     if spec == 'der':
         return make_der_rows(W.sum(axis=1), S, first), None
     mult = make_multipliers(sol.circuit.loads.num_elements, S, seed, spec)
+    if device is not None and W.shape[0] * W.shape[1] * S > 4e9:
+        import torch
+        m = torch.from_numpy(mult).to(device)
+        re = torch.from_numpy(np.ascontiguousarray(W.real)).to(device) @ m.T
+        im = torch.from_numpy(np.ascontiguousarray(W.imag)).to(device) @ m.T
+        rows = torch.complex(re, im).contiguous()
+        del m, re, im
+        return rows, None
     return np.ascontiguousarray(W @ mult.T), mult
 
 
@@ -271,8 +308,24 @@ def make_probe_inputs(workload, S=0):
     return sol, rows
 
 
+class HostFeeder:
+    """Host-only view of a feeder (parse + flatten): what the CPU arms need to synthesise the workload's
+    scenario rows.  Imports neither the CUDA library nor torch."""
+
+    def __init__(self, path, solver='fbs'):
+        from gigpower_b200.circuit import Circuit
+        from gigpower_b200.dss_reader import read_dss
+        from gigpower_b200 import flatten
+        self.circuit = Circuit(read_dss(path))
+        self.tables = flatten.flatten_fbs(self.circuit) if solver == 'fbs' else flatten.flatten_nr3(self.circuit)
+        self._lw = flatten.load_weights
+
+    def load_weights(self):
+        return self._lw(self.circuit, self.tables.srow, self.tables.n_srows)
+
+
 # --------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port on the host cores
+# CPU arms: (1) the oracle port, (2) the unmodified reference from baseline/_ref
 # --------------------------------------------------------------------------
 def _cpu_worker(args):
     feeder, solver, rows = args
@@ -293,6 +346,61 @@ def _cpu_worker(args):
     t0 = time.perf_counter()
     r = o.solve(spu)
     return time.perf_counter() - t0, int(r['iterations'].sum())
+
+
+_REF = {}
+
+
+def reference_available():
+    return os.path.exists(os.path.join(REF_DIR, 'gigpower', 'solution_fbs.py'))
+
+
+def _ref_init(feeder, solver):
+    """Pool initialiser: one UNMODIFIED reference Solution object per worker,
+    imported from baseline/_ref behind the opendssdirect stand-in."""
+    for var in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):
+        os.environ[var] = '1'
+    for p in (REF_DIR, STANDIN_DIR):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import warnings
+    warnings.filterwarnings('ignore')
+    if solver == 'fbs':
+        from gigpower.solution_fbs import SolutionFBS as Ref
+    else:
+        from gigpower.solution_nr3 import SolutionNR3 as Ref
+    s = Ref(feeder_file(feeder))
+    _REF['s'], _REF['solver'] = s, solver
+    _REF['base'] = [(n, s.circuit.loads.get_element(n).kW, s.circuit.loads.get_element(n).kvar)
+                    for n in s.circuit.loads.all_names()]
+
+
+def _ref_worker(args):
+    """K scenarios through the reference's own solve() (solution_fbs.py:76-136 / solution_nr3.py:592-632),
+    state reset between scenarios as BASELINE.md section 3 describes.  FBS: spu_k [K, nb, 3] complex, the
+    scenario's Solution.spu; NR3: mult_k [K, n_loads], set through the reference's own set_kW / set_kvar."""
+    spu_k, mult_k = args
+    s, solver = _REF['s'], _REF['solver']
+    t0 = time.perf_counter()
+    its = 0
+    if solver == 'fbs':
+        for spu in spu_k:
+            s.V[:] = 0
+            s.I[:] = 0
+            s.iterations = 0
+            s.Vtest = np.zeros(3, dtype=complex)
+            s.spu = spu.copy()
+            s.solve()
+            its += int(s.iterations)
+    else:
+        for m in mult_k:
+            for (n, kw, kvar), f in zip(_REF['base'], m):
+                s.circuit.set_kW(n, kw * f)
+                s.circuit.set_kvar(n, kvar * f)
+            s._init_KCL_matrices()
+            s._init_XNR()
+            s.solve()
+    return time.perf_counter() - t0, its
 
 
 class CpuPool:
@@ -323,8 +431,48 @@ class CpuPool:
         self.pool.join()
 
 
+class RefPool:
+    """Persistent process pool: one unmodified reference Solution per core (baseline/_ref)."""
+
+    def __init__(self, feeder, solver, srow, nb, cores=None):
+        import multiprocessing as mp
+        self.cores = cores or (os.cpu_count() or 1)
+        self.srow, self.nb = np.asarray(srow), nb
+        t0 = time.perf_counter()
+        self.pool = mp.get_context('spawn').Pool(self.cores, initializer=_ref_init, initargs=(feeder, solver))
+        self.pool.map(_ref_ready, range(self.cores))
+        self.setup_s = time.perf_counter() - t0
+
+    def step(self, rows, k_per_proc, mult=None):
+        """Every core solves k_per_proc scenarios: columns of the packed spu rows (FBS) or rows of the
+        per-load multipliers (NR3, whose loads enter through the circuit's setters)."""
+        S = rows.shape[1]
+        b, p = np.nonzero(self.srow >= 0)
+        jobs = []
+        for i in range(self.cores):
+            lo = (i * k_per_proc) % max(S - k_per_proc + 1, 1)
+            if mult is not None:
+                jobs.append((None, np.ascontiguousarray(mult[lo:lo + k_per_proc])))
+                continue
+            piece = rows[:, lo:lo + k_per_proc]
+            spu = np.zeros((piece.shape[1], self.nb, 3), dtype=complex)
+            spu[:, b, p] = piece[self.srow[b, p]].T
+            jobs.append((spu, None))
+        t0 = time.perf_counter()
+        out = self.pool.map(_ref_worker, jobs)
+        return sum(len(j[0] if j[0] is not None else j[1]) for j in jobs), time.perf_counter() - t0, sum(o[1] for o in out)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def _ref_ready(_):
+    return 's' in _REF
+
+
 def cpu_sample_size(solver, nb):
-    """Scenarios per core per step, sized so that a step of the port takes ~0.2-10 s.  NR3 up to
+    """Scenarios per core per step of the PORT, sized so that a step takes ~0.2-10 s.  NR3 up to
     45 buses runs the literal dense restatement of the reference (H tensors of 0.4 GB and ~5 s per
     solve at 37 buses, like the reference itself): one scenario per core per step."""
     if solver == 'fbs':
@@ -332,79 +480,140 @@ def cpu_sample_size(solver, nb):
     return 1 if nb <= 45 else max(2, min(64, 126 * 64 // nb))
 
 
+def ref_sample_size(solver, nb):
+    """Scenarios per core per step of the UNMODIFIED reference (FBS ~0.8 ms per bus per solve)."""
+    if solver == 'fbs':
+        return max(2, min(64, 1000 // nb))
+    return 1
+
+
+def time_port(feeder, solver, rows, nb, seconds, max_calls=200, warm=True):
+    pool = CpuPool()
+    n_per = cpu_sample_size(solver, nb)
+    if warm and not (solver == 'nr3' and n_per == 1):
+        pool.step(feeder, solver, rows, max(n_per // 8, 1))      # warm the workers
+    n, wall, reps = 0, 0.0, 0
+    while wall < seconds and reps < max_calls:
+        dn, dw = pool.step(feeder, solver, rows, n_per)
+        n, wall, reps = n + dn, wall + dw, reps + 1
+    pool.close()
+    return {'value': n / wall, 'unit': 'solves/s', 'cores': pool.cores, 'kind': 'port',
+            'sample': f'{n} scenarios of the workload ({n_per} per core per call, {reps} calls, {wall:.1f} s), '
+                      f'oracle/gp_oracle.py batched NumPy port on a process pool'}
+
+
+def time_reference_python(feeder, solver, rows, host, seconds, max_calls=50, mult=None):
+    """The unmodified reference's own solve() on all host cores; None when baseline/_ref is absent or the
+    workload is one the reference cannot hold (123-bus NR3: 15 GB of dense H per process)."""
+    nb = host.circuit.buses.num_elements
+    if not reference_available() or (solver == 'nr3' and (nb > 45 or mult is None)):
+        return None
+    pool = RefPool(feeder, solver, host.tables.srow, nb)
+    k = ref_sample_size(solver, nb)
+    mm = mult if solver == 'nr3' else None
+    pool.step(rows, 1, mm)                                       # warm-up: one solve per core
+    n, wall, reps, its = 0, 0.0, 0, 0
+    while wall < seconds and reps < max_calls:
+        dn, dw, di = pool.step(rows, k, mm)
+        n, wall, reps, its = n + dn, wall + dw, reps + 1, its + di
+    pool.close()
+    return {'value': n / wall, 'unit': 'solves/s', 'cores': pool.cores, 'kind': 'reference', 'K': k,
+            'mean_iterations': its / n if (n and solver == 'fbs') else None,
+            'sample': f'{n} scenarios of the workload ({k} per core per call, {reps} calls, {wall:.1f} s) through the '
+                      f'UNMODIFIED gigpower {"SolutionFBS" if solver == "fbs" else "SolutionNR3"}.solve() '
+                      f'(baseline/_ref behind oracle/standin/opendssdirect), one object per core, state reset per scenario '
+                      f'(BASELINE.md section 3); pool + constructors {pool.setup_s:.1f} s, not timed'}
+
+
 def run_reference(args, wl):
     feeder, solver, S, seed, spec, desc = wl
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from gigpower_b200.solution_fbs import SolutionFBS
-    from gigpower_b200.dss_reader import read_dss
-    from gigpower_b200.circuit import Circuit
-    from gigpower_b200.flatten import flatten_fbs
-
-    class _Host:        # host-only view of the feeder: load weights without touching the GPU
-        def __init__(self, path):
-            self.circuit = Circuit(read_dss(path))
-            self.tables = flatten_fbs(self.circuit)
-        load_weights = SolutionFBS.load_weights
-    sol = _Host(feeder_file(feeder))
-    nb = sol.circuit.buses.num_elements
-    rows, mult = make_scenarios(sol, min(S, 16384), seed, spec)
-    pool = CpuPool()
-    cores = pool.cores
-    n_per = cpu_sample_size(solver, nb)
-    slow = solver == 'nr3' and n_per == 1           # dense NR3 restatement: seconds per solve
-    for _ in range(1 if slow else max(args.warmup, 1)):
-        pool.step(feeder, solver, rows, max(n_per // 8, 1))
-    t0 = time.perf_counter()
-    tot, done = 0, 0
-    for _ in range(args.steps):
-        n, _w = pool.step(feeder, solver, rows, n_per)
-        tot, done = tot + n, done + 1
-        if time.perf_counter() - t0 > (60.0 if slow else 150.0):      # keep the whole arm within a few minutes
-            break
-    wall = time.perf_counter() - t0
-    pool.close()
+    host = HostFeeder(feeder_file(feeder), solver)
+    nb = host.circuit.buses.num_elements
+    rows, mult = make_scenarios(host, min(S, 16384), seed, spec)
+    use_ref = reference_available() and not (solver == 'nr3' and (nb > 45 or mult is None))
+    mm = mult if solver == 'nr3' else None
+    warm = max(args.warmup, 1)
+    if use_ref:
+        pool = RefPool(feeder, solver, host.tables.srow, nb)
+        cores, k = pool.cores, ref_sample_size(solver, nb)
+        for _ in range(min(warm, 2)):
+            pool.step(rows, 1, mm)
+        t0 = time.perf_counter()
+        tot, done = 0, 0
+        for _ in range(args.steps):
+            n, _w, _i = pool.step(rows, k, mm)
+            tot, done = tot + n, done + 1
+            if time.perf_counter() - t0 > 120.0:        # keep the whole arm within a few minutes
+                break
+        wall = time.perf_counter() - t0
+        pool.close()
+        kind = 'reference'
+        sample = (f'{k} scenarios of the workload per core per step through the UNMODIFIED gigpower solve() '
+                  f'(baseline/_ref behind oracle/standin/opendssdirect), one object per core, state reset per scenario')
+        port = time_port(feeder, solver, rows, nb, 8.0)
+    else:
+        pool = CpuPool()
+        cores = pool.cores
+        n_per = cpu_sample_size(solver, nb)
+        slow = solver == 'nr3' and n_per == 1           # dense NR3 restatement: seconds per solve
+        for _ in range(1 if slow else warm):
+            pool.step(feeder, solver, rows, max(n_per // 8, 1))
+        t0 = time.perf_counter()
+        tot, done = 0, 0
+        for _ in range(args.steps):
+            n, _w = pool.step(feeder, solver, rows, n_per)
+            tot, done = tot + n, done + 1
+            if time.perf_counter() - t0 > (60.0 if slow else 150.0):
+                break
+        wall = time.perf_counter() - t0
+        pool.close()
+        kind = 'port'
+        sample = (f'{n_per} scenarios of the workload per core per step, oracle/gp_oracle.py (NumPy port of the '
+                  f'reference, batched), persistent process pool')
+        port = None
     value = tot / wall
     line = {
         'impl': 'reference', 'metric': 'power-flow solves/sec', 'value': value, 'unit': 'solves/s',
-        'n_gpus': args.gpus, 'steps': done, 'warmup': max(args.warmup, 1),
+        'n_gpus': args.gpus, 'steps': done, 'warmup': warm,
         'ms_per_step': 1e3 * wall / done, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': desc, 'solver': solver},
-        'cpu_baseline': {'value': value, 'unit': 'solves/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{n_per} scenarios of the workload per core per step, oracle/gp_oracle.py '
-                                   f'(NumPy port of the reference, batched), persistent process pool'},
+        'cpu_baseline': {'value': value, 'unit': 'solves/s', 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': 'solves/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+    if port is not None:
+        line['cpu_baseline']['port'] = port
     emit(line)
 
 
 # --------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------
-def run_ours(args, wl):
+class Ctx:
+    pass
+
+
+def run_workload(ctx, args, name, steps, main):
+    """One workload on this rank's GPU: K timed steps (repeated until the timed region lasts
+    MIN_TIMED_SECONDS for the main workload), roofline of the solve kernel, e2e through host buffers
+    (main workload only).  Returns the result dict on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
     from gigpower_b200 import _cabi
-    feeder, solver, S, seed, spec, desc = wl
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        # NCCL writes its version / debug lines to stdout by default; stdout carries the one JSON line
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=dev)
+    feeder, solver, S, seed, spec, desc = WORKLOADS[name]
+    world, rank, local, dev = ctx.world, ctx.rank, ctx.local, ctx.dev
+    t_setup = time.perf_counter()
     if solver == 'fbs':
         from gigpower_b200.solution_fbs import SolutionFBS
         sol = SolutionFBS(feeder_file(feeder), device=local)
     else:
         from gigpower_b200.solution_nr3 import SolutionNR3
         sol = SolutionNR3(feeder_file(feeder), device=local)
-    rows, mult = make_scenarios(sol, S, seed + 1000 * rank, spec, first=rank * S)
+    rows, mult = make_scenarios(sol, S, seed + 1000 * rank, spec, first=rank * S, device=dev)
     _cabi.check(_cabi.gp_set_option(b'jit_i_global', args.jit_ig))
     _cabi.check(_cabi.gp_set_option(b'fbs_share_rows', args.share_rows))
     if args.host_warps:
@@ -420,7 +629,8 @@ def run_ours(args, wl):
         sol.specialise()        # what solve_batch does by itself for a batch this size
     active = int(_cabi.gp_fbs_active_kernel(h)) if solver == 'fbs' else 0
     ld = S
-    spu_h = torch.from_numpy(rows).pin_memory()
+    on_device = hasattr(rows, 'data_ptr')
+    spu_src = rows if on_device else torch.from_numpy(rows).pin_memory()
     c128, f64, i32 = torch.complex128, torch.float64, torch.int32
     stream = torch.cuda.current_stream()
     side = torch.cuda.Stream(device=dev)          # the gather of step k overlaps the solve of step k+1
@@ -435,7 +645,7 @@ def run_ours(args, wl):
         step never finds its inputs or state in L2 from the previous use (total > 2.5 x L2)."""
 
         def __init__(self):
-            self.spu = spu_h.to(dev)
+            self.spu = spu_src.to(dev) if not on_device else (spu_src if not sets else spu_src.clone())
             self.Vmag = torch.empty((t.n_vrows, ld), dtype=f64, device=dev)
             self.loss = torch.empty(S, dtype=c128, device=dev)
             self.iters = torch.empty(S, dtype=i32, device=dev)
@@ -515,7 +725,8 @@ def run_ours(args, wl):
                 self.gathered.record(side)
 
     L2_BYTES = 126 << 20
-    sets = [BufSet()]
+    sets = []
+    sets.append(BufSet())
     n_sets = max(1, min(8, -(-int(2.5 * L2_BYTES) // sets[0].nbytes())))
     sets += [BufSet() for _ in range(n_sets - 1)]
     n_slots = max(2, n_sets)
@@ -529,7 +740,7 @@ def run_ours(args, wl):
         except Exception as e:          # no CUDA IPC between the ranks (container policy): NCCL does the gather
             pg, ok = None, torch.zeros(1, device=dev)
             gather_note = f'peer-mapped gather unavailable ({e}); NCCL all-gather instead'
-            print(gather_note, file=sys.stderr)
+            log(gather_note)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)       # all ranks or none
         if float(ok.item()) == 0.0:
             if pg is not None:
@@ -562,21 +773,40 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 3)
+    for k in range(n_warm):
         step(k)
     barrier()
-    # ---- timed region: K steps back to back between two events; solve kernels timed individually ----
+    # one timed pass of the warm-up length sizes the number of repeats of the K steps
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record(stream)
+    for k in range(n_warm):
+        step(k)
+    stream.wait_stream(side)
+    w1.record(stream)
+    barrier()
+    est_ms = torch.tensor([w0.elapsed_time(w1) / n_warm], dtype=f64, device=dev)
+    if world > 1:
+        dist.all_reduce(est_ms, op=dist.ReduceOp.MAX)
+    repeats = 1
+    if main:
+        repeats = max(1, min(2000, int(math.ceil(MIN_TIMED_SECONDS * 1e3 / (float(est_ms.item()) * steps)))))
+    total_steps = steps * repeats
+    if rank == 0:
+        log(f'{name}: set-up {time.perf_counter() - t_setup:.1f} s, ~{float(est_ms.item()):.3f} ms/step, '
+            f'{steps} steps x {repeats} repeat(s), {n_sets} buffer set(s)')
+    # ---- timed region: K steps (x repeats) back to back between two events; solve kernels timed individually ----
     sampler = make_sampler(local)
     if rank == 0:
         sampler.start()
     launches0 = _cabi.gp_launch_count()
-    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(total_steps)]
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     mids = []
     barrier()
     t_wall0 = time.perf_counter()
     e_begin.record(stream)
-    for k in range(args.steps):
+    for k in range(total_steps):
         e0[k].record(stream)
         mids.append(step(k))
     stream.wait_stream(side)                      # the last gathers belong to the timed steps
@@ -584,121 +814,112 @@ def run_ours(args, wl):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
-    launches = _cabi.gp_launch_count() - launches0
+    launches = (_cabi.gp_launch_count() - launches0) // repeats
     if pg is not None:
         # every rank's last step sits in block r of the slot on this rank
-        slot = (args.steps - 1) % n_slots
-        mine = sets[(args.steps - 1) % n_sets]
+        slot = (total_steps - 1) % n_slots
+        mine = sets[(total_steps - 1) % n_sets]
         got = pg.vmag_all(slot)
         assert torch.equal(got[rank], mine.Vmag), 'gathered |V| differs from the local result'
         assert torch.equal(pg.loss_all(slot)[rank], mine.loss), 'gathered losses differ from the local result'
         other = got[(rank + 1) % world]
         assert bool(torch.isfinite(other).all()) and float(other.min()) > 0.3, 'peer block not filled'
     ms_total = e_begin.elapsed_time(e_end)
-    ms_solve = np.array([e0[k].elapsed_time(mids[k]) for k in range(args.steps)])
+    ms_solve = np.array([e0[k].elapsed_time(mids[k]) for k in range(total_steps)])
     tot_ms = torch.tensor([ms_total], dtype=f64, device=dev)
     if world > 1:
         dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(tot_ms.item()) / args.steps
-    ms_steps = np.full(args.steps, ms_per_step)
+    ms_per_step = float(tot_ms.item()) / total_steps
     value = world * S / (ms_per_step * 1e-3)
-    last = sets[(args.steps - 1) % n_sets]
+    last = sets[(total_steps - 1) % n_sets]
     iters, status = last.iters, last.status
     spu_d = last.spu
-    if solver == 'nr3':
-        X = last.X
-
-        def solve_kernel():
-            last.solve()
     its = iters.cpu().numpy().astype(np.int64)
     assert (status.cpu().numpy() == 0).all(), 'bench scenarios must all converge'
 
     # ---- end to end: host buffers in, results out, copies inside the timed region -----------
-    e2e_steps = max(3, min(args.steps, 10))
-    e2e_extra = {}
-    if args.workload == 'c4ts':
-        # the study driver: hour / DER tables up (kilobytes), 36 bytes of summaries per scenario down
-        from gigpower_b200.study import DerStudy
-        H, D = 8760, 128
-        h_all = np.arange(H)
-        rng = np.random.Generator(np.random.PCG64(123))
-        m_h = np.clip(0.6 + 0.25 * np.sin(2 * np.pi * ((h_all % 24) - 9) / 24) + 0.1 * np.sin(2 * np.pi * h_all / H)
-                      + rng.normal(0, 0.02, H), 0.3, 1.2)
-        pv_h = np.maximum(0.0, np.sin(np.pi * ((h_all % 24) - 6) / 12))
-        mask, pen = np.zeros((D, t.n_srows)), np.zeros(D)
-        for dd in range(D):
-            r = np.random.Generator(np.random.PCG64(1230 + dd))
-            frac = r.uniform(0.1, 0.4)
-            mask[dd, r.permutation(t.n_srows)[:max(1, int(round(frac * t.n_srows)))]] = 1.0
-            pen[dd] = r.uniform(0.0, 0.8)
-        for b in sets:      # the study allocates its own chunk buffers
-            del b.V, b.I
-        torch.cuda.empty_cache()
+    e2e = None
+    if main or args.sub_e2e:
+        e2e_steps = max(3, min(steps, 10))
+        e2e_extra = {}
+        spu_h = spu_src if not on_device else spu_src.cpu().pin_memory()
+        h2d_override = None
+        if name == 'c4ts':
+            # the study driver: hour / DER tables up (kilobytes), 36 bytes of summaries per scenario down
+            from gigpower_b200.study import DerStudy
+            m_h, pv_h, mask, pen = der_tables(t.n_srows)
+            for b in sets:      # the study allocates its own chunk buffers
+                del b.V, b.I
+            torch.cuda.empty_cache()
+            study = DerStudy(sol, m_h, pv_h, mask, pen)
 
-        study = DerStudy(sol, m_h, pv_h, mask, pen)
-
-        def e2e_step():
-            study.upload(m_h, pv_h, mask, pen)                   # the step's inputs: the tables
-            return study.run(first=rank * S, count=S, chunk=S)
-        out = e2e_step()
-        assert np.array_equal(out['iterations'], its), 'study and explicit batch disagree'
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_api = ('DerStudy.run: gp_der_rows + gp_fbs_solve_post_batch + gp_vmag_summary per chunk '
-                   '(one chunk here); returns iterations, status, loss, min|V|, max|V|, violations')
-        h2d_override = int((m_h.size + pv_h.size + mask.size + pen.size) * 8 + t.n_srows * 16)
-        d2h = int(S * (4 + 4 + 16 + 8 + 8 + 4))
-    elif solver == 'fbs':
-        V_h = torch.empty((t.n_vrows, ld), dtype=c128).pin_memory()
-        loss_h = torch.empty(S, dtype=c128).pin_memory()
-        sol.solve_batch_host(spu_h, V_h, None, None, loss_h)      # warm-up (allocates staging)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            it_h, st_h, df_h = sol.solve_batch_host(spu_h, V_h, None, None, loss_h)
-        torch.cuda.synchronize()
-        e2e_api = 'gp_fbs_solve_batch_host (pinned host buffers; returns V, losses, iterations, status)'
-        d2h = int(V_h.numel() * 16 + loss_h.numel() * 16 + S * (4 + 4 + 8))
-        t_full = (time.perf_counter() - t0) / e2e_steps
-        # the same call returning what the sharded path gathers (|V| and losses) instead of complex V
-        Vm_h = torch.empty((t.n_vrows, ld), dtype=f64).pin_memory()
-        sol.solve_batch_host(spu_h, None, None, Vm_h, loss_h)
-        barrier()
-        t1 = time.perf_counter()
-        for _ in range(e2e_steps):
+            def e2e_step():
+                study.upload(m_h, pv_h, mask, pen)                   # the step's inputs: the tables
+                return study.run(first=rank * S, count=S, chunk=S)
+            out = e2e_step()
+            assert np.array_equal(out['iterations'], its), 'study and explicit batch disagree'
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            torch.cuda.synchronize()
+            e2e_api = ('DerStudy.run: gp_der_rows + gp_fbs_solve_post_batch + gp_vmag_summary per chunk '
+                       '(one chunk here); returns iterations, status, loss, min|V|, max|V|, violations')
+            h2d_override = int((m_h.size + pv_h.size + mask.size + pen.size) * 8 + t.n_srows * 16)
+            d2h = int(S * (4 + 4 + 16 + 8 + 8 + 4))
+        elif solver == 'fbs':
+            V_h = torch.empty((t.n_vrows, ld), dtype=c128).pin_memory()
+            loss_h = torch.empty(S, dtype=c128).pin_memory()
+            sol.solve_batch_host(spu_h, V_h, None, None, loss_h)      # warm-up (allocates staging)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                it_h, st_h, df_h = sol.solve_batch_host(spu_h, V_h, None, None, loss_h)
+            torch.cuda.synchronize()
+            assert np.array_equal(np.asarray(it_h), its), 'host path and device path disagree on iteration counts'
+            e2e_api = 'gp_fbs_solve_batch_host (pinned host buffers; returns V, losses, iterations, status)'
+            d2h = int(V_h.numel() * 16 + loss_h.numel() * 16 + S * (4 + 4 + 8))
+            t_full = (time.perf_counter() - t0) / e2e_steps
+            # the same call returning what the sharded path gathers (|V| and losses) instead of complex V
+            Vm_h = torch.empty((t.n_vrows, ld), dtype=f64).pin_memory()
             sol.solve_batch_host(spu_h, None, None, Vm_h, loss_h)
-        torch.cuda.synchronize()
-        e2e_extra = {'returning_vmag_and_losses_only': {
-            'seconds_per_step_this_rank': (time.perf_counter() - t1) / e2e_steps,
-            'value_this_rank': S / ((time.perf_counter() - t1) / e2e_steps), 'unit': 'solves/s per GPU',
-            'd2h_bytes_per_step': int(Vm_h.numel() * 8 + loss_h.numel() * 16 + S * (4 + 4 + 8))}}
-        t0 = time.perf_counter() - t_full * e2e_steps      # the headline e2e stays the call that returns V
-    else:
-        X_h = torch.empty((t.n_vrows + t.n_irows, ld), dtype=c128).pin_memory()
-        it_h = torch.empty(S, dtype=i32).pin_memory()
+            barrier()
+            t1 = time.perf_counter()
+            for _ in range(e2e_steps):
+                sol.solve_batch_host(spu_h, None, None, Vm_h, loss_h)
+            torch.cuda.synchronize()
+            e2e_extra = {'returning_vmag_and_losses_only': {
+                'seconds_per_step_this_rank': (time.perf_counter() - t1) / e2e_steps,
+                'value_this_rank': S / ((time.perf_counter() - t1) / e2e_steps), 'unit': 'solves/s per GPU',
+                'd2h_bytes_per_step': int(Vm_h.numel() * 8 + loss_h.numel() * 16 + S * (4 + 4 + 8))}}
+            t0 = time.perf_counter() - t_full * e2e_steps      # the headline e2e stays the call that returns V
+        else:
+            X_h = torch.empty((t.n_vrows + t.n_irows, ld), dtype=c128).pin_memory()
+            it_h = torch.empty(S, dtype=i32).pin_memory()
+            X = last.X
 
-        def e2e_step():
-            spu_d.copy_(spu_h, non_blocking=True)
-            solve_kernel()
-            X_h.copy_(X, non_blocking=True)
-            it_h.copy_(iters, non_blocking=True)
-            stream.synchronize()
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+            def e2e_step():
+                spu_d.copy_(spu_h, non_blocking=True)
+                last.solve()
+                X_h.copy_(X, non_blocking=True)
+                it_h.copy_(iters, non_blocking=True)
+                stream.synchronize()
             e2e_step()
-        e2e_api = 'pinned spu -> device, gp_nr3_solve_batch, X and iterations -> pinned host'
-        d2h = int(X_h.numel() * 16 + S * 4)
-    e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=f64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = world * S / float(e2e_t.item())
-    h2d = int(spu_h.numel() * 16) if args.workload != 'c4ts' else h2d_override
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            e2e_api = 'pinned spu -> device, gp_nr3_solve_batch, X and iterations -> pinned host'
+            d2h = int(X_h.numel() * 16 + S * 4)
+        e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=f64, device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        h2d = int(spu_h.numel() * 16) if h2d_override is None else h2d_override
+        e2e = {'value': world * S / float(e2e_t.item()), 'unit': 'solves/s', 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'api': e2e_api,
+               'pcie_gbs_per_rank': (h2d + d2h) / float(e2e_t.item()) / 1e9, **e2e_extra}
 
+    res = None
     if rank == 0:
         pk, pk_kind = peaks()
         solve_ms = float(np.mean(ms_solve))
@@ -708,17 +929,16 @@ def run_ours(args, wl):
         variant = {0: None, 1: 'fused-dfs', 2: 'phase-parallel', 3: 'two-sweep streaming (state in HBM)',
                    4: 'on-chip two-sweep (state in shared memory), table-driven',
                    5: 'on-chip two-sweep (state in shared memory), feeder-specialised (NVRTC)'}[active]
+        # per sweep read I, write V | read V, read spu, write I, write V; once: read spu, write V, I
+        stream_per_it = 16 * (2 * t.n_irows + 3 * t.n_vrows + t.n_srows)
+        stream_once = 16 * (t.n_srows + t.n_vrows + t.n_irows)
         if solver == 'fbs' and active in (4, 5):
-            # on-chip kernel: per iteration only the spu rows are read (L2-resident after the first
-            # sweep); V and I leave the SM once.  The kernel is bound by the FP64 pipe, so the
-            # headline roofline is FP64 (algorithmic flops of the sweeps);
-            # the HBM fraction of the same launch is reported next to it.
-            per_it, once = 16 * t.n_srows, 16 * (t.n_vrows + t.n_irows) + 16
+            # on-chip kernel: V and I cross the HBM interface once, the load rows once (they are re-read
+            # through L2 every sweep, which is not DRAM traffic)
+            per_it, once = 0, 16 * (t.n_srows + t.n_vrows + t.n_irows) + 8 * t.n_vrows + 16
             kname = kernel_names[active]
         elif solver == 'fbs':
-            # per sweep read I, write V | read V, read spu, write I, write V
-            per_it = 16 * (2 * t.n_irows + 3 * t.n_vrows + t.n_srows)
-            once = 16 * (t.n_srows + t.n_vrows + t.n_irows)
+            per_it, once = stream_per_it, stream_once
             kname = kernel_names[active]
         else:
             # per Newton iteration: X read+write, spu read, dV write+read, fronts (Y, a, r1) write+read
@@ -731,12 +951,12 @@ def run_ours(args, wl):
             kname = 'nr3_phase_kernel' if phase_lanes else 'nr3_solve_kernel'
         alg_bytes = n_it * per_it + S * once            # solve kernel, per launch
         achieved = alg_bytes / (solve_ms * 1e-3) / 1e9
-        traffic = ncu_traffic(args.workload, kname)
+        traffic = ncu_traffic(name, kname)
         roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': achieved,
                     'peak': pk['hbm_gbs'], 'peak_kind': pk_kind, 'unit': 'GB/s',
                     'frac': achieved / pk['hbm_gbs'], 'traffic': traffic,
                     'algorithmic_bytes_per_launch': alg_bytes, 'kernel_ms': solve_ms,
-                    'kernel_share_of_step': solve_ms / float(np.mean(ms_steps))}
+                    'kernel_share_of_step': solve_ms / ms_per_step}
         if solver == 'fbs' and active in (4, 5):
             tf = ctypes.c_double(0.0)
             _cabi.check(_cabi.gp_measure_fp64_peak(local, ctypes.byref(tf)))
@@ -746,15 +966,22 @@ def run_ours(args, wl):
                         'peak_kind': 'measured live (gp_measure_fp64_peak: DFMA chains, 2 flop each)',
                         'unit': 'TFLOP/s', 'frac': ach_tf / tf.value, 'traffic': traffic,
                         'algorithmic_flops_per_launch': flops, 'kernel_ms': solve_ms,
-                        'kernel_share_of_step': solve_ms / float(np.mean(ms_steps)),
+                        'kernel_share_of_step': solve_ms / ms_per_step,
                         'hbm': {'achieved': achieved, 'peak': pk['hbm_gbs'], 'peak_kind': pk_kind, 'unit': 'GB/s',
                                 'frac': achieved / pk['hbm_gbs'], 'algorithmic_bytes_per_launch': alg_bytes,
+                                'note': 'one-time bytes only (SURVEY 8(d): spu in, V, I, |V|, loss out); the state never '
+                                        'leaves the SM between sweeps',
                                 'streaming_formulation_equivalent_gbs':
-                                    (n_it * 16 * (2 * t.n_irows + 3 * t.n_vrows + t.n_srows)
-                                     + S * 16 * (t.n_srows + t.n_vrows + t.n_irows)) / (solve_ms * 1e-3) / 1e9}}
-        line = {
+                                    (n_it * stream_per_it + S * stream_once) / (solve_ms * 1e-3) / 1e9}}
+        if world > 1:
+            nv_bytes = (world - 1) * (t.n_vrows * 8 + 16) * S
+            roofline['nvlink'] = {'ingress_bytes_per_gpu_per_step': nv_bytes,
+                                  'achieved_gbs': nv_bytes / (ms_per_step * 1e-3) / 1e9, 'peak_gbs': 900.0,
+                                  'note': 'all-gather of |V| and losses; overlaps the next step\'s solve, so this is '
+                                          'bytes over the whole step time (a lower bound of the link rate)'}
+        res = {
             'metric': 'power-flow solves/sec', 'value': value, 'unit': 'solves/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
+            'steps': steps, 'repeats': repeats, 'warmup': n_warm, 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
             'config': {'workload': desc, 'solver': solver, 'scenarios_per_gpu': S,
@@ -763,9 +990,9 @@ def run_ours(args, wl):
                        'mean_iterations': float(its.mean()), 'max_iterations': int(its.max()),
                        'l2': f'no reuse across steps: {n_sets} rotating buffer set(s) of {sets[0].nbytes() >> 20} MiB '
                              f'(inputs + state + outputs) against a 126 MiB L2',
-                       'timing': 'CUDA events around the K back-to-back steps on the launch stream (gather of step k '
-                                 'on a side stream, overlapping the solve of step k+1), max over ranks; solve kernels '
-                                 'timed individually for the roofline',
+                       'timing': f'CUDA events around {repeats} x {steps} back-to-back steps on the launch stream '
+                                 f'(ms_per_step = total / {total_steps}; gather of step k on a side stream, overlapping '
+                                 f'the solve of step k+1), max over ranks; solve kernels timed individually for the roofline',
                        'parallelism': f'scenario-sharded x{world}, ' + (
                            'single GPU: no exchange' if world == 1 else
                            'all-gather of |V| and losses by NCCL on a side stream' if pg is None else
@@ -775,39 +1002,94 @@ def run_ours(args, wl):
                            'every rank\'s peer-mapped buffer)' if fused else
                            'all-gather of |V| and losses by copy-engine pushes into every rank\'s peer-mapped buffer '
                            'on a side stream')},
-            'e2e': {'value': e2e_value, 'unit': 'solves/s', 'h2d_bytes_per_step': h2d,
-                    'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
-                    'api': e2e_api, **e2e_extra},
             'gpu_launches': int(launches),
             'roofline': roofline,
             'clocks': clocks, 'wall_s_timed_region': t_wall,
         }
-        if world == 1 and not args.no_cpu:
-            pool = CpuPool()
-            n_per = cpu_sample_size(solver, sol.circuit.buses.num_elements)
-            if not (solver == 'nr3' and n_per == 1):
-                pool.step(feeder, solver, rows, max(n_per // 8, 1))      # warm the workers
-            n, wall, reps = 0, 0.0, 0
-            while wall < 10.0 and reps < 200:
-                dn, dw = pool.step(feeder, solver, rows, n_per)
-                n, wall, reps = n + dn, wall + dw, reps + 1
-            pool.close()
-            line['cpu_baseline'] = {
-                'value': n / wall, 'unit': 'solves/s', 'cores': pool.cores, 'kind': 'port',
-                'sample': f'{n} scenarios of the workload ({n_per} per core per call, {reps} calls, '
-                          f'{wall:.1f} s), oracle/gp_oracle.py batched NumPy port on a process pool'}
+        if gather_note:
+            res['config']['gather_note'] = gather_note
+        if e2e is not None:
+            res['e2e'] = e2e
+        if main and world == 1 and not args.no_cpu:
+            host_rows = rows if not on_device else rows[:, :16384].cpu().numpy()
+            nb = sol.circuit.buses.num_elements
+            res['cpu_baseline'] = time_port(feeder, solver, host_rows, nb, 10.0)
+            try:
+                ref = time_reference_python(feeder, solver, host_rows, sol, 10.0, mult=mult)
+            except Exception as e:          # the reference leg must never cost the line
+                ref = {'unavailable': f'{type(e).__name__}: {e}'}
+            res['cpu_baseline']['reference'] = ref if ref is not None else {
+                'unavailable': 'baseline/_ref not shipped (run __graft_entry__.build() where /root/reference exists)'
+                if not reference_available() else 'the reference holds 15 GB of dense H per process for this feeder'}
+    # release this workload's memory before the next one
+    if pg is not None:
+        pg.close()
+    del sets[:]
+    del sol
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    ctx = Ctx()
+    ctx.world = int(os.environ.get('WORLD_SIZE', '1'))
+    ctx.rank = int(os.environ.get('RANK', '0'))
+    ctx.local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(ctx.local)
+    ctx.dev = torch.device('cuda', ctx.local)
+    if ctx.world > 1:
+        # NCCL writes its version / debug lines to stdout by default; stdout carries the one JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        dist.init_process_group('nccl', device_id=ctx.dev)
+    line = run_workload(ctx, args, args.workload, args.steps, main=True)
+    subs = [] if args.sub in ('none', '') else [s for s in args.sub.split(',') if s and s != args.workload]
+    sub_results = {}
+    for name in subs:
+        if name not in WORKLOADS:
+            raise SystemExit(f'unknown sub-workload {name}')
+        try:
+            r = run_workload(ctx, args, name, max(3, min(args.steps, args.sub_steps)), main=False)
+        except Exception as e:      # a failing sub-workload is reported, not fatal to the headline line
+            if ctx.world > 1:
+                raise
+            r = {'error': f'{type(e).__name__}: {e}'}
+        if ctx.rank == 0:
+            if 'error' in r:
+                sub_results[name] = r
+            else:
+                rf = r['roofline']
+                sub_results[name] = {
+                    'workload': r['config']['workload'], 'value': r['value'], 'unit': r['unit'],
+                    'ms_per_step': r['ms_per_step'], 'steps': r['steps'], 'kernel': rf['kernel'],
+                    'kernel_ms': rf['kernel_ms'], 'bound': rf['bound'], 'frac': rf['frac'],
+                    'achieved': rf['achieved'], 'peak': rf['peak'], 'roofline_unit': rf['unit'],
+                    'traffic': rf['traffic'], 'hbm_frac': rf.get('hbm', rf)['frac'],
+                    'mean_iterations': r['config']['mean_iterations'], 'gpu_launches': r['gpu_launches'],
+                    'clocks': r['clocks'], 'scenarios_per_gpu': r['config']['scenarios_per_gpu'],
+                    **({'nvlink': rf['nvlink']} if 'nvlink' in rf else {}),
+                    **({'e2e': r['e2e']} if 'e2e' in r else {})}
+    if ctx.rank == 0:
+        if sub_results:
+            line['sub_results'] = sub_results
         emit(line)
-    if world > 1:
+    if ctx.world > 1:
         dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument('--sub', default=None,
+                    help='comma-separated workloads reported under sub_results after the headline one '
+                         f'(default {",".join(DEFAULT_SUBS)} with the default workload, none otherwise)')
+    ap.add_argument('--sub-steps', type=int, default=10, help='timed steps of each sub-workload')
+    ap.add_argument('--sub-e2e', action='store_true', help='also measure e2e for the sub-workloads')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--gather', default='peer', choices=['peer', 'dma', 'nccl'],
                     help='N > 1: the all-gather of |V| and losses through peer-mapped memory (fused into the '
@@ -827,12 +1109,13 @@ def main():
                          '1 = fused depth-first, 2 = phase-parallel lanes, 3 = two-sweep streaming, 4 = on-chip table-driven, '
                          '5 = on-chip feeder-specialised')
     args = ap.parse_args()
+    if args.sub is None:
+        args.sub = ','.join(DEFAULT_SUBS) if args.workload == DEFAULT_WORKLOAD else 'none'
     protect_stdout()
-    wl = WORKLOADS[args.workload]
     if args.impl == 'reference':
-        run_reference(args, wl)
+        run_reference(args, WORKLOADS[args.workload])
     else:
-        run_ours(args, wl)
+        run_ours(args)
 
 
 if __name__ == '__main__':

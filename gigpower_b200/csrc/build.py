@@ -9,7 +9,8 @@ OUT = os.path.join(PKG, 'libgigpower_b200.so')
 SOURCES = ['gp_fbs.cu', 'gp_fbs_jit.cu', 'gp_nr3.cu', 'gp_study.cu', 'gp_peer.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
-         '-Xcompiler', '-fPIC', '-shared', '--use_fast_math=false'.replace('--use_fast_math=false', '-Xptxas=-v')]
+         '-Xcompiler', '-fPIC', '-shared', '--fmad=true']
+VERBOSE_FLAGS = ['-Xptxas=-v']      # register / spill report, only when asked for
 
 
 def build(verbose=False, force=False):
@@ -19,7 +20,7 @@ def build(verbose=False, force=False):
     deps += [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith('.cuh')]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
-    cmd = [NVCC] + FLAGS + srcs + ['-o', OUT, '-lcudart', '-ldl']
+    cmd = [NVCC] + FLAGS + (VERBOSE_FLAGS if verbose else []) + srcs + ['-o', OUT, '-lcudart', '-ldl']
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(' '.join(cmd) + '\n' + res.stdout + res.stderr)

@@ -1172,8 +1172,12 @@ extern "C" int gp_measure_fp64_peak(int device, double* tflops) {
 // the source generator)
 static int fbs_tables_from_desc(const GpFbsDesc* d, std::vector<FbsStep>& steps, std::vector<int4>& child4,
                                 FbsConst& k, std::vector<int>& vrow_srow, std::vector<double>& vrow_cap) {
-    if (d->n_steps < 0 || d->n_vrows <= 0 || d->n_irows < 0 || d->n_srows < 0 || d->n_child < 0)
+    if (d->n_steps < 0 || d->n_vrows <= 0 || d->n_irows < 0 || d->n_srows < 0 || d->n_child < 0 || d->n_lines < 0)
         return fail(GP_EINVAL, "gp_fbs_create: bad sizes");
+    for (int l = 0; l < 3 * d->n_lines; ++l)
+        if (d->line_irow[l] < -1 || d->line_irow[l] >= d->n_irows || d->line_tx_vrow[l] < -1 ||
+            d->line_tx_vrow[l] >= d->n_vrows || d->line_rx_vrow[l] < -1 || d->line_rx_vrow[l] >= d->n_vrows)
+            return fail(GP_EINVAL, "gp_fbs_create: line %d row index out of range", l / 3);
     steps.assign((size_t)d->n_steps, FbsStep());
     vrow_srow.assign((size_t)d->n_vrows, -1);
     vrow_cap.assign((size_t)d->n_vrows, 0.0);
@@ -1363,6 +1367,43 @@ extern "C" int gp_fbs_specialise(GpFeeder* f) {
     return GP_OK;
 }
 
+// Everything an FbsImpl owns (device tables, modules, staging, streams); also the error path of gp_fbs_create.
+static void fbs_impl_free(FbsImpl* im) {
+    if (!im) return;
+    cudaFree(im->d_steps);
+    cudaFree(im->d_child);
+    cudaFree(im->d_steps_a);
+    cudaFree(im->d_child_a);
+    cudaFree(im->d_alias);
+    cudaFree(im->d_lines);
+    cudaFree(im->d_vrow_srow);
+    cudaFree(im->d_vrow_cap);
+    cudaFree(im->d_events);
+    cudaFree(im->d_evrows);
+    cudaFree(im->d_sched);
+    cudaFree(im->d_unfed);
+    cudaFree(im->d_zc);
+    if (im->jit_module) driver().ModuleUnload(im->jit_module);
+    if (im->jit_module_host) driver().ModuleUnload(im->jit_module_host);
+    for (int i = 0; i < FbsImpl::NSTREAM; ++i) {
+        if (im->d_stage[i]) cudaFree(im->d_stage[i]);
+        if (im->streams[i]) cudaStreamDestroy(im->streams[i]);
+    }
+    delete im;
+}
+
+extern "C" int gp_feeder_destroy(GpFeeder* f) {
+    if (!f) return GP_OK;
+    cudaSetDevice(f->device);
+    if (f->kind == 1) {
+        fbs_impl_free((FbsImpl*)f->impl);
+    } else if (f->kind == 2) {
+        gp_nr3_destroy_impl(f->impl);
+    }
+    delete f;
+    return GP_OK;
+}
+
 extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
     if (!d || !out) return fail(GP_EINVAL, "gp_fbs_create: null argument");
     std::vector<FbsStep> steps;
@@ -1530,13 +1571,13 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
         im->n_unfed = (int)unfed.size();
         if (e == cudaSuccess) e = up((void**)&im->d_unfed, unfed.data(), unfed.size() * sizeof(int));
     }
-    if (e == cudaSuccess) e = cudaMalloc((void**)&im->d_sched, 16);
-    if (e == cudaSuccess) e = cudaMemset(im->d_sched, 0, 16);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&im->d_sched, (FbsImpl::NSCHED + 1) * 16);
+    if (e == cudaSuccess) e = cudaMemset(im->d_sched, 0, (FbsImpl::NSCHED + 1) * 16);
     int smem_optin = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&im->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) {
-        delete im;
+        fbs_impl_free(im);
         return fail(GP_ECUDA, "gp_fbs_create: %s", cudaGetErrorString(e));
     }
     {   // warps per block of the on-chip kernel: one 32-scenario slice of V and I rows per warp
@@ -1571,6 +1612,10 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
         im->jit_plan_warps = im->jit_plan_ig ? w_ig : w_is;
     }
     GpFeeder* f = new (std::nothrow) GpFeeder();
+    if (!f) {
+        fbs_impl_free(im);
+        return fail(GP_ENOMEM, "gp_fbs_create: out of host memory");
+    }
     f->device = device;
     f->kind = 1;
     f->impl = im;
@@ -1578,41 +1623,31 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
     return GP_OK;
 }
 
-extern "C" int gp_feeder_destroy(GpFeeder* f) {
-    if (!f) return GP_OK;
-    cudaSetDevice(f->device);
-    if (f->kind == 1) {
-        FbsImpl* im = (FbsImpl*)f->impl;
-        cudaFree(im->d_steps);
-        cudaFree(im->d_child);
-        cudaFree(im->d_steps_a);
-        cudaFree(im->d_child_a);
-        cudaFree(im->d_alias);
-        cudaFree(im->d_lines);
-        cudaFree(im->d_vrow_srow);
-        cudaFree(im->d_vrow_cap);
-        cudaFree(im->d_events);
-        cudaFree(im->d_evrows);
-        cudaFree(im->d_sched);
-        cudaFree(im->d_unfed);
-        cudaFree(im->d_zc);
-        if (im->jit_module) driver().ModuleUnload(im->jit_module);
-        if (im->jit_module_host) driver().ModuleUnload(im->jit_module_host);
-        for (int i = 0; i < FbsImpl::NSTREAM; ++i) {
-            if (im->d_stage[i]) cudaFree(im->d_stage[i]);
-            if (im->streams[i]) cudaStreamDestroy(im->streams[i]);
-        }
-        delete im;
-    } else if (f->kind == 2) {
-        gp_nr3_destroy_impl(f->impl);
-    }
-    delete f;
-    return GP_OK;
-}
-
 static int fbs_check(GpFeeder* f, int64_t S, int64_t ld, const char* who) {
     if (!f || f->kind != 1) return fail(GP_EINVAL, "%s: not an FBS feeder handle", who);
     if (S < 0 || ld < S) return fail(GP_EINVAL, "%s: need 0 <= S <= ld (S=%lld ld=%lld)", who, (long long)S, (long long)ld);
+    return GP_OK;
+}
+
+// Scheduler words {next tile, warps done} of a launch of a persistent FBS kernel on stream `st`.  The words
+// re-arm themselves when the last warp of a launch leaves, which is only correct for ONE kernel in flight
+// per pair: every stream gets its own pair (launches on one stream are ordered).  A handle that has seen
+// more than NSCHED streams shares the overflow pair, which is zeroed on the launch stream after waiting
+// for that pair's previous launch.
+static int sched_words(FbsImpl* im, cudaStream_t st, unsigned** out) {
+    for (int i = 0; i < im->n_sched_streams; ++i)
+        if (im->sched_stream[i] == st) {
+            *out = im->d_sched + 4 * i;
+            return GP_OK;
+        }
+    if (im->n_sched_streams < FbsImpl::NSCHED) {
+        im->sched_stream[im->n_sched_streams] = st;
+        *out = im->d_sched + 4 * im->n_sched_streams++;
+        return GP_OK;
+    }
+    GP_CUDA(cudaDeviceSynchronize());
+    GP_CUDA(cudaMemsetAsync(im->d_sched + 4 * FbsImpl::NSCHED, 0, 16, st));
+    *out = im->d_sched + 4 * FbsImpl::NSCHED;
     return GP_OK;
 }
 
@@ -1635,12 +1670,18 @@ static int fbs_jit_launch(FbsImpl* im, int64_t S, int64_t ld, const double* spu,
     PeerDst pd;
     memset(&pd, 0, sizeof(pd));
     if (peers) pd = *peers;
+    unsigned* sched = nullptr;
+    int rcs = sched_words(im, st, &sched);
+    if (rcs) return rcs;
     void* args[] = {(void*)&spu, (void*)&V, (void*)&I, (void*)&iters, (void*)&status, (void*)&diff,
-                    (void*)&S_arg, (void*)&ldb_arg, (void*)&tol_arg, (void*)&maxiter_arg, (void*)&im->d_sched,
+                    (void*)&S_arg, (void*)&ldb_arg, (void*)&tol_arg, (void*)&maxiter_arg, (void*)&sched,
                     (void*)&Vmag, (void*)&loss, (void*)&stage, (void*)&Iout, (void*)&pd};
     const int cr = driver().LaunchKernel(kernel ? kernel : im->jit_kernel, (unsigned)blocks, 1, 1, (unsigned)nw * 32, 1, 1, smem,
                                          (void*)st, args, nullptr);
-    if (cr != 0) return fail(GP_ECUDA, "gp_fbs_solve_batch: cuLaunchKernel failed (%d)", cr);
+    if (cr != 0) {
+        cudaMemsetAsync(sched, 0, 16, st);      // a launch that never ran must not leave the words armed
+        return fail(GP_ECUDA, "gp_fbs_solve_batch: cuLaunchKernel failed (%d)", cr);
+    }
     return GP_OK;
 }
 
@@ -1715,6 +1756,9 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
         const long long n_tiles = (S + 31) / 32;
         const int nw = im->onchip_warps;
         const size_t smem = (size_t)nw * (size_t)(im->n_vrows + im->n_irows) * 512;
+        unsigned* sched = nullptr;
+        rc = sched_words(im, st, &sched);
+        if (rc) return rc;
         long long blocks = (n_tiles + nw - 1) / nw;
         if (blocks > im->n_sm) blocks = im->n_sm;
 #define GP_ONCHIP(NW)                                                                                           \
@@ -1727,7 +1771,7 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
         }                                                                                                       \
         fbs_onchip_kernel<NW><<<(unsigned)blocks, NW * 32, smem, st>>>(                                         \
             im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows, im->n_irows, S, ldb, (const char*)spu,   \
-            (char*)V, (char*)I, iters, status, diff, tol, maxiter, im->d_sched);                                \
+            (char*)V, (char*)I, iters, status, diff, tol, maxiter, sched);                                      \
         break;                                                                                                  \
     }
         switch (nw) {
@@ -1918,9 +1962,17 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
             if (!im->streams[0]) GP_CUDA(cudaStreamCreateWithFlags(&im->streams[0], cudaStreamNonBlocking));
             // the host path's own build of the kernel (next tile's PCIe reads issued before this tile's stores);
             // feeders with more than 32 load rows, or a failed build, keep the device-path kernel
+            const int want_host_warps = im->jit_warps < g_host_warps ? im->jit_warps : g_host_warps;
+            if (im->jit_host_tried && im->jit_kernel_host && im->jit_warps_host != want_host_warps) {
+                // gp_set_option("host_warps") changed since this handle's host kernel was built: build again
+                GP_CUDA(cudaStreamSynchronize(im->streams[0]));
+                driver().ModuleUnload(im->jit_module_host);
+                im->jit_module_host = im->jit_kernel_host = nullptr;
+                im->jit_host_tried = false;
+            }
             if (!im->jit_host_tried && im->n_srows <= 32 && g_host_read_ahead) {
                 im->jit_host_tried = true;
-                im->jit_warps_host = im->jit_warps < g_host_warps ? im->jit_warps : g_host_warps;
+                im->jit_warps_host = want_host_warps;
                 if (fbs_jit_build(f, im->jit_warps_host, im->jit_ig, true, &im->jit_module_host, &im->jit_kernel_host) != GP_OK)
                     im->jit_module_host = im->jit_kernel_host = nullptr;
             }
@@ -1949,6 +2001,7 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
                  b_loss = (size_t)C * 16, b_diff = (size_t)C * 8, b_i32 = (size_t)C * 4;
     const size_t need = b_spu + b_V + b_I + b_mag + b_loss + b_diff + 2 * b_i32 + 1024;
     if (need > im->stage_bytes) {
+        im->stage_bytes = 0;        // stays 0 unless every slot is allocated
         for (int i = 0; i < FbsImpl::NSTREAM; ++i) {
             if (im->d_stage[i]) cudaFree(im->d_stage[i]);
             im->d_stage[i] = nullptr;

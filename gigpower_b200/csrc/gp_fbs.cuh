@@ -69,7 +69,13 @@ struct FbsImpl {
     // warps per block that fit the feeder's V and I rows in shared memory (0 = does not fit)
     int* d_unfed = nullptr;       // V rows no forward step writes (kept at the flat start's zero)
     int n_unfed = 0;
-    unsigned* d_sched = nullptr;
+    // One pair of self-resetting scheduler words PER STREAM (sched_words()): the words are only correct for
+    // one kernel in flight, launches on one stream are ordered, launches on different streams (the chunked
+    // host path, callers with their own streams) each get their own pair.
+    static constexpr int NSCHED = 32;
+    unsigned* d_sched = nullptr;                  // [NSCHED + 1][4] words; pair NSCHED is the overflow pair
+    cudaStream_t sched_stream[NSCHED] = {};
+    int n_sched_streams = 0;
     int n_sm = 0, onchip_warps = 0;
     // feeder-specialised on-chip kernel (gp_fbs_specialise): host copies of the tables the
     // generator reads, the loaded module and its kernel

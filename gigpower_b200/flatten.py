@@ -88,6 +88,18 @@ def gamma_row_map(kind: np.ndarray, vr_gamma: np.ndarray, gamma_vr: np.ndarray):
     return grow, np.array(owner, dtype=np.int32)
 
 
+def load_weights(c: Circuit, srow: np.ndarray, n_srows: int) -> np.ndarray:
+    """``[n_srows, n_loads]`` complex W with ``spu_rows = W @ mult.T`` for per-load multipliers
+    (load.py:16-24: a load's power split per phase of its bus-name suffix, summed per bus-phase).
+    Host-only: needs the circuit and the packed-row map of either solver's tables, no device."""
+    W = np.zeros((n_srows, c.loads.num_elements), dtype=complex)
+    for j, e in enumerate(c.loads.get_elements()):
+        b = c.buses.get_idx(e.related_bus)
+        for p in e.get_ph_idx_matrix():
+            W[srow[b, p], j] += e.spu[p]
+    return W
+
+
 def reverse_adjacency(adj: Dict[str, List[str]]) -> Dict[str, List[str]]:
     rev: Dict[str, List[str]] = {}
     for node, nbrs in adj.items():

@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 from . import _cabi
-from .flatten import FbsTables, flatten_fbs
+from .flatten import FbsTables, flatten_fbs, load_weights
 from .solution import Solution
 
 
@@ -165,13 +165,7 @@ class SolutionFBS(Solution):
     def load_weights(self) -> np.ndarray:
         """``[n_srows, n_loads]`` complex W with ``spu_rows = W @ mult.T`` for
         per-load multipliers (load.py:16-24 split per phase, summed per bus)."""
-        t, c = self.tables, self.circuit
-        W = np.zeros((t.n_srows, c.loads.num_elements), dtype=complex)
-        for j, e in enumerate(c.loads.get_elements()):
-            b = c.buses.get_idx(e.related_bus)
-            for p in e.get_ph_idx_matrix():
-                W[t.srow[b, p], j] += e.spu[p]
-        return W
+        return load_weights(self.circuit, self.tables.srow, self.tables.n_srows)
 
     # ---- batched solve -------------------------------------------------------
     def solve_batch(self, spu=None, load_mult=None, spu_rows=None, outputs=('V', 'Vmag', 'loss'),
@@ -319,6 +313,62 @@ class SolutionFBS(Solution):
             self._feeder.handle, S, ld, ptr(spu_rows), ptr(V_out), ptr(I_out), ptr(Vmag_out), ptr(loss_out),
             iters.ctypes.data, status.ctypes.data, diff.ctypes.data, tol, maxiter))
         return iters, status, diff
+
+    # ---- derived results of the CURRENT snapshot state (solution.py:177-233) --------
+    def _post_snapshot(self, want):
+        """``self.V`` / ``self.I`` / ``self.spu`` / ``self.wpu`` as they stand (``n x 3``, the caller may have
+        changed them) through ``gp_fbs_post_ex`` as a batch of one scenario: the same kernels that
+        produce sV, |V|, Stx, Srx for a batch.  Returns the unpacked ``n x 3`` arrays asked for."""
+        torch, dev = self._dev()
+        t = self.tables
+
+        def pack(mat, rowmap, n_rows, dtype):
+            rows = np.zeros((max(n_rows, 1), 1), dtype=dtype)
+            b, p = np.nonzero(rowmap >= 0)
+            rows[rowmap[b, p], 0] = np.asarray(mat)[b, p]
+            return torch.from_numpy(rows).to(dev)
+
+        V = pack(self.V, t.vrow, t.n_vrows, complex)
+        I = pack(self.I, t.irow, t.n_irows, complex)
+        spu = torch.from_numpy(self.pack_spu(self.spu)).to(dev) if t.n_srows else torch.zeros((1, 1), dtype=torch.complex128, device=dev)
+        wpu = pack(self.wpu, t.vrow, t.n_vrows, float) if np.any(self.wpu) else None
+        ex = _cabi.make_extras(wpu=wpu)
+        mk = lambda rows, dt: torch.zeros((max(rows, 1), 1), dtype=dt, device=dev)
+        out = {'sV': mk(t.n_vrows, torch.complex128) if 'sV' in want else None,
+               'Vmag': mk(t.n_vrows, torch.float64) if 'Vmag' in want else None,
+               'Stx': mk(t.n_irows, torch.complex128) if 'Stx' in want else None,
+               'Srx': mk(t.n_irows, torch.complex128) if 'Srx' in want else None}
+        p = lambda x: x.data_ptr() if x is not None else None
+        st = torch.cuda.current_stream(dev)
+        _cabi.check(_cabi.gp_fbs_post_ex(self._feeder.handle, 1, 1, spu.data_ptr(),
+                                         C.byref(ex) if ex is not None else None, V.data_ptr(), I.data_ptr(),
+                                         p(out['sV']), p(out['Vmag']), p(out['Stx']), p(out['Srx']), None, st.cuda_stream))
+        st.synchronize()
+        res = BatchResult(tables=t, S=1, iterations=None, status=None, sV_rows=out['sV'], Vmag_rows=out['Vmag'],
+                          Stx_rows=out['Stx'], Srx_rows=out['Srx'])
+        return {k: getattr(res, k)[0] for k in want}
+
+    def calc_sV(self, bus=None):
+        """``sV = spu (aPQ + aI |V| + aZ |V|^2) - j cappu |V|^2 + j wpu`` from the current ``self.V``, zero on
+        absent phases (solution.py:177-220); with ``bus`` only that bus's row of ``self.sV`` is updated."""
+        sV = self._post_snapshot(('sV',))['sV']
+        if bus:
+            i = self.circuit.buses.get_idx(bus)
+            self.sV[i] = sV[i]
+        else:
+            self.sV = sV
+
+    def calc_Vmag(self):
+        """``Vmag = abs(V)`` (solution.py:232-233)."""
+        self.Vmag = self._post_snapshot(('Vmag',))['Vmag']
+
+    def calc_Stx(self):
+        """``Stx = V[tx] conj(I)`` of the real lines (solution.py:222-225)."""
+        self.Stx = self._post_snapshot(('Stx',))['Stx']
+
+    def calc_Srx(self):
+        """``Srx = V[rx] conj(I)`` of the real lines (solution.py:227-230)."""
+        self.Srx = self._post_snapshot(('Srx',))['Srx']
 
     # ---- single snapshot (solution_fbs.py:76-136) -------------------------------
     def solve(self):

@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 from . import _cabi
-from .flatten import Nr3Tables, flatten_nr3
+from .flatten import Nr3Tables, flatten_nr3, load_weights
 from .solution import Solution
 from .solution_fbs import _Feeder
 
@@ -119,13 +119,7 @@ class SolutionNR3(Solution):
         return rows
 
     def load_weights(self) -> np.ndarray:
-        t, c = self.tables, self.circuit
-        W = np.zeros((t.n_srows, c.loads.num_elements), dtype=complex)
-        for j, e in enumerate(c.loads.get_elements()):
-            b = c.buses.get_idx(e.related_bus)
-            for p in e.get_ph_idx_matrix():
-                W[t.srow[b, p], j] += e.spu[p]
-        return W
+        return load_weights(self.circuit, self.tables.srow, self.tables.n_srows)
 
     def solve_batch(self, spu=None, load_mult=None, spu_rows=None,
                     outputs=('X', 'V', 'Vmag', 'loss'), maxiter=None, return_device=False,

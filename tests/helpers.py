@@ -56,6 +56,31 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0
 
 
+def true_rel_err(a, b, floor=1e-6):
+    """max |a-b| / |b| over the entries with |b| > floor: a STRICTLY relative error (rel_err above is
+    absolute below 1 pu, which is 100x looser than "relative" for currents and powers of ~1e-2 pu).
+    Entries at or below the floor (structural zeros, absent phases) are held to an absolute floor * tol
+    by the callers through ``small_abs_err``."""
+    a, b = np.asarray(a), np.asarray(b)
+    m = np.abs(b) > floor
+    return float(np.max(np.abs(a[m] - b[m]) / np.abs(b[m]))) if m.any() else 0.0
+
+
+def small_abs_err(a, b, floor=1e-6):
+    """max |a-b| over the entries with |b| <= floor."""
+    a, b = np.asarray(a), np.asarray(b)
+    m = np.abs(b) <= floor
+    return float(np.max(np.abs(a[m] - b[m]))) if m.any() else 0.0
+
+
+def ref_123():
+    """tests/golden/ref_123.npz (oracle/make_golden_123.py): the unmodified reference's FBS and NR3 on
+    the authored IEEE 123-bus feeder and its FBS on the 2,541-bus feeder."""
+    if 'r123' not in _cache:
+        _cache['r123'] = np.load(os.path.join(GOLDEN, 'ref_123.npz'))
+    return _cache['r123']
+
+
 def taps_golden():
     """tests/golden/ref_taps.npz (oracle/make_golden_taps.py): one unmodified reference object
     per scenario, built with that scenario's regulator taps."""

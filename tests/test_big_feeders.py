@@ -8,7 +8,7 @@ import pytest
 from gigpower_b200.dss_reader import read_dss
 from gigpower_b200.circuit import Circuit
 from gigpower_b200.flatten import flatten_fbs, flatten_nr3
-from helpers import REPO, ZIPS, rel_err
+from helpers import REPO, ZIPS, rel_err, true_rel_err, small_abs_err, ref_123
 
 FEEDERS = os.path.join(REPO, 'gigpower_b200', 'feeders')
 F123 = os.path.join(FEEDERS, 'ieee123_allwye_noxfm_noreg.dss')
@@ -38,6 +38,89 @@ def test_tree_oracle_equals_dense_oracle_on_123():
     a, b = NR3Oracle(m).solve(), NR3TreeOracle(m).solve()
     assert np.array_equal(a['iterations'], b['iterations'])
     assert np.abs(a['XNR'] - b['XNR']).max() <= 1e-12
+
+
+def _spu_from_rows(c, rows):
+    """packed rows [n_srows, S] -> the reference's [S, nb, 3] spu matrices (oracle circuit c)."""
+    b, p = np.nonzero(c.zip_mask * c.bus_pm)
+    spu = np.zeros((rows.shape[1], c.nb, 3), dtype=complex)
+    spu[:, b, p] = rows.T
+    return spu
+
+
+def test_oracles_match_the_reference_on_the_authored_feeders():
+    """tests/golden/ref_123.npz holds the UNMODIFIED reference's results on the two authored feeders
+    (oracle/make_golden_123.py).  The FBS oracle, the dense NR3 oracle and the NR3 tree oracle are held
+    to them: <= 1e-12 on V and I, equal iteration counts - the same bar as on the reference's own feeders."""
+    from oracle.gp_oracle import FBSOracle, NR3Oracle
+    from oracle.nr3_tree import NR3TreeOracle
+    g = ref_123()
+    m = read_dss(F123)
+    o = FBSOracle(m, ZIPS['test_zip'])
+    mult = g['123/mult']
+    r = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+    assert list(r['iterations']) == list(g['123/FBS/iterations'])
+    for k in ('V', 'I', 'sV', 'Stx', 'Srx'):
+        assert np.abs(r[k] - g['123/FBS/' + k]).max() <= 1e-12, k
+    rd = o.solve(_spu_from_rows(o.c, g['123/der/rows']))
+    assert list(rd['iterations']) == list(g['123/der/FBS/iterations'])
+    assert np.abs(rd['V'] - g['123/der/FBS/V']).max() <= 1e-12 and np.abs(rd['I'] - g['123/der/FBS/I']).max() <= 1e-12
+    o5 = FBSOracle(read_dss(F2500), ZIPS['test_zip'])
+    m5 = g['2541/mult']
+    r5 = o5.solve(o5.c.spu_matrix(o5.c.load_kw * m5, o5.c.load_kvar * m5))
+    assert list(r5['iterations']) == list(g['2541/FBS/iterations'])
+    assert np.abs(r5['V'] - g['2541/FBS/V']).max() <= 1e-12 and np.abs(r5['I'] - g['2541/FBS/I']).max() <= 1e-12
+    pick = g['123/NR3/scenarios']
+    for cls in (NR3TreeOracle, NR3Oracle):
+        on = cls(m, ZIPS['test_zip'])
+        mm = mult[pick] if cls is NR3TreeOracle else mult[pick[:2]]        # the dense restatement: two scenarios
+        rn = on.solve(on.c.spu_matrix(on.c.load_kw * mm, on.c.load_kvar * mm))
+        assert list(rn['iterations']) == list(g['123/NR3/iterations'][:len(mm)]), cls.__name__
+        assert np.abs(rn['XNR'] - g['123/NR3/XNR'][:len(mm)]).max() <= 1e-11, cls.__name__
+        Vn = rn['V'] if rn['V'].shape[1] == 3 else np.swapaxes(rn['V'], 1, 2)      # [S, 3, nb] like the reference
+        assert np.abs(Vn - g['123/NR3/V'][:len(mm)]).max() <= 1e-11, cls.__name__
+
+
+@pytest.mark.gpu
+def test_gpu_matches_the_reference_on_the_authored_feeders():
+    """Every FBS kernel that takes the 123-bus feeder, the 2,541-bus streaming path and both NR3 kernels
+    against the unmodified reference's own vectors (ref_123.npz): 1e-9 relative on V - and STRICTLY
+    relative (|a-b|/|b|) on currents and powers above 1e-6 pu - with equal iteration counts."""
+    from gigpower_b200 import _cabi
+    from gigpower_b200.solution_fbs import SolutionFBS
+    from gigpower_b200.solution_nr3 import SolutionNR3
+    g = ref_123()
+    z = np.asarray(ZIPS['test_zip'])
+    s = SolutionFBS(F123, zip_v=z)
+    try:
+        for kern in (3, 1, 2, 0):
+            _cabi.check(_cabi.gp_set_option(b'fbs_kernel', kern))
+            r = s.solve_batch(load_mult=g['123/mult'], outputs=('V', 'I', 'sV', 'Stx', 'Srx'))
+            assert list(r.iterations) == list(g['123/FBS/iterations']), kern
+            for k in ('V', 'I', 'sV', 'Stx', 'Srx'):
+                want = g['123/FBS/' + k]
+                assert rel_err(getattr(r, k), want) <= 1e-9, (kern, k)
+                assert true_rel_err(getattr(r, k), want) <= 1e-9, (kern, k)
+                assert small_abs_err(getattr(r, k), want) <= 1e-15, (kern, k)
+            rd = s.solve_batch(spu_rows=g['123/der/rows'], outputs=('V', 'I'))
+            assert list(rd.iterations) == list(g['123/der/FBS/iterations']), kern
+            assert true_rel_err(rd.V, g['123/der/FBS/V']) <= 1e-9 and true_rel_err(rd.I, g['123/der/FBS/I']) <= 1e-9
+    finally:
+        _cabi.gp_set_option(b'fbs_kernel', 0)
+    s5 = SolutionFBS(F2500, zip_v=z)
+    r5 = s5.solve_batch(load_mult=g['2541/mult'], outputs=('V', 'I'))
+    assert list(r5.iterations) == list(g['2541/FBS/iterations'])
+    assert true_rel_err(r5.V, g['2541/FBS/V']) <= 1e-9 and true_rel_err(r5.I, g['2541/FBS/I']) <= 1e-9
+    n = SolutionNR3(F123, zip_v=z)
+    try:
+        for kern in (1, 2):
+            _cabi.check(_cabi.gp_set_option(b'nr3_kernel', kern))
+            rn = n.solve_batch(load_mult=g['123/mult'][g['123/NR3/scenarios']], outputs=('X', 'V'))
+            assert list(rn.iterations) == list(g['123/NR3/iterations']), kern
+            assert rel_err(rn.XNR, g['123/NR3/XNR']) <= 1e-9, kern
+            assert true_rel_err(rn.V, g['123/NR3/V']) <= 1e-9, kern
+    finally:
+        _cabi.gp_set_option(b'nr3_kernel', 0)
 
 
 @pytest.mark.gpu

@@ -20,22 +20,17 @@ def _c_array(ctype, name, a):
 
 
 def _build(tmp_path):
-    from gigpower_b200.solution_fbs import SolutionFBS      # host side only: parse + flatten, no GPU needed
     from gigpower_b200.circuit import Circuit
     from gigpower_b200.dss_reader import read_dss
-    from gigpower_b200.flatten import flatten_fbs
+    from gigpower_b200.flatten import flatten_fbs, load_weights
     from gigpower_b200.solution import Solution
     Solution.set_zip_values(np.asarray(ZIPS['test_zip']))
     model = read_dss(feeder_path(FEEDER), {'reg1': 9, 'reg2': 7, 'reg3': 9})
     circuit = Circuit(model)
     t = flatten_fbs(circuit)
 
-    class _Host:
-        load_weights = SolutionFBS.load_weights
-    h = _Host()
-    h.circuit, h.tables = circuit, t
     mult = np.random.Generator(np.random.PCG64(99)).uniform(0.5, 1.5, size=(S, circuit.loads.num_elements))
-    rows = np.ascontiguousarray(h.load_weights() @ mult.T)                 # [n_srows, S] complex
+    rows = np.ascontiguousarray(load_weights(circuit, t.srow, t.n_srows) @ mult.T)                 # [n_srows, S] complex
     hdr = [f'#define GP_DEMO_S {S}\n', f'#define GP_DEMO_N_STEPS {t.n_steps}\n', f'#define GP_DEMO_N_VROWS {t.n_vrows}\n',
            f'#define GP_DEMO_N_IROWS {t.n_irows}\n', f'#define GP_DEMO_N_SROWS {t.n_srows}\n',
            f'#define GP_DEMO_N_CHILD {t.child_irow.shape[0]}\n', f'#define GP_DEMO_N_LINES {t.n_lines}\n',

@@ -391,3 +391,67 @@ def test_specialised_kernel_with_i_rows_in_shared_or_global_memory(feeder):
     finally:
         _cabi.gp_set_option(b'jit_i_global', -1)
         _cabi.gp_set_option(b'fbs_kernel', 0)
+
+
+@pytest.mark.parametrize('kernel', [5, 4])
+def test_chunked_host_path_runs_persistent_kernels_on_several_streams(kernel):
+    """The staged host path cuts a batch into chunks on up to four streams.  The persistent kernels
+    (feeder-specialised, table-driven on-chip) pull tiles from scheduler words that are only right
+    for ONE kernel in flight, so each stream has its own pair: four chunks in flight must give
+    exactly the one-chunk result (every tile solved, once)."""
+    import torch
+    from gigpower_b200 import _cabi
+    feeder, S = 'IEEE_13_Bus_allwye_noxfm_noreg', 4 * 9000 + 77
+    s = _fbs(feeder)
+    assert s.specialise()
+    rng = np.random.Generator(np.random.PCG64(71))
+    rows = np.ascontiguousarray(s.load_weights() @ rng.uniform(0.5, 1.5, size=(S, s.circuit.loads.num_elements)).T)
+    t = s.tables
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+    spu_h = torch.from_numpy(rows).pin_memory()
+    out = {}
+    try:
+        _cabi.check(_cabi.gp_set_option(b'host_zero_copy', 0))
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', kernel))
+        for chunks in (1, 4, 7):
+            _cabi.check(_cabi.gp_set_option(b'host_chunks', chunks))
+            for rep in range(3):            # relaunches: the words must have re-armed themselves
+                V, I = pin((t.n_vrows, S), torch.complex128), pin((t.n_irows, S), torch.complex128)
+                V.fill_(float('nan')), I.fill_(float('nan'))
+                Vmag, loss = pin((t.n_vrows, S), torch.float64), pin(S, torch.complex128)
+                it, st, df = s.solve_batch_host(spu_h, V, I, Vmag, loss)
+                res = (it.copy(), st.copy(), df.copy(), V.numpy().copy(), I.numpy().copy(), Vmag.numpy().copy(),
+                       loss.numpy().copy())
+                if chunks == 1 and rep == 0:
+                    out = res
+                    assert np.isfinite(res[3]).all() and (res[1] == 0).all()
+                else:
+                    for a, b in zip(out, res):
+                        assert np.array_equal(a, b), f'{chunks} chunks, repeat {rep}'
+    finally:
+        _cabi.gp_set_option(b'host_zero_copy', 1)
+        _cabi.gp_set_option(b'host_chunks', 0)
+        _cabi.gp_set_option(b'fbs_kernel', 0)
+
+
+@pytest.mark.parametrize('feeder', ['IEEE_13_Bus_allwye_noxfm_noreg', 'IEEE_13_Bus_allwye', 'IEEE_37_Bus_allwye_noxfm_noreg'])
+def test_calc_methods_match_the_reference(feeder):
+    """Solution.calc_sV / calc_sV(bus) / calc_Vmag / calc_Stx / calc_Srx (solution.py:177-233) on an object
+    whose V, I, spu and wpu were set by the caller: against the unmodified reference's own methods on
+    the same arbitrary state (tests/golden/ref_calc.npz, oracle/make_golden_calc.py)."""
+    import os
+    from helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'ref_calc.npz'))
+    s = _fbs(feeder)
+    k = feeder + '/'
+    s.V, s.I, s.wpu, s.spu = g[k + 'V'].copy(), g[k + 'I'].copy(), g[k + 'wpu'].copy(), g[k + 'spu'].copy()
+    s.calc_sV()
+    s.calc_Vmag()
+    s.calc_Stx()
+    s.calc_Srx()
+    nl = s.circuit.lines.num_elements
+    assert np.abs(s.sV - g[k + 'sV']).max() <= 1e-13 and np.abs(s.Vmag - g[k + 'Vmag']).max() <= 1e-13
+    assert np.abs(s.Stx[:nl] - g[k + 'Stx']).max() <= 1e-13 and np.abs(s.Srx[:nl] - g[k + 'Srx']).max() <= 1e-13
+    s.V = g[k + 'bus_V'].copy()
+    s.calc_sV(s.circuit.buses.get_element(str(g[k + 'bus_name'])))
+    assert np.abs(s.sV - g[k + 'bus_sV']).max() <= 1e-13

@@ -138,3 +138,14 @@ def test_gamma_rows_follow_the_step_table(feeder, n_rows):
             assert ((t.grow >= 0) == ((t.kind[:, None] == EDGE_VR) & (t.vr_gamma != 0))).all()
             for i, p in zip(*np.nonzero(t.grow >= 0)):
                 assert t.vr_gamma[i, p] == vrs[t.grow_vr[t.grow[i, p]]].gamma
+
+
+def test_packaged_feeders_are_the_golden_ones():
+    """bench.py and smoke() read their input feeders from gigpower_b200/feeders; the three IEEE ones are
+    copies of the parsed reference feeders under tests/golden/feeders."""
+    import filecmp
+    import os
+    from helpers import REPO, GOLDEN
+    for f in ('IEEE_13_Bus_allwye_noxfm_noreg', 'IEEE_34_Bus_allwye_noxfm_noreg', 'IEEE_37_Bus_allwye_noxfm_noreg'):
+        assert filecmp.cmp(os.path.join(REPO, 'gigpower_b200', 'feeders', f + '.json'),
+                           os.path.join(GOLDEN, 'feeders', f + '.json'), shallow=False)
