@@ -618,7 +618,10 @@ def run_workload(ctx, args, name, steps, main):
     _cabi.check(_cabi.gp_set_option(b'fbs_share_rows', args.share_rows))
     if args.host_warps:
         _cabi.check(_cabi.gp_set_option(b'host_warps', args.host_warps))
+    _cabi.check(_cabi.gp_set_option(b'host_chunks', args.host_chunks))
     _cabi.check(_cabi.gp_set_option(b'nr3_kernel', args.nr3_kernel))
+    _cabi.check(_cabi.gp_set_option(b'fbs_order', args.fbs_order))
+    _cabi.check(_cabi.gp_set_option(b'fbs_walk_blocks', args.walk_blocks))
     sol._dev()
     _cabi.check(_cabi.gp_set_option(b'fbs_kernel', args.fbs_kernel))
     if args.prefetch is not None:
@@ -925,10 +928,11 @@ def run_workload(ctx, args, name, steps, main):
         solve_ms = float(np.mean(ms_solve))
         n_it = float(its.sum())
         kernel_names = {1: 'fbs_dfs_kernel', 2: 'fbs_phase_kernel', 3: 'fbs_solve_kernel', 4: 'fbs_onchip_kernel',
-                        5: 'gp_fbs_jit_kernel'}
+                        5: 'gp_fbs_jit_kernel', 6: 'fbs_walk_kernel'}
         variant = {0: None, 1: 'fused-dfs', 2: 'phase-parallel', 3: 'two-sweep streaming (state in HBM)',
                    4: 'on-chip two-sweep (state in shared memory), table-driven',
-                   5: 'on-chip two-sweep (state in shared memory), feeder-specialised (NVRTC)'}[active]
+                   5: 'on-chip two-sweep (state in shared memory), feeder-specialised (NVRTC)',
+                   6: 'tree walk (depth-first, current bus in registers, rows in HBM)'}[active]
         # per sweep read I, write V | read V, read spu, write I, write V; once: read spu, write V, I
         stream_per_it = 16 * (2 * t.n_irows + 3 * t.n_vrows + t.n_srows)
         stream_once = 16 * (t.n_srows + t.n_vrows + t.n_irows)
@@ -1098,16 +1102,22 @@ def main():
                     help='I rows of the specialised FBS kernel in global memory: -1 automatic, 0 no, 1 yes')
     ap.add_argument('--host-warps', type=int, default=0,
                     help='warps per SM of the one-launch host path (e2e); 0 = the library default')
+    ap.add_argument('--host-chunks', type=int, default=0,
+                    help='pipeline chunks of the staged host path (e2e of feeders without a specialised kernel); 0 = automatic')
     ap.add_argument('--share-rows', type=int, default=1, choices=[0, 1],
                     help='streaming FBS kernel: 1 = I rows that repeat a child\'s current or stay zero make no HBM round '
                          'trips (default), 0 = every row travels')
+    ap.add_argument('--fbs-order', type=int, default=1, choices=[0, 1],
+                    help='streaming FBS kernel: 1 = depth-first order of the forward / backward steps (default), 0 = two full sweeps')
     ap.add_argument('--nr3-kernel', type=int, default=0, choices=[0, 1, 2],
                     help='0 automatic, 1 one thread per scenario, 2 three phase lanes per scenario')
     ap.add_argument('--prefetch', type=int, default=None, help='L2 prefetch distance of the streaming FBS kernel / the NR3 kernel')
-    ap.add_argument('--fbs-kernel', type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
+    ap.add_argument('--walk-blocks', type=int, default=4, choices=[4, 5, 6, 8],
+                    help='tree-walk FBS kernel: resident 128-thread blocks per SM it is compiled for (128/96/80/64 registers)')
+    ap.add_argument('--fbs-kernel', type=int, default=0, choices=[0, 1, 2, 3, 4, 5, 6],
                     help='0 = automatic (on-chip when the feeder fits in shared memory, else two-sweep streaming), '
                          '1 = fused depth-first, 2 = phase-parallel lanes, 3 = two-sweep streaming, 4 = on-chip table-driven, '
-                         '5 = on-chip feeder-specialised')
+                         '5 = on-chip feeder-specialised, 6 = tree walk')
     args = ap.parse_args()
     if args.sub is None:
         args.sub = ','.join(DEFAULT_SUBS) if args.workload == DEFAULT_WORKLOAD else 'none'

@@ -49,6 +49,12 @@ static int g_fbs_prefetch = 0;
 // gp_set_option("fbs_share_rows", 0|1): the streaming kernel skips the HBM round trips of I rows that only
 // repeat a child's current or stay zero (default 1; 0 = every row travels, for A/B measurements)
 static int g_fbs_share_rows = 1;
+// gp_set_option("fbs_order", 0|1): 1 (default) = the streaming kernel walks the tree depth-first (forward step on
+// the way down, backward step on the way up; same steps, same rows, same values), 0 = two full sweeps
+static int g_fbs_order = 1;
+// gp_set_option("fbs_walk_blocks", n): resident 128-thread blocks per SM the tree-walk kernel is compiled for
+// (4 = up to 128 registers per thread, 5 = 96, 6 = 80, 8 = 64)
+static int g_fbs_walk_blocks = 4;
 
 // |v| as numpy computes it for the ZIP model (abs then square, solution.py:202)
 __device__ __forceinline__ double cabs2(double2 v, double& a) {
@@ -190,13 +196,13 @@ __device__ __forceinline__ void bwd_fast(const FbsStep* __restrict__ st, const i
         for (int p = 0; p < 3; ++p)
             if ((M >> p) & 1) In[p] = make_double2(nan_to_num(In[p].x), nan_to_num(In[p].y));
     }
-    const int no_store = (bv.w >> 16) & 7;
+    const int no_store = (bv.w >> 16) & 7, no_pstore = (bv.w >> 19) & 7;
 #pragma unroll
     for (int p = 0; p < 3; ++p)
         if (((M >> p) & 1) && !((no_store >> p) & 1)) m.stI(erow[p], In[p]);
 #pragma unroll
     for (int p = 0; p < 3; ++p)
-        if ((M >> p) & 1) {                             // update_voltage_backward (:207-232)
+        if (((M >> p) & 1) && !((no_pstore >> p) & 1)) {    // update_voltage_backward (:207-232), surviving stores only
             double2 v = Vb[p];
 #pragma unroll
             for (int q = 0; q < 3; ++q)
@@ -283,6 +289,9 @@ __device__ __forceinline__ void fbs_bwd_step(const FbsStep* __restrict__ st, con
     const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
     const int kind = bv.w & 0xff, fast = (bv.w >> 8) & 0xff;
     const int no_store = (bv.w >> 16) & 7;      // phases whose I row is a shared row: value in place already
+    // phases whose parent-voltage rewrite a sibling earlier in topo order overwrites before anything reads it
+    // (fbs_mark_dead_parent_stores): only the store that survives is made
+    const int no_pstore = (bv.w >> 19) & 7;
     GP_FAST_SWITCH(bwd_fast, false, st, bv, pv, child_irow, k, m, sp)
     const int brow[3] = {bv.x, bv.y, bv.z};
     const int prow[3] = {pv.x, pv.y, pv.z};
@@ -294,7 +303,7 @@ __device__ __forceinline__ void fbs_bwd_step(const FbsStep* __restrict__ st, con
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
             const double g = __ldg(&st->gamma[p]);
-            if (g != 0.0 && prow[p] >= 0) {
+            if (g != 0.0 && prow[p] >= 0 && !((no_pstore >> p) & 1)) {
                 double ig = __ldg(&st->inv_gamma[p]);
                 if (m.hasG()) ig = 1.0 / m.ldG(__ldg(&st->gam_row[p]));     // 1/gamma * V (:205)
                 m.stV(prow[p], make_double2(ig * Vb[p].x, ig * Vb[p].y));
@@ -349,7 +358,7 @@ __device__ __forceinline__ void fbs_bwd_step(const FbsStep* __restrict__ st, con
     // update_voltage_backward (:207-232): phases of the child bus, masked by the parent
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
-        if (brow[p] < 0 || prow[p] < 0) continue;
+        if (brow[p] < 0 || prow[p] < 0 || ((no_pstore >> p) & 1)) continue;
         double2 v = Vb[p];
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
@@ -393,7 +402,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
                  int* __restrict__ status_out, double* __restrict__ diff_out, double tol,
                  int maxiter, int PF, const int* __restrict__ unfed, int n_unfed,
                  const char* __restrict__ gam, int warm, const char* __restrict__ wpu,
-                 const int2* __restrict__ alias, int n_alias) {
+                 const int2* __restrict__ alias, int n_alias, const int2* __restrict__ events, int n_events) {
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (s >= S) return;
     typedef GMemT<EX> GMem;
@@ -423,6 +432,31 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
     while (!converged && it < maxiter) {
 #pragma unroll
         for (int p = 0; p < 3; ++p) m.stV(k.root_vrow[p], k.vref[p]);      // V[root] = Vref  (:89)
+        if (n_events > 0) {
+            // Depth-first order of the SAME steps on the same rows (gp_set_option("fbs_order")).  A bus's forward
+            // step runs when the walk descends its edge, its backward step when the walk comes back up, children
+            // latest-in-topo-order first.  Every value a step reads is the one the reference's two full sweeps
+            // give it: a forward step needs its parent's FORWARD voltage, and of a bus's children only the one
+            // earliest in topo order - visited last here - rewrites a phase of the parent (the other rewrites
+            // are overwritten before anything reads them and are not made: no_pstore); a backward step needs
+            // its children's new currents and its own bus as they rewrote it, all done when the walk returns;
+            // the edge current a forward step reads is last iteration's, its row is only written on the way up.
+            // What changes is WHEN rows are touched: a bus's voltage is written and read again within its own
+            // subtree, for most buses a few steps apart, so the backward step finds it in L2 instead of DRAM.
+            const bool first = it == 0 && !(EX && warm);
+            for (int e = 0; e < n_events; ++e) {
+                const int2 ev = __ldg(events + e);
+                if (ev.y & 1) {
+                    double2 sp[3];
+                    fbs_load_spu(steps + ev.x, m, sp);
+                    fbs_bwd_step(steps + ev.x, child_irow, k, m, sp);
+                } else if (first) {
+                    fbs_fwd_step<GMem, true>(steps + ev.x, m);
+                } else {
+                    fbs_fwd_step<GMem, false>(steps + ev.x, m);
+                }
+            }
+        } else {
         for (int pos = 0; pos < n_steps; ++pos) {                                      // :92-98
             if (PF > 0 && pos + PF < n_steps) {
                 const int4 ev = __ldg(reinterpret_cast<const int4*>(steps[pos + PF].edge_irow));
@@ -447,6 +481,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
             double2 sp[3];
             fbs_load_spu(steps + pos, m, sp);
             fbs_bwd_step(steps + pos, child_irow, k, m, sp);
+        }
         }
         ++it;
         diff = fbs_root_diff(k, m);
@@ -978,6 +1013,299 @@ fbs_dfs_kernel(const FbsStep* __restrict__ steps, const int2* __restrict__ event
     status_out[s] = converged ? GP_ST_CONVERGED : ((diff != diff || isinf(diff)) ? GP_ST_NONFINITE : GP_ST_MAXITER);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Tree-walk kernel (fbs_kernel = 6; the automatic choice for feeders that do not fit on chip).
+//
+// Same arithmetic as fbs_solve_kernel in depth-first order (see there), but the walk carries the
+// state of the bus it stands on in REGISTERS instead of passing every value through memory:
+//   cv[3]  the voltage of the current bus: its forward value, overwritten phase by phase as the
+//          child that survives the reference's overwrite order (the one earliest in topo order,
+//          visited last) rewrites it - the two never coexist, which is why one array suffices;
+//   ca[3]  the sum of the new currents of the children visited so far.
+// An event is one of
+//   DESC  descend into a bus that has children: forward step, the child becomes the current bus
+//         (the parent's voltage is already in its V rows; its partial current sum is parked in
+//         its own - at that moment unused - I rows);
+//   LEAF  a bus without children: forward step, load current, parent rewrite and the
+//         contribution to the parent's current sum, all from registers;
+//   ASC   come back up from a bus whose children are done: its backward step from registers,
+//         then the parent becomes the current bus again (its voltage is taken back from its V
+//         rows except for the phases this bus has just rewritten, its parked current sum from
+//         its I rows).
+// Per iteration a thread therefore reads from memory only what it cannot know: last iteration's
+// edge currents, the loads, and a parent's state when it returns from a subtree - none of which
+// depends on the arithmetic in flight.  The rows of event e+1 that come from DRAM (edge currents,
+// loads, parked sums) are requested while event e is computed, so a thread never sits in front of
+// a DRAM round trip with nothing to do; V rows are only ever stored (and re-read after a subtree).
+// Stores: every V row once per iteration with its forward value, plus the surviving rewrites;
+// every owned I row once (plus parked partial sums at the few branch points).
+//
+// Values: those of the two-sweep kernels up to the order in which a bus's child currents are
+// added (visit order instead of adjacency order: a rounding-level difference, <= 1e-15 relative);
+// iteration counts and status are the same (tests/test_fbs_gpu.py, tests/test_fbs_walk_host.py).
+// ---------------------------------------------------------------------------------------
+struct __align__(16) WalkEv {
+    int step;
+    int flags;      // 0-1 type; 2 VR edge; 3-5 bus phases; 6-8 I rows this step stores; 9-11 parent phases it rewrites;
+                    // 12-14 phases added to the parent's current sum; 15-17 phases with a load or capacitor;
+                    // 18-20 edge phases; 21-23 compile-time mask of a uniform step (0 = runtime masks)
+    int e_row[3];   // this step's I rows as addressed (shared rows resolved), -1 = none / always zero
+    int ld_i[3];    // rows requested ahead into oI: DESC/LEAF last iteration's edge current, ASC the parent's parked sum
+    int ld_v[3];    // ASC: the parent's V rows to take back (-1: phase rewritten by this step, or absent)
+    int st_ca[3];   // DESC: rows to park the parent's partial current sum in (-1: nothing to park)
+    int ld_s[3];    // LEAF/ASC: load rows of the bus (-1: none)
+    int pad[3];
+};
+static_assert(sizeof(WalkEv) == 80, "WalkEv layout");
+constexpr int WK_DESC = 0, WK_LEAF = 1, WK_ASC = 2;
+
+__device__ __forceinline__ WalkEv walk_ld_event(const WalkEv* __restrict__ e) {
+    WalkEv r;
+    const int4* q = reinterpret_cast<const int4*>(e);
+    const int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), f = __ldg(q + 4);
+    r.step = a.x; r.flags = a.y; r.e_row[0] = a.z; r.e_row[1] = a.w;
+    r.e_row[2] = b.x; r.ld_i[0] = b.y; r.ld_i[1] = b.z; r.ld_i[2] = b.w;
+    r.ld_v[0] = c.x; r.ld_v[1] = c.y; r.ld_v[2] = c.z; r.st_ca[0] = c.w;
+    r.st_ca[1] = d.x; r.st_ca[2] = d.y; r.ld_s[0] = d.z; r.ld_s[1] = d.w;
+    r.ld_s[2] = f.x; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    return r;
+}
+
+// ZIP load + capacitor current of one bus phase (calc_sV solution.py:177-220, update_current :256-288)
+__device__ __forceinline__ double2 walk_load_current(const double2 v, const double2 sp, const double cap, const FbsConst& k) {
+    double a;
+    const double a2 = cabs2(v, a);
+    const double f = k.aPQ + k.aI * a + k.aZ * a2;
+    double2 sv = make_double2(sp.x * f, sp.y * f);
+    sv.y -= cap * a2;
+    double2 r = make_double2(0.0, 0.0);
+    if (v.x != 0.0 || v.y != 0.0) {
+        const double inv = 1.0 / fma(v.x, v.x, v.y * v.y);
+        r.x = (sv.x * v.x + sv.y * v.y) * inv;
+        r.y = -((sv.y * v.x - sv.x * v.y) * inv);
+    }
+    return r;
+}
+
+// One event.  M != 0: the step is uniform (bus phases = edge phases = M, all present on the parent) and M is a
+// compile-time constant; M == 0: every mask is read from the event's flags.
+template <int M>
+__device__ __forceinline__ void walk_event(const WalkEv& ev, const FbsStep* __restrict__ st, const FbsConst& k,
+                                           const GMem& m, const bool first, double2 (&cv)[3], double2 (&ca)[3],
+                                           const double2 (&oI)[3], const double2 (&oS)[3]) {
+    const double2 zero = make_double2(0.0, 0.0);
+    const int fl = ev.flags, type = fl & 3;
+    const int mb = M ? M : (fl >> 3) & 7, me = M ? M : (fl >> 18) & 7;
+    const int ms = (fl >> 6) & 7, mw = (fl >> 9) & 7, mc = (fl >> 12) & 7, ml = (fl >> 15) & 7;
+    const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
+    const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
+    const int brow[3] = {bv.x, bv.y, bv.z}, prow[3] = {pv.x, pv.y, pv.z};
+    if (type == WK_DESC) {
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+            if (ev.st_ca[p] >= 0) m.stI(ev.st_ca[p], ca[p]);            // park the parent's partial current sum
+    }
+    // the parent's V rows this event takes back from memory at its end: requested now
+    double2 rV[3];
+    if (type == WK_ASC) {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) rV[p] = ev.ld_v[p] >= 0 ? m.ldV(ev.ld_v[p]) : zero;
+    }
+    if (fl & 4) {   // regulator edge: vr_forward :138-160, vr_backward :186-205, no current (vr_current leaves Itx = 0)
+        double2 b[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            b[p] = cv[p];
+            if (type != WK_ASC) {
+                const double g = __ldg(&st->gamma[p]);
+                b[p] = ((mb >> p) & 1) ? make_double2(g * cv[p].x, g * cv[p].y) : zero;
+                if ((mb >> p) & 1) m.stV(brow[p], b[p]);
+            }
+        }
+        if (type == WK_DESC) {
+#pragma unroll
+            for (int p = 0; p < 3; ++p) { cv[p] = b[p]; ca[p] = zero; }
+            return;
+        }
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            double2 nv = zero;
+            if ((mw >> p) & 1) {
+                const double ig = __ldg(&st->inv_gamma[p]);
+                nv = make_double2(ig * b[p].x, ig * b[p].y);
+                m.stV(prow[p], nv);
+            }
+            if (type == WK_ASC) {
+                cv[p] = ((mw >> p) & 1) ? nv : rV[p];
+                ca[p] = oI[p];
+            } else if ((mw >> p) & 1) {
+                cv[p] = nv;
+            }
+        }
+        return;
+    }
+    // ---- forward step on the way down (update_voltage_forward :162-184) ----
+    double2 b[3];
+    if (type != WK_ASC) {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            b[p] = zero;
+            if ((mb >> p) & 1) {
+                double2 v = cv[p];
+                if (!first) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                        if ((me >> q) & 1) {
+                            const double2 z = __ldg(&st->z[3 * p + q]);
+                            v.x -= z.x * oI[q].x - z.y * oI[q].y;
+                            v.y -= z.x * oI[q].y + z.y * oI[q].x;
+                        }
+                }
+                m.stV(brow[p], v);
+                b[p] = v;
+            }
+        }
+        if (type == WK_DESC) {
+#pragma unroll
+            for (int p = 0; p < 3; ++p) { cv[p] = b[p]; ca[p] = zero; }
+            return;
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) b[p] = cv[p];
+    }
+    // ---- backward step (calc_sV, update_current, update_voltage_backward) of a leaf or on the way up ----
+    double2 In[3];
+    double sum = 0.0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        In[p] = zero;
+        if ((me >> p) & 1) {
+            if (type == WK_ASC) In[p] = ca[p];
+            if ((ml >> p) & 1) {
+                const double2 q = walk_load_current(b[p], oS[p], __ldg(&st->cap[p]), k);
+                In[p].x += q.x;
+                In[p].y += q.y;
+            } else {
+                // no load, no capacitor: conj(0 / V) adds an exact zero - unless V is not finite, in which case the
+                // reference's 0 * inf makes the whole current NaN (and nan_to_num then zeroes it): x - x does both
+                const double t = (b[p].x - b[p].x) + (b[p].y - b[p].y);
+                In[p].x += t;
+                In[p].y += t;
+            }
+            sum += fabs(In[p].x) + fabs(In[p].y);
+        }
+    }
+    if (!(sum <= 1.7976931348623157e308)) {             // nan_to_num (:288) acts on non-finite values only
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+            if ((me >> p) & 1) In[p] = make_double2(nan_to_num(In[p].x), nan_to_num(In[p].y));
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+        if ((ms >> p) & 1) m.stI(ev.e_row[p], In[p]);
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        double2 nv = zero;
+        if ((mw >> p) & 1) {
+            nv = b[p];
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if ((me >> q) & 1) {
+                    const double2 z = __ldg(&st->z[3 * p + q]);
+                    nv.x += z.x * In[q].x - z.y * In[q].y;
+                    nv.y += z.x * In[q].y + z.y * In[q].x;
+                }
+            m.stV(prow[p], nv);
+        }
+        if (type == WK_ASC) {           // the parent is the current bus again
+            cv[p] = ((mw >> p) & 1) ? nv : rV[p];
+            ca[p] = oI[p];
+        } else if ((mw >> p) & 1) {
+            cv[p] = nv;
+        }
+        if ((mc >> p) & 1) {
+            ca[p].x += In[p].x;
+            ca[p].y += In[p].y;
+        }
+    }
+}
+
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+fbs_walk_kernel(const FbsStep* __restrict__ steps, const WalkEv* __restrict__ events, int n_events, FbsConst k,
+                int n_vrows, int n_irows, long long S, unsigned ldb, const char* __restrict__ spu, char* __restrict__ V,
+                char* __restrict__ I, int* __restrict__ iters_out, int* __restrict__ status_out,
+                double* __restrict__ diff_out, double tol, int maxiter, const int2* __restrict__ alias, int n_alias) {
+    const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (s >= S) return;
+    const GMem m{V + s * 16, I + s * 16, spu + s * 16, ldb, nullptr, nullptr};
+    const double2 zero = make_double2(0.0, 0.0);
+    int it = 0;
+    double diff = -1.0;
+    bool converged = false;
+    while (!converged && it < maxiter) {
+        const bool first = it == 0;     // flat start: the currents are zero and are not read
+        double2 cv[3], ca[3], pI[3], pS[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            cv[p] = k.vref[p];                              // V[root] = Vref (:89)
+            m.stV(k.root_vrow[p], k.vref[p]);
+            ca[p] = zero;
+        }
+        // operands of event e that come from DRAM (last iteration's edge currents / a parked sum, the loads) are
+        // requested one event ahead: only the row numbers of event e + 1 are read here, not its whole record
+        auto request = [&](const WalkEv* __restrict__ ne) {
+            const int4* q = reinterpret_cast<const int4*>(ne);
+            const int4 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 3), f = __ldg(q + 4);
+            const bool skip_i = first && (a.y & 3) != WK_ASC;
+            pI[0] = (b.y >= 0 && !skip_i) ? m.ldI(b.y) : zero;
+            pI[1] = (b.z >= 0 && !skip_i) ? m.ldI(b.z) : zero;
+            pI[2] = (b.w >= 0 && !skip_i) ? m.ldI(b.w) : zero;
+            pS[0] = d.z >= 0 ? m.ldS(d.z) : zero;
+            pS[1] = d.w >= 0 ? m.ldS(d.w) : zero;
+            pS[2] = f.x >= 0 ? m.ldS(f.x) : zero;
+        };
+        request(events);
+        for (int e = 0; e < n_events; ++e) {
+            const WalkEv ev = walk_ld_event(events + e);
+            double2 oI[3], oS[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) { oI[p] = pI[p]; oS[p] = pS[p]; }
+            if (e + 1 < n_events) request(events + e + 1);
+            const FbsStep* st = steps + ev.step;
+            switch ((ev.flags >> 21) & 7) {
+                case 7: walk_event<7>(ev, st, k, m, first, cv, ca, oI, oS); break;
+                case 1: walk_event<1>(ev, st, k, m, first, cv, ca, oI, oS); break;
+                case 2: walk_event<2>(ev, st, k, m, first, cv, ca, oI, oS); break;
+                case 4: walk_event<4>(ev, st, k, m, first, cv, ca, oI, oS); break;
+                default: walk_event<0>(ev, st, k, m, first, cv, ca, oI, oS); break;
+            }
+        }
+        ++it;
+        // root mismatch (:123-128) from the registers: the root is the current bus after the last event
+        diff = 0.0;
+        bool nan = false;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const double dx = cv[p].x - k.vref[p].x, dy = cv[p].y - k.vref[p].y;
+            const double d = sqrt(fma(dx, dx, dy * dy));
+            nan |= (d != d);
+            diff = fmax(diff, d);
+        }
+        if (nan) diff = __longlong_as_double(0x7ff8000000000000LL);
+        converged = diff <= tol;
+    }
+    for (int j = 0; j < n_alias; ++j) {         // shared I rows: the caller's array gets every row, once
+        const int2 a = __ldg(alias + j);
+        m.stI(a.x, a.y >= 0 ? m.ldI(a.y) : zero);
+    }
+    iters_out[s] = it;
+    diff_out[s] = diff;
+    status_out[s] = fbs_status(converged, diff);
+}
+
 // Derived results: sV, |V| per V row; Stx/Srx per line row; loss per scenario.
 __global__ void fbs_post_rows_kernel(int n_vrows, const int* __restrict__ vrow_srow,
                                      const double* __restrict__ vrow_cap, FbsConst k, long long S,
@@ -1059,7 +1387,11 @@ extern "C" int gp_last_error(char* buf, size_t len) {
 extern "C" int64_t gp_launch_count(void) { return g_launches.load(); }
 
 extern "C" int gp_set_option(const char* name, int value) {
-    if (name && strcmp(name, "fbs_kernel") == 0 && value >= 0 && value <= 5) {
+    if (name && strcmp(name, "fbs_walk_blocks") == 0 && (value == 4 || value == 5 || value == 6 || value == 8)) {
+        g_fbs_walk_blocks = value;
+        return GP_OK;
+    }
+    if (name && strcmp(name, "fbs_kernel") == 0 && value >= 0 && value <= 6) {
         g_fbs_kernel = value;
         return GP_OK;
     }
@@ -1069,6 +1401,10 @@ extern "C" int gp_set_option(const char* name, int value) {
     }
     if (name && strcmp(name, "fbs_share_rows") == 0 && (value == 0 || value == 1)) {
         g_fbs_share_rows = value;
+        return GP_OK;
+    }
+    if (name && strcmp(name, "fbs_order") == 0 && (value == 0 || value == 1)) {
+        g_fbs_order = value;
         return GP_OK;
     }
     if (name && strcmp(name, "nr3_kernel") == 0 && value >= 0 && value <= 2) {
@@ -1116,9 +1452,10 @@ extern "C" int gp_fbs_active_kernel(GpFeeder* f) {
     if (!f || f->kind != 1) return fail(GP_EINVAL, "gp_fbs_active_kernel: not an FBS feeder handle");
     const FbsImpl* im = (const FbsImpl*)f->impl;
     if (g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) return 5;
+    if ((g_fbs_kernel == 6 || g_fbs_kernel == 0) && im->n_walk > 0) return 6;
     if (g_fbs_kernel == 4) return 4;
     if (g_fbs_kernel == 2) return 2;
-    if (g_fbs_kernel == 1 && im->n_events > 0) return 1;
+    if (g_fbs_kernel == 1 && im->n_events > 0 && im->dfs_stack_ok) return 1;
     return 3;
 }
 
@@ -1230,6 +1567,24 @@ static int fbs_tables_from_desc(const GpFbsDesc* d, std::vector<FbsStep>& steps,
             mp |= (s.par_vrow[p] >= 0) << p;
         }
         if (mb != 0 && mb == me && (mp & mb) == mb) s.kind |= mb << 8;
+    }
+    // Dead parent-voltage stores (bits 19..21 of kind).  The backward sweep runs over reversed(topo_order) and
+    // every child rewrites the phases it shares with its parent (solution_fbs.py:207-232): of the children of a
+    // bus only the one EARLIEST in topo order survives per phase, nothing reads the others' values.  They are
+    // not stored (IEEE 123: about 40 % of the backward sweep's V stores), which is also what lets the kernel
+    // walk the tree depth-first on one V array.
+    {
+        std::vector<char> written((size_t)d->n_vrows, 0);
+        for (int i = 0; i < d->n_steps; ++i) {
+            FbsStep& s = steps[i];
+            const bool vr = (s.kind & 0xff) == GP_EDGE_VR;
+            for (int p = 0; p < 3; ++p) {
+                const bool stores = s.par_vrow[p] >= 0 && (vr ? s.gamma[p] != 0.0 : s.bus_vrow[p] >= 0);
+                if (!stores) continue;
+                if (written[s.par_vrow[p]]) s.kind |= 1 << (19 + p);
+                else written[s.par_vrow[p]] = 1;
+            }
+        }
     }
     for (int p = 0; p < 3; ++p) {
         k.root_vrow[p] = d->root_vrow[p];
@@ -1367,77 +1722,18 @@ extern "C" int gp_fbs_specialise(GpFeeder* f) {
     return GP_OK;
 }
 
-// Everything an FbsImpl owns (device tables, modules, staging, streams); also the error path of gp_fbs_create.
-static void fbs_impl_free(FbsImpl* im) {
-    if (!im) return;
-    cudaFree(im->d_steps);
-    cudaFree(im->d_child);
-    cudaFree(im->d_steps_a);
-    cudaFree(im->d_child_a);
-    cudaFree(im->d_alias);
-    cudaFree(im->d_lines);
-    cudaFree(im->d_vrow_srow);
-    cudaFree(im->d_vrow_cap);
-    cudaFree(im->d_events);
-    cudaFree(im->d_evrows);
-    cudaFree(im->d_sched);
-    cudaFree(im->d_unfed);
-    cudaFree(im->d_zc);
-    if (im->jit_module) driver().ModuleUnload(im->jit_module);
-    if (im->jit_module_host) driver().ModuleUnload(im->jit_module_host);
-    for (int i = 0; i < FbsImpl::NSTREAM; ++i) {
-        if (im->d_stage[i]) cudaFree(im->d_stage[i]);
-        if (im->streams[i]) cudaStreamDestroy(im->streams[i]);
-    }
-    delete im;
-}
-
-extern "C" int gp_feeder_destroy(GpFeeder* f) {
-    if (!f) return GP_OK;
-    cudaSetDevice(f->device);
-    if (f->kind == 1) {
-        fbs_impl_free((FbsImpl*)f->impl);
-    } else if (f->kind == 2) {
-        gp_nr3_destroy_impl(f->impl);
-    }
-    delete f;
-    return GP_OK;
-}
-
-extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
-    if (!d || !out) return fail(GP_EINVAL, "gp_fbs_create: null argument");
-    std::vector<FbsStep> steps;
-    std::vector<int4> child4;
-    std::vector<int> vrow_srow;
-    std::vector<double> vrow_cap;
-    FbsConst k0;
-    int rc0 = fbs_tables_from_desc(d, steps, child4, k0, vrow_srow, vrow_cap);
-    if (rc0) return rc0;
-    GP_CUDA(cudaSetDevice(device));
-    FbsImpl* im = new (std::nothrow) FbsImpl();
-    if (!im) return fail(GP_ENOMEM, "gp_fbs_create: out of host memory");
-    im->n_steps = d->n_steps;
-    im->n_vrows = d->n_vrows;
-    im->n_irows = d->n_irows;
-    im->n_srows = d->n_srows;
-    im->n_child = d->n_child;
-    im->n_lines = d->n_lines;
-    for (const FbsStep& st : steps)
-        for (int p = 0; p < 3; ++p) im->n_grows += st.gam_row[p] >= 0;
-    im->k = k0;
-    im->h_steps = steps;
-    im->h_child = child4;
-    std::vector<int> lines((size_t)d->n_lines * 9);
-    for (int l = 0; l < d->n_lines; ++l)
-        for (int p = 0; p < 3; ++p) {
-            lines[9 * l + p] = d->line_irow[3 * l + p];
-            lines[9 * l + 3 + p] = d->line_tx_vrow[3 * l + p];
-            lines[9 * l + 6 + p] = d->line_rx_vrow[3 * l + p];
-        }
-    im->h_lines = lines;
+// Depth-first schedule of the feeder: parent step of every step, children visited latest-in-topo-order first,
+// one descend and one ascend event {step, (level << 4) | flags} per step.  The streaming kernel runs its forward
+// and backward steps in this order (fbs_order); fbs_dfs_kernel additionally keeps the path state on a stack, for
+// which regulators must cover every phase of their bus and the tree must be at most 64 deep (stack_ok).
+// Empty when the step table is not a tree in topo order.
+static void fbs_build_events(const GpFbsDesc* d, const std::vector<FbsStep>& steps, std::vector<int2>& events,
+                             int& depth_out, bool& stack_ok) {
+    events.clear();
+    depth_out = 0;
+    stack_ok = true;
     // depth-first schedule for fbs_dfs_kernel: parent step of every step, children visited
     // latest-in-topo-order first, {step, 2*level + ascend} events.
-    std::vector<int2> events;
     {
         std::vector<int> row_step((size_t)d->n_vrows, -2);
         for (int p = 0; p < 3; ++p) row_step[d->root_vrow[p]] = -1;
@@ -1452,9 +1748,9 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
                 if (steps[i].par_vrow[p] >= 0) par = row_step[steps[i].par_vrow[p]];
             if (par < -1 || par >= i) ok = false;                     // parents come first in topo order
             else kids[par + 1].push_back(i);
-            if ((steps[i].kind & 0xff) == GP_EDGE_VR)                 // regulator must cover every bus phase
+            if ((steps[i].kind & 0xff) == GP_EDGE_VR)                 // fbs_dfs_kernel: a regulator must cover every bus phase
                 for (int p = 0; p < 3; ++p)
-                    if (steps[i].bus_vrow[p] >= 0 && steps[i].gamma[p] == 0.0) ok = false;
+                    if (steps[i].bus_vrow[p] >= 0 && steps[i].gamma[p] == 0.0) stack_ok = false;
         }
         if (ok) {
             // Flags: what the parent must keep across this child's subtree.
@@ -1503,11 +1799,289 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
                     stack.pop_back();
                 }
             }
-            im->depth = depth;
-            if ((int)events.size() != 2 * d->n_steps || depth > 64) events.clear();
+            depth_out = depth;
+            if ((int)events.size() != 2 * d->n_steps) events.clear();
+            if (depth > 64) stack_ok = false;
         }
-        im->n_events = (int)events.size();
     }
+}
+
+// Host-only view of what the kernels are given for a feeder (no device needed): the depth-first event list
+// and the per-step `kind` words with their flag bits (8..15 fast mask, 19..21 dead parent stores).  Used by the
+// CPU tests, which run the kernel's loop over exactly these tables in NumPy.
+extern "C" int gp_fbs_schedule(const GpFbsDesc* d, int32_t* events_out, int32_t* kind_out) {
+    if (!d) return fail(GP_EINVAL, "gp_fbs_schedule: null descriptor");
+    std::vector<FbsStep> steps;
+    std::vector<int4> child4;
+    std::vector<int> vrow_srow;
+    std::vector<double> vrow_cap;
+    FbsConst k;
+    int rc = fbs_tables_from_desc(d, steps, child4, k, vrow_srow, vrow_cap);
+    if (rc) return rc;
+    std::vector<int2> events;
+    int depth = 0;
+    bool stack_ok = true;
+    fbs_build_events(d, steps, events, depth, stack_ok);
+    if (events_out)
+        for (size_t e = 0; e < events.size(); ++e) {
+            events_out[2 * e] = events[e].x;
+            events_out[2 * e + 1] = events[e].y;
+        }
+    if (kind_out)
+        for (size_t i = 0; i < steps.size(); ++i) kind_out[i] = steps[i].kind;
+    return (int)events.size();
+}
+
+
+// Event table of fbs_walk_kernel from the step tables with shared I rows (steps_a: alias rows resolved, rows that
+// stay zero dropped, bits 16-18 = rows this step does not store) - see the kernel for what each field means.
+// Empty when the feeder cannot be walked this way (not a tree in topo order, a V row that no forward step writes).
+static void fbs_build_walk(const GpFbsDesc* d, const std::vector<FbsStep>& steps, const std::vector<FbsStep>& steps_a,
+                           int n_unfed, std::vector<WalkEv>& out) {
+    out.clear();
+    const int n = d->n_steps;
+    if (n_unfed > 0 || n == 0) return;
+    std::vector<int> row_step((size_t)d->n_vrows, -2);
+    for (int p = 0; p < 3; ++p) row_step[d->root_vrow[p]] = -1;
+    for (int i = 0; i < n; ++i)
+        for (int p = 0; p < 3; ++p)
+            if (steps[i].bus_vrow[p] >= 0) row_step[steps[i].bus_vrow[p]] = i;
+    std::vector<int> par((size_t)n, -2);
+    std::vector<std::vector<int>> kids((size_t)n + 1);       // index 0 = root; children latest-in-topo-order first
+    for (int i = 0; i < n; ++i) {
+        for (int p = 0; p < 3; ++p)
+            if (steps[i].par_vrow[p] >= 0) par[i] = row_step[steps[i].par_vrow[p]];
+        if (par[i] < -1 || par[i] >= i) return;
+        kids[par[i] + 1].push_back(i);
+    }
+    for (auto& ks : kids) std::sort(ks.begin(), ks.end(), std::greater<int>());
+    // V rows of a bus (step or root) by phase
+    auto vrow_of = [&](int node, int p) { return node < 0 ? d->root_vrow[p] : steps[node].bus_vrow[p]; };
+    struct Frame { int node, next; };
+    std::vector<Frame> stack;
+    stack.push_back({-1, 0});
+    auto base_event = [&](int c, int type) {
+        WalkEv ev;
+        memset(&ev, 0, sizeof(ev));
+        const FbsStep& st = steps[c];
+        const FbsStep& sa = steps_a[c];
+        const bool vr = (st.kind & 0xff) == GP_EDGE_VR;
+        ev.step = c;
+        int mb = 0, me = 0, ms = 0, mw = 0, mc = 0, ml = 0;
+        for (int p = 0; p < 3; ++p) {
+            ev.e_row[p] = vr ? -1 : sa.edge_irow[p];
+            ev.ld_i[p] = ev.ld_v[p] = ev.st_ca[p] = ev.ld_s[p] = -1;
+            if (st.bus_vrow[p] >= 0) mb |= 1 << p;
+            if (ev.e_row[p] >= 0) {
+                me |= 1 << p;
+                if (!((sa.kind >> (16 + p)) & 1)) ms |= 1 << p;
+                // every line-kind child adds its edge current to the sum of its parent (:274-284); a parent
+                // without that edge phase discards it
+                if (par[c] >= 0 && (steps[par[c]].kind & 0xff) != GP_EDGE_VR && steps_a[par[c]].edge_irow[p] >= 0) mc |= 1 << p;
+            }
+            const bool stores = st.par_vrow[p] >= 0 && (vr ? st.gamma[p] != 0.0 : st.bus_vrow[p] >= 0);
+            if (stores && !((st.kind >> (19 + p)) & 1)) mw |= 1 << p;
+            if (st.bus_vrow[p] >= 0 && (st.load_srow[p] >= 0 || st.cap[p] != 0.0)) ml |= 1 << p;
+            if (type != WK_DESC && !vr) ev.ld_s[p] = st.bus_vrow[p] >= 0 ? st.load_srow[p] : -1;
+            if (type != WK_ASC) ev.ld_i[p] = ev.e_row[p];       // last iteration's edge current
+        }
+        int uni = 0;    // compile-time mask: bus phases = edge phases, all on the parent, a Line edge
+        if (!vr && mb != 0 && mb == me && (mb == 7 || mb == 1 || mb == 2 || mb == 4)) {
+            bool on_parent = true;
+            for (int p = 0; p < 3; ++p)
+                if (((mb >> p) & 1) && st.par_vrow[p] < 0) on_parent = false;
+            if (on_parent) uni = mb;
+        }
+        ev.flags = type | (vr ? 4 : 0) | (mb << 3) | (ms << 6) | (mw << 9) | (mc << 12) | (ml << 15) | (me << 18) | (uni << 21);
+        return ev;
+    };
+    // contributed[node + 1][p]: a child visited so far has added to phase p of the bus's current sum
+    std::vector<int> contributed((size_t)n + 1, 0);
+    while (!stack.empty()) {
+        Frame& f = stack.back();
+        auto& ks = kids[f.node + 1];
+        if (f.next < (int)ks.size()) {
+            const int c = ks[f.next++];
+            const bool leaf = kids[c + 1].empty();
+            WalkEv ev = base_event(c, leaf ? WK_LEAF : WK_DESC);
+            const int k = f.node;
+            if (leaf) {
+                contributed[k + 1] |= (ev.flags >> 12) & 7;
+                out.push_back(ev);
+            } else {
+                // park the parent's partial sum: owner rows of its edge that already hold contributions
+                if (k >= 0)
+                    for (int p = 0; p < 3; ++p)
+                        if (((contributed[k + 1] >> p) & 1) && steps_a[k].edge_irow[p] >= 0 &&
+                            !((steps_a[k].kind >> (16 + p)) & 1))
+                            ev.st_ca[p] = steps_a[k].edge_irow[p];
+                out.push_back(ev);
+                stack.push_back({c, 0});
+            }
+        } else {
+            const int c = f.node;
+            stack.pop_back();
+            if (c < 0) break;
+            const int k = stack.back().node;
+            WalkEv ev = base_event(c, WK_ASC);
+            const int mw = (ev.flags >> 9) & 7;
+            for (int p = 0; p < 3; ++p) {
+                ev.ld_i[p] = -1;
+                if (k >= 0 && ((contributed[k + 1] >> p) & 1)) ev.ld_i[p] = steps_a[k].edge_irow[p];   // parked sum / shared row
+                const int vr = vrow_of(k, p);
+                ev.ld_v[p] = (vr >= 0 && !((mw >> p) & 1)) ? vr : -1;
+            }
+            contributed[k + 1] |= (ev.flags >> 12) & 7;
+            out.push_back(ev);
+        }
+    }
+    if ((int)out.size() < n || (int)out.size() > 2 * n) out.clear();
+}
+
+// Host only: the event table of the tree-walk kernel for a descriptor, 20 int32 per event (struct WalkEv in
+// gp_fbs.cu: step, flags, e_row[3], ld_i[3], ld_v[3], st_ca[3], ld_s[3], pad[3]) together with the step tables the
+// kernel addresses (shared I rows resolved): edge_rows_out[n_steps][3].  Returns the number of events (0: the
+// feeder is not walked) or a negative GP_E*.  The CPU tests run the kernel's loop over this table in NumPy.
+static void fbs_shared_tables(const std::vector<FbsStep>& steps, const std::vector<int4>& child4, int n_irows,
+                              std::vector<FbsStep>& steps_a, std::vector<int4>& child_a, std::vector<int2>& alias);
+static void fbs_unfed_rows(const GpFbsDesc* d, const std::vector<FbsStep>& steps, std::vector<int>& unfed);
+
+extern "C" int gp_fbs_walk_events(const GpFbsDesc* d, int32_t* events_out, int64_t cap_events) {
+    if (!d) return fail(GP_EINVAL, "gp_fbs_walk_events: null descriptor");
+    std::vector<FbsStep> steps, steps_a;
+    std::vector<int4> child4, child_a;
+    std::vector<int2> alias;
+    std::vector<int> vrow_srow, unfed;
+    std::vector<double> vrow_cap;
+    FbsConst k;
+    int rc = fbs_tables_from_desc(d, steps, child4, k, vrow_srow, vrow_cap);
+    if (rc) return rc;
+    fbs_shared_tables(steps, child4, d->n_irows, steps_a, child_a, alias);
+    fbs_unfed_rows(d, steps, unfed);
+    std::vector<WalkEv> ev;
+    fbs_build_walk(d, steps, steps_a, (int)unfed.size(), ev);
+    if (events_out) {
+        if ((int64_t)ev.size() > cap_events) return fail(GP_EINVAL, "gp_fbs_walk_events: buffer too small");
+        memcpy(events_out, ev.data(), ev.size() * sizeof(WalkEv));
+    }
+    return (int)ev.size();
+}
+
+// Everything an FbsImpl owns (device tables, modules, staging, streams); also the error path of gp_fbs_create.
+static void fbs_impl_free(FbsImpl* im) {
+    if (!im) return;
+    cudaFree(im->d_steps);
+    cudaFree(im->d_child);
+    cudaFree(im->d_steps_a);
+    cudaFree(im->d_child_a);
+    cudaFree(im->d_alias);
+    cudaFree(im->d_lines);
+    cudaFree(im->d_vrow_srow);
+    cudaFree(im->d_vrow_cap);
+    cudaFree(im->d_events);
+    cudaFree(im->d_evrows);
+    cudaFree(im->d_sched);
+    cudaFree(im->d_unfed);
+    cudaFree(im->d_walk);
+    cudaFree(im->d_zc);
+    if (im->jit_module) driver().ModuleUnload(im->jit_module);
+    if (im->jit_module_host) driver().ModuleUnload(im->jit_module_host);
+    for (int i = 0; i < FbsImpl::NSTREAM; ++i) {
+        if (im->d_stage[i]) cudaFree(im->d_stage[i]);
+        if (im->streams[i]) cudaStreamDestroy(im->streams[i]);
+    }
+    delete im;
+}
+
+extern "C" int gp_feeder_destroy(GpFeeder* f) {
+    if (!f) return GP_OK;
+    cudaSetDevice(f->device);
+    if (f->kind == 1) {
+        fbs_impl_free((FbsImpl*)f->impl);
+    } else if (f->kind == 2) {
+        gp_nr3_destroy_impl(f->impl);
+    }
+    delete f;
+    return GP_OK;
+}
+
+
+// The streaming kernels' tables with shared I rows (fbs_jit_islots has the rule): an I row of a bus-phase without
+// load and capacitor that is fed by exactly one child row IS that row's value (0 + I_child), so its forward
+// read goes to the child's row and its backward store is dropped (bits 16..18 of `kind`); one that nothing feeds
+// stays zero and leaves the tables altogether (the step then takes the generic body, which skips absent rows).
+// Per sweep that is one write and one read less per such row; `alias` lists {row, source row or -1} for the one
+// copy-out after the last sweep.
+static void fbs_shared_tables(const std::vector<FbsStep>& steps, const std::vector<int4>& child4, int n_irows,
+                              std::vector<FbsStep>& steps_a, std::vector<int4>& child_a, std::vector<int2>& alias) {
+    std::vector<int> slot;
+    std::vector<char> owner;
+    fbs_jit_islots(steps, child4, n_irows, slot, owner);
+    std::vector<int> owner_row(slot.size() + 1, -1);
+    for (size_t r = 0; r < slot.size(); ++r)
+        if (owner[r] && slot[r] >= 0) owner_row[slot[r]] = (int)r;
+    auto remap = [&](int r) { return (r < 0 || r >= n_irows) ? r : (slot[r] < 0 ? -1 : owner_row[slot[r]]); };
+    steps_a = steps;
+    child_a = child4;
+    alias.clear();
+    for (FbsStep& st : steps_a)
+        for (int p = 0; p < 3; ++p) {
+            const int r = st.edge_irow[p];
+            if (r < 0 || r >= n_irows || owner[r]) continue;
+            alias.push_back(make_int2(r, remap(r)));
+            st.edge_irow[p] = remap(r);
+            if (st.edge_irow[p] < 0) st.kind &= ~0xff00;        // a dropped row: no mask-specialised body
+            else st.kind |= 1 << (16 + p);
+        }
+    for (int4& c : child_a) c = make_int4(remap(c.x), remap(c.y), remap(c.z), c.w);
+}
+
+// V rows that no forward step writes (non-regulated phases below a regulator): they must hold the flat start's zero
+static void fbs_unfed_rows(const GpFbsDesc* d, const std::vector<FbsStep>& steps, std::vector<int>& unfed) {
+    std::vector<char> fed((size_t)d->n_vrows, 0);
+    for (int p = 0; p < 3; ++p) fed[d->root_vrow[p]] = 1;
+    for (const FbsStep& st : steps)
+        for (int p = 0; p < 3; ++p)
+            if (st.bus_vrow[p] >= 0 && ((st.kind & 0xff) != GP_EDGE_VR || st.gamma[p] != 0.0)) fed[st.bus_vrow[p]] = 1;
+    unfed.clear();
+    for (int r = 0; r < d->n_vrows; ++r)
+        if (!fed[r]) unfed.push_back(r);
+}
+
+extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
+    if (!d || !out) return fail(GP_EINVAL, "gp_fbs_create: null argument");
+    std::vector<FbsStep> steps;
+    std::vector<int4> child4;
+    std::vector<int> vrow_srow;
+    std::vector<double> vrow_cap;
+    FbsConst k0;
+    int rc0 = fbs_tables_from_desc(d, steps, child4, k0, vrow_srow, vrow_cap);
+    if (rc0) return rc0;
+    GP_CUDA(cudaSetDevice(device));
+    FbsImpl* im = new (std::nothrow) FbsImpl();
+    if (!im) return fail(GP_ENOMEM, "gp_fbs_create: out of host memory");
+    im->n_steps = d->n_steps;
+    im->n_vrows = d->n_vrows;
+    im->n_irows = d->n_irows;
+    im->n_srows = d->n_srows;
+    im->n_child = d->n_child;
+    im->n_lines = d->n_lines;
+    for (const FbsStep& st : steps)
+        for (int p = 0; p < 3; ++p) im->n_grows += st.gam_row[p] >= 0;
+    im->k = k0;
+    im->h_steps = steps;
+    im->h_child = child4;
+    std::vector<int> lines((size_t)d->n_lines * 9);
+    for (int l = 0; l < d->n_lines; ++l)
+        for (int p = 0; p < 3; ++p) {
+            lines[9 * l + p] = d->line_irow[3 * l + p];
+            lines[9 * l + 3 + p] = d->line_tx_vrow[3 * l + p];
+            lines[9 * l + 6 + p] = d->line_rx_vrow[3 * l + p];
+        }
+    im->h_lines = lines;
+    std::vector<int2> events;
+    fbs_build_events(d, steps, events, im->depth, im->dfs_stack_ok);
+    im->n_events = (int)events.size();
     std::vector<int4> evrows(events.size());
     for (size_t e = 0; e < events.size(); ++e) {
         const FbsStep& st = steps[events[e].x];
@@ -1526,32 +2100,11 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
     if (e == cudaSuccess) e = up((void**)&im->d_evrows, evrows.data(), evrows.size() * sizeof(int4));
     if (e == cudaSuccess) e = up((void**)&im->d_child, child4.data(), child4.size() * sizeof(int4));
     if (e == cudaSuccess) e = up((void**)&im->d_lines, lines.data(), lines.size() * sizeof(int));
-    {   // the streaming kernel's tables with shared I rows (fbs_jit_islots has the rule): an I row of a
-        // bus-phase without load and capacitor that is fed by exactly one child row IS that row's value
-        // (0 + I_child), so its forward read goes to the child's row and its backward store is dropped
-        // (bits 16..18 of `kind`); one that nothing feeds stays zero and leaves the tables altogether
-        // (the step then takes the generic body, which skips absent rows).  Per sweep that is one write
-        // and one read less per such row; the rows themselves are filled in once after the last sweep.
-        std::vector<int> slot;
-        std::vector<char> owner;
-        fbs_jit_islots(steps, child4, d->n_irows, slot, owner);
-        std::vector<int> owner_row(slot.size() + 1, -1);
-        for (size_t r = 0; r < slot.size(); ++r)
-            if (owner[r] && slot[r] >= 0) owner_row[slot[r]] = (int)r;
-        auto remap = [&](int r) { return (r < 0 || r >= d->n_irows) ? r : (slot[r] < 0 ? -1 : owner_row[slot[r]]); };
-        std::vector<FbsStep> steps_a = steps;
-        std::vector<int4> child_a = child4;
+    std::vector<FbsStep> steps_a;
+    std::vector<int4> child_a;
+    {
         std::vector<int2> alias;
-        for (FbsStep& st : steps_a)
-            for (int p = 0; p < 3; ++p) {
-                const int r = st.edge_irow[p];
-                if (r < 0 || r >= d->n_irows || owner[r]) continue;
-                alias.push_back(make_int2(r, remap(r)));
-                st.edge_irow[p] = remap(r);
-                if (st.edge_irow[p] < 0) st.kind &= ~0xff00;        // a dropped row: no mask-specialised body
-                else st.kind |= 1 << (16 + p);
-            }
-        for (int4& c : child_a) c = make_int4(remap(c.x), remap(c.y), remap(c.z), c.w);
+        fbs_shared_tables(steps, child4, d->n_irows, steps_a, child_a, alias);
         im->n_alias = (int)alias.size();
         if (e == cudaSuccess) e = up((void**)&im->d_steps_a, steps_a.data(), steps_a.size() * sizeof(FbsStep));
         if (e == cudaSuccess) e = up((void**)&im->d_child_a, child_a.data(), child_a.size() * sizeof(int4));
@@ -1559,17 +2112,15 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
     }
     if (e == cudaSuccess) e = up((void**)&im->d_vrow_srow, vrow_srow.data(), vrow_srow.size() * sizeof(int));
     if (e == cudaSuccess) e = up((void**)&im->d_vrow_cap, vrow_cap.data(), vrow_cap.size() * sizeof(double));
-    {   // V rows that no forward step writes: they must hold the flat start's zero
-        std::vector<char> fed((size_t)d->n_vrows, 0);
-        for (int p = 0; p < 3; ++p) fed[d->root_vrow[p]] = 1;
-        for (const FbsStep& st : steps)
-            for (int p = 0; p < 3; ++p)
-                if (st.bus_vrow[p] >= 0 && ((st.kind & 0xff) != GP_EDGE_VR || st.gamma[p] != 0.0)) fed[st.bus_vrow[p]] = 1;
+    {
         std::vector<int> unfed;
-        for (int r = 0; r < d->n_vrows; ++r)
-            if (!fed[r]) unfed.push_back(r);
+        fbs_unfed_rows(d, steps, unfed);
         im->n_unfed = (int)unfed.size();
         if (e == cudaSuccess) e = up((void**)&im->d_unfed, unfed.data(), unfed.size() * sizeof(int));
+        std::vector<WalkEv> walk;
+        fbs_build_walk(d, steps, steps_a, im->n_unfed, walk);
+        im->n_walk = (int)walk.size();
+        if (e == cudaSuccess) e = up((void**)&im->d_walk, walk.data(), walk.size() * sizeof(WalkEv));
     }
     if (e == cudaSuccess) e = cudaMalloc((void**)&im->d_sched, (FbsImpl::NSCHED + 1) * 16);
     if (e == cudaSuccess) e = cudaMemset(im->d_sched, 0, (FbsImpl::NSCHED + 1) * 16);
@@ -1727,7 +2278,7 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int BLOCK = 128;
     const unsigned gx = (unsigned)((S + BLOCK - 1) / BLOCK);
-    const bool dfs = im->n_events > 0 && g_fbs_kernel == 1;
+    const bool dfs = im->n_events > 0 && im->dfs_stack_ok && g_fbs_kernel == 1;
     const unsigned ldb = (unsigned)(ld * 16);
     // automatic choice: the feeder-specialised on-chip kernel when gp_fbs_specialise has built it,
     // else the two-sweep kernel that streams the state through HBM.  (The table-driven on-chip
@@ -1741,7 +2292,8 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
         fbs_solve_kernel<BLOCK, true><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
                                                             im->n_irows, S, ldb, (const char*)spu, (char*)V,
                                                             (char*)I, iters, status, diff, tol, maxiter, g_fbs_prefetch,
-                                                            im->d_unfed, im->n_unfed, gam, warm, wpu, nullptr, 0);
+                                                            im->d_unfed, im->n_unfed, gam, warm, wpu, nullptr, 0,
+                                                            im->d_events, g_fbs_order ? im->n_events : 0);
     } else if ((g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) && (maxiter >= 1 || !im->jit_kernel)) {
         if (!im->jit_kernel)
             return fail(GP_EINVAL, "gp_fbs_solve_batch: fbs_kernel = 5 needs a successful gp_fbs_specialise");
@@ -1795,14 +2347,30 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
         else if (im->depth <= 32) GP_DFS(32);
         else GP_DFS(64);
 #undef GP_DFS
+    } else if ((g_fbs_kernel == 6 || g_fbs_kernel == 0) && im->n_walk > 0 && maxiter >= 1) {
+        // tree walk with the state of the current bus in registers (always on the shared-row tables)
+#define GP_WALK(MINB)                                                                                                   \
+    fbs_walk_kernel<BLOCK, MINB><<<gx, BLOCK, 0, st>>>(im->d_steps_a, (const WalkEv*)im->d_walk, im->n_walk, im->k,     \
+                                                       im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V,    \
+                                                       (char*)I, iters, status, diff, tol, maxiter, im->d_alias,        \
+                                                       im->n_alias)
+        switch (g_fbs_walk_blocks) {
+            case 8: GP_WALK(8); break;
+            case 6: GP_WALK(6); break;
+            case 5: GP_WALK(5); break;
+            default: GP_WALK(4); break;
+        }
+#undef GP_WALK
     } else {
+        if (g_fbs_kernel == 6) return fail(GP_EINVAL, "gp_fbs_solve_batch: fbs_kernel = 6 needs a feeder the tree-walk kernel takes");
         const bool share = g_fbs_share_rows && im->n_alias > 0;
         fbs_solve_kernel<BLOCK, false><<<gx, BLOCK, 0, st>>>(share ? im->d_steps_a : im->d_steps,
                                                              share ? im->d_child_a : im->d_child, im->k, im->n_steps,
                                                              im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V,
                                                              (char*)I, iters, status, diff, tol, maxiter, g_fbs_prefetch,
                                                              im->d_unfed, im->n_unfed, nullptr, 0, nullptr,
-                                                             share ? im->d_alias : nullptr, share ? im->n_alias : 0);
+                                                             share ? im->d_alias : nullptr, share ? im->n_alias : 0,
+                                                             im->d_events, g_fbs_order ? im->n_events : 0);
     }
     count_launch();
     GP_CUDA(cudaGetLastError());

@@ -65,8 +65,11 @@ struct FbsImpl {
     int2* d_events = nullptr;
     int4* d_evrows = nullptr;   // per event: the 3 rows to prefetch, .w = 1 for I rows (descend), 0 for spu rows
     int n_events = 0, depth = 0;
+    bool dfs_stack_ok = true;     // fbs_dfs_kernel's extra conditions (regulators cover their bus, depth <= 64)
     // on-chip kernel (fbs_onchip_kernel): tile scheduler words {next tile, warps done}, SM count,
     // warps per block that fit the feeder's V and I rows in shared memory (0 = does not fit)
+    void* d_walk = nullptr;       // event table of fbs_walk_kernel (WalkEv[n_walk]); n_walk = 0: the feeder is not walked
+    int n_walk = 0;
     int* d_unfed = nullptr;       // V rows no forward step writes (kept at the flat start's zero)
     int n_unfed = 0;
     // One pair of self-resetting scheduler words PER STREAM (sched_words()): the words are only correct for

@@ -116,6 +116,16 @@ int64_t gp_launch_count(void);
  * "fbs_share_rows": 1 (default) = in the streaming FBS kernel an I row that only repeats a child's current (a
  *   bus-phase without load and capacitor fed by one child edge) or stays zero makes no HBM round trips during
  *   the sweeps and is filled in once at the end; 0 = every row is stored and re-read each sweep.  Same results.
+ * "fbs_kernel" 6 / automatic for feeders without a specialised kernel: the tree-walk kernel - the depth-first
+ *   order below with the state of the bus the walk stands on held in registers and next-event operands requested
+ *   ahead; "fbs_walk_blocks" (4, 5, 6, 8) = resident 128-thread blocks per SM it is compiled for (128 / 96 / 80 /
+ *   64 registers per thread).  Per-scenario extras (taps, warm start, wpu) run on the two-sweep kernel.
+ * "fbs_order": 1 (default) = the streaming FBS kernel runs a bus's forward step when a depth-first walk of the
+ *   tree descends its edge and its backward step when the walk comes back up (children latest in topo order
+ *   first); 0 = two full sweeps as the reference writes them (solution_fbs.py:92-121).  Same steps, same rows,
+ *   same values - a forward step only ever sees its parent's forward voltage because of a bus's children only
+ *   the earliest in topo order rewrites a phase of the parent, and that child is visited last - but a bus's
+ *   voltage is re-read a few steps after it was written (an L2 hit) instead of a whole sweep later (DRAM).
  * "host_warps": warps per SM of the one-launch host path's kernel build (1..8, default 4; read when that build is
  *   made, i.e. at the first gp_fbs_solve_batch_host call of a handle).  The host path is PCIe-bound and a smaller
  *   wave of warps shortens the part of a call in which only one PCIe direction is busy.
@@ -156,6 +166,24 @@ int gp_fbs_onchip_warps(GpFeeder* f);
  *                         to *cubin_bytes, the cubin itself into cubin (cap bytes) when not NULL
  */
 int gp_fbs_specialise(GpFeeder* f);
+/*
+ * Host only (no device): the schedule the kernels are given for a descriptor.  events_out[2 e], [2 e + 1] =
+ * {step, (level << 4) | flags} of the depth-first walk (flag bit 0: 1 = backward step on the way up, 0 =
+ * forward step on the way down); kind_out[step] = the step's edge kind (bits 0..7) with the library's flag bits:
+ * 8..15 phase mask of the mask-specialised body, 19..21 phases whose parent-voltage rewrite is dead
+ * (solution_fbs.py:207-232: a sibling earlier in topo order overwrites it before anything reads it).  Either
+ * pointer may be NULL; events_out needs 4 * n_steps entries, kind_out n_steps.  Returns the number of events
+ * (2 * n_steps; 0 when the step table is not a tree in topo order) or a negative GP_E*.  The CPU tests run the
+ * kernel's loop over these tables in NumPy and hold it to the oracle.
+ */
+int gp_fbs_schedule(const GpFbsDesc* desc, int32_t* events_out, int32_t* kind_out);
+/*
+ * Host only: the event table of the tree-walk kernel ("fbs_kernel" 6) for a descriptor, 20 int32 per event:
+ * step, flags, e_row[3], ld_i[3], ld_v[3], st_ca[3], ld_s[3], pad[3] (struct WalkEv in csrc/gp_fbs.cu, which
+ * documents the fields).  cap_events = room in events_out, in events.  Returns the number of events (between
+ * n_steps and 2 n_steps; 0 = the feeder is not walked and runs on the two-sweep kernel) or a negative GP_E*.
+ */
+int gp_fbs_walk_events(const GpFbsDesc* desc, int32_t* events_out, int64_t cap_events);
 int64_t gp_fbs_jit_source(const GpFbsDesc* desc, int32_t warps, int32_t i_global, char* buf, int64_t cap);
 int gp_fbs_jit_warps(GpFeeder* f);
 int gp_jit_compile(const char* source, void* cubin, int64_t cap, int64_t* cubin_bytes);

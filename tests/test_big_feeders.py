@@ -93,7 +93,7 @@ def test_gpu_matches_the_reference_on_the_authored_feeders():
     z = np.asarray(ZIPS['test_zip'])
     s = SolutionFBS(F123, zip_v=z)
     try:
-        for kern in (3, 1, 2, 0):
+        for kern in (3, 1, 2, 6, 0):
             _cabi.check(_cabi.gp_set_option(b'fbs_kernel', kern))
             r = s.solve_batch(load_mult=g['123/mult'], outputs=('V', 'I', 'sV', 'Stx', 'Srx'))
             assert list(r.iterations) == list(g['123/FBS/iterations']), kern

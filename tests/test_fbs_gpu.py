@@ -190,7 +190,7 @@ def test_errors_are_python_exceptions():
 
 
 KERNELS = {0: 'automatic', 1: 'fused depth-first', 2: 'phase-parallel', 3: 'two-sweep streaming', 4: 'on-chip',
-           5: 'feeder-specialised on-chip'}
+           5: 'feeder-specialised on-chip', 6: 'tree walk'}
 
 
 @pytest.mark.parametrize('feeder', ['IEEE_13_Bus_allwye', 'IEEE_13_Bus_allwye_noxfm_noreg',
@@ -210,6 +210,8 @@ def test_all_fbs_kernels_agree(feeder):
     try:
         for mode in KERNELS:
             _cabi.check(_cabi.gp_set_option(b'fbs_kernel', mode))
+            if mode == 6 and _cabi.gp_fbs_active_kernel(s._feeder.handle) != 6:
+                continue        # a regulator that leaves phases of its bus unregulated: not walked
             res[mode] = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
         # the streaming kernel with every I row travelling (no shared rows)
         _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 3))
@@ -218,7 +220,7 @@ def test_all_fbs_kernels_agree(feeder):
     finally:
         _cabi.gp_set_option(b'fbs_kernel', 0)
         _cabi.gp_set_option(b'fbs_share_rows', 1)
-    for mode in KERNELS:
+    for mode in res:
         assert np.array_equal(res[mode].iterations, want['iterations']), KERNELS[mode]
         assert rel_err(res[mode].V, want['V']) <= TOL and rel_err(res[mode].I, want['I']) <= TOL, KERNELS[mode]
         assert rel_err(res[3].V, res[mode].V) <= 1e-12, KERNELS[mode]
@@ -455,3 +457,85 @@ def test_calc_methods_match_the_reference(feeder):
     s.V = g[k + 'bus_V'].copy()
     s.calc_sV(s.circuit.buses.get_element(str(g[k + 'bus_name'])))
     assert np.abs(s.sV - g[k + 'bus_sV']).max() <= 1e-13
+
+
+@pytest.mark.parametrize('feeder', ['IEEE_13_Bus_allwye', 'IEEE_34_Bus_allwye', 'IEEE_37_Bus_allwye_noxfm_noreg', 'ieee123'])
+def test_depth_first_order_is_bit_identical_to_two_sweeps(feeder):
+    """The streaming kernel's depth-first step order (fbs_order = 1) runs the same steps on the same values
+    as the two full sweeps (fbs_order = 0): results must be bit-identical, with and without shared I rows,
+    and also for warm starts and per-scenario taps (the EX instance)."""
+    import os
+    from gigpower_b200 import _cabi
+    from helpers import REPO
+    if feeder == 'ieee123':
+        from gigpower_b200.solution_fbs import SolutionFBS
+        s = SolutionFBS(os.path.join(REPO, 'gigpower_b200', 'feeders', 'ieee123_allwye_noxfm_noreg.dss'))
+    else:
+        s = _fbs(feeder)
+    rng = np.random.Generator(np.random.PCG64(77))
+    mult = rng.uniform(0.4, 1.4, size=(3000, s.circuit.loads.num_elements))
+    out = {}
+    try:
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 3))
+        for order in (0, 1):
+            for share in (0, 1):
+                _cabi.check(_cabi.gp_set_option(b'fbs_order', order))
+                _cabi.check(_cabi.gp_set_option(b'fbs_share_rows', share))
+                r = s.solve_batch(load_mult=mult, outputs=('V', 'I', 'Vmag', 'loss'))
+                out[order, share] = (r.iterations, r.status, np.asarray(r.V_rows), np.asarray(r.I_rows), r.losses)
+                w = s.solve_batch(load_mult=mult * 1.05, outputs=('V', 'I'), return_device=True)
+                w2 = s.solve_batch(load_mult=mult, outputs=('V', 'I'), warm_start=w)
+                out['warm', order, share] = (w2.iterations, np.asarray(w2.V_rows), np.asarray(w2.I_rows))
+        for share in (0, 1):
+            for a, b in zip(out[0, share], out[1, share]):
+                assert np.array_equal(a, b), share
+            for a, b in zip(out['warm', 0, share], out['warm', 1, share]):
+                assert np.array_equal(a, b), ('warm', share)
+    finally:
+        _cabi.gp_set_option(b'fbs_kernel', 0)
+        _cabi.gp_set_option(b'fbs_order', 1)
+        _cabi.gp_set_option(b'fbs_share_rows', 1)
+
+
+@pytest.mark.parametrize('feeder', ['ieee123', 'synth2500', 'IEEE_37_Bus_allwye_noxfm_noreg', 'IEEE_13_Bus_allwye'])
+def test_tree_walk_kernel_matches_oracle_and_two_sweep_kernel(feeder):
+    """fbs_walk_kernel in each of its register budgets (fbs_walk_blocks 4/5/6/8) on ragged batch sizes:
+    oracle at 1e-9 with equal iteration counts, the two-sweep streaming kernel at 1e-12 (the only
+    difference is the order in which a bus's child currents are added), status words equal -
+    including scenarios that do not converge."""
+    import os
+    from gigpower_b200 import _cabi
+    from gigpower_b200.dss_reader import read_dss
+    from gigpower_b200.solution_fbs import SolutionFBS
+    from oracle.gp_oracle import FBSOracle
+    from helpers import REPO
+    files = {'ieee123': 'ieee123_allwye_noxfm_noreg.dss', 'synth2500': 'synth2500_radial.dss'}
+    if feeder in files:
+        path = os.path.join(REPO, 'gigpower_b200', 'feeders', files[feeder])
+        s, o = SolutionFBS(path, zip_v=np.asarray(ZIPS['test_zip'])), FBSOracle(read_dss(path), ZIPS['test_zip'])
+    else:
+        s, o = _fbs(feeder), _oracle(feeder)
+    S = 150 if feeder == 'synth2500' else 1031
+    rng = np.random.Generator(np.random.PCG64(66))
+    mult = rng.uniform(0.4, 1.3, size=(S, len(o.c.load_names)))
+    mult[5] = 6.0           # overloaded: does not converge / diverges
+    want = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+    try:
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 3))
+        ref = s.solve_batch(load_mult=mult, outputs=('V', 'I', 'Vmag', 'loss'))
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 6))
+        assert _cabi.gp_fbs_active_kernel(s._feeder.handle) == 6
+        for blocks in (4, 5, 6, 8):
+            _cabi.check(_cabi.gp_set_option(b'fbs_walk_blocks', blocks))
+            r = s.solve_batch(load_mult=mult, outputs=('V', 'I', 'Vmag', 'loss'))
+            ok = ref.status == 0
+            assert ok.sum() >= S - 3
+            assert np.array_equal(r.status, ref.status), blocks
+            assert np.array_equal(r.iterations[ok], ref.iterations[ok]), blocks
+            assert np.array_equal(r.iterations[ok], want['iterations'][ok]), blocks
+            assert rel_err(r.V[ok], want['V'][ok]) <= TOL and rel_err(r.I[ok], want['I'][ok]) <= TOL, blocks
+            assert rel_err(r.V[ok], ref.V[ok]) <= 1e-12 and rel_err(r.I[ok], ref.I[ok]) <= 1e-12, blocks
+            assert rel_err(r.Vmag[ok], ref.Vmag[ok]) <= 1e-12 and rel_err(r.losses[ok], ref.losses[ok]) <= 1e-12, blocks
+    finally:
+        _cabi.gp_set_option(b'fbs_kernel', 0)
+        _cabi.gp_set_option(b'fbs_walk_blocks', 4)
