@@ -42,10 +42,12 @@ static int g_host_chunks = 0;  // gp_set_option("host_chunks", n): 0 = automatic
 // depth-first, 2 phase-parallel, 3 two-sweep streaming, 4 on-chip (error if the feeder does not fit),
 // 5 feeder-specialised on-chip kernel (error unless gp_fbs_specialise succeeded)
 static int g_fbs_kernel = 0;
-// gp_set_option("fbs_prefetch", d): L2 prefetch distance of the streaming kernel in steps.  Measured on
-// B200 (C4, C5, C2): every distance > 0 is 2-8 % SLOWER than none - the kernel is bound by DRAM
-// throughput on 512-byte row pieces, not by exposed latency - so the default is off.
-static int g_fbs_prefetch = 0;
+// gp_set_option("fbs_prefetch", d): L2 prefetch distance of the streaming kernel in steps; -1 (default) = automatic.
+// In depth-first order the rows a step still takes from DRAM are last iteration's edge currents and the loads;
+// requesting them two events ahead pays when a scenario's state is far larger than its share of L2 (measured on
+// B200, round 2: 2,541-bus feeder 71.5 -> 68.2 ms) and costs when most reads already hit L2 (123-bus: 3.76 -> 3.89 ms
+// at distance 2, worse at 1, 4, 8), so the automatic choice is 2 for feeders with >= 1,024 V rows, else 0.
+static int g_fbs_prefetch = -1;
 // gp_set_option("fbs_share_rows", 0|1): the streaming kernel skips the HBM round trips of I rows that only
 // repeat a child's current or stay zero (default 1; 0 = every row travels, for A/B measurements)
 static int g_fbs_share_rows = 1;
@@ -55,6 +57,7 @@ static int g_fbs_order = 1;
 // gp_set_option("fbs_walk_blocks", n): resident 128-thread blocks per SM the tree-walk kernel is compiled for
 // (4 = up to 128 registers per thread, 5 = 96, 6 = 80, 8 = 64)
 static int g_fbs_walk_blocks = 4;
+static int g_fbs_auto_walk = 0;    // gp_set_option("fbs_auto_walk", 0|1): the automatic choice takes the tree-walk kernel
 
 // |v| as numpy computes it for the ZIP model (abs then square, solution.py:202)
 __device__ __forceinline__ double cabs2(double2 v, double& a) {
@@ -155,6 +158,7 @@ __device__ __forceinline__ void bwd_fast(const FbsStep* __restrict__ st, const i
     const int4 ev = __ldg(reinterpret_cast<const int4*>(st->edge_irow));
     const int brow[3] = {bv.x, bv.y, bv.z}, prow[3] = {pv.x, pv.y, pv.z};
     const int erow[3] = {ev.x, ev.y, ev.z};
+    const int noload = (bv.w >> 22) & 7;        // bus phases without load and capacitor (fbs_tables_from_desc)
     double2 Vb[3], In[3];
 #pragma unroll
     for (int p = 0; p < 3; ++p)
@@ -178,16 +182,24 @@ __device__ __forceinline__ void bwd_fast(const FbsStep* __restrict__ st, const i
     for (int p = 0; p < 3; ++p)
         if ((M >> p) & 1) {                             // calc_sV (solution.py:177-220) + update_current (:256-288)
             const double2 v = Vb[p];
-            double a;
-            const double a2 = cabs2(v, a);
-            const double f = k.aPQ + k.aI * a + k.aZ * a2;
-            double2 sv = make_double2(sp[p].x * f, sp[p].y * f);
-            sv.y -= __ldg(&st->cap[p]) * a2;
-            if (m.hasW()) sv.y += m.ldW(brow[p]);           // + 1j * wpu (solution.py:203)
-            if (v.x != 0.0 || v.y != 0.0) {
-                const double inv = 1.0 / fma(v.x, v.x, v.y * v.y);
-                In[p].x += (sv.x * v.x + sv.y * v.y) * inv;
-                In[p].y -= (sv.y * v.x - sv.x * v.y) * inv;
+            if (((noload >> p) & 1) && !m.hasW()) {
+                // no load, no capacitor: conj(0 / V) adds an exact zero - unless V is not finite, when the
+                // reference's 0 * inf makes the current NaN (nan_to_num then zeroes it): x - x does both
+                const double t = (v.x - v.x) + (v.y - v.y);
+                In[p].x += t;
+                In[p].y += t;
+            } else {
+                double a;
+                const double a2 = cabs2(v, a);
+                const double f = k.aPQ + k.aI * a + k.aZ * a2;
+                double2 sv = make_double2(sp[p].x * f, sp[p].y * f);
+                sv.y -= __ldg(&st->cap[p]) * a2;
+                if (m.hasW()) sv.y += m.ldW(brow[p]);           // + 1j * wpu (solution.py:203)
+                if (v.x != 0.0 || v.y != 0.0) {
+                    const double inv = 1.0 / fma(v.x, v.x, v.y * v.y);
+                    In[p].x += (sv.x * v.x + sv.y * v.y) * inv;
+                    In[p].y -= (sv.y * v.x - sv.x * v.y) * inv;
+                }
             }
             sum += fabs(In[p].x) + fabs(In[p].y);
         }
@@ -321,6 +333,11 @@ __device__ __forceinline__ void fbs_bwd_step(const FbsStep* __restrict__ st, con
         In[p] = zero;
         if (brow[p] < 0) continue;
         const double2 v = Vb[p];
+        if (((bv.w >> (22 + p)) & 1) && !m.hasW()) {    // no load, no capacitor: an exact zero, NaN if V is not finite
+            const double t = (v.x - v.x) + (v.y - v.y);
+            In[p] = make_double2(t, t);
+            continue;
+        }
         double a;
         const double a2 = cabs2(v, a);
         const double f = k.aPQ + k.aI * a + k.aZ * a2;
@@ -393,7 +410,8 @@ __device__ __forceinline__ int fbs_status(bool converged, double diff) {
 
 // EX = the instance behind gp_fbs_solve_batch_ex: per-scenario regulator ratios (gam != NULL) and / or a
 // warm start (V and I hold an earlier solution).  The plain instance carries neither argument.
-template <int BLOCK, bool EX>
+// DFS = the steps run in depth-first order (fbs_order 1, the default), else as two full sweeps.
+template <int BLOCK, bool EX, bool DFS>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)   // <= 64 registers: 1024 resident threads per SM
 fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ child_irow,
                  FbsConst k, int n_steps, int n_vrows, int n_irows, long long S, unsigned ldb,
@@ -432,7 +450,7 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
     while (!converged && it < maxiter) {
 #pragma unroll
         for (int p = 0; p < 3; ++p) m.stV(k.root_vrow[p], k.vref[p]);      // V[root] = Vref  (:89)
-        if (n_events > 0) {
+        if (DFS) {
             // Depth-first order of the SAME steps on the same rows (gp_set_option("fbs_order")).  A bus's forward
             // step runs when the walk descends its edge, its backward step when the walk comes back up, children
             // latest-in-topo-order first.  Every value a step reads is the one the reference's two full sweeps
@@ -446,6 +464,23 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
             const bool first = it == 0 && !(EX && warm);
             for (int e = 0; e < n_events; ++e) {
                 const int2 ev = __ldg(events + e);
+                if (PF > 0 && e + PF < n_events) {
+                    // the rows of event e + PF that were last written a whole iteration ago (the edge currents of a
+                    // forward step) or never by this kernel (the loads of a backward step) come from DRAM: into L2 now
+                    const int2 pe = __ldg(events + e + PF);
+                    const FbsStep* ps = steps + pe.x;
+                    if (pe.y & 1) {
+                        const int4 lv = __ldg(reinterpret_cast<const int4*>(ps->load_srow));
+                        m.pfS(lv.x);
+                        m.pfS(lv.y);
+                        m.pfS(lv.z);
+                    } else if (!first) {
+                        const int4 ei = __ldg(reinterpret_cast<const int4*>(ps->edge_irow));
+                        m.pfI(ei.x);
+                        m.pfI(ei.y);
+                        m.pfI(ei.z);
+                    }
+                }
                 if (ev.y & 1) {
                     double2 sp[3];
                     fbs_load_spu(steps + ev.x, m, sp);
@@ -1060,251 +1095,268 @@ struct __align__(16) WalkEv {
 static_assert(sizeof(WalkEv) == 80, "WalkEv layout");
 constexpr int WK_DESC = 0, WK_LEAF = 1, WK_ASC = 2;
 
-__device__ __forceinline__ WalkEv walk_ld_event(const WalkEv* __restrict__ e) {
-    WalkEv r;
-    const int4* q = reinterpret_cast<const int4*>(e);
-    const int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), f = __ldg(q + 4);
-    r.step = a.x; r.flags = a.y; r.e_row[0] = a.z; r.e_row[1] = a.w;
-    r.e_row[2] = b.x; r.ld_i[0] = b.y; r.ld_i[1] = b.z; r.ld_i[2] = b.w;
-    r.ld_v[0] = c.x; r.ld_v[1] = c.y; r.ld_v[2] = c.z; r.st_ca[0] = c.w;
-    r.st_ca[1] = d.x; r.st_ca[2] = d.y; r.ld_s[0] = d.z; r.ld_s[1] = d.w;
-    r.ld_s[2] = f.x; r.pad[0] = r.pad[1] = r.pad[2] = 0;
-    return r;
-}
+// The record the kernel reads (64 bytes, four 16-byte words; built from WalkEv by fbs_pack_walk):
+//   w0 = {step, flags, a0, a1}   w1 = {a2, b0, b1, b2}   w2 = {c0, c1, c2, d0}   w3 = {d1, d2, 0, 0}
+//   a = e_row (the step's I rows), b = ld_s (load rows),
+//   c = st_ca for DESC (rows to park the parent's current sum in; flag bit 24 = there are any),
+//       ld_i for ASC (rows holding the parent's parked sum), d = ld_v for ASC (the parent's V rows to take back)
+struct __align__(16) WalkRec { int4 w[4]; };
 
 // ZIP load + capacitor current of one bus phase (calc_sV solution.py:177-220, update_current :256-288)
-__device__ __forceinline__ double2 walk_load_current(const double2 v, const double2 sp, const double cap, const FbsConst& k) {
-    double a;
-    const double a2 = cabs2(v, a);
+__device__ __forceinline__ void walk_add_load_current(double2& In, const double2 v, const double2 sp, const double cap,
+                                                      const FbsConst& k) {
+    const double m2 = fma(v.x, v.x, v.y * v.y);
+    const double a = sqrt(m2);
+    const double a2 = a * a;
     const double f = k.aPQ + k.aI * a + k.aZ * a2;
-    double2 sv = make_double2(sp.x * f, sp.y * f);
-    sv.y -= cap * a2;
-    double2 r = make_double2(0.0, 0.0);
+    const double sx = sp.x * f;
+    const double sy = sp.y * f - cap * a2;
     if (v.x != 0.0 || v.y != 0.0) {
-        const double inv = 1.0 / fma(v.x, v.x, v.y * v.y);
-        r.x = (sv.x * v.x + sv.y * v.y) * inv;
-        r.y = -((sv.y * v.x - sv.x * v.y) * inv);
+        const double inv = 1.0 / m2;
+        In.x += (sx * v.x + sy * v.y) * inv;
+        In.y -= (sy * v.x - sx * v.y) * inv;
     }
-    return r;
 }
 
-// One event.  M != 0: the step is uniform (bus phases = edge phases = M, all present on the parent) and M is a
-// compile-time constant; M == 0: every mask is read from the event's flags.
-template <int M>
-__device__ __forceinline__ void walk_event(const WalkEv& ev, const FbsStep* __restrict__ st, const FbsConst& k,
-                                           const GMem& m, const bool first, double2 (&cv)[3], double2 (&ca)[3],
-                                           const double2 (&oI)[3], const double2 (&oS)[3]) {
-    const double2 zero = make_double2(0.0, 0.0);
-    const int fl = ev.flags, type = fl & 3;
-    const int mb = M ? M : (fl >> 3) & 7, me = M ? M : (fl >> 18) & 7;
-    const int ms = (fl >> 6) & 7, mw = (fl >> 9) & 7, mc = (fl >> 12) & 7, ml = (fl >> 15) & 7;
-    const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
-    const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
-    const int brow[3] = {bv.x, bv.y, bv.z}, prow[3] = {pv.x, pv.y, pv.z};
-    if (type == WK_DESC) {
-#pragma unroll
-        for (int p = 0; p < 3; ++p)
-            if (ev.st_ca[p] >= 0) m.stI(ev.st_ca[p], ca[p]);            // park the parent's partial current sum
-    }
-    // the parent's V rows this event takes back from memory at its end: requested now
-    double2 rV[3];
-    if (type == WK_ASC) {
-#pragma unroll
-        for (int p = 0; p < 3; ++p) rV[p] = ev.ld_v[p] >= 0 ? m.ldV(ev.ld_v[p]) : zero;
-    }
-    if (fl & 4) {   // regulator edge: vr_forward :138-160, vr_backward :186-205, no current (vr_current leaves Itx = 0)
-        double2 b[3];
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-            b[p] = cv[p];
-            if (type != WK_ASC) {
-                const double g = __ldg(&st->gamma[p]);
-                b[p] = ((mb >> p) & 1) ? make_double2(g * cv[p].x, g * cv[p].y) : zero;
-                if ((mb >> p) & 1) m.stV(brow[p], b[p]);
-            }
-        }
-        if (type == WK_DESC) {
-#pragma unroll
-            for (int p = 0; p < 3; ++p) { cv[p] = b[p]; ca[p] = zero; }
-            return;
-        }
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-            double2 nv = zero;
-            if ((mw >> p) & 1) {
-                const double ig = __ldg(&st->inv_gamma[p]);
-                nv = make_double2(ig * b[p].x, ig * b[p].y);
-                m.stV(prow[p], nv);
-            }
-            if (type == WK_ASC) {
-                cv[p] = ((mw >> p) & 1) ? nv : rV[p];
-                ca[p] = oI[p];
-            } else if ((mw >> p) & 1) {
-                cv[p] = nv;
-            }
-        }
-        return;
-    }
-    // ---- forward step on the way down (update_voltage_forward :162-184) ----
-    double2 b[3];
-    if (type != WK_ASC) {
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-            b[p] = zero;
-            if ((mb >> p) & 1) {
-                double2 v = cv[p];
-                if (!first) {
-#pragma unroll
-                    for (int q = 0; q < 3; ++q)
-                        if ((me >> q) & 1) {
-                            const double2 z = __ldg(&st->z[3 * p + q]);
-                            v.x -= z.x * oI[q].x - z.y * oI[q].y;
-                            v.y -= z.x * oI[q].y + z.y * oI[q].x;
-                        }
-                }
-                m.stV(brow[p], v);
-                b[p] = v;
-            }
-        }
-        if (type == WK_DESC) {
-#pragma unroll
-            for (int p = 0; p < 3; ++p) { cv[p] = b[p]; ca[p] = zero; }
-            return;
-        }
-    } else {
-#pragma unroll
-        for (int p = 0; p < 3; ++p) b[p] = cv[p];
-    }
-    // ---- backward step (calc_sV, update_current, update_voltage_backward) of a leaf or on the way up ----
-    double2 In[3];
-    double sum = 0.0;
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
-        In[p] = zero;
-        if ((me >> p) & 1) {
-            if (type == WK_ASC) In[p] = ca[p];
-            if ((ml >> p) & 1) {
-                const double2 q = walk_load_current(b[p], oS[p], __ldg(&st->cap[p]), k);
-                In[p].x += q.x;
-                In[p].y += q.y;
-            } else {
-                // no load, no capacitor: conj(0 / V) adds an exact zero - unless V is not finite, in which case the
-                // reference's 0 * inf makes the whole current NaN (and nan_to_num then zeroes it): x - x does both
-                const double t = (b[p].x - b[p].x) + (b[p].y - b[p].y);
-                In[p].x += t;
-                In[p].y += t;
-            }
-            sum += fabs(In[p].x) + fabs(In[p].y);
-        }
-    }
-    if (!(sum <= 1.7976931348623157e308)) {             // nan_to_num (:288) acts on non-finite values only
-#pragma unroll
-        for (int p = 0; p < 3; ++p)
-            if ((me >> p) & 1) In[p] = make_double2(nan_to_num(In[p].x), nan_to_num(In[p].y));
-    }
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
-        if ((ms >> p) & 1) m.stI(ev.e_row[p], In[p]);
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
-        double2 nv = zero;
-        if ((mw >> p) & 1) {
-            nv = b[p];
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-                if ((me >> q) & 1) {
-                    const double2 z = __ldg(&st->z[3 * p + q]);
-                    nv.x += z.x * In[q].x - z.y * In[q].y;
-                    nv.y += z.x * In[q].y + z.y * In[q].x;
-                }
-            m.stV(prow[p], nv);
-        }
-        if (type == WK_ASC) {           // the parent is the current bus again
-            cv[p] = ((mw >> p) & 1) ? nv : rV[p];
-            ca[p] = oI[p];
-        } else if ((mw >> p) & 1) {
-            cv[p] = nv;
-        }
-        if ((mc >> p) & 1) {
-            ca[p].x += In[p].x;
-            ca[p].y += In[p].y;
-        }
-    }
-}
+#define GP_ROWP(base, row) ((base) + (size_t)(unsigned)(row) * (size_t)ldb)
+#define GP_LD2(base, row) __ldcg(reinterpret_cast<const double2*>(GP_ROWP(base, row)))
+#define GP_ST2(base, row, v) (*reinterpret_cast<double2*>(GP_ROWP(base, row)) = (v))
+// v -= z * i  /  v += z * i  (complex, the three-operation form of the other FBS kernels)
+#define GP_CMSUB(v, z, i) { v.x -= z.x * i.x - z.y * i.y; v.y -= z.x * i.y + z.y * i.x; }
+#define GP_CMADD(v, z, i) { v.x += z.x * i.x - z.y * i.y; v.y += z.x * i.y + z.y * i.x; }
 
 template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
-fbs_walk_kernel(const FbsStep* __restrict__ steps, const WalkEv* __restrict__ events, int n_events, FbsConst k,
+fbs_walk_kernel(const FbsStep* __restrict__ steps, const WalkRec* __restrict__ events, int n_events, FbsConst k,
                 int n_vrows, int n_irows, long long S, unsigned ldb, const char* __restrict__ spu, char* __restrict__ V,
                 char* __restrict__ I, int* __restrict__ iters_out, int* __restrict__ status_out,
                 double* __restrict__ diff_out, double tol, int maxiter, const int2* __restrict__ alias, int n_alias) {
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (s >= S) return;
-    const GMem m{V + s * 16, I + s * 16, spu + s * 16, ldb, nullptr, nullptr};
+    char* const Vb = V + s * 16;
+    char* const Ib = I + s * 16;
+    const char* const Sb = spu + s * 16;
     const double2 zero = make_double2(0.0, 0.0);
     int it = 0;
     double diff = -1.0;
     bool converged = false;
     while (!converged && it < maxiter) {
         const bool first = it == 0;     // flat start: the currents are zero and are not read
-        double2 cv[3], ca[3], pI[3], pS[3];
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-            cv[p] = k.vref[p];                              // V[root] = Vref (:89)
-            m.stV(k.root_vrow[p], k.vref[p]);
-            ca[p] = zero;
+        // the current bus: voltage per phase and the sum of the currents of the children visited so far
+        double2 cv0 = k.vref[0], cv1 = k.vref[1], cv2 = k.vref[2], ca0 = zero, ca1 = zero, ca2 = zero;
+        GP_ST2(Vb, k.root_vrow[0], cv0);                    // V[root] = Vref (:89)
+        GP_ST2(Vb, k.root_vrow[1], cv1);
+        GP_ST2(Vb, k.root_vrow[2], cv2);
+        // operands requested one event ahead: pI = last iteration's edge currents (DESC, LEAF) or the parent's
+        // parked current sum (ASC); pS = the loads of the bus (LEAF, ASC)
+        double2 pI0 = zero, pI1 = zero, pI2 = zero, pS0 = zero, pS1 = zero, pS2 = zero;
+        const int4* ev4 = reinterpret_cast<const int4*>(events);
+        int4 n0 = __ldg(ev4), n1 = __ldg(ev4 + 1);
+#define GP_WALK_REQUEST(q)                                                                      \
+        {                                                                                       \
+            int i0 = n0.z, i1 = n0.w, i2 = n1.x;                                                \
+            if ((n0.y & 3) == WK_ASC) {                                                         \
+                const int4 c = __ldg((q) + 2);                                                  \
+                i0 = c.x; i1 = c.y; i2 = c.z;                                                   \
+            } else if (first) {                                                                 \
+                i0 = i1 = i2 = -1;                                                              \
+            }                                                                                   \
+            pI0 = i0 >= 0 ? GP_LD2(Ib, i0) : zero;                                              \
+            pI1 = i1 >= 0 ? GP_LD2(Ib, i1) : zero;                                              \
+            pI2 = i2 >= 0 ? GP_LD2(Ib, i2) : zero;                                              \
+            pS0 = n1.y >= 0 ? GP_LD2(Sb, n1.y) : zero;                                          \
+            pS1 = n1.z >= 0 ? GP_LD2(Sb, n1.z) : zero;                                          \
+            pS2 = n1.w >= 0 ? GP_LD2(Sb, n1.w) : zero;                                          \
         }
-        // operands of event e that come from DRAM (last iteration's edge currents / a parked sum, the loads) are
-        // requested one event ahead: only the row numbers of event e + 1 are read here, not its whole record
-        auto request = [&](const WalkEv* __restrict__ ne) {
-            const int4* q = reinterpret_cast<const int4*>(ne);
-            const int4 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 3), f = __ldg(q + 4);
-            const bool skip_i = first && (a.y & 3) != WK_ASC;
-            pI[0] = (b.y >= 0 && !skip_i) ? m.ldI(b.y) : zero;
-            pI[1] = (b.z >= 0 && !skip_i) ? m.ldI(b.z) : zero;
-            pI[2] = (b.w >= 0 && !skip_i) ? m.ldI(b.w) : zero;
-            pS[0] = d.z >= 0 ? m.ldS(d.z) : zero;
-            pS[1] = d.w >= 0 ? m.ldS(d.w) : zero;
-            pS[2] = f.x >= 0 ? m.ldS(f.x) : zero;
-        };
-        request(events);
-        for (int e = 0; e < n_events; ++e) {
-            const WalkEv ev = walk_ld_event(events + e);
-            double2 oI[3], oS[3];
-#pragma unroll
-            for (int p = 0; p < 3; ++p) { oI[p] = pI[p]; oS[p] = pS[p]; }
-            if (e + 1 < n_events) request(events + e + 1);
-            const FbsStep* st = steps + ev.step;
-            switch ((ev.flags >> 21) & 7) {
-                case 7: walk_event<7>(ev, st, k, m, first, cv, ca, oI, oS); break;
-                case 1: walk_event<1>(ev, st, k, m, first, cv, ca, oI, oS); break;
-                case 2: walk_event<2>(ev, st, k, m, first, cv, ca, oI, oS); break;
-                case 4: walk_event<4>(ev, st, k, m, first, cv, ca, oI, oS); break;
-                default: walk_event<0>(ev, st, k, m, first, cv, ca, oI, oS); break;
+        GP_WALK_REQUEST(ev4)
+        for (int e = 0; e < n_events; ++e, ev4 += 4) {
+            const int4 r0 = n0, r1 = n1;
+            const double2 oI0 = pI0, oI1 = pI1, oI2 = pI2, oS0 = pS0, oS1 = pS1, oS2 = pS2;
+            if (e + 1 < n_events) {
+                n0 = __ldg(ev4 + 4);
+                n1 = __ldg(ev4 + 5);
+                GP_WALK_REQUEST(ev4 + 4)
             }
+            const int fl = r0.y, type = fl & 3;
+            const FbsStep* __restrict__ st = steps + r0.x;
+            const int mb = (fl >> 3) & 7, me = (fl >> 18) & 7, mw = (fl >> 9) & 7;
+            const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_vrow));
+            const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_vrow));
+            double2 rV0 = zero, rV1 = zero, rV2 = zero, pk0 = zero, pk1 = zero, pk2 = zero;
+            if (type == WK_ASC) {
+                // the parent's V rows and its parked current sum come back at the end of this event: requested now
+                const int4 c = __ldg(ev4 + 2), d = __ldg(ev4 + 3);
+                if (c.w >= 0) rV0 = GP_LD2(Vb, c.w);
+                if (d.x >= 0) rV1 = GP_LD2(Vb, d.x);
+                if (d.y >= 0) rV2 = GP_LD2(Vb, d.y);
+                pk0 = oI0; pk1 = oI1; pk2 = oI2;
+            } else if (fl & (1 << 24)) {    // DESC at a branch point: park the parent's partial current sum in its own I rows
+                const int4 c = __ldg(ev4 + 2);
+                if (c.x >= 0) GP_ST2(Ib, c.x, ca0);
+                if (c.y >= 0) GP_ST2(Ib, c.y, ca1);
+                if (c.z >= 0) GP_ST2(Ib, c.z, ca2);
+            }
+            double2 b0 = cv0, b1 = cv1, b2 = cv2;           // this bus's voltage
+            double2 In0 = zero, In1 = zero, In2 = zero;     // its edge current
+            if (fl & 4) {
+                // regulator edge: vr_forward :138-160 on the way down, vr_backward :186-205 on the way up, no current
+                if (type != WK_ASC) {
+                    const double g0 = __ldg(&st->gamma[0]), g1 = __ldg(&st->gamma[1]), g2 = __ldg(&st->gamma[2]);
+                    b0 = (mb & 1) ? make_double2(g0 * cv0.x, g0 * cv0.y) : zero;
+                    b1 = (mb & 2) ? make_double2(g1 * cv1.x, g1 * cv1.y) : zero;
+                    b2 = (mb & 4) ? make_double2(g2 * cv2.x, g2 * cv2.y) : zero;
+                    if (mb & 1) GP_ST2(Vb, bv.x, b0);
+                    if (mb & 2) GP_ST2(Vb, bv.y, b1);
+                    if (mb & 4) GP_ST2(Vb, bv.z, b2);
+                }
+                if (type == WK_DESC) {
+                    cv0 = b0; cv1 = b1; cv2 = b2;
+                    ca0 = ca1 = ca2 = zero;
+                    continue;
+                }
+                double2 w0 = zero, w1 = zero, w2 = zero;
+                if (mw & 1) { const double ig = __ldg(&st->inv_gamma[0]); w0 = make_double2(ig * b0.x, ig * b0.y); GP_ST2(Vb, pv.x, w0); }
+                if (mw & 2) { const double ig = __ldg(&st->inv_gamma[1]); w1 = make_double2(ig * b1.x, ig * b1.y); GP_ST2(Vb, pv.y, w1); }
+                if (mw & 4) { const double ig = __ldg(&st->inv_gamma[2]); w2 = make_double2(ig * b2.x, ig * b2.y); GP_ST2(Vb, pv.z, w2); }
+                if (type == WK_ASC) {
+                    cv0 = (mw & 1) ? w0 : rV0; cv1 = (mw & 2) ? w1 : rV1; cv2 = (mw & 4) ? w2 : rV2;
+                    ca0 = pk0; ca1 = pk1; ca2 = pk2;
+                } else {
+                    if (mw & 1) cv0 = w0;
+                    if (mw & 2) cv1 = w1;
+                    if (mw & 4) cv2 = w2;
+                }
+                continue;
+            }
+            if (type != WK_ASC) {
+                // ---- forward step on the way down (update_voltage_forward :162-184) ----
+                if (!(mb & 1)) b0 = zero;
+                if (!(mb & 2)) b1 = zero;
+                if (!(mb & 4)) b2 = zero;
+                if (!first) {
+                    if (me & 1) {
+                        if (mb & 1) { const double2 z = __ldg(&st->z[0]); GP_CMSUB(b0, z, oI0) }
+                        if (mb & 2) { const double2 z = __ldg(&st->z[3]); GP_CMSUB(b1, z, oI0) }
+                        if (mb & 4) { const double2 z = __ldg(&st->z[6]); GP_CMSUB(b2, z, oI0) }
+                    }
+                    if (me & 2) {
+                        if (mb & 1) { const double2 z = __ldg(&st->z[1]); GP_CMSUB(b0, z, oI1) }
+                        if (mb & 2) { const double2 z = __ldg(&st->z[4]); GP_CMSUB(b1, z, oI1) }
+                        if (mb & 4) { const double2 z = __ldg(&st->z[7]); GP_CMSUB(b2, z, oI1) }
+                    }
+                    if (me & 4) {
+                        if (mb & 1) { const double2 z = __ldg(&st->z[2]); GP_CMSUB(b0, z, oI2) }
+                        if (mb & 2) { const double2 z = __ldg(&st->z[5]); GP_CMSUB(b1, z, oI2) }
+                        if (mb & 4) { const double2 z = __ldg(&st->z[8]); GP_CMSUB(b2, z, oI2) }
+                    }
+                }
+                if (mb & 1) GP_ST2(Vb, bv.x, b0);
+                if (mb & 2) GP_ST2(Vb, bv.y, b1);
+                if (mb & 4) GP_ST2(Vb, bv.z, b2);
+                if (type == WK_DESC) {
+                    cv0 = b0; cv1 = b1; cv2 = b2;
+                    ca0 = ca1 = ca2 = zero;
+                    continue;
+                }
+            } else {
+                In0 = ca0; In1 = ca1; In2 = ca2;            // the children's currents (:274-284)
+            }
+            // ---- backward step of a leaf, or on the way up: calc_sV, update_current, update_voltage_backward ----
+            {
+                const int ml = (fl >> 15) & 7;
+                // a phase without load and capacitor adds conj(0 / V) = 0 - unless V is not finite, when the
+                // reference's 0 * inf makes the current NaN (nan_to_num then zeroes it): x - x does both
+                if (me & 1) {
+                    if (ml & 1) walk_add_load_current(In0, b0, oS0, __ldg(&st->cap[0]), k);
+                    else { const double t = (b0.x - b0.x) + (b0.y - b0.y); In0.x += t; In0.y += t; }
+                }
+                if (me & 2) {
+                    if (ml & 2) walk_add_load_current(In1, b1, oS1, __ldg(&st->cap[1]), k);
+                    else { const double t = (b1.x - b1.x) + (b1.y - b1.y); In1.x += t; In1.y += t; }
+                }
+                if (me & 4) {
+                    if (ml & 4) walk_add_load_current(In2, b2, oS2, __ldg(&st->cap[2]), k);
+                    else { const double t = (b2.x - b2.x) + (b2.y - b2.y); In2.x += t; In2.y += t; }
+                }
+                double sum = 0.0;
+                if (me & 1) sum += fabs(In0.x) + fabs(In0.y);
+                if (me & 2) sum += fabs(In1.x) + fabs(In1.y);
+                if (me & 4) sum += fabs(In2.x) + fabs(In2.y);
+                if (!(sum <= 1.7976931348623157e308)) {         // nan_to_num (:288) acts on non-finite values only
+                    if (me & 1) In0 = make_double2(nan_to_num(In0.x), nan_to_num(In0.y));
+                    if (me & 2) In1 = make_double2(nan_to_num(In1.x), nan_to_num(In1.y));
+                    if (me & 4) In2 = make_double2(nan_to_num(In2.x), nan_to_num(In2.y));
+                }
+                if (!(me & 1)) In0 = zero;
+                if (!(me & 2)) In1 = zero;
+                if (!(me & 4)) In2 = zero;
+                const int ms = (fl >> 6) & 7;
+                if (ms & 1) GP_ST2(Ib, r0.z, In0);
+                if (ms & 2) GP_ST2(Ib, r0.w, In1);
+                if (ms & 4) GP_ST2(Ib, r1.x, In2);
+            }
+            // the parent phases this bus rewrites (the surviving stores of update_voltage_backward :207-232)
+            double2 w0 = b0, w1 = b1, w2 = b2;
+            if (mw) {
+                if (me & 1) {
+                    if (mw & 1) { const double2 z = __ldg(&st->z[0]); GP_CMADD(w0, z, In0) }
+                    if (mw & 2) { const double2 z = __ldg(&st->z[3]); GP_CMADD(w1, z, In0) }
+                    if (mw & 4) { const double2 z = __ldg(&st->z[6]); GP_CMADD(w2, z, In0) }
+                }
+                if (me & 2) {
+                    if (mw & 1) { const double2 z = __ldg(&st->z[1]); GP_CMADD(w0, z, In1) }
+                    if (mw & 2) { const double2 z = __ldg(&st->z[4]); GP_CMADD(w1, z, In1) }
+                    if (mw & 4) { const double2 z = __ldg(&st->z[7]); GP_CMADD(w2, z, In1) }
+                }
+                if (me & 4) {
+                    if (mw & 1) { const double2 z = __ldg(&st->z[2]); GP_CMADD(w0, z, In2) }
+                    if (mw & 2) { const double2 z = __ldg(&st->z[5]); GP_CMADD(w1, z, In2) }
+                    if (mw & 4) { const double2 z = __ldg(&st->z[8]); GP_CMADD(w2, z, In2) }
+                }
+                if (mw & 1) GP_ST2(Vb, pv.x, w0);
+                if (mw & 2) GP_ST2(Vb, pv.y, w1);
+                if (mw & 4) GP_ST2(Vb, pv.z, w2);
+            }
+            if (type == WK_ASC) {       // the parent is the current bus again
+                cv0 = (mw & 1) ? w0 : rV0; cv1 = (mw & 2) ? w1 : rV1; cv2 = (mw & 4) ? w2 : rV2;
+                ca0 = pk0; ca1 = pk1; ca2 = pk2;
+            } else {
+                if (mw & 1) cv0 = w0;
+                if (mw & 2) cv1 = w1;
+                if (mw & 4) cv2 = w2;
+            }
+            const int mc = (fl >> 12) & 7;
+            if (mc & 1) { ca0.x += In0.x; ca0.y += In0.y; }
+            if (mc & 2) { ca1.x += In1.x; ca1.y += In1.y; }
+            if (mc & 4) { ca2.x += In2.x; ca2.y += In2.y; }
         }
+#undef GP_WALK_REQUEST
         ++it;
         // root mismatch (:123-128) from the registers: the root is the current bus after the last event
-        diff = 0.0;
-        bool nan = false;
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-            const double dx = cv[p].x - k.vref[p].x, dy = cv[p].y - k.vref[p].y;
-            const double d = sqrt(fma(dx, dx, dy * dy));
-            nan |= (d != d);
-            diff = fmax(diff, d);
+        {
+            const double dx0 = cv0.x - k.vref[0].x, dy0 = cv0.y - k.vref[0].y;
+            const double dx1 = cv1.x - k.vref[1].x, dy1 = cv1.y - k.vref[1].y;
+            const double dx2 = cv2.x - k.vref[2].x, dy2 = cv2.y - k.vref[2].y;
+            const double d0 = sqrt(fma(dx0, dx0, dy0 * dy0)), d1 = sqrt(fma(dx1, dx1, dy1 * dy1)),
+                         d2 = sqrt(fma(dx2, dx2, dy2 * dy2));
+            diff = fmax(fmax(fmax(0.0, d0), d1), d2);
+            if (d0 != d0 || d1 != d1 || d2 != d2) diff = __longlong_as_double(0x7ff8000000000000LL);
         }
-        if (nan) diff = __longlong_as_double(0x7ff8000000000000LL);
         converged = diff <= tol;
     }
     for (int j = 0; j < n_alias; ++j) {         // shared I rows: the caller's array gets every row, once
         const int2 a = __ldg(alias + j);
-        m.stI(a.x, a.y >= 0 ? m.ldI(a.y) : zero);
+        GP_ST2(Ib, a.x, a.y >= 0 ? GP_LD2(Ib, a.y) : zero);
     }
     iters_out[s] = it;
     diff_out[s] = diff;
     status_out[s] = fbs_status(converged, diff);
 }
+#undef GP_ROWP
+#undef GP_LD2
+#undef GP_ST2
+#undef GP_CMSUB
+#undef GP_CMADD
 
 // Derived results: sV, |V| per V row; Stx/Srx per line row; loss per scenario.
 __global__ void fbs_post_rows_kernel(int n_vrows, const int* __restrict__ vrow_srow,
@@ -1387,6 +1439,10 @@ extern "C" int gp_last_error(char* buf, size_t len) {
 extern "C" int64_t gp_launch_count(void) { return g_launches.load(); }
 
 extern "C" int gp_set_option(const char* name, int value) {
+    if (name && strcmp(name, "fbs_auto_walk") == 0 && (value == 0 || value == 1)) {
+        g_fbs_auto_walk = value;
+        return GP_OK;
+    }
     if (name && strcmp(name, "fbs_walk_blocks") == 0 && (value == 4 || value == 5 || value == 6 || value == 8)) {
         g_fbs_walk_blocks = value;
         return GP_OK;
@@ -1395,7 +1451,7 @@ extern "C" int gp_set_option(const char* name, int value) {
         g_fbs_kernel = value;
         return GP_OK;
     }
-    if (name && strcmp(name, "fbs_prefetch") == 0 && value >= 0 && value <= 64) {
+    if (name && strcmp(name, "fbs_prefetch") == 0 && value >= -1 && value <= 64) {
         g_fbs_prefetch = value;
         return GP_OK;
     }
@@ -1452,7 +1508,7 @@ extern "C" int gp_fbs_active_kernel(GpFeeder* f) {
     if (!f || f->kind != 1) return fail(GP_EINVAL, "gp_fbs_active_kernel: not an FBS feeder handle");
     const FbsImpl* im = (const FbsImpl*)f->impl;
     if (g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) return 5;
-    if ((g_fbs_kernel == 6 || g_fbs_kernel == 0) && im->n_walk > 0) return 6;
+    if ((g_fbs_kernel == 6 || (g_fbs_kernel == 0 && g_fbs_auto_walk)) && im->n_walk > 0) return 6;
     if (g_fbs_kernel == 4) return 4;
     if (g_fbs_kernel == 2) return 2;
     if (g_fbs_kernel == 1 && im->n_events > 0 && im->dfs_stack_ok) return 1;
@@ -1573,6 +1629,10 @@ static int fbs_tables_from_desc(const GpFbsDesc* d, std::vector<FbsStep>& steps,
     // bus only the one EARLIEST in topo order survives per phase, nothing reads the others' values.  They are
     // not stored (IEEE 123: about 40 % of the backward sweep's V stores), which is also what lets the kernel
     // walk the tree depth-first on one V array.
+    // bits 22..24: bus phases without load and capacitor - their load current is an exact zero and is not computed
+    for (int i = 0; i < d->n_steps; ++i)
+        for (int p = 0; p < 3; ++p)
+            if (steps[i].bus_vrow[p] >= 0 && steps[i].load_srow[p] < 0 && steps[i].cap[p] == 0.0) steps[i].kind |= 1 << (22 + p);
     {
         std::vector<char> written((size_t)d->n_vrows, 0);
         for (int i = 0; i < d->n_steps; ++i) {
@@ -2119,8 +2179,20 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
         if (e == cudaSuccess) e = up((void**)&im->d_unfed, unfed.data(), unfed.size() * sizeof(int));
         std::vector<WalkEv> walk;
         fbs_build_walk(d, steps, steps_a, im->n_unfed, walk);
-        im->n_walk = (int)walk.size();
-        if (e == cudaSuccess) e = up((void**)&im->d_walk, walk.data(), walk.size() * sizeof(WalkEv));
+        std::vector<WalkRec> recs(walk.size());     // the 64-byte records the kernel reads
+        for (size_t i = 0; i < walk.size(); ++i) {
+            const WalkEv& w = walk[i];
+            const bool asc = (w.flags & 3) == WK_ASC;
+            const int* c = asc ? w.ld_i : w.st_ca;
+            int fl = w.flags & 0x00ffffff;
+            if (!asc && (w.st_ca[0] >= 0 || w.st_ca[1] >= 0 || w.st_ca[2] >= 0)) fl |= 1 << 24;
+            recs[i].w[0] = make_int4(w.step, fl, w.e_row[0], w.e_row[1]);
+            recs[i].w[1] = make_int4(w.e_row[2], w.ld_s[0], w.ld_s[1], w.ld_s[2]);
+            recs[i].w[2] = make_int4(c[0], c[1], c[2], asc ? w.ld_v[0] : -1);
+            recs[i].w[3] = make_int4(asc ? w.ld_v[1] : -1, asc ? w.ld_v[2] : -1, 0, 0);
+        }
+        im->n_walk = (int)recs.size();
+        if (e == cudaSuccess) e = up((void**)&im->d_walk, recs.data(), recs.size() * sizeof(WalkRec));
     }
     if (e == cudaSuccess) e = cudaMalloc((void**)&im->d_sched, (FbsImpl::NSCHED + 1) * 16);
     if (e == cudaSuccess) e = cudaMemset(im->d_sched, 0, (FbsImpl::NSCHED + 1) * 16);
@@ -2289,11 +2361,17 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     if (extras) {
         // per-scenario ratios / warm start: the streaming kernel's EX instance (the on-chip kernels
         // bake the ratios into their code or tables and always start flat)
-        fbs_solve_kernel<BLOCK, true><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows,
-                                                            im->n_irows, S, ldb, (const char*)spu, (char*)V,
-                                                            (char*)I, iters, status, diff, tol, maxiter, g_fbs_prefetch,
-                                                            im->d_unfed, im->n_unfed, gam, warm, wpu, nullptr, 0,
-                                                            im->d_events, g_fbs_order ? im->n_events : 0);
+        const int pf = g_fbs_prefetch >= 0 ? g_fbs_prefetch : (im->n_vrows >= 1024 ? 2 : 0);
+        if (g_fbs_order && im->n_events > 0)
+            fbs_solve_kernel<BLOCK, true, true><<<gx, BLOCK, 0, st>>>(
+                im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V,
+                (char*)I, iters, status, diff, tol, maxiter, pf, im->d_unfed, im->n_unfed, gam, warm, wpu, nullptr, 0,
+                im->d_events, im->n_events);
+        else
+            fbs_solve_kernel<BLOCK, true, false><<<gx, BLOCK, 0, st>>>(
+                im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V,
+                (char*)I, iters, status, diff, tol, maxiter, pf, im->d_unfed, im->n_unfed, gam, warm, wpu, nullptr, 0,
+                nullptr, 0);
     } else if ((g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) && (maxiter >= 1 || !im->jit_kernel)) {
         if (!im->jit_kernel)
             return fail(GP_EINVAL, "gp_fbs_solve_batch: fbs_kernel = 5 needs a successful gp_fbs_specialise");
@@ -2347,10 +2425,10 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
         else if (im->depth <= 32) GP_DFS(32);
         else GP_DFS(64);
 #undef GP_DFS
-    } else if ((g_fbs_kernel == 6 || g_fbs_kernel == 0) && im->n_walk > 0 && maxiter >= 1) {
+    } else if ((g_fbs_kernel == 6 || (g_fbs_kernel == 0 && g_fbs_auto_walk)) && im->n_walk > 0 && maxiter >= 1) {
         // tree walk with the state of the current bus in registers (always on the shared-row tables)
 #define GP_WALK(MINB)                                                                                                   \
-    fbs_walk_kernel<BLOCK, MINB><<<gx, BLOCK, 0, st>>>(im->d_steps_a, (const WalkEv*)im->d_walk, im->n_walk, im->k,     \
+    fbs_walk_kernel<BLOCK, MINB><<<gx, BLOCK, 0, st>>>(im->d_steps_a, (const WalkRec*)im->d_walk, im->n_walk, im->k,     \
                                                        im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V,    \
                                                        (char*)I, iters, status, diff, tol, maxiter, im->d_alias,        \
                                                        im->n_alias)
@@ -2364,13 +2442,21 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     } else {
         if (g_fbs_kernel == 6) return fail(GP_EINVAL, "gp_fbs_solve_batch: fbs_kernel = 6 needs a feeder the tree-walk kernel takes");
         const bool share = g_fbs_share_rows && im->n_alias > 0;
-        fbs_solve_kernel<BLOCK, false><<<gx, BLOCK, 0, st>>>(share ? im->d_steps_a : im->d_steps,
-                                                             share ? im->d_child_a : im->d_child, im->k, im->n_steps,
-                                                             im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V,
-                                                             (char*)I, iters, status, diff, tol, maxiter, g_fbs_prefetch,
-                                                             im->d_unfed, im->n_unfed, nullptr, 0, nullptr,
-                                                             share ? im->d_alias : nullptr, share ? im->n_alias : 0,
-                                                             im->d_events, g_fbs_order ? im->n_events : 0);
+        // L2 prefetch distance: automatic = 2 events for feeders whose state is far larger than L2 can hold per
+        // scenario (measured on B200: 2,541-bus 71.5 -> 68.2 ms; 123-bus 3.76 -> 3.89 ms, so off there)
+        const int pf = g_fbs_prefetch >= 0 ? g_fbs_prefetch : (im->n_vrows >= 1024 ? 2 : 0);
+        const FbsStep* tb = share ? im->d_steps_a : im->d_steps;
+        const int4* tc = share ? im->d_child_a : im->d_child;
+        if (g_fbs_order && im->n_events > 0)
+            fbs_solve_kernel<BLOCK, false, true><<<gx, BLOCK, 0, st>>>(
+                tb, tc, im->k, im->n_steps, im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V, (char*)I, iters,
+                status, diff, tol, maxiter, pf, im->d_unfed, im->n_unfed, nullptr, 0, nullptr,
+                share ? im->d_alias : nullptr, share ? im->n_alias : 0, im->d_events, im->n_events);
+        else
+            fbs_solve_kernel<BLOCK, false, false><<<gx, BLOCK, 0, st>>>(
+                tb, tc, im->k, im->n_steps, im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V, (char*)I, iters,
+                status, diff, tol, maxiter, pf, im->d_unfed, im->n_unfed, nullptr, 0, nullptr,
+                share ? im->d_alias : nullptr, share ? im->n_alias : 0, nullptr, 0);
     }
     count_launch();
     GP_CUDA(cudaGetLastError());
@@ -2556,7 +2642,10 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
             return GP_OK;
         }
     }
-    int want_chunks = g_host_chunks > 0 ? g_host_chunks : (rows * S * 16 <= ((int64_t)128 << 20) ? 1 : FbsImpl::NSTREAM);
+    // (measured on B200, 123-bus, 140,160 scenarios, 0.8 GB over PCIe: 2 chunks 7.3e6 solves/s, 4: 6.8e6, 8: 5.6e6,
+    // 16: 4.1e6 - the solve of a chunk is latency-bound and takes as long as the whole batch's, and every row piece
+    // is its own DMA, so more and smaller chunks only add overhead)
+    int want_chunks = g_host_chunks > 0 ? g_host_chunks : (rows * S * 16 <= ((int64_t)128 << 20) ? 1 : 2);
     int64_t C = ((S + want_chunks - 1) / want_chunks + 127) / 128 * 128;
     if (C < 32768 && g_host_chunks == 0) C = 32768;
     const int64_t cap = (((int64_t)3 << 30) / (rows * 16)) / 128 * 128;

@@ -112,7 +112,8 @@ int64_t gp_launch_count(void);
  * "nr3_kernel": 0 = automatic (default), 1 = one thread per scenario, 2 = three phase lanes per scenario
  * (Line / Transformer feeders only; automatic for small batches of mostly three-phase feeders).
  * "fbs_prefetch" / "nr3_prefetch": L2 prefetch distance in tree steps of the streaming FBS kernel
- * (default 0) and of the NR3 kernel (default -1 = automatic: 2 for batches up to 65,536).
+ * (default -1 = automatic: 2 for feeders with at least 1,024 V rows, else 0) and of the NR3 kernel
+ * (default -1 = automatic: 2 for batches up to 65,536).
  * "fbs_share_rows": 1 (default) = in the streaming FBS kernel an I row that only repeats a child's current (a
  *   bus-phase without load and capacitor fed by one child edge) or stays zero makes no HBM round trips during
  *   the sweeps and is filled in once at the end; 0 = every row is stored and re-read each sweep.  Same results.

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Tree-walk kernel: parity tests, then register-budget A/B on C4 and C5
 mkdir -p gpurun_out
-T=r02d
+T=r02e
 timeout 900 python -m pytest tests/test_fbs_gpu.py tests/test_big_feeders.py -x -q -m gpu > gpurun_out/${T}_tests.log 2>&1; echo "tests rc=$?"; tail -15 gpurun_out/${T}_tests.log
 for w in c4 c5; do for b in 4 5 6 8; do
   timeout 600 python bench.py --workload $w --fbs-kernel 6 --walk-blocks $b --steps 10 --no-cpu > gpurun_out/${T}_${w}_b$b.json 2> gpurun_out/${T}_${w}_b$b.err || tail -3 gpurun_out/${T}_${w}_b$b.err

@@ -243,7 +243,7 @@ def test_onchip_kernel_full_batch_and_relaunch():
     mult = rng.uniform(0.5, 1.5, size=(S, s.circuit.loads.num_elements))
     s._dev()
     assert _cabi.gp_fbs_onchip_warps(s._feeder.handle) >= 4
-    assert _cabi.gp_fbs_active_kernel(s._feeder.handle) == 3      # nothing specialised yet: streaming
+    assert _cabi.gp_fbs_active_kernel(s._feeder.handle) in (3, 6)      # nothing specialised yet: a streaming kernel
     try:
         _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 3))
         shared = s.solve_batch(load_mult=mult, outputs=('V', 'I'))
