@@ -619,6 +619,8 @@ def run_workload(ctx, args, name, steps, main):
     if args.host_warps:
         _cabi.check(_cabi.gp_set_option(b'host_warps', args.host_warps))
     _cabi.check(_cabi.gp_set_option(b'host_chunks', args.host_chunks))
+    if args.push_streams:
+        _cabi.check(_cabi.gp_set_option(b'peer_push_streams', args.push_streams))
     _cabi.check(_cabi.gp_set_option(b'nr3_kernel', args.nr3_kernel))
     _cabi.check(_cabi.gp_set_option(b'fbs_order', args.fbs_order))
     _cabi.check(_cabi.gp_set_option(b'fbs_walk_blocks', args.walk_blocks))
@@ -1102,6 +1104,8 @@ def main():
                     help='I rows of the specialised FBS kernel in global memory: -1 automatic, 0 no, 1 yes')
     ap.add_argument('--host-warps', type=int, default=0,
                     help='warps per SM of the one-launch host path (e2e); 0 = the library default')
+    ap.add_argument('--push-streams', type=int, default=0,
+                    help='N > 1: copy streams the copy-engine all-gather spreads its destinations over (0 = library default)')
     ap.add_argument('--host-chunks', type=int, default=0,
                     help='pipeline chunks of the staged host path (e2e of feeders without a specialised kernel); 0 = automatic')
     ap.add_argument('--share-rows', type=int, default=1, choices=[0, 1],

@@ -95,7 +95,8 @@ gp_fbs_solve_batch_host = _sig('gp_fbs_solve_batch_host', C.c_int,
 class GpSolveExtras(C.Structure):
     """Optional per-scenario inputs of a solve (include/gigpower_b200.h: GpSolveExtras)."""
     _fields_ = [('gamma_dev', vp), ('warm_start', C.c_int32), ('n_peers', C.c_int32),
-                ('peer_vmag', C.POINTER(vp)), ('peer_loss', C.POINTER(vp)), ('wpu_dev', vp)]
+                ('peer_vmag', C.POINTER(vp)), ('peer_loss', C.POINTER(vp)), ('wpu_dev', vp),
+                ('vv_ctl_dev', vp), ('vv_points', C.c_double * 4), ('vv_q', C.c_double * 2)]
 
 
 GP_MAX_PEERS = 16
@@ -131,22 +132,31 @@ gp_nr3_solve_batch_ex = _sig('gp_nr3_solve_batch_ex', C.c_int,
 gp_nr3_map_output = _sig('gp_nr3_map_output', C.c_int,
                          [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
 
+gp_nr3_map_output_ex = _sig('gp_nr3_map_output_ex', C.c_int,
+                            [vp, C.c_int64, C.c_int64, vp, C.POINTER(GpSolveExtras), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])
+
 EXPORTS = ['gp_version', 'gp_last_error', 'gp_launch_count', 'gp_set_option', 'gp_fbs_active_kernel',
            'gp_fbs_onchip_warps', 'gp_measure_fp64_peak', 'gp_fbs_specialise', 'gp_fbs_jit_source', 'gp_fbs_jit_warps',
            'gp_jit_compile', 'gp_fbs_create', 'gp_feeder_destroy',
            'gp_fbs_solve_batch', 'gp_fbs_solve_post_batch', 'gp_fbs_post', 'gp_fbs_solve_batch_host', 'gp_der_rows', 'gp_vmag_summary', 'gp_nr3_create',
            'gp_nr3_workspace_bytes', 'gp_nr3_solve_batch', 'gp_nr3_map_output',
            'gp_gamma_rows', 'gp_fbs_solve_batch_ex', 'gp_nr3_solve_batch_ex', 'gp_der_rows_strided',
-           'gp_fbs_schedule', 'gp_fbs_walk_events', 'gp_peer_alloc', 'gp_peer_free', 'gp_peer_open', 'gp_peer_close', 'gp_peer_push', 'gp_fbs_post_ex']
+           'gp_fbs_schedule', 'gp_fbs_walk_events', 'gp_nr3_map_output_ex', 'gp_peer_alloc', 'gp_peer_free', 'gp_peer_open', 'gp_peer_close', 'gp_peer_push', 'gp_fbs_post_ex']
 
 
-def make_extras(gamma=None, warm_start=False, peers=None, wpu=None):
+def make_extras(gamma=None, warm_start=False, peers=None, wpu=None, volt_var=None):
     """GpSolveExtras for a device tensor of regulator ratios ``[n_gamma_rows, ld]`` float64, a warm
     start and / or the destinations of the fused all-gather (``peers`` = (|V| pointers, loss pointers),
     two equally long lists of device addresses); returns None when nothing is asked for."""
-    if gamma is None and not warm_start and not peers and wpu is None:
+    if gamma is None and not warm_start and not peers and wpu is None and volt_var is None:
         return None
     ex = GpSolveExtras()
+    if volt_var is not None:        # (int32 device tensor [n_vrows], (V1, V2, V3, V4), minQ, maxQ)
+        ctl, points, minQ, maxQ = volt_var
+        ex._vv_keep = ctl
+        ex.vv_ctl_dev = ctl.data_ptr()
+        ex.vv_points = (C.c_double * 4)(*[float(x) for x in points])
+        ex.vv_q = (C.c_double * 2)(float(minQ), float(maxQ))
     ex.gamma_dev = gamma.data_ptr() if gamma is not None else None
     ex.wpu_dev = wpu.data_ptr() if wpu is not None else None
     ex.warm_start = 1 if warm_start else 0

@@ -27,6 +27,9 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 extern int g_nr3_prefetch;     // gp_nr3.cu
 extern int g_nr3_kernel;
+}  // namespace gp
+extern int g_peer_push_streams;   // gp_peer.cu
+namespace gp {
 int nr3_gamma_rows(GpFeeder* f);   // gp_nr3.cu
 static int g_jit_i_global = -1;    // gp_set_option("jit_i_global", -1|0|1): I rows of the specialised kernel in global memory
 static int g_host_read_ahead = 1;  // gp_set_option("host_read_ahead", 0|1): read-ahead build of the one-launch host path
@@ -65,6 +68,19 @@ __device__ __forceinline__ double cabs2(double2 v, double& a) {
     return a * a;
 }
 
+// VoltVARController.get_Q (volt_var_controller.py:20-38) with the same operations in the same order: maxQ below V1,
+// a ramp to 0 at V2, 0 up to V3, a ramp to minQ at V4, minQ above; the sign is flipped as the reference does.  The
+// ramps' slope and intercept come from the host (same double arithmetic); slope * V + b is two roundings, not an FMA.
+__device__ __forceinline__ double fbs_droop(double a, const FbsConst& k) {
+    double q;
+    if (a <= k.vv_v[0]) q = k.vv_q[1];
+    else if (a <= k.vv_v[1]) q = __dadd_rn(__dmul_rn(k.vv_lo[0], a), k.vv_lo[1]);
+    else if (a <= k.vv_v[2]) q = 0.0;
+    else if (a <= k.vv_v[3]) q = __dadd_rn(__dmul_rn(k.vv_hi[0], a), k.vv_hi[1]);
+    else q = k.vv_q[0];
+    return -q;
+}
+
 // ---- where the state rows live --------------------------------------------------------------
 // The sweep bodies below are written once against a row accessor:
 //   GMem: rows in HBM, [row][ld] complex128 with the scenario innermost.  Row r of scenario s is
@@ -84,8 +100,14 @@ struct GMemT {
     unsigned ldb;
     const char* G;
     const char* W;      // this scenario's column of the per-scenario Solution.wpu rows ([V row][ld] doubles)
-    __device__ __forceinline__ bool hasW() const { return TAPS && W != nullptr; }
-    __device__ __forceinline__ double ldW(int r) const { return __ldg(reinterpret_cast<const double*>(W + (size_t)(unsigned)r * (size_t)(ldb >> 1))); }
+    const int* VV;      // [V row] non-zero = a volt-var controller sets wpu = get_Q(|V|) there at every calc_sV
+    __device__ __forceinline__ bool hasW() const { return TAPS && (W != nullptr || VV != nullptr); }
+    // Solution.wpu of V row r whose voltage magnitude is a: the caller's row, or the droop of the row's controller
+    __device__ __forceinline__ double wq(int r, double a, const FbsConst& k) const {
+        double w = W ? __ldg(reinterpret_cast<const double*>(W + (size_t)(unsigned)r * (size_t)(ldb >> 1))) : 0.0;
+        if (VV && __ldg(VV + r)) w = fbs_droop(a, k);
+        return w;
+    }
     __device__ __forceinline__ bool hasG() const { return TAPS && G != nullptr; }
     __device__ __forceinline__ double ldG(int r) const { return __ldg(reinterpret_cast<const double*>(G + (size_t)(unsigned)r * (size_t)(ldb >> 1))); }
     __device__ __forceinline__ double2 ldV(int r) const { return __ldcg(reinterpret_cast<const double2*>(V + (size_t)(unsigned)r * (size_t)ldb)); }
@@ -104,7 +126,7 @@ using GMem = GMemT<false>;
 struct SMem {
     static constexpr bool kTaps = false;
     __device__ __forceinline__ bool hasW() const { return false; }
-    __device__ __forceinline__ double ldW(int) const { return 0.0; }
+    __device__ __forceinline__ double wq(int, double, const FbsConst&) const { return 0.0; }
     __device__ __forceinline__ bool hasG() const { return false; }
     __device__ __forceinline__ double ldG(int) const { return 0.0; }
     double2* V;         // this lane's column of the warp's V rows (shared memory)
@@ -194,7 +216,7 @@ __device__ __forceinline__ void bwd_fast(const FbsStep* __restrict__ st, const i
                 const double f = k.aPQ + k.aI * a + k.aZ * a2;
                 double2 sv = make_double2(sp[p].x * f, sp[p].y * f);
                 sv.y -= __ldg(&st->cap[p]) * a2;
-                if (m.hasW()) sv.y += m.ldW(brow[p]);           // + 1j * wpu (solution.py:203)
+                if (m.hasW()) sv.y += m.wq(brow[p], a, k);      // + 1j * wpu (solution.py:203)
                 if (v.x != 0.0 || v.y != 0.0) {
                     const double inv = 1.0 / fma(v.x, v.x, v.y * v.y);
                     In[p].x += (sv.x * v.x + sv.y * v.y) * inv;
@@ -343,7 +365,7 @@ __device__ __forceinline__ void fbs_bwd_step(const FbsStep* __restrict__ st, con
         const double f = k.aPQ + k.aI * a + k.aZ * a2;
         double2 sv = make_double2(sp[p].x * f, sp[p].y * f);   // sp = 0 where there is no load
         sv.y -= __ldg(&st->cap[p]) * a2;
-        if (m.hasW()) sv.y += m.ldW(brow[p]);                   // + 1j * wpu (solution.py:203)
+        if (m.hasW()) sv.y += m.wq(brow[p], a, k);              // + 1j * wpu (solution.py:203)
         if (v.x != 0.0 || v.y != 0.0) {
             // conj(sV / V) computed as (sV * conj(V)) / |V|^2, conjugated
             const double inv = 1.0 / fma(v.x, v.x, v.y * v.y);
@@ -420,12 +442,13 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
                  int* __restrict__ status_out, double* __restrict__ diff_out, double tol,
                  int maxiter, int PF, const int* __restrict__ unfed, int n_unfed,
                  const char* __restrict__ gam, int warm, const char* __restrict__ wpu,
-                 const int2* __restrict__ alias, int n_alias, const int2* __restrict__ events, int n_events) {
+                 const int2* __restrict__ alias, int n_alias, const int2* __restrict__ events, int n_events,
+                 const int* __restrict__ vv) {
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (s >= S) return;
     typedef GMemT<EX> GMem;
     const GMem m{V + s * 16, I + s * 16, spu + s * 16, ldb, (EX && gam) ? gam + s * 8 : nullptr,
-                 (EX && wpu) ? wpu + s * 8 : nullptr};
+                 (EX && wpu) ? wpu + s * 8 : nullptr, EX ? vv : nullptr};
     const double2 zero = make_double2(0.0, 0.0);
     if (EX && warm) n_unfed = 0;    // warm start: every V and I row keeps the earlier solution
 
@@ -1364,7 +1387,7 @@ __global__ void fbs_post_rows_kernel(int n_vrows, const int* __restrict__ vrow_s
                                      long long ld, const double2* __restrict__ spu,
                                      const double2* __restrict__ V, double2* __restrict__ sV,
                                      double* __restrict__ Vmag, const PeerDst peers,
-                                     const double* __restrict__ wpu) {
+                                     const double* __restrict__ wpu, const int* __restrict__ vv) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     for (int r = blockIdx.y; r < n_vrows; r += gridDim.y) {
@@ -1385,7 +1408,11 @@ __global__ void fbs_post_rows_kernel(int n_vrows, const int* __restrict__ vrow_s
                 sv.y = sp.y * f;
             }
             sv.y -= __ldg(vrow_cap + r) * a2;
-            if (wpu) sv.y += wpu[(long long)r * ld + s];
+            if (wpu || vv) {                        // + 1j * wpu: the caller's row, or the droop of the row's controller
+                double w = wpu ? wpu[(long long)r * ld + s] : 0.0;
+                if (vv && __ldg(vv + r)) w = fbs_droop(a, k);
+                sv.y += w;
+            }
             sV[(long long)r * ld + s] = sv;
         }
     }
@@ -1439,6 +1466,10 @@ extern "C" int gp_last_error(char* buf, size_t len) {
 extern "C" int64_t gp_launch_count(void) { return g_launches.load(); }
 
 extern "C" int gp_set_option(const char* name, int value) {
+    if (name && strcmp(name, "peer_push_streams") == 0 && value >= 1 && value <= 8) {
+        g_peer_push_streams = value;
+        return GP_OK;
+    }
     if (name && strcmp(name, "fbs_auto_walk") == 0 && (value == 0 || value == 1)) {
         g_fbs_auto_walk = value;
         return GP_OK;
@@ -2323,6 +2354,28 @@ static int peers_from_extras(const GpSolveExtras* ex, PeerDst& pd) {
     return GP_OK;
 }
 
+// GpSolveExtras.vv_* -> the droop fields of the FbsConst copy a launch passes (the ramps' slope and intercept with
+// VoltVARController.get_Q's own operations, volt_var_controller.py:25-33)
+static int droop_from_extras(const GpSolveExtras* ex, FbsConst& k, const int** vv) {
+    *vv = nullptr;
+    for (int i = 0; i < 4; ++i) k.vv_v[i] = 0.0;
+    k.vv_lo[0] = k.vv_lo[1] = k.vv_hi[0] = k.vv_hi[1] = k.vv_q[0] = k.vv_q[1] = 0.0;
+    if (!ex || !ex->vv_ctl_dev) return GP_OK;
+    const double V1 = ex->vv_points[0], V2 = ex->vv_points[1], V3 = ex->vv_points[2], V4 = ex->vv_points[3];
+    if (!(V1 < V2 && V2 <= V3 && V3 < V4))
+        return fail(GP_EINVAL, "GpSolveExtras: volt-var breakpoints need V1 < V2 <= V3 < V4");
+    const double minQ = ex->vv_q[0], maxQ = ex->vv_q[1];
+    k.vv_v[0] = V1; k.vv_v[1] = V2; k.vv_v[2] = V3; k.vv_v[3] = V4;
+    k.vv_lo[0] = (-maxQ) / (V2 - V1);
+    k.vv_lo[1] = -(k.vv_lo[0] * V2);
+    k.vv_hi[0] = (minQ) / (V4 - V3);
+    k.vv_hi[1] = -(k.vv_hi[0] * V3);
+    k.vv_q[0] = minQ;
+    k.vv_q[1] = maxQ;
+    *vv = ex->vv_ctl_dev;
+    return GP_OK;
+}
+
 // Launch the solve kernel; *fused is set when the kernel also produced Vmag / loss.
 static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* spu, double* V, double* I,
                             int32_t* iters, int32_t* status, double* diff, double tol, int32_t maxiter,
@@ -2338,7 +2391,11 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     const char* wpu = ex ? (const char*)ex->wpu_dev : nullptr;
     if (warm != 0 && warm != 1) return fail(GP_EINVAL, "gp_fbs_solve_batch_ex: warm_start must be 0 or 1");
     if (gam && im->n_grows == 0) gam = nullptr;     // no regulators: nothing to read
-    const bool extras = gam || warm || wpu;
+    FbsConst kx = im->k;
+    const int* vv = nullptr;
+    rc = droop_from_extras(ex, kx, &vv);
+    if (rc) return rc;
+    const bool extras = gam || warm || wpu || vv;
     PeerDst pd;
     rc = peers_from_extras(ex, pd);
     if (rc) return rc;
@@ -2364,14 +2421,14 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
         const int pf = g_fbs_prefetch >= 0 ? g_fbs_prefetch : (im->n_vrows >= 1024 ? 2 : 0);
         if (g_fbs_order && im->n_events > 0)
             fbs_solve_kernel<BLOCK, true, true><<<gx, BLOCK, 0, st>>>(
-                im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V,
+                im->d_steps, im->d_child, kx, im->n_steps, im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V,
                 (char*)I, iters, status, diff, tol, maxiter, pf, im->d_unfed, im->n_unfed, gam, warm, wpu, nullptr, 0,
-                im->d_events, im->n_events);
+                im->d_events, im->n_events, vv);
         else
             fbs_solve_kernel<BLOCK, true, false><<<gx, BLOCK, 0, st>>>(
-                im->d_steps, im->d_child, im->k, im->n_steps, im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V,
+                im->d_steps, im->d_child, kx, im->n_steps, im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V,
                 (char*)I, iters, status, diff, tol, maxiter, pf, im->d_unfed, im->n_unfed, gam, warm, wpu, nullptr, 0,
-                nullptr, 0);
+                nullptr, 0, vv);
     } else if ((g_fbs_kernel == 5 || (g_fbs_kernel == 0 && im->jit_kernel)) && (maxiter >= 1 || !im->jit_kernel)) {
         if (!im->jit_kernel)
             return fail(GP_EINVAL, "gp_fbs_solve_batch: fbs_kernel = 5 needs a successful gp_fbs_specialise");
@@ -2451,12 +2508,12 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
             fbs_solve_kernel<BLOCK, false, true><<<gx, BLOCK, 0, st>>>(
                 tb, tc, im->k, im->n_steps, im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V, (char*)I, iters,
                 status, diff, tol, maxiter, pf, im->d_unfed, im->n_unfed, nullptr, 0, nullptr,
-                share ? im->d_alias : nullptr, share ? im->n_alias : 0, im->d_events, im->n_events);
+                share ? im->d_alias : nullptr, share ? im->n_alias : 0, im->d_events, im->n_events, nullptr);
         else
             fbs_solve_kernel<BLOCK, false, false><<<gx, BLOCK, 0, st>>>(
                 tb, tc, im->k, im->n_steps, im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V, (char*)I, iters,
                 status, diff, tol, maxiter, pf, im->d_unfed, im->n_unfed, nullptr, 0, nullptr,
-                share ? im->d_alias : nullptr, share ? im->n_alias : 0, nullptr, 0);
+                share ? im->d_alias : nullptr, share ? im->n_alias : 0, nullptr, 0, nullptr);
     }
     count_launch();
     GP_CUDA(cudaGetLastError());
@@ -2485,7 +2542,7 @@ extern "C" int gp_fbs_solve_post_batch(GpFeeder* f, int64_t S, int64_t ld, const
 
 static int fbs_post_impl(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const double* V, const double* I,
                          double* sV, double* Vmag, double* Stx, double* Srx, double* loss, void* stream,
-                         const PeerDst& pd, const double* wpu = nullptr);
+                         const PeerDst& pd, const double* wpu = nullptr, const GpSolveExtras* ex = nullptr);
 
 extern "C" int gp_fbs_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const GpSolveExtras* ex,
                                      double* V, double* I, int32_t* iters, int32_t* status, double* diff,
@@ -2516,13 +2573,17 @@ extern "C" int gp_fbs_post_ex(GpFeeder* f, int64_t S, int64_t ld, const double* 
                               double* loss, void* stream) {
     PeerDst pd;
     memset(&pd, 0, sizeof(pd));
-    return fbs_post_impl(f, S, ld, spu, V, I, sV, Vmag, Stx, Srx, loss, stream, pd, ex ? ex->wpu_dev : nullptr);
+    return fbs_post_impl(f, S, ld, spu, V, I, sV, Vmag, Stx, Srx, loss, stream, pd, ex ? ex->wpu_dev : nullptr, ex);
 }
 
 static int fbs_post_impl(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const double* V, const double* I,
                          double* sV, double* Vmag, double* Stx, double* Srx, double* loss, void* stream,
-                         const PeerDst& pd, const double* wpu) {
+                         const PeerDst& pd, const double* wpu, const GpSolveExtras* ex) {
     int rc = fbs_check(f, S, ld, "gp_fbs_post");
+    if (rc) return rc;
+    FbsConst kx = ((FbsImpl*)f->impl)->k;
+    const int* vv = nullptr;
+    rc = droop_from_extras(ex, kx, &vv);
     if (rc) return rc;
     if (S == 0) return GP_OK;
     FbsImpl* im = (FbsImpl*)f->impl;
@@ -2534,8 +2595,8 @@ static int fbs_post_impl(GpFeeder* f, int64_t S, int64_t ld, const double* spu, 
     const unsigned gx = (unsigned)((S + BLOCK - 1) / BLOCK);
     if (sV || Vmag || pd.n) {
         dim3 g(gx, 8);
-        fbs_post_rows_kernel<<<g, BLOCK, 0, st>>>(im->n_vrows, im->d_vrow_srow, im->d_vrow_cap, im->k, S, ld,
-                                                  (const double2*)spu, (const double2*)V, (double2*)sV, Vmag, pd, wpu);
+        fbs_post_rows_kernel<<<g, BLOCK, 0, st>>>(im->n_vrows, im->d_vrow_srow, im->d_vrow_cap, kx, S, ld,
+                                                  (const double2*)spu, (const double2*)V, (double2*)sV, Vmag, pd, wpu, vv);
         count_launch();
     }
     if (Stx || Srx || loss || pd.n) {

@@ -43,6 +43,9 @@ struct FbsConst {
     double root_cap[3];
     double2 vref[3];
     double aPQ, aI, aZ;
+    // volt-var droop evaluated inside the iteration (GpSolveExtras.vv_*, set per launch): breakpoints V1..V4, the
+    // two ramps as slope / intercept (computed on the host the way VoltVARController.get_Q does), minQ, maxQ
+    double vv_v[4], vv_lo[2], vv_hi[2], vv_q[2];
 };
 
 struct FbsImpl {

@@ -123,10 +123,13 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                  const double2* __restrict__ spu, double2* __restrict__ X,
                  double2* __restrict__ W, double2* __restrict__ DV, int* __restrict__ iters_out,
                  int* __restrict__ status_out, double* __restrict__ fmax_out, int maxiter, int PF,
-                 const double* __restrict__ gam, int warm) {
+                 const double* __restrict__ gam, int warm, const double* __restrict__ wpu) {
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (s >= S) return;
     const double* Gs = (EX && gam) ? gam + s : nullptr;
+    // per-scenario Solution.wpu rows [V row][ld]: change_KCL_matrices subtracts wpu from the constant term of BOTH
+    // KCL rows of a bus-phase (solution_nr3.py:588)
+    const double* Wp = (EX && wpu) ? wpu + s : nullptr;
     const bool flat = !(EX && warm);
     const double2* spu_s = spu + s;
     double2* Xs = X + s;
@@ -230,10 +233,11 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                     const double pl = sp1.x, ql = sp1.y;
                     const double cA = p == 0 ? k.cA[0] : (p == 1 ? k.cA[1] : k.cA[2]);
                     const double cB = p == 0 ? k.cB[0] : (p == 1 ? k.cB[1] : k.cB[2]);
-                    const double hAr = -pl * cA, hBr = -pl * cB, b0r = -pl * k.betaS;
+                    const double wq = (EX && Wp) ? __ldg(Wp + (long long)rb * ld) : 0.0;
+                    const double hAr = -pl * cA, hBr = -pl * cB, b0r = -pl * k.betaS - wq;
                     const double hAi = -ql * cA + cap * cA;
                     const double hBi = -ql * cB + cap * cB;
-                    const double b0i = (-ql * k.betaS) + (cap * k.betaS);
+                    const double b0i = (-ql * k.betaS) + (cap * k.betaS) - wq;
                     const double fr = A * Cn + B * Dn + hAr * A * A + hBr * B * B + b0r;
                     const double fi = B * Cn - A * Dn + hAi * A * A + hBi * B * B + b0i;
                     nanflag |= (fr != fr) | (fi != fi);
@@ -357,10 +361,11 @@ nr3_solve_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                 const double A = v[p].x, B = v[p].y, Cn = inet[p].x, Dn = inet[p].y;
                 const double pl = spl[p].x, ql = spl[p].y;
                 const double cap = __ldg(&st->cap[p]);
-                const double hAr = -pl * k.cA[p], hBr = -pl * k.cB[p], b0r = -pl * k.betaS;
+                const double wq = (EX && Wp) ? __ldg(Wp + (long long)brow[p] * ld) : 0.0;
+                const double hAr = -pl * k.cA[p], hBr = -pl * k.cB[p], b0r = -pl * k.betaS - wq;
                 const double hAi = -ql * k.cA[p] + cap * k.cA[p];
                 const double hBi = -ql * k.cB[p] + cap * k.cB[p];
-                const double b0i = (-ql * k.betaS) + (cap * k.betaS);
+                const double b0i = (-ql * k.betaS) + (cap * k.betaS) - wq;
                 const double fr = A * Cn + B * Dn + hAr * A * A + hBr * B * B + b0r;
                 const double fi = B * Cn - A * Dn + hAi * A * A + hBi * B * B + b0i;
                 nanflag |= (fr != fr) | (fi != fi);
@@ -1086,7 +1091,8 @@ __global__ void nr3_map_rows_kernel(int n_vrows, int n_irows, const int* __restr
                                     long long ld, const double2* __restrict__ spu,
                                     const double2* __restrict__ X, double2* __restrict__ V,
                                     double2* __restrict__ I, double2* __restrict__ sV,
-                                    double2* __restrict__ iN, double* __restrict__ Vmag) {
+                                    double2* __restrict__ iN, double* __restrict__ Vmag,
+                                    const double* __restrict__ wpu) {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     for (int r = blockIdx.y; r < n_vrows + n_irows; r += gridDim.y) {
@@ -1108,6 +1114,7 @@ __global__ void nr3_map_rows_kernel(int n_vrows, int n_irows, const int* __restr
                 sv.y = sp.y * f;
             }
             sv.y -= __ldg(vrow_cap + r);          // no |V|^2 factor here (map_output.py:60)
+            if (wpu) sv.y += wpu[(long long)r * ld + s];    // + 1j * wpu (map_output.py:60)
             sv = scrub(sv);
             if (sV) sV[(long long)r * ld + s] = sv;
             if (iN) {
@@ -1336,7 +1343,8 @@ extern "C" int gp_nr3_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const d
     const double* gam = (ex && im->n_grows > 0) ? ex->gamma_dev : nullptr;
     const int warm = ex ? ex->warm_start : 0;
     if (warm != 0 && warm != 1) return fail(GP_EINVAL, "gp_nr3_solve_batch_ex: warm_start must be 0 or 1");
-    const bool extras = gam || warm;
+    const double* wpu = ex ? ex->wpu_dev : nullptr;
+    const bool extras = gam || warm || wpu;
     if (!X || !iters || !status || !fmax || !workspace || (!spu && im->n_srows > 0))
         return fail(GP_EINVAL, "gp_nr3_solve_batch: null buffer");
     if (workspace_bytes < gp_nr3_workspace_bytes(f, ld))
@@ -1358,7 +1366,7 @@ extern "C" int gp_nr3_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const d
     if (extras) {
         nr3_solve_kernel<BLOCK, true><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_vrows, im->n_irows, S,
                                                             ld, (const double2*)spu, (double2*)X, W, DV, iters, status,
-                                                            fmax, maxiter, gp_nr3_prefetch_distance(S), gam, warm);
+                                                            fmax, maxiter, gp_nr3_prefetch_distance(S), gam, warm, wpu);
     } else if (phase) {
         if (!im->lines_only)
             return fail(GP_EINVAL, "gp_nr3_solve_batch: the phase-parallel kernel does not handle regulator edges");
@@ -1370,7 +1378,7 @@ extern "C" int gp_nr3_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const d
     } else {
         nr3_solve_kernel<BLOCK, false><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_vrows, im->n_irows, S,
                                                              ld, (const double2*)spu, (double2*)X, W, DV, iters, status,
-                                                             fmax, maxiter, gp_nr3_prefetch_distance(S), nullptr, 0);
+                                                             fmax, maxiter, gp_nr3_prefetch_distance(S), nullptr, 0, nullptr);
     }
     count_launch();
     GP_CUDA(cudaGetLastError());
@@ -1380,6 +1388,13 @@ extern "C" int gp_nr3_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const d
 extern "C" int gp_nr3_map_output(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const double* X,
                                  double* V, double* I, double* Stx, double* Srx, double* sV, double* iN,
                                  double* Vmag, double* loss, void* stream) {
+    return gp_nr3_map_output_ex(f, S, ld, spu, nullptr, X, V, I, Stx, Srx, sV, iN, Vmag, loss, stream);
+}
+
+extern "C" int gp_nr3_map_output_ex(GpFeeder* f, int64_t S, int64_t ld, const double* spu, const GpSolveExtras* ex,
+                                    const double* X, double* V, double* I, double* Stx, double* Srx, double* sV,
+                                    double* iN, double* Vmag, double* loss, void* stream) {
+    const double* wpu = ex ? ex->wpu_dev : nullptr;
     int rc = nr3_check(f, S, ld, "gp_nr3_map_output");
     if (rc) return rc;
     if (S == 0) return GP_OK;
@@ -1394,7 +1409,7 @@ extern "C" int gp_nr3_map_output(GpFeeder* f, int64_t S, int64_t ld, const doubl
         dim3 g(gx, 8);
         nr3_map_rows_kernel<<<g, BLOCK, 0, st>>>(im->n_vrows, im->n_irows, im->d_vrow_srow, im->d_vrow_cap, im->k,
                                                  S, ld, (const double2*)spu, (const double2*)X, (double2*)V,
-                                                 (double2*)I, (double2*)sV, (double2*)iN, Vmag);
+                                                 (double2*)I, (double2*)sV, (double2*)iN, Vmag, wpu);
         count_launch();
     }
     if (Stx || Srx || loss) {

@@ -170,7 +170,7 @@ class SolutionFBS(Solution):
     # ---- batched solve -------------------------------------------------------
     def solve_batch(self, spu=None, load_mult=None, spu_rows=None, outputs=('V', 'Vmag', 'loss'),
                     maxiter=None, tol=None, return_device=False, stream=None, taps=None,
-                    warm_start=None, gather=None, wpu=None) -> BatchResult:
+                    warm_start=None, gather=None, wpu=None, volt_var=None) -> BatchResult:
         """Solve S scenarios from flat start.
 
         Give ONE of: ``spu`` ``[S, nb, 3]`` complex; ``load_mult`` ``[S, n_loads]``
@@ -194,6 +194,11 @@ class SolutionFBS(Solution):
         ``wpu``: per-scenario ``Solution.wpu`` - the controllable reactive injection ``+ 1j * wpu`` of
         ``calc_sV`` (solution.py:106, 203), zero in the reference unless the caller sets the attribute:
         ``[S, nb, 3]`` real pu, or packed ``[n_vrows, S]`` float64 rows (NumPy or CUDA tensor).
+        ``volt_var``: ``(controllers, points, minQ, maxQ)`` - volt-var droop INSIDE the iteration: at every
+        ``(bus name or index, phase)`` of ``controllers`` the injection is ``wpu = VoltVARController.get_Q(|V|)``
+        (volt_var_controller.py:20-38, breakpoints ``points = (V1, V2, V3, V4)``, ``minQ``/``maxQ`` in pu),
+        re-evaluated from the bus's current voltage whenever its power is formed - what the reference's
+        ``SolutionFBS`` computes when its own controller objects are consulted before each ``calc_sV``.
         """
         torch, dev = self._dev()
         t = self.tables
@@ -249,7 +254,18 @@ class SolutionFBS(Solution):
                                          f'[{t.n_vrows}, {ld}]')
                     own = len(gather) > 2 and gather[2] == 'own'
                     peers = pg.own_destination(slot) if own else pg.destinations(slot)
-                extras = _cabi.make_extras(gamma, warm_start is not None, peers, d_wpu)
+                vv = None
+                if volt_var is not None:
+                    ctl, points, minQ, maxQ = volt_var
+                    names = self.circuit.buses.all_names()
+                    flags = np.zeros(t.n_vrows, dtype=np.int32)
+                    for bus, ph in ctl:
+                        b_i = names.index(bus) if isinstance(bus, str) else int(bus)
+                        if t.vrow[b_i, int(ph)] < 0:
+                            raise ValueError(f'bus {names[b_i]} has no phase {ph}')
+                        flags[t.vrow[b_i, int(ph)]] = 1
+                    vv = (torch.from_numpy(flags).to(dev), tuple(points), float(minQ), float(maxQ))
+                extras = _cabi.make_extras(gamma, warm_start is not None, peers, d_wpu, vv)
                 iters = torch.empty(S, dtype=torch.int32, device=dev)
                 status = torch.empty(S, dtype=torch.int32, device=dev)
                 diff = torch.empty(S, dtype=torch.float64, device=dev)

@@ -123,7 +123,7 @@ class SolutionNR3(Solution):
 
     def solve_batch(self, spu=None, load_mult=None, spu_rows=None,
                     outputs=('X', 'V', 'Vmag', 'loss'), maxiter=None, return_device=False,
-                    stream=None, taps=None, warm_start=None) -> Nr3BatchResult:
+                    stream=None, taps=None, warm_start=None, wpu=None) -> Nr3BatchResult:
         """Newton-solve S scenarios from flat start.  Inputs as in
         ``SolutionFBS.solve_batch``; ``outputs`` from X, V, I, Vmag, sV, i_Node,
         Stx, Srx, loss.
@@ -131,7 +131,12 @@ class SolutionNR3(Solution):
         ``taps``: per-scenario regulator tap numbers (``gamma_rows_from_taps``).  ``warm_start``: an
         ``Nr3BatchResult`` of an earlier ``solve_batch(..., return_device=True)`` with X among its
         outputs and the same S: Newton starts from that X (as ``SolutionNR3.solve()`` called a second
-        time starts from ``self.XNR``, solution_nr3.py:598) and updates the same tensor in place."""
+        time starts from ``self.XNR``, solution_nr3.py:598) and updates the same tensor in place.
+        ``wpu``: per-scenario ``Solution.wpu`` (``[S, nb, 3]`` real pu, or packed ``[n_vrows, S]`` float64 rows,
+        NumPy or CUDA tensor): what a reference object computes after ``change_KCL_matrices`` has rewritten the
+        constant term of its KCL rows with a non-zero ``circuit.get_wpu_matrix()`` (``b = ... - wpu`` on the real
+        and the imaginary row of a bus-phase alike, solution_nr3.py:559-588); ``sV`` and ``i_Node`` carry
+        ``+ 1j * wpu`` (nr3_lib/map_output.py:60)."""
         torch, dev = self._dev()
         t = self.tables
         maxiter = self.maxiter if maxiter is None else int(maxiter)
@@ -166,7 +171,21 @@ class SolutionNR3(Solution):
                 else:
                     X = torch.empty((t.n_vrows + t.n_irows, ld), dtype=c128, device=dev)
                 gamma = self.gamma_rows_from_taps(taps, S, dev) if taps is not None else None
-                extras = _cabi.make_extras(gamma, warm_start is not None)
+                d_wpu = None
+                if wpu is not None:
+                    if isinstance(wpu, np.ndarray) or not hasattr(wpu, 'data_ptr'):
+                        w = np.asarray(wpu, dtype=np.float64)
+                        if w.ndim == 3:                    # [S, nb, 3] like Solution.wpu per scenario
+                            b_, p_ = np.nonzero(t.vrow >= 0)
+                            rows_w = np.zeros((t.n_vrows, w.shape[0]))
+                            rows_w[t.vrow[b_, p_]] = w[:, b_, p_].T
+                            w = rows_w
+                        d_wpu = torch.from_numpy(np.ascontiguousarray(w)).to(dev)
+                    else:
+                        d_wpu = wpu.to(device=dev, dtype=f64).contiguous()
+                    if tuple(d_wpu.shape) != (t.n_vrows, ld):
+                        raise ValueError(f'wpu must be [S, nb, 3] or packed [{t.n_vrows}, {ld}], got {tuple(d_wpu.shape)}')
+                extras = _cabi.make_extras(gamma, warm_start is not None, None, d_wpu)
                 iters = torch.empty(S, dtype=torch.int32, device=dev)
                 status = torch.empty(S, dtype=torch.int32, device=dev)
                 fmax = torch.empty(S, dtype=f64, device=dev)
@@ -189,8 +208,9 @@ class SolutionNR3(Solution):
                 loss = torch.empty(S, dtype=c128, device=dev) if 'loss' in want else None
                 if want & {'V', 'I', 'Stx', 'Srx', 'sV', 'i_Node', 'Vmag', 'loss'}:
                     p = lambda x: x.data_ptr() if x is not None else None
-                    _cabi.check(_cabi.gp_nr3_map_output(h, S, ld, d_spu.data_ptr(), X.data_ptr(), p(V), p(I), p(Stx),
-                                                        p(Srx), p(sV), p(iN), p(Vmag), p(loss), st.cuda_stream))
+                    _cabi.check(_cabi.gp_nr3_map_output_ex(
+                        h, S, ld, d_spu.data_ptr(), C.byref(extras) if extras is not None else None, X.data_ptr(), p(V),
+                        p(I), p(Stx), p(Srx), p(sV), p(iN), p(Vmag), p(loss), st.cuda_stream))
                 del work
         res = Nr3BatchResult(tables=t, S=S, iterations=iters, status=status, fmax=fmax,
                              X_rows=X if ('X' in want or warm_start is not None) else None, V_rows=V, I_rows=I, Vmag_rows=Vmag, sV_rows=sV,
@@ -217,8 +237,9 @@ class SolutionNR3(Solution):
         """Not provided (solution_nr3.py:517-590).  The reference rewrites its dense
         H and b tensors in place with ONE scalar `der` / `capacitance` for every bus; this engine never builds
         those tensors.  The same studies are explicit per-scenario inputs here: ``solve_batch(spu=...)`` or
-        ``solve_batch(load_mult=...)`` for loads and DER injections, ``circuit.set_kW`` / ``set_kvar`` for a
-        single snapshot."""
+        ``solve_batch(load_mult=...)`` for loads and DER injections, ``solve_batch(wpu=...)`` for the reactive
+        injection the method subtracts from the constant term (``- wpu``, :588), ``circuit.set_kW`` / ``set_kvar``
+        for a single snapshot."""
         raise NotImplementedError(
             'change_KCL_matrices rewrites the dense NR3 tensors of the reference, which this engine does not build; '
             'pass per-scenario loads / DER injections to solve_batch(spu=... | load_mult=...) instead')

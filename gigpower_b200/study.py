@@ -185,7 +185,7 @@ def volt_var_q(Vmag, points, minQ: float, maxQ: float):
 
 
 class VoltVarStudy:
-    """Quasi-static volt-var droop around the batched FBS solve.
+    """Quasi-static volt-var droop around the batched FBS or NR3 solve.
 
     One controller per listed (bus, phase): after every solve its reactive injection becomes
     ``wpu = get_Q(|V|)`` (``VoltVARController``, volt_var_controller.py:20-38; Q in pu) and the next
@@ -207,13 +207,35 @@ class VoltVarStudy:
             self.ctl.append(row)
         self.points, self.minQ, self.maxQ = tuple(points), float(minQ), float(maxQ)
 
+    def run_in_iteration(self, spu_rows=None, load_mult=None, outputs=('V', 'Vmag'), **kw):
+        """The droop INSIDE the FBS iteration: one solve in which every controlled
+        bus-phase injects ``get_Q(|V|)`` of its current voltage whenever its power is formed
+        (``GpSolveExtras.vv_*``).  Returns (BatchResult, Q ``[n_controllers, S]`` CUDA tensor: the injections at
+        the returned voltages)."""
+        torch, dev = self.sol._dev()
+        t = self.sol.tables
+        if hasattr(t, 'xnr_index'):
+            raise NotImplementedError('the in-iteration droop is an FBS input; NR3 takes wpu rows (run())')
+        names = self.sol.circuit.buses.all_names()
+        ctl = []
+        for row in self.ctl:
+            b, p = np.argwhere(t.vrow == row)[0]
+            ctl.append((int(b), int(p)))
+        r = self.sol.solve_batch(spu_rows=spu_rows, load_mult=load_mult, outputs=tuple(set(outputs) | {'Vmag'}),
+                                 return_device=True, volt_var=(ctl, self.points, self.minQ, self.maxQ), **kw)
+        rows = torch.as_tensor(self.ctl, device=dev, dtype=torch.long)
+        return r, volt_var_q(r.Vmag_rows.index_select(0, rows), self.points, self.minQ, self.maxQ)
+
     def run(self, spu_rows=None, load_mult=None, rounds: int = 4, outputs=('V', 'Vmag')):
         """``rounds`` solves; returns (last BatchResult, Q ``[rounds, n_controllers, S]`` CUDA tensor of the
         injections computed after each round, iterations ``[rounds, S]`` CUDA tensor)."""
         torch, dev = self.sol._dev()
         t = self.sol.tables
         rows = torch.as_tensor(self.ctl, device=dev, dtype=torch.long)
-        want = tuple(set(outputs) | {'V', 'I', 'Vmag'})
+        # the state a warm start continues from: V and I rows (FBS), X rows (NR3, whose wpu enters the constant
+        # term of the KCL rows, solution_nr3.py:588)
+        state = {'X'} if hasattr(t, 'xnr_index') else {'V', 'I'}
+        want = tuple(set(outputs) | state | {'Vmag'})
         prev, wpu, Q, its = None, None, [], []
         for _ in range(int(rounds)):
             prev = self.sol.solve_batch(spu_rows=spu_rows, load_mult=load_mult, outputs=want, return_device=True,

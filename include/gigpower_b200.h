@@ -284,6 +284,16 @@ int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const double* sp
  *   zero (circuit.py:164-171) but it is a plain attribute of the object; a caller that sets it - a volt-var
  *   droop evaluated between solves, volt_var_controller.py:20-38 - gets this term.  Runs on the streaming
  *   kernel; gp_fbs_post_ex gives the matching sV.
+ * vv_ctl_dev, vv_points, vv_q (FBS): volt-var droop INSIDE the iteration.  On the flagged V rows
+ *   Solution.wpu is not an input but wpu = VoltVARController.get_Q(|V|) (volt_var_controller.py:20-38: maxQ below
+ *   V1, a ramp to 0 at V2, 0 up to V3, a ramp to minQ at V4, minQ above, sign flipped), re-evaluated from the bus's
+ *   current voltage every time its power is formed - in every backward step of every sweep and in the final sV of
+ *   gp_fbs_post_ex - which is what the reference's SolutionFBS does when its own controller objects are consulted
+ *   before each calc_sV (oracle/make_golden_vvc_iter.py).  Runs on the streaming kernel.
+ * wpu_dev (NR3): the same rows in SolutionNR3.  There wpu reaches the solve through change_KCL_matrices, which
+ *   subtracts it from the constant term of BOTH KCL rows of a bus-phase (b = -load beta_S + cap gamma_S - wpu for
+ *   the real and for the imaginary row alike, solution_nr3.py:559-588), and reaches sV as + j wpu
+ *   (nr3_lib/map_output.py:60; gp_nr3_map_output_ex).  Runs on the thread-per-scenario kernel.
  *
  * n_peers, peer_vmag, peer_loss: the path's one exchange (the all-gather of per-scenario
  *   voltage magnitudes and losses across the GPUs of a box) fused into the solve.  Each destination is
@@ -302,7 +312,11 @@ typedef struct {
     int32_t n_peers;            /* fused all-gather of |V| and losses: number of destinations (0 = none)     */
     double* const* peer_vmag;   /* host array [n_peers] of device pointers, each a [n_vrows][ld] double block */
     double* const* peer_loss;   /* host array [n_peers] of device pointers, each a [S] complex block          */
-    const double* wpu_dev;      /* FBS: [n_vrows][ld] doubles, Solution.wpu per scenario (NULL = zeros)       */
+    const double* wpu_dev;      /* [n_vrows][ld] doubles, Solution.wpu per scenario (NULL = zeros)            */
+    const int32_t* vv_ctl_dev;  /* FBS: [n_vrows] int32 on the device, non-zero = a volt-var controller on this  */
+                                /* V row (NULL = none); its wpu is get_Q(|V|) at every calc_sV, see above       */
+    double vv_points[4];        /* the controllers' voltage breakpoints V1 < V2 <= V3 < V4 (pu)                  */
+    double vv_q[2];             /* minQ, maxQ (pu)                                                              */
 } GpSolveExtras;
 
 /*
@@ -313,8 +327,10 @@ typedef struct {
  *   gp_peer_open   map a peer's allocation into this process (on this process' current device `device`,
  *                  peer access over NVLink is enabled on demand); gp_peer_close unmaps it;
  *   gp_peer_push   copy-engine all-gather step for results that already sit in device memory: copies
- *                  `bytes` from src_dev to dst[q] for every q, asynchronously on `stream` (DMA over NVLink,
- *                  no SM involved).
+ *                  `bytes` from src_dev to dst[q] for every q, asynchronously with respect to the host and ordered
+ *                  in `stream` (DMA over NVLink, no SM involved).  The destinations are spread over
+ *                  "peer_push_streams" internal copy streams (gp_set_option, 1..8, default 1: more were measured slower) that fork from and
+ *                  join back into `stream`, so that several copy engines work at once.
  */
 #define GP_PEER_HANDLE_BYTES 64
 int gp_peer_alloc(int device, int64_t bytes, void** ptr_out, void* handle_out);
@@ -448,6 +464,11 @@ int gp_nr3_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const double* spu_
 int gp_nr3_map_output(GpFeeder* f, int64_t S, int64_t ld, const double* spu_dev, const double* X_dev,
                       double* V_dev, double* I_dev, double* Stx_dev, double* Srx_dev, double* sV_dev,
                       double* iNode_dev, double* Vmag_dev, double* loss_dev, void* stream);
+/* gp_nr3_map_output with GpSolveExtras.wpu_dev added to sV (+ 1j * wpu, map_output.py:60) and through it to i_Node
+ * (extras may be NULL; its other fields are ignored). */
+int gp_nr3_map_output_ex(GpFeeder* f, int64_t S, int64_t ld, const double* spu_dev, const GpSolveExtras* extras,
+                         const double* X_dev, double* V_dev, double* I_dev, double* Stx_dev, double* Srx_dev,
+                         double* sV_dev, double* iNode_dev, double* Vmag_dev, double* loss_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -255,9 +255,17 @@ class FBSOracle:
         self.nrows_I = c.nl + c.ntf + c.nvr                                       # circuit.py:173-184
 
     # solution.py:177-220
-    def _calc_sV(self, V, spu, b=None, wpu=None):
+    def _calc_sV(self, V, spu, b=None, wpu=None, droop=None):
         c = self.c
         w = c.wpu if wpu is None else wpu          # Solution.wpu (solution.py:106, 188-203): [nb,3] or [S,nb,3]
+        if droop is not None:
+            # volt-var controllers that set wpu = get_Q(|V|) every time calc_sV is evaluated (the hook of
+            # oracle/make_golden_vvc_iter.py around the reference's calc_sV): droop = (ctl, points, minQ, maxQ)
+            ctl, points, minQ, maxQ = droop
+            w = np.broadcast_to(w, V.shape).copy() if np.ndim(w) == 2 else np.array(w, dtype=float)
+            for k, p in ctl:
+                if b is None or k == b:
+                    w[:, k, p] = vvc_get_Q(np.abs(V[:, k, p]), points, minQ, maxQ)
         if b is None:
             aV = np.abs(V)
             upd = spu * (c.aPQ + c.aI * aV + c.aZ * aV ** 2) - 1j * c.cappu * aV ** 2 + 1j * w
@@ -269,7 +277,7 @@ class FBSOracle:
         upd[:, c.bus_pm[b] == 0] = 0
         return upd
 
-    def _sweep(self, V, I, spu, wpu=None):
+    def _sweep(self, V, I, spu, wpu=None, droop=None):
         """One pass of the while-body of ``solve`` (:88-121) on arrays
         ``V[S,nb,3]``, ``I[S,rows,3]`` in place."""
         c = self.c
@@ -285,14 +293,14 @@ class FBSOracle:
                     _, row, Z, _pm = e
                     newV = V[:, bus] - np.einsum('ij,sj->si', Z, I[:, row])
                     V[:, child] = newV * c.bus_pm[child]
-        sV = self._calc_sV(V, spu, wpu=wpu)                                       # :101
+        sV = self._calc_sV(V, spu, wpu=wpu, droop=droop)                          # :101
         for bus in reversed(self.topo_order):                                     # :104-121
             parents = self.parents.get(bus, [])
             if len(parents) > 1:
                 raise ValueError(f"Network not radial. Bus {bus} has parents {parents}")
             if len(parents) == 1:
                 parent = parents[0]
-                sV[:, bus] = self._calc_sV(V, spu, bus, wpu=wpu)                  # :114
+                sV[:, bus] = self._calc_sV(V, spu, bus, wpu=wpu, droop=droop)     # :114
                 e = self.edge[(parent, bus)]
                 if e[0] == 'vr':
                     # vr_current :234-254 -> Itx stays 0 (aliased row never written)
@@ -319,7 +327,7 @@ class FBSOracle:
                 V[:, parent] = V[:, parent] * c.bus_pm[parent]
         return V, I
 
-    def solve(self, spu=None, maxiter=MAXITER, V0=None, I0=None, wpu=None):
+    def solve(self, spu=None, maxiter=MAXITER, V0=None, I0=None, wpu=None, droop=None):
         """Flat-start solve of ``S`` scenarios; ``spu[S,nb,3]`` complex (default:
         the feeder's nominal loads, ``S=1``).  Each scenario stops at its own
         iteration exactly as a separate reference object would.
@@ -328,7 +336,10 @@ class FBSOracle:
         ``iterations`` are reset before ``solve()`` is called again: ``self.V`` and
         ``self.I`` keep the earlier solution (:76-90 never re-initialise them).
         ``wpu[S,nb,3]`` real: per-scenario ``Solution.wpu`` (the controllable reactive
-        injection of ``calc_sV``, solution.py:106, 203; all zeros unless a caller sets it)."""
+        injection of ``calc_sV``, solution.py:106, 203; all zeros unless a caller sets it).
+        ``droop = (ctl, points, minQ, maxQ)``: volt-var controllers at the (bus, phase) pairs ``ctl`` whose
+        injection is ``wpu = VoltVARController.get_Q(|V|)`` (volt_var_controller.py:20-38) re-evaluated from the
+        current voltage at every ``calc_sV``, i.e. inside every sweep."""
         c = self.c
         if spu is None:
             spu = c.spu_matrix()[None]
@@ -345,7 +356,7 @@ class FBSOracle:
         active = (~converged) & (iters < maxiter)
         while active.any():                                                       # :87
             idx = np.nonzero(active)[0]
-            Vs, Is = self._sweep(V[idx], I[idx], spu[idx], None if wpu is None else wpu[idx])
+            Vs, Is = self._sweep(V[idx], I[idx], spu[idx], None if wpu is None else wpu[idx], droop)
             V[idx], I[idx] = Vs, Is
             iters[idx] += 1                                                       # :123
             Vtest[idx] = Vs[:, self.root]                                         # :125
@@ -353,7 +364,7 @@ class FBSOracle:
                 diff[idx] = np.max(np.abs(Vtest[idx] - self.Vref), axis=1)        # :126
                 converged[idx] = diff[idx] <= self.tolerance                      # :128
             active = (~converged) & (iters < maxiter)
-        sV = self._calc_sV(V, spu, wpu=wpu)                                       # :132
+        sV = self._calc_sV(V, spu, wpu=wpu, droop=droop)                          # :132
         Vmag = np.abs(V)                                                          # solution.py:232
         nl = c.nl
         Srx = V[:, c.line_rx] * np.conj(I[:, :nl])                                # solution.py:227-230

@@ -97,7 +97,9 @@ class NR3TreeOracle:
         absent = [(k, ph) for k in range(1, c.nb) for ph in range(3) if c.bus_pm[k][ph] == 0]
         self.f0_absent = max([max(abs(VSLACK[ph].real), abs(VSLACK[ph].imag)) for _, ph in absent] + [0.0])
 
-    def solve(self, spu=None, maxiter=MAXITER):
+    def solve(self, spu=None, maxiter=MAXITER, wpu=None):
+        """``wpu[S, nb, 3]`` real: per-scenario ``Solution.wpu`` as ``change_KCL_matrices`` enters it, subtracted
+        from the constant term of both KCL rows of a bus-phase (solution_nr3.py:588)."""
         c = self.c
         if spu is None:
             spu = c.spu_matrix()[None]
@@ -114,7 +116,8 @@ class NR3TreeOracle:
         first = True
         while active.any():
             idx = np.nonzero(active)[0]
-            Vn, Iin_n, Iout_n, fmax = self._newton_step(V[idx], Iin[idx], Iout[idx], spu[idx], first)
+            Vn, Iin_n, Iout_n, fmax = self._newton_step(V[idx], Iin[idx], Iout[idx], spu[idx], first,
+                                                        None if wpu is None else np.asarray(wpu)[idx])
             V[idx], Iin[idx], Iout[idx] = Vn, Iin_n, Iout_n
             iters[idx] += 1
             with np.errstate(invalid='ignore'):
@@ -152,7 +155,7 @@ class NR3TreeOracle:
         """[S] x 4 -> [S,2,2]"""
         return np.stack([np.stack([a, b], -1), np.stack([c_, d], -1)], -2)
 
-    def _newton_step(self, V, Iin, Iout, spu, first):
+    def _newton_step(self, V, Iin, Iout, spu, first, wpu=None):
         c = self.c
         S = V.shape[0]
         beta_S = c.aPQ_p
@@ -178,6 +181,8 @@ class NR3TreeOracle:
             hAi = -q_ * self.cA + cap * self.cA
             hBi = -q_ * self.cB + cap * self.cB
             b0i = (-q_ * beta_S) + (cap * beta_S)
+            if wpu is not None:                                   # b = b_temp - wpu, both rows (:588)
+                b0r, b0i = b0r - wpu[:, k], b0i - wpu[:, k]
             fr = (A * Cn + B * Dn + hAr * A ** 2 + hBr * B ** 2 + b0r) * pm      # KCL residual (:265-299)
             fi = (B * Cn - A * Dn + hAi * A ** 2 + hBi * B ** 2 + b0i) * pm
             r2 = np.stack([fr, fi], axis=-1).reshape(S, 6)

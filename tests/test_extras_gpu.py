@@ -317,3 +317,121 @@ def test_volt_var_study_batch_matches_oracle_loop():
     assert rel_err(Qg.cpu().numpy().transpose(0, 2, 1), Q) <= TOL
     assert rel_err(last.V, V[-1]) <= TOL
     assert np.abs(Q).max() > 0.01 and (its[-1] <= its[0]).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# wpu in SolutionNR3 (change_KCL_matrices' "- wpu" and map_output's "+ 1j wpu")
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('feeder', ['IEEE_13_Bus_allwye_noxfm_noreg', 'IEEE_13_Bus_allwye', 'IEEE_37_Bus_allwye_noxfm_noreg'])
+def test_nr3_reactive_injection_matches_reference_objects(feeder):
+    """tests/golden/ref_wpu_nr3.npz: unmodified reference SolutionNR3 objects whose circuit reports a non-zero wpu
+    matrix, after the reference's own change_KCL_matrices (oracle/make_golden_wpu_nr3.py)."""
+    import os
+    from helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'ref_wpu_nr3.npz'))
+    s = _nr3(feeder, taps=WARM_FEEDERS.get(feeder, {}))
+    r = s.solve_batch(load_mult=g[feeder + '/mult'], wpu=g[feeder + '/wpu'], outputs=('X', 'V', 'sV', 'i_Node'))
+    assert list(r.iterations) == list(g[feeder + '/NR3/iterations'])
+    assert rel_err(r.XNR, g[feeder + '/NR3/XNR']) <= TOL and rel_err(r.V, g[feeder + '/NR3/V']) <= TOL
+    assert rel_err(r.sV, g[feeder + '/NR3/sV']) <= TOL and rel_err(r.i_Node, g[feeder + '/NR3/i_Node']) <= TOL
+    r0 = s.solve_batch(load_mult=g[feeder + '/mult'], outputs=('X',))
+    assert rel_err(r0.XNR, g[feeder + '/NR3/XNR']) > 1e-5       # the term is really applied
+
+
+def test_nr3_reactive_injection_random_batch_matches_tree_oracle():
+    import torch
+    from oracle.nr3_tree import NR3TreeOracle
+    feeder, S = 'IEEE_34_Bus_allwye_noxfm_noreg', 300
+    rng = np.random.Generator(np.random.PCG64(52))
+    o = NR3TreeOracle(load_model(feeder), ZIPS['test_zip'])
+    c = o.c
+    mult = rng.uniform(0.5, 1.2, size=(S, len(c.load_names)))
+    wpu = rng.uniform(-0.02, 0.02, size=(S, c.nb, 3)) * (c.bus_pm[None] != 0) * (rng.uniform(size=(S, c.nb, 3)) < 0.3)
+    wpu[:, 0] = 0
+    want = o.solve(c.spu_matrix(c.load_kw * mult, c.load_kvar * mult), wpu=wpu)
+    s = _nr3(feeder)
+    r = s.solve_batch(load_mult=mult, wpu=wpu, outputs=('X',))
+    assert np.array_equal(r.iterations, want['iterations'])
+    assert rel_err(r.XNR, want['XNR']) <= TOL
+    b, p = np.nonzero(s.tables.vrow >= 0)
+    rows = np.zeros((s.tables.n_vrows, S))
+    rows[s.tables.vrow[b, p]] = wpu[:, b, p].T
+    r2 = s.solve_batch(load_mult=mult, wpu=torch.from_numpy(rows).cuda(), outputs=('X',))
+    assert np.array_equal(np.asarray(r2.X_rows), np.asarray(r.X_rows))
+    with pytest.raises(ValueError):
+        s.solve_batch(load_mult=mult, wpu=rows[:, :5])
+
+
+def test_volt_var_study_runs_on_nr3_too():
+    """The quasi-static droop loop (solve, wpu = get_Q(|V|), solve again from the last X) around SolutionNR3:
+    every round is held to the tree oracle given the same wpu, and the injections move the controlled voltages
+    towards the dead band."""
+    from oracle.nr3_tree import NR3TreeOracle
+    from gigpower_b200.study import VoltVarStudy, volt_var_q
+    feeder, S, rounds = 'IEEE_13_Bus_allwye_noxfm_noreg', 64, 3
+    rng = np.random.Generator(np.random.PCG64(62))
+    o = NR3TreeOracle(load_model(feeder), ZIPS['test_zip'])
+    c = o.c
+    mult = rng.uniform(0.8, 1.6, size=(S, len(c.load_names)))
+    s = _nr3(feeder)
+    pts = (0.93, 0.97, 1.0, 1.04)
+    study = VoltVarStudy(s, [('675', 0), ('675', 1), ('675', 2)], points=pts, minQ=-0.1, maxQ=0.1)
+    last, Q, its = study.run(load_mult=mult, rounds=rounds, outputs=('X', 'Vmag'))
+    Q = Q.cpu().numpy()                                     # [rounds, 3, S]
+    assert np.abs(Q).max() > 0.01
+    # the last round's solve used wpu = Q[rounds - 2]: flat-started oracle with that wpu gives the same X (Newton
+    # converges to the same solution from either start)
+    k = c.bus_names.index('675')
+    wpu = np.zeros((S, c.nb, 3))
+    wpu[:, k, :] = Q[rounds - 2].T
+    want = o.solve(c.spu_matrix(c.load_kw * mult, c.load_kvar * mult), wpu=wpu)
+    assert rel_err(last.XNR, want['XNR']) <= 1e-8
+
+
+# ---------------------------------------------------------------------------------------------
+# volt-var droop inside the FBS iteration (GpSolveExtras.vv_*)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('feeder', ['IEEE_13_Bus_allwye_noxfm_noreg', 'IEEE_13_Bus_allwye', 'IEEE_37_Bus_allwye_noxfm_noreg'])
+def test_droop_inside_the_iteration_matches_the_reference_with_its_controllers(feeder):
+    """tests/golden/ref_vvc_iter.npz (oracle/make_golden_vvc_iter.py): the reference's SolutionFBS with its own
+    VoltVARController objects consulted before every calc_sV - including scenarios in which the droop keeps
+    the sweep from converging within maxiter (equal status and iteration counts)."""
+    import os
+    from helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'ref_vvc_iter.npz'))
+    s = _fbs(feeder, taps=WARM_FEEDERS.get(feeder, {}))
+    ctl = [tuple(int(v) for v in x) for x in g[feeder + '/ctl']]
+    minQ, maxQ = g['q']
+    r = s.solve_batch(load_mult=g[feeder + '/mult'], outputs=('V', 'I', 'sV'),
+                      volt_var=(ctl, tuple(g['points']), minQ, maxQ))
+    want_it = g[feeder + '/iterations']
+    assert list(r.iterations) == list(want_it)
+    ok = want_it < 100
+    assert (r.status[ok] == 0).all() and (r.status[~ok] != 0).all()
+    assert rel_err(r.V, g[feeder + '/V']) <= TOL and rel_err(r.sV, g[feeder + '/sV']) <= TOL
+    assert rel_err(r.I, g[feeder + '/I'][:, :r.I.shape[1]]) <= TOL
+    r0 = s.solve_batch(load_mult=g[feeder + '/mult'], outputs=('V',))
+    assert rel_err(r0.V, g[feeder + '/V']) > 1e-5
+
+
+def test_droop_inside_the_iteration_random_batch_matches_oracle():
+    from oracle.gp_oracle import FBSOracle
+    from gigpower_b200.study import VoltVarStudy
+    feeder, S = 'IEEE_34_Bus_allwye_noxfm_noreg', 500
+    rng = np.random.Generator(np.random.PCG64(71))
+    o = FBSOracle(load_model(feeder), ZIPS['test_zip'])
+    c = o.c
+    mult = rng.uniform(0.4, 1.2, size=(S, len(c.load_names)))
+    three = [k for k in range(1, c.nb) if c.bus_pm[k].all()]
+    ctl = [(three[len(three) // 3], 0), (three[len(three) // 3], 2), (three[-1], 1), (three[-2], 0)]
+    pts, minQ, maxQ = (0.92, 0.96, 1.0, 1.04), -0.03, 0.03
+    want = o.solve(c.spu_matrix(c.load_kw * mult, c.load_kvar * mult), droop=(ctl, pts, minQ, maxQ))
+    s = _fbs(feeder)
+    study = VoltVarStudy(s, ctl, points=pts, minQ=minQ, maxQ=maxQ)
+    r, Q = study.run_in_iteration(load_mult=mult, outputs=('V', 'Vmag'))
+    it, st = r.iterations.cpu().numpy(), r.status.cpu().numpy()
+    assert np.array_equal(it, want['iterations'])
+    ok = st == 0
+    assert ok.sum() > S // 2
+    assert rel_err(r.V[ok], want['V'][ok]) <= TOL
+    assert float(Q.abs().max()) > 1e-3

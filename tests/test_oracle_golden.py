@@ -287,3 +287,45 @@ def test_volt_var_loop_matches_the_reference_controller(feeder):
     assert np.abs(np.swapaxes(Q, 0, 1) - g[feeder + '/VVC/Q']).max() <= TOL
     assert np.abs(Q).max() > 1e-3            # the droop is active in these cases
     assert vvc_get_Q(np.array([0.9, 1.0, 1.1]), (0.95, 0.98, 1.02, 1.05), -0.05, 0.05).tolist() == [-0.05, -0.0, 0.05]
+
+
+@pytest.mark.parametrize('feeder', ['IEEE_13_Bus_allwye_noxfm_noreg', 'IEEE_13_Bus_allwye', 'IEEE_37_Bus_allwye_noxfm_noreg'])
+def test_nr3_tree_oracle_with_wpu_matches_the_reference(feeder):
+    """tests/golden/ref_wpu_nr3.npz (oracle/make_golden_wpu_nr3.py): unmodified reference SolutionNR3 objects whose
+    circuit reports a non-zero wpu matrix, after the reference's own change_KCL_matrices has written ``- wpu``
+    into the constant term of their KCL rows.  The tree oracle's ``wpu`` argument must reproduce them, and the
+    injection must matter (the same loads without it give a different answer)."""
+    import os
+    from helpers import GOLDEN, load_model, ZIPS
+    from oracle.nr3_tree import NR3TreeOracle
+    g = np.load(os.path.join(GOLDEN, 'ref_wpu_nr3.npz'))
+    o = NR3TreeOracle(load_model(feeder), ZIPS['test_zip'])
+    mult, wpu = g[feeder + '/mult'], g[feeder + '/wpu']
+    spu = o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult)
+    r = o.solve(spu, wpu=wpu)
+    assert list(r['iterations']) == list(g[feeder + '/NR3/iterations'])
+    assert np.abs(r['XNR'] - g[feeder + '/NR3/XNR']).max() <= 1e-11
+    r0 = o.solve(spu)
+    assert np.abs(r0['XNR'] - g[feeder + '/NR3/XNR']).max() >= 1e-5
+
+
+@pytest.mark.parametrize('feeder', ['IEEE_13_Bus_allwye_noxfm_noreg', 'IEEE_13_Bus_allwye', 'IEEE_37_Bus_allwye_noxfm_noreg'])
+def test_fbs_oracle_with_droop_inside_the_iteration_matches_the_reference(feeder):
+    """tests/golden/ref_vvc_iter.npz (oracle/make_golden_vvc_iter.py): the reference's SolutionFBS with its own
+    VoltVARController objects consulted before every calc_sV.  The oracle's ``droop`` argument reproduces V, I, sV,
+    the iteration counts and the final injections."""
+    import os
+    from helpers import GOLDEN, load_model, ZIPS
+    from oracle.gp_oracle import FBSOracle, vvc_get_Q
+    g = np.load(os.path.join(GOLDEN, 'ref_vvc_iter.npz'))
+    o = FBSOracle(load_model(feeder), ZIPS['test_zip'])
+    mult = g[feeder + '/mult']
+    ctl = [tuple(int(v) for v in x) for x in g[feeder + '/ctl']]
+    minQ, maxQ = g['q']
+    spu = o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult)
+    r = o.solve(spu, droop=(ctl, tuple(g['points']), minQ, maxQ))
+    assert list(r['iterations']) == list(g[feeder + '/iterations'])
+    for k in ('V', 'I', 'sV'):
+        assert np.abs(r[k] - g[feeder + '/' + k]).max() <= 1e-12, k
+    Q = np.stack([vvc_get_Q(np.abs(r['V'][:, k, p]), tuple(g['points']), minQ, maxQ) for k, p in ctl], axis=1)
+    assert np.abs(Q - g[feeder + '/Q']).max() <= 1e-12 and np.abs(Q).max() > 1e-3
