@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(BLOCK)
 nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ childs, Nr3Const k,
                  long long S, long long ld, const double2* __restrict__ spu, double2* __restrict__ X,
                  double2* __restrict__ W, double2* __restrict__ DV, int* __restrict__ iters_out,
-                 int* __restrict__ status_out, double* __restrict__ fmax_out, int maxiter) {
+                 int* __restrict__ status_out, double* __restrict__ fmax_out, int maxiter, int PF) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * BLOCK + threadIdx.x) >> 5;
     const int j = lane % 10;
@@ -719,6 +719,13 @@ nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
     const double2 my_slack = g == 0 ? k.vslack[0] : (g == 1 ? k.vslack[1] : k.vslack[2]);
     const double my_cA = g == 0 ? k.cA[0] : (g == 1 ? k.cA[1] : k.cA[2]);
     const double my_cB = g == 0 ? k.cB[0] : (g == 1 ? k.cB[1] : k.cB[2]);
+    // L2 prefetch, PF steps ahead, of the rows of this lane's phase that were written a sweep ago: X rows and the load
+    // in the backward sweep, the step's front and X rows in the forward sweep.  At the BASELINE batch sizes a scenario's
+    // state is far beyond its share of L2 (C3: 20 kB per scenario, 330 MB in all), so each of them is a DRAM round trip
+    // that the three warps per scheduler this kernel's registers allow cannot hide.
+    auto pf = [&](const double2* base, long long row) {
+        if (row >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + row * ld));
+    };
 
     // flat start (solution_nr3.py:37-82)
     if (owner) {
@@ -741,6 +748,15 @@ nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
         bool nanl = false;
         // ================= backward sweep =================
         for (int pos = n_steps - 1; pos >= 0; --pos) {
+            if (PF > 0 && pos >= PF) {
+                const Nr3Step* sn = steps + (pos - PF);
+                const int b2 = pick3(__ldg(reinterpret_cast<const int4*>(sn->bus_row)), g);
+                if (b2 >= 0) {
+                    pf(Xs, b2);
+                    pf(Xs, pick3(__ldg(reinterpret_cast<const int4*>(sn->edge_row)), g));
+                    pf(spu_s, pick3(__ldg(reinterpret_cast<const int4*>(sn->load_srow)), g));
+                }
+            }
             const Nr3Step* st = steps + pos;
             const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_row));
             const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_row));
@@ -998,6 +1014,20 @@ nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
         }
         __syncwarp();       // the dv of a parent is read by the other two lanes of the scenario below
         for (int pos = 0; pos < n_steps; ++pos) {
+            if (PF > 0 && pos + PF < n_steps) {
+                const Nr3Step* sn = steps + (pos + PF);
+                const int4 b2 = __ldg(reinterpret_cast<const int4*>(sn->bus_row));
+                if (pick3(b2, g) >= 0) {
+                    const double2* Wn = Ws + (long long)(pos + PF) * FRONT_D2 * ld;
+                    pf(Xs, pick3(b2, g));
+                    pf(Xs, pick3(__ldg(reinterpret_cast<const int4*>(sn->edge_row)), g));
+                    pf(Wn, 18 + g);
+                    pf(Wn, 21 + g);
+                    if (b2.x >= 0) { pf(Wn, (2 * g) * 3 + 0); pf(Wn, (2 * g + 1) * 3 + 0); }
+                    if (b2.y >= 0) { pf(Wn, (2 * g) * 3 + 1); pf(Wn, (2 * g + 1) * 3 + 1); }
+                    if (b2.z >= 0) { pf(Wn, (2 * g) * 3 + 2); pf(Wn, (2 * g + 1) * 3 + 2); }
+                }
+            }
             const Nr3Step* st = steps + pos;
             const int4 bv = __ldg(reinterpret_cast<const int4*>(st->bus_row));
             const int4 pv = __ldg(reinterpret_cast<const int4*>(st->par_row));
@@ -1374,7 +1404,8 @@ extern "C" int gp_nr3_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const d
         const long long warps = (S + 9) / 10;
         const unsigned gp2 = (unsigned)((warps * 32 + PB - 1) / PB);
         nr3_phase_kernel<PB><<<gp2, PB, 0, st>>>(im->d_steps, im->d_child, im->k, S, ld, (const double2*)spu,
-                                                 (double2*)X, W, DV, iters, status, fmax, maxiter);
+                                                 (double2*)X, W, DV, iters, status, fmax, maxiter,
+                                                 gp_nr3_prefetch_distance(S));
     } else {
         nr3_solve_kernel<BLOCK, false><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_vrows, im->n_irows, S,
                                                              ld, (const double2*)spu, (double2*)X, W, DV, iters, status,

@@ -73,6 +73,15 @@ def small_abs_err(a, b, floor=1e-6):
     return float(np.max(np.abs(a[m] - b[m]))) if m.any() else 0.0
 
 
+def assert_close(a, b, tol=1e-9, what='', small=1e-13):
+    """The parity bar on one result array, three ways: rel_err (absolute below 1 pu, the bar of BASELINE.json on
+    voltages), STRICTLY relative above 1e-6 pu (currents and powers of 1e-2 pu are not let off 100x easier) and
+    absolute on the entries below that floor (structural zeros, absent phases)."""
+    assert rel_err(a, b) <= tol, (what, 'rel_err', rel_err(a, b))
+    assert true_rel_err(a, b) <= tol, (what, 'true_rel_err', true_rel_err(a, b))
+    assert small_abs_err(a, b) <= small, (what, 'small_abs_err', small_abs_err(a, b))
+
+
 def ref_123():
     """tests/golden/ref_123.npz (oracle/make_golden_123.py): the unmodified reference's FBS and NR3 on
     the authored IEEE 123-bus feeder and its FBS on the 2,541-bus feeder."""

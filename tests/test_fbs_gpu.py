@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from helpers import (ZIPS, ALL_FEEDERS, LINES_ONLY, feeder_path, load_model, snapshots, scenarios, rel_err,
-                     recorded, pinned_34, pinned_34_taps)
+                     recorded, pinned_34, pinned_34_taps, assert_close)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -33,7 +33,7 @@ def test_snapshot_matches_reference(feeder, zname):
     assert abs(s.convergence_diff - float(snap[k + 'convergence_diff'])) <= 1e-12
     for p in ('V', 'I', 'sV', 'Vmag', 'Stx', 'Srx'):
         assert getattr(s, p).shape == snap[k + p].shape, p
-        assert rel_err(getattr(s, p), snap[k + p]) <= TOL, p
+        assert_close(getattr(s, p), snap[k + p], TOL, p)
     # accessors: reference shapes (tests/test_api.py:47-71)
     for p in s.SOLUTION_PARAMS:
         rows, cols = s.get_data_frame(p, orient='rows'), s.get_data_frame(p, orient='cols')
@@ -96,7 +96,7 @@ def test_random_batch_matches_oracle(feeder, S, seed):
     assert np.array_equal(r.iterations, want['iterations'])
     assert np.array_equal(r.converged, want['converged'])
     for p in ('V', 'I', 'Vmag', 'sV', 'Stx', 'Srx'):
-        assert rel_err(getattr(r, p), want[p] if p != 'I' else want['I']) <= TOL, p
+        assert_close(getattr(r, p), want[p], TOL, p)
     loss = (want['Stx'] - want['Srx']).sum(axis=(1, 2))
     assert rel_err(r.losses, loss) <= TOL
     assert np.abs(r.convergence_diff - want['convergence_diff']).max() <= 1e-12

@@ -4,7 +4,7 @@ complex bus voltages, identical Newton iteration counts."""
 import numpy as np
 import pytest
 
-from helpers import (ZIPS, ALL_FEEDERS, LINES_ONLY, feeder_path, load_model, snapshots, scenarios, rel_err,
+from helpers import (ZIPS, ALL_FEEDERS, LINES_ONLY, feeder_path, load_model, snapshots, scenarios, rel_err, assert_close,
                      recorded, pinned_34, pinned_34_taps)
 
 pytestmark = pytest.mark.gpu
@@ -29,7 +29,7 @@ def test_snapshot_matches_reference(feeder, zname):
     assert rel_err(s.XNR, snap[k + 'XNR']) <= TOL
     for p in ('V', 'I', 'sV', 'Vmag', 'Stx', 'Srx', 'i_Node'):
         assert getattr(s, p).shape == snap[k + p].shape, p
-        assert rel_err(getattr(s, p), snap[k + p]) <= TOL, p
+        assert_close(getattr(s, p), snap[k + p], TOL, p, small=1e-12)
     for p in s.SOLUTION_PARAMS:
         rows, cols = s.get_data_frame(p, orient='rows'), s.get_data_frame(p, orient='cols')
         assert not rows.empty and rows.shape[1] == 3 and cols.shape[0] == 3
