@@ -622,6 +622,7 @@ def run_workload(ctx, args, name, steps, main):
     if args.push_streams:
         _cabi.check(_cabi.gp_set_option(b'peer_push_streams', args.push_streams))
     _cabi.check(_cabi.gp_set_option(b'nr3_kernel', args.nr3_kernel))
+    _cabi.check(_cabi.gp_set_option(b'nr3_ring', args.nr3_ring))
     _cabi.check(_cabi.gp_set_option(b'fbs_order', args.fbs_order))
     _cabi.check(_cabi.gp_set_option(b'fbs_walk_blocks', args.walk_blocks))
     sol._dev()
@@ -1111,6 +1112,8 @@ def main():
     ap.add_argument('--share-rows', type=int, default=1, choices=[0, 1],
                     help='streaming FBS kernel: 1 = I rows that repeat a child\'s current or stay zero make no HBM round '
                          'trips (default), 0 = every row travels')
+    ap.add_argument('--nr3-ring', type=int, default=-1, choices=[-1, 0, 1],
+                    help='NR3 phase-lane kernel: 1 = next-step rows staged in shared memory with cp.async, 0 = direct loads, -1 = automatic')
     ap.add_argument('--fbs-order', type=int, default=1, choices=[0, 1],
                     help='streaming FBS kernel: 1 = depth-first order of the forward / backward steps (default), 0 = two full sweeps')
     ap.add_argument('--nr3-kernel', type=int, default=0, choices=[0, 1, 2],

@@ -27,6 +27,7 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 extern int g_nr3_prefetch;     // gp_nr3.cu
 extern int g_nr3_kernel;
+extern int g_nr3_ring;
 }  // namespace gp
 extern int g_peer_push_streams;   // gp_peer.cu
 namespace gp {
@@ -1492,6 +1493,10 @@ extern "C" int gp_set_option(const char* name, int value) {
     }
     if (name && strcmp(name, "fbs_order") == 0 && (value == 0 || value == 1)) {
         g_fbs_order = value;
+        return GP_OK;
+    }
+    if (name && strcmp(name, "nr3_ring") == 0 && value >= -1 && value <= 1) {
+        g_nr3_ring = value;
         return GP_OK;
     }
     if (name && strcmp(name, "nr3_kernel") == 0 && value >= 0 && value <= 2) {

@@ -694,8 +694,12 @@ __device__ __forceinline__ double2 shfl_d2(double2 v, int src) {
 __device__ __forceinline__ int pick3(const int4 v, int g) { return g == 0 ? v.x : (g == 1 ? v.y : v.z); }
 __device__ __forceinline__ int pick3c(const int4 v, int g) { return g == 0 ? v.y : (g == 1 ? v.z : v.w); }
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+// RING: the rows of a step whose addresses do not depend on this sweep's arithmetic (backward: the bus's X rows and
+// load; forward: its front, r1 and X rows) are staged two steps ahead in shared memory with cp.async - the kernel's
+// registers (150, 12 warps per SM, all of which the BASELINE batch sizes need) leave no room to stage them there,
+// its shared memory is otherwise unused.  A lane copies and reads only its own 16-byte column: no barrier.
+template <int BLOCK, bool RING>
+__global__ void __launch_bounds__(BLOCK, 3)     // <= 168 registers: 12 warps per SM, what C3 (11.1) and C4-NR3 need
 nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ childs, Nr3Const k,
                  long long S, long long ld, const double2* __restrict__ spu, double2* __restrict__ X,
                  double2* __restrict__ W, double2* __restrict__ DV, int* __restrict__ iters_out,
@@ -726,6 +730,52 @@ nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
     auto pf = [&](const double2* base, long long row) {
         if (row >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + row * ld));
     };
+    constexpr int NSTAGE = 3, NSLOT = 10;               // [stage][slot][lane] per warp, 15 kB
+    extern __shared__ __align__(16) double2 nr3_ring[];
+    double2* const my_ring = nr3_ring + (size_t)(threadIdx.x >> 5) * (NSTAGE * NSLOT * 32) + lane;
+    auto cpa = [&](int stage, int slot, const double2* src, bool have) {     // absent rows are zero-filled
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(my_ring + (stage * NSLOT + slot) * 32);
+        const int n = have ? 16 : 0;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(have ? src : dummy), "r"(n) : "memory");
+    };
+    auto staged = [&](int stage, int slot) { return my_ring[(stage * NSLOT + slot) * 32]; };
+    auto issue_bwd = [&](int pos) {
+        if (pos >= 0) {
+            const Nr3Step* sn = steps + pos;
+            const int b = pick3(__ldg(reinterpret_cast<const int4*>(sn->bus_row)), g);
+            const int e = pick3(__ldg(reinterpret_cast<const int4*>(sn->edge_row)), g);
+            const int pr = pick3(__ldg(reinterpret_cast<const int4*>(sn->par_row)), g);
+            const int l = pick3(__ldg(reinterpret_cast<const int4*>(sn->load_srow)), g);
+            const int stg = pos % NSTAGE;
+            cpa(stg, 0, Xs + (long long)b * ld, b >= 0);
+            cpa(stg, 1, Xs + (long long)e * ld, b >= 0 && e >= 0);
+            cpa(stg, 2, Xs + (long long)pr * ld, b >= 0 && pr >= 0);
+            cpa(stg, 3, spu_s + (long long)l * ld, b >= 0 && l >= 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto issue_fwd = [&](int pos) {
+        if (pos < n_steps) {
+            const Nr3Step* sn = steps + pos;
+            const int4 b4 = __ldg(reinterpret_cast<const int4*>(sn->bus_row));
+            const int b = pick3(b4, g);
+            const int e = pick3(__ldg(reinterpret_cast<const int4*>(sn->edge_row)), g);
+            const double2* Wn = Ws + (long long)pos * FRONT_D2 * ld;
+            const int stg = pos % NSTAGE;
+            const bool hb2 = b >= 0;
+            cpa(stg, 0, Wn + (long long)(18 + g) * ld, hb2);
+            cpa(stg, 1, Wn + (long long)(21 + g) * ld, hb2);
+            cpa(stg, 2, Xs + (long long)b * ld, hb2);
+            cpa(stg, 3, Xs + (long long)e * ld, hb2 && e >= 0);
+            cpa(stg, 4, Wn + (long long)((2 * g) * 3 + 0) * ld, hb2 && b4.x >= 0);
+            cpa(stg, 5, Wn + (long long)((2 * g) * 3 + 1) * ld, hb2 && b4.y >= 0);
+            cpa(stg, 6, Wn + (long long)((2 * g) * 3 + 2) * ld, hb2 && b4.z >= 0);
+            cpa(stg, 7, Wn + (long long)((2 * g + 1) * 3 + 0) * ld, hb2 && b4.x >= 0);
+            cpa(stg, 8, Wn + (long long)((2 * g + 1) * 3 + 1) * ld, hb2 && b4.y >= 0);
+            cpa(stg, 9, Wn + (long long)((2 * g + 1) * 3 + 2) * ld, hb2 && b4.z >= 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
 
     // flat start (solution_nr3.py:37-82)
     if (owner) {
@@ -747,8 +797,16 @@ nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
         double fml = (it == 0) ? k.f0_absent : 0.0;          // this lane's share of max |F|
         bool nanl = false;
         // ================= backward sweep =================
+        if (RING) {
+            issue_bwd(n_steps - 1);
+            issue_bwd(n_steps - 2);
+        }
         for (int pos = n_steps - 1; pos >= 0; --pos) {
-            if (PF > 0 && pos >= PF) {
+            if (RING) {
+                issue_bwd(pos - 2);
+                asm volatile("cp.async.wait_group 2;" ::: "memory");
+            }
+            if (!RING && PF > 0 && pos >= PF) {
                 const Nr3Step* sn = steps + (pos - PF);
                 const int b2 = pick3(__ldg(reinterpret_cast<const int4*>(sn->bus_row)), g);
                 if (b2 >= 0) {
@@ -769,10 +827,11 @@ nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                 // single-phase bus: the system is the identity outside one 2x2 block, which the lane of
                 // that phase solves alone (no shuffles); the other two lanes have nothing to do
                 if (hb) {
-                    const double2 v1 = ld_sel(true, Xs + (long long)my_b * ld, dummy);
-                    double2 in1 = ld_sel(true, Xs + (long long)my_e * ld, dummy);
-                    const double2 vp1 = ld_sel(my_p >= 0, Xs + (long long)my_p * ld, dummy);
-                    const double2 sp1 = ld_sel(my_l >= 0, spu_s + (long long)my_l * ld, dummy);
+                    const int stg = pos % NSTAGE;
+                    const double2 v1 = RING ? staged(stg, 0) : ld_sel(true, Xs + (long long)my_b * ld, dummy);
+                    double2 in1 = RING ? staged(stg, 1) : ld_sel(true, Xs + (long long)my_e * ld, dummy);
+                    const double2 vp1 = RING ? staged(stg, 2) : ld_sel(my_p >= 0, Xs + (long long)my_p * ld, dummy);
+                    const double2 sp1 = RING ? staged(stg, 3) : ld_sel(my_l >= 0, spu_s + (long long)my_l * ld, dummy);
                     const double2 z = g == 0 ? __ldg(&st->z[0]) : (g == 1 ? __ldg(&st->z[4]) : __ldg(&st->z[8]));
                     const double cap = g == 0 ? __ldg(&st->cap[0]) : (g == 1 ? __ldg(&st->cap[1]) : __ldg(&st->cap[2]));
                     double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0, ra = 0.0, rb2 = 0.0;
@@ -847,10 +906,11 @@ nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                 }
                 continue;
             }
-            const double2 v = ld_sel(hb, Xs + (long long)my_b * ld, dummy);
-            double2 inet = ld_sel(hb, Xs + (long long)my_e * ld, dummy);
-            const double2 vpar = ld_sel(hb && my_p >= 0, Xs + (long long)my_p * ld, dummy);
-            const double2 spl = ld_sel(hb && my_l >= 0, spu_s + (long long)my_l * ld, dummy);
+            const int stg = pos % NSTAGE;
+            const double2 v = RING ? staged(stg, 0) : ld_sel(hb, Xs + (long long)my_b * ld, dummy);
+            double2 inet = RING ? staged(stg, 1) : ld_sel(hb, Xs + (long long)my_e * ld, dummy);
+            const double2 vpar = RING ? staged(stg, 2) : ld_sel(hb && my_p >= 0, Xs + (long long)my_p * ld, dummy);
+            const double2 spl = RING ? staged(stg, 3) : ld_sel(hb && my_l >= 0, spu_s + (long long)my_l * ld, dummy);
             // KVL residual r1 = E v_p - v - Z i (:141-158): the currents of all three phases
             const double2 i0 = shfl_d2(inet, src0), i1 = shfl_d2(inet, src1), i2 = shfl_d2(inet, src2);
             const double2 zg0 = __ldg(&st->z[3 * g]), zg1 = __ldg(&st->z[3 * g + 1]), zg2 = __ldg(&st->z[3 * g + 2]);
@@ -1013,8 +1073,16 @@ nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
             }
         }
         __syncwarp();       // the dv of a parent is read by the other two lanes of the scenario below
+        if (RING) {
+            issue_fwd(0);
+            issue_fwd(1);
+        }
         for (int pos = 0; pos < n_steps; ++pos) {
-            if (PF > 0 && pos + PF < n_steps) {
+            if (RING) {
+                issue_fwd(pos + 2);
+                asm volatile("cp.async.wait_group 2;" ::: "memory");
+            }
+            if (!RING && PF > 0 && pos + PF < n_steps) {
                 const Nr3Step* sn = steps + (pos + PF);
                 const int4 b2 = __ldg(reinterpret_cast<const int4*>(sn->bus_row));
                 if (pick3(b2, g) >= 0) {
@@ -1040,12 +1108,13 @@ nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                 if (hb) {
                     const int my_p = pick3(pv, g);
                     const double2 dvp1 = ld_sel(my_p >= 0, DVs + (long long)my_p * ld, dummy);
-                    double2 di1 = ld_sel(true, Wk + (long long)(18 + g) * ld, dummy);
-                    const double2 r1f1 = ld_sel(true, Wk + (long long)(21 + g) * ld, dummy);
-                    const double2 xv1 = ld_sel(true, Xs + (long long)my_b * ld, dummy);
-                    const double2 xi1 = ld_sel(true, Xs + (long long)my_e * ld, dummy);
-                    const double2 ya = ld_sel(true, Wk + (long long)((2 * g) * 3 + g) * ld, dummy);
-                    const double2 yb = ld_sel(true, Wk + (long long)((2 * g + 1) * 3 + g) * ld, dummy);
+                    const int stg = pos % NSTAGE;
+                    double2 di1 = RING ? staged(stg, 0) : ld_sel(true, Wk + (long long)(18 + g) * ld, dummy);
+                    const double2 r1f1 = RING ? staged(stg, 1) : ld_sel(true, Wk + (long long)(21 + g) * ld, dummy);
+                    const double2 xv1 = RING ? staged(stg, 2) : ld_sel(true, Xs + (long long)my_b * ld, dummy);
+                    const double2 xi1 = RING ? staged(stg, 3) : ld_sel(true, Xs + (long long)my_e * ld, dummy);
+                    const double2 ya = RING ? staged(stg, 4 + g) : ld_sel(true, Wk + (long long)((2 * g) * 3 + g) * ld, dummy);
+                    const double2 yb = RING ? staged(stg, 7 + g) : ld_sel(true, Wk + (long long)((2 * g + 1) * 3 + g) * ld, dummy);
                     const double2 z = g == 0 ? __ldg(&st->z[0]) : (g == 1 ? __ldg(&st->z[4]) : __ldg(&st->z[8]));
                     di1.x -= ya.x * dvp1.x + ya.y * dvp1.y;
                     di1.y -= yb.x * dvp1.x + yb.y * dvp1.y;
@@ -1061,17 +1130,18 @@ nr3_phase_kernel(const Nr3Step* __restrict__ steps, const int4* __restrict__ chi
                 __syncwarp();
                 continue;
             }
-            double2 di = ld_sel(hb, Wk + (long long)(18 + g) * ld, dummy);
-            const double2 r1f = ld_sel(hb, Wk + (long long)(21 + g) * ld, dummy);
-            const double2 xv = ld_sel(hb, Xs + (long long)my_b * ld, dummy);
-            const double2 xi = ld_sel(hb, Xs + (long long)my_e * ld, dummy);
+            const int stg = pos % NSTAGE;
+            double2 di = RING ? staged(stg, 0) : ld_sel(hb, Wk + (long long)(18 + g) * ld, dummy);
+            const double2 r1f = RING ? staged(stg, 1) : ld_sel(hb, Wk + (long long)(21 + g) * ld, dummy);
+            const double2 xv = RING ? staged(stg, 2) : ld_sel(hb, Xs + (long long)my_b * ld, dummy);
+            const double2 xi = RING ? staged(stg, 3) : ld_sel(hb, Xs + (long long)my_e * ld, dummy);
             double2 dvp[3], y0[3], y1[3];
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 const bool hq = hb && br[q] >= 0;
                 dvp[q] = ld_sel(hq && pr[q] >= 0, DVs + (long long)pr[q] * ld, dummy);
-                y0[q] = ld_sel(hq, Wk + (long long)((2 * g) * 3 + q) * ld, dummy);
-                y1[q] = ld_sel(hq, Wk + (long long)((2 * g + 1) * 3 + q) * ld, dummy);
+                y0[q] = RING ? staged(stg, 4 + q) : ld_sel(hq, Wk + (long long)((2 * g) * 3 + q) * ld, dummy);
+                y1[q] = RING ? staged(stg, 7 + q) : ld_sel(hq, Wk + (long long)((2 * g + 1) * 3 + q) * ld, dummy);
             }
 #pragma unroll
             for (int q = 0; q < 3; ++q) {                   // di = a - Y dv_p
@@ -1336,6 +1406,7 @@ void gp_nr3_destroy_impl(void* impl) {
 // gp_set_option("nr3_prefetch", d): -1 = automatic (on for batches that leave the SMs latency-bound)
 namespace gp {
 int g_nr3_prefetch = -1;
+int g_nr3_ring = -1;     // gp_set_option("nr3_ring", -1|0|1): the phase-lane kernel stages next-step rows in shared memory
 int g_nr3_kernel = 0;
 int nr3_gamma_rows(GpFeeder* f) { return ((Nr3Impl*)f->impl)->n_grows; }
 }
@@ -1403,9 +1474,23 @@ extern "C" int gp_nr3_solve_batch_ex(GpFeeder* f, int64_t S, int64_t ld, const d
         constexpr int PB = 128;
         const long long warps = (S + 9) / 10;
         const unsigned gp2 = (unsigned)((warps * 32 + PB - 1) / PB);
-        nr3_phase_kernel<PB><<<gp2, PB, 0, st>>>(im->d_steps, im->d_child, im->k, S, ld, (const double2*)spu,
-                                                 (double2*)X, W, DV, iters, status, fmax, maxiter,
-                                                 gp_nr3_prefetch_distance(S));
+        // cp.async ring ("nr3_ring": -1 automatic, 0, 1).  Measured on B200, round 2 (profiles/r02j_*): C3 (37-bus, every
+        // bus three-phase) 1.115 -> 1.061 ms; C4-NR3 (123-bus, 55 of 125 buses single-phase, whose 2x2 steps are too
+        // short to pay for staging ten rows) 3.21 -> 3.35 ms: automatic = on when at least 5 of 6 buses are three-phase
+        if (g_nr3_ring == 1 || (g_nr3_ring < 0 && im->mostly_3ph)) {
+            constexpr size_t smem = (size_t)(PB / 32) * 3 * 10 * 32 * sizeof(double2);     // one 15 kB ring per warp
+            static bool attr_set = false;
+            if (!attr_set) {
+                GP_CUDA(cudaFuncSetAttribute(nr3_phase_kernel<PB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set = true;
+            }
+            nr3_phase_kernel<PB, true><<<gp2, PB, smem, st>>>(im->d_steps, im->d_child, im->k, S, ld, (const double2*)spu,
+                                                              (double2*)X, W, DV, iters, status, fmax, maxiter, 0);
+        } else {
+            nr3_phase_kernel<PB, false><<<gp2, PB, 0, st>>>(im->d_steps, im->d_child, im->k, S, ld, (const double2*)spu,
+                                                            (double2*)X, W, DV, iters, status, fmax, maxiter,
+                                                            gp_nr3_prefetch_distance(S));
+        }
     } else {
         nr3_solve_kernel<BLOCK, false><<<gx, BLOCK, 0, st>>>(im->d_steps, im->d_child, im->k, im->n_vrows, im->n_irows, S,
                                                              ld, (const double2*)spu, (double2*)X, W, DV, iters, status,

@@ -114,6 +114,10 @@ int64_t gp_launch_count(void);
  * "fbs_prefetch" / "nr3_prefetch": L2 prefetch distance in tree steps of the streaming FBS kernel
  * (default -1 = automatic: 2 for feeders with at least 1,024 V rows, else 0) and of the NR3 kernel
  * (default -1 = automatic: 2 for batches up to 65,536).
+ * "nr3_ring": the phase-lane NR3 kernel stages the rows of the next two steps whose addresses do not depend on the
+ *   sweep in flight (backward: the bus's X rows and load; forward: its front, r1 and X rows) in shared memory with
+ *   cp.async, one 15 kB ring per warp: -1 (default) = on for feeders on which at least 5 of 6 buses are three-phase,
+ *   0 = direct loads with an L2 prefetch "nr3_prefetch" steps ahead, 1 = always.
  * "fbs_share_rows": 1 (default) = in the streaming FBS kernel an I row that only repeats a child's current (a
  *   bus-phase without load and capacitor fed by one child edge) or stays zero makes no HBM round trips during
  *   the sweeps and is filled in once at the end; 0 = every row is stored and re-read each sweep.  Same results.

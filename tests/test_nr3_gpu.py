@@ -158,3 +158,36 @@ def test_both_nr3_kernels_meet_the_oracle_and_each_other(feeder, S):
         assert (res[kern].status == 0).all()
         assert rel_err(res[kern].XNR, want['XNR']) <= TOL, kern
     assert rel_err(res[1].XNR, res[2].XNR) <= 1e-11
+
+
+@pytest.mark.parametrize('feeder', ['IEEE_37_Bus_allwye_noxfm_noreg', 'IEEE_13_Bus_allwye_noxfm_noreg', 'ieee123'])
+def test_phase_kernel_with_staged_rows_is_bit_identical(feeder):
+    """The phase-lane kernel with its cp.async ring (nr3_ring 1: next-step rows staged in shared memory) and with
+    direct loads (0, with and without the L2 prefetch) does the same arithmetic on the same values: bit-identical X,
+    on ragged batch sizes, incl. a feeder with single-phase and two-phase buses."""
+    import os
+    from gigpower_b200 import _cabi
+    from helpers import REPO
+    if feeder == 'ieee123':
+        from gigpower_b200.solution_nr3 import SolutionNR3
+        s = SolutionNR3(os.path.join(REPO, 'gigpower_b200', 'feeders', 'ieee123_allwye_noxfm_noreg.dss'))
+    else:
+        s = _nr3(feeder)
+    rng = np.random.Generator(np.random.PCG64(91))
+    mult = rng.uniform(0.4, 1.3, size=(1237, s.circuit.loads.num_elements))
+    out = {}
+    try:
+        _cabi.check(_cabi.gp_set_option(b'nr3_kernel', 2))
+        for ring, pf in ((0, 0), (0, 2), (1, 0)):
+            _cabi.check(_cabi.gp_set_option(b'nr3_ring', ring))
+            _cabi.check(_cabi.gp_set_option(b'nr3_prefetch', pf))
+            r = s.solve_batch(load_mult=mult, outputs=('X',))
+            out[ring, pf] = (r.iterations, r.status, np.asarray(r.X_rows))
+    finally:
+        _cabi.gp_set_option(b'nr3_kernel', 0)
+        _cabi.gp_set_option(b'nr3_ring', -1)
+        _cabi.gp_set_option(b'nr3_prefetch', -1)
+    for key in ((0, 2), (1, 0)):
+        for a, b in zip(out[0, 0], out[key]):
+            assert np.array_equal(a, b), key
+    assert (out[0, 0][1] == 0).all()
