@@ -72,6 +72,7 @@ gp_set_option = _sig('gp_set_option', C.c_int, [C.c_char_p, C.c_int])
 gp_fbs_active_kernel = _sig('gp_fbs_active_kernel', C.c_int, [vp])
 gp_fbs_onchip_warps = _sig('gp_fbs_onchip_warps', C.c_int, [vp])
 gp_measure_fp64_peak = _sig('gp_measure_fp64_peak', C.c_int, [C.c_int, f64p])
+gp_measure_dmma = _sig('gp_measure_dmma', C.c_int, [C.c_int, f64p])
 gp_fbs_specialise = _sig('gp_fbs_specialise', C.c_int, [vp])
 gp_fbs_schedule = _sig('gp_fbs_schedule', C.c_int, [C.POINTER(GpFbsDesc), i32p, i32p])
 gp_fbs_walk_events = _sig('gp_fbs_walk_events', C.c_int, [C.POINTER(GpFbsDesc), i32p, C.c_int64])
@@ -141,7 +142,7 @@ EXPORTS = ['gp_version', 'gp_last_error', 'gp_launch_count', 'gp_set_option', 'g
            'gp_fbs_solve_batch', 'gp_fbs_solve_post_batch', 'gp_fbs_post', 'gp_fbs_solve_batch_host', 'gp_der_rows', 'gp_vmag_summary', 'gp_nr3_create',
            'gp_nr3_workspace_bytes', 'gp_nr3_solve_batch', 'gp_nr3_map_output',
            'gp_gamma_rows', 'gp_fbs_solve_batch_ex', 'gp_nr3_solve_batch_ex', 'gp_der_rows_strided',
-           'gp_fbs_schedule', 'gp_fbs_walk_events', 'gp_nr3_map_output_ex', 'gp_peer_alloc', 'gp_peer_free', 'gp_peer_open', 'gp_peer_close', 'gp_peer_push', 'gp_fbs_post_ex']
+           'gp_measure_dmma', 'gp_fbs_schedule', 'gp_fbs_walk_events', 'gp_nr3_map_output_ex', 'gp_peer_alloc', 'gp_peer_free', 'gp_peer_open', 'gp_peer_close', 'gp_peer_push', 'gp_fbs_post_ex']
 
 
 def make_extras(gamma=None, warm_start=False, peers=None, wpu=None, volt_var=None):

@@ -1597,6 +1597,79 @@ extern "C" int gp_measure_fp64_peak(int device, double* tflops) {
     return GP_OK;
 }
 
+// ---- FP64 tensor-core (DMMA) probe ---------------------------------------------------------------------
+// mode 0: 8 independent chains of mma.sync.m8n8k4.f64 per warp; mode 1: 8 chains of DFMA per thread; mode 2: both
+// interleaved in one instruction stream.  If DMMA ran on its own pipe next to the FP64 FMA pipe, mode 2 would take
+// about max(t0, t1); if they share the pipe (or the issue slots), about t0 + t1.
+namespace gp {
+template <int MODE>
+__global__ void __launch_bounds__(256) fp64_dmma_probe_kernel(double* out, int iters, double b, double c) {
+    double acc[8][2], f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        acc[j][0] = (double)(threadIdx.x + j);
+        acc[j][1] = (double)(threadIdx.x - j);
+        f[j] = (double)(threadIdx.x + 3 * j);
+    }
+    const double a_frag = b, b_frag = c;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (MODE == 0 || MODE == 2)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                             : "+d"(acc[j][0]), "+d"(acc[j][1]) : "d"(a_frag), "d"(b_frag));
+            if (MODE == 1 || MODE == 2) f[j] = fma(f[j], b, c);
+        }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += acc[j][0] + acc[j][1] + f[j];
+    if (sum == 12345.678) out[0] = sum;
+}
+}  // namespace gp
+
+// out[0] = DMMA TFLOP/s (512 flop per warp instruction), out[1] = DFMA TFLOP/s (this kernel's 8 chains),
+// out[2], out[3] = the same two rates while both run interleaved, out[4..6] = the three durations in ms
+extern "C" int gp_measure_dmma(int device, double* out7) {
+    if (!out7) return fail(GP_EINVAL, "gp_measure_dmma: null argument");
+    GP_CUDA(cudaSetDevice(device));
+    int n_sm = 0;
+    GP_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    double* d_out = nullptr;
+    GP_CUDA(cudaMalloc(&d_out, 8));
+    cudaEvent_t e0, e1;
+    GP_CUDA(cudaEventCreate(&e0));
+    GP_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = n_sm * 8;
+    double ms[3] = {1e30, 1e30, 1e30};
+    for (int mode = 0; mode < 3; ++mode)
+        for (int rep = 0; rep < 5; ++rep) {
+            GP_CUDA(cudaEventRecord(e0, 0));
+            if (mode == 0) fp64_dmma_probe_kernel<0><<<blocks, 256>>>(d_out, iters, 0.999999, 1e-9);
+            else if (mode == 1) fp64_dmma_probe_kernel<1><<<blocks, 256>>>(d_out, iters, 0.999999, 1e-9);
+            else fp64_dmma_probe_kernel<2><<<blocks, 256>>>(d_out, iters, 0.999999, 1e-9);
+            GP_CUDA(cudaEventRecord(e1, 0));
+            GP_CUDA(cudaEventSynchronize(e1));
+            float t = 0.f;
+            GP_CUDA(cudaEventElapsedTime(&t, e0, e1));
+            if (rep > 0 && t < ms[mode]) ms[mode] = t;
+        }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    GP_CUDA(cudaGetLastError());
+    const double warps = (double)blocks * 8.0, threads = (double)blocks * 256.0;
+    const double mma_flop = 512.0 * 8.0 * iters * warps, fma_flop = 2.0 * 8.0 * iters * threads;
+    out7[0] = mma_flop / (ms[0] * 1e-3) / 1e12;
+    out7[1] = fma_flop / (ms[1] * 1e-3) / 1e12;
+    out7[2] = mma_flop / (ms[2] * 1e-3) / 1e12;
+    out7[3] = fma_flop / (ms[2] * 1e-3) / 1e12;
+    out7[4] = ms[0];
+    out7[5] = ms[1];
+    out7[6] = ms[2];
+    return GP_OK;
+}
+
 // GpFbsDesc -> step records, child table, constants (host side; shared by gp_fbs_create and
 // the source generator)
 static int fbs_tables_from_desc(const GpFbsDesc* d, std::vector<FbsStep>& steps, std::vector<int4>& child4,

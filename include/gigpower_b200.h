@@ -199,6 +199,12 @@ int gp_jit_compile(const char* source, void* cubin, int64_t cap, int64_t* cubin_
  * FP64 roofline of the on-chip FBS kernel and of the NR3 elimination.
  */
 int gp_measure_fp64_peak(int device, double* tflops);
+/*
+ * FP64 tensor-core probe (the "DMMA question" of DESIGN.md): out7[0] = TFLOP/s of mma.sync.m8n8k4.f64 alone (8
+ * independent chains per warp), [1] = of DFMA alone, [2], [3] = of each while both are interleaved in one instruction
+ * stream, [4..6] = the three kernel durations in ms.  Separate pipes would give t_both ~ max(t_mma, t_fma).
+ */
+int gp_measure_dmma(int device, double* out7);
 
 /*
  * Build the device-resident feeder tables.  Replaces SolutionFBS.__init__'s
