@@ -1015,6 +1015,9 @@ def run_workload(ctx, args, name, steps, main):
         }
         if gather_note:
             res['config']['gather_note'] = gather_note
+        if ctx.world > 1:
+            res['config']['host_affinity'] = (f'rank 0 pinned to the {len(ctx.numa_cores)} cores NVML reports local to its GPU '
+                                              f'(every rank likewise)' if ctx.numa_cores else 'not set')
         if e2e is not None:
             res['e2e'] = e2e
         if main and world == 1 and not args.no_cpu:
@@ -1046,6 +1049,11 @@ def run_ours(args):
     ctx.local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(ctx.local)
     ctx.dev = torch.device('cuda', ctx.local)
+    ctx.numa_cores = None
+    if ctx.world > 1 and not args.no_numa:
+        # one process per GPU: run on the cores of the GPU's NUMA node, so the pinned e2e buffers are local to it
+        from gigpower_b200.sharding import bind_to_gpu_numa
+        ctx.numa_cores = bind_to_gpu_numa(ctx.local)
     if ctx.world > 1:
         # NCCL writes its version / debug lines to stdout by default; stdout carries the one JSON line
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
@@ -1098,6 +1106,7 @@ def main():
     ap.add_argument('--sub-steps', type=int, default=10, help='timed steps of each sub-workload')
     ap.add_argument('--sub-e2e', action='store_true', help='also measure e2e for the sub-workloads')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-numa', action='store_true', help='N > 1: do not pin the ranks to their GPU\'s NUMA node')
     ap.add_argument('--gather', default='peer', choices=['peer', 'dma', 'nccl'],
                     help='N > 1: the all-gather of |V| and losses through peer-mapped memory (fused into the '
                          'specialised FBS kernel, copy-engine pushes otherwise) or by NCCL')

@@ -24,6 +24,35 @@ def shard_range(S: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def bind_to_gpu_numa(device_index: int) -> Optional[list]:
+    """Pin this process to the CPU cores NVML reports as local to GPU ``device_index`` (its NUMA node / PCIe root),
+    so that the pinned host buffers it allocates afterwards are first-touched on that node and its copies do not
+    cross the socket interconnect.  One process per GPU makes this a per-rank setting.  Returns the core list, or
+    None when NVML or the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = device_index
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            try:
+                idx = int(vis.split(',')[device_index])
+            except ValueError:
+                pass
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_words = (os.cpu_count() + 63) // 64
+        masks = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cores = [64 * w + b for w, m in enumerate(masks) for b in range(64) if (int(m) >> b) & 1]
+        cores = [c for c in cores if c in os.sched_getaffinity(0)]
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return None
+
+
 def gather_rows(local, S: int, group=None):
     """All-gather a per-scenario array whose LAST dimension is this rank's
     scenario block (``[..., n_local]``) into ``[..., S]`` on every rank.
