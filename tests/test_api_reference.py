@@ -91,9 +91,24 @@ def test_params_and_result_shapes_match_the_reference(api, feeder, cls):
 
 
 def test_out_of_scope_entry_points_fail_with_an_explanation():
-    """N10 change_KCL_matrices and SolutionDSS are outside the accelerated path: a caller gets a clear error."""
+    """N10 change_KCL_matrices is outside the accelerated path (its inputs are per-scenario arrays of solve_batch): a
+    caller gets a clear error.  SolutionDSS - OpenDSS itself behind gigpower's accessors - is not part of this package
+    at all: there is no such module."""
     s = _cls('SolutionNR3')(feeder_path(ALL_FEEDERS[1]))
     with pytest.raises(NotImplementedError, match='solve_batch'):
         s.change_KCL_matrices(der=0.1)
-    with pytest.raises(ImportError, match='OpenDSS'):
-        from gigpower_b200.solution_dss import SolutionDSS  # noqa: F401
+    with pytest.raises(ModuleNotFoundError):
+        import gigpower_b200.solution_dss  # noqa: F401
+
+
+def test_solution_keeps_the_reference_method_names():
+    """The public methods of the reference's Solution classes a caller may invoke (solution.py:127-315,
+    solution_fbs.py, solution_nr3.py) exist on the drop-in classes."""
+    fbs, nr3 = _cls('SolutionFBS'), _cls('SolutionNR3')
+    for name in ('solve', 'get_V', 'get_Vmag', 'get_I', 'get_Stx', 'get_Srx', 'get_sV', 'get_data_frame',
+                 'get_nominal_bus_powers', 'get_params', 'print_solution', 'set_zip_values'):
+        assert callable(getattr(fbs, name)) and callable(getattr(nr3, name)), name
+    for name in ('calc_sV', 'calc_Vmag', 'calc_Stx', 'calc_Srx'):           # solution.py:177-233
+        assert callable(getattr(fbs, name)), name
+    for name in ('map_XNR', 'change_KCL_matrices'):
+        assert callable(getattr(nr3, name)), name
