@@ -46,11 +46,13 @@ static int g_host_chunks = 0;  // gp_set_option("host_chunks", n): 0 = automatic
 // depth-first, 2 phase-parallel, 3 two-sweep streaming, 4 on-chip (error if the feeder does not fit),
 // 5 feeder-specialised on-chip kernel (error unless gp_fbs_specialise succeeded)
 static int g_fbs_kernel = 0;
-// gp_set_option("fbs_prefetch", d): L2 prefetch distance of the streaming kernel in steps; -1 (default) = automatic.
-// In depth-first order the rows a step still takes from DRAM are last iteration's edge currents and the loads;
-// requesting them two events ahead pays when a scenario's state is far larger than its share of L2 (measured on
-// B200, round 2: 2,541-bus feeder 71.5 -> 68.2 ms) and costs when most reads already hit L2 (123-bus: 3.76 -> 3.89 ms
-// at distance 2, worse at 1, 4, 8), so the automatic choice is 2 for feeders with >= 1,024 V rows, else 0.
+// gp_set_option("fbs_prefetch", d): prefetch distance of the streaming kernel in steps; -1 (default) = automatic = 0.
+// d in 1..64: last iteration's edge currents / the loads of event e + d are requested into L2; 100 + d: into L1, and
+// the I / spu loads then look in L1 first.  Measured on B200, round 2 (depth-first order; profiles/r02f_*, r02m_*,
+// r02n_*): with the final kernel build every distance costs time on both feeders - 123-bus 3.44 ms without, 3.63 ms
+// into L1 at 1..3; 2,541-bus 61.4 ms without, 65.2-65.6 ms into L2 at 1, 2, 4, 64.1-64.2 ms into L1 - so it is off.
+// (An earlier build of the same kernel gained 5 % on the 2,541-bus feeder from distance 2; the gain went away when
+// the load path changed, which says how close to noise the effect is.)
 static int g_fbs_prefetch = -1;
 // gp_set_option("fbs_share_rows", 0|1): the streaming kernel skips the HBM round trips of I rows that only
 // repeat a child's current or stay zero (default 1; 0 = every row travels, for A/B measurements)
@@ -102,6 +104,7 @@ struct GMemT {
     const char* G;
     const char* W;      // this scenario's column of the per-scenario Solution.wpu rows ([V row][ld] doubles)
     const int* VV;      // [V row] non-zero = a volt-var controller sets wpu = get_Q(|V|) there at every calc_sV
+    bool l1;            // prefetches go into L1 and the I / spu loads look there first (fbs_prefetch >= 100)
     __device__ __forceinline__ bool hasW() const { return TAPS && (W != nullptr || VV != nullptr); }
     // Solution.wpu of V row r whose voltage magnitude is a: the caller's row, or the droop of the row's controller
     __device__ __forceinline__ double wq(int r, double a, const FbsConst& k) const {
@@ -112,12 +115,21 @@ struct GMemT {
     __device__ __forceinline__ bool hasG() const { return TAPS && G != nullptr; }
     __device__ __forceinline__ double ldG(int r) const { return __ldg(reinterpret_cast<const double*>(G + (size_t)(unsigned)r * (size_t)(ldb >> 1))); }
     __device__ __forceinline__ double2 ldV(int r) const { return __ldcg(reinterpret_cast<const double2*>(V + (size_t)(unsigned)r * (size_t)ldb)); }
-    __device__ __forceinline__ double2 ldI(int r) const { return __ldcg(reinterpret_cast<const double2*>(I + (size_t)(unsigned)r * (size_t)ldb)); }
-    __device__ __forceinline__ double2 ldS(int r) const { return __ldcg(reinterpret_cast<const double2*>(S + (size_t)(unsigned)r * (size_t)ldb)); }
+    __device__ __forceinline__ double2 ldI(int r) const {
+        const double2* p = reinterpret_cast<const double2*>(I + (size_t)(unsigned)r * (size_t)ldb);
+        return l1 ? __ldca(p) : __ldcg(p);
+    }
+    __device__ __forceinline__ double2 ldS(int r) const {
+        const double2* p = reinterpret_cast<const double2*>(S + (size_t)(unsigned)r * (size_t)ldb);
+        return l1 ? __ldca(p) : __ldcg(p);
+    }
     __device__ __forceinline__ void stV(int r, double2 v) const { *reinterpret_cast<double2*>(V + (size_t)(unsigned)r * (size_t)ldb) = v; }
     __device__ __forceinline__ void stI(int r, double2 v) const { *reinterpret_cast<double2*>(I + (size_t)(unsigned)r * (size_t)ldb) = v; }
     // L2 prefetch of a row this thread will read a couple of steps from now (no register held)
-    static __device__ __forceinline__ void pf(const char* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+    __device__ __forceinline__ void pf(const char* p) const {
+        if (l1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+        else asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
     __device__ __forceinline__ void pfV(int r) const { if (r >= 0) pf(V + (size_t)(unsigned)r * (size_t)ldb); }
     __device__ __forceinline__ void pfI(int r) const { if (r >= 0) pf(I + (size_t)(unsigned)r * (size_t)ldb); }
     __device__ __forceinline__ void pfS(int r) const { if (r >= 0) pf(S + (size_t)(unsigned)r * (size_t)ldb); }
@@ -449,7 +461,8 @@ fbs_solve_kernel(const FbsStep* __restrict__ steps, const int4* __restrict__ chi
     if (s >= S) return;
     typedef GMemT<EX> GMem;
     const GMem m{V + s * 16, I + s * 16, spu + s * 16, ldb, (EX && gam) ? gam + s * 8 : nullptr,
-                 (EX && wpu) ? wpu + s * 8 : nullptr, EX ? vv : nullptr};
+                 (EX && wpu) ? wpu + s * 8 : nullptr, EX ? vv : nullptr, PF >= 100};
+    if (PF >= 100) PF -= 100;
     const double2 zero = make_double2(0.0, 0.0);
     if (EX && warm) n_unfed = 0;    // warm start: every V and I row keeps the earlier solution
 
@@ -1483,7 +1496,7 @@ extern "C" int gp_set_option(const char* name, int value) {
         g_fbs_kernel = value;
         return GP_OK;
     }
-    if (name && strcmp(name, "fbs_prefetch") == 0 && value >= -1 && value <= 64) {
+    if (name && strcmp(name, "fbs_prefetch") == 0 && ((value >= -1 && value <= 64) || (value >= 100 && value <= 164))) {
         g_fbs_prefetch = value;
         return GP_OK;
     }
@@ -2496,7 +2509,7 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     if (extras) {
         // per-scenario ratios / warm start: the streaming kernel's EX instance (the on-chip kernels
         // bake the ratios into their code or tables and always start flat)
-        const int pf = g_fbs_prefetch >= 0 ? g_fbs_prefetch : (im->n_vrows >= 1024 ? 2 : 0);
+        const int pf = g_fbs_prefetch >= 0 ? g_fbs_prefetch : 0;
         if (g_fbs_order && im->n_events > 0)
             fbs_solve_kernel<BLOCK, true, true><<<gx, BLOCK, 0, st>>>(
                 im->d_steps, im->d_child, kx, im->n_steps, im->n_vrows, im->n_irows, S, ldb, (const char*)spu, (char*)V,
@@ -2577,9 +2590,7 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     } else {
         if (g_fbs_kernel == 6) return fail(GP_EINVAL, "gp_fbs_solve_batch: fbs_kernel = 6 needs a feeder the tree-walk kernel takes");
         const bool share = g_fbs_share_rows && im->n_alias > 0;
-        // L2 prefetch distance: automatic = 2 events for feeders whose state is far larger than L2 can hold per
-        // scenario (measured on B200: 2,541-bus 71.5 -> 68.2 ms; 123-bus 3.76 -> 3.89 ms, so off there)
-        const int pf = g_fbs_prefetch >= 0 ? g_fbs_prefetch : (im->n_vrows >= 1024 ? 2 : 0);
+        const int pf = g_fbs_prefetch >= 0 ? g_fbs_prefetch : 0;       // see g_fbs_prefetch: every distance measured slower
         const FbsStep* tb = share ? im->d_steps_a : im->d_steps;
         const int4* tc = share ? im->d_child_a : im->d_child;
         if (g_fbs_order && im->n_events > 0)

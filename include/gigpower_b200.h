@@ -111,9 +111,9 @@ int64_t gp_launch_count(void);
  * 5 = the feeder-specialised on-chip kernel (GP_EINVAL unless gp_fbs_specialise succeeded).
  * "nr3_kernel": 0 = automatic (default), 1 = one thread per scenario, 2 = three phase lanes per scenario
  * (Line / Transformer feeders only; automatic for small batches of mostly three-phase feeders).
- * "fbs_prefetch" / "nr3_prefetch": L2 prefetch distance in tree steps of the streaming FBS kernel
- * (default -1 = automatic: 2 for feeders with at least 1,024 V rows, else 0) and of the NR3 kernel
- * (default -1 = automatic: 2 for batches up to 65,536).
+ * "fbs_prefetch" / "nr3_prefetch": prefetch distance in tree steps of the streaming FBS kernel (default -1 =
+ * automatic = off: every distance measured slower with the final kernel; 1..64 into L2, 100 + d into L1) and of
+ * the NR3 kernels (default -1 = automatic: 2 for batches up to 65,536).
  * "nr3_ring": the phase-lane NR3 kernel stages the rows of the next two steps whose addresses do not depend on the
  *   sweep in flight (backward: the bus's X rows and load; forward: its front, r1 and X rows) in shared memory with
  *   cp.async, one 15 kB ring per warp: -1 (default) = on for feeders on which at least 5 of 6 buses are three-phase,
