@@ -1807,7 +1807,7 @@ extern "C" int64_t gp_fbs_jit_source(const GpFbsDesc* d, int32_t warps, int32_t 
             lines[9 * l + 6 + p] = d->line_rx_vrow[3 * l + p];
         }
     const std::string src = fbs_jit_source(steps, child4, lines, k, d->n_vrows, d->n_irows, d->n_srows, warps,
-                                           i_global != 0);
+                                           (i_global & 1) != 0, false, (i_global & 2) != 0);
     if (src.empty()) return fail(GP_EJIT, "gp_fbs_jit_source: non-finite impedance in the descriptor");
     if (buf && cap > 0) {
         const size_t n = std::min((size_t)cap - 1, src.size());
@@ -1860,12 +1860,12 @@ Driver& driver() {
 // Generate, compile and load one variant of the feeder-specialised kernel: the device-buffer kernel
 // (read_ahead = false) or the kernel of the one-launch host path, which fetches a warp's next tile over
 // PCIe before it stores the current one (read_ahead = true; more registers, so it is its own build).
-static int fbs_jit_build(GpFeeder* f, int nw, bool ig, bool read_ahead, void** mod_out, void** fn_out) {
+static int fbs_jit_build(GpFeeder* f, int nw, bool ig, bool read_ahead, void** mod_out, void** fn_out, bool ex = false) {
     FbsImpl* im = (FbsImpl*)f->impl;
     GP_CUDA(cudaSetDevice(f->device));
     GP_CUDA(cudaFree(0));       // make sure the primary context exists and is current
     const std::string src = fbs_jit_source(im->h_steps, im->h_child, im->h_lines, im->k, im->n_vrows, im->n_irows,
-                                           im->n_srows, nw, ig, read_ahead);
+                                           im->n_srows, nw, ig, read_ahead, ex);
     if (src.empty()) return fail(GP_EJIT, "gp_fbs_specialise: non-finite impedance");
     std::vector<char> bin;
     std::string log;
@@ -2168,6 +2168,7 @@ static void fbs_impl_free(FbsImpl* im) {
     cudaFree(im->d_zc);
     if (im->jit_module) driver().ModuleUnload(im->jit_module);
     if (im->jit_module_host) driver().ModuleUnload(im->jit_module_host);
+    if (im->jit_module_ex) driver().ModuleUnload(im->jit_module_ex);
     for (int i = 0; i < FbsImpl::NSTREAM; ++i) {
         if (im->d_stage[i]) cudaFree(im->d_stage[i]);
         if (im->streams[i]) cudaStreamDestroy(im->streams[i]);
@@ -2402,7 +2403,8 @@ static int sched_words(FbsImpl* im, cudaStream_t st, unsigned** out) {
 static int fbs_jit_launch(FbsImpl* im, int64_t S, int64_t ld, const double* spu, double* V, double* I,
                           int32_t* iters, int32_t* status, double* diff, double tol, int32_t maxiter,
                           cudaStream_t st, double* Vmag, double* loss, void* stage, double* Iout,
-                          const PeerDst* peers = nullptr, void* kernel = nullptr, int kernel_warps = 0) {
+                          const PeerDst* peers = nullptr, void* kernel = nullptr, int kernel_warps = 0,
+                          const char* gam = nullptr, int warm = 0) {
     const long long n_tiles = (S + 31) / 32;
     const int nw = (kernel && kernel_warps > 0) ? kernel_warps : im->jit_warps;   // a build's own block size
     long long blocks = (n_tiles + nw - 1) / nw;
@@ -2420,7 +2422,8 @@ static int fbs_jit_launch(FbsImpl* im, int64_t S, int64_t ld, const double* spu,
     if (rcs) return rcs;
     void* args[] = {(void*)&spu, (void*)&V, (void*)&I, (void*)&iters, (void*)&status, (void*)&diff,
                     (void*)&S_arg, (void*)&ldb_arg, (void*)&tol_arg, (void*)&maxiter_arg, (void*)&sched,
-                    (void*)&Vmag, (void*)&loss, (void*)&stage, (void*)&Iout, (void*)&pd};
+                    (void*)&Vmag, (void*)&loss, (void*)&stage, (void*)&Iout, (void*)&pd,
+                    (void*)&gam, (void*)&warm};        // the last two are parameters of the EX build only
     const int cr = driver().LaunchKernel(kernel ? kernel : im->jit_kernel, (unsigned)blocks, 1, 1, (unsigned)nw * 32, 1, 1, smem,
                                          (void*)st, args, nullptr);
     if (cr != 0) {
@@ -2506,9 +2509,25 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     // warps per SM - and runs only on request.)
     const bool onchip = g_fbs_kernel == 4;
     // (the specialised kernel always runs at least one sweep: maxiter < 1 goes to the table-driven ones)
-    if (extras) {
-        // per-scenario ratios / warm start: the streaming kernel's EX instance (the on-chip kernels
-        // bake the ratios into their code or tables and always start flat)
+    if (extras && !wpu && !vv && im->jit_kernel && !im->jit_ig && maxiter >= 1 &&
+        (g_fbs_kernel == 0 || g_fbs_kernel == 5)) {
+        // per-scenario ratios / warm start on a specialised feeder: the EX build of the specialised kernel
+        // (built on first use; a failed build leaves the streaming kernel's EX instance below)
+        if (!im->jit_ex_tried) {
+            im->jit_ex_tried = true;
+            if (fbs_jit_build(f, im->jit_warps, false, false, &im->jit_module_ex, &im->jit_kernel_ex, true) != GP_OK)
+                im->jit_module_ex = im->jit_kernel_ex = nullptr;
+        }
+    }
+    if (extras && !wpu && !vv && im->jit_kernel_ex && !im->jit_ig && maxiter >= 1 &&
+        (g_fbs_kernel == 0 || g_fbs_kernel == 5)) {
+        rc = fbs_jit_launch(im, S, ld, spu, V, I, iters, status, diff, tol, maxiter, st, Vmag, loss, nullptr, nullptr,
+                            &pd, im->jit_kernel_ex, im->jit_warps, gam, warm);
+        if (rc) return rc;
+        *fused = true;
+    } else if (extras) {
+        // per-scenario ratios / warm start / wpu / droop: the streaming kernel's EX instance (the table-driven
+        // on-chip kernel bakes the ratios into its tables and always starts flat)
         const int pf = g_fbs_prefetch >= 0 ? g_fbs_prefetch : 0;
         if (g_fbs_order && im->n_events > 0)
             fbs_solve_kernel<BLOCK, true, true><<<gx, BLOCK, 0, st>>>(

@@ -93,6 +93,9 @@ struct FbsImpl {
     void* jit_module_host = nullptr;  // the read-ahead build of the one-launch host path (built on first use)
     void* jit_kernel_host = nullptr;
     bool jit_host_tried = false;
+    void* jit_module_ex = nullptr;    // the build with per-scenario regulator ratios and warm starts (built on first use)
+    void* jit_kernel_ex = nullptr;
+    bool jit_ex_tried = false;
     int jit_warps = 0;
     int jit_warps_host = 0;       // warps per block of the host path's build (gp_set_option("host_warps"))
     bool jit_ig = false;          // the specialised kernel keeps the I rows in global memory (the I array)
@@ -112,7 +115,7 @@ struct FbsImpl {
 // gp_fbs_jit.cu: CUDA source of the feeder-specialised on-chip kernel, NVRTC compilation
 std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<int4>& child,
                            const std::vector<int>& lines, const FbsConst& k, int n_vrows, int n_irows, int n_srows,
-                           int nw, bool ig, bool read_ahead = false);
+                           int nw, bool ig, bool read_ahead = false, bool ex = false);
 int fbs_jit_islots(const std::vector<FbsStep>& steps, const std::vector<int4>& child, int n_irows,
                    std::vector<int>& slot, std::vector<char>& owner);
 int jit_compile(const std::string& src, std::vector<char>& cubin, std::string& log);

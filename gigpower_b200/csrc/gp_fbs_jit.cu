@@ -93,7 +93,7 @@ int fbs_jit_islots(const std::vector<FbsStep>& steps, const std::vector<int4>& c
 
 std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<int4>& child,
                            const std::vector<int>& lines, const FbsConst& k, int n_vrows, int n_irows, int n_srows,
-                           int nw, bool ig, bool read_ahead) {
+                           int nw, bool ig, bool read_ahead, bool ex) {
     // ig: the I rows live in global memory (the caller's I array, L2-resident) instead of shared
     // memory.  Only the V rows then take shared memory, so about twice as many warps fit per SM.
     // The forward sweep's I loads have static addresses and are issued two steps ahead; the
@@ -126,6 +126,13 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
     o("#define NW %d\n#define NV %d\n#define NI %d\n#define NIP %d\n#define NS %d\n", nw, n_vrows, n_irows, n_islots,
       n_srows);
     o("#define IG_MODE %d\n", ig ? 1 : 0);
+    // EX: the build behind gp_fbs_solve_batch_ex - per-scenario regulator ratios (GpSolveExtras.gamma_dev: the sweep
+    // reads this scenario's ratio where the plain build has a constant; 1 / gamma is formed first, as 1/gamma * V is in
+    // Python, solution_fbs.py:160, 205) and warm starts (the V rows and I slots are loaded from the caller's arrays
+    // instead of the flat start, also when a non-finite current sends the scenario to the exact path)
+    o("#define EX_MODE %d\n", ex ? 1 : 0);
+    o("#define GP_SWEEP_EXTRA_PARAM %s\n#define GP_SWEEP_EXTRA_ARG %s\n", ex ? ", const char* __restrict__ gp" : "",
+      ex ? ", gp" : "");
     o("#define READ_AHEAD %d\n", (read_ahead && n_srows <= 32) ? 1 : 0);   // the next tile's loads are held in registers
     o("struct GpPeerDst { double* vmag[%d]; double2* loss[%d]; int n; int pad; };\n", GP_MAX_PEERS, GP_MAX_PEERS);
     if (ig)
@@ -191,7 +198,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
     // stays finite the two agree to rounding, so the restart only costs time on diverging scenarios.
     o("template <bool EXACT>\n"
       "__device__ __noinline__ double gp_sweep(double2* __restrict__ Vs, IPTR __restrict__ Ip,\n"
-      "                                        const char* __restrict__ sp, unsigned ldb, bool& bad_out) {\n"
+      "                                        const char* __restrict__ sp, unsigned ldb, bool& bad_out GP_SWEEP_EXTRA_PARAM) {\n"
       "    bool bad = false;\n"
       "    const double2 zero = make_double2(0.0, 0.0);\n"
       "    const double aPQ = KC[0], aI = KC[1], aZ = KC[2];\n");
@@ -221,12 +228,16 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
         if (kind == GP_EDGE_VR) {           // vr_forward :138-160
             for (int p = 0; p < 3; ++p) {
                 if (st.gamma[p] == 0.0 || st.bus_vrow[p] < 0) continue;
-                if (st.par_vrow[p] >= 0)
-                    o("                { const double2 a = Vs[%d]; Vs[%d] = make_double2(GAM[%d] * a.x, GAM[%d] * a.y); }\n",
-                      st.par_vrow[p] * 32, st.bus_vrow[p] * 32, 6 * i + p, 6 * i + p);
+                if (ex)
+                    o("                { const double g = gp ? __ldg(reinterpret_cast<const double*>(gp + (size_t)%d * (size_t)(ldb >> 1))) : GAM[%d];\n",
+                      st.gam_row[p], 6 * i + p);
                 else
-                    o("                Vs[%d] = make_double2(GAM[%d] * 0.0, GAM[%d] * 0.0);\n", st.bus_vrow[p] * 32,
-                      6 * i + p, 6 * i + p);
+                    o("                { const double g = GAM[%d];\n", 6 * i + p);
+                if (st.par_vrow[p] >= 0)
+                    o("                  const double2 a = Vs[%d]; Vs[%d] = make_double2(g * a.x, g * a.y); }\n",
+                      st.par_vrow[p] * 32, st.bus_vrow[p] * 32);
+                else
+                    o("                  Vs[%d] = make_double2(g * 0.0, g * 0.0); }\n", st.bus_vrow[p] * 32);
             }
             o("            }\n");
             continue;
@@ -265,12 +276,16 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
         if (kind == GP_EDGE_VR) {           // vr_current leaves Itx = 0; vr_backward :186-205
             for (int p = 0; p < 3; ++p) {
                 if (st.gamma[p] == 0.0 || st.par_vrow[p] < 0) continue;
-                if (st.bus_vrow[p] >= 0)
-                    o("                { const double2 a = Vs[%d]; Vs[%d] = make_double2(GAM[%d] * a.x, GAM[%d] * a.y); }\n",
-                      st.bus_vrow[p] * 32, st.par_vrow[p] * 32, 6 * i + 3 + p, 6 * i + 3 + p);
+                if (ex)
+                    o("                { const double g = gp ? 1.0 / __ldg(reinterpret_cast<const double*>(gp + (size_t)%d * (size_t)(ldb >> 1))) : GAM[%d];\n",
+                      st.gam_row[p], 6 * i + 3 + p);
                 else
-                    o("                Vs[%d] = make_double2(GAM[%d] * 0.0, GAM[%d] * 0.0);\n", st.par_vrow[p] * 32,
-                      6 * i + 3 + p, 6 * i + 3 + p);
+                    o("                { const double g = GAM[%d];\n", 6 * i + 3 + p);
+                if (st.bus_vrow[p] >= 0)
+                    o("                  const double2 a = Vs[%d]; Vs[%d] = make_double2(g * a.x, g * a.y); }\n",
+                      st.bus_vrow[p] * 32, st.par_vrow[p] * 32);
+                else
+                    o("                  Vs[%d] = make_double2(g * 0.0, g * 0.0); }\n", st.par_vrow[p] * 32);
             }
             o("            }\n");
             continue;
@@ -379,12 +394,22 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
     for (int r = 0; r < n_irows; ++r)
         o(" \\\n    *reinterpret_cast<double2*>((dst) + (size_t)%d * (size_t)ldb) = %s;", r, ild(r).c_str());
     o("\n");
+    // warm start: every I slot from the row that owns it
+    o("#define GP_I_SLOTS_IN(src)");
+    for (int r = 0; r < n_irows; ++r)
+        if (!ig && iowner[r] && islot[r] >= 0)
+            o(" \\\n    IST(%d, *reinterpret_cast<const double2*>((src) + (size_t)%d * (size_t)ldb));", islot[r], r);
+    o("\n");
     o("extern \"C\" __global__ void __launch_bounds__(NW * 32, 1)\n"
       "gp_fbs_jit_kernel(const char* __restrict__ spu, char* __restrict__ V, char* __restrict__ I,\n"
       "                  int* __restrict__ iters_out, int* __restrict__ status_out, double* __restrict__ diff_out,\n"
       "                  long long S, unsigned ldb, double tol, int maxiter, unsigned* __restrict__ sched,\n"
       "                  double* __restrict__ Vmag, double2* __restrict__ loss, char* __restrict__ stage,\n"
-      "                  char* __restrict__ Iout, const GpPeerDst peers) {\n"
+      "                  char* __restrict__ Iout, const GpPeerDst peers\n"
+      "#if EX_MODE\n"
+      "                  , const char* __restrict__ gam, int warm\n"
+      "#endif\n"
+      "                  ) {\n"
       "    extern __shared__ __align__(16) double2 gp_smem[];\n"
       "    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n"
       "    double2* const Vs = gp_smem + warp * (SROWS * 32) + lane;\n"
@@ -431,18 +456,35 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
       "            sp = sd;\n"
       "        }\n"
       "        IPTR const Ip = %s;\n"
+      "#if EX_MODE\n"
+      "        const char* const gp = gam ? gam + s * 8 : nullptr;\n"
+      "        if (warm) {     // the caller's V and I rows hold an earlier solution (solution_fbs.py:76-90)\n"
+      "            for (int r = 0; r < NV; ++r) Vs[r * 32] = *reinterpret_cast<const double2*>(V + s * 16 + (size_t)r * (size_t)ldb);\n"
+      "            { const char* Iw = I + s * 16; GP_I_SLOTS_IN(Iw) }\n"
+      "        } else\n"
+      "#endif\n"
+      "        {\n"
       "        for (int r = 0; r < NV; ++r) Vs[r * 32] = zero;           // flat start (solution.py:108-125)\n"
       "        for (int r = 0; r < NIP; ++r) IST(r, zero);\n"
+      "        }\n"
       "        int it = 0;\n"
       "        double diff = -1.0;\n"
       "        bool converged = false, exact = false;\n"
       "        while (!converged && it < maxiter) {\n"
       "            bool bad = false;\n"
-      "            if (exact) diff = gp_sweep<true>(Vs, Ip, sp, ldb, bad);\n"
-      "            else diff = gp_sweep<false>(Vs, Ip, sp, ldb, bad);\n"
-      "            if (bad) {      // a non-finite current: redo this scenario from flat start, exact arithmetic\n"
+      "            if (exact) diff = gp_sweep<true>(Vs, Ip, sp, ldb, bad GP_SWEEP_EXTRA_ARG);\n"
+      "            else diff = gp_sweep<false>(Vs, Ip, sp, ldb, bad GP_SWEEP_EXTRA_ARG);\n"
+      "            if (bad) {      // a non-finite current: redo this scenario from its start, exact arithmetic\n"
+      "#if EX_MODE\n"
+      "                if (warm) {\n"
+      "                    for (int r = 0; r < NV; ++r) Vs[r * 32] = *reinterpret_cast<const double2*>(V + s * 16 + (size_t)r * (size_t)ldb);\n"
+      "                    { const char* Iw = I + s * 16; GP_I_SLOTS_IN(Iw) }\n"
+      "                } else\n"
+      "#endif\n"
+      "                {\n"
       "                for (int r = 0; r < NV; ++r) Vs[r * 32] = zero;\n"
       "                for (int r = 0; r < NIP; ++r) IST(r, zero);\n"
+      "                }\n"
       "                it = 0;\n"
       "                exact = true;\n"
       "                continue;\n"

@@ -161,7 +161,9 @@ int gp_fbs_onchip_warps(GpFeeder* f);
  *                         keeps using the table-driven kernels
  *   gp_fbs_jit_source     host only: the CUDA source for a descriptor and `warps` warps per
  *                         block, with the I rows in shared memory (i_global = 0) or in global
- *                         memory (1); returns its length (excluding the NUL) or a negative GP_E*;
+ *                         memory (1); + 2 = the build with per-scenario regulator ratios and warm starts
+ *                         that gp_fbs_solve_batch_ex launches on a specialised feeder;
+ *                         returns its length (excluding the NUL) or a negative GP_E*;
  *                         copies at most cap-1 characters into buf when buf is not NULL
  *   gp_fbs_jit_warps      warps per block gp_fbs_specialise uses for this handle (0 = the feeder
  *                         does not fit): the V rows of a warp's 32 scenarios take shared memory, the
@@ -293,7 +295,9 @@ int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const double* sp
  *   - j cappu |V|^2 + j wpu (solution.py:203), per scenario and V row.  The reference keeps Solution.wpu at
  *   zero (circuit.py:164-171) but it is a plain attribute of the object; a caller that sets it - a volt-var
  *   droop evaluated between solves, volt_var_controller.py:20-38 - gets this term.  Runs on the streaming
- *   kernel; gp_fbs_post_ex gives the matching sV.
+ *   kernel; gp_fbs_post_ex gives the matching sV.  (gamma_dev and warm_start run on the feeder-specialised kernel
+ *   once gp_fbs_specialise has built it - its own build, compiled at the first such call - and on the streaming
+ *   kernel otherwise; wpu_dev and vv_* always take the streaming kernel.)
  * vv_ctl_dev, vv_points, vv_q (FBS): volt-var droop INSIDE the iteration.  On the flagged V rows
  *   Solution.wpu is not an input but wpu = VoltVARController.get_Q(|V|) (volt_var_controller.py:20-38: maxQ below
  *   V1, a ramp to 0 at V2, 0 up to V3, a ramp to minQ at V4, minQ above, sign flipped), re-evaluated from the bus's

@@ -435,3 +435,45 @@ def test_droop_inside_the_iteration_random_batch_matches_oracle():
     assert ok.sum() > S // 2
     assert rel_err(r.V[ok], want['V'][ok]) <= TOL
     assert float(Q.abs().max()) > 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# per-scenario taps and warm starts on the feeder-specialised kernel (its EX build)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('feeder', ['IEEE_13_Bus_allwye', 'IEEE_37_Bus_allwye', 'IEEE_34_Bus_allwye',
+                                    'IEEE_13_Bus_allwye_noxfm_noreg'])
+def test_specialised_kernel_takes_taps_and_warm_starts(feeder):
+    """Once gp_fbs_specialise has built the feeder's kernel, gp_fbs_solve_batch_ex with regulator ratios and / or a
+    warm start runs on that kernel's EX build (one launch incl. |V| and losses) instead of the streaming kernel:
+    same iteration counts and status, V / I / |V| / losses within 1e-12 of the streaming kernel's, on ragged batch
+    sizes; the golden per-scenario-tap vectors of the reference are met by the taps tests above through either."""
+    from gigpower_b200 import _cabi
+    s = _fbs(feeder)
+    S = 2111
+    rng = np.random.Generator(np.random.PCG64(81))
+    mult = rng.uniform(0.5, 1.3, size=(S, s.circuit.loads.num_elements))
+    nreg = s.circuit.voltage_regulators.num_elements
+    taps = rng.integers(-16, 17, size=(S, nreg)) if nreg else None
+    outs = ('V', 'I', 'Vmag', 'loss')
+
+    def run():
+        a = s.solve_batch(load_mult=mult, taps=taps, outputs=outs, return_device=True)
+        n0 = _cabi.gp_launch_count()
+        b = s.solve_batch(load_mult=mult * 1.07, taps=taps, outputs=outs, warm_start=a)
+        return a, b, _cabi.gp_launch_count() - n0
+
+    try:
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 3))
+        a3, b3, n3 = run()
+        a3 = (a3.iterations.cpu().numpy(), a3.status.cpu().numpy())
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 0))
+        assert s.specialise()
+        a5, b5, n5 = run()
+        assert n5 == 1 and n3 >= 2                      # one fused launch against solve + |V| + loss kernels
+        assert np.array_equal(a5.iterations.cpu().numpy(), a3[0]) and np.array_equal(a5.status.cpu().numpy(), a3[1])
+        assert np.array_equal(b5.iterations, b3.iterations) and np.array_equal(b5.status, b3.status)
+        assert (b3.status == 0).all() and b3.iterations.mean() < a3[0].mean()      # the warm start is a warm start
+        assert rel_err(b5.V, b3.V) <= 1e-12 and rel_err(b5.I, b3.I) <= 1e-12
+        assert rel_err(b5.Vmag, b3.Vmag) <= 1e-12 and rel_err(b5.losses, b3.losses) <= 1e-12
+    finally:
+        _cabi.gp_set_option(b'fbs_kernel', 0)
