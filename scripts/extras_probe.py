@@ -47,7 +47,7 @@ rows = torch.from_numpy(np.ascontiguousarray(s13.load_weights() @ mult.T)).cuda(
 taps = torch.from_numpy(rng.integers(-16, 17, size=(S, 3))).cuda()
 wpu = torch.zeros((s13.tables.n_vrows, S), dtype=torch.float64, device='cuda')
 wpu[5] = 0.01
-for name, kw in (('plain (specialised on-chip kernel)', {}), ('taps per scenario (streaming kernel)', {'taps': taps}),
+for name, kw in (('plain (specialised on-chip kernel)', {}), ('taps per scenario (EX build of the specialised kernel since round 2)', {'taps': taps}),
                  ('wpu per scenario (streaming kernel)', {'wpu': wpu})):
     seg0 = torch.cuda.memory_stats()['segment.all.allocated']
     t, _ = wall(lambda: s13.solve_batch(spu_rows=rows, outputs=('Vmag', 'loss'), return_device=True, **kw), reps=10)
