@@ -615,6 +615,7 @@ def run_workload(ctx, args, name, steps, main):
         sol = SolutionNR3(feeder_file(feeder), device=local)
     rows, mult = make_scenarios(sol, S, seed + 1000 * rank, spec, first=rank * S, device=dev)
     _cabi.check(_cabi.gp_set_option(b'jit_i_global', args.jit_ig))
+    _cabi.check(_cabi.gp_set_option(b'jit_dfs', args.jit_dfs))
     _cabi.check(_cabi.gp_set_option(b'fbs_share_rows', args.share_rows))
     if args.host_warps:
         _cabi.check(_cabi.gp_set_option(b'host_warps', args.host_warps))
@@ -934,7 +935,8 @@ def run_workload(ctx, args, name, steps, main):
                         5: 'gp_fbs_jit_kernel', 6: 'fbs_walk_kernel'}
         variant = {0: None, 1: 'fused-dfs', 2: 'phase-parallel', 3: 'two-sweep streaming (state in HBM)',
                    4: 'on-chip two-sweep (state in shared memory), table-driven',
-                   5: 'on-chip two-sweep (state in shared memory), feeder-specialised (NVRTC)',
+                   5: 'on-chip, feeder-specialised (NVRTC): two sweeps with V and I in shared memory, or depth-first with I '
+                      'in shared memory and V in the caller\'s array',
                    6: 'tree walk (depth-first, current bus in registers, rows in HBM)'}[active]
         # per sweep read I, write V | read V, read spu, write I, write V; once: read spu, write V, I
         stream_per_it = 16 * (2 * t.n_irows + 3 * t.n_vrows + t.n_srows)
@@ -1112,6 +1114,8 @@ def main():
                          'specialised FBS kernel, copy-engine pushes otherwise) or by NCCL')
     ap.add_argument('--jit-ig', type=int, default=-1, choices=[-1, 0, 1],
                     help='I rows of the specialised FBS kernel in global memory: -1 automatic, 0 no, 1 yes')
+    ap.add_argument('--jit-dfs', type=int, default=-1, choices=[-1, 0, 1],
+                    help='depth-first build of the specialised FBS kernel (V rows off chip): -1 automatic, 0 no, 1 yes')
     ap.add_argument('--host-warps', type=int, default=0,
                     help='warps per SM of the one-launch host path (e2e); 0 = the library default')
     ap.add_argument('--push-streams', type=int, default=0,

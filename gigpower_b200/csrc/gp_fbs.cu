@@ -32,6 +32,7 @@ extern int g_nr3_ring;
 extern int g_peer_push_streams;   // gp_peer.cu
 namespace gp {
 int nr3_gamma_rows(GpFeeder* f);   // gp_nr3.cu
+static int g_jit_dfs = -1;         // gp_set_option("jit_dfs", -1|0|1): depth-first build of the specialised kernel (V rows off chip)
 static int g_jit_i_global = -1;    // gp_set_option("jit_i_global", -1|0|1): I rows of the specialised kernel in global memory
 static int g_host_read_ahead = 1;  // gp_set_option("host_read_ahead", 0|1): read-ahead build of the one-launch host path
 static int g_host_zero_copy = 1;   // gp_set_option("host_zero_copy", 0|1): one-launch host path of the specialised kernel
@@ -1520,6 +1521,10 @@ extern "C" int gp_set_option(const char* name, int value) {
         g_nr3_prefetch = value;
         return GP_OK;
     }
+    if (name && strcmp(name, "jit_dfs") == 0 && value >= -1 && value <= 1) {
+        g_jit_dfs = value;          // takes effect for feeders created afterwards
+        return GP_OK;
+    }
     if (name && strcmp(name, "jit_i_global") == 0 && value >= -1 && value <= 1) {
         g_jit_i_global = value;      // takes effect for feeders created afterwards
         return GP_OK;
@@ -1807,7 +1812,7 @@ extern "C" int64_t gp_fbs_jit_source(const GpFbsDesc* d, int32_t warps, int32_t 
             lines[9 * l + 6 + p] = d->line_rx_vrow[3 * l + p];
         }
     const std::string src = fbs_jit_source(steps, child4, lines, k, d->n_vrows, d->n_irows, d->n_srows, warps,
-                                           (i_global & 1) != 0, false, (i_global & 2) != 0);
+                                           (i_global & 1) != 0, false, (i_global & 2) != 0, (i_global & 4) != 0);
     if (src.empty()) return fail(GP_EJIT, "gp_fbs_jit_source: non-finite impedance in the descriptor");
     if (buf && cap > 0) {
         const size_t n = std::min((size_t)cap - 1, src.size());
@@ -1860,12 +1865,13 @@ Driver& driver() {
 // Generate, compile and load one variant of the feeder-specialised kernel: the device-buffer kernel
 // (read_ahead = false) or the kernel of the one-launch host path, which fetches a warp's next tile over
 // PCIe before it stores the current one (read_ahead = true; more registers, so it is its own build).
-static int fbs_jit_build(GpFeeder* f, int nw, bool ig, bool read_ahead, void** mod_out, void** fn_out, bool ex = false) {
+static int fbs_jit_build(GpFeeder* f, int nw, bool ig, bool read_ahead, void** mod_out, void** fn_out, bool ex = false,
+                         bool dfs = false) {
     FbsImpl* im = (FbsImpl*)f->impl;
     GP_CUDA(cudaSetDevice(f->device));
     GP_CUDA(cudaFree(0));       // make sure the primary context exists and is current
     const std::string src = fbs_jit_source(im->h_steps, im->h_child, im->h_lines, im->k, im->n_vrows, im->n_irows,
-                                           im->n_srows, nw, ig, read_ahead, ex);
+                                           im->n_srows, nw, ig, read_ahead, ex, dfs);
     if (src.empty()) return fail(GP_EJIT, "gp_fbs_specialise: non-finite impedance");
     std::vector<char> bin;
     std::string log;
@@ -1878,7 +1884,8 @@ static int fbs_jit_build(GpFeeder* f, int nw, bool ig, bool read_ahead, void** m
     int cr = dr.ModuleLoadData(&mod, bin.data());
     if (cr != 0) return fail(GP_EJIT, "gp_fbs_specialise: cuModuleLoadData failed (%d)", cr);
     cr = dr.ModuleGetFunction(&fn, mod, "gp_fbs_jit_kernel");
-    const int smem = nw * (im->n_vrows + (ig ? 0 : im->n_islots)) * 512;
+    const int rows = dfs ? im->n_islots + im->n_dfs_stack : im->n_vrows + (ig ? 0 : im->n_islots);
+    const int smem = nw * rows * 512;
     if (cr == 0) cr = dr.FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, smem);
     if (cr != 0) {
         dr.ModuleUnload(mod);
@@ -1895,10 +1902,12 @@ extern "C" int gp_fbs_specialise(GpFeeder* f) {
     if (im->jit_kernel) return GP_OK;
     if (im->jit_plan_warps < 1) return fail(GP_EJIT, "gp_fbs_specialise: the feeder does not fit the on-chip kernel");
     void *mod = nullptr, *fn = nullptr;
-    int rc = fbs_jit_build(f, im->jit_plan_warps, im->jit_plan_ig, false, &mod, &fn);
+    int rc = fbs_jit_build(f, im->jit_plan_warps, im->jit_plan_ig, false, &mod, &fn, false, im->jit_plan_dfs);
     if (rc) return rc;
     im->jit_warps = im->jit_plan_warps;
     im->jit_ig = im->jit_plan_ig;
+    im->jit_dfs = im->jit_plan_dfs;
+    im->jit_rows = im->jit_dfs ? im->n_islots + im->n_dfs_stack : im->n_vrows + (im->jit_ig ? 0 : im->n_islots);
     im->jit_module = mod;
     im->jit_kernel = fn;
     return GP_OK;
@@ -2356,6 +2365,19 @@ extern "C" int gp_fbs_create(const GpFbsDesc* d, int device, GpFeeder** out) {
         // 34-bus 2 -> 4 warps: 1.21x; 37-bus 1 -> 3 warps: 1.49x  =>  only when it at least doubles the warps
         im->jit_plan_ig = g_jit_i_global == 1 || (g_jit_i_global < 0 && w_ig >= 2 * w_is && w_ig > 0);
         im->jit_plan_warps = im->jit_plan_ig ? w_ig : w_is;
+        // depth-first build: the V rows leave shared memory altogether (I slots + a small stack stay).  Automatic when
+        // it at least doubles the warps of the two-sweep build (34-bus 3 -> 6, 37-bus 2 -> 4; 13-bus 7 -> 8: no)
+        im->jit_alt_warps = im->jit_plan_warps;     // the two-sweep plan: what the one-launch host path runs when the
+        im->jit_alt_ig = im->jit_plan_ig;           // device path takes the depth-first build
+        im->n_dfs_stack = fbs_jit_dfs_stack(im->h_steps, im->h_child, im->k, d->n_vrows, d->n_irows);
+        if (im->n_dfs_stack >= 0 && g_jit_dfs != 0) {
+            const int w_dfs = pick((size_t)(im->n_islots + im->n_dfs_stack) * 512);
+            if (w_dfs > 0 && (g_jit_dfs == 1 || w_dfs >= 2 * im->jit_plan_warps)) {
+                im->jit_plan_dfs = true;
+                im->jit_plan_ig = false;
+                im->jit_plan_warps = w_dfs;
+            }
+        }
     }
     GpFeeder* f = new (std::nothrow) GpFeeder();
     if (!f) {
@@ -2404,12 +2426,12 @@ static int fbs_jit_launch(FbsImpl* im, int64_t S, int64_t ld, const double* spu,
                           int32_t* iters, int32_t* status, double* diff, double tol, int32_t maxiter,
                           cudaStream_t st, double* Vmag, double* loss, void* stage, double* Iout,
                           const PeerDst* peers = nullptr, void* kernel = nullptr, int kernel_warps = 0,
-                          const char* gam = nullptr, int warm = 0) {
+                          const char* gam = nullptr, int warm = 0, int kernel_rows = 0) {
     const long long n_tiles = (S + 31) / 32;
     const int nw = (kernel && kernel_warps > 0) ? kernel_warps : im->jit_warps;   // a build's own block size
     long long blocks = (n_tiles + nw - 1) / nw;
     if (blocks > im->n_sm) blocks = im->n_sm;
-    const unsigned smem = (unsigned)nw * (unsigned)(im->n_vrows + (im->jit_ig ? 0 : im->n_islots)) * 512u;
+    const unsigned smem = (unsigned)nw * (unsigned)((kernel && kernel_rows > 0) ? kernel_rows : im->jit_rows) * 512u;
     long long S_arg = S;
     double tol_arg = tol;
     int maxiter_arg = maxiter;
@@ -2509,7 +2531,7 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     // warps per SM - and runs only on request.)
     const bool onchip = g_fbs_kernel == 4;
     // (the specialised kernel always runs at least one sweep: maxiter < 1 goes to the table-driven ones)
-    if (extras && !wpu && !vv && im->jit_kernel && !im->jit_ig && maxiter >= 1 &&
+    if (extras && !wpu && !vv && im->jit_kernel && !im->jit_ig && !im->jit_dfs && maxiter >= 1 &&
         (g_fbs_kernel == 0 || g_fbs_kernel == 5)) {
         // per-scenario ratios / warm start on a specialised feeder: the EX build of the specialised kernel
         // (built on first use; a failed build leaves the streaming kernel's EX instance below)
@@ -2519,7 +2541,7 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
                 im->jit_module_ex = im->jit_kernel_ex = nullptr;
         }
     }
-    if (extras && !wpu && !vv && im->jit_kernel_ex && !im->jit_ig && maxiter >= 1 &&
+    if (extras && !wpu && !vv && im->jit_kernel_ex && !im->jit_ig && !im->jit_dfs && maxiter >= 1 &&
         (g_fbs_kernel == 0 || g_fbs_kernel == 5)) {
         rc = fbs_jit_launch(im, S, ld, spu, V, I, iters, status, diff, tol, maxiter, st, Vmag, loss, nullptr, nullptr,
                             &pd, im->jit_kernel_ex, im->jit_warps, gam, warm);
@@ -2756,7 +2778,10 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
     // One-launch path: with the feeder-specialised kernel and pinned (device-mapped) host buffers the
     // kernel reads spu and writes its results over PCIe itself, tile by tile: upload, solve and
     // download overlap inside one launch and there is nothing to chunk.
-    if (im->jit_kernel && maxiter >= 1 && g_host_zero_copy && (g_fbs_kernel == 0 || g_fbs_kernel == 5) &&
+    // (a handle whose device kernel is the depth-first build writes its V rows every sweep, which must not cross
+    // PCIe: its host path runs the two-sweep build, compiled here on first use, when that build fits at all)
+    if (im->jit_kernel && (!im->jit_dfs || (im->jit_alt_warps >= 1 && !im->jit_alt_ig)) && maxiter >= 1 &&
+        g_host_zero_copy && (g_fbs_kernel == 0 || g_fbs_kernel == 5) &&
         ld * 16 < ((int64_t)1 << 32)) {
         const void* hp[] = {spu_h, V_h, I_h, Vmag_h, loss_h, iters_h, status_h, diff_h};
         void* dp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -2785,7 +2810,8 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
             if (!im->streams[0]) GP_CUDA(cudaStreamCreateWithFlags(&im->streams[0], cudaStreamNonBlocking));
             // the host path's own build of the kernel (next tile's PCIe reads issued before this tile's stores);
             // feeders with more than 32 load rows, or a failed build, keep the device-path kernel
-            const int want_host_warps = im->jit_warps < g_host_warps ? im->jit_warps : g_host_warps;
+            const int dev_warps = im->jit_dfs ? im->jit_alt_warps : im->jit_warps;
+            const int want_host_warps = dev_warps < g_host_warps ? dev_warps : g_host_warps;
             if (im->jit_host_tried && im->jit_kernel_host && im->jit_warps_host != want_host_warps) {
                 // gp_set_option("host_warps") changed since this handle's host kernel was built: build again
                 GP_CUDA(cudaStreamSynchronize(im->streams[0]));
@@ -2793,24 +2819,28 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
                 im->jit_module_host = im->jit_kernel_host = nullptr;
                 im->jit_host_tried = false;
             }
-            if (!im->jit_host_tried && im->n_srows <= 32 && g_host_read_ahead) {
+            if (!im->jit_host_tried && ((im->n_srows <= 32 && g_host_read_ahead) || im->jit_dfs)) {
                 im->jit_host_tried = true;
                 im->jit_warps_host = want_host_warps;
-                if (fbs_jit_build(f, im->jit_warps_host, im->jit_ig, true, &im->jit_module_host, &im->jit_kernel_host) != GP_OK)
+                if (fbs_jit_build(f, im->jit_warps_host, im->jit_dfs ? false : im->jit_ig, g_host_read_ahead != 0, &im->jit_module_host,
+                                  &im->jit_kernel_host) != GP_OK)
                     im->jit_module_host = im->jit_kernel_host = nullptr;
             }
+            if (im->jit_dfs && !im->jit_kernel_host) goto staged;       // no two-sweep build: copy - solve - copy
             // I rows kept in global memory must stay on the device; the host copy is a second destination
             double* I_state = im->jit_ig ? (double*)((char*)im->d_zc + b_stage) : (double*)dp[2];
             rc = fbs_jit_launch(im, S, ld, (const double*)dp[0], (double*)dp[1], I_state, (int32_t*)dp[5],
                                 (int32_t*)dp[6], (double*)dp[7], tol, maxiter, im->streams[0], (double*)dp[3],
                                 (double*)dp[4], im->d_zc, im->jit_ig ? (double*)dp[2] : nullptr, nullptr,
-                                g_host_read_ahead ? im->jit_kernel_host : nullptr, im->jit_warps_host);
+                                (g_host_read_ahead || im->jit_dfs) ? im->jit_kernel_host : nullptr, im->jit_warps_host,
+                                nullptr, 0, im->n_vrows + im->n_islots);
             if (rc) return rc;
             count_launch();
             GP_CUDA(cudaStreamSynchronize(im->streams[0]));
             return GP_OK;
         }
     }
+staged:
     // (measured on B200, 123-bus, 140,160 scenarios, 0.8 GB over PCIe: 2 chunks 7.3e6 solves/s, 4: 6.8e6, 8: 5.6e6,
     // 16: 4.1e6 - the solve of a chunk is latency-bound and takes as long as the whole batch's, and every row piece
     // is its own DMA, so more and smaller chunks only add overhead)

@@ -99,6 +99,11 @@ struct FbsImpl {
     int jit_warps = 0;
     int jit_warps_host = 0;       // warps per block of the host path's build (gp_set_option("host_warps"))
     bool jit_ig = false;          // the specialised kernel keeps the I rows in global memory (the I array)
+    bool jit_dfs = false, jit_plan_dfs = false;   // the depth-first build (V rows in the caller's array, I slots + a stack on chip)
+    int jit_alt_warps = 0;        // warps and I placement of the two-sweep plan (the host path's build when jit_dfs)
+    bool jit_alt_ig = false;
+    int n_dfs_stack = -1;         // its stack slots (-1: the feeder cannot be built that way)
+    int jit_rows = 0;             // shared-memory rows per warp of the built kernel
     int n_islots = 0;             // shared-memory slots the specialised kernel needs for the I rows (fbs_jit_islots)
     int jit_plan_warps = 0;       // warps per block gp_fbs_specialise will use (0 = feeder does not fit)
     bool jit_plan_ig = false;
@@ -115,7 +120,9 @@ struct FbsImpl {
 // gp_fbs_jit.cu: CUDA source of the feeder-specialised on-chip kernel, NVRTC compilation
 std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<int4>& child,
                            const std::vector<int>& lines, const FbsConst& k, int n_vrows, int n_irows, int n_srows,
-                           int nw, bool ig, bool read_ahead = false, bool ex = false);
+                           int nw, bool ig, bool read_ahead = false, bool ex = false, bool dfs = false);
+int fbs_jit_dfs_stack(const std::vector<FbsStep>& steps, const std::vector<int4>& child, const FbsConst& k, int n_vrows,
+                      int n_irows);
 int fbs_jit_islots(const std::vector<FbsStep>& steps, const std::vector<int4>& child, int n_irows,
                    std::vector<int>& slot, std::vector<char>& owner);
 int jit_compile(const std::string& src, std::vector<char>& cubin, std::string& log);

@@ -21,8 +21,11 @@
 
 #include <dlfcn.h>
 
+#include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
+#include <functional>
 
 namespace gp {
 
@@ -91,9 +94,117 @@ int fbs_jit_islots(const std::vector<FbsStep>& steps, const std::vector<int4>& c
     return n_slots;
 }
 
+namespace {
+// Tree of the step table for the depth-first build: parent step (-1 = root) and children latest-in-topo-order first.
+// false when the table is not a tree in topo order or a regulator leaves a phase of its bus unregulated.
+bool dfs_tree(const std::vector<FbsStep>& steps, const FbsConst& k, int n_vrows, std::vector<int>& par,
+              std::vector<std::vector<int>>& kids, std::vector<int>& size) {
+    const int n = (int)steps.size();
+    std::vector<int> row_step((size_t)n_vrows, -2);
+    for (int p = 0; p < 3; ++p) row_step[k.root_vrow[p]] = -1;
+    for (int i = 0; i < n; ++i)
+        for (int p = 0; p < 3; ++p)
+            if (steps[i].bus_vrow[p] >= 0) row_step[steps[i].bus_vrow[p]] = i;
+    par.assign((size_t)n, -2);
+    kids.assign((size_t)n + 1, {});
+    for (int i = 0; i < n; ++i) {
+        for (int p = 0; p < 3; ++p)
+            if (steps[i].par_vrow[p] >= 0) par[i] = row_step[steps[i].par_vrow[p]];
+        if (par[i] < -1 || par[i] >= i) return false;
+        kids[par[i] + 1].push_back(i);
+        if ((steps[i].kind & 0xff) == GP_EDGE_VR)
+            for (int p = 0; p < 3; ++p)
+                if (steps[i].bus_vrow[p] >= 0 && steps[i].gamma[p] == 0.0) return false;
+    }
+    for (auto& ks : kids) std::sort(ks.begin(), ks.end(), std::greater<int>());
+    size.assign((size_t)n, 1);
+    for (int i = n - 1; i >= 0; --i)
+        if (par[i] >= 0) size[par[i]] += size[i];
+    return true;
+}
+
+struct DfsLive { std::vector<std::pair<int, int>> vals; };     // (kind 0 = f / 1 = a, phase) of the parent kept across a child
+
+// What of bus k (step index, -1 = root) must survive the visit of its j-th child (see fbs_jit_source, DFS build)
+DfsLive dfs_live(const std::vector<FbsStep>& steps, const std::vector<int>& islot, const std::vector<std::vector<int>>& kids,
+                 const std::vector<std::array<bool, 3>>& win, int k, int j) {
+    DfsLive L;
+    const auto& ks = kids[k + 1];
+    for (int p = 0; p < 3; ++p) {
+        if (k >= 0 && steps[k].bus_vrow[p] < 0) continue;
+        bool needed_later = false, rewritten = false;
+        for (int j2 = 0; j2 < (int)ks.size(); ++j2) {
+            const FbsStep& c2 = steps[ks[j2]];
+            if (j2 > j && c2.par_vrow[p] >= 0 && (c2.bus_vrow[p] >= 0 || (c2.kind & 0xff) == GP_EDGE_VR)) needed_later = true;
+            if (j2 >= j && win[ks[j2]][p]) rewritten = true;
+        }
+        if (needed_later || !rewritten) L.vals.push_back({0, p});
+    }
+    if (k >= 0 && (steps[k].kind & 0xff) != GP_EDGE_VR)
+        for (int p = 0; p < 3; ++p) {
+            const int r = steps[k].edge_irow[p];
+            if (r < 0 || islot[r] < 0) continue;
+            bool earlier = false;
+            for (int j2 = 0; j2 < j; ++j2) {
+                const FbsStep& c2 = steps[ks[j2]];
+                if ((c2.kind & 0xff) != GP_EDGE_VR && c2.edge_irow[p] >= 0 && islot[c2.edge_irow[p]] >= 0) earlier = true;
+            }
+            if (earlier) L.vals.push_back({1, p});
+        }
+    return L;
+}
+}  // namespace
+
+// Shared-memory stack slots the depth-first build needs (-1: the feeder cannot be built that way)
+int fbs_jit_dfs_stack(const std::vector<FbsStep>& steps, const std::vector<int4>& child, const FbsConst& k, int n_vrows,
+                      int n_irows) {
+    const int n = (int)steps.size();
+    if (n == 0 || n > 64) return -1;         // straight-line code of a larger feeder outgrows the instruction cache
+    std::vector<int> par, size, islot;
+    std::vector<char> iowner;
+    std::vector<std::vector<int>> kids;
+    if (!dfs_tree(steps, k, n_vrows, par, kids, size)) return -1;
+    fbs_jit_islots(steps, child, n_irows, islot, iowner);
+    std::vector<std::array<bool, 3>> win((size_t)n);
+    {
+        std::vector<char> written((size_t)n_vrows, 0);
+        for (int i = 0; i < n; ++i)
+            for (int p = 0; p < 3; ++p) {
+                const bool vr = (steps[i].kind & 0xff) == GP_EDGE_VR;
+                const bool stores = steps[i].par_vrow[p] >= 0 && (vr ? steps[i].gamma[p] != 0.0 : steps[i].bus_vrow[p] >= 0);
+                win[i][p] = stores && !written[steps[i].par_vrow[p]];
+                if (stores) written[steps[i].par_vrow[p]] = 1;
+            }
+    }
+    int nst = 0;
+    std::function<void(int, int)> walk = [&](int kk, int sp) {
+        const auto& ks = kids[kk + 1];
+        for (int j = 0; j < (int)ks.size(); ++j) {
+            const int c = ks[j];
+            int m = 0;
+            if (size[c] >= 2) m = (int)dfs_live(steps, islot, kids, win, kk, j).vals.size();
+            nst = std::max(nst, sp + m);
+            walk(c, sp + m);
+        }
+    };
+    walk(-1, 0);
+    return nst;
+}
+
 std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<int4>& child,
                            const std::vector<int>& lines, const FbsConst& k, int n_vrows, int n_irows, int n_srows,
-                           int nw, bool ig, bool read_ahead, bool ex) {
+                           int nw, bool ig, bool read_ahead, bool ex, bool dfs) {
+    // dfs: the depth-first build.  The sweep walks the tree depth-first (a bus's forward step on the way down, its
+    // backward step on the way up, children latest-in-topo-order first - the order fbs_solve_kernel uses, see there
+    // for why every value is the reference's) and keeps a bus's voltage in a C++ variable of the block that is its
+    // subtree, so V needs NO shared memory: a row goes to the caller's V array once per sweep when it is final, and
+    // the epilogue reads it back from there.  Shared memory holds the I slots and a small stack: what a bus must
+    // keep across the visit of a child with children of its own (its forward voltage if later children still read
+    // it, its partial current sum) is parked there around that child, so the registers are free inside the subtree.
+    // 34-bus feeder: 144 -> 66 rows per warp, 3 -> 6 warps per SM; 37-bus: 194 -> 95 rows, 2 -> 4 warps.
+    if (dfs && (ig || ex || read_ahead)) return std::string();
+    const int n_stack = dfs ? fbs_jit_dfs_stack(steps, child, k, n_vrows, n_irows) : 0;
+    if (dfs && n_stack < 0) return std::string();
     // ig: the I rows live in global memory (the caller's I array, L2-resident) instead of shared
     // memory.  Only the V rows then take shared memory, so about twice as many warps fit per SM.
     // The forward sweep's I loads have static addresses and are issued two steps ahead; the
@@ -126,13 +237,14 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
     o("#define NW %d\n#define NV %d\n#define NI %d\n#define NIP %d\n#define NS %d\n", nw, n_vrows, n_irows, n_islots,
       n_srows);
     o("#define IG_MODE %d\n", ig ? 1 : 0);
+    o("#define DFS_MODE %d\n#define NST %d\n#define NVS %s\n", dfs ? 1 : 0, n_stack, dfs ? "0" : "NV");
     // EX: the build behind gp_fbs_solve_batch_ex - per-scenario regulator ratios (GpSolveExtras.gamma_dev: the sweep
     // reads this scenario's ratio where the plain build has a constant; 1 / gamma is formed first, as 1/gamma * V is in
     // Python, solution_fbs.py:160, 205) and warm starts (the V rows and I slots are loaded from the caller's arrays
     // instead of the flat start, also when a non-finite current sends the scenario to the exact path)
     o("#define EX_MODE %d\n", ex ? 1 : 0);
-    o("#define GP_SWEEP_EXTRA_PARAM %s\n#define GP_SWEEP_EXTRA_ARG %s\n", ex ? ", const char* __restrict__ gp" : "",
-      ex ? ", gp" : "");
+    o("#define GP_SWEEP_EXTRA_PARAM %s\n#define GP_SWEEP_EXTRA_ARG %s\n",
+      ex ? ", const char* __restrict__ gp" : (dfs ? ", char* __restrict__ Vw" : ""), ex ? ", gp" : (dfs ? ", Vw" : ""));
     o("#define READ_AHEAD %d\n", (read_ahead && n_srows <= 32) ? 1 : 0);   // the next tile's loads are held in registers
     o("struct GpPeerDst { double* vmag[%d]; double2* loss[%d]; int n; int pad; };\n", GP_MAX_PEERS, GP_MAX_PEERS);
     if (ig)
@@ -140,9 +252,16 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
           "#define ILD(r) __ldcg(reinterpret_cast<const double2*>(Ip + (size_t)(r) * (size_t)ldb))\n"
           "#define IST(r, v) (*reinterpret_cast<double2*>(Ip + (size_t)(r) * (size_t)ldb) = (v))\n");
     else
-        o("#define IPTR double2*\n#define SROWS (NV + NIP)\n"
+        o("#define IPTR double2*\n#define SROWS (NVS + NIP + NST)\n"
           "#define ILD(r) Ip[(r) * 32]\n"
-          "#define IST(r, v) (Ip[(r) * 32] = (v))\n");
+          "#define IST(r, v) (Ip[(r) * 32] = (v))\n"
+          "#define SLD(j) Ip[(NIP + (j)) * 32]\n"
+          "#define SST(j, v) (Ip[(NIP + (j)) * 32] = (v))\n");
+    if (dfs)
+        o("#define VLD(r) __ldcg(reinterpret_cast<const double2*>(Vw + (size_t)(r) * (size_t)ldb))\n"
+          "#define VST(r, v) (*reinterpret_cast<double2*>(Vw + (size_t)(r) * (size_t)ldb) = (v))\n");
+    else
+        o("#define VLD(r) Vs[(r) * 32]\n");
     std::vector<int> row2step((size_t)(n_irows > 0 ? n_irows : 1), -1);
     for (int i = 0; i < n_steps; ++i)
         for (int p = 0; p < 3; ++p)
@@ -215,6 +334,205 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
         fwd_loads(0);
         fwd_loads(1);
     }
+    if (dfs) {
+        if (spu_regs)
+            for (int r = 0; r < n_srows; ++r) o("    const double2 L%d = LDS_(%d);\n", r, r);
+        std::vector<int> par, size;
+        std::vector<std::vector<int>> kids;
+        dfs_tree(steps, k, n_vrows, par, kids, size);
+        std::vector<std::array<bool, 3>> win((size_t)n_steps);
+        {
+            std::vector<char> written((size_t)n_vrows, 0);
+            for (int i = 0; i < n_steps; ++i)
+                for (int p = 0; p < 3; ++p) {
+                    const bool vr = (steps[i].kind & 0xff) == GP_EDGE_VR;
+                    const bool stores = steps[i].par_vrow[p] >= 0 && (vr ? steps[i].gamma[p] != 0.0 : steps[i].bus_vrow[p] >= 0);
+                    win[i][p] = stores && !written[steps[i].par_vrow[p]];
+                    if (stores) written[steps[i].par_vrow[p]] = 1;
+                }
+        }
+        auto vname = [&](int node, int p) {
+            char b[32];
+            if (node < 0) snprintf(b, sizeof(b), "fR%d", p);
+            else snprintf(b, sizeof(b), "f%d_%d", node, p);
+            return std::string(b);
+        };
+        for (int p = 0; p < 3; ++p) o("    double2 fR%d = make_double2(KC[%d], KC[%d]);\n", p, 3 + 2 * p, 4 + 2 * p);
+        // `restore`: what the PARENT parked around this bus's visit; it is taken back after this bus's own children,
+        // right before the backward step that adds to the parent's current sum and may rewrite its voltage
+        std::function<void(int, int, const std::string&)> emit = [&](int i, int sp, const std::string& restore) {
+            const FbsStep& st = steps[i];
+            const bool vr = (st.kind & 0xff) == GP_EDGE_VR;
+            const int pk = par[i];
+            o("    {   // bus of step %d\n", i);
+            // ---- on the way down: forward step (update_voltage_forward :162-184 / vr_forward :138-160) ----
+            if (!vr)
+                for (int q = 0; q < 3; ++q)
+                    if (st.edge_irow[q] >= 0 && islot[st.edge_irow[q]] >= 0)
+                        o("      const double2 i%d = %s;\n", q, ild(st.edge_irow[q]).c_str());
+            for (int p = 0; p < 3; ++p) {
+                if (st.bus_vrow[p] < 0) continue;
+                const std::string P = st.par_vrow[p] >= 0 ? vname(pk, p) : std::string("zero");
+                if (vr) {
+                    o("      double2 f%d_%d = make_double2(GAM[%d] * %s.x, GAM[%d] * %s.y);\n", i, p, 6 * i + p, P.c_str(),
+                      6 * i + p, P.c_str());
+                    continue;
+                }
+                o("      double2 f%d_%d = %s;\n", i, p, P.c_str());
+                for (int q = 0; q < 3; ++q) {
+                    if (st.edge_irow[q] < 0 || islot[st.edge_irow[q]] < 0) continue;
+                    const int zi = 9 * i + 3 * p + q;
+                    o("      if (EXACT) {\n");
+                    o("        f%d_%d.x -= ZR[%d] * i%d.x - ZI[%d] * i%d.y;\n", i, p, zi, q, zi, q);
+                    o("        f%d_%d.y -= ZR[%d] * i%d.y + ZI[%d] * i%d.x;\n", i, p, zi, q, zi, q);
+                    o("      } else {\n");
+                    o("        f%d_%d.x = fma(ZI[%d], i%d.y, fma(-ZR[%d], i%d.x, f%d_%d.x));\n", i, p, zi, q, zi, q, i, p);
+                    o("        f%d_%d.y = fma(-ZI[%d], i%d.x, fma(-ZR[%d], i%d.y, f%d_%d.y));\n", i, p, zi, q, zi, q, i, p);
+                    o("      }\n");
+                }
+            }
+            if (!vr)
+                for (int p = 0; p < 3; ++p)
+                    if (st.edge_irow[p] >= 0 && islot[st.edge_irow[p]] >= 0) o("      double2 a%d_%d = zero;\n", i, p);
+            // ---- the children, latest in topo order first ----
+            const auto& ks = kids[i + 1];
+            for (int j = 0; j < (int)ks.size(); ++j) {
+                const int c = ks[j];
+                DfsLive L;
+                if (size[c] >= 2) L = dfs_live(steps, islot, kids, win, i, j);
+                std::string back;
+                for (size_t m = 0; m < L.vals.size(); ++m) {
+                    char b[96];
+                    o("      SST(%d, %c%d_%d);\n", sp + (int)m, L.vals[m].first ? 'a' : 'f', i, L.vals[m].second);
+                    snprintf(b, sizeof(b), "      %c%d_%d = SLD(%d);\n", L.vals[m].first ? 'a' : 'f', i, L.vals[m].second, sp + (int)m);
+                    back += b;
+                }
+                emit(c, sp + (int)L.vals.size(), back);
+            }
+            o("%s", restore.c_str());
+            // ---- on the way up: backward step ----
+            if (vr) {       // vr_current leaves Itx = 0; vr_backward :186-205
+                for (int p = 0; p < 3; ++p) {
+                    if (!win[i][p]) continue;
+                    if (st.bus_vrow[p] >= 0)
+                        o("      %s = make_double2(GAM[%d] * f%d_%d.x, GAM[%d] * f%d_%d.y);\n", vname(pk, p).c_str(),
+                          6 * i + 3 + p, i, p, 6 * i + 3 + p, i, p);
+                    else
+                        o("      %s = make_double2(GAM[%d] * 0.0, GAM[%d] * 0.0);\n", vname(pk, p).c_str(), 6 * i + 3 + p,
+                          6 * i + 3 + p);
+                }
+                for (int p = 0; p < 3; ++p)
+                    if (st.bus_vrow[p] >= 0) o("      VST(%d, f%d_%d);\n", st.bus_vrow[p], i, p);
+                o("    }\n");
+                return;
+            }
+            bool any_edge = false;
+            for (int p = 0; p < 3; ++p) {
+                if (st.edge_irow[p] < 0) continue;
+                any_edge = true;
+                if (islot[st.edge_irow[p]] >= 0) o("      double2 n%d = a%d_%d;\n", p, i, p);
+                else o("      double2 n%d = zero;\n", p);
+                const bool has_load = st.bus_vrow[p] >= 0 && st.load_srow[p] >= 0;
+                const bool has_cap = st.bus_vrow[p] >= 0 && st.cap[p] != 0.0;
+                if (has_load || has_cap) {      // calc_sV (solution.py:177-220) + update_current (:256-288)
+                    o("      {\n"
+                      "        const double m2 = fma(f%d_%d.x, f%d_%d.x, f%d_%d.y * f%d_%d.y);\n"
+                      "        double a, inv;\n"
+                      "        if (EXACT) { a = sqrt(m2); inv = 0.0; } else gp_abs_inv(m2, a, inv);\n"
+                      "        const double a2 = a * a;\n", i, p, i, p, i, p, i, p);
+                    if (has_load) {
+                        if (spu_regs) o("        const double2 l = L%d;\n", st.load_srow[p]);
+                        else o("        const double2 l = LDS_(%d);\n", st.load_srow[p]);
+                        o("        const double f = aPQ + aI * a + aZ * a2;\n"
+                          "        double2 sv = make_double2(l.x * f, l.y * f);\n");
+                    } else {
+                        o("        double2 sv = zero;\n");
+                    }
+                    o("        sv.y -= CAP[%d] * a2;\n", 3 * i + p);
+                    o("        if (EXACT) {\n"
+                      "          if (f%d_%d.x != 0.0 || f%d_%d.y != 0.0) {\n"
+                      "            inv = 1.0 / m2;\n"
+                      "            n%d.x += (sv.x * f%d_%d.x + sv.y * f%d_%d.y) * inv;\n"
+                      "            n%d.y -= (sv.y * f%d_%d.x - sv.x * f%d_%d.y) * inv;\n"
+                      "          }\n"
+                      "        } else {\n"
+                      "          n%d.x += (sv.x * f%d_%d.x + sv.y * f%d_%d.y) * inv;\n"
+                      "          n%d.y -= (sv.y * f%d_%d.x - sv.x * f%d_%d.y) * inv;\n"
+                      "        }\n"
+                      "      }\n", i, p, i, p, p, i, p, i, p, p, i, p, i, p, p, i, p, i, p, p, i, p, i, p);
+                }
+            }
+            if (any_edge) {                     // nan_to_num (:288) acts on non-finite values only
+                o("      {\n        const bool nf = !(0.0");
+                for (int p = 0; p < 3; ++p)
+                    if (st.edge_irow[p] >= 0) o(" + fabs(n%d.x) + fabs(n%d.y)", p, p);
+                o(" <= 1.7976931348623157e308);\n"
+                  "        if (EXACT) {\n"
+                  "          if (nf) {\n");
+                for (int p = 0; p < 3; ++p)
+                    if (st.edge_irow[p] >= 0) o("            n%d = make_double2(gp_n2n(n%d.x), gp_n2n(n%d.y));\n", p, p, p);
+                o("          }\n"
+                  "        } else {\n"
+                  "          bad |= nf;\n"
+                  "        }\n"
+                  "      }\n");
+                for (int p = 0; p < 3; ++p)
+                    if (st.edge_irow[p] >= 0 && iowner[st.edge_irow[p]]) o("      IST(%d, n%d);\n", islot[st.edge_irow[p]], p);
+            }
+            for (int p = 0; p < 3; ++p) {       // the surviving parent rewrites (update_voltage_backward :207-232)
+                if (!win[i][p]) continue;
+                const std::string P = vname(pk, p);
+                o("      %s = f%d_%d;\n", P.c_str(), i, p);
+                for (int q = 0; q < 3; ++q) {
+                    if (st.edge_irow[q] < 0 || islot[st.edge_irow[q]] < 0) continue;
+                    const int zi = 9 * i + 3 * p + q;
+                    o("      if (EXACT) {\n");
+                    o("        %s.x += ZR[%d] * n%d.x - ZI[%d] * n%d.y;\n", P.c_str(), zi, q, zi, q);
+                    o("        %s.y += ZR[%d] * n%d.y + ZI[%d] * n%d.x;\n", P.c_str(), zi, q, zi, q);
+                    o("      } else {\n");
+                    o("        %s.x = fma(-ZI[%d], n%d.y, fma(ZR[%d], n%d.x, %s.x));\n", P.c_str(), zi, q, zi, q, P.c_str());
+                    o("        %s.y = fma(ZI[%d], n%d.x, fma(ZR[%d], n%d.y, %s.y));\n", P.c_str(), zi, q, zi, q, P.c_str());
+                    o("      }\n");
+                }
+            }
+            if (pk >= 0 && (steps[pk].kind & 0xff) != GP_EDGE_VR)       // the parent's current sum (:274-284)
+                for (int p = 0; p < 3; ++p) {
+                    const int r = st.edge_irow[p], rp = steps[pk].edge_irow[p];
+                    if (r < 0 || islot[r] < 0 || rp < 0 || islot[rp] < 0) continue;
+                    o("      a%d_%d.x += n%d.x; a%d_%d.y += n%d.y;\n", pk, p, p, pk, p, p);
+                }
+            for (int p = 0; p < 3; ++p)
+                if (st.bus_vrow[p] >= 0) o("      VST(%d, f%d_%d);\n", st.bus_vrow[p], i, p);
+            o("    }\n");
+        };
+        {
+            const auto& ks = kids[0];
+            for (int j = 0; j < (int)ks.size(); ++j) {
+                const int c = ks[j];
+                DfsLive L;
+                if (size[c] >= 2) L = dfs_live(steps, islot, kids, win, -1, j);
+                std::string back;
+                for (size_t m = 0; m < L.vals.size(); ++m) {
+                    char b[96];
+                    o("    SST(%d, fR%d);\n", (int)m, L.vals[m].second);
+                    snprintf(b, sizeof(b), "      fR%d = SLD(%d);\n", L.vals[m].second, (int)m);
+                    back += b;
+                }
+                emit(c, (int)L.vals.size(), back);
+            }
+        }
+        for (int p = 0; p < 3; ++p) o("    VST(%d, fR%d);\n", k.root_vrow[p], p);
+        o("    double diff = 0.0;\n"
+          "    bool nan = false;\n");
+        for (int p = 0; p < 3; ++p)
+            o("    { const double dx = fR%d.x - KC[%d], dy = fR%d.y - KC[%d];\n"
+              "      const double d = sqrt(fma(dx, dx, dy * dy)); nan |= (d != d); diff = fmax(diff, d); }\n",
+              p, 3 + 2 * p, p, 4 + 2 * p);
+        o("    if (nan) diff = __longlong_as_double(0x7ff8000000000000LL);\n"
+          "    bad_out = bad;\n"
+          "    return diff;\n"
+          "}\n");
+    } else {
     if (spu_regs)       // the loads of the scenario: in flight during the forward sweep
         for (int r = 0; r < n_srows; ++r) o("    const double2 L%d = LDS_(%d);\n", r, r);
     for (int p = 0; p < 3; ++p)
@@ -389,6 +707,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
       "            bad_out = bad;\n"
       "            return diff;\n"
       "}\n");
+    }
     // every I row of the caller's layout from its slot (shared rows are written once per row that carries them)
     o("#define GP_I_ROWS_OUT(dst)");
     for (int r = 0; r < n_irows; ++r)
@@ -456,6 +775,9 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
       "            sp = sd;\n"
       "        }\n"
       "        IPTR const Ip = %s;\n"
+      "#if DFS_MODE\n"
+      "        char* const Vw = V + s * 16;        // every V row goes here once per sweep, when it is final\n"
+      "#endif\n"
       "#if EX_MODE\n"
       "        const char* const gp = gam ? gam + s * 8 : nullptr;\n"
       "        if (warm) {     // the caller's V and I rows hold an earlier solution (solution_fbs.py:76-90)\n"
@@ -464,7 +786,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
       "        } else\n"
       "#endif\n"
       "        {\n"
-      "        for (int r = 0; r < NV; ++r) Vs[r * 32] = zero;           // flat start (solution.py:108-125)\n"
+      "        for (int r = 0; r < NVS; ++r) Vs[r * 32] = zero;          // flat start (solution.py:108-125)\n"
       "        for (int r = 0; r < NIP; ++r) IST(r, zero);\n"
       "        }\n"
       "        int it = 0;\n"
@@ -482,7 +804,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
       "                } else\n"
       "#endif\n"
       "                {\n"
-      "                for (int r = 0; r < NV; ++r) Vs[r * 32] = zero;\n"
+      "                for (int r = 0; r < NVS; ++r) Vs[r * 32] = zero;\n"
       "                for (int r = 0; r < NIP; ++r) IST(r, zero);\n"
       "                }\n"
       "                it = 0;\n"
@@ -506,7 +828,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
       "        }\n"
       "        if (live) {         // final V and I rows: one coalesced 512-byte store per row and warp\n"
       "            char* Vg = V + s * 16;\n"
-      "            if (V) for (int r = 0; r < NV; ++r) *reinterpret_cast<double2*>(Vg + (size_t)r * (size_t)ldb) = Vs[r * 32];\n"
+      "            if (V && !DFS_MODE) for (int r = 0; r < NV; ++r) *reinterpret_cast<double2*>(Vg + (size_t)r * (size_t)ldb) = Vs[r * 32];\n"
       "            // I rows: already in place when they live in the caller's (device) I array; copied out of shared\n"
       "            // memory otherwise; Iout is an optional second destination (mapped host memory in the one-launch path)\n"
       "            if (!IG_MODE && I) { char* Ig = I + s * 16; GP_I_ROWS_OUT(Ig) }\n"
@@ -514,7 +836,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
       "            iters_out[s] = it;\n"
       "            diff_out[s] = diff;\n"
       "            status_out[s] = converged ? %d : ((diff != diff || isinf(diff)) ? %d : %d);\n",
-      ig ? "I + s * 16" : "Vs + NV * 32", GP_ST_CONVERGED, GP_ST_NONFINITE, GP_ST_MAXITER);
+      ig ? "I + s * 16" : "Vs + NVS * 32", GP_ST_CONVERGED, GP_ST_NONFINITE, GP_ST_MAXITER);
     // derived results of gp_fbs_post while the state is still on chip: |V| per V row
     // (calc_Vmag, solution.py:222-224) and loss = sum over real lines of Stx - Srx (:226-233),
     // same operations in the same order as fbs_post_rows_kernel / fbs_post_lines_kernel
@@ -523,7 +845,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
     o("            if (peers.n) {\n"
       "                char* Mg = reinterpret_cast<char*>(Vmag) + s * 8;\n"
       "                for (int r = 0; r < NV; ++r) {\n"
-      "                    const double2 v = Vs[r * 32];\n"
+      "                    const double2 v = VLD(r);\n"
       "                    const double a = sqrt(fma(v.x, v.x, v.y * v.y));\n"
       "                    const size_t off = (size_t)s * 8 + (size_t)r * (size_t)(ldb >> 1);\n"
       "                    if (Vmag) *reinterpret_cast<double*>(Mg + (size_t)r * (size_t)(ldb >> 1)) = a;\n"
@@ -534,7 +856,7 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
       "            } else if (Vmag) {\n"
       "                char* Mg = reinterpret_cast<char*>(Vmag) + s * 8;\n"
       "                for (int r = 0; r < NV; ++r) {\n"
-      "                    const double2 v = Vs[r * 32];\n"
+      "                    const double2 v = VLD(r);\n"
       "                    *reinterpret_cast<double*>(Mg + (size_t)r * (size_t)(ldb >> 1)) = sqrt(fma(v.x, v.x, v.y * v.y));\n"
       "                }\n"
       "            }\n"
@@ -545,9 +867,9 @@ std::string fbs_jit_source(const std::vector<FbsStep>& steps, const std::vector<
             const int ir = lines[9 * l + p], tr = lines[9 * l + 3 + p], rr = lines[9 * l + 6 + p];
             if (ir < 0) continue;
             o("                { const double2 i = %s;", ild(ir).c_str());
-            if (tr >= 0) o(" const double2 vt = Vs[%d];", tr * 32);
+            if (tr >= 0) o(" const double2 vt = VLD(%d);", tr);
             else o(" const double2 vt = zero;");
-            if (rr >= 0) o(" const double2 vr = Vs[%d];", rr * 32);
+            if (rr >= 0) o(" const double2 vr = VLD(%d);", rr);
             else o(" const double2 vr = zero;");
             o("\n                  const double2 st = make_double2(vt.x * i.x + vt.y * i.y, vt.y * i.x - vt.x * i.y);\n"
               "                  const double2 sr = make_double2(vr.x * i.x + vr.y * i.y, vr.y * i.x - vr.x * i.y);\n"

@@ -539,3 +539,43 @@ def test_tree_walk_kernel_matches_oracle_and_two_sweep_kernel(feeder):
     finally:
         _cabi.gp_set_option(b'fbs_kernel', 0)
         _cabi.gp_set_option(b'fbs_walk_blocks', 4)
+
+
+@pytest.mark.parametrize('feeder', ['IEEE_34_Bus_allwye_noxfm_noreg', 'IEEE_37_Bus_allwye', 'IEEE_13_Bus_allwye', 'IEEE_34_Bus_allwye'])
+def test_depth_first_build_of_the_specialised_kernel(feeder):
+    """jit_dfs = 1: the specialised kernel walks the tree depth-first with the V rows in the caller's array and only the
+    I slots and a small stack in shared memory (more warps per SM on the 34- / 37-bus class).  Same iteration counts and
+    status as the streaming kernel, V / I / |V| / losses within 1e-12, through the device entry point (ragged batch, two
+    launches in a row) and the host entry point (which stages through device memory for this build); diverging
+    scenarios take the exact restart path."""
+    import torch
+    from gigpower_b200 import _cabi
+    S = 2500 + 13
+    rng = np.random.Generator(np.random.PCG64(41))
+    try:
+        _cabi.check(_cabi.gp_set_option(b'jit_dfs', 1))
+        s = _fbs(feeder)
+        mult = rng.uniform(0.5, 1.4, size=(S, s.circuit.loads.num_elements))
+        mult[7] = 9.0       # overloaded
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 3))
+        ref = s.solve_batch(load_mult=mult, outputs=('V', 'I', 'Vmag', 'loss'))
+        _cabi.check(_cabi.gp_set_option(b'fbs_kernel', 0))
+        assert s.specialise() and _cabi.gp_fbs_active_kernel(s._feeder.handle) == 5
+        ok = ref.status == 0
+        assert ok.sum() >= S - 2
+        for _ in range(2):
+            r = s.solve_batch(load_mult=mult, outputs=('V', 'I', 'Vmag', 'loss'))
+            assert np.array_equal(r.iterations, ref.iterations) and np.array_equal(r.status, ref.status)
+            assert rel_err(r.V[ok], ref.V[ok]) <= 1e-12 and rel_err(r.I[ok], ref.I[ok]) <= 1e-12
+            assert rel_err(r.Vmag[ok], ref.Vmag[ok]) <= 1e-12 and rel_err(r.losses[ok], ref.losses[ok]) <= 1e-12
+        rows = np.ascontiguousarray(s.load_weights() @ mult.T)
+        t = s.tables
+        spu_h = torch.from_numpy(rows).pin_memory()
+        V = torch.empty((t.n_vrows, S), dtype=torch.complex128).pin_memory()
+        I = torch.empty((t.n_irows, S), dtype=torch.complex128).pin_memory()
+        it, st, df = s.solve_batch_host(spu_h, V, I)
+        assert np.array_equal(it, ref.iterations)
+        assert np.array_equal(V.numpy()[:, ok], np.asarray(r.V_rows)[:, ok]) and np.array_equal(I.numpy()[:, ok], np.asarray(r.I_rows)[:, ok])
+    finally:
+        _cabi.gp_set_option(b'jit_dfs', -1)
+        _cabi.gp_set_option(b'fbs_kernel', 0)

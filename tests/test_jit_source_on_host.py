@@ -258,3 +258,96 @@ def test_generated_sweep_with_per_scenario_taps_matches_the_oracle(feeder, tmp_p
     assert list(its) == list(want['iterations'])
     bb, pp = np.nonzero(t.vrow >= 0)
     assert np.abs(Vr[t.vrow[bb, pp]].T - want['V'][:, bb, pp]).max() <= 1e-9
+
+
+MAIN_DFS = r'''
+int main(int argc, char** argv) {
+    // argv: S tol maxiter in.bin out.bin ; the depth-first build: V rows live in the caller's array
+    const long S = atol(argv[1]); const double tol = atof(argv[2]); const int maxiter = atoi(argv[3]);
+    std::vector<double2> spu((size_t)(NS > 0 ? NS : 1) * S), V((size_t)NV * S), I((size_t)(NI > 0 ? NI : 1) * S);
+    std::vector<double> its(S);
+    FILE* f = fopen(argv[4], "rb"); if (!f) return 2;
+    if (NS > 0 && fread(spu.data(), 16, (size_t)NS * S, f) != (size_t)NS * S) return 3;
+    fclose(f);
+    const unsigned ldb = (unsigned)(S * 16);
+    const double2 zero = make_double2(0.0, 0.0);
+    for (long s = 0; s < S; ++s) {
+        std::vector<double2> sm((size_t)SROWS * 32 + 32, zero);
+        double2* const Vs = sm.data();
+        IPTR const Ip = Vs + NVS * 32;
+        char* const Vw = reinterpret_cast<char*>(V.data() + s);
+        const char* sp = reinterpret_cast<const char*>(spu.data() + s);
+        for (int r = 0; r < NIP; ++r) IST(r, zero);
+        int it = 0; double diff = -1.0; bool converged = false, exact = false;
+        while (!converged && it < maxiter) {
+            bool bad = false;
+            if (exact) diff = gp_sweep<true>(Vs, Ip, sp, ldb, bad, Vw);
+            else diff = gp_sweep<false>(Vs, Ip, sp, ldb, bad, Vw);
+            if (bad) {
+                for (int r = 0; r < NIP; ++r) IST(r, zero);
+                it = 0; exact = true; continue;
+            }
+            ++it; converged = diff <= tol;
+        }
+        char* Ig = reinterpret_cast<char*>(I.data() + s);
+        GP_I_ROWS_OUT(Ig)
+        its[s] = it;
+    }
+    f = fopen(argv[5], "wb"); if (!f) return 4;
+    fwrite(V.data(), 16, (size_t)NV * S, f);
+    fwrite(I.data(), 16, (size_t)(NI > 0 ? NI : 1) * S, f);
+    fwrite(its.data(), 8, S, f);
+    fclose(f);
+    return 0;
+}
+'''
+
+
+@pytest.mark.parametrize('feeder', ALL_FEEDERS)
+def test_generated_depth_first_sweep_run_on_the_host_matches_the_oracle(feeder, tmp_path):
+    """The depth-first build of the specialised kernel (gp_fbs_jit_source mode + 4: V rows in the caller's array, I slots
+    and a small stack in shared memory, a bus's forward step on the way down and its backward step on the way up):
+    compiled for the host and run scenario by scenario against the oracle - V, I, iteration counts - incl. scenarios
+    that take the exact restart path."""
+    from gigpower_b200 import _cabi
+    from gigpower_b200.circuit import Circuit
+    from gigpower_b200.flatten import flatten_fbs
+    from oracle.gp_oracle import FBSOracle
+    model = load_model(feeder)
+    t = flatten_fbs(Circuit(model))
+    d, keep = _cabi.make_fbs_desc(t)
+    n = _cabi.gp_fbs_jit_source(C.byref(d), 2, 4, None, 0)
+    assert n > 0
+    buf = C.create_string_buffer(n + 1)
+    assert _cabi.gp_fbs_jit_source(C.byref(d), 2, 4, buf, n + 1) == n
+    src = buf.value.decode()
+    defs = dict(ln.split()[1:3] for ln in src.splitlines() if ln.startswith('#define N') or ln.startswith('#define DFS'))
+    assert defs['DFS_MODE'] == '1' and defs['NVS'] == '0' and 0 < int(defs['NST']) <= 24
+    prog = host_program(src)
+    prog = prog[:prog.index('int main(')] + MAIN_DFS
+    cpp, exe = tmp_path / 'sweep_dfs.cpp', tmp_path / 'sweep_dfs'
+    cpp.write_text(prog)
+    subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-w', '-o', str(exe), str(cpp)], check=True)
+    o = FBSOracle(model, ZIPS['test_zip'])
+    rng = np.random.Generator(np.random.PCG64(98))
+    S = 12
+    mult = rng.uniform(0.4, 1.6, size=(S, len(o.c.load_names)))
+    mult[0] = 1.0
+    spu = o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult)
+    want = o.solve(spu)
+    b, p = np.nonzero(t.srow >= 0)
+    rows = np.zeros((max(t.n_srows, 1), S), dtype=complex)
+    rows[t.srow[b, p]] = spu[:, b, p].T
+    fin, fout = tmp_path / 'in.bin', tmp_path / 'out.bin'
+    rows[:t.n_srows].astype(np.complex128).tofile(fin)
+    subprocess.run([str(exe), str(S), repr(float(t.tolerance)), '100', str(fin), str(fout)], check=True)
+    raw = np.fromfile(fout, dtype=np.float64)
+    nv, ni = t.n_vrows, max(t.n_irows, 1)
+    Vr = raw[:2 * nv * S].view(np.complex128).reshape(nv, S)
+    Ir = raw[2 * nv * S:2 * (nv + ni) * S].view(np.complex128).reshape(ni, S)
+    its = raw[2 * (nv + ni) * S:].astype(int)
+    assert list(its) == list(want['iterations'])
+    bb, pp = np.nonzero(t.vrow >= 0)
+    assert np.abs(Vr[t.vrow[bb, pp]].T - want['V'][:, bb, pp]).max() <= 1e-9
+    ll, qq = np.nonzero(t.irow >= 0)
+    assert np.abs(Ir[t.irow[ll, qq]].T - want['I'][:, ll, qq]).max() <= 1e-9
