@@ -1813,7 +1813,9 @@ extern "C" int64_t gp_fbs_jit_source(const GpFbsDesc* d, int32_t warps, int32_t 
         }
     const std::string src = fbs_jit_source(steps, child4, lines, k, d->n_vrows, d->n_irows, d->n_srows, warps,
                                            (i_global & 1) != 0, false, (i_global & 2) != 0, (i_global & 4) != 0);
-    if (src.empty()) return fail(GP_EJIT, "gp_fbs_jit_source: non-finite impedance in the descriptor");
+    if (src.empty())
+        return fail(GP_EJIT, "gp_fbs_jit_source: non-finite impedance in the descriptor, or a depth-first build (mode 4) "
+                             "combined with mode 1 / 2 or asked of a feeder with more than 64 steps");
     if (buf && cap > 0) {
         const size_t n = std::min((size_t)cap - 1, src.size());
         memcpy(buf, src.data(), n);
@@ -2780,7 +2782,7 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
     // download overlap inside one launch and there is nothing to chunk.
     // (a handle whose device kernel is the depth-first build writes its V rows every sweep, which must not cross
     // PCIe: its host path runs the two-sweep build, compiled here on first use, when that build fits at all)
-    if (im->jit_kernel && (!im->jit_dfs || (im->jit_alt_warps >= 1 && !im->jit_alt_ig)) && maxiter >= 1 &&
+    if (im->jit_kernel && (!im->jit_dfs || im->jit_alt_warps >= 1) && maxiter >= 1 &&
         g_host_zero_copy && (g_fbs_kernel == 0 || g_fbs_kernel == 5) &&
         ld * 16 < ((int64_t)1 << 32)) {
         const void* hp[] = {spu_h, V_h, I_h, Vmag_h, loss_h, iters_h, status_h, diff_h};
@@ -2798,8 +2800,9 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
             }
         }
         if (ok) {
+            const bool host_ig = im->jit_dfs ? im->jit_alt_ig : im->jit_ig;     // I rows of the host path's build
             const size_t b_stage = ((size_t)im->n_srows * (size_t)ld * 16 + 255) & ~(size_t)255;
-            const size_t need_stage = b_stage + (im->jit_ig ? (size_t)im->n_irows * (size_t)ld * 16 : 0) + 256;
+            const size_t need_stage = b_stage + (host_ig ? (size_t)im->n_irows * (size_t)ld * 16 : 0) + 256;
             if (need_stage > im->zc_bytes) {
                 if (im->d_zc) cudaFree(im->d_zc);
                 im->d_zc = nullptr;
@@ -2822,18 +2825,18 @@ extern "C" int gp_fbs_solve_batch_host(GpFeeder* f, int64_t S, int64_t ld, const
             if (!im->jit_host_tried && ((im->n_srows <= 32 && g_host_read_ahead) || im->jit_dfs)) {
                 im->jit_host_tried = true;
                 im->jit_warps_host = want_host_warps;
-                if (fbs_jit_build(f, im->jit_warps_host, im->jit_dfs ? false : im->jit_ig, g_host_read_ahead != 0, &im->jit_module_host,
+                if (fbs_jit_build(f, im->jit_warps_host, host_ig, g_host_read_ahead != 0, &im->jit_module_host,
                                   &im->jit_kernel_host) != GP_OK)
                     im->jit_module_host = im->jit_kernel_host = nullptr;
             }
             if (im->jit_dfs && !im->jit_kernel_host) goto staged;       // no two-sweep build: copy - solve - copy
             // I rows kept in global memory must stay on the device; the host copy is a second destination
-            double* I_state = im->jit_ig ? (double*)((char*)im->d_zc + b_stage) : (double*)dp[2];
+            double* I_state = host_ig ? (double*)((char*)im->d_zc + b_stage) : (double*)dp[2];
             rc = fbs_jit_launch(im, S, ld, (const double*)dp[0], (double*)dp[1], I_state, (int32_t*)dp[5],
                                 (int32_t*)dp[6], (double*)dp[7], tol, maxiter, im->streams[0], (double*)dp[3],
-                                (double*)dp[4], im->d_zc, im->jit_ig ? (double*)dp[2] : nullptr, nullptr,
+                                (double*)dp[4], im->d_zc, host_ig ? (double*)dp[2] : nullptr, nullptr,
                                 (g_host_read_ahead || im->jit_dfs) ? im->jit_kernel_host : nullptr, im->jit_warps_host,
-                                nullptr, 0, im->n_vrows + im->n_islots);
+                                nullptr, 0, im->n_vrows + (host_ig ? 0 : im->n_islots));
             if (rc) return rc;
             count_launch();
             GP_CUDA(cudaStreamSynchronize(im->streams[0]));

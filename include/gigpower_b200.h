@@ -135,6 +135,13 @@ int64_t gp_launch_count(void);
  *   made, i.e. at the first gp_fbs_solve_batch_host call of a handle).  The host path is PCIe-bound and a smaller
  *   wave of warps shortens the part of a call in which only one PCIe direction is busy.
  * "host_chunks": number of pipeline chunks of gp_fbs_solve_batch_host (0 = automatic).
+ * "jit_dfs": depth-first build of the feeder-specialised kernel - the tree is walked in the "fbs_order" order as nested
+ *   straight-line code, a bus's forward voltage and accumulated current travel in registers between its descend
+ *   and ascend, and the V rows live in the caller's V array (L2) instead of shared memory, which then holds only
+ *   the I slots and a small stack: -1 (default) = automatic, when that at least doubles the warps per SM of the
+ *   two-sweep build (34- and 37-bus class; not the 13-bus class); 0 = never; 1 = whenever the feeder has at
+ *   most 64 steps.  Read by gp_fbs_create.  gp_fbs_solve_batch_host on such a handle runs a two-sweep build in its
+ *   one-launch path (V rows must not cross PCIe once per sweep).
  * "host_read_ahead": 1 (default) = the one-launch host path uses its own build of the specialised kernel
  *   in which a warp issues the PCIe reads of its next tile before the stores of the tile it has solved
  *   (upload and download then overlap instead of alternating); 0 = the device-path kernel.
@@ -162,7 +169,9 @@ int gp_fbs_onchip_warps(GpFeeder* f);
  *   gp_fbs_jit_source     host only: the CUDA source for a descriptor and `warps` warps per
  *                         block, with the I rows in shared memory (i_global = 0) or in global
  *                         memory (1); + 2 = the build with per-scenario regulator ratios and warm starts
- *                         that gp_fbs_solve_batch_ex launches on a specialised feeder;
+ *                         that gp_fbs_solve_batch_ex launches on a specialised feeder; + 4 = the
+ *                         depth-first build ("jit_dfs"; GP_EJIT when combined with 1 or 2 or asked of a
+ *                         feeder with more than 64 steps);
  *                         returns its length (excluding the NUL) or a negative GP_E*;
  *                         copies at most cap-1 characters into buf when buf is not NULL
  *   gp_fbs_jit_warps      warps per block gp_fbs_specialise uses for this handle (0 = the feeder

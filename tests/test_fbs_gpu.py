@@ -546,7 +546,7 @@ def test_depth_first_build_of_the_specialised_kernel(feeder):
     """jit_dfs = 1: the specialised kernel walks the tree depth-first with the V rows in the caller's array and only the
     I slots and a small stack in shared memory (more warps per SM on the 34- / 37-bus class).  Same iteration counts and
     status as the streaming kernel, V / I / |V| / losses within 1e-12, through the device entry point (ragged batch, two
-    launches in a row) and the host entry point (which stages through device memory for this build); diverging
+    launches in a row) and the host entry point (one launch of the two-sweep build; staged when zero copy is off); diverging
     scenarios take the exact restart path."""
     import torch
     from gigpower_b200 import _cabi
@@ -573,9 +573,18 @@ def test_depth_first_build_of_the_specialised_kernel(feeder):
         spu_h = torch.from_numpy(rows).pin_memory()
         V = torch.empty((t.n_vrows, S), dtype=torch.complex128).pin_memory()
         I = torch.empty((t.n_irows, S), dtype=torch.complex128).pin_memory()
+        n0 = _cabi.gp_launch_count()
         it, st, df = s.solve_batch_host(spu_h, V, I)
-        assert np.array_equal(it, ref.iterations)
-        assert np.array_equal(V.numpy()[:, ok], np.asarray(r.V_rows)[:, ok]) and np.array_equal(I.numpy()[:, ok], np.asarray(r.I_rows)[:, ok])
+        assert _cabi.gp_launch_count() - n0 == 1        # one launch: the two-sweep build, compiled for the host path
+        assert np.array_equal(it, ref.iterations) and np.array_equal(st, ref.status)
+        assert rel_err(V.numpy()[:, ok], np.asarray(r.V_rows)[:, ok]) <= 1e-12
+        assert rel_err(I.numpy()[:, ok], np.asarray(r.I_rows)[:, ok]) <= 1e-12
+        # the staged path (copy - solve with the depth-first build - copy) gives the device path's numbers exactly
+        _cabi.check(_cabi.gp_set_option(b'host_zero_copy', 0))
+        V2 = torch.empty((t.n_vrows, S), dtype=torch.complex128).pin_memory()
+        it2, _, _ = s.solve_batch_host(spu_h, V2)
+        assert np.array_equal(it2, ref.iterations) and np.array_equal(V2.numpy()[:, ok], np.asarray(r.V_rows)[:, ok])
     finally:
+        _cabi.gp_set_option(b'host_zero_copy', 1)
         _cabi.gp_set_option(b'jit_dfs', -1)
         _cabi.gp_set_option(b'fbs_kernel', 0)
