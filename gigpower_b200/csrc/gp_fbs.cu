@@ -2533,20 +2533,22 @@ static int fbs_solve_launch(GpFeeder* f, int64_t S, int64_t ld, const double* sp
     // warps per SM - and runs only on request.)
     const bool onchip = g_fbs_kernel == 4;
     // (the specialised kernel always runs at least one sweep: maxiter < 1 goes to the table-driven ones)
-    if (extras && !wpu && !vv && im->jit_kernel && !im->jit_ig && !im->jit_dfs && maxiter >= 1 &&
-        (g_fbs_kernel == 0 || g_fbs_kernel == 5)) {
+    // (a handle whose plain kernel is the depth-first build takes the two-sweep plan saved at create for this build)
+    const bool ex_fits = im->jit_kernel && (im->jit_dfs ? (im->jit_alt_warps >= 1 && !im->jit_alt_ig) : !im->jit_ig);
+    const int ex_warps = im->jit_dfs ? im->jit_alt_warps : im->jit_warps;
+    if (extras && !wpu && !vv && ex_fits && maxiter >= 1 && (g_fbs_kernel == 0 || g_fbs_kernel == 5)) {
         // per-scenario ratios / warm start on a specialised feeder: the EX build of the specialised kernel
         // (built on first use; a failed build leaves the streaming kernel's EX instance below)
         if (!im->jit_ex_tried) {
             im->jit_ex_tried = true;
-            if (fbs_jit_build(f, im->jit_warps, false, false, &im->jit_module_ex, &im->jit_kernel_ex, true) != GP_OK)
+            if (fbs_jit_build(f, ex_warps, false, false, &im->jit_module_ex, &im->jit_kernel_ex, true) != GP_OK)
                 im->jit_module_ex = im->jit_kernel_ex = nullptr;
         }
     }
-    if (extras && !wpu && !vv && im->jit_kernel_ex && !im->jit_ig && !im->jit_dfs && maxiter >= 1 &&
+    if (extras && !wpu && !vv && im->jit_kernel_ex && ex_fits && maxiter >= 1 &&
         (g_fbs_kernel == 0 || g_fbs_kernel == 5)) {
         rc = fbs_jit_launch(im, S, ld, spu, V, I, iters, status, diff, tol, maxiter, st, Vmag, loss, nullptr, nullptr,
-                            &pd, im->jit_kernel_ex, im->jit_warps, gam, warm);
+                            &pd, im->jit_kernel_ex, ex_warps, gam, warm, im->n_vrows + im->n_islots);
         if (rc) return rc;
         *fused = true;
     } else if (extras) {
