@@ -121,10 +121,12 @@ int64_t gp_launch_count(void);
  * "fbs_share_rows": 1 (default) = in the streaming FBS kernel an I row that only repeats a child's current (a
  *   bus-phase without load and capacitor fed by one child edge) or stays zero makes no HBM round trips during
  *   the sweeps and is filled in once at the end; 0 = every row is stored and re-read each sweep.  Same results.
- * "fbs_kernel" 6 / automatic for feeders without a specialised kernel: the tree-walk kernel - the depth-first
+ * "fbs_kernel" 6 (on request, see "fbs_auto_walk"): the tree-walk kernel - the depth-first
  *   order below with the state of the bus the walk stands on held in registers and next-event operands requested
  *   ahead; "fbs_walk_blocks" (4, 5, 6, 8) = resident 128-thread blocks per SM it is compiled for (128 / 96 / 80 /
  *   64 registers per thread).  Per-scenario extras (taps, warm start, wpu) run on the two-sweep kernel.
+ *   "fbs_auto_walk": 0 (default) = the automatic choice never takes the tree-walk kernel (it measured slower than the
+ *   two-sweep kernel on B200); 1 = it does for feeders the walk covers.
  * "fbs_order": 1 (default) = the streaming FBS kernel runs a bus's forward step when a depth-first walk of the
  *   tree descends its edge and its backward step when the walk comes back up (children latest in topo order
  *   first); 0 = two full sweeps as the reference writes them (solution_fbs.py:92-121).  Same steps, same rows,
@@ -135,6 +137,8 @@ int64_t gp_launch_count(void);
  *   made, i.e. at the first gp_fbs_solve_batch_host call of a handle).  The host path is PCIe-bound and a smaller
  *   wave of warps shortens the part of a call in which only one PCIe direction is busy.
  * "host_chunks": number of pipeline chunks of gp_fbs_solve_batch_host (0 = automatic).
+ * "host_zero_copy": 1 (default) = with pinned (device-mapped) host buffers and a specialised feeder,
+ *   gp_fbs_solve_batch_host is ONE launch that reads and writes the host buffers itself; 0 = always copy - solve - copy.
  * "jit_dfs": depth-first build of the feeder-specialised kernel - the tree is walked in the "fbs_order" order as nested
  *   straight-line code, a bus's forward voltage and accumulated current travel in registers between its descend
  *   and ascend, and the V rows live in the caller's V array (L2) instead of shared memory, which then holds only
