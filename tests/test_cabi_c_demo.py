@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import REPO, ZIPS, feeder_path, load_model, rel_err
+from helpers import REPO, ZIPS, feeder_path, rel_err
 
 FEEDER, S = 'IEEE_13_Bus_allwye', 5
 

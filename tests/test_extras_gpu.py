@@ -367,7 +367,7 @@ def test_volt_var_study_runs_on_nr3_too():
     every round is held to the tree oracle given the same wpu, and the injections move the controlled voltages
     towards the dead band."""
     from oracle.nr3_tree import NR3TreeOracle
-    from gigpower_b200.study import VoltVarStudy, volt_var_q
+    from gigpower_b200.study import VoltVarStudy
     feeder, S, rounds = 'IEEE_13_Bus_allwye_noxfm_noreg', 64, 3
     rng = np.random.Generator(np.random.PCG64(62))
     o = NR3TreeOracle(load_model(feeder), ZIPS['test_zip'])

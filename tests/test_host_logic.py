@@ -8,7 +8,7 @@ import pytest
 
 from gigpower_b200.circuit import Circuit
 from gigpower_b200.flatten import flatten_fbs, topo_sort
-from oracle.gp_oracle import OracleCircuit, FBSOracle
+from oracle.gp_oracle import OracleCircuit
 from helpers import ALL_FEEDERS, LINES_ONLY, ZIPS, REPO, load_model, snapshots
 
 

@@ -6,7 +6,6 @@ generator's schedule, row offsets, constants and the shared I slots (fbs_jit_isl
 the GPU tests then check the same source as compiled by NVRTC.  Test infrastructure only: nothing
 in the product runs on the host."""
 import ctypes as C
-import os
 import subprocess
 
 import numpy as np
