@@ -948,7 +948,8 @@ def run_workload(ctx, args, name, steps, main):
         n_it = float(its.sum())
         kernel_names = {1: 'fbs_dfs_kernel', 2: 'fbs_phase_kernel', 3: 'fbs_solve_kernel', 4: 'fbs_onchip_kernel',
                         5: 'gp_fbs_jit_kernel', 6: 'fbs_walk_kernel'}
-        variant = {0: None, 1: 'fused-dfs', 2: 'phase-parallel', 3: 'two-sweep streaming (state in HBM)',
+        variant = {0: None, 1: 'fused-dfs', 2: 'phase-parallel', 3: 'streaming (state in HBM), forward and backward steps of the two sweeps '
+                      + ('in depth-first order' if args.fbs_order else 'as two full sweeps'),
                    4: 'on-chip two-sweep (state in shared memory), table-driven',
                    5: 'on-chip, feeder-specialised (NVRTC): two sweeps with V and I in shared memory, or depth-first with I '
                       'in shared memory and V in the caller\'s array',
