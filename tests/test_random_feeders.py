@@ -1,0 +1,175 @@
+"""Sixteen seeded RANDOM radial feeders (oracle/make_golden_random.py): random tree shapes, 1- / 2- / 3-phase laterals
+(some declared in reverse phase order), four kinds of line definition, 1- / 2- / 3-phase loads, capacitors, per-phase
+regulators with random taps and a 4.16 / 0.48 kV transformer on some.  The golden vectors are the UNMODIFIED
+reference's own ``SolutionFBS`` / ``SolutionNR3`` results on them (tests/golden/ref_random.npz), so every check here
+is against the reference, not against the oracle:
+
+* the oracles (FBS; NR3 dense and tree elimination) - pins them on topologies nobody hand-picked;
+* the streaming kernel's loop run in NumPy over the library's own schedule (``gp_fbs_schedule``), both step orders,
+  and the tree-walk kernel's loop over ``gp_fbs_walk_events``;
+* the GENERATED sweeps of the feeder-specialised kernel (two-sweep with I slots in shared or global memory, and the
+  depth-first build), compiled for the host.
+
+No GPU needed; the GPU counterpart is tests/test_random_feeders_gpu.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, ZIPS
+from gigpower_b200.dss_reader import read_dss
+
+RANDOM = [f'rnd{i:02d}' for i in range(16)]
+HOST_COMPILED = RANDOM
+TOL = 1e-12
+_cache = {}
+
+
+def gold():
+    if 'g' not in _cache:
+        _cache['g'] = np.load(os.path.join(GOLDEN, 'ref_random.npz'))
+    return _cache['g']
+
+
+def rmodel(name):
+    return read_dss(os.path.join(GOLDEN, 'random_feeders', name + '.json'))
+
+
+def _tables(name):
+    from gigpower_b200.circuit import Circuit
+    from gigpower_b200.flatten import flatten_fbs
+    from gigpower_b200.solution import Solution
+    Solution.set_zip_values(np.asarray(ZIPS['test_zip']))
+    model = rmodel(name)
+    return model, flatten_fbs(Circuit(model))
+
+
+def _packed(t, o, mult):
+    spu = o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult)
+    b, p = np.nonzero(t.srow >= 0)
+    rows = np.zeros((max(t.n_srows, 1), len(mult)), dtype=complex)
+    rows[t.srow[b, p]] = spu[:, b, p].T
+    return rows
+
+
+def _check_rows(t, V, I, its, name, tol=TOL, i_rows=None):
+    g = gold()
+    assert list(its) == list(g[name + '/FBS/iterations'])
+    bb, pp = np.nonzero(t.vrow >= 0)
+    assert np.abs(V[t.vrow[bb, pp]].T - g[name + '/FBS/V'][:, bb, pp]).max() <= tol
+    ll, qq = np.nonzero(t.irow >= 0)
+    if i_rows is not None:
+        keep = np.array([int(t.irow[l, q]) in i_rows for l, q in zip(ll, qq)])
+        ll, qq = ll[keep], qq[keep]
+    assert np.abs(I[t.irow[ll, qq]].T - g[name + '/FBS/I'][:, ll, qq]).max() <= tol
+
+
+def test_the_random_set_covers_what_it_claims():
+    """Reverse-declared two-phase lines, every line kind, multi-phase loads, regulators, a transformer, and a bus
+    whose phases are rewritten by several children all occur."""
+    n_rev = n_sw = n_2ph_load = n_3ph_load = n_reg = n_xfm = n_multi_child = 0
+    for name in RANDOM:
+        m = rmodel(name)
+        for ln in m.lines:
+            ph = [int(x) for x in ln.bus1.split('.')[1:]]
+            n_rev += ph != sorted(ph)
+            n_sw += bool(ln.is_switch)
+        n_2ph_load += sum(ld.nphases == 2 for ld in m.loads)
+        n_3ph_load += sum(ld.nphases == 3 for ld in m.loads)
+        n_reg += len(m.regcontrols)
+        n_xfm += sum(t.nphases == 3 for t in m.transformers)
+        parents = [ln.bus1.split('.')[0] for ln in m.lines]
+        n_multi_child += sum(parents.count(b) >= 3 for b in set(parents))
+        assert bool(gold()[name + '/FBS/converged'].all())
+    assert n_rev >= 3 and n_sw >= 1 and n_2ph_load >= 5 and n_3ph_load >= 5 and n_reg >= 10 and n_xfm >= 2
+    assert n_multi_child >= 5
+
+
+@pytest.mark.parametrize('name', RANDOM)
+def test_fbs_oracle_matches_the_reference(name):
+    from oracle.gp_oracle import FBSOracle
+    g = gold()
+    o = FBSOracle(rmodel(name), ZIPS['test_zip'])
+    mult = g[name + '/mult']
+    r = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+    assert list(r['iterations']) == list(g[name + '/FBS/iterations'])
+    for p in ('V', 'I', 'sV', 'Stx', 'Srx'):
+        assert np.abs(r[p] - g[f'{name}/FBS/{p}']).max() <= TOL, p
+    assert list(o.topo_order) == list(g[name + "/FBS/topo_order"])
+
+
+@pytest.mark.parametrize('name', [n for n in RANDOM if int(n[3:]) in (0, 1, 2, 3, 4, 5, 6, 7, 12, 13, 14)])
+def test_nr3_oracles_match_the_reference(name):
+    from oracle.gp_oracle import NR3Oracle
+    from oracle.nr3_tree import NR3TreeOracle
+    g = gold()
+    model = rmodel(name)
+    X = g[name + '/NR3/XNR']
+    mult = g[name + '/mult'][:len(X)]
+    for cls in (NR3Oracle, NR3TreeOracle):
+        o = cls(model, ZIPS['test_zip'])
+        r = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult))
+        assert list(r['iterations']) == list(g[name + '/NR3/iterations']), cls.__name__
+        assert np.abs(r['XNR'] - X).max() <= 1e-11, cls.__name__
+
+
+@pytest.mark.parametrize('order', ['dfs', 'sweeps'])
+@pytest.mark.parametrize('name', RANDOM)
+def test_streaming_kernel_loop_over_the_library_schedule_matches_the_reference(name, order):
+    from oracle.gp_oracle import FBSOracle
+    from test_fbs_order_host import _schedule, emulate
+    model, t = _tables(name)
+    events, kind = _schedule(t)
+    o = FBSOracle(model, ZIPS['test_zip'])
+    V, I, its = emulate(t, _packed(t, o, gold()[name + '/mult']), events, kind, order)
+    _check_rows(t, V, I, its, name)
+
+
+@pytest.mark.parametrize('name', RANDOM)
+def test_tree_walk_loop_over_the_library_events_matches_the_reference(name):
+    from oracle.gp_oracle import FBSOracle
+    from test_fbs_walk_host import _events, emulate_walk
+    model, t = _tables(name)
+    ev = _events(t)
+    if len(ev) == 0:
+        pytest.skip('feeder has V rows below a regulator that no forward step writes: two-sweep kernel')
+    o = FBSOracle(model, ZIPS['test_zip'])
+    V, I, its = emulate_walk(t, _packed(t, o, gold()[name + '/mult']), ev)
+    stored = {int(e[2 + q]) for e in ev for q in range(3) if (e[1] >> (6 + q)) & 1}
+    _check_rows(t, V, I, its, name, i_rows=stored)
+
+
+@pytest.mark.parametrize('mode', [0, 1, 4])
+@pytest.mark.parametrize('name', HOST_COMPILED)
+def test_generated_sweeps_compiled_for_the_host_match_the_reference(name, mode, tmp_path):
+    """mode: gp_fbs_jit_source's - 0 two sweeps with the I slots in shared memory, 1 I rows in global memory,
+    4 the depth-first build."""
+    from gigpower_b200 import _cabi
+    from oracle.gp_oracle import FBSOracle
+    from test_jit_source_on_host import MAIN_DFS, host_program
+    model, t = _tables(name)
+    d, keep = _cabi.make_fbs_desc(t)
+    n = _cabi.gp_fbs_jit_source(C.byref(d), 2, mode, None, 0)
+    assert n > 0
+    buf = C.create_string_buffer(n + 1)
+    assert _cabi.gp_fbs_jit_source(C.byref(d), 2, mode, buf, n + 1) == n
+    prog = host_program(buf.value.decode())
+    if mode == 4:
+        prog = prog[:prog.index('int main(')] + MAIN_DFS
+    cpp, exe = tmp_path / 'sweep.cpp', tmp_path / 'sweep'
+    cpp.write_text(prog)
+    subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-w', '-o', str(exe), str(cpp)], check=True)
+    o = FBSOracle(model, ZIPS['test_zip'])
+    rows = _packed(t, o, gold()[name + '/mult'])
+    S = rows.shape[1]
+    fin, fout = tmp_path / 'in.bin', tmp_path / 'out.bin'
+    rows[:t.n_srows].astype(np.complex128).tofile(fin)
+    subprocess.run([str(exe), str(S), repr(float(t.tolerance)), '100', str(fin), str(fout)], check=True)
+    raw = np.fromfile(fout, dtype=np.float64)
+    nv, ni = t.n_vrows, max(t.n_irows, 1)
+    Vr = raw[:2 * nv * S].view(np.complex128).reshape(nv, S)
+    Ir = raw[2 * nv * S:2 * (nv + ni) * S].view(np.complex128).reshape(ni, S)
+    its = raw[2 * (nv + ni) * S:].astype(int)
+    _check_rows(t, Vr, Ir, its, name, tol=1e-9)
