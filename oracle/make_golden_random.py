@@ -211,6 +211,114 @@ def main():
         print(msg, flush=True)
     np.savez_compressed(os.path.join(mg.OUT, 'ref_random.npz'), **res)
     print('wrote', os.path.join(mg.OUT, 'ref_random.npz'))
+    extras(tmp)
+
+
+TAP_CASES = {'rnd03': 3, 'rnd06': 3, 'rnd08': 0, 'rnd11': 0, 'rnd13': 3}      # feeder: NR3 scenarios (FBS: 5 each)
+WARM_CASES = {'rnd02': (4, 3), 'rnd03': (4, 3), 'rnd05': (4, 3), 'rnd10': (4, 0)}   # feeder: (FBS steps, NR3 steps)
+WPU_CASES = ['rnd04', 'rnd13', 'rnd09']
+
+
+def extras(tmp):
+    """The per-scenario inputs of SURVEY.md section 8(f)-2, -3 on the random feeders, each as the reference defines it:
+    taps = one reference object per scenario built with that scenario's taps (oracle/make_golden_taps.py), warm start =
+    one reference object driven through a load sequence (make_golden_warm.py), wpu = reference objects whose ``wpu``
+    attribute is set (make_golden_wpu.py).  -> tests/golden/ref_random_extras.npz"""
+    from make_golden_warm import set_loads
+    z = mg.ZIPS['test_zip']
+    out = {}
+    for name, n_nr3 in TAP_CASES.items():
+        seed = FEEDERS[name][0]
+        fp = os.path.join(tmp, name + '.dss')
+        model = mg.read_dss(fp, {})
+        regs = [rc.name for rc in model.regcontrols]
+        rng = np.random.Generator(np.random.PCG64(seed + 7000))
+        taps = rng.integers(-16, 17, size=(5, len(regs)))
+        taps[0], taps[1] = 16, -16
+        mult = rng.uniform(0.5, 1.4, size=(5, len(model.loads)))
+        out[name + '/taps/regs'], out[name + '/taps/taps'], out[name + '/taps/mult'] = np.array(regs), taps, mult
+        V, I, it = [], [], []
+        for i in range(5):
+            mg.dss.TAPS = {r: int(t) for r, t in zip(regs, taps[i])}
+            s = mg.ref_fbs(fp, z, mult[i])
+            V.append(s.V.copy()), I.append(s.I.copy()), it.append(s.iterations)
+        out[name + '/taps/FBS/V'], out[name + '/taps/FBS/I'], out[name + '/taps/FBS/iterations'] = np.array(V), np.array(I), np.array(it)
+        X, itn = [], []
+        for i in range(n_nr3):
+            mg.dss.TAPS = {r: int(t) for r, t in zip(regs, taps[i])}
+            n, its = mg.ref_nr3(fp, z, mult[i])
+            X.append(n.XNR[:, 0].copy()), itn.append(its)
+            del n
+        if n_nr3:
+            out[name + '/taps/NR3/XNR'], out[name + '/taps/NR3/iterations'] = np.array(X), np.array(itn)
+        print(name, 'taps: FBS it', it, 'NR3 it', itn, flush=True)
+    for name, (n_fbs, n_nr3) in WARM_CASES.items():
+        seed = FEEDERS[name][0]
+        fp = os.path.join(tmp, name + '.dss')
+        _, taps = make_feeder(name, *FEEDERS[name])
+        mg.dss.TAPS = taps
+        rng = np.random.Generator(np.random.PCG64(seed + 8000))
+        s = mg.SolutionFBS(fp, zip_v=np.asarray(z))
+        nload = s.circuit.loads.num_elements
+        level = 1.0 + np.cumsum(rng.uniform(-0.15, 0.15, size=n_fbs))
+        mult = level[:, None] * (1 + rng.normal(0, 0.03, size=(n_fbs, nload)))
+        mult[0] = 1.0
+        out[name + '/warm/mult'] = mult
+        base = [(s.circuit.loads.get_element(n).kW, s.circuit.loads.get_element(n).kvar) for n in s.circuit.loads.all_names()]
+        V, I, it = [], [], []
+        for h in range(n_fbs):
+            set_loads(s, base, mult[h])
+            s._set_sV_params()
+            s.Vtest = np.zeros(3, dtype=complex)
+            s.iterations = 0
+            s.solve()
+            V.append(s.V.copy()), I.append(s.I.copy()), it.append(s.iterations)
+        out[name + '/warm/FBS/V'], out[name + '/warm/FBS/I'], out[name + '/warm/FBS/iterations'] = np.array(V), np.array(I), np.array(it)
+        X, itn = [], []
+        if n_nr3:
+            n = mg.SolutionNR3(fp, zip_v=np.asarray(z))
+            for h in range(n_nr3):
+                set_loads(n, base, mult[h])
+                n._init_KCL_matrices()
+                mg._ft_calls[0] = 0
+                n.solve()
+                X.append(n.XNR[:, 0].copy()), itn.append(mg._ft_calls[0])
+            out[name + '/warm/NR3/XNR'], out[name + '/warm/NR3/iterations'] = np.array(X), np.array(itn)
+            del n
+        print(name, 'warm: FBS it', it, 'NR3 it', itn, flush=True)
+    for name in WPU_CASES:
+        seed = FEEDERS[name][0]
+        fp = os.path.join(tmp, name + '.dss')
+        _, taps = make_feeder(name, *FEEDERS[name])
+        mg.dss.TAPS = taps
+        rng = np.random.Generator(np.random.PCG64(seed + 9000))
+        s0 = mg.SolutionFBS(fp, zip_v=np.asarray(z))
+        nb = s0.circuit.buses.num_elements
+        pm = s0.phase_matrix.astype(bool)
+        n = 4
+        mult = rng.uniform(0.6, 1.3, size=(n, s0.circuit.loads.num_elements))
+        wpu = np.zeros((n, nb, 3))
+        for i in range(n):
+            b, p = np.nonzero(pm)
+            pick = rng.permutation(len(b))[:max(2, len(b) // 4)]
+            wpu[i, b[pick], p[pick]] = rng.uniform(-0.05, 0.05, size=len(pick))
+        out[name + '/wpu/mult'], out[name + '/wpu/wpu'] = mult, wpu
+        V, I, sV, it = [], [], [], []
+        for i in range(n):
+            s = mg.SolutionFBS(fp, zip_v=np.asarray(z))
+            for j, lname in enumerate(s.circuit.loads.all_names()):
+                ld = s.circuit.loads.get_element(lname)
+                s.circuit.set_kW(lname, ld.kW * mult[i][j])
+                s.circuit.set_kvar(lname, ld.kvar * mult[i][j])
+            s._set_sV_params()
+            s.wpu = wpu[i].copy()
+            s.solve()
+            V.append(s.V.copy()), I.append(s.I.copy()), sV.append(s.sV.copy()), it.append(s.iterations)
+        out[name + '/wpu/FBS/V'], out[name + '/wpu/FBS/I'], out[name + '/wpu/FBS/sV'] = np.array(V), np.array(I), np.array(sV)
+        out[name + '/wpu/FBS/iterations'] = np.array(it)
+        print(name, 'wpu: FBS it', it, flush=True)
+    np.savez_compressed(os.path.join(mg.OUT, 'ref_random_extras.npz'), **out)
+    print('wrote', os.path.join(mg.OUT, 'ref_random_extras.npz'))
 
 
 if __name__ == '__main__':

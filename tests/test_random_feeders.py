@@ -173,3 +173,125 @@ def test_generated_sweeps_compiled_for_the_host_match_the_reference(name, mode, 
     Ir = raw[2 * nv * S:2 * (nv + ni) * S].view(np.complex128).reshape(ni, S)
     its = raw[2 * (nv + ni) * S:].astype(int)
     _check_rows(t, Vr, Ir, its, name, tol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------
+# per-scenario taps, warm starts and reactive injections on the random feeders:
+# tests/golden/ref_random_extras.npz, each case as the reference defines it (oracle/make_golden_random.py: extras)
+# ---------------------------------------------------------------------------------------------
+TAP_CASES = ['rnd03', 'rnd06', 'rnd08', 'rnd11', 'rnd13']
+WARM_CASES = ['rnd02', 'rnd03', 'rnd05', 'rnd10']
+WPU_CASES = ['rnd04', 'rnd13', 'rnd09']
+
+
+def extras():
+    if 'x' not in _cache:
+        _cache['x'] = np.load(os.path.join(GOLDEN, 'ref_random_extras.npz'))
+    return _cache['x']
+
+
+def test_the_extras_set_holds_a_scenario_the_reference_does_not_converge():
+    """Taps all at -16 on the 40-bus feeder: the reference stops at maxiter = 100 (a slow geometric approach that
+    would take 159 sweeps), so the maxiter exit is pinned by the reference too."""
+    it = extras()['rnd11/taps/FBS/iterations']
+    assert it.max() == 100 and (it < 100).sum() == 4 and np.isfinite(extras()['rnd11/taps/FBS/V']).all()
+
+
+@pytest.mark.parametrize('name', TAP_CASES)
+def test_oracles_with_per_scenario_taps_match_reference_objects(name):
+    from oracle.gp_oracle import FBSOracle, NR3Oracle, OracleCircuit, solve_with_taps
+    from oracle.nr3_tree import NR3TreeOracle
+    x = extras()
+    model = rmodel(name)
+    assert [rc.name for rc in model.regcontrols] == list(x[name + '/taps/regs'])
+    c = OracleCircuit(model)
+    mult, taps = x[name + '/taps/mult'], x[name + '/taps/taps']
+    spu = c.spu_matrix(c.load_kw * mult, c.load_kvar * mult)
+    r = solve_with_taps(FBSOracle, model, spu, taps, ZIPS['test_zip'])
+    assert list(r['iterations']) == list(x[name + '/taps/FBS/iterations'])
+    assert np.abs(r['V'] - x[name + '/taps/FBS/V']).max() <= TOL
+    assert np.abs(r['I'] - x[name + '/taps/FBS/I']).max() <= TOL
+    if name + '/taps/NR3/XNR' in x.files:
+        X = x[name + '/taps/NR3/XNR']
+        for cls, tol in ((NR3Oracle, 1e-11), (NR3TreeOracle, 1e-10)):
+            n = solve_with_taps(cls, model, spu[:len(X)], taps[:len(X)], ZIPS['test_zip'])
+            assert list(n['iterations']) == list(x[name + '/taps/NR3/iterations'])
+            assert np.abs(n['XNR'] - X).max() <= tol
+
+
+@pytest.mark.parametrize('name', WARM_CASES)
+def test_oracles_warm_started_match_a_reused_reference_object(name):
+    from oracle.gp_oracle import FBSOracle, NR3Oracle
+    x = extras()
+    model = rmodel(name)
+    o = FBSOracle(model, ZIPS['test_zip'])
+    c = o.c
+    mult = x[name + '/warm/mult']
+    V0 = I0 = None
+    for h in range(len(mult)):
+        r = o.solve(c.spu_matrix(c.load_kw * mult[h], c.load_kvar * mult[h])[None], V0=V0, I0=I0)
+        assert int(r['iterations'][0]) == int(x[name + '/warm/FBS/iterations'][h]), h
+        assert np.abs(r['V'][0] - x[name + '/warm/FBS/V'][h]).max() <= TOL
+        assert np.abs(r['I'][0] - x[name + '/warm/FBS/I'][h]).max() <= TOL
+        V0, I0 = r['V'], r['I']
+    if name + '/warm/NR3/XNR' in x.files:
+        n = NR3Oracle(model, ZIPS['test_zip'])
+        X0 = None
+        for h in range(len(x[name + '/warm/NR3/iterations'])):
+            r = n.solve(c.spu_matrix(c.load_kw * mult[h], c.load_kvar * mult[h])[None], X0=X0)
+            assert int(r['iterations'][0]) == int(x[name + '/warm/NR3/iterations'][h]), h
+            assert np.abs(r['XNR'][0] - x[name + '/warm/NR3/XNR'][h]).max() <= 1e-11
+            X0 = r['XNR']
+
+
+@pytest.mark.parametrize('name', WPU_CASES)
+def test_fbs_oracle_with_reactive_injection_matches_reference_objects(name):
+    from oracle.gp_oracle import FBSOracle
+    x = extras()
+    o = FBSOracle(rmodel(name), ZIPS['test_zip'])
+    c = o.c
+    mult = x[name + '/wpu/mult']
+    r = o.solve(c.spu_matrix(c.load_kw * mult, c.load_kvar * mult), wpu=x[name + '/wpu/wpu'])
+    assert list(r['iterations']) == list(x[name + '/wpu/FBS/iterations'])
+    for p in ('V', 'I', 'sV'):
+        assert np.abs(r[p] - x[f'{name}/wpu/FBS/{p}']).max() <= TOL, p
+
+
+@pytest.mark.parametrize('name', TAP_CASES)
+def test_generated_sweep_with_per_scenario_taps_matches_reference_objects(name, tmp_path):
+    """The EX build of the specialised kernel (gp_fbs_jit_source mode 2), compiled for the host, with the golden's
+    taps as per-scenario ratio rows."""
+    from gigpower_b200 import _cabi
+    from oracle.gp_oracle import FBSOracle
+    from test_jit_source_on_host import MAIN_EX, host_program
+    x = extras()
+    model, t = _tables(name)
+    d, keep = _cabi.make_fbs_desc(t)
+    n = _cabi.gp_fbs_jit_source(C.byref(d), 2, 2, None, 0)
+    buf = C.create_string_buffer(n + 1)
+    assert _cabi.gp_fbs_jit_source(C.byref(d), 2, 2, buf, n + 1) == n
+    prog = host_program(buf.value.decode())
+    prog = prog[:prog.index('int main(')] + MAIN_EX
+    cpp, exe = tmp_path / 'sweep_ex.cpp', tmp_path / 'sweep_ex'
+    cpp.write_text(prog)
+    subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-w', '-o', str(exe), str(cpp)], check=True)
+    o = FBSOracle(model, ZIPS['test_zip'])
+    taps = x[name + '/taps/taps']
+    rows = _packed(t, o, x[name + '/taps/mult'])
+    S = rows.shape[1]
+    g = (taps.astype(float) + 16) / 32
+    g = g * (1.10 - .90)
+    g = g + .90                                             # voltage_regulator.py:23-39, same operation order
+    gam = np.ascontiguousarray(g.T[np.asarray(t.grow_vr, dtype=int)])       # [n_gamma_rows, S]
+    fin, fg, fout = tmp_path / 'in.bin', tmp_path / 'gam.bin', tmp_path / 'out.bin'
+    rows[:t.n_srows].astype(np.complex128).tofile(fin)
+    gam.astype(np.float64).tofile(fg)
+    subprocess.run([str(exe), str(S), repr(float(t.tolerance)), '100', str(fin), str(fg), str(fout), str(gam.shape[0])], check=True)
+    raw = np.fromfile(fout, dtype=np.float64)
+    nv, ni = t.n_vrows, max(t.n_irows, 1)
+    Vr = raw[:2 * nv * S].view(np.complex128).reshape(nv, S)
+    its = raw[2 * (nv + ni) * S:].astype(int)
+    want_it = x[name + '/taps/FBS/iterations']
+    assert list(its) == list(want_it)
+    bb, pp = np.nonzero(t.vrow >= 0)
+    assert np.abs(Vr[t.vrow[bb, pp]].T - x[name + '/taps/FBS/V'][:, bb, pp]).max() <= 1e-9

@@ -74,3 +74,73 @@ def test_nr3_on_random_feeders_matches_the_reference(name):
             assert rel_err(r.V, g[name + '/NR3/V']) <= TOL, kern
     finally:
         _cabi.gp_set_option(b'nr3_kernel', 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# per-scenario taps, warm starts, reactive injections (tests/golden/ref_random_extras.npz)
+# ---------------------------------------------------------------------------------------------
+from test_random_feeders import TAP_CASES, WARM_CASES, WPU_CASES, extras      # noqa: E402
+
+
+@pytest.mark.parametrize('name', TAP_CASES)
+def test_per_scenario_taps_on_random_feeders_match_reference_objects(name):
+    """One unmodified reference object per scenario, built with that scenario's taps: the streaming kernel's EX
+    instance, then (two feeders) the EX build of the specialised kernel; NR3 where the reference ran it.  The 40-bus
+    feeder holds a scenario the reference leaves unconverged at maxiter = 100: same count, status 1."""
+    from gigpower_b200 import _cabi
+    from gigpower_b200.solution_fbs import SolutionFBS
+    from gigpower_b200.solution_nr3 import SolutionNR3
+    x = extras()
+    s = SolutionFBS(_path(name), zip_v=np.asarray(ZIPS['test_zip']))
+    assert [vr.__name__ for vr in s.circuit.voltage_regulators.get_elements()] == list(x[name + '/taps/regs'])
+    mult, taps = x[name + '/taps/mult'], x[name + '/taps/taps']
+    want_it = x[name + '/taps/FBS/iterations']
+    ok = want_it < 100
+    for specialised in ((False, True) if name in ('rnd03', 'rnd13') else (False,)):
+        if specialised:
+            assert s.specialise() and _cabi.gp_fbs_active_kernel(s._feeder.handle) == 5
+        r = s.solve_batch(load_mult=mult, taps=taps, outputs=('V', 'I'))
+        assert list(r.iterations) == list(want_it), specialised
+        assert list(r.status) == [0 if k else 1 for k in ok]
+        # (the unconverged scenario is a slow geometric approach - it would take 159 sweeps -, so its values are held too)
+        assert rel_err(r.V, x[name + '/taps/FBS/V']) <= TOL
+        assert rel_err(r.I, x[name + '/taps/FBS/I'][:, :r.I.shape[1]]) <= TOL
+    if name + '/taps/NR3/XNR' in x.files:
+        X = x[name + '/taps/NR3/XNR']
+        n = SolutionNR3(_path(name), zip_v=np.asarray(ZIPS['test_zip']))
+        rn = n.solve_batch(load_mult=mult[:len(X)], taps=taps[:len(X)], outputs=('X',))
+        assert list(rn.iterations) == list(x[name + '/taps/NR3/iterations'])
+        assert rel_err(rn.XNR, X) <= TOL
+
+
+@pytest.mark.parametrize('name', WARM_CASES)
+def test_warm_started_sequences_on_random_feeders_match_a_reused_reference_object(name):
+    from gigpower_b200.solution_fbs import SolutionFBS
+    from gigpower_b200.solution_nr3 import SolutionNR3
+    x = extras()
+    s = SolutionFBS(_path(name), zip_v=np.asarray(ZIPS['test_zip']))
+    mult = x[name + '/warm/mult']
+    prev = None
+    for h in range(len(mult)):
+        prev = s.solve_batch(load_mult=mult[h:h + 1], outputs=('V', 'I'), return_device=True, warm_start=prev)
+        assert int(prev.iterations[0]) == int(x[name + '/warm/FBS/iterations'][h]), h
+        assert rel_err(prev.V[0], x[name + '/warm/FBS/V'][h]) <= TOL
+        assert rel_err(prev.I[0], x[name + '/warm/FBS/I'][h][:prev.I.shape[1]]) <= TOL
+    if name + '/warm/NR3/XNR' in x.files:
+        n = SolutionNR3(_path(name), zip_v=np.asarray(ZIPS['test_zip']))
+        prev = None
+        for h in range(len(x[name + '/warm/NR3/iterations'])):
+            prev = n.solve_batch(load_mult=mult[h:h + 1], outputs=('X',), return_device=True, warm_start=prev)
+            assert int(prev.iterations[0]) == int(x[name + '/warm/NR3/iterations'][h]), h
+            assert rel_err(prev.XNR[0], x[name + '/warm/NR3/XNR'][h]) <= TOL
+
+
+@pytest.mark.parametrize('name', WPU_CASES)
+def test_reactive_injection_on_random_feeders_matches_reference_objects(name):
+    from gigpower_b200.solution_fbs import SolutionFBS
+    x = extras()
+    s = SolutionFBS(_path(name), zip_v=np.asarray(ZIPS['test_zip']))
+    r = s.solve_batch(load_mult=x[name + '/wpu/mult'], wpu=x[name + '/wpu/wpu'], outputs=('V', 'I', 'sV'))
+    assert list(r.iterations) == list(x[name + '/wpu/FBS/iterations'])
+    assert rel_err(r.V, x[name + '/wpu/FBS/V']) <= TOL and rel_err(r.sV, x[name + '/wpu/FBS/sV']) <= TOL
+    assert rel_err(r.I, x[name + '/wpu/FBS/I'][:, :r.I.shape[1]]) <= TOL
