@@ -177,11 +177,16 @@ def main():
     z = mg.ZIPS['test_zip']
     res = {}
     tmp = tempfile.mkdtemp(prefix='gp_random_')
+    parts = None
+    if '--extras' in sys.argv:                   # only (some of) the extras: python ... --extras droop,wpu_nr3
+        parts = sys.argv[sys.argv.index('--extras') + 1].split(',')
     for name, (seed, nb, reg, xfm) in FEEDERS.items():
         text, taps = make_feeder(name, seed, nb, reg, xfm)
         fp = os.path.join(tmp, name + '.dss')
         with open(fp, 'w') as fh:
             fh.write(text)
+        if parts is not None:
+            continue
         mg.dss.TAPS = taps
         model = mg.read_dss(fp, taps)
         with open(os.path.join(OUT, name + '.json'), 'w') as fh:
@@ -209,25 +214,34 @@ def main():
             res[f'{name}/NR3/XNR'], res[f'{name}/NR3/V'], res[f'{name}/NR3/iterations'] = np.array(X), np.array(Vn), np.array(itn)
             msg += f', NR3 it {itn}'
         print(msg, flush=True)
-    np.savez_compressed(os.path.join(mg.OUT, 'ref_random.npz'), **res)
-    print('wrote', os.path.join(mg.OUT, 'ref_random.npz'))
-    extras(tmp)
+    if parts is None:
+        np.savez_compressed(os.path.join(mg.OUT, 'ref_random.npz'), **res)
+        print('wrote', os.path.join(mg.OUT, 'ref_random.npz'))
+    extras(tmp, parts or ALL_PARTS)
 
 
 TAP_CASES = {'rnd03': 3, 'rnd06': 3, 'rnd08': 0, 'rnd11': 0, 'rnd13': 3}      # feeder: NR3 scenarios (FBS: 5 each)
 WARM_CASES = {'rnd02': (4, 3), 'rnd03': (4, 3), 'rnd05': (4, 3), 'rnd10': (4, 0)}   # feeder: (FBS steps, NR3 steps)
 WPU_CASES = ['rnd04', 'rnd13', 'rnd09']
+DROOP_CASES = ['rnd09', 'rnd13', 'rnd10', 'rnd11']
+WPU_NR3_CASES = ['rnd04', 'rnd13']
+DROOP_POINTS, DROOP_Q = (0.94, 0.97, 1.0, 1.03), (-0.08, 0.08)
+ALL_PARTS = ['taps', 'warm', 'wpu', 'droop', 'wpu_nr3']
 
 
-def extras(tmp):
+def extras(tmp, parts):
     """The per-scenario inputs of SURVEY.md section 8(f)-2, -3 on the random feeders, each as the reference defines it:
     taps = one reference object per scenario built with that scenario's taps (oracle/make_golden_taps.py), warm start =
     one reference object driven through a load sequence (make_golden_warm.py), wpu = reference objects whose ``wpu``
     attribute is set (make_golden_wpu.py).  -> tests/golden/ref_random_extras.npz"""
     from make_golden_warm import set_loads
     z = mg.ZIPS['test_zip']
+    path = os.path.join(mg.OUT, 'ref_random_extras.npz')
     out = {}
-    for name, n_nr3 in TAP_CASES.items():
+    if os.path.exists(path):                     # parts not asked for keep what the file holds
+        old = np.load(path)
+        out = {k: old[k] for k in old.files if k.split('/')[1] not in parts}
+    for name, n_nr3 in (TAP_CASES.items() if 'taps' in parts else ()):
         seed = FEEDERS[name][0]
         fp = os.path.join(tmp, name + '.dss')
         model = mg.read_dss(fp, {})
@@ -252,7 +266,7 @@ def extras(tmp):
         if n_nr3:
             out[name + '/taps/NR3/XNR'], out[name + '/taps/NR3/iterations'] = np.array(X), np.array(itn)
         print(name, 'taps: FBS it', it, 'NR3 it', itn, flush=True)
-    for name, (n_fbs, n_nr3) in WARM_CASES.items():
+    for name, (n_fbs, n_nr3) in (WARM_CASES.items() if 'warm' in parts else ()):
         seed = FEEDERS[name][0]
         fp = os.path.join(tmp, name + '.dss')
         _, taps = make_feeder(name, *FEEDERS[name])
@@ -286,7 +300,7 @@ def extras(tmp):
             out[name + '/warm/NR3/XNR'], out[name + '/warm/NR3/iterations'] = np.array(X), np.array(itn)
             del n
         print(name, 'warm: FBS it', it, 'NR3 it', itn, flush=True)
-    for name in WPU_CASES:
+    for name in (WPU_CASES if 'wpu' in parts else ()):
         seed = FEEDERS[name][0]
         fp = os.path.join(tmp, name + '.dss')
         _, taps = make_feeder(name, *FEEDERS[name])
@@ -317,8 +331,82 @@ def extras(tmp):
         out[name + '/wpu/FBS/V'], out[name + '/wpu/FBS/I'], out[name + '/wpu/FBS/sV'] = np.array(V), np.array(I), np.array(sV)
         out[name + '/wpu/FBS/iterations'] = np.array(it)
         print(name, 'wpu: FBS it', it, flush=True)
-    np.savez_compressed(os.path.join(mg.OUT, 'ref_random_extras.npz'), **out)
-    print('wrote', os.path.join(mg.OUT, 'ref_random_extras.npz'))
+    if 'droop' in parts:
+        # volt-var droop INSIDE the FBS iteration: the reference's SolutionFBS with its own VoltVARController objects
+        # consulted before every calc_sV (oracle/make_golden_vvc_iter.py has the construction)
+        from make_golden_vvc_iter import DroopFBS, VoltVARController
+        out['droop/points'], out['droop/q'] = np.array(DROOP_POINTS), np.array(DROOP_Q)
+        for name in DROOP_CASES:
+            seed = FEEDERS[name][0]
+            fp = os.path.join(tmp, name + '.dss')
+            _, taps = make_feeder(name, *FEEDERS[name])
+            mg.dss.TAPS = taps
+            rng = np.random.Generator(np.random.PCG64(seed + 10000))
+            s0 = mg.SolutionFBS(fp, zip_v=np.asarray(z))
+            nb = s0.circuit.buses.num_elements
+            pm = s0.phase_matrix.astype(bool)
+            names = s0.circuit.buses.all_names()
+            cand = [k for k in range(1, nb) if pm[k].all()]
+            ctl = [(k, p) for k in (cand[len(cand) // 2], cand[-1]) for p in range(3)]
+            single = [k for k in range(1, nb) if pm[k].sum() == 1]
+            if single:
+                ctl.append((single[-1], int(np.nonzero(pm[single[-1]])[0][0])))
+            n = 4
+            mult = rng.uniform(0.5, 1.5, size=(n, s0.circuit.loads.num_elements))
+            out[name + '/droop/ctl'], out[name + '/droop/mult'] = np.array(ctl), mult
+            V, I, sV, it, Q = [], [], [], [], []
+            for i in range(n):
+                s = DroopFBS(fp, zip_v=np.asarray(z))
+                for j, lname in enumerate(s.circuit.loads.all_names()):
+                    ld = s.circuit.loads.get_element(lname)
+                    s.circuit.set_kW(lname, ld.kW * mult[i][j])
+                    s.circuit.set_kvar(lname, ld.kvar * mult[i][j])
+                s._set_sV_params()
+                s.controllers = [((k, p), VoltVARController(DROOP_POINTS, *DROOP_Q, names[k], p)) for k, p in ctl]
+                s.solve()
+                V.append(s.V.copy()), I.append(s.I.copy()), sV.append(s.sV.copy()), it.append(s.iterations)
+                Q.append(np.array([s.wpu[k, p] for k, p in ctl]))
+            out[name + '/droop/V'], out[name + '/droop/I'], out[name + '/droop/sV'] = np.array(V), np.array(I), np.array(sV)
+            out[name + '/droop/iterations'], out[name + '/droop/Q'] = np.array(it), np.array(Q)
+            print(name, 'droop: FBS it', it, 'max|Q|', np.abs(np.array(Q)).max(), flush=True)
+    for name in (WPU_NR3_CASES if 'wpu_nr3' in parts else ()):
+        # a non-zero wpu in the reference's SolutionNR3 (oracle/make_golden_wpu_nr3.py has the construction)
+        seed = FEEDERS[name][0]
+        fp = os.path.join(tmp, name + '.dss')
+        _, taps = make_feeder(name, *FEEDERS[name])
+        mg.dss.TAPS = taps
+        rng = np.random.Generator(np.random.PCG64(seed + 11000))
+        s0 = mg.SolutionNR3(fp, zip_v=np.asarray(z))
+        nb = s0.circuit.buses.num_elements
+        pm = np.asarray(s0.circuit.buses.get_phase_matrix('rows')).astype(bool)
+        n = 3
+        mult = rng.uniform(0.6, 1.3, size=(n, s0.circuit.loads.num_elements))
+        wpu = np.zeros((n, nb, 3))
+        for i in range(n):
+            b, p = np.nonzero(pm[1:])
+            pick = rng.permutation(len(b))[:max(2, len(b) // 4)]
+            wpu[i, b[pick] + 1, p[pick]] = rng.uniform(-0.04, 0.04, size=len(pick))
+        del s0
+        out[name + '/wpu_nr3/mult'], out[name + '/wpu_nr3/wpu'] = mult, wpu
+        X, sV, it = [], [], []
+        for i in range(n):
+            s = mg.SolutionNR3(fp, zip_v=np.asarray(z))
+            for j, lname in enumerate(s.circuit.loads.all_names()):
+                ld = s.circuit.loads.get_element(lname)
+                s.circuit.set_kW(lname, ld.kW * mult[i][j])
+                s.circuit.set_kvar(lname, ld.kvar * mult[i][j])
+            s._init_KCL_matrices()
+            w = wpu[i]
+            s.circuit.get_wpu_matrix = (lambda w=w, c=s.circuit: c._orient_switch(w.copy()))
+            s.change_KCL_matrices(der=1e-300)
+            mg._ft_calls[0] = 0
+            s.solve()
+            X.append(s.XNR[:, 0].copy()), sV.append(s.sV.copy()), it.append(mg._ft_calls[0])
+            del s
+        out[name + '/wpu_nr3/XNR'], out[name + '/wpu_nr3/sV'], out[name + '/wpu_nr3/iterations'] = np.array(X), np.array(sV), np.array(it)
+        print(name, 'wpu_nr3: it', it, flush=True)
+    np.savez_compressed(path, **out)
+    print('wrote', path)
 
 
 if __name__ == '__main__':

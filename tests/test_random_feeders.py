@@ -295,3 +295,40 @@ def test_generated_sweep_with_per_scenario_taps_matches_reference_objects(name, 
     assert list(its) == list(want_it)
     bb, pp = np.nonzero(t.vrow >= 0)
     assert np.abs(Vr[t.vrow[bb, pp]].T - x[name + '/taps/FBS/V'][:, bb, pp]).max() <= 1e-9
+
+
+DROOP_CASES = ['rnd09', 'rnd13', 'rnd10', 'rnd11']
+WPU_NR3_CASES = ['rnd04', 'rnd13']
+
+
+@pytest.mark.parametrize('name', DROOP_CASES)
+def test_fbs_oracle_with_droop_inside_the_iteration_matches_the_reference_controllers(name):
+    """The reference's SolutionFBS with its own VoltVARController objects consulted before every calc_sV
+    (oracle/make_golden_vvc_iter.py has the construction), on random feeders; the injections saturate on two of them."""
+    from oracle.gp_oracle import FBSOracle, vvc_get_Q
+    x = extras()
+    o = FBSOracle(rmodel(name), ZIPS['test_zip'])
+    mult = x[name + '/droop/mult']
+    ctl = [tuple(int(v) for v in row) for row in x[name + '/droop/ctl']]
+    pts, (minQ, maxQ) = tuple(x['droop/points']), x['droop/q']
+    r = o.solve(o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult), droop=(ctl, pts, minQ, maxQ))
+    assert list(r['iterations']) == list(x[name + '/droop/iterations'])
+    for k in ('V', 'I', 'sV'):
+        assert np.abs(r[k] - x[f'{name}/droop/{k}']).max() <= TOL, k
+    Q = np.stack([vvc_get_Q(np.abs(r['V'][:, k, p]), pts, minQ, maxQ) for k, p in ctl], axis=1)
+    assert np.abs(Q - x[name + '/droop/Q']).max() <= TOL and np.abs(Q).max() > 1e-2
+
+
+@pytest.mark.parametrize('name', WPU_NR3_CASES)
+def test_nr3_tree_oracle_with_wpu_matches_the_reference_on_random_feeders(name):
+    """Reference SolutionNR3 objects whose circuit reports a non-zero wpu, after the reference's own
+    change_KCL_matrices has written it into their KCL constants (oracle/make_golden_wpu_nr3.py)."""
+    from oracle.nr3_tree import NR3TreeOracle
+    x = extras()
+    o = NR3TreeOracle(rmodel(name), ZIPS['test_zip'])
+    mult, wpu = x[name + '/wpu_nr3/mult'], x[name + '/wpu_nr3/wpu']
+    spu = o.c.spu_matrix(o.c.load_kw * mult, o.c.load_kvar * mult)
+    r = o.solve(spu, wpu=wpu)
+    assert list(r['iterations']) == list(x[name + '/wpu_nr3/iterations'])
+    assert np.abs(r['XNR'] - x[name + '/wpu_nr3/XNR']).max() <= 1e-11
+    assert np.abs(o.solve(spu)['XNR'] - x[name + '/wpu_nr3/XNR']).max() >= 1e-5

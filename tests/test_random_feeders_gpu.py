@@ -144,3 +144,31 @@ def test_reactive_injection_on_random_feeders_matches_reference_objects(name):
     assert list(r.iterations) == list(x[name + '/wpu/FBS/iterations'])
     assert rel_err(r.V, x[name + '/wpu/FBS/V']) <= TOL and rel_err(r.sV, x[name + '/wpu/FBS/sV']) <= TOL
     assert rel_err(r.I, x[name + '/wpu/FBS/I'][:, :r.I.shape[1]]) <= TOL
+
+
+from test_random_feeders import DROOP_CASES, WPU_NR3_CASES      # noqa: E402
+
+
+@pytest.mark.parametrize('name', DROOP_CASES)
+def test_droop_inside_the_iteration_on_random_feeders_matches_the_reference_controllers(name):
+    from gigpower_b200.solution_fbs import SolutionFBS
+    x = extras()
+    s = SolutionFBS(_path(name), zip_v=np.asarray(ZIPS['test_zip']))
+    ctl = [tuple(int(v) for v in row) for row in x[name + '/droop/ctl']]
+    minQ, maxQ = x['droop/q']
+    r = s.solve_batch(load_mult=x[name + '/droop/mult'], outputs=('V', 'I', 'sV'),
+                      volt_var=(ctl, tuple(x['droop/points']), minQ, maxQ))
+    assert list(r.iterations) == list(x[name + '/droop/iterations']) and (r.status == 0).all()
+    assert rel_err(r.V, x[name + '/droop/V']) <= TOL and rel_err(r.sV, x[name + '/droop/sV']) <= TOL
+    assert rel_err(r.I, x[name + '/droop/I'][:, :r.I.shape[1]]) <= TOL
+
+
+@pytest.mark.parametrize('name', WPU_NR3_CASES)
+def test_nr3_reactive_injection_on_random_feeders_matches_reference_objects(name):
+    from gigpower_b200.solution_nr3 import SolutionNR3
+    x = extras()
+    n = SolutionNR3(_path(name), zip_v=np.asarray(ZIPS['test_zip']))
+    r = n.solve_batch(load_mult=x[name + '/wpu_nr3/mult'], wpu=x[name + '/wpu_nr3/wpu'], outputs=('X', 'sV'))
+    assert list(r.iterations) == list(x[name + '/wpu_nr3/iterations'])
+    assert rel_err(r.XNR, x[name + '/wpu_nr3/XNR']) <= TOL
+    assert rel_err(r.sV, x[name + '/wpu_nr3/sV']) <= TOL
