@@ -674,7 +674,8 @@ class NR3Oracle:
                 FT, JT = self._FT_JT(Xc[idx], hA[idx], hB[idx], b0[idx])
                 with np.errstate(all='ignore'):
                     FTmax[idx] = np.amax(np.abs(FT), axis=1)
-                FTmax[~np.isfinite(FTmax)] = np.inf
+                # (np.amax propagates NaN and ``NaN >= 1e-9`` is False: the reference's loop ends on the first residual
+                # that holds a NaN - as nr3_solve_kernel's nanflag does - and goes on while it is merely infinite)
                 if return_history:
                     for j, i in enumerate(idx):
                         hist[s0 + i].append(FTmax[i])

@@ -38,8 +38,11 @@ def lower_tri(m):
     return ' | '.join(' '.join(f'{m[i][j]:.9g}' for j in range(i + 1)) for i in range(len(m)))
 
 
-def make_feeder(name, seed, n_bus, with_reg, with_xfm):
-    """.dss text of one random radial feeder and its regulator taps."""
+def make_feeder(name, seed, n_bus, with_reg, with_xfm, exotic=False):
+    """.dss text of one random radial feeder and its regulator taps.  exotic (the fuzzer's, oracle/fuzz_random_feeders.py;
+    the committed fixtures are made without it): lines and loads below the transformer, a second regulator bank,
+    regulator banks on a subset of the parent's phases, generation (negative kW), loads up to 8 x heavier so that
+    some scenarios stop at maxiter or go non-finite."""
     rng = np.random.Generator(np.random.PCG64(seed))
     out = ['Clear', f'! random radial feeder {name} (oracle/make_golden_random.py, seed {seed})',
            f'New Circuit.{name} basekv=4.16 pu=1.0 phases=3 bus1=src MVAsc3=20000 MVAsc1=21000']
@@ -61,6 +64,13 @@ def make_feeder(name, seed, n_bus, with_reg, with_xfm):
     n_reg = 0
     reg_at = int(rng.integers(1, max(2, n_bus // 2))) if with_reg else -1
     xfm_at = n_bus - 2 if with_xfm else -1
+    reg2_at, reg_parent = -1, -1
+    if exotic:
+        if with_xfm:
+            xfm_at = int(rng.integers(max(3, n_bus // 2), n_bus - 1))
+        if with_reg and n_bus > 8 and rng.random() < 0.5:
+            reg2_at = int(rng.integers(n_bus // 2, n_bus - 1))
+            reg2_at = -1 if reg2_at in (reg_at, xfm_at) else reg2_at
     lv = set()                                   # buses of the 0.48 kV zone
     while len(buses) < n_bus:
         b = len(buses)
@@ -68,8 +78,17 @@ def make_feeder(name, seed, n_bus, with_reg, with_xfm):
         while True:
             p = 0 if b == 1 else int(min(b - 1, max(0, b - 1 - rng.geometric(0.35) + 1)))
             if b == xfm_at:                      # the transformer hangs off a three-phase bus
-                p = int(rng.choice([i for i in range(1, b) if len(buses[i][1]) == 3]))
-            if kids.get(p, 0) < (1 if p == 0 else 4) and p not in lv:
+                three = [i for i in range(1, b) if len(buses[i][1]) == 3 and i not in lv]
+                if not three:
+                    xfm_at = -1
+                    continue
+                p = int(rng.choice(three))
+            # (two regulator banks off ONE bus are left out: the reference de-duplicates a bus's regulator edges with
+            # list(set(...)) - voltage_regulator_group.py:60-72 -, so their order, the topo order and the result then
+            # depend on PYTHONHASHSEED; seed 30029 of the fuzzer found it: 3 or 5 sweeps, voltages apart by 1e-6)
+            if b == reg2_at and p == reg_parent:
+                continue
+            if kids.get(p, 0) < (1 if p == 0 else 4) and (p not in lv or (exotic and b != xfm_at and b not in (reg_at, reg2_at))):
                 break
         pph = buses[p][1]
         if len(pph) == 3:
@@ -90,7 +109,10 @@ def make_feeder(name, seed, n_bus, with_reg, with_xfm):
         if len(spec) == 2 and rng.random() < 0.4:
             spec = spec[::-1]                    # declared in reverse order (line.py / utils.py pad_phases sort them)
         dots = ''.join(f'.{q}' for q in spec)
-        if b == reg_at:
+        if exotic and b in (reg_at, reg2_at) and len(ph) > 1 and rng.random() < 0.4:
+            ph = tuple(sorted(int(q) for q in rng.choice(ph, len(ph) - 1, replace=False)))   # a bank on some phases only
+        if b in (reg_at, reg2_at):
+            reg_parent = p if b == reg_at else reg_parent
             # per-phase regulators (the 13-bus feeder's pattern): parent -> this bus through one 1-phase
             # regulating transformer per phase, each with its own tap
             for q in ph:
@@ -123,6 +145,8 @@ def make_feeder(name, seed, n_bus, with_reg, with_xfm):
             else:
                 cname = codes[n][int(rng.integers(3))][0]
                 out.append(head + f' LineCode={cname} Length={length} units=kft')
+        if p in lv:
+            lv.add(b)
         buses.append((bname, ph))
         kids[p] = kids.get(p, 0) + 1
         kids[b] = 0
@@ -130,6 +154,8 @@ def make_feeder(name, seed, n_bus, with_reg, with_xfm):
         edges.append((p, b))
     # loads: light enough that every feeder converges from flat start, heavy enough for 5-12 sweeps
     heavy = rng.uniform(0.6, 1.6) * (1.0 if seed % 3 else 3.0)      # every third feeder is loaded hard
+    if exotic:
+        heavy *= float(rng.choice([1.0, 1.0, 2.5, 5.0, 8.0]))
     n_load = 0
     for b in range(1, n_bus):
         bname, ph = buses[b]
@@ -151,6 +177,8 @@ def make_feeder(name, seed, n_bus, with_reg, with_xfm):
         else:
             q = int(rng.choice(ph))
             kw = rng.uniform(15, 120) * scale
+            if exotic and rng.random() < 0.15:
+                kw = -kw                         # generation
             out.append(f'New Load.ld{n_load} Bus1={bname}.{q} Phases=1 Conn=Wye Model=1 kV={kv_ln} '
                        f'kW={kw:.2f} kvar={kw * rng.uniform(0.2, 0.6):.2f}')
     if n_load == 0:

@@ -332,3 +332,57 @@ def test_nr3_tree_oracle_with_wpu_matches_the_reference_on_random_feeders(name):
     assert list(r['iterations']) == list(x[name + '/wpu_nr3/iterations'])
     assert np.abs(r['XNR'] - x[name + '/wpu_nr3/XNR']).max() <= 1e-11
     assert np.abs(o.solve(spu)['XNR'] - x[name + '/wpu_nr3/XNR']).max() >= 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# a feeder on which the reference itself has two answers (oracle/make_golden_two_banks.py)
+# ---------------------------------------------------------------------------------------------
+def test_two_regulator_banks_off_one_bus_follow_the_order_of_definition(tmp_path):
+    """Bus b1 feeds two regulator banks.  The reference de-duplicates a bus's regulator edges with ``list(set(...))``
+    (voltage_regulator_group.py:60-72), so the banks' order in its adjacency list - and with it the topo order, the
+    child that rewrites b1 last and the voltages of the source and of b1 (3.6e-7 apart) - follows PYTHONHASHSEED: the
+    golden file holds both answers, each from several hash seeds.  The flattener, the oracle, the kernel loops over the
+    library's schedules and the generated sweeps all give the one with the banks in the order of definition."""
+    from gigpower_b200 import _cabi
+    from oracle.gp_oracle import FBSOracle
+    from test_fbs_order_host import _schedule, emulate
+    from test_jit_source_on_host import MAIN_DFS, host_program
+    g = np.load(os.path.join(GOLDEN, 'ref_two_banks.npz'))
+    assert int(g['n_variants']) == 2
+    ours, other = ('v0', 'v1') if bool(g['v0/definition_order']) else ('v1', 'v0')
+    assert bool(g[ours + '/definition_order']) and not bool(g[other + '/definition_order'])
+    assert len(g[ours + '/hash_seeds']) >= 2 and len(g[other + '/hash_seeds']) >= 2
+    assert np.abs(g[ours + '/V'] - g[other + '/V']).max() > 1e-7            # the two answers really differ
+    model, t = _tables('two_banks')
+    o = FBSOracle(model, ZIPS['test_zip'])
+    assert list(o.topo_order) == list(g[ours + '/topo_order'])
+    assert [model.bus_names.index(n) for n in t.topo_order] == list(g[ours + '/topo_order'])
+    r = o.solve(o.c.spu_matrix(o.c.load_kw[None], o.c.load_kvar[None]))
+    assert int(r['iterations'][0]) == int(g[ours + '/iterations'])
+    assert np.abs(r['V'][0] - g[ours + '/V']).max() <= TOL and np.abs(r['I'][0] - g[ours + '/I']).max() <= TOL
+    rows = _packed(t, o, np.ones((1, len(o.c.load_names))))
+    bb, pp = np.nonzero(t.vrow >= 0)
+    events, kind = _schedule(t)
+    for order in ('dfs', 'sweeps'):
+        V, I, its = emulate(t, rows, events, kind, order)
+        assert int(its[0]) == int(g[ours + '/iterations'])
+        assert np.abs(V[t.vrow[bb, pp], 0] - g[ours + '/V'][bb, pp]).max() <= TOL
+    d, keep = _cabi.make_fbs_desc(t)
+    for mode in (0, 4):
+        n = _cabi.gp_fbs_jit_source(C.byref(d), 2, mode, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        assert _cabi.gp_fbs_jit_source(C.byref(d), 2, mode, buf, n + 1) == n
+        prog = host_program(buf.value.decode())
+        if mode == 4:
+            prog = prog[:prog.index('int main(')] + MAIN_DFS
+        cpp, exe = tmp_path / f'sweep{mode}.cpp', tmp_path / f'sweep{mode}'
+        cpp.write_text(prog)
+        subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-w', '-o', str(exe), str(cpp)], check=True)
+        fin, fout = tmp_path / 'in.bin', tmp_path / 'out.bin'
+        rows[:t.n_srows].astype(np.complex128).tofile(fin)
+        subprocess.run([str(exe), '1', repr(float(t.tolerance)), '100', str(fin), str(fout)], check=True)
+        raw = np.fromfile(fout, dtype=np.float64)
+        Vr = raw[:2 * t.n_vrows].view(np.complex128).reshape(t.n_vrows, 1)
+        assert int(raw[2 * (t.n_vrows + max(t.n_irows, 1)):][0]) == int(g[ours + '/iterations'])
+        assert np.abs(Vr[t.vrow[bb, pp], 0] - g[ours + '/V'][bb, pp]).max() <= 1e-9
+        assert np.abs(Vr[t.vrow[bb, pp], 0] - g[other + '/V'][bb, pp]).max() > 1e-7
