@@ -74,7 +74,24 @@ def one(seed, tmp, stats):
     if list(o.topo_order) != [ref[0].circuit.buses.get_idx(n) for n in ref[0].topo_order]:
         bad.append('topo order')
     Solution.set_zip_values(np.asarray(z))
-    t = flatten_fbs(Circuit(model))
+    ours = Circuit(model)
+    # the Circuit accessors the drop-in mirrors (circuit.py:90-205, circuit_element_group.py:39-91), on the nominal object
+    rc = mg.SolutionFBS(fp, zip_v=np.asarray(z)).circuit
+    try:
+        for grp in ('buses', 'lines', 'loads', 'capacitors', 'transformers', 'voltage_regulators'):
+            a, b_ = getattr(ours, grp), getattr(rc, grp)
+            assert a.num_elements == b_.num_elements and [str(x) for x in a.all_names()] == [str(x) for x in b_.all_names()], grp
+        assert np.array_equal(ours.buses.get_phase_matrix('rows'), rc.buses.get_phase_matrix('rows'))
+        for m in ('get_spu_matrix', 'get_cappu_matrix', 'get_aPQ_matrix', 'get_aI_matrix', 'get_aZ_matrix', 'get_wpu_matrix'):
+            assert np.abs(np.asarray(getattr(ours, m)()) - np.asarray(getattr(rc, m)())).max() <= 1e-15, m
+        assert list(ours.get_tx_idx_matrix()) == list(rc.get_tx_idx_matrix()) and list(ours.get_rx_idx_matrix()) == list(rc.get_rx_idx_matrix())
+        assert ours.get_total_lines() == rc.get_total_lines()
+        assert np.abs(ours.get_nominal_bus_powers().to_numpy() - rc.get_nominal_bus_powers().to_numpy()).max() <= 1e-15
+        for la, lb in zip(ours.lines.get_elements(), rc.lines.get_elements()):
+            assert np.abs(la.FZpu - lb.FZpu).max() <= 1e-15 * max(1.0, np.abs(lb.FZpu).max()), 'FZpu'
+    except AssertionError as e:
+        bad.append(f'Circuit accessors: {e}')
+    t = flatten_fbs(ours)
     b, p = np.nonzero(t.srow >= 0)
     rows = np.zeros((max(t.n_srows, 1), len(mult)), dtype=complex)
     rows[t.srow[b, p]] = spu[:, b, p].T
