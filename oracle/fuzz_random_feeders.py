@@ -7,7 +7,8 @@ feeders, ``SolutionNR3``) solves it at nominal load and at one random load vecto
 * the FBS oracle and the flattener's topo order (1e-12, equal iteration counts);
 * the streaming kernel's loop run in NumPy over ``gp_fbs_schedule`` in the depth-first order, and the tree-walk
   kernel's loop over ``gp_fbs_walk_events`` (tests/test_fbs_order_host.py, tests/test_fbs_walk_host.py);
-* the dense and the tree NR3 oracles (1e-11).
+* the dense and the tree NR3 oracles (1e-11), and the tree elimination run over the product's own NR3 tables
+  (``flatten_nr3``; tests/nr3_tables_oracle.py).
 
 Sixteen of these feeders are committed as fixtures (tests/golden/random_feeders, tests/test_random_feeders*.py); this
 script is the wider net.  Usage: python oracle/fuzz_random_feeders.py [--jit] [first_seed] [count]   (--jit: also the
@@ -108,7 +109,7 @@ def one(seed, tmp, stats):
         if list(its) != itr or differs(V[t.vrow[bb, pp]].T, Vr[:, bb, pp], tol):
             bad.append('walk loop over gp_fbs_walk_events')
         stats['walked'] += 1
-    if nb <= 14:
+    if nb <= NR3_MAX_BUSES:
         n, itn = mg.ref_nr3(fp, z, mult[1])
         X = n.XNR[:, 0].copy()
         del n
@@ -122,6 +123,17 @@ def one(seed, tmp, stats):
             # - the reference at iteration 83 with seed 31191, the dense oracle at 87 with seed 32067)
             if np.isfinite(X).all() and itn < 100 and (int(rq['iterations'][0]) != itn or differs(rq['XNR'][0], X, 1e-11)):
                 bad.append(cls.__name__)
+        if np.isfinite(X).all() and itn < 100:
+            # the same Newton step run over the PRODUCT's NR3 tables (tests/nr3_tables_oracle.py)
+            from nr3_tables_oracle import NR3TablesOracle
+            from gigpower_b200.flatten import flatten_nr3
+            tn = flatten_nr3(ours)
+            bn, pn = np.nonzero(tn.srow >= 0)
+            rn = np.zeros((max(tn.n_srows, 1), 1), dtype=complex)
+            rn[tn.srow[bn, pn]] = spu[1:, bn, pn].T
+            rq = NR3TablesOracle(tn).solve_rows(rn)
+            if int(rq['iterations'][0]) != itn or differs(rq['XNR'][0], X, 1e-11):
+                bad.append('Newton over flatten_nr3 tables')
         stats['nr3'] += 1
         stats['nr3_unconverged'] = stats.get('nr3_unconverged', 0) + int(itn >= 100)
     if JIT:
@@ -208,6 +220,9 @@ def one(seed, tmp, stats):
     return not bad
 
 
+NR3_MAX_BUSES = 18 if '--nr3' in sys.argv else 14         # --nr3: NR3 on more (bigger) feeders
+if '--nr3' in sys.argv:
+    sys.argv.remove('--nr3')
 JIT = '--jit' in sys.argv
 if JIT:
     sys.argv.remove('--jit')

@@ -386,3 +386,53 @@ def test_two_regulator_banks_off_one_bus_follow_the_order_of_definition(tmp_path
         assert int(raw[2 * (t.n_vrows + max(t.n_irows, 1)):][0]) == int(g[ours + '/iterations'])
         assert np.abs(Vr[t.vrow[bb, pp], 0] - g[ours + '/V'][bb, pp]).max() <= 1e-9
         assert np.abs(Vr[t.vrow[bb, pp], 0] - g[other + '/V'][bb, pp]).max() > 1e-7
+
+
+# ---------------------------------------------------------------------------------------------
+# the PRODUCT's NR3 tables (flatten_nr3) exercised without a GPU: tests/nr3_tables_oracle.py
+# ---------------------------------------------------------------------------------------------
+def _nr3_tables(model):
+    from gigpower_b200.circuit import Circuit
+    from gigpower_b200.flatten import flatten_nr3
+    from gigpower_b200.solution import Solution
+    Solution.set_zip_values(np.asarray(ZIPS['test_zip']))
+    return flatten_nr3(Circuit(model))
+
+
+def _rows_nr3(t, spu):
+    b, p = np.nonzero(t.srow >= 0)
+    rows = np.zeros((max(t.n_srows, 1), spu.shape[0]), dtype=complex)
+    rows[t.srow[b, p]] = spu[:, b, p].T
+    return rows
+
+
+@pytest.mark.parametrize('name', [n for n in RANDOM if int(n[3:]) in (0, 1, 2, 3, 4, 5, 6, 7, 12, 13, 14)])
+def test_newton_over_the_products_nr3_tables_matches_the_reference_on_random_feeders(name):
+    """The tree elimination run over flatten_nr3's tables (topology, blocks, ratios, capacitors, load rows, XNR map)
+    gives the reference's X and iteration counts."""
+    from nr3_tables_oracle import NR3TablesOracle
+    from oracle.gp_oracle import OracleCircuit
+    g = gold()
+    model = rmodel(name)
+    t = _nr3_tables(model)
+    X = g[name + '/NR3/XNR']
+    mult = g[name + '/mult'][:len(X)]
+    c = OracleCircuit(model, ZIPS['test_zip'])
+    r = NR3TablesOracle(t).solve_rows(_rows_nr3(t, c.spu_matrix(c.load_kw * mult, c.load_kvar * mult)))
+    assert list(r['iterations']) == list(g[name + '/NR3/iterations'])
+    assert np.abs(r['XNR'] - X).max() <= 1e-11
+
+
+@pytest.mark.parametrize('feeder', ['IEEE_13_Bus_allwye', 'IEEE_13_Bus_allwye_noxfm_noreg', 'IEEE_34_Bus_allwye',
+                                    'IEEE_34_Bus_allwye_noxfm_noreg', 'IEEE_37_Bus_allwye', 'IEEE_37_Bus_allwye_noxfm_noreg'])
+def test_newton_over_the_products_nr3_tables_matches_the_reference_snapshots(feeder):
+    from helpers import load_model, snapshots
+    from nr3_tables_oracle import NR3TablesOracle
+    from oracle.gp_oracle import OracleCircuit
+    model = load_model(feeder)
+    t = _nr3_tables(model)
+    c = OracleCircuit(model, ZIPS['test_zip'])
+    r = NR3TablesOracle(t).solve_rows(_rows_nr3(t, c.spu_matrix()[None]))
+    k = f'{feeder}/test_zip/NR3/'
+    assert int(r['iterations'][0]) == int(snapshots()[k + 'iterations'])
+    assert np.abs(r['XNR'][0] - snapshots()[k + 'XNR'][:, 0]).max() <= 1e-11
