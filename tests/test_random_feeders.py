@@ -436,3 +436,39 @@ def test_newton_over_the_products_nr3_tables_matches_the_reference_snapshots(fee
     k = f'{feeder}/test_zip/NR3/'
     assert int(r['iterations'][0]) == int(snapshots()[k + 'iterations'])
     assert np.abs(r['XNR'][0] - snapshots()[k + 'XNR'][:, 0]).max() <= 1e-11
+
+
+@pytest.mark.parametrize('source,name', [('taps', 'IEEE_13_Bus_allwye'), ('taps', 'IEEE_37_Bus_allwye'),
+                                         ('random', 'rnd03'), ('random', 'rnd06'), ('random', 'rnd13')])
+def test_per_scenario_gamma_rows_of_the_nr3_tables_match_reference_objects(source, name):
+    """``grow`` (step, phase -> row of the per-scenario ratio array) and ``grow_vr`` (row -> regulator) of
+    flatten_nr3, as ``Solution.gamma_rows_from_taps`` uses them: the Newton step over the product's tables with every
+    regulated phase's ratio taken from its scenario's gamma row meets one reference object per scenario."""
+    from helpers import load_model, taps_golden
+    from nr3_tables_oracle import NR3TablesOracle
+    from oracle.gp_oracle import OracleCircuit
+    if source == 'taps':
+        g, model, key = taps_golden(), load_model(name), name
+        X, its, mult, taps = g[key + '/NR3/XNR'], g[key + '/NR3/iterations'], g[key + '/mult'], g[key + '/taps']
+    else:
+        g, model, key = extras(), rmodel(name), name + '/taps'
+        X, its, mult, taps = g[key + '/NR3/XNR'], g[key + '/NR3/iterations'], g[key + '/mult'], g[key + '/taps']
+    t = _nr3_tables(model)
+    c = OracleCircuit(model, ZIPS['test_zip'])
+    n = len(X)
+    rows = _rows_nr3(t, c.spu_matrix(c.load_kw * mult[:n], c.load_kvar * mult[:n]))
+    gq = (taps[:n].astype(float) + 16) / 32
+    gq = gq * (1.10 - .90)
+    gq = gq + .90                                           # voltage_regulator.py:23-39, same operation order
+    gam = gq.T[np.asarray(t.grow_vr, dtype=int)]            # [n_gamma_rows, S], as gamma_rows_from_taps builds it
+    assert gam.shape[0] == int((t.grow >= 0).sum()) > 0
+    for s in range(n):
+        o = NR3TablesOracle(t)
+        for i, e in enumerate(o.edges):
+            for p in range(3):
+                if t.grow[i, p] >= 0:
+                    assert e['kind'] == 'vr' and e['pm'][p]
+                    e['gamma'][p] = gam[t.grow[i, p], s]
+        r = o.solve_rows(rows[:, s:s + 1])
+        assert int(r['iterations'][0]) == int(its[s]), s
+        assert np.abs(r['XNR'][0] - X[s]).max() <= 1e-10, s
