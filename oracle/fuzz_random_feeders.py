@@ -11,7 +11,7 @@ feeders, ``SolutionNR3``) solves it at nominal load and at one random load vecto
   (``flatten_nr3``; tests/nr3_tables_oracle.py).
 
 Sixteen of these feeders are committed as fixtures (tests/golden/random_feeders, tests/test_random_feeders*.py); this
-script is the wider net.  Usage: python oracle/fuzz_random_feeders.py [--jit] [first_seed] [count]   (--jit: also the
+script is the wider net.  Usage: python oracle/fuzz_random_feeders.py [--jit] [--nr3] [--big] [first_seed] [count]   (--jit: also the
 generated sweeps of the feeder-specialised kernel, compiled for the host with g++; prints one summary line
 per 25 feeders and every mismatch; exit status 1 if there was one)
 """
@@ -47,7 +47,7 @@ def differs(a, b, tol):
 
 def one(seed, tmp, stats):
     rng = np.random.Generator(np.random.PCG64(seed * 7 + 1))
-    nb = int(rng.integers(4, 45))
+    nb = int(rng.integers(45, 160)) if BIG else int(rng.integers(4, 45))
     reg, xfm = bool(rng.random() < 0.35), bool(rng.random() < 0.25 and nb >= 8)
     name = f'fz{seed}'
     text, taps = make_feeder(name, seed, nb, reg, xfm, exotic=bool(seed % 2))
@@ -223,6 +223,9 @@ def one(seed, tmp, stats):
 NR3_MAX_BUSES = 18 if '--nr3' in sys.argv else 14         # --nr3: NR3 on more (bigger) feeders
 if '--nr3' in sys.argv:
     sys.argv.remove('--nr3')
+BIG = '--big' in sys.argv                                     # --big: 45-160 buses instead of 4-44
+if BIG:
+    sys.argv.remove('--big')
 JIT = '--jit' in sys.argv
 if JIT:
     sys.argv.remove('--jit')
